@@ -1,0 +1,104 @@
+// rejit.h — public C++ interface of rejit_b200.
+//
+// Source-compatible with the interface of coreperf/rejit
+// (/root/reference/include/rejit.h:41-138): the same names, argument meaning
+// and error behaviour, so that a program written against rejit (the regexdna
+// and jrep samples, the benchmark engine) compiles and links against this
+// library unchanged.  Behind it the pattern is lowered ahead of time to
+// tables for hand-written sm_100a CUDA kernels instead of being JIT-compiled
+// to x64 (see include/rejit_b200.h for the C boundary and DESIGN.md).
+//
+// Additions: Regej::MatchAllParallel and the free MatchAllParallel helper.
+//
+// Written from scratch for this project; only the declarations' shapes are
+// shared with the reference, because they ARE the compatibility contract.
+#ifndef REJIT_H_
+#define REJIT_H_
+
+#include <string>
+#include <vector>
+
+using namespace std;   // the reference header exports std:: names to its users
+
+namespace rejit {
+
+// Half-open byte range [begin, end) inside the searched text.
+// A zero-length match has begin == end (e.g. "^$" on "" yields one match whose
+// two pointers both address the terminator).
+struct Match {
+  const char* begin;
+  const char* end;
+};
+
+enum MatchType { kMatchFull, kMatchAnywhere, kMatchFirst, kMatchAll, kNMatchTypes };
+
+// RejitSuccess or a (negative) parser error; the message of the most recent
+// error is kept in rejit_status_string (a process-wide 200-byte buffer).
+enum Status { RejitSuccess = 0, ParserError = -1 };
+extern char* const rejit_status_string;
+
+namespace internal { class RegexpInfo; }
+
+class Regej {
+ public:
+  explicit Regej(const char* regexp);
+  explicit Regej(const string& regexp);
+  ~Regej();
+
+  Status status() const { return status_; }
+
+  // True iff the whole text is one match.
+  bool MatchFull(const string& text);
+  bool MatchFull(const char* text, size_t text_size);
+  // True iff some match exists.
+  bool MatchAnywhere(const string& text);
+  bool MatchAnywhere(const char* text, size_t text_size);
+  // Left-most longest match.
+  bool MatchFirst(const string& text, Match* match);
+  bool MatchFirst(const char* text, size_t text_size, Match* match);
+  // All left-most longest, non-overlapping matches, APPENDED to *matches;
+  // returns matches->size().
+  size_t MatchAll(const string& text, std::vector<struct Match>* matches);
+  size_t MatchAll(const char* text, size_t text_size, std::vector<struct Match>* matches);
+  size_t MatchAllCount(const string& text);
+  size_t MatchAllCount(const char* text, size_t text_size);
+  // Same result as MatchAll, with the text sharded by contiguous slab over
+  // n_gpus devices of this machine (new in rejit_b200).
+  size_t MatchAllParallel(const char* text, size_t text_size, std::vector<struct Match>* matches,
+                          int n_gpus);
+
+  bool ReplaceFirst(string& text, const string& with);
+  size_t ReplaceAll(string& text, const string& with);
+
+  // Builds the matcher eagerly (it is otherwise built on first use).
+  bool Compile(MatchType match_type);
+
+ private:
+  char const* const regexp_;
+  internal::RegexpInfo* rinfo_;
+  Status status_;
+};
+
+// One-shot helpers; each call parses and lowers the pattern again.
+bool MatchFull(const char* regexp, const string& text);
+bool MatchFull(const char* regexp, const char* text, size_t text_size);
+bool MatchAnywhere(const char* regexp, const string& text);
+bool MatchAnywhere(const char* regexp, const char* text, size_t text_size);
+bool MatchFirst(const char* regexp, const string& text, Match* match);
+bool MatchFirst(const char* regexp, const char* text, size_t text_size, Match* match);
+size_t MatchAll(const char* regexp, const string& text, std::vector<struct Match>* matches);
+size_t MatchAll(const char* regexp, const char* text, size_t text_size,
+                std::vector<struct Match>* matches);
+size_t MatchAllCount(const char* regexp, const string& text);
+size_t MatchAllCount(const char* regexp, const char* text, size_t text_size);
+size_t MatchAllParallel(const char* regexp, const char* text, size_t text_size,
+                        std::vector<struct Match>* matches, int n_gpus);
+
+void Replace(Match to_replace, string& text, const string& with);
+void Replace(vector<Match>* to_replace, string& text, const string& with);
+bool ReplaceFirst(const char* regexp, string& text, const string& with);
+size_t ReplaceAll(const char* regexp, string& text, const string& with);
+
+}  // namespace rejit
+
+#endif  // REJIT_H_

@@ -1,0 +1,150 @@
+/* include/rejit_b200.h — the C ABI of the B200-native matching engine.
+ *
+ * This is the drop-in boundary for rejit's MatchAll hot path.  In the
+ * reference, `Regej::Compile` turns the lowered regexp (RegexpInfo,
+ * /root/reference/src/regexp.h:538-636) into four JIT'd x64 functions
+ *     bool     MatchFull    (const char*, size_t)
+ *     bool     MatchAnywhere(const char*, size_t)
+ *     bool     MatchFirst   (const char*, size_t, Match*)
+ *     unsigned MatchAll     (const char*, size_t, std::vector<Match>*)
+ * (/root/reference/src/regexp.h:533-536) that `Regej::Match*` call through
+ * function pointers (/root/reference/src/rejit.cc:154,167,180,193).  The entry
+ * points below replace exactly that pair — "compile the lowered regexp" and
+ * "call the compiled matcher" — with an ahead-of-time lowering to tables for
+ * hand-written sm_100a kernels.  Plain pointers and sizes only; offsets (not
+ * pointers) cross the boundary, the C++ facade converts them back to
+ * rejit::Match {begin,end}.  INTEGRATION.md shows the reference-side binding.
+ *
+ * There is no CPU fallback: every matching entry point fails with an error
+ * when no CUDA device (or the CUDA part of the library) is available.
+ */
+#ifndef REJIT_B200_H_
+#define REJIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- the lowered regexp: a flat restatement of RegexpInfo ---------------
+ * One rejit_b200_edge per "physical regexp" of re_matching_list_ /
+ * re_control_list_ (src/regexp.h:586-600); `kind` follows the order of
+ * LIST_PHYSICAL_REGEXP_TYPES (src/regexp.h:27-41).                          */
+enum {
+  REJIT_B200_EDGE_MULTIPLE_CHAR = 0, /* payload: the bytes                    */
+  REJIT_B200_EDGE_PERIOD = 1,
+  REJIT_B200_EDGE_BRACKET = 2,       /* payload: u16 n_single, singles, u16 n_range, (lo,hi)*; flags bit0 = non_matching */
+  REJIT_B200_EDGE_START_OF_LINE = 3,
+  REJIT_B200_EDGE_END_OF_LINE = 4,
+  REJIT_B200_EDGE_EPSILON = 5
+};
+
+typedef struct rejit_b200_edge {
+  int32_t kind;
+  int32_t entry_state;
+  int32_t exit_state;
+  int32_t payload_offset;
+  int32_t payload_length;
+  int32_t flags;
+} rejit_b200_edge;
+
+typedef struct rejit_b200_ir {
+  int32_t n_states;      /* RegexpInfo::last_state() + 1                      */
+  int32_t entry_state;   /* RegexpInfo::entry_state()                         */
+  int32_t exit_state;    /* RegexpInfo::exit_state()                          */
+  int32_t n_matching;    /* edges[0 .. n_matching) = re_matching_list_        */
+  int32_t n_control;     /* edges[n_matching .. +n_control) = re_control_list_ */
+  const rejit_b200_edge* edges;
+  const uint8_t* payload;
+  size_t payload_length;
+} rejit_b200_ir;
+
+typedef struct rejit_b200_program rejit_b200_program;
+
+/* Chain state carried across a slab boundary when one text is scanned in
+ * pieces (multi-GPU sharding): `cur` = smallest offset at which the next match
+ * may begin, `tail` = end of the last selected non-empty match (UINT64_MAX if
+ * none).                                                                     */
+typedef struct rejit_b200_carry {
+  uint64_t cur;
+  uint64_t tail;
+} rejit_b200_carry;
+
+typedef struct rejit_b200_stats {
+  float scan_ms;        /* text-scanning kernel(s), CUDA events on the engine stream */
+  float total_ms;       /* whole device pipeline                                  */
+  uint32_t launches;    /* kernels launched by the call                           */
+  uint32_t reruns;
+  uint64_t candidates;
+  uint64_t matches;
+  int32_t strategy;     /* 0 literal, 1 fixed-length DFA, 2 literal+window, 3 generic */
+  int32_t large_path;
+} rejit_b200_stats;
+
+/* ---- front end (host only; mirrors Parser + RegexpIndexer + RegexpLister) -- */
+/* Parses an ERE and lowers it.  Returns 0 (RejitSuccess) or -1 (ParserError,
+ * message — reference format — copied to err).  The IR must be released with
+ * rejit_b200_ir_free.  parser_opt mirrors the reference's --use_parser_opt.    */
+int rejit_b200_parse(const char* pattern, size_t pattern_length, int parser_opt,
+                     rejit_b200_ir** out_ir, char* err, size_t err_length);
+void rejit_b200_ir_free(rejit_b200_ir* ir);
+/* Text dump of the lowered IR (tests diff it against the reference's
+ * --print_re_list output).  Returns bytes needed (excluding NUL).             */
+size_t rejit_b200_ir_dump(const rejit_b200_ir* ir, char* buffer, size_t buffer_length);
+
+/* ---- compile: replaces Codegen::Compile (src/codegen.cc:591-656) ----------- */
+/* Needs no GPU: builds the automaton tables; device copies are made lazily.    */
+rejit_b200_program* rejit_b200_compile(const rejit_b200_ir* ir, char* err, size_t err_length);
+void rejit_b200_program_free(rejit_b200_program* program);
+/* One-line description of the chosen scan strategy.                            */
+const char* rejit_b200_program_describe(const rejit_b200_program* program);
+
+/* ---- the compiled matchers: replace the four JIT'd functions -------------- */
+/* Host text in, results out.  MatchAll writes up to `capacity` (begin,end)
+ * byte-offset pairs and returns the number of matches found (may exceed
+ * capacity), or -1 on error (no device, CUDA failure; message in err).        */
+int64_t rejit_b200_match_all(rejit_b200_program* program, const char* text, size_t text_length,
+                             uint64_t* out_pairs, size_t capacity, char* err, size_t err_length);
+/* As above but returns a malloc'ed array of pairs (free with rejit_b200_free). */
+int64_t rejit_b200_match_all_alloc(rejit_b200_program* program, const char* text, size_t text_length,
+                                   uint64_t** out_pairs, rejit_b200_stats* stats,
+                                   char* err, size_t err_length);
+/* 1 = found (out_pair filled), 0 = not found, -1 = error.                      */
+int rejit_b200_match_first(rejit_b200_program* program, const char* text, size_t text_length,
+                           uint64_t out_pair[2], char* err, size_t err_length);
+int rejit_b200_match_full(rejit_b200_program* program, const char* text, size_t text_length,
+                          char* err, size_t err_length);
+int rejit_b200_match_anywhere(rejit_b200_program* program, const char* text, size_t text_length,
+                              char* err, size_t err_length);
+/* MatchAllParallel (new; named by BASELINE.json, absent from the reference):
+ * the text is cut into n_gpus contiguous slabs, one per device.               */
+int64_t rejit_b200_match_all_multi_gpu(rejit_b200_program* program, const char* text, size_t text_length,
+                                       int n_gpus, uint64_t** out_pairs, rejit_b200_stats* stats,
+                                       char* err, size_t err_length);
+
+/* ---- device-resident text (benchmarks, pipelines that keep text in HBM) ---- */
+int rejit_b200_device_count(void);
+void* rejit_b200_device_alloc(int device, size_t bytes);          /* 16-byte aligned, padded */
+void rejit_b200_device_free(int device, void* ptr);
+void* rejit_b200_pinned_alloc(size_t bytes);
+void rejit_b200_pinned_free(void* ptr);
+int rejit_b200_copy_to_device(int device, void* dst, const void* src, size_t bytes);
+int rejit_b200_copy_from_device(int device, void* dst, const void* src, size_t bytes);
+void rejit_b200_flush_l2(int device);
+/* d_text: device pointer (16-byte aligned) to text_length bytes; d_out_pairs:
+ * device buffer for `capacity` pairs (may be NULL with capacity 0 to count).
+ * carry_in / carry_out may be NULL (whole text in one call).                   */
+int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, const void* d_text,
+                                    size_t text_length, uint64_t* d_out_pairs, size_t capacity,
+                                    const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
+                                    rejit_b200_stats* stats, char* err, size_t err_length);
+
+void rejit_b200_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* REJIT_B200_H_ */

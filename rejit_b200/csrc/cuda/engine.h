@@ -1,0 +1,81 @@
+// Internal C++ interface of the sm_100a matching engine (below the C ABI of
+// include/rejit_b200.h, above the kernels of engine.cu).
+#ifndef REJIT_B200_CUDA_ENGINE_H_
+#define REJIT_B200_CUDA_ENGINE_H_
+
+#include <stdint.h>
+#include <string>
+
+#include "../host/automaton.h"
+
+namespace rejit_b200 {
+
+struct Carry {                  // chain state crossing a slab boundary (§8e)
+  uint64_t cur = 0;             // smallest offset where the next match may begin
+  uint64_t tail = ~0ull;        // end of the last selected non-empty match
+};
+
+struct RunStats {
+  float scan_ms = 0;            // the text-scanning kernel(s) only (CUDA events)
+  float total_ms = 0;           // whole device pipeline (scan + verify + resolve)
+  uint32_t launches = 0;        // kernels launched by this call
+  uint32_t reruns = 0;          // pipeline restarts after a capacity overflow
+  uint64_t candidates = 0;      // (begin, E(begin)) pairs before selection
+  uint64_t matches = 0;
+  int strategy = 0;
+  int large_path = 0;
+};
+
+class DeviceProgram;            // per-device tables of one compiled pattern
+class DeviceContext;            // per-device stream and scratch buffers
+
+// A compiled pattern: host automaton + lazily created per-device tables.
+class Program {
+ public:
+  static Program* Create(const LoweredRegexp& lr, std::string* error);
+  ~Program();
+  const CompiledAutomaton& automaton() const { return automaton_; }
+  DeviceProgram* OnDevice(int device, std::string* error);
+
+ private:
+  Program() {}
+  CompiledAutomaton automaton_;
+  DeviceProgram* per_device_[16] = {nullptr};
+};
+
+// ---- device plumbing ------------------------------------------------------
+int DeviceCount();
+bool CudaOk(std::string* error);                       // is a usable GPU present
+DeviceContext* ContextFor(int device, std::string* error);
+void* DeviceAlloc(int device, size_t bytes, std::string* error);
+void DeviceFree(int device, void* p);
+void* PinnedAlloc(size_t bytes);
+void PinnedFree(void* p);
+bool CopyToDevice(int device, void* dst, const void* src, size_t bytes, std::string* error);
+bool CopyFromDevice(int device, void* dst, const void* src, size_t bytes, std::string* error);
+void FlushL2(int device);                              // writes a buffer larger than L2
+
+// ---- the hot path -----------------------------------------------------------
+// MatchAll over text resident in device memory (16-byte aligned).  Writes up to
+// out_cap (begin,end) offset pairs to d_out (device memory, may be null when
+// out_cap == 0) and returns the number of matches, or -1 with *error set.
+int64_t MatchAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_t n,
+                       uint64_t* d_out, uint64_t out_cap, const Carry& in, Carry* out,
+                       RunStats* stats, std::string* error);
+
+// MatchAll over host text: H2D copy, device pipeline, D2H of the match list.
+// *pairs is malloc'ed by the callee (count*2 uint64), caller frees.
+int64_t MatchAllHost(int device, Program* prog, const uint8_t* text, uint64_t n,
+                     uint64_t** pairs, RunStats* stats, std::string* error);
+
+// Same, with the text cut into `n_gpus` contiguous slabs, one per device, each
+// scanned with a right halo; chains are stitched at the slab edges (§8e).
+int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int n_gpus,
+                             uint64_t** pairs, RunStats* stats, std::string* error);
+
+// MatchFull: 1 / 0, or -1 on error.
+int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error);
+
+}  // namespace rejit_b200
+
+#endif  // REJIT_B200_CUDA_ENGINE_H_

@@ -1,0 +1,302 @@
+// Implementation of the C ABI declared in include/rejit_b200.h.
+#include "../../../include/rejit_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../cuda/engine.h"
+#include "automaton.h"
+#include "ir.h"
+
+using namespace rejit_b200;
+
+namespace {
+
+struct IrHolder {
+  rejit_b200_ir ir;                 // must stay the first member
+  std::vector<rejit_b200_edge> edges;
+  std::vector<uint8_t> payload;
+};
+
+void SetErr(char* err, size_t len, const std::string& msg) {
+  if (!err || !len) return;
+  size_t k = msg.size() < len - 1 ? msg.size() : len - 1;
+  memcpy(err, msg.data(), k);
+  err[k] = 0;
+}
+
+void PutU16(std::vector<uint8_t>* v, size_t x) {
+  v->push_back(static_cast<uint8_t>(x & 0xFF));
+  v->push_back(static_cast<uint8_t>((x >> 8) & 0xFF));
+}
+
+void Flatten(const LoweredRegexp& lr, IrHolder* h) {
+  auto add = [&](const Edge& e) {
+    rejit_b200_edge f;
+    f.kind = e.kind;
+    f.entry_state = e.entry;
+    f.exit_state = e.exit;
+    f.payload_offset = static_cast<int32_t>(h->payload.size());
+    f.flags = 0;
+    if (e.kind == kEdgeLiteral) {
+      h->payload.insert(h->payload.end(), e.bytes.begin(), e.bytes.end());
+    } else if (e.kind == kEdgeCharSet) {
+      PutU16(&h->payload, e.singles.size());
+      h->payload.insert(h->payload.end(), e.singles.begin(), e.singles.end());
+      PutU16(&h->payload, e.ranges.size());
+      for (const ByteRange& r : e.ranges) { h->payload.push_back(r.lo); h->payload.push_back(r.hi); }
+      f.flags = e.negated ? 1 : 0;
+    }
+    f.payload_length = static_cast<int32_t>(h->payload.size()) - f.payload_offset;
+    h->edges.push_back(f);
+  };
+  for (const Edge& e : lr.matching) add(e);
+  for (const Edge& e : lr.control) add(e);
+  h->ir.n_states = lr.n_states;
+  h->ir.entry_state = lr.entry_state;
+  h->ir.exit_state = lr.exit_state;
+  h->ir.n_matching = static_cast<int32_t>(lr.matching.size());
+  h->ir.n_control = static_cast<int32_t>(lr.control.size());
+  h->ir.edges = h->edges.data();
+  h->ir.payload = h->payload.data();
+  h->ir.payload_length = h->payload.size();
+}
+
+bool Unflatten(const rejit_b200_ir* ir, LoweredRegexp* lr, std::string* error) {
+  lr->n_states = ir->n_states;
+  lr->entry_state = ir->entry_state;
+  lr->exit_state = ir->exit_state;
+  int total = ir->n_matching + ir->n_control;
+  for (int i = 0; i < total; ++i) {
+    const rejit_b200_edge& f = ir->edges[i];
+    Edge e;
+    e.kind = f.kind;
+    e.entry = f.entry_state;
+    e.exit = f.exit_state;
+    if (e.entry < 0 || e.exit < 0 || e.entry >= ir->n_states || e.exit >= ir->n_states ||
+        f.payload_offset < 0 || f.payload_length < 0 ||
+        static_cast<size_t>(f.payload_offset) + f.payload_length > ir->payload_length) {
+      *error = "rejit_b200_compile: malformed IR";
+      return false;
+    }
+    const uint8_t* p = ir->payload + f.payload_offset;
+    if (f.kind == kEdgeLiteral) {
+      if (f.payload_length == 0) { *error = "rejit_b200_compile: empty MultipleChar"; return false; }
+      e.bytes.assign(p, p + f.payload_length);
+    } else if (f.kind == kEdgeCharSet) {
+      size_t at = 0;
+      auto need = [&](size_t k) { return at + k <= static_cast<size_t>(f.payload_length); };
+      if (!need(2)) { *error = "rejit_b200_compile: malformed Bracket"; return false; }
+      size_t ns = p[at] | (p[at + 1] << 8); at += 2;
+      if (!need(ns + 2)) { *error = "rejit_b200_compile: malformed Bracket"; return false; }
+      e.singles.assign(p + at, p + at + ns); at += ns;
+      size_t nr = p[at] | (p[at + 1] << 8); at += 2;
+      if (!need(2 * nr)) { *error = "rejit_b200_compile: malformed Bracket"; return false; }
+      for (size_t r = 0; r < nr; ++r) e.ranges.push_back({p[at + 2 * r], p[at + 2 * r + 1]});
+      e.negated = (f.flags & 1) != 0;
+    } else if (f.kind < 0 || f.kind > kEdgeEpsilon) {
+      *error = "rejit_b200_compile: unknown edge kind";
+      return false;
+    }
+    bool control = f.kind >= kEdgeLineStart;
+    if (control != (i >= ir->n_matching)) { *error = "rejit_b200_compile: edge in the wrong list"; return false; }
+    (control ? lr->control : lr->matching).push_back(e);
+  }
+  return true;
+}
+
+}  // namespace
+
+struct rejit_b200_program {
+  Program* prog;
+};
+
+extern "C" {
+
+int rejit_b200_parse(const char* pattern, size_t pattern_length, int parser_opt,
+                     rejit_b200_ir** out_ir, char* err, size_t err_length) {
+  if (out_ir) *out_ir = nullptr;
+  ParseOptions opt;
+  opt.parser_opt = parser_opt != 0;
+  std::string msg;
+  NodePtr root = ParseERE(pattern, pattern_length, opt, &msg);
+  if (!root) {
+    SetErr(err, err_length, msg);
+    return -1;
+  }
+  LoweredRegexp lr = Lower(root.get());
+  IrHolder* h = new IrHolder();
+  Flatten(lr, h);
+  if (out_ir) *out_ir = &h->ir; else delete h;
+  return 0;
+}
+
+void rejit_b200_ir_free(rejit_b200_ir* ir) {
+  delete reinterpret_cast<IrHolder*>(ir);
+}
+
+size_t rejit_b200_ir_dump(const rejit_b200_ir* ir, char* buffer, size_t buffer_length) {
+  LoweredRegexp lr;
+  std::string error;
+  std::string text = Unflatten(ir, &lr, &error) ? DumpLowered(lr) : ("error: " + error);
+  if (buffer && buffer_length) {
+    size_t k = text.size() < buffer_length - 1 ? text.size() : buffer_length - 1;
+    memcpy(buffer, text.data(), k);
+    buffer[k] = 0;
+  }
+  return text.size();
+}
+
+rejit_b200_program* rejit_b200_compile(const rejit_b200_ir* ir, char* err, size_t err_length) {
+  LoweredRegexp lr;
+  std::string error;
+  if (!ir || !Unflatten(ir, &lr, &error)) {
+    SetErr(err, err_length, ir ? error : "rejit_b200_compile: null IR");
+    return nullptr;
+  }
+  Program* p = Program::Create(lr, &error);
+  if (!p) {
+    SetErr(err, err_length, error);
+    return nullptr;
+  }
+  rejit_b200_program* h = new rejit_b200_program;
+  h->prog = p;
+  return h;
+}
+
+void rejit_b200_program_free(rejit_b200_program* program) {
+  if (!program) return;
+  delete program->prog;
+  delete program;
+}
+
+const char* rejit_b200_program_describe(const rejit_b200_program* program) {
+  return program ? program->prog->automaton().describe.c_str() : "";
+}
+
+static void FillStats(const RunStats& s, rejit_b200_stats* out) {
+  if (!out) return;
+  out->scan_ms = s.scan_ms;
+  out->total_ms = s.total_ms;
+  out->launches = s.launches;
+  out->reruns = s.reruns;
+  out->candidates = s.candidates;
+  out->matches = s.matches;
+  out->strategy = s.strategy;
+  out->large_path = s.large_path;
+}
+
+int64_t rejit_b200_match_all_alloc(rejit_b200_program* program, const char* text, size_t text_length,
+                                   uint64_t** out_pairs, rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  RunStats rs;
+  uint64_t* pairs = nullptr;
+  int64_t r = MatchAllHost(0, program->prog, reinterpret_cast<const uint8_t*>(text), text_length, &pairs,
+                           stats ? &rs : nullptr, &error);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  FillStats(rs, stats);
+  if (out_pairs) *out_pairs = pairs; else free(pairs);
+  return r;
+}
+
+int64_t rejit_b200_match_all(rejit_b200_program* program, const char* text, size_t text_length,
+                             uint64_t* out_pairs, size_t capacity, char* err, size_t err_length) {
+  uint64_t* pairs = nullptr;
+  int64_t r = rejit_b200_match_all_alloc(program, text, text_length, &pairs, nullptr, err, err_length);
+  if (r < 0) return r;
+  size_t k = static_cast<size_t>(r) < capacity ? static_cast<size_t>(r) : capacity;
+  if (k && out_pairs) memcpy(out_pairs, pairs, k * 16);
+  free(pairs);
+  return r;
+}
+
+int rejit_b200_match_first(rejit_b200_program* program, const char* text, size_t text_length,
+                           uint64_t out_pair[2], char* err, size_t err_length) {
+  // MatchFirst := first element of MatchAll
+  uint64_t* pairs = nullptr;
+  int64_t r = rejit_b200_match_all_alloc(program, text, text_length, &pairs, nullptr, err, err_length);
+  if (r < 0) return -1;
+  if (r > 0 && out_pair) { out_pair[0] = pairs[0]; out_pair[1] = pairs[1]; }
+  free(pairs);
+  return r > 0 ? 1 : 0;
+}
+
+int rejit_b200_match_full(rejit_b200_program* program, const char* text, size_t text_length,
+                          char* err, size_t err_length) {
+  std::string error;
+  int r = MatchFullHost(0, program->prog, reinterpret_cast<const uint8_t*>(text), text_length, &error);
+  if (r < 0) SetErr(err, err_length, error);
+  return r;
+}
+
+int rejit_b200_match_anywhere(rejit_b200_program* program, const char* text, size_t text_length,
+                              char* err, size_t err_length) {
+  uint64_t* pairs = nullptr;
+  int64_t r = rejit_b200_match_all_alloc(program, text, text_length, &pairs, nullptr, err, err_length);
+  if (r < 0) return -1;
+  free(pairs);
+  return r > 0 ? 1 : 0;
+}
+
+int64_t rejit_b200_match_all_multi_gpu(rejit_b200_program* program, const char* text, size_t text_length,
+                                       int n_gpus, uint64_t** out_pairs, rejit_b200_stats* stats,
+                                       char* err, size_t err_length) {
+  std::string error;
+  RunStats rs;
+  uint64_t* pairs = nullptr;
+  int64_t r = MatchAllHostMultiGpu(program->prog, reinterpret_cast<const uint8_t*>(text), text_length, n_gpus,
+                                   &pairs, &rs, &error);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  FillStats(rs, stats);
+  if (out_pairs) *out_pairs = pairs; else free(pairs);
+  return r;
+}
+
+int rejit_b200_device_count(void) { return DeviceCount(); }
+
+void* rejit_b200_device_alloc(int device, size_t bytes) {
+  std::string error;
+  void* p = DeviceAlloc(device, bytes, &error);
+  if (!p) fprintf(stderr, "rejit_b200_device_alloc: %s\n", error.c_str());
+  return p;
+}
+void rejit_b200_device_free(int device, void* ptr) { DeviceFree(device, ptr); }
+void* rejit_b200_pinned_alloc(size_t bytes) { return PinnedAlloc(bytes); }
+void rejit_b200_pinned_free(void* ptr) { PinnedFree(ptr); }
+
+int rejit_b200_copy_to_device(int device, void* dst, const void* src, size_t bytes) {
+  std::string error;
+  if (CopyToDevice(device, dst, src, bytes, &error)) return 0;
+  fprintf(stderr, "rejit_b200_copy_to_device: %s\n", error.c_str());
+  return -1;
+}
+int rejit_b200_copy_from_device(int device, void* dst, const void* src, size_t bytes) {
+  std::string error;
+  if (CopyFromDevice(device, dst, src, bytes, &error)) return 0;
+  fprintf(stderr, "rejit_b200_copy_from_device: %s\n", error.c_str());
+  return -1;
+}
+void rejit_b200_flush_l2(int device) { FlushL2(device); }
+
+int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, const void* d_text,
+                                    size_t text_length, uint64_t* d_out_pairs, size_t capacity,
+                                    const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
+                                    rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  Carry in, out;
+  if (carry_in) { in.cur = carry_in->cur; in.tail = carry_in->tail; }
+  RunStats rs;
+  int64_t r = MatchAllDevice(device, program->prog, static_cast<const uint8_t*>(d_text), text_length,
+                             d_out_pairs, capacity, in, &out, stats ? &rs : nullptr, &error);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  if (carry_out) { carry_out->cur = out.cur; carry_out->tail = out.tail; }
+  FillStats(rs, stats);
+  return r;
+}
+
+void rejit_b200_free(void* ptr) { free(ptr); }
+
+}  // extern "C"

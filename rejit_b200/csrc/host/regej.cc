@@ -1,0 +1,201 @@
+// The rejit::Regej facade over the C ABI (include/rejit_b200.h).
+//
+// Mirrors the behaviour of the reference's API glue
+// (/root/reference/src/rejit.cc:29-267): the constructor parses (ERE only) and
+// records the status; matchers build lazily; MatchAll APPENDS to the caller's
+// vector and returns its size; MatchAllCount/ReplaceAll are built on MatchAll;
+// Replace rebuilds the string in one pass.  Internal failures (no CUDA device,
+// CUDA errors) are fatal, like the reference's rejit_fatal
+// (/root/reference/src/checks.cc:19-26): there is no CPU matcher to fall back to.
+#include "../../../include/rejit.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../../include/rejit_b200.h"
+
+namespace rejit {
+
+namespace {
+char g_status[200] = "";
+}
+char* const rejit_status_string = g_status;
+
+namespace internal {
+class RegexpInfo {
+ public:
+  rejit_b200_ir* ir = nullptr;
+  rejit_b200_program* program = nullptr;
+  ~RegexpInfo() {
+    if (program) rejit_b200_program_free(program);
+    if (ir) rejit_b200_ir_free(ir);
+  }
+};
+}  // namespace internal
+
+namespace {
+
+[[noreturn]] void Fatal(const char* what, const char* detail) {
+  fprintf(stderr, "rejit_b200 fatal: %s: %s\n", what, detail);
+  abort();
+}
+
+Status ParseInto(const char* regexp, internal::RegexpInfo* info) {
+  char err[sizeof g_status];
+  err[0] = 0;
+  int rc = rejit_b200_parse(regexp, regexp ? strlen(regexp) : 0, /*parser_opt=*/1, &info->ir, err, sizeof err);
+  if (rc != 0) {
+    snprintf(g_status, sizeof g_status, "%s", err);
+    return ParserError;
+  }
+  return RejitSuccess;
+}
+
+}  // namespace
+
+Regej::Regej(const char* regexp) : regexp_(regexp), rinfo_(new internal::RegexpInfo()) {
+  status_ = ParseInto(regexp_, rinfo_);
+}
+
+Regej::Regej(const string& regexp) : regexp_(regexp.c_str()), rinfo_(new internal::RegexpInfo()) {
+  status_ = ParseInto(regexp_, rinfo_);
+}
+
+Regej::~Regej() { delete rinfo_; }
+
+bool Regej::Compile(MatchType) {
+  if (status_ != RejitSuccess) return false;
+  if (rinfo_->program) return true;
+  char err[256];
+  err[0] = 0;
+  rinfo_->program = rejit_b200_compile(rinfo_->ir, err, sizeof err);
+  if (!rinfo_->program) {
+    snprintf(g_status, sizeof g_status, "%s", err);
+    return false;
+  }
+  return true;
+}
+
+bool Regej::MatchFull(const string& text) { return MatchFull(text.c_str(), text.size()); }
+bool Regej::MatchFull(const char* text, size_t text_size) {
+  if (!Compile(kMatchFull)) return false;
+  char err[256];
+  int r = rejit_b200_match_full(rinfo_->program, text, text_size, err, sizeof err);
+  if (r < 0) Fatal("MatchFull", err);
+  return r == 1;
+}
+
+bool Regej::MatchAnywhere(const string& text) { return MatchAnywhere(text.c_str(), text.size()); }
+bool Regej::MatchAnywhere(const char* text, size_t text_size) {
+  if (!Compile(kMatchAnywhere)) return false;
+  char err[256];
+  int r = rejit_b200_match_anywhere(rinfo_->program, text, text_size, err, sizeof err);
+  if (r < 0) Fatal("MatchAnywhere", err);
+  return r == 1;
+}
+
+bool Regej::MatchFirst(const string& text, Match* match) { return MatchFirst(text.c_str(), text.size(), match); }
+bool Regej::MatchFirst(const char* text, size_t text_size, Match* match) {
+  if (!Compile(kMatchFirst)) return false;
+  char err[256];
+  uint64_t pair[2] = {0, 0};
+  int r = rejit_b200_match_first(rinfo_->program, text, text_size, pair, err, sizeof err);
+  if (r < 0) Fatal("MatchFirst", err);
+  if (r == 1 && match) {
+    match->begin = text + pair[0];
+    match->end = text + pair[1];
+  }
+  return r == 1;
+}
+
+size_t Regej::MatchAll(const string& text, vector<Match>* matches) {
+  return MatchAll(text.c_str(), text.size(), matches);
+}
+size_t Regej::MatchAll(const char* text, size_t text_size, vector<Match>* matches) {
+  if (!Compile(kMatchAll)) return 0;
+  char err[256];
+  uint64_t* pairs = nullptr;
+  int64_t n = rejit_b200_match_all_alloc(rinfo_->program, text, text_size, &pairs, nullptr, err, sizeof err);
+  if (n < 0) Fatal("MatchAll", err);
+  if (matches) {
+    matches->reserve(matches->size() + static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) matches->push_back(Match{text + pairs[2 * i], text + pairs[2 * i + 1]});
+  }
+  rejit_b200_free(pairs);
+  return matches ? matches->size() : static_cast<size_t>(n);
+}
+
+size_t Regej::MatchAllParallel(const char* text, size_t text_size, vector<Match>* matches, int n_gpus) {
+  if (!Compile(kMatchAll)) return 0;
+  char err[256];
+  uint64_t* pairs = nullptr;
+  int64_t n = rejit_b200_match_all_multi_gpu(rinfo_->program, text, text_size, n_gpus, &pairs, nullptr, err, sizeof err);
+  if (n < 0) Fatal("MatchAllParallel", err);
+  if (matches) {
+    matches->reserve(matches->size() + static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) matches->push_back(Match{text + pairs[2 * i], text + pairs[2 * i + 1]});
+  }
+  rejit_b200_free(pairs);
+  return matches ? matches->size() : static_cast<size_t>(n);
+}
+
+size_t Regej::MatchAllCount(const string& text) { return MatchAllCount(text.c_str(), text.size()); }
+size_t Regej::MatchAllCount(const char* text, size_t text_size) {
+  vector<Match> found;
+  return MatchAll(text, text_size, &found);
+}
+
+bool Regej::ReplaceFirst(string& text, const string& with) {
+  Match m;
+  if (!MatchFirst(text, &m)) return false;
+  Replace(m, text, with);
+  return true;
+}
+
+size_t Regej::ReplaceAll(string& text, const string& with) {
+  vector<Match> found;
+  MatchAll(text, &found);
+  Replace(&found, text, with);
+  return found.size();
+}
+
+// ---- free helpers ------------------------------------------------------------
+bool MatchFull(const char* regexp, const string& text) { return MatchFull(regexp, text.c_str(), text.size()); }
+bool MatchFull(const char* regexp, const char* text, size_t n) { Regej re(regexp); return re.MatchFull(text, n); }
+bool MatchAnywhere(const char* regexp, const string& text) { return MatchAnywhere(regexp, text.c_str(), text.size()); }
+bool MatchAnywhere(const char* regexp, const char* text, size_t n) { Regej re(regexp); return re.MatchAnywhere(text, n); }
+bool MatchFirst(const char* regexp, const string& text, Match* m) { return MatchFirst(regexp, text.c_str(), text.size(), m); }
+bool MatchFirst(const char* regexp, const char* text, size_t n, Match* m) { Regej re(regexp); return re.MatchFirst(text, n, m); }
+size_t MatchAll(const char* regexp, const string& text, vector<Match>* out) { return MatchAll(regexp, text.c_str(), text.size(), out); }
+size_t MatchAll(const char* regexp, const char* text, size_t n, vector<Match>* out) { Regej re(regexp); return re.MatchAll(text, n, out); }
+size_t MatchAllCount(const char* regexp, const string& text) { return MatchAllCount(regexp, text.c_str(), text.size()); }
+size_t MatchAllCount(const char* regexp, const char* text, size_t n) { Regej re(regexp); return re.MatchAllCount(text, n); }
+size_t MatchAllParallel(const char* regexp, const char* text, size_t n, vector<Match>* out, int n_gpus) {
+  Regej re(regexp);
+  return re.MatchAllParallel(text, n, out, n_gpus);
+}
+
+void Replace(Match to_replace, string& text, const string& with) {
+  vector<Match> one(1, to_replace);
+  Replace(&one, text, with);
+}
+
+void Replace(vector<Match>* to_replace, string& text, const string& with) {
+  string rebuilt;
+  rebuilt.reserve(text.size() + text.size() / 16);
+  const char* base = text.c_str();
+  const char* at = base;
+  for (const Match& m : *to_replace) {
+    rebuilt.append(at, static_cast<size_t>(m.begin - at));
+    rebuilt.append(with);
+    at = m.end;
+  }
+  rebuilt.append(at, static_cast<size_t>(base + text.size() - at));
+  text.swap(rebuilt);
+}
+
+bool ReplaceFirst(const char* regexp, string& text, const string& with) { Regej re(regexp); return re.ReplaceFirst(text, with); }
+size_t ReplaceAll(const char* regexp, string& text, const string& with) { Regej re(regexp); return re.ReplaceAll(text, with); }
+
+}  // namespace rejit

@@ -1,0 +1,233 @@
+// tests/hostsim.cc — TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Runs the product's host front end (parser, lowering, automaton tables) and the
+// host+device shared logic of rejit_b200/csrc/cuda/device_program.h (NfaRun,
+// ChainTake) on the CPU, emulating what each kernel of engine.cu does with the
+// tables: the literal scan, the sub-stream DFA scan with its warm-up, the
+// needle-window verification, the generic per-start run, and both resolve
+// paths (sequential chain and restart-point segments).  It exists so that the
+// CPU-only test tier (`pytest -m "not gpu"`, run where no GPU exists) can
+// compare the tables and the selection logic with the oracle; the kernels
+// themselves are only exercised by the GPU tier.
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../rejit_b200/csrc/cuda/device_program.h"
+#include "../rejit_b200/csrc/host/automaton.h"
+#include "../rejit_b200/csrc/host/ir.h"
+
+using namespace rejit_b200;
+
+namespace {
+
+struct Compiled {
+  CompiledAutomaton ca;
+  FlatTables ft;
+  NfaTables nfa;
+};
+
+bool CompilePattern(const char* pattern, size_t plen, int parser_opt, Compiled* c, std::string* error) {
+  ParseOptions opt;
+  opt.parser_opt = parser_opt != 0;
+  NodePtr root = ParseERE(pattern, plen, opt, error);
+  if (!root) return false;
+  LoweredRegexp lr = Lower(root.get());
+  if (!BuildAutomaton(lr, &c->ca, error)) return false;
+  FlattenTables(c->ca, &c->ft);
+  NfaTables& t = c->nfa;
+  t.n_pos = c->ft.n_pos;
+  t.words = c->ft.words;
+  t.has_anchor = c->ca.nfa.has_anchor ? 1 : 0;
+  t.byte_mask = c->ft.byte_mask.data();
+  t.first = c->ft.first.data();
+  t.follow = c->ft.follow.data();
+  t.accept = c->ft.accept.data();
+  t.chain = c->ft.chain.data();
+  t.start_ok = c->ft.start_ok.data();
+  for (int i = 0; i < 4; ++i) t.accept_empty[i] = c->ft.accept_empty[i];
+  return true;
+}
+
+typedef std::vector<std::pair<uint64_t, uint64_t>> Cands;
+
+void ScanLiteral(const std::vector<uint8_t>& needle, const uint8_t* text, uint64_t n, Cands* out) {
+  uint64_t m = needle.size();
+  for (uint64_t p = 0; p + m <= n; ++p)
+    if (memcmp(text + p, needle.data(), m) == 0) out->push_back({p, p + m});
+}
+
+// Emulates k_dfa_scan: independent sub-streams with a rounded-up warm-up.
+void ScanDfaStreams(const Compiled& c, const uint8_t* text, uint64_t n, uint32_t stream_bytes, Cands* out) {
+  const ScanDfa& d = c.ca.dfa;
+  const uint32_t L = (uint32_t)d.match_len;
+  const uint32_t warm = (L - 1 + 15) & ~15u;
+  const uint32_t acc = (uint32_t)(d.first_accept * d.n_classes);
+  uint64_t n_streams = (n + stream_bytes - 1) / stream_bytes;
+  for (uint64_t sidx = 0; sidx < n_streams; ++sidx) {
+    uint64_t a = sidx * stream_bytes;
+    uint64_t b = std::min<uint64_t>(n, a + stream_bytes);
+    uint64_t p = (a >= warm) ? a - warm : 0;
+    uint32_t state = 0;
+    for (; p < b; ++p) {
+      state = c.ft.dfa_next[state + c.ft.dfa_class[text[p]]];
+      if (state >= acc) {
+        uint64_t e = p + 1;
+        if (e > a && e >= L) out->push_back({e - L, e});
+      }
+    }
+  }
+}
+
+void ScanWindow(const Compiled& c, const uint8_t* text, uint64_t n, Cands* out) {
+  Cands hits;
+  ScanLiteral(c.ca.literal, text, n, &hits);
+  uint32_t lo = c.ca.window_lo, hi = c.ca.window_hi;
+  for (auto& h : hits)
+    for (uint32_t j = 0; j <= hi - lo; ++j) {
+      if (h.first + j < hi) continue;
+      uint64_t s = h.first + j - hi;
+      int ctx = c.nfa.has_anchor ? ContextAt(text, n, s) : 0;
+      if (!(s < n && c.nfa.start_ok[ctx * 256 + text[s]])) continue;
+      uint64_t e = NfaRunAny(c.nfa, text, n, s);
+      if (e != kNoMatch) out->push_back({s, e});
+    }
+}
+
+void ScanGeneric(const Compiled& c, const uint8_t* text, uint64_t n, Cands* out) {
+  for (uint64_t s = 0; s <= n; ++s) {
+    int ctx = c.nfa.has_anchor ? ContextAt(text, n, s) : 0;
+    bool ok = c.nfa.accept_empty[ctx] || (s < n && c.nfa.start_ok[ctx * 256 + text[s]]);
+    if (!ok) continue;
+    uint64_t e = NfaRunAny(c.nfa, text, n, s);
+    if (e != kNoMatch) out->push_back({s, e});
+  }
+}
+
+// k_resolve_small's chain
+void ResolveSequential(Cands cands, ChainState st, Cands* out, ChainState* final_state) {
+  std::sort(cands.begin(), cands.end());
+  uint64_t prev = kNoMatch;
+  for (auto& c : cands) {
+    if (c.first == prev) continue;
+    prev = c.first;
+    if (ChainTake(&st, c.first, c.second)) out->push_back(c);
+  }
+  if (final_state) *final_state = st;
+}
+
+// the large path: exclusive max scan, restart points, per-segment chains
+void ResolveSegments(Cands cands, ChainState carry, Cands* out) {
+  std::sort(cands.begin(), cands.end());
+  size_t m = cands.size();
+  std::vector<uint64_t> reach(m);
+  uint64_t run = carry.cur;
+  for (size_t i = 0; i < m; ++i) { reach[i] = run; run = std::max(run, cands[i].second); }
+  auto restart = [&](size_t i) {
+    return reach[i] < cands[i].first || (reach[i] == cands[i].first && cands[i].second > cands[i].first);
+  };
+  std::vector<char> take(m, 0);
+  for (size_t i = 0; i < m; ++i) {
+    bool head = (i == 0) || (cands[i].first != cands[i - 1].first && restart(i));
+    if (!head) continue;
+    ChainState st = (i == 0) ? carry : ChainState{0, kNoMatch};
+    uint64_t prev = kNoMatch;
+    for (size_t j = i; j < m; ++j) {
+      if (j > i && cands[j].first != cands[j - 1].first && restart(j)) break;
+      if (cands[j].first == prev) { take[j] = 0; continue; }
+      prev = cands[j].first;
+      take[j] = ChainTake(&st, cands[j].first, cands[j].second);
+    }
+  }
+  for (size_t i = 0; i < m; ++i) if (take[i]) out->push_back(cands[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+// strategy: -1 = the one the compiler chose, 0..3 = force (3 always legal).
+// Returns the match count; -1 parse/compile error; -2 the two resolve paths
+// disagree; -3 forced strategy not applicable.
+int64_t hostsim_match_all(const char* pattern, size_t plen, int parser_opt, const uint8_t* text, uint64_t n,
+                          int strategy, uint64_t* out_pairs, uint64_t cap, char* describe, size_t dlen) {
+  Compiled c;
+  std::string error;
+  if (!CompilePattern(pattern, plen, parser_opt, &c, &error)) {
+    if (describe && dlen) snprintf(describe, dlen, "%s", error.c_str());
+    return -1;
+  }
+  if (describe && dlen) snprintf(describe, dlen, "%s", c.ca.describe.c_str());
+  int chosen = (int)c.ca.strategy;
+  int use = strategy < 0 ? chosen : strategy;
+  if (use != 3 && use != chosen) return -3;
+  Cands cands;
+  switch (use) {
+    case 0: ScanLiteral(c.ca.literal, text, n, &cands); break;
+    case 1: ScanDfaStreams(c, text, n, 512, &cands); break;
+    case 2: ScanWindow(c, text, n, &cands); break;
+    default: ScanGeneric(c, text, n, &cands);
+  }
+  Cands a, b;
+  ChainState st{0, kNoMatch};
+  ResolveSequential(cands, st, &a, nullptr);
+  ResolveSegments(cands, st, &b);
+  if (a != b) return -2;
+  for (size_t i = 0; i < a.size() && i < cap; ++i) {
+    out_pairs[2 * i] = a[i].first;
+    out_pairs[2 * i + 1] = a[i].second;
+  }
+  return (int64_t)a.size();
+}
+
+// Slab-sharded run with the carry protocol of MatchAllHostMultiGpu (engine.cu):
+// every slab first resolved with carry = (slab start, none), then re-resolved
+// when the chain arriving from the left differs.
+int64_t hostsim_match_all_slabs(const char* pattern, size_t plen, const uint8_t* text, uint64_t n, int slabs,
+                                uint64_t* out_pairs, uint64_t cap) {
+  Compiled c;
+  std::string error;
+  if (!CompilePattern(pattern, plen, 1, &c, &error)) return -1;
+  Cands all;
+  ScanGeneric(c, text, n, &all);
+  std::vector<Cands> part(slabs);
+  std::vector<ChainState> carry_out(slabs);
+  auto bound = [&](int i) { return (n / slabs) * (uint64_t)i; };
+  auto run = [&](int i, ChainState in) {
+    uint64_t lo = bound(i), hi = (i + 1 == slabs) ? n + 1 : bound(i + 1);
+    Cands mine;
+    for (auto& x : all) if (x.first >= lo && x.first < hi) mine.push_back(x);
+    part[i].clear();
+    ResolveSequential(mine, in, &part[i], &carry_out[i]);
+  };
+  for (int i = 0; i < slabs; ++i) run(i, ChainState{bound(i), kNoMatch});
+  ChainState running = carry_out[0];
+  for (int i = 1; i < slabs; ++i) {
+    uint64_t lo = bound(i);
+    if (running.cur > lo || running.tail == lo) {
+      ChainState in = running;
+      if (in.cur < lo) in.cur = lo;
+      run(i, in);
+    }
+    running = carry_out[i];
+  }
+  uint64_t k = 0;
+  for (auto& p : part)
+    for (auto& x : p) {
+      if (k < cap) { out_pairs[2 * k] = x.first; out_pairs[2 * k + 1] = x.second; }
+      ++k;
+    }
+  return (int64_t)k;
+}
+
+int hostsim_match_full(const char* pattern, size_t plen, const uint8_t* text, uint64_t n) {
+  Compiled c;
+  std::string error;
+  if (!CompilePattern(pattern, plen, 1, &c, &error)) return -1;
+  return NfaRunAny(c.nfa, text, n, 0, true) == n ? 1 : 0;
+}
+
+}  // extern "C"
