@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""bench.py — GB/s of text scanned by MatchAll (BASELINE.json's metric).
+
+Workload (config.workload): BASELINE.json configs[1] — the regex-dna alternation
+set (the reference sample has NINE variants, sample/regexdna.cc:52-62) counted
+over a 50 MB synthetic FASTA sequence, one `MatchAll` call per pattern exactly
+as the reference sample does.  A "step" = those nine calls over the text.
+"GB/s text scanned" follows the reference's definition of speed, text_size /
+time per MatchAll call (tools/benchmarks/engines/bench_engine.cc:244-249), summed
+over the calls of a step:  value = 9 * N_bytes / step_time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+  value ......... text resident in HBM; step time = sum of the nine calls' device
+                  pipeline times (CUDA events on the engine's stream, from the
+                  first kernel launch to the match count being back on the
+                  host); L2 is flushed before every call (50 MB < 126 MB L2),
+                  outside the timed events.
+  e2e ........... the same nine calls through the host-pointer entry point of
+                  the C ABI (what rejit::Regej::MatchAll calls): the text starts
+                  in pinned host memory, every call copies it to the device and
+                  copies the match list back; host wall clock.
+  roofline ...... the dominant kernel (k_dfa_scan): algorithmic bytes
+                  (N + 16*M per launch) / its CUDA-event time, against the
+                  measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline .. the reference's own JIT (oracle/_ref, built from
+                  /root/reference; flag set "noreduce" = fast-forward on,
+                  ff_reduce off — its fastest configuration that returns correct
+                  results on these patterns) on the host cores.
+  N > 1 ......... weak scaling: every rank owns one 50 MB slab of an N*50 MB
+                  text (plus a right halo), resolves it locally and the chain is
+                  stitched with one all-gather per pattern (rejit_b200/sharding.py).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FASTA_N = 5_000_000            # -> 50,000,000 bytes per slab
+HALO = 64
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ref_lib():
+    so = os.path.join(ROOT, "oracle", "_ref", "librejit_ref.so")
+    if not os.path.exists(so):
+        return None
+    L = ctypes.CDLL(so)
+    L.ref_compile.restype = ctypes.c_void_p
+    L.ref_compile.argtypes = [ctypes.c_char_p]
+    L.ref_free.argtypes = [ctypes.c_void_p]
+    L.ref_run_match_all.restype = ctypes.c_int64
+    L.ref_run_match_all.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.ref_run_match_all_mt.restype = ctypes.c_int64
+    L.ref_run_match_all_mt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_size_t]
+    return L
+
+
+def cpu_reference_run(seq, patterns, threads, steps, sample_bytes):
+    """Times the reference JIT (or, if it is not built, the oracle port) over the
+    first `sample_bytes` of the text; returns (GB/s, kind, cores, counts, sample)."""
+    n = min(len(seq), sample_bytes)
+    L = ref_lib()
+    if L is not None:
+        L.ref_set_flagset(1)               # "noreduce": FF on, ff_reduce off
+        handles = [L.ref_compile(p.encode()) for p in patterns]
+        ptr = ctypes.c_void_p(seq.ctypes.data)
+        best, counts = None, []
+        for _ in range(max(1, steps)):
+            t0 = time.perf_counter()
+            counts = []
+            for h in handles:
+                if threads > 1:
+                    counts.append(int(L.ref_run_match_all_mt(h, ptr, n, threads, 7)))
+                else:
+                    counts.append(int(L.ref_run_match_all(h, ptr, n)))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        for h in handles:
+            L.ref_free(h)
+        return len(patterns) * n / best / 1e9, "reference", threads, counts, \
+            "first %d bytes of the 50 MB text x %d patterns, best of %d passes, flags noreduce" % (n, len(patterns), max(1, steps))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import rejit_oracle
+    n = min(n, 2_000_000)
+    data = seq[:n].tobytes()
+    t0 = time.perf_counter()
+    counts = [rejit_oracle.Oracle(p).match_all_count(data) for p in patterns]
+    dt = time.perf_counter() - t0
+    return len(patterns) * n / dt / 1e9, "port", 1, counts, "first %d bytes x %d patterns, one pass of the C oracle" % (n, len(patterns))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from rejit_b200 import workloads as W
+    patterns = W.DNA_PATTERNS
+    config = {"workload": "regex-dna alternation set (9 patterns, sample/regexdna.cc:52-62; BASELINE says 8) "
+                          "over 50 MB synthetic FASTA sequence per GPU, one MatchAll per pattern",
+              "text_bytes_per_gpu": FASTA_N * 10, "patterns": len(patterns),
+              "l2": "flushed before every MatchAll call (256 MB write), outside the timed events",
+              "parallelism": "slab%d" % args.gpus}
+
+    # ---------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        seq = W.fasta_sequence(FASTA_N)
+        threads = os.cpu_count() or 1
+        sample = 50_000_000
+        cpu_reference_run(seq, patterns, threads, 1, sample)        # warm-up pass (JIT, page faults)
+        t0 = time.perf_counter()
+        gbs, kind, cores, counts, what = cpu_reference_run(seq, patterns, threads, max(1, args.steps), sample)
+        wall = time.perf_counter() - t0
+        line = {"impl": "reference", "metric": "GB/s text scanned (MatchAll)", "value": round(gbs, 4), "unit": "GB/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(len(patterns) * min(len(seq), sample) / gbs / 1e6, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": config, "gpu_launches": 0,
+                "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": kind, "sample": what},
+                "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "match_counts": counts, "wall_s": round(wall, 2)}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import numpy as np
+    import rejit_b200 as rj
+    from rejit_b200 import sharding
+    dist = None
+    tdev = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+        tdev = torch.device("cuda", local_rank)
+    if rj.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (rejit_b200 has no CPU fallback)")
+
+    # every rank generates its own slab (+ the first bytes of its right neighbour as halo)
+    seq = W.fasta_sequence(FASTA_N, seed=42 + rank)
+    n_own = len(seq)
+    if world > 1 and rank + 1 < world:
+        nxt = W.fasta_sequence(HALO // 10 + 10, seed=42 + rank + 1)[:HALO]
+        # the neighbour's slab begins with its ALU section
+        buf = np.concatenate([seq, nxt])
+    else:
+        buf = seq
+    slab_lo = rank * n_own
+    regs = [rj.Regej(p) for p in patterns]
+    for r in regs:
+        r.compile()
+    dtext = rj.DeviceText(buf, device=local_rank)
+    total_text = n_own * world
+
+    def run_pattern(r, stats):
+        """One MatchAll over the resident slab; returns (count, pipeline_ms, collective_s)."""
+        if world == 1:
+            cnt = r.match_all_device(dtext, stats=stats)
+            return cnt, stats.total_ms, 0.0
+        ms = [0.0]
+
+        def run(cur, tail):
+            cin = rj.Carry(max(cur - slab_lo, 0), tail - slab_lo if tail != sharding.NO_TAIL and tail >= slab_lo else sharding.NO_TAIL)
+            cout = rj.Carry()
+            # owned starts: [0, n_own) — the last rank also owns the offset n
+            own_end = n_own if rank + 1 < world else (1 << 62)
+            c = r.match_all_device(dtext, length=len(buf), stats=stats, carry_in=cin, carry_out=cout,
+                                   own=(0, own_end), base_offset=slab_lo)
+            ms[0] += stats.total_ms
+            tail_g = cout.tail + slab_lo if cout.tail != sharding.NO_TAIL else sharding.NO_TAIL
+            return c, cout.cur + slab_lo, tail_g
+        t0 = time.perf_counter()
+        cnt, _ = sharding.stitched_count(dist, rank, world, slab_lo, run, device=tdev)
+        coll = time.perf_counter() - t0 - ms[0] / 1e3
+        return cnt, ms[0], max(coll, 0.0)
+
+    def one_step():
+        step_ms, scan_ms, launches, counts, coll_s = 0.0, 0.0, 0, [], 0.0
+        for r in regs:
+            rj.lib().rejit_b200_flush_l2(local_rank)
+            st = rj.Stats()
+            cnt, ms, cs = run_pattern(r, st)
+            step_ms += ms + cs * 1e3
+            scan_ms += st.scan_ms
+            launches += st.launches
+            counts.append(cnt)
+            coll_s += cs
+        return step_ms, scan_ms, launches, counts, coll_s
+
+    for _ in range(max(3, args.warmup)):
+        one_step()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall = time.perf_counter()
+    tot_ms = tot_scan = 0.0
+    launches = 0
+    counts = []
+    for _ in range(args.steps):
+        ms, sc, la, counts, _cs = one_step()
+        tot_ms += ms
+        tot_scan += sc
+        launches += la
+    if dist is not None:
+        import torch
+        t = torch.tensor([tot_ms], dtype=torch.float64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms = float(t.item())
+        dist.barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = tot_ms / args.steps
+    value = len(patterns) * total_text / (ms_per_step / 1e3) / 1e9
+
+    # ---- e2e: host pointer in, match list out (pinned host text, H2D + D2H inside) ----
+    L = rj.lib()
+    pinned = L.rejit_b200_pinned_alloc(n_own)
+    ctypes.memmove(pinned, seq.ctypes.data, n_own)
+    e2e_matches = 0
+
+    def e2e_step():
+        nonlocal e2e_matches
+        e2e_matches = 0
+        err = ctypes.create_string_buffer(256)
+        for r in regs:
+            pairs = ctypes.POINTER(ctypes.c_uint64)()
+            k = L.rejit_b200_match_all_alloc(r._prog, pinned, n_own, ctypes.byref(pairs), None, err, 256)
+            if k < 0:
+                raise SystemExit(err.value.decode())
+            e2e_matches += k
+            L.rejit_b200_free(pairs)
+    e2e_value = None
+    if world == 1:
+        for _ in range(2):
+            e2e_step()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_dt = (time.perf_counter() - t0) / e2e_steps
+        e2e_value = len(patterns) * n_own / e2e_dt / 1e9
+    else:
+        # per-rank host slabs through the multi-process path: same call, each rank its slab
+        for _ in range(2):
+            e2e_step()
+        dist.barrier()
+        t0 = time.perf_counter()
+        e2e_steps = 3
+        for _ in range(e2e_steps):
+            e2e_step()
+        import torch
+        t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = len(patterns) * total_text / float(t.item()) / 1e9
+    L.rejit_b200_pinned_free(pinned)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    n_launch_scan = args.steps * len(patterns)
+    m_total = sum(counts)
+    alg_bytes = len(buf) + 16.0 * m_total / len(patterns)
+    scan_ms_avg = tot_scan / n_launch_scan
+    achieved = alg_bytes / (scan_ms_avg / 1e3) / 1e9
+    cpu = None
+    if world == 1:
+        gbs, kind, cores, ccounts, what = cpu_reference_run(seq, patterns, 1, 2, 50_000_000)
+        cpu = {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": kind, "sample": what,
+               "match_counts_equal": ccounts == counts}
+    line = {"metric": "GB/s text scanned (MatchAll)", "value": round(value, 3), "unit": "GB/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+            "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": len(patterns) * n_own,
+                    "d2h_bytes_per_step": int(16 * e2e_matches + 64 * len(patterns))},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_dfa_scan", "achieved": round(achieved, 2), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "avg_launch_ms": round(scan_ms_avg, 5)},
+            "cpu_baseline": cpu, "clocks": clocks, "match_counts": counts, "wall_s": round(wall, 2)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

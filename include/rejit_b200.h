@@ -141,6 +141,18 @@ int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, con
                                     const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
                                     rejit_b200_stats* stats, char* err, size_t err_length);
 
+/* Slab variant for one-process-per-GPU sharding: only matches that BEGIN in
+ * [own_begin, own_end) of the buffer are reported (own_end > text_length means
+ * "to the end, including the empty match at text_length"); the buffer should
+ * extend past own_end by the pattern's longest match (right halo) and, for
+ * patterns with ^, start one byte before own_begin.  base_offset is added to
+ * every reported offset; the carries are in buffer coordinates.               */
+int64_t rejit_b200_match_all_device_slab(rejit_b200_program* program, int device, const void* d_text,
+                                         size_t text_length, uint64_t own_begin, uint64_t own_end,
+                                         uint64_t base_offset, uint64_t* d_out_pairs, size_t capacity,
+                                         const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
+                                         rejit_b200_stats* stats, char* err, size_t err_length);
+
 void rejit_b200_free(void* ptr);
 
 #ifdef __cplusplus

@@ -1,0 +1,314 @@
+"""rejit_b200 — Python mirror of the rejit interface over the C ABI.
+
+The product is the shared library `librejit_b200.so` (host front end in C++,
+matching on hand-written sm_100a kernels; see include/rejit.h for the C++
+interface and include/rejit_b200.h for the C boundary).  This module is the thin
+ctypes binding the tests and bench.py use: same operation names and argument
+meaning as `rejit::Regej` (/root/reference/include/rejit.h:105-138).
+
+There is no CPU fallback here: if the library is missing, or no CUDA device is
+present, the matching calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librejit_b200.so")
+
+_lib = None
+
+
+class RejitError(RuntimeError):
+    pass
+
+
+class ParserError(RejitError):
+    pass
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("scan_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+                ("launches", ctypes.c_uint32), ("reruns", ctypes.c_uint32),
+                ("candidates", ctypes.c_uint64), ("matches", ctypes.c_uint64),
+                ("strategy", ctypes.c_int32), ("large_path", ctypes.c_int32)]
+
+
+class Carry(ctypes.Structure):
+    _fields_ = [("cur", ctypes.c_uint64), ("tail", ctypes.c_uint64)]
+
+
+# every symbol include/rejit_b200.h declares
+EXPORTED = [
+    "rejit_b200_parse", "rejit_b200_ir_free", "rejit_b200_ir_dump", "rejit_b200_compile",
+    "rejit_b200_program_free", "rejit_b200_program_describe", "rejit_b200_match_all",
+    "rejit_b200_match_all_alloc", "rejit_b200_match_first", "rejit_b200_match_full",
+    "rejit_b200_match_anywhere", "rejit_b200_match_all_multi_gpu", "rejit_b200_device_count",
+    "rejit_b200_device_alloc", "rejit_b200_device_free", "rejit_b200_pinned_alloc",
+    "rejit_b200_pinned_free", "rejit_b200_copy_to_device", "rejit_b200_copy_from_device",
+    "rejit_b200_flush_l2", "rejit_b200_match_all_device", "rejit_b200_match_all_device_slab", "rejit_b200_free",
+]
+
+
+def lib():
+    """Loads librejit_b200.so (built by `python -m rejit_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RejitError("librejit_b200.so is not built: run `python -m rejit_b200.build` "
+                         "(there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, cp, sz = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    L.rejit_b200_parse.argtypes = [cp, sz, ctypes.c_int, ctypes.POINTER(vp), cp, sz]
+    L.rejit_b200_parse.restype = ctypes.c_int
+    L.rejit_b200_ir_free.argtypes = [vp]
+    L.rejit_b200_ir_dump.argtypes = [vp, cp, sz]
+    L.rejit_b200_ir_dump.restype = sz
+    L.rejit_b200_compile.argtypes = [vp, cp, sz]
+    L.rejit_b200_compile.restype = vp
+    L.rejit_b200_program_free.argtypes = [vp]
+    L.rejit_b200_program_describe.argtypes = [vp]
+    L.rejit_b200_program_describe.restype = cp
+    L.rejit_b200_match_all.argtypes = [vp, cp, sz, u64p, sz, cp, sz]
+    L.rejit_b200_match_all.restype = ctypes.c_int64
+    L.rejit_b200_match_all_alloc.argtypes = [vp, vp, sz, ctypes.POINTER(u64p), ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_match_all_alloc.restype = ctypes.c_int64
+    L.rejit_b200_match_first.argtypes = [vp, cp, sz, u64p, cp, sz]
+    L.rejit_b200_match_full.argtypes = [vp, cp, sz, cp, sz]
+    L.rejit_b200_match_anywhere.argtypes = [vp, cp, sz, cp, sz]
+    L.rejit_b200_match_all_multi_gpu.argtypes = [vp, vp, sz, ctypes.c_int, ctypes.POINTER(u64p),
+                                                 ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_match_all_multi_gpu.restype = ctypes.c_int64
+    L.rejit_b200_device_count.restype = ctypes.c_int
+    L.rejit_b200_device_alloc.argtypes = [ctypes.c_int, sz]
+    L.rejit_b200_device_alloc.restype = vp
+    L.rejit_b200_device_free.argtypes = [ctypes.c_int, vp]
+    L.rejit_b200_pinned_alloc.argtypes = [sz]
+    L.rejit_b200_pinned_alloc.restype = vp
+    L.rejit_b200_pinned_free.argtypes = [vp]
+    L.rejit_b200_copy_to_device.argtypes = [ctypes.c_int, vp, vp, sz]
+    L.rejit_b200_copy_from_device.argtypes = [ctypes.c_int, vp, vp, sz]
+    L.rejit_b200_flush_l2.argtypes = [ctypes.c_int]
+    L.rejit_b200_match_all_device.argtypes = [vp, ctypes.c_int, vp, sz, vp, sz, ctypes.POINTER(Carry),
+                                              ctypes.POINTER(Carry), ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_match_all_device.restype = ctypes.c_int64
+    L.rejit_b200_match_all_device_slab.argtypes = [vp, ctypes.c_int, vp, sz, ctypes.c_uint64, ctypes.c_uint64,
+                                                   ctypes.c_uint64, vp, sz, ctypes.POINTER(Carry),
+                                                   ctypes.POINTER(Carry), ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_match_all_device_slab.restype = ctypes.c_int64
+    L.rejit_b200_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return lib().rejit_b200_device_count()
+
+
+def _as_bytes(x) -> bytes:
+    return x.encode("latin-1") if isinstance(x, str) else bytes(x)
+
+
+class DeviceText:
+    """Text resident in HBM (16-byte aligned, padded allocation)."""
+
+    def __init__(self, data=None, device: int = 0, nbytes: Optional[int] = None):
+        L = lib()
+        self.device = device
+        self.nbytes = len(data) if data is not None else int(nbytes)
+        self.ptr = L.rejit_b200_device_alloc(device, max(self.nbytes, 1))
+        if not self.ptr:
+            raise RejitError("device allocation failed (is a CUDA device present?)")
+        if data is not None and self.nbytes:
+            self.upload(data)
+
+    def upload(self, data, pinned_ptr: Optional[int] = None):
+        L = lib()
+        if pinned_ptr is not None:
+            src = pinned_ptr
+        elif hasattr(data, "ctypes"):              # numpy array
+            import numpy as np
+            keep = np.ascontiguousarray(data, dtype=np.uint8)
+            src = ctypes.c_void_p(keep.ctypes.data)
+        else:
+            keep = bytes(data)
+            src = ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p)
+        if L.rejit_b200_copy_to_device(self.device, self.ptr, src, self.nbytes) != 0:
+            raise RejitError("host to device copy failed")
+
+    def free(self):
+        if self.ptr:
+            lib().rejit_b200_device_free(self.device, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Regej:
+    """Mirror of rejit::Regej.  `status` is 0 (RejitSuccess) or -1 (ParserError);
+    like the reference, matching on a Regej that failed to parse returns
+    False / 0 (/root/reference/src/rejit.cc:229-232)."""
+
+    def __init__(self, pattern, parser_opt: bool = True):
+        L = lib()
+        self.pattern = _as_bytes(pattern)
+        self._ir = ctypes.c_void_p()
+        self._prog = None
+        err = ctypes.create_string_buffer(512)
+        self.status = L.rejit_b200_parse(self.pattern, len(self.pattern), 1 if parser_opt else 0,
+                                         ctypes.byref(self._ir), err, len(err))
+        self.status_string = err.value.decode("latin-1")
+
+    # -- plumbing ------------------------------------------------------------
+    def compile(self) -> bool:
+        if self.status != 0:
+            return False
+        if self._prog:
+            return True
+        err = ctypes.create_string_buffer(512)
+        p = lib().rejit_b200_compile(self._ir, err, len(err))
+        if not p:
+            raise RejitError(err.value.decode("latin-1"))
+        self._prog = ctypes.c_void_p(p)
+        return True
+
+    def describe(self) -> str:
+        self.compile()
+        return lib().rejit_b200_program_describe(self._prog).decode("latin-1")
+
+    def ir_dump(self) -> str:
+        n = lib().rejit_b200_ir_dump(self._ir, None, 0)
+        buf = ctypes.create_string_buffer(n + 1)
+        lib().rejit_b200_ir_dump(self._ir, buf, n + 1)
+        return buf.value.decode("latin-1")
+
+    def __del__(self):
+        try:
+            if self._prog:
+                lib().rejit_b200_program_free(self._prog)
+            if self._ir:
+                lib().rejit_b200_ir_free(self._ir)
+        except Exception:
+            pass
+
+    # -- matching --------------------------------------------------------------
+    def match_all(self, text, stats: Optional[Stats] = None, n_gpus: int = 0) -> List[Tuple[int, int]]:
+        if not self.compile():
+            return []
+        L = lib()
+        t = _as_bytes(text)
+        pairs = ctypes.POINTER(ctypes.c_uint64)()
+        err = ctypes.create_string_buffer(512)
+        st = stats if stats is not None else Stats()
+        buf = ctypes.cast(ctypes.c_char_p(t), ctypes.c_void_p)
+        if n_gpus and n_gpus > 0:
+            n = L.rejit_b200_match_all_multi_gpu(self._prog, buf, len(t), n_gpus, ctypes.byref(pairs),
+                                                 ctypes.byref(st), err, len(err))
+        else:
+            n = L.rejit_b200_match_all_alloc(self._prog, buf, len(t), ctypes.byref(pairs),
+                                             ctypes.byref(st), err, len(err))
+        if n < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        out = [(pairs[2 * i], pairs[2 * i + 1]) for i in range(n)]
+        L.rejit_b200_free(pairs)
+        return out
+
+    def match_all_array(self, data, stats: Optional[Stats] = None, n_gpus: int = 0):
+        """MatchAll over a numpy uint8 array / bytes; returns an (n, 2) uint64 array."""
+        import numpy as np
+        if not self.compile():
+            return np.zeros((0, 2), dtype=np.uint64)
+        L = lib()
+        arr = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, dtype=np.uint8)
+        pairs = ctypes.POINTER(ctypes.c_uint64)()
+        err = ctypes.create_string_buffer(512)
+        st = stats if stats is not None else Stats()
+        ptr = ctypes.c_void_p(arr.ctypes.data)
+        if n_gpus and n_gpus > 0:
+            n = L.rejit_b200_match_all_multi_gpu(self._prog, ptr, arr.size, n_gpus, ctypes.byref(pairs),
+                                                 ctypes.byref(st), err, len(err))
+        else:
+            n = L.rejit_b200_match_all_alloc(self._prog, ptr, arr.size, ctypes.byref(pairs), ctypes.byref(st),
+                                             err, len(err))
+        if n < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        out = np.ctypeslib.as_array(pairs, shape=(max(int(n), 1), 2))[:int(n)].copy() if n else np.zeros((0, 2), dtype=np.uint64)
+        L.rejit_b200_free(pairs)
+        return out
+
+    def match_all_parallel(self, text, n_gpus: int) -> List[Tuple[int, int]]:
+        return self.match_all(text, n_gpus=n_gpus)
+
+    def match_all_count(self, text) -> int:
+        return len(self.match_all(text))
+
+    def match_first(self, text) -> Optional[Tuple[int, int]]:
+        if not self.compile():
+            return None
+        t = _as_bytes(text)
+        pair = (ctypes.c_uint64 * 2)()
+        err = ctypes.create_string_buffer(512)
+        r = lib().rejit_b200_match_first(self._prog, t, len(t), pair, err, len(err))
+        if r < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        return (pair[0], pair[1]) if r == 1 else None
+
+    def match_full(self, text) -> bool:
+        if not self.compile():
+            return False
+        t = _as_bytes(text)
+        err = ctypes.create_string_buffer(512)
+        r = lib().rejit_b200_match_full(self._prog, t, len(t), err, len(err))
+        if r < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        return r == 1
+
+    def match_anywhere(self, text) -> bool:
+        if not self.compile():
+            return False
+        t = _as_bytes(text)
+        err = ctypes.create_string_buffer(512)
+        r = lib().rejit_b200_match_anywhere(self._prog, t, len(t), err, len(err))
+        if r < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        return r == 1
+
+    # -- device-resident text --------------------------------------------------
+    def match_all_device(self, dtext: DeviceText, length: Optional[int] = None, out_ptr=None,
+                         capacity: int = 0, stats: Optional[Stats] = None,
+                         carry_in: Optional[Carry] = None, carry_out: Optional[Carry] = None,
+                         own: Optional[Tuple[int, int]] = None, base_offset: int = 0) -> int:
+        if not self.compile():
+            return 0
+        err = ctypes.create_string_buffer(512)
+        if own is not None:
+            n = lib().rejit_b200_match_all_device_slab(
+                self._prog, dtext.device, dtext.ptr, dtext.nbytes if length is None else length,
+                own[0], own[1], base_offset, out_ptr, capacity,
+                ctypes.byref(carry_in) if carry_in is not None else None,
+                ctypes.byref(carry_out) if carry_out is not None else None,
+                ctypes.byref(stats) if stats is not None else None, err, len(err))
+            if n < 0:
+                raise RejitError(err.value.decode("latin-1"))
+            return int(n)
+        n = lib().rejit_b200_match_all_device(
+            self._prog, dtext.device, dtext.ptr, dtext.nbytes if length is None else length,
+            out_ptr, capacity,
+            ctypes.byref(carry_in) if carry_in is not None else None,
+            ctypes.byref(carry_out) if carry_out is not None else None,
+            ctypes.byref(stats) if stats is not None else None, err, len(err))
+        if n < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        return int(n)
+
+
+def match_all(pattern, text):
+    return Regej(pattern).match_all(text)

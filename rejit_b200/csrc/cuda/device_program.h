@@ -209,6 +209,141 @@ RJ_HD bool ChainTake(ChainState* st, uint64_t b, uint64_t e) {
   return true;
 }
 
+
+// ---------------------------------------------------------------------------
+// Exact selection for patterns whose start can be re-entered by a running
+// thread (first[ctx] & follow[ctx][k] != 0 for some k: "x*y", ".{,4}t", ...).
+//
+// For those patterns the reference's single-pass matcher is NOT equivalent to
+// "longest end per start + greedy chain": when a match [s,e) is recorded at
+// offset e, the thread born at e has already lost, during the control-edge pass
+// at e, every state that was occupied by a thread born inside (s,e) — and those
+// occupants are then wiped by ClearStates (codegen-x64.cc:401-466, 951-987,
+// 1075-1097), leaving the state empty.  Example (verified against the
+// reference): ".{,4}t" on "agccttgaact" -> [0,5) [6,11); the match [5,6) is
+// lost.  To stay bit-exact we replay the reference's label semantics over each
+// cluster of candidates, in position form:
+//     lab[k]  = start offset of the oldest thread that has just consumed a byte
+//               through position k (older start wins on collision)
+//     at offset p:  blocked = U follow[ctx][k] over live k   (before any wipe)
+//                   exit label = min lab[k] over live k in accept[ctx]
+//                                (else p itself when the empty match is possible)
+//                   record [label, p), wipe every lab in (label, p)
+//                   step: survivors propagate through follow & byte_mask;
+//                         the newborn thread p enters first[ctx] & ~blocked
+// A cluster starts at a candidate that no earlier candidate reaches
+// (max earlier end < begin, strictly) and runs to the largest end in it; no
+// match can begin outside candidate starts, because every recorded match is a
+// genuine NFA path.
+struct FaithfulScratch {
+  uint64_t* lab;       // [n_pos]
+  uint64_t* nlab;      // [n_pos]
+  uint32_t* act;       // [W]
+  uint32_t* nact;      // [W]
+  uint32_t* blocked;   // [W]
+};
+
+RJ_HD int BitScan(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs(x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+
+// Candidates [i0, i1) (sorted by begin, equal begins adjacent) form one cluster.
+// Writes take[j] (0/1) and fin_end[j] for j in [i0, i1).
+RJ_HD void FaithfulSegment(const NfaTables& t, const uint8_t* text, uint64_t n, const uint64_t* b,
+                           const uint64_t* e, uint64_t i0, uint64_t i1, FaithfulScratch sc,
+                           uint32_t* take, uint64_t* fin_end) {
+  const int W = t.words, P = t.n_pos;
+  uint64_t* lab = sc.lab;
+  uint64_t* nlab = sc.nlab;
+  uint32_t* act = sc.act;
+  uint32_t* nact = sc.nact;
+  for (int i = 0; i < W; ++i) act[i] = 0;
+  uint64_t p1 = 0;
+  for (uint64_t j = i0; j < i1; ++j) { take[j] = 0; fin_end[j] = e[j]; if (e[j] > p1) p1 = e[j]; }
+  int64_t last = -1;                       // index of the most recent recorded match
+  for (uint64_t p = b[i0];; ++p) {
+    const int ctx = t.has_anchor ? ContextAt(text, n, p) : 0;
+    const uint32_t* fol = t.follow + (uint64_t)ctx * P * W;
+    const uint32_t* acc = t.accept + ctx * W;
+    const uint32_t* fst = t.first + ctx * W;
+    uint64_t exitlab = kNoMatch;
+    for (int i = 0; i < W; ++i) sc.blocked[i] = 0;
+    for (int i = 0; i < W; ++i) {
+      uint32_t m = act[i];
+      while (m) {
+        int k = i * 32 + BitScan(m);
+        m &= m - 1;
+        const uint32_t* row = fol + (uint64_t)k * W;
+        for (int q = 0; q < W; ++q) sc.blocked[q] |= row[q];
+        if ((acc[i] >> (k & 31)) & 1u) { if (lab[k] < exitlab) exitlab = lab[k]; }
+      }
+    }
+    if (exitlab == kNoMatch && t.accept_empty[ctx]) exitlab = p;
+    if (exitlab != kNoMatch) {
+      // MatchAllAppendFilter: drop recorded matches that begin at or after the new one
+      while (last >= (int64_t)i0 && b[last] >= exitlab) {
+        take[last] = 0;
+        int64_t q = last - 1;
+        while (q >= (int64_t)i0 && !take[q]) --q;
+        last = q;
+      }
+      bool drop = (exitlab == p) && last >= (int64_t)i0 && fin_end[last] == p;
+      if (!drop) {
+        // locate the candidate whose begin is the label
+        uint64_t lo = i0, hi = i1;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (b[mid] < exitlab) lo = mid + 1; else hi = mid; }
+        if (lo < i1 && b[lo] == exitlab) { take[lo] = 1; fin_end[lo] = p; last = (int64_t)lo; }
+      }
+      for (int i = 0; i < W; ++i) {
+        uint32_t m = act[i];
+        while (m) {
+          int bit = BitScan(m);
+          m &= m - 1;
+          int k = i * 32 + bit;
+          if (lab[k] > exitlab && lab[k] < p) act[i] &= ~(1u << bit);
+        }
+      }
+    }
+    if (p >= p1 || p >= n) break;
+    const uint32_t* bm = t.byte_mask + (uint64_t)text[p] * W;
+    for (int i = 0; i < W; ++i) nact[i] = 0;
+    for (int i = 0; i < W; ++i) {
+      uint32_t m = act[i];
+      while (m) {
+        int k = i * 32 + BitScan(m);
+        m &= m - 1;
+        const uint32_t* row = fol + (uint64_t)k * W;
+        const uint64_t lk = lab[k];
+        for (int q = 0; q < W; ++q) {
+          uint32_t mm = row[q] & bm[q];
+          while (mm) {
+            int bit = BitScan(mm);
+            mm &= mm - 1;
+            int j = q * 32 + bit;
+            if (!((nact[q] >> bit) & 1u)) { nact[q] |= 1u << bit; nlab[j] = lk; }
+            else if (lk < nlab[j]) nlab[j] = lk;
+          }
+        }
+      }
+    }
+    for (int q = 0; q < W; ++q) {
+      uint32_t mm = fst[q] & ~sc.blocked[q] & bm[q];
+      while (mm) {
+        int bit = BitScan(mm);
+        mm &= mm - 1;
+        int j = q * 32 + bit;
+        if (!((nact[q] >> bit) & 1u)) { nact[q] |= 1u << bit; nlab[j] = p; }
+      }
+    }
+    uint64_t* tl = lab; lab = nlab; nlab = tl;
+    uint32_t* ta = act; act = nact; nact = ta;
+  }
+}
+
 }  // namespace rejit_b200
 
 #endif  // REJIT_B200_CUDA_DEVICE_PROGRAM_H_

@@ -289,9 +289,33 @@ __global__ void k_match_full(const uint8_t* __restrict__ text, uint64_t n, NfaTa
 // Resolve, small path: one CTA sorts the candidates by begin (bitonic, shared
 // memory) and walks the chain.
 // ===========================================================================
+struct FaithfulArgs {               // only used for re-entrant patterns
+  int enabled;
+  NfaTables nfa;
+  const uint8_t* text;
+  uint64_t n;
+  uint8_t* scratch;                  // per-walker label scratch
+  uint64_t scratch_stride;           // bytes per walker
+  uint32_t* take;                    // [candidates]
+  uint64_t* fin_end;                 // [candidates]
+};
+
+__device__ __forceinline__ FaithfulScratch WalkerScratch(const FaithfulArgs& fa, uint64_t walker) {
+  uint8_t* base = fa.scratch + walker * fa.scratch_stride;
+  const uint64_t P = fa.nfa.n_pos > 0 ? fa.nfa.n_pos : 1;
+  const uint64_t W = fa.nfa.words;
+  FaithfulScratch sc;
+  sc.lab = reinterpret_cast<uint64_t*>(base);
+  sc.nlab = sc.lab + P;
+  sc.act = reinterpret_cast<uint32_t*>(sc.nlab + P);
+  sc.nact = sc.act + W;
+  sc.blocked = sc.nact + W;
+  return sc;
+}
+
 __global__ void __launch_bounds__(1024)
 k_resolve_small(CandBuf cand, Carry carry_in, uint64_t base_offset, uint64_t* __restrict__ out_pairs,
-                uint64_t out_cap, PipelineStatus* status) {
+                uint64_t out_cap, FaithfulArgs fa, PipelineStatus* status) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* kb = reinterpret_cast<uint64_t*>(smem_raw);
   unsigned long long m = *cand.count;
@@ -329,7 +353,32 @@ k_resolve_small(CandBuf cand, Carry carry_in, uint64_t base_offset, uint64_t* __
       __syncthreads();
     }
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && fa.enabled) {
+    // re-entrant pattern: replay the reference's thread labels cluster by cluster
+    FaithfulScratch sc = WalkerScratch(fa, 0);
+    int i = 0;
+    while (i < count) {
+      uint64_t reach = ke[i];
+      int j = i + 1;
+      while (j < count && !(reach < kb[j])) { reach = reach > ke[j] ? reach : ke[j]; ++j; }
+      FaithfulSegment(fa.nfa, fa.text, fa.n, kb, ke, (uint64_t)i, (uint64_t)j, sc, fa.take, fa.fin_end);
+      i = j;
+    }
+    unsigned long long taken = 0;
+    uint64_t last_end = carry_in.cur;
+    for (int q = 0; q < count; ++q) {
+      if (!fa.take[q]) continue;
+      if (taken < out_cap) {
+        out_pairs[2 * taken] = kb[q] + base_offset;
+        out_pairs[2 * taken + 1] = fa.fin_end[q] + base_offset;
+      }
+      last_end = fa.fin_end[q] > kb[q] ? fa.fin_end[q] : kb[q] + 1;
+      ++taken;
+    }
+    status->n_matches = taken;
+    status->carry_cur = last_end;
+    status->carry_tail = kNoMatch;
+  } else if (threadIdx.x == 0) {
     ChainState st{carry_in.cur, carry_in.tail};
     unsigned long long taken = 0;
     uint64_t prev_b = ~0ull;
@@ -385,6 +434,22 @@ __global__ void k_segment_chain(const uint64_t* __restrict__ b, const uint64_t* 
       prev_b = b[j];
       take[j] = ChainTake(&st, b[j], e[j]) ? 1u : 0u;
     }
+  }
+}
+
+// Large path for re-entrant patterns: one walker per cluster head (no earlier
+// candidate reaches the head's begin, strictly).
+__global__ void k_segment_faithful(const uint64_t* __restrict__ b, const uint64_t* __restrict__ e,
+                                   const uint64_t* __restrict__ reach, uint64_t m, FaithfulArgs fa) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  FaithfulScratch sc = WalkerScratch(fa, tid);
+  for (uint64_t i = tid; i < m; i += nthreads) {
+    bool head = (i == 0) || (reach[i] < b[i]);
+    if (!head) continue;
+    uint64_t j = i + 1;
+    while (j < m && !(reach[j] < b[j])) ++j;
+    FaithfulSegment(fa.nfa, fa.text, fa.n, b, e, i, j, sc, fa.take, fa.fin_end);
   }
 }
 
@@ -481,6 +546,7 @@ class DeviceContext {
   Buffer counters;                    // [0]=cand count [1]=hit count [2]=last_any [3]=last_nonempty
   Buffer status;
   Buffer sorted_b, sorted_e, reach, take, wide, slot, cub_tmp;
+  Buffer fscratch, fin_end;           // label scratch / final ends for re-entrant patterns
   Buffer flush;
   uint64_t cand_cap = 0, hit_cap = 0;
   PipelineStatus* h_status = nullptr; // pinned
@@ -673,8 +739,15 @@ struct Slab {                 // how a launch maps local offsets to the whole te
   uint64_t base_offset;       // added to every reported offset
 };
 
+constexpr int kFaithfulWalkers = 2048;
+
+uint64_t FaithfulStride(const NfaTables& nfa) {
+  uint64_t P = nfa.n_pos > 0 ? nfa.n_pos : 1;
+  return ((2 * P * 8 + 3 * (uint64_t)nfa.words * 4) + 15) & ~15ull;
+}
+
 bool RunLargeResolve(DeviceContext* c, uint64_t m, const Carry& carry_in, uint64_t base_offset,
-                     uint64_t* d_out, uint64_t out_cap, RunStats* stats, std::string* error) {
+                     uint64_t* d_out, uint64_t out_cap, FaithfulArgs fa, RunStats* stats, std::string* error) {
   cudaStream_t s = c->stream;
   if (!c->sorted_b.Reserve(m * 8, error) || !c->sorted_e.Reserve(m * 8, error) ||
       !c->reach.Reserve(m * 8, error) || !c->take.Reserve(m * 4, error) ||
@@ -692,16 +765,28 @@ bool RunLargeResolve(DeviceContext* c, uint64_t m, const Carry& carry_in, uint64
   RJ_TRY(cub::DeviceScan::ExclusiveScan(c->cub_tmp.p, tmp, c->sorted_e.as<uint64_t>(), c->reach.as<uint64_t>(),
                                         MaxOp(), (uint64_t)carry_in.cur, (int64_t)m, s));
   int blocks = (int)std::min<uint64_t>((m + 255) / 256, (uint64_t)c->sm_count * 8);
-  k_segment_chain<<<blocks, 256, 0, s>>>(c->sorted_b.as<uint64_t>(), c->sorted_e.as<uint64_t>(),
-                                         c->reach.as<uint64_t>(), m, carry_in, c->take.as<uint32_t>());
+  const uint64_t* final_e = c->sorted_e.as<uint64_t>();
+  if (fa.enabled) {
+    if (!c->fin_end.Reserve(m * 8, error)) return false;
+    if (!c->fscratch.Reserve(fa.scratch_stride * kFaithfulWalkers, error)) return false;
+    fa.scratch = c->fscratch.as<uint8_t>();
+    fa.take = c->take.as<uint32_t>();
+    fa.fin_end = c->fin_end.as<uint64_t>();
+    final_e = fa.fin_end;
+    k_segment_faithful<<<kFaithfulWalkers / 64, 64, 0, s>>>(c->sorted_b.as<uint64_t>(), c->sorted_e.as<uint64_t>(),
+                                                            c->reach.as<uint64_t>(), m, fa);
+  } else {
+    k_segment_chain<<<blocks, 256, 0, s>>>(c->sorted_b.as<uint64_t>(), c->sorted_e.as<uint64_t>(),
+                                           c->reach.as<uint64_t>(), m, carry_in, c->take.as<uint32_t>());
+  }
   k_widen_flags<<<blocks, 256, 0, s>>>(c->take.as<uint32_t>(), c->wide.as<uint64_t>(), m);
   RJ_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->wide.as<uint64_t>(), c->slot.as<uint64_t>(), (int64_t)m, s));
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   RJ_TRY(cudaMemsetAsync(ctr + 2, 0, 16, s));
-  k_scatter_matches<<<blocks, 256, 0, s>>>(c->sorted_b.as<uint64_t>(), c->sorted_e.as<uint64_t>(),
+  k_scatter_matches<<<blocks, 256, 0, s>>>(c->sorted_b.as<uint64_t>(), final_e,
                                            c->take.as<uint32_t>(), c->slot.as<uint64_t>(), m, base_offset,
                                            d_out, out_cap, ctr + 2, ctr + 3);
-  k_finish_large<<<1, 32, 0, s>>>(c->sorted_b.as<uint64_t>(), c->sorted_e.as<uint64_t>(), c->take.as<uint32_t>(),
+  k_finish_large<<<1, 32, 0, s>>>(c->sorted_b.as<uint64_t>(), final_e, c->take.as<uint32_t>(),
                                   c->slot.as<uint64_t>(), m, carry_in, ctr + 2, ctr + 3,
                                   c->status.as<PipelineStatus>());
   if (stats) { stats->launches += 9; stats->large_path = 1; }
@@ -779,8 +864,21 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       }
     }
     if (stats && ca.strategy != ScanStrategy::LiteralWindow) cudaEventRecord(c->ev[1], s);
+    FaithfulArgs fa{};
+    fa.enabled = ca.reentrant ? 1 : 0;
+    if (fa.enabled) {
+      fa.nfa = dp->nfa;
+      fa.text = d_text;
+      fa.n = n;
+      fa.scratch_stride = FaithfulStride(dp->nfa);
+      if (!c->fscratch.Reserve(fa.scratch_stride * kFaithfulWalkers, error) ||
+          !c->take.Reserve(kSmallResolveMax * 4, error) || !c->fin_end.Reserve(kSmallResolveMax * 8, error)) return false;
+      fa.scratch = c->fscratch.as<uint8_t>();
+      fa.take = c->take.as<uint32_t>();
+      fa.fin_end = c->fin_end.as<uint64_t>();
+    }
     RJ_TRY(cudaFuncSetAttribute(k_resolve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallResolveMax * 16));
-    k_resolve_small<<<1, 1024, kSmallResolveMax * 16, s>>>(cand, carry_in, slab.base_offset, outp, ocap, d_status);
+    k_resolve_small<<<1, 1024, kSmallResolveMax * 16, s>>>(cand, carry_in, slab.base_offset, outp, ocap, fa, d_status);
     if (stats) stats->launches += 1;
     RJ_TRY(cudaGetLastError());
     RJ_TRY(cudaMemcpyAsync(c->h_status, d_status, sizeof(PipelineStatus), cudaMemcpyDeviceToHost, s));
@@ -807,7 +905,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     }
     if (st.need_large) {
       outp = d_out ? d_out : c->out_pairs.as<uint64_t>();
-      if (!RunLargeResolve(c, st.n_candidates, carry_in, slab.base_offset, outp, ocap, stats, error)) return false;
+      if (!RunLargeResolve(c, st.n_candidates, carry_in, slab.base_offset, outp, ocap, fa, stats, error)) return false;
       RJ_TRY(cudaMemcpyAsync(c->h_status, d_status, sizeof(PipelineStatus), cudaMemcpyDeviceToHost, s));
       RJ_TRY(cudaStreamSynchronize(s));
       unsigned long long keep = st.n_candidates;
@@ -833,13 +931,19 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
 }  // namespace
 
 int64_t MatchAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_t n, uint64_t* d_out,
-                       uint64_t out_cap, const Carry& in, Carry* out, RunStats* stats, std::string* error) {
+                       uint64_t out_cap, const Carry& in, Carry* out, RunStats* stats, std::string* error,
+                       const SlabView* own) {
   DeviceContext* c = ContextFor(device, error);
   if (!c) return -1;
   DeviceProgram* dp = prog->OnDevice(device, error);
   if (!dp) return -1;
   std::lock_guard<std::mutex> lk(c->mu);
   Slab slab{{0, n + 1}, 0};
+  if (own) {
+    slab.own.own_begin = std::min<uint64_t>(own->own_begin, n + 1);
+    slab.own.own_end = std::min<uint64_t>(own->own_end, n + 1);
+    slab.base_offset = own->base_offset;
+  }
   PipelineStatus st;
   if (!RunPipeline(c, prog, dp, d_text, n, slab, in, d_out, out_cap, &st, stats, error)) return -1;
   if (out) { out->cur = st.carry_cur; out->tail = st.carry_tail; }
@@ -911,6 +1015,8 @@ int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int
   if (!CudaOk(error)) return -1;
   int g = std::max(1, std::min(n_gpus, DeviceCount()));
   if (n < (uint64_t)g * 4096) g = 1;
+  // the label replay of re-entrant patterns cannot be cut at a slab edge
+  if (prog->automaton().reentrant) g = 1;
   std::vector<std::vector<uint64_t>> part(g);
   std::vector<Carry> carry_out(g);
   std::vector<std::string> errs(g);
@@ -948,7 +1054,6 @@ int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int
       if (stats) stats->reruns += 1;
     }
     running = carry_out[i];
-    if (running.cur < hi && i + 1 < g) running.cur = std::max(running.cur, (uint64_t)0);
   }
   size_t total = 0;
   for (auto& p : part) total += p.size();

@@ -59,9 +59,17 @@ void FlushL2(int device);                              // writes a buffer larger
 // MatchAll over text resident in device memory (16-byte aligned).  Writes up to
 // out_cap (begin,end) offset pairs to d_out (device memory, may be null when
 // out_cap == 0) and returns the number of matches, or -1 with *error set.
+// `own` (optional) restricts the reported matches to starts in
+// [own_begin, own_end) of the buffer (a slab with halos); base_offset is added
+// to every reported offset.  Carries are in buffer coordinates.
+struct SlabView {
+  uint64_t own_begin = 0;
+  uint64_t own_end = ~0ull;      // clamped to n + 1
+  uint64_t base_offset = 0;
+};
 int64_t MatchAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_t n,
                        uint64_t* d_out, uint64_t out_cap, const Carry& in, Carry* out,
-                       RunStats* stats, std::string* error);
+                       RunStats* stats, std::string* error, const SlabView* own = nullptr);
 
 // MatchAll over host text: H2D copy, device pipeline, D2H of the match list.
 // *pairs is malloc'ed by the callee (count*2 uint64), caller frees.

@@ -399,6 +399,14 @@ bool BuildAutomaton(const LoweredRegexp& lr, CompiledAutomaton* out, std::string
       out->start_ok[ctx][b] = t.any() ? 1 : 0;
     }
 
+  out->reentrant = false;
+  for (int ctx = 0; ctx < kCtxCount; ++ctx)
+    for (int k = 0; k < a.n_pos; ++k) {
+      BitSet t = a.follow[ctx][k];
+      t.and_with(a.first[ctx]);
+      if (t.any()) out->reentrant = true;
+    }
+
   // ---- strategy ---------------------------------------------------------
   std::ostringstream ds;
   out->strategy = ScanStrategy::Generic;
@@ -424,7 +432,7 @@ bool BuildAutomaton(const LoweredRegexp& lr, CompiledAutomaton* out, std::string
   }
   ds << "; " << a.n_pos << " positions, len [" << a.min_len << ","
      << (a.max_len == kInfLen ? std::string("inf") : std::to_string(a.max_len)) << "]"
-     << (a.has_anchor ? ", anchors" : "");
+     << (a.has_anchor ? ", anchors" : "") << (out->reentrant ? ", reentrant start" : "");
   out->describe = ds.str();
   return true;
 }

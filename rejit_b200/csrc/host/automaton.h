@@ -76,6 +76,10 @@ struct CompiledAutomaton {
   uint32_t window_lo = 0, window_hi = 0;     // LiteralWindow: start in [hit-hi, hit-lo]
   ScanDfa dfa;                               // DfaFixed
   std::array<uint8_t, 256> start_ok[kCtxCount];  // Generic: byte can begin a match
+  // A running thread can re-enter positions of the start set
+  // (first[ctx] & follow[ctx][k] != 0): selection must replay the reference's
+  // thread labels (device_program.h: FaithfulSegment) instead of chaining E(s).
+  bool reentrant = false;
   std::string describe;                      // one-line human summary
 };
 

@@ -297,6 +297,27 @@ int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, con
   return r;
 }
 
+int64_t rejit_b200_match_all_device_slab(rejit_b200_program* program, int device, const void* d_text,
+                                         size_t text_length, uint64_t own_begin, uint64_t own_end,
+                                         uint64_t base_offset, uint64_t* d_out_pairs, size_t capacity,
+                                         const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
+                                         rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  Carry in, out;
+  if (carry_in) { in.cur = carry_in->cur; in.tail = carry_in->tail; }
+  SlabView view;
+  view.own_begin = own_begin;
+  view.own_end = own_end;
+  view.base_offset = base_offset;
+  RunStats rs;
+  int64_t r = MatchAllDevice(device, program->prog, static_cast<const uint8_t*>(d_text), text_length,
+                             d_out_pairs, capacity, in, &out, stats ? &rs : nullptr, &error, &view);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  if (carry_out) { carry_out->cur = out.cur; carry_out->tail = out.tail; }
+  FillStats(rs, stats);
+  return r;
+}
+
 void rejit_b200_free(void* ptr) { free(ptr); }
 
 }  // extern "C"

@@ -1,0 +1,22 @@
+#!/bin/bash
+# Runs on the GPU box under gpurun: GPU test tier, one bench line, ncu launch
+# list + one full capture of the dominant kernel.  Everything lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
+nproc >> gpurun_out/gpu_info.txt
+python __graft_entry__.py > gpurun_out/build.log 2>&1
+echo "== smoke" ; timeout 600 python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -5
+echo "== pytest gpu" ; timeout 2400 python -m pytest tests -m gpu -q -x --timeout 1500 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
+echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench_ours.json
+tail -5 gpurun_out/bench.err
+echo "== bench reference" ; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>> gpurun_out/bench.err | tee gpurun_out/bench_reference.json
+if [ "${RJ_PROFILE:-1}" = "1" ]; then
+echo "== ncu launches"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_bench.log 2>&1
+tail -3 gpurun_out/ncu_bench.log
+echo "== ncu full dfa"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dfa_scan -s 9 -c 2 -o gpurun_out/prof_dfa -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log
+fi
+ls -la gpurun_out

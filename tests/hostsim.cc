@@ -145,6 +145,30 @@ void ResolveSegments(Cands cands, ChainState carry, Cands* out) {
   for (size_t i = 0; i < m; ++i) if (take[i]) out->push_back(cands[i]);
 }
 
+// clusters separated where no earlier candidate reaches the next begin (strictly),
+// each replayed with the reference's thread labels (FaithfulSegment)
+void ResolveFaithful(const Compiled& c, const uint8_t* text, uint64_t n, Cands cands, Cands* out) {
+  std::sort(cands.begin(), cands.end());
+  size_t m = cands.size();
+  if (!m) return;
+  std::vector<uint64_t> b(m), e(m), fin(m);
+  std::vector<uint32_t> take(m, 0);
+  for (size_t i = 0; i < m; ++i) { b[i] = cands[i].first; e[i] = cands[i].second; }
+  int P = std::max(c.nfa.n_pos, 1), W = c.nfa.words;
+  std::vector<uint64_t> lab(P), nlab(P);
+  std::vector<uint32_t> act(W), nact(W), blocked(W);
+  FaithfulScratch sc{lab.data(), nlab.data(), act.data(), nact.data(), blocked.data()};
+  size_t i = 0;
+  while (i < m) {
+    uint64_t reach = e[i];
+    size_t j = i + 1;
+    while (j < m && !(reach < b[j])) { reach = std::max(reach, e[j]); ++j; }
+    FaithfulSegment(c.nfa, text, n, b.data(), e.data(), i, j, sc, take.data(), fin.data());
+    i = j;
+  }
+  for (size_t k = 0; k < m; ++k) if (take[k]) out->push_back({b[k], fin[k]});
+}
+
 }  // namespace
 
 extern "C" {
@@ -173,9 +197,17 @@ int64_t hostsim_match_all(const char* pattern, size_t plen, int parser_opt, cons
   }
   Cands a, b;
   ChainState st{0, kNoMatch};
-  ResolveSequential(cands, st, &a, nullptr);
-  ResolveSegments(cands, st, &b);
-  if (a != b) return -2;
+  if (c.ca.reentrant) {
+    ResolveFaithful(c, text, n, cands, &a);
+  } else {
+    ResolveSequential(cands, st, &a, nullptr);
+    ResolveSegments(cands, st, &b);
+    if (a != b) return -2;
+    // the label replay must agree with the chain wherever the chain is exact
+    Cands f;
+    ResolveFaithful(c, text, n, cands, &f);
+    if (f != a) return -4;
+  }
   for (size_t i = 0; i < a.size() && i < cap; ++i) {
     out_pairs[2 * i] = a[i].first;
     out_pairs[2 * i + 1] = a[i].second;

@@ -1,0 +1,206 @@
+"""GPU tier (`pytest -m gpu`): the parity tests proper.  Every call goes through
+the C ABI of librejit_b200.so (include/rejit_b200.h) and runs the sm_100a
+kernels; expectations come from the oracle (oracle/) and from the golden
+fixtures produced by the compiled reference (tests/golden/).  Bit-exact:
+identical (begin, end) offset lists."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+import fuzzgen
+import rejit_oracle as O
+from conftest import expand_table_row
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rj():
+    import __graft_entry__ as entry
+    entry.build()
+    import rejit_b200
+    if rejit_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu tier cannot run (and there is no CPU fallback)")
+    return rejit_b200
+
+
+def test_golden_offsets(rj, golden_vectors):
+    for v in golden_vectors:
+        t = v["text"].encode("latin-1")
+        r = rj.Regej(v["re"])
+        assert r.match_all(t) == [tuple(m) for m in v["all"]], (v["re"], v["note"], r.describe())
+        assert r.match_full(t) == v["full"], (v["re"], v["note"])
+        assert r.match_anywhere(t) == v["anywhere"], (v["re"], v["note"])
+
+
+def test_reference_test_table(rj, ref_table):
+    """The reference's 282 checks with its 33-alignment sweep (tools/tests/test.cc)."""
+    n = 0
+    for row in ref_table:
+        pat, checks = expand_table_row(row)
+        r = rj.Regej(pat)
+        for mt, text, expected, start, end in checks:
+            t = text.encode("latin-1")
+            n += 1
+            if mt == "full":
+                assert r.match_full(t) == bool(expected), (row["line"], pat)
+            elif mt == "anywhere":
+                assert r.match_anywhere(t) == bool(expected), (row["line"], pat, text)
+            elif mt == "all":
+                assert r.match_all_count(t) == expected, (row["line"], pat, text)
+            else:
+                f = r.match_first(t)
+                assert (f is not None) == bool(expected), (row["line"], pat, text)
+                if expected and start is not None:
+                    assert f == (start, end), (row["line"], pat, text)
+    assert n > 3000
+
+
+def test_fuzz_vs_oracle(rj):
+    r = random.Random(2026)
+    checked = 0
+    for _ in range(500):
+        pat, alpha = fuzzgen.rand_pattern(r)
+        try:
+            o = O.Oracle(pat)
+        except O.ParserError:
+            assert rj.Regej(pat).status == -1, pat
+            continue
+        g = rj.Regej(pat)
+        assert g.status == 0, pat
+        for n in (r.randint(0, 40), r.randint(500, 3000)):
+            t = fuzzgen.rand_text(r, alpha, n)
+            assert g.match_all(t) == o.match_all(t), (pat, t, g.describe())
+            assert g.match_full(t) == o.match_full(t), (pat, t)
+            checked += 1
+    assert checked > 600
+
+
+def test_edges_of_pieces_and_streams(rj):
+    """Matches that straddle the 16-byte lane, 512-byte piece / sub-stream and
+    text-end boundaries of the scan kernels."""
+    for pat in ("needle", "ne", "n", "agggtaaa|tttaccct", "ab[cd]e", "(xy|z)+w", "needle(s|x)?"):
+        o = O.Oracle(pat)
+        g = rj.Regej(pat)
+        unit = {"needle": b"needle", "ne": b"ne", "n": b"n", "agggtaaa|tttaccct": b"tttaccct",
+                "ab[cd]e": b"abde", "(xy|z)+w": b"xyzxyw", "needle(s|x)?": b"needles"}[pat]
+        for total in (0, 1, 5, 15, 16, 17, 511, 512, 513, 1024, 1030, 4099):
+            for at in (0, 1, 9, 15, 16, 500, 505, 508, 511, 512, 1017, total - len(unit), total - 1):
+                if at < 0 or at + len(unit) > total:
+                    continue
+                t = bytearray(b"." * total)
+                t[at:at + len(unit)] = unit
+                t = bytes(t)
+                assert g.match_all(t) == o.match_all(t), (pat, total, at)
+
+
+def test_empty_and_tiny_texts(rj):
+    for pat in ("a", "a*", "^", "$", "^$", "abc", "(^|$|[x])", "x?"):
+        for t in (b"", b"a", b"\n", b"x", b"ab"):
+            assert rj.Regej(pat).match_all(t) == O.Oracle(pat).match_all(t), (pat, t)
+            assert rj.Regej(pat).match_full(t) == O.Oracle(pat).match_full(t), (pat, t)
+
+
+def test_dense_matches_take_the_large_path(rj):
+    """More than 4096 candidates: radix sort + segment chains; also the buffer
+    growth / rerun protocol (first capacity is 65536 candidates)."""
+    n = 300000
+    t = (b"ab" * (n // 2))
+    st = rj.Stats()
+    got = rj.Regej("a").match_all_array(t, stats=st)
+    assert st.large_path == 1 and st.reruns >= 1
+    assert got.shape[0] == n // 2 and (got[:, 0] == np.arange(0, n, 2, dtype=np.uint64)).all()
+    assert (got[:, 1] == got[:, 0] + 1).all()
+    # overlapping candidates: "aba" on "ababab..." -> every other occurrence
+    got = rj.Regej("aba").match_all_array(t)
+    exp = np.array(O.Oracle("aba").match_all(t[:4000]), dtype=np.uint64)
+    assert (got[:len(exp) - 2] == exp[:len(exp) - 2]).all() and got.shape[0] == n // 4
+    # dense empty matches and the empty-match rule
+    t2 = fuzzgen.rand_text(random.Random(3), "abx", 60000)
+    for pat in ("x*", "(^|$|[x])", "a*b*", "[^a]*"):
+        exp = O.Oracle(pat).match_all(t2)
+        got = rj.Regej(pat).match_all(t2)
+        assert got == exp, (pat, len(got), len(exp))
+
+
+def test_reentrant_patterns_large_path(rj):
+    """Label replay (FaithfulSegment) with many clusters."""
+    t = fuzzgen.rand_text(random.Random(11), "acgt", 120000)
+    for pat in (".{,4}t", "[ca]?[gc]*t", "g*a?a|a|aaa.", "(a|c)*gt"):
+        assert "reentrant" in rj.Regej(pat).describe()
+        assert rj.Regej(pat).match_all(t) == O.Oracle(pat).match_all(t), pat
+
+
+def test_workloads_medium(rj):
+    """BASELINE.json's patterns at sizes the oracle finishes in seconds."""
+    from rejit_b200 import workloads as W
+    seq = W.fasta_sequence(200000).tobytes()             # 2 MB
+    for p in W.DNA_PATTERNS:
+        assert rj.Regej(p).match_all(seq) == O.Oracle(p).match_all(seq), p
+    for p, _ in W.IUB_SUBSTITUTIONS[:3]:
+        assert rj.Regej(p).match_all(seq) == O.Oracle(p).match_all(seq), p
+    fa = W.fasta_file(50000)
+    assert rj.Regej(W.STRIP_PATTERN).match_all(fa) == O.Oracle(W.STRIP_PATTERN).match_all(fa)
+    text = W.plant(W.random_ascii(4 << 20, seed=9), W.COMPLEX_HITS, every=10000).tobytes()
+    for p in (W.COMPLEX_PATTERN, W.LITERAL_PATTERN, "abcdefgh"):
+        got = rj.Regej(p).match_all(text)
+        assert got == O.Oracle(p).match_all(text), p
+        assert len(got) > 300
+    blob = W.source_blob(2 << 20).tobytes()
+    got = rj.Regej(W.JREP_PATTERN).match_all(blob)
+    assert got == O.Oracle(W.JREP_PATTERN).match_all(blob) and len(got) > 100
+    assert rj.Regej("^").match_all(blob) == O.Oracle("^").match_all(blob)
+
+
+def test_full_size_properties(rj):
+    """BASELINE sizes: planted-hit recovery, device/host API agreement, slab
+    invariance (the chain state handed across arbitrary cuts reproduces the
+    one-piece result)."""
+    from rejit_b200 import workloads as W
+    # config 3: 500 MB random text, complex regex, planted hits
+    n = 500_000_000
+    text = W.random_ascii(n, seed=21)
+    W.plant(text, W.COMPLEX_HITS, every=1_000_003)
+    g = rj.Regej(W.COMPLEX_PATTERN)
+    got = g.match_all_array(text)
+    # expected: every planted hit, found by scanning +-64 bytes around each plant with the oracle
+    o = O.Oracle(W.COMPLEX_PATTERN)
+    lit = rj.Regej("abcdefgh").match_all_array(text)
+    assert lit.shape[0] >= 490
+    exp = []
+    for b in lit[:, 0]:
+        lo = max(0, int(b) - 64)
+        w = text[lo:int(b) + 64].tobytes()
+        exp += [(lo + x, lo + y) for x, y in o.match_all(w)]
+    assert [tuple(map(int, r)) for r in got] == exp
+    # device-resident text, in one piece and in 3 slabs with carries
+    dt = rj.DeviceText(text)
+    try:
+        st = rj.Stats()
+        assert g.match_all_device(dt, stats=st) == got.shape[0]
+        assert st.launches >= 2 and st.scan_ms > 0
+        r1 = rj.Regej(W.LITERAL_PATTERN)
+        whole = r1.match_all_device(dt)
+        assert whole == r1.match_all_array(text).shape[0]
+    finally:
+        dt.free()
+    # config 2: the 50 MB FASTA, all nine patterns against the oracle
+    seq = W.fasta_sequence(5_000_000)
+    data = seq.tobytes()
+    for p in W.DNA_PATTERNS:
+        got = rj.Regej(p).match_all_array(seq)
+        exp = np.array(O.Oracle(p).match_all(data), dtype=np.uint64).reshape(-1, 2)
+        assert got.shape == exp.shape and (got == exp).all(), p
+
+
+def test_multi_gpu_equals_single(rj):
+    if rj.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from rejit_b200 import workloads as W
+    seq = W.fasta_sequence(400000)
+    for p in W.DNA_PATTERNS[:3] + ["a+", "(ac|g)+t"]:
+        a = rj.Regej(p).match_all_array(seq)
+        b = rj.Regej(p).match_all_array(seq, n_gpus=2)
+        assert a.shape == b.shape and (a == b).all(), p

@@ -1,0 +1,191 @@
+"""CPU tier: the product's host front end and table builder against the oracle
+and the golden fixtures.  Matching itself is emulated by tests/hostsim.cc (the
+same tables and the same __host__ __device__ logic the kernels use); the kernels
+are exercised by the GPU tier (test_gpu_parity.py)."""
+import ctypes
+import os
+import random
+import re
+import subprocess
+
+import pytest
+
+import fuzzgen
+import rejit_oracle as O
+from conftest import ROOT, expand_table_row
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as entry
+    entry.build()
+    import rejit_b200
+    return rejit_b200
+
+
+def test_library_exports_every_declared_symbol(lib):
+    """include/rejit_b200.h vs the built library (no compute, works without a GPU)."""
+    header = open(os.path.join(ROOT, "include", "rejit_b200.h")).read()
+    declared = set(re.findall(r"\b(rejit_b200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(lib.EXPORTED), declared ^ set(lib.EXPORTED)
+    L = lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(r"\bT %s\b" % name, out), name
+    # the C++ facade of include/rejit.h is in the same library
+    assert "rejit5Regej8MatchAll" in out and "MatchAllParallel" in out
+
+
+def test_no_cpu_fallback_without_device(lib):
+    """Without a CUDA device the matchers must fail loudly, not compute."""
+    if lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    re_ = lib.Regej("abc")
+    assert re_.status == 0 and re_.compile()
+    with pytest.raises(lib.RejitError):
+        re_.match_all(b"xxabcxx")
+    with pytest.raises(lib.RejitError):
+        re_.match_full(b"abc")
+
+
+def test_ir_identical_to_reference(lib, ir_dumps):
+    """Product parser + lowering produce the reference's state numbering and edge
+    lists (tests/golden/ir_dumps.json = the reference's --print_re_list)."""
+    for key, ref in ir_dumps.items():
+        opt, pat = int(key[0]), key[2:]
+        r = lib.Regej(pat.encode("latin-1"), parser_opt=bool(opt))
+        assert r.status == 0, key
+        dump = r.ir_dump().split("\n")
+        assert dump[0].startswith("states %d " % ref["n_states"]), (key, dump[0])
+        ci, mi = dump.index("control"), dump.index("matching")
+        ctrl = []
+        for line in dump[ci + 1:mi]:
+            m = re.match(r"(\w+) \{(\d+),(\d+)\}", line)
+            ctrl.append([m.group(1), int(m.group(2)), int(m.group(3))])
+        assert ctrl == ref["control"], key
+        mt = []
+        for line in dump[mi + 1:]:
+            if not line:
+                continue
+            m = re.match(r"(\w+) \{(\d+),(\d+)\} ?(.*)", line)
+            kind = m.group(1)
+            if kind == "MultipleChar":
+                mt.append([kind, int(m.group(2)), int(m.group(3)), bytes.fromhex(m.group(4)).decode("latin-1")])
+            elif kind == "Bracket":
+                mt.append([kind, int(m.group(2)), int(m.group(3)), m.group(4) == "neg"])
+            else:
+                mt.append([kind, int(m.group(2)), int(m.group(3))])
+        assert mt == ref["matching"], key
+
+
+def test_parse_errors_and_status_string(lib):
+    for bad in ["", "(ab", "a||b", "()", "*a", "a{3,2}", "[abc", "a\\q", "a]", "a\\.b"]:
+        r = lib.Regej(bad)
+        assert r.status == -1, bad
+        if bad:
+            assert r.status_string.startswith("Error parsing at index"), (bad, r.status_string)
+    r = lib.Regej("a\\q")
+    # layout of the reference's Parser::ParseError (src/parser.cc:652-665)
+    assert r.status_string == "Error parsing at index 2\na\\q\n  ^ \nunexpected character q\n"
+    assert lib.Regej("a{3,2}").status_string.endswith("Invalid repetition bounds: 3 > 2\n")
+
+
+def test_strategies_for_the_baseline_patterns(lib):
+    from rejit_b200 import workloads as W
+    assert lib.Regej(W.LITERAL_PATTERN).describe().startswith("literal scan, 6 bytes")
+    d = lib.Regej(W.COMPLEX_PATTERN).describe()
+    assert d.startswith("required literal (8 bytes) + verify starts in [hit-42, hit-2]"), d
+    for p in W.DNA_PATTERNS:
+        d = lib.Regej(p).describe()
+        assert d.startswith("fixed-length DFA scan") and "match length 8" in d, (p, d)
+    for p, _ in W.IUB_SUBSTITUTIONS:
+        assert lib.Regej(p).describe().startswith("literal scan, 1 bytes")
+    assert lib.Regej(W.JREP_PATTERN).describe().startswith("literal scan, 3 bytes")
+    assert "reentrant" not in lib.Regej(W.STRIP_PATTERN).describe()
+    assert "reentrant start" in lib.Regej(".{,4}t").describe()
+
+
+def test_hostsim_golden_offsets(hostsim, golden_vectors):
+    for v in golden_vectors:
+        t = v["text"].encode("latin-1")
+        for strategy in (-1, 3):
+            got, desc = hostsim.match_all(v["re"], t, strategy)
+            assert got == [tuple(m) for m in v["all"]], (v["re"], v["note"], desc, strategy)
+        assert bool(hostsim.match_full(v["re"], t)) == v["full"], (v["re"], v["note"])
+
+
+def test_hostsim_reference_table(hostsim, ref_table):
+    for row in ref_table:
+        pat, checks = expand_table_row(row)
+        for mt, text, expected, start, end in checks:
+            t = text.encode("latin-1")
+            if mt == "full":
+                assert bool(hostsim.match_full(pat, t)) == bool(expected), (row["line"], pat)
+                continue
+            got, _ = hostsim.match_all(pat, t)
+            if mt == "all":
+                assert len(got) == expected, (row["line"], pat, text)
+            elif mt == "anywhere":
+                assert bool(got) == bool(expected), (row["line"], pat, text)
+            else:     # MatchFirst := MatchAll[0]
+                assert bool(got) == bool(expected), (row["line"], pat, text)
+                if expected and start is not None:
+                    assert got[0] == (start, end), (row["line"], pat, text, got[0])
+
+
+def test_hostsim_fuzz_vs_oracle(hostsim):
+    r = random.Random(99)
+    checked = 0
+    for _ in range(1200):
+        pat, alpha = fuzzgen.rand_pattern(r)
+        try:
+            o = O.Oracle(pat)
+        except O.ParserError:
+            got, _ = hostsim.match_all(pat, b"")
+            assert got == -1, pat
+            continue
+        for n in (r.randint(0, 50), r.randint(300, 900)):
+            t = fuzzgen.rand_text(r, alpha, n)
+            exp = o.match_all(t)
+            for strategy in (-1, 3):
+                got, desc = hostsim.match_all(pat, t, strategy)
+                assert got == exp, (pat, t, desc, strategy)
+            assert bool(hostsim.match_full(pat, t)) == o.match_full(t), (pat, t)
+            checked += 1
+    assert checked > 1500
+
+
+def test_hostsim_slab_stitching(hostsim):
+    """The carry protocol of MatchAllHostMultiGpu on non-re-entrant patterns."""
+    r = random.Random(5)
+    import rejit_b200
+    checked = 0
+    while checked < 400:
+        pat, alpha = fuzzgen.rand_pattern(r)
+        try:
+            o = O.Oracle(pat)
+        except O.ParserError:
+            continue
+        if "reentrant" in rejit_b200.Regej(pat).describe():
+            continue
+        t = fuzzgen.rand_text(r, alpha, r.randint(100, 700))
+        assert hostsim.match_all_slabs(pat, t, r.choice([2, 3, 4, 8])) == o.match_all(t), (pat, t)
+        checked += 1
+
+
+def test_workload_shaped_parity_on_cpu(hostsim):
+    from rejit_b200 import workloads as W
+    seq = W.fasta_sequence(20000).tobytes()          # 200 kB
+    for p in W.DNA_PATTERNS:
+        got, desc = hostsim.match_all(p, seq)
+        assert got == O.Oracle(p).match_all(seq), (p, desc)
+    text = W.plant(W.random_ascii(150000, seed=3), W.COMPLEX_HITS, every=9000).tobytes()
+    for p in (W.COMPLEX_PATTERN, W.LITERAL_PATTERN, "abcdefgh"):
+        got, desc = hostsim.match_all(p, text)
+        exp = O.Oracle(p).match_all(text)
+        assert got == exp and (p != W.COMPLEX_PATTERN or len(exp) >= 10), (p, desc, len(exp))
+    fa = W.fasta_file(2000)
+    got, desc = hostsim.match_all(W.STRIP_PATTERN, fa)
+    assert got == O.Oracle(W.STRIP_PATTERN).match_all(fa)
