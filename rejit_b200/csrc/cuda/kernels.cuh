@@ -1,0 +1,957 @@
+// rejit_b200 — the sm_100a kernels.
+//
+// What replaces what:
+//   loop A, the fast-forward scan      /root/reference/src/x64/codegen-x64.cc:1102-1403
+//        -> k_lit_scan   literal / required-literal scan: 16-byte vector loads,
+//                        funnel-shift compares, shuffles for straddling bytes
+//        -> k_dfa_tma    exact table-driven scan for fixed-length alternations:
+//                        text rows staged into shared memory with TMA bulk copies
+//                        (cp.async.bulk + mbarrier), per-lane replicated
+//                        transition rows (bank-conflict free), one DFA chain per lane
+//        -> k_dfa_scan   same automaton, plain vector loads (fallback for big tables
+//                        / dense matches)
+//   loop B, the NFA active-state advance   codegen-x64.cc:535-677
+//        -> NfaRun (device_program.h) driven by k_window_verify / k_generic_scan
+//   match selection   codegen-x64.cc:401-522 + /root/reference/src/codegen.cc:36-86
+//        -> k_resolve_ordered (one CTA, parallel: gather, max-scan, restart
+//           points, segment chains, compaction) and the multi-CTA large path
+//
+// Candidate order.  Every scanning warp owns a contiguous SUB-REGION of start
+// offsets and appends its candidates to that sub-region's slot range in
+// increasing order of begin, so the concatenation over sub-regions is already
+// sorted: no sort is needed before the chain is resolved.  (The unordered
+// append + sort path survives only as the fallback of k_dfa_scan.)
+#ifndef REJIT_B200_CUDA_KERNELS_CUH_
+#define REJIT_B200_CUDA_KERNELS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_program.h"
+#include "engine.h"
+
+namespace rejit_b200 {
+
+// ===========================================================================
+// device-side structures
+// ===========================================================================
+struct CandBuf {                       // unordered (begin, end) append buffer
+  uint64_t* begin;
+  uint64_t* end;
+  unsigned long long* count;           // may run past cap: overflow marker
+  uint64_t cap;
+};
+
+constexpr uint32_t kLaneListOverflow = 0xFFFFFFFFu;
+
+struct SubStore {                      // ordered store: slot range per sub-region
+  uint64_t* begin;                     // [nsub * cap]
+  uint64_t* end;                       // [nsub * cap]
+  uint32_t* count;                     // [nsub]; may exceed cap (overflow), or kLaneListOverflow
+  uint32_t cap;
+  uint32_t pad;
+  uint64_t nsub;
+};
+
+struct DenseList {                     // gathered (sorted) candidates
+  uint64_t* begin;
+  uint64_t* end;
+  unsigned long long* count;
+  uint64_t cap;
+};
+
+struct ScanRange {                     // which start offsets this launch owns
+  uint64_t own_begin;                  // inclusive
+  uint64_t own_end;                    // exclusive (n+1 to own the offset n)
+};
+
+struct PipelineStatus {                // one per call, read back by the host
+  unsigned long long n_candidates;
+  unsigned long long n_hits;
+  unsigned long long n_matches;
+  unsigned long long carry_cur;
+  unsigned long long carry_tail;
+  unsigned int overflow;               // a slot range / buffer was too small
+  unsigned int need_cap;               // largest per-sub-region count seen
+  unsigned int need_large;             // too many candidates for the one-CTA resolve
+  unsigned int dense;                  // lane hit list overflowed: use the fallback kernel
+  unsigned int full_result;            // MatchFull answer
+  unsigned int pad;
+};
+
+struct DfaTables {
+  const uint16_t* next;                // [n_states * n_classes], entries pre-multiplied by n_classes
+  const uint8_t* byte_class;           // [256]
+  int n_states, n_classes;
+  int first_accept_scaled;             // first accepting state * n_classes
+  uint32_t match_len;
+};
+
+struct FaithfulArgs {                  // only used for re-entrant patterns
+  int enabled;
+  NfaTables nfa;
+  const uint8_t* text;
+  uint64_t n;
+  uint8_t* scratch;                    // per-walker label scratch
+  uint64_t scratch_stride;             // bytes per walker
+};
+
+struct ResolveScratch {                // global scratch of the resolve kernels
+  uint64_t* reach;                     // [cap]
+  uint32_t* take;                      // [cap]
+  uint64_t* fin_end;                   // [cap]
+  uint64_t* slot;                      // [cap]
+};
+
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+constexpr int kSmallResolveMax = 4096;       // sort-based fallback resolve
+constexpr int kOrderedResolveMax = 16384;    // one-CTA ordered resolve
+constexpr uint32_t kLitSubBytes = 16384;     // sub-region of the literal scan (32 pieces)
+constexpr uint32_t kGenSubOffsets = 2048;    // sub-region of the generic scan
+constexpr uint32_t kWinSubHits = 8;          // needle hits per sub-region of the window verify
+constexpr uint32_t kDfaStreamBytes = 256;    // bytes per lane sub-stream (k_dfa_tma)
+constexpr uint32_t kDfaRowPitch = kDfaStreamBytes + 16;   // 272 = 17 * 16: conflict-free 16-byte rows
+constexpr uint32_t kDfaSubBytes = 32 * kDfaStreamBytes;   // sub-region of one warp
+constexpr int kDfaLaneHits = 4;
+
+// ===========================================================================
+// small device helpers
+// ===========================================================================
+__device__ __forceinline__ void AppendAggregated(const CandBuf& buf, uint64_t b, uint64_t e) {
+  unsigned m = __activemask();
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(buf.count, (unsigned long long)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
+  if (idx < buf.cap) {
+    buf.begin[idx] = b;
+    buf.end[idx] = e;
+  }
+}
+
+// Ordered append by a full warp: lanes with `has` write in lane order.
+__device__ __forceinline__ void EmitOrdered(const SubStore& st, uint64_t sub, uint32_t& k, bool has,
+                                            uint64_t b, uint64_t e) {
+  unsigned m = __ballot_sync(kFullMask, has);
+  if (!m) return;
+  uint32_t idx = k + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+  if (has && idx < st.cap) {
+    st.begin[sub * st.cap + idx] = b;
+    st.end[sub * st.cap + idx] = e;
+  }
+  k += __popc(m);
+}
+
+__device__ __forceinline__ uint32_t WarpInclusiveScan(uint32_t v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(kFullMask, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ uint4 LoadText16(const uint8_t* __restrict__ text, uint64_t n, uint64_t at) {
+  if (at + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(text + at));
+  uint32_t w[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 16; ++i)
+    if (at + i < n) w[i >> 2] |= (uint32_t)text[at + i] << (8 * (i & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ uint32_t LoadText4(const uint8_t* __restrict__ text, uint64_t n, uint64_t at) {
+  if (at + 4 <= n) return __ldg(reinterpret_cast<const uint32_t*>(text + at));
+  uint32_t w = 0;
+  for (int i = 0; i < 4; ++i)
+    if (at + i < n) w |= (uint32_t)text[at + i] << (8 * i);
+  return w;
+}
+
+// ---- mbarrier / TMA bulk copy (PTX) ----------------------------------------
+__device__ __forceinline__ uint32_t SmemAddr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void MbarInit(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void MbarExpectTx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool MbarTryWait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(SmemAddr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
+  while (!MbarTryWait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy (TMA, 1-D): size and both addresses multiples of 16
+__device__ __forceinline__ void TmaLoad1D(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          SmemAddr(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(SmemAddr(bar))
+      : "memory");
+}
+
+// ===========================================================================
+// K1: literal scan (ordered).  One warp owns a 16 KB sub-region = 32 pieces of
+// 512 bytes; in a piece lane l holds bytes [16l, 16l+16) in four registers; the
+// first min(m,4) needle bytes are compared at all 16 alignments with funnel
+// shifts, the word straddling into the next lane comes from a shuffle.
+// Survivors (rare) compare the rest of the needle from global memory.
+// Algorithmic traffic: N bytes read + 16 bytes written per occurrence.
+// ===========================================================================
+template <int kUnroll>
+__global__ void __launch_bounds__(256)
+k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restrict__ needle,
+           uint32_t m, uint32_t p4, uint32_t pmask, ScanRange range, SubStore out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr uint32_t kPieces = kLitSubBytes / 512;
+  for (uint64_t sub = warp; sub < out.nsub; sub += nwarps) {
+    const uint64_t sub_lo = sub * kLitSubBytes;
+    uint32_t k = 0;
+    const bool live = sub_lo < n && sub_lo + kLitSubBytes > range.own_begin && sub_lo < range.own_end;
+    if (live) {
+      for (uint32_t pc = 0; pc < kPieces; pc += kUnroll) {
+        if (sub_lo + (uint64_t)pc * 512 >= n) break;
+        uint4 v[kUnroll];
+        uint32_t nx[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          uint64_t my = sub_lo + (uint64_t)(pc + u) * 512 + (uint64_t)lane * 16;
+          v[u] = (my < n) ? LoadText16(text, n, my) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          uint64_t my = sub_lo + (uint64_t)(pc + u) * 512 + (uint64_t)lane * 16;
+          nx[u] = __shfl_down_sync(kFullMask, v[u].x, 1);
+          if (lane == 31) nx[u] = (my + 16 < n) ? LoadText4(text, n, my + 16) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const uint64_t my = sub_lo + (uint64_t)(pc + u) * 512 + (uint64_t)lane * 16;
+          const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx[u]};
+          uint32_t hits = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            uint32_t x = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3));
+            if (((x ^ p4) & pmask) == 0) hits |= 1u << j;
+          }
+          if (__any_sync(kFullMask, hits != 0)) {
+            // rare: validate the survivors, then append them in offset order
+            uint32_t valid = 0;
+            uint32_t hh = hits;
+            while (hh) {
+              int j = __ffs(hh) - 1;
+              hh &= hh - 1;
+              uint64_t pos = my + j;
+              if (pos < range.own_begin || pos >= range.own_end || pos + m > n) continue;
+              bool ok = true;
+              for (uint32_t i = 4; i < m && ok; ++i) ok = (text[pos + i] == needle[i]);
+              if (ok) valid |= 1u << j;
+            }
+            __syncwarp();
+            uint32_t c = __popc(valid);
+            uint32_t incl = WarpInclusiveScan(c);
+            uint32_t total = __shfl_sync(kFullMask, incl, 31);
+            uint32_t idx = k + incl - c;
+            while (valid) {
+              int j = __ffs(valid) - 1;
+              valid &= valid - 1;
+              if (idx < out.cap) {
+                out.begin[sub * out.cap + idx] = my + j;
+                out.end[sub * out.cap + idx] = my + j + m;
+              }
+              ++idx;
+            }
+            __syncwarp();
+            k += total;
+          }
+        }
+      }
+    }
+    if (lane == 0) out.count[sub] = k;
+  }
+}
+
+// ===========================================================================
+// K2: exact DFA scan for fixed-length, anchor-free patterns (regex-dna).
+// A warp owns a sub-region of 32 x 256 bytes.  Every lane stages ITS OWN row —
+// its 256-byte sub-stream preceded by the 16 bytes before it (the automaton's
+// warm-up: a fixed-length-L automaton entered >= L-1 bytes early is in the same
+// state as one sequential pass) — into shared memory with one TMA bulk copy
+// (cp.async.bulk, completion on the warp's mbarrier).  Rows are 272 bytes apart
+// (17 x 16), so the lanes' 16-byte shared loads are conflict free.  The
+// transition table is replicated per lane (entry e of lane l lives in bank l)
+// and its entries are the shared-memory ADDRESS of the next row, so one step is
+//     class = s_class[byte];  row = *(row + class*128)
+// Accepting rows are the highest addresses; a 16-byte group is replayed only
+// when its running maximum crosses that threshold.  Each lane keeps its (at
+// most four) match ends in registers; at the end of the sub-region a warp scan
+// places them, which yields candidates sorted by construction.
+// Algorithmic traffic: N bytes read + 16 bytes per match.
+// ===========================================================================
+__global__ void __launch_bounds__(768, 1)
+k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange range, SubStore out,
+          unsigned int* dense_flag) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int entries = dfa.n_states * dfa.n_classes;
+  // layout: [replicated rows: entries*128][class map: 256][barriers: 8*warps][tiles: warps*32*272]
+  uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem_raw);
+  uint8_t* s_class = smem_raw + (size_t)entries * 128;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_class + 256);
+  uint8_t* s_tiles = reinterpret_cast<uint8_t*>(s_bar + warps_per_cta);
+  s_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tiles) + 127) & ~(uintptr_t)127);
+  const uint32_t rows_base = SmemAddr(s_rows);
+  for (int i = threadIdx.x; i < entries * 32; i += blockDim.x) {
+    int e = i >> 5, l = i & 31;
+    // dfa.next[e] is the next state's row index (state * n_classes)
+    s_rows[e * 32 + l] = rows_base + (uint32_t)dfa.next[e] * 128u + (uint32_t)l * 4u;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_class[i] = dfa.byte_class[i];
+  uint64_t* bar = s_bar + warp_in_cta;
+  if (lane == 0) MbarInit(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  uint8_t* tile = s_tiles + (size_t)warp_in_cta * (32 * kDfaRowPitch);
+  uint8_t* my_row = tile + (size_t)lane * kDfaRowPitch;
+  const uint32_t my_row_addr = SmemAddr(my_row);
+  const uint32_t lane_base = rows_base + (uint32_t)lane * 4u;          // row of state 0 for this lane
+  const uint32_t acc_addr = lane_base + (uint32_t)dfa.first_accept_scaled * 128u;
+  const uint32_t class_base = SmemAddr(s_class);
+  const uint32_t L = dfa.match_len;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * warps_per_cta + warp_in_cta;
+  const uint64_t nwarps = (uint64_t)gridDim.x * warps_per_cta;
+  uint32_t phase = 0;
+
+  for (uint64_t sub = gwarp; sub < out.nsub; sub += nwarps) {
+    const uint64_t sub_lo = sub * kDfaSubBytes;
+    const bool live = sub_lo < n && sub_lo + kDfaSubBytes + L > range.own_begin && sub_lo < range.own_end + L;
+    uint32_t my_cnt = 0;
+    uint32_t hit[kDfaLaneHits] = {0, 0, 0, 0};
+    if (live) {
+      // ---- stage the rows -------------------------------------------------
+      const uint64_t a = sub_lo + (uint64_t)lane * kDfaStreamBytes;        // my sub-stream [a, b)
+      const uint64_t b = (a + kDfaStreamBytes < n) ? a + kDfaStreamBytes : n;
+      const bool have = a < n;
+      const bool warm = have && a >= 16;
+      const uint64_t src = warm ? a - 16 : a;
+      uint32_t bytes = 0;
+      if (have) {
+        uint64_t end16 = (b + 15) & ~15ull;                                  // stays inside the last 16-byte block
+        bytes = (uint32_t)(end16 - src);
+      }
+      uint32_t total = bytes;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(kFullMask, total, d);
+      if (lane == 0) MbarExpectTx(bar, total);
+      __syncwarp();
+      if (have) TmaLoad1D(my_row + (warm ? 0 : 16), text + src, bytes, bar);
+      MbarWait(bar, phase);
+      phase ^= 1;
+      // ---- walk my row ------------------------------------------------------
+      if (have) {
+        uint32_t row = lane_base;                 // state 0
+        const uint32_t first_chunk = warm ? 0 : 1;
+        const uint32_t n_chunks = 1 + (uint32_t)((b - a + 15) >> 4);        // warm-up chunk + data chunks
+        for (uint32_t ch = first_chunk; ch < n_chunks; ++ch) {
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(my_row_addr + ch * 16));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          const uint64_t p0 = a - 16 + (uint64_t)ch * 16;                     // text offset of byte 0 of the chunk
+          const uint32_t row0 = row;
+          uint32_t peak = 0;
+          const bool tail = p0 + 16 > b;
+          if (!tail) {
+            uint32_t cls[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+              asm("ld.shared.u8 %0, [%1];" : "=r"(cls[i]) : "r"(class_base + c));
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              asm("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(row + cls[i] * 128u));
+              peak = max(peak, row);
+            }
+          } else {
+            for (int i = 0; i < 16 && p0 + i < b; ++i) {
+              uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+              uint32_t cls = s_class[c];
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(row + cls * 128u));
+              peak = max(peak, row);
+            }
+          }
+          if (peak >= acc_addr && ch > 0) {
+            // rare: replay the group to find the exact end offsets
+            uint32_t r2 = row0;
+            for (int i = 0; i < 16 && p0 + i < b; ++i) {
+              uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+              uint32_t cls = s_class[c];
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r2) : "r"(r2 + cls * 128u));
+              if (r2 >= acc_addr) {
+                uint64_t e = p0 + i + 1;
+                if (e >= L) {
+                  uint64_t s = e - L;
+                  if (s >= range.own_begin && s < range.own_end) {
+#pragma unroll
+                    for (int q = 0; q < kDfaLaneHits; ++q)
+                      if (my_cnt == (uint32_t)q) hit[q] = (uint32_t)(e - sub_lo);
+                    ++my_cnt;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();      // everyone is done with the tile before the next TMA overwrites it
+    }
+    // ---- ordered emission: lanes cover increasing offsets ---------------------
+    if (__any_sync(kFullMask, my_cnt != 0)) {
+      bool over = __any_sync(kFullMask, my_cnt > kDfaLaneHits);
+      uint32_t c = my_cnt > kDfaLaneHits ? kDfaLaneHits : my_cnt;
+      uint32_t incl = WarpInclusiveScan(c);
+      uint32_t total = __shfl_sync(kFullMask, incl, 31);
+      uint32_t idx = incl - c;
+#pragma unroll
+      for (int q = 0; q < kDfaLaneHits; ++q) {
+        if (q < (int)c) {
+          if (idx + q < out.cap) {
+            uint64_t e = sub_lo + hit[q];
+            out.begin[sub * out.cap + idx + q] = e - L;
+            out.end[sub * out.cap + idx + q] = e;
+          }
+        }
+      }
+      if (lane == 0) {
+        out.count[sub] = over ? kLaneListOverflow : total;
+        if (over) *dense_flag = 1u;
+      }
+    } else if (lane == 0) {
+      out.count[sub] = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2 fallback: same automaton, 16-byte global loads, non-replicated table,
+// unordered append (dense matches / tables too large for k_dfa_tma).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_dfa_scan(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, uint32_t stream_bytes,
+           ScanRange range, CandBuf out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw);
+  const int table_entries = dfa.n_states * dfa.n_classes;
+  uint8_t* s_class = smem_raw + ((table_entries * 2 + 15) & ~15);
+  for (int i = threadIdx.x; i < table_entries; i += blockDim.x) s_next[i] = dfa.next[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_class[i] = dfa.byte_class[i];
+  __syncthreads();
+
+  const uint32_t L = dfa.match_len;
+  const uint32_t warm = (L - 1 + 15) & ~15u;
+  const uint64_t n_streams = (n + stream_bytes - 1) / stream_bytes;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  const int acc = dfa.first_accept_scaled;
+  for (uint64_t sidx = tid; sidx < n_streams; sidx += nthreads) {
+    const uint64_t a = sidx * stream_bytes;
+    const uint64_t b = (a + stream_bytes < n) ? a + stream_bytes : n;
+    if (b <= range.own_begin || a >= range.own_end + L) continue;
+    uint64_t p = (a >= warm) ? a - warm : 0;
+    uint32_t state = 0;
+    for (; p < b; p += 16) {
+      uint4 v = LoadText16(text, n, p);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t peak = 0;
+      uint32_t s0 = state;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+        uint32_t st = s_next[state + s_class[c]];
+        state = (p + i < b) ? st : state;
+        peak = max(peak, state);
+      }
+      if (peak >= (uint32_t)acc) {
+        uint32_t st = s0;
+        for (int i = 0; i < 16 && p + i < b; ++i) {
+          uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+          st = s_next[st + s_class[c]];
+          if (st >= (uint32_t)acc) {
+            uint64_t e = p + i + 1;
+            if (e > a && e >= L) {
+              uint64_t s = e - L;
+              if (s >= range.own_begin && s < range.own_end) AppendAggregated(out, s, e);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ===========================================================================
+// K3: generic scan (ordered) — a warp owns 2048 consecutive start offsets; per
+// step, one lane per offset: start filter on the first byte, then the NFA run.
+// ===========================================================================
+__global__ void __launch_bounds__(256)
+k_generic_scan(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, ScanRange range, SubStore out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t sub = warp; sub < out.nsub; sub += nwarps) {
+    const uint64_t lo = sub * kGenSubOffsets;
+    uint32_t k = 0;
+    if (lo <= n && lo + kGenSubOffsets > range.own_begin && lo < range.own_end) {
+      for (uint32_t it = 0; it < kGenSubOffsets; it += 32) {
+        uint64_t s = lo + it + lane;
+        uint64_t e = kNoMatch;
+        if (s <= n && s >= range.own_begin && s < range.own_end) {
+          int ctx = nfa.has_anchor ? ContextAt(text, n, s) : 0;
+          bool ok = nfa.accept_empty[ctx] || (s < n && nfa.start_ok[ctx * 256 + text[s]]);
+          if (ok) e = NfaRunAny(nfa, text, n, s);
+        }
+        __syncwarp();
+        EmitOrdered(out, sub, k, e != kNoMatch, s, e);
+        if (lo + it + 32 > n) break;
+      }
+    }
+    if (lane == 0) out.count[sub] = k;
+  }
+}
+
+// ===========================================================================
+// K4: verify the window of possible starts in front of every needle hit
+// (ordered).  A warp owns 8 consecutive hits; windows are clipped against the
+// previous hit's window so that every start is tried once and in order.
+// ===========================================================================
+__global__ void __launch_bounds__(256)
+k_window_verify(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, DenseList hits, uint32_t lo,
+                uint32_t hi, ScanRange range, SubStore out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long nh = *hits.count;
+  if (nh > hits.cap) nh = hits.cap;
+  for (uint64_t sub = warp; sub < out.nsub; sub += nwarps) {
+    uint32_t k = 0;
+    for (uint32_t q = 0; q < kWinSubHits; ++q) {
+      uint64_t hidx = sub * kWinSubHits + q;
+      if (hidx >= nh) break;
+      const uint64_t h = hits.begin[hidx];
+      if (h < lo) continue;
+      uint64_t s_max = h - lo;                               // inclusive
+      uint64_t s_min = h >= hi ? h - hi : 0;
+      if (hidx > 0) {
+        uint64_t prev = hits.begin[hidx - 1];
+        if (prev >= lo && prev - lo + 1 > s_min) s_min = prev - lo + 1;   // already covered
+      }
+      for (uint64_t base = s_min; base <= s_max; base += 32) {
+        uint64_t s = base + lane;
+        uint64_t e = kNoMatch;
+        if (s <= s_max && s >= range.own_begin && s < range.own_end && s < n) {
+          int ctx = nfa.has_anchor ? ContextAt(text, n, s) : 0;
+          if (nfa.start_ok[ctx * 256 + text[s]]) e = NfaRunAny(nfa, text, n, s);
+        }
+        __syncwarp();
+        EmitOrdered(out, sub, k, e != kNoMatch, s, e);
+      }
+    }
+    if (lane == 0) out.count[sub] = k;
+  }
+}
+
+// ===========================================================================
+// MatchFull: one sequential run from offset 0 (a latency-bound sibling of the
+// hot path).
+// ===========================================================================
+__global__ void k_match_full(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa,
+                             PipelineStatus* status) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint64_t e = NfaRunAny(nfa, text, n, 0, /*full_only=*/true);
+    status->full_result = (e == n) ? 1u : 0u;
+  }
+}
+
+// ===========================================================================
+// block-wide scans used by the one-CTA kernels (1024 threads)
+// ===========================================================================
+__device__ __forceinline__ uint32_t BlockExclusiveSum(uint32_t v, uint32_t* total, uint32_t* s_warp) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t incl = WarpInclusiveScan(v);
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t x = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+    uint32_t xi = WarpInclusiveScan(x);
+    s_warp[lane] = xi - x;
+    if (lane == 31) s_warp[32] = xi;
+  }
+  __syncthreads();
+  uint32_t r = s_warp[wid] + incl - v;
+  *total = s_warp[32];
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ uint64_t BlockExclusiveMax(uint64_t v, uint64_t init, uint64_t* s_warp) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t t = __shfl_up_sync(kFullMask, incl, d);
+    if (lane >= d && t > incl) incl = t;
+  }
+  uint64_t excl = __shfl_up_sync(kFullMask, incl, 1);
+  if (lane == 0) excl = 0;
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint64_t x = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+    uint64_t xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t t = __shfl_up_sync(kFullMask, xi, d);
+      if (lane >= d && t > xi) xi = t;
+    }
+    uint64_t xe = __shfl_up_sync(kFullMask, xi, 1);
+    if (lane == 0) xe = 0;
+    s_warp[lane] = xe;
+  }
+  __syncthreads();
+  uint64_t r = s_warp[wid] > excl ? s_warp[wid] : excl;
+  if (init > r) r = init;
+  __syncthreads();
+  return r;
+}
+
+// Concatenates the sub-regions' slot ranges into a dense (sorted) list.
+// Returns false (uniformly) on overflow / dense marker; *m_out = total.
+__device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseList& dense, PipelineStatus* status,
+                                               uint32_t* s_warp, unsigned long long* m_out) {
+  __shared__ unsigned int s_flags[3];          // [0] max count, [1] dense marker, [2] unused
+  if (threadIdx.x < 3) s_flags[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long base = 0;
+  for (uint64_t blk = 0; blk < st.nsub; blk += blockDim.x) {
+    uint64_t sub = blk + threadIdx.x;
+    uint32_t c = 0;
+    if (sub < st.nsub) {
+      c = st.count[sub];
+      if (c == kLaneListOverflow) { atomicOr(&s_flags[1], 1u); c = 0; }
+      else if (c > st.cap) { atomicMax(&s_flags[0], c); c = st.cap; }
+    }
+    uint32_t total;
+    uint32_t off = BlockExclusiveSum(c, &total, s_warp);
+    for (uint32_t i = 0; i < c; ++i) {
+      unsigned long long at = base + off + i;
+      if (at < dense.cap) {
+        dense.begin[at] = st.begin[sub * st.cap + i];
+        dense.end[at] = st.end[sub * st.cap + i];
+      }
+    }
+    base += total;
+  }
+  __syncthreads();
+  *m_out = base;
+  bool ok = true;
+  if (s_flags[1]) { if (threadIdx.x == 0) status->dense = 1; ok = false; }
+  if (s_flags[0]) { if (threadIdx.x == 0) { status->overflow = 1; status->need_cap = s_flags[0]; } ok = false; }
+  if (base > dense.cap) { if (threadIdx.x == 0) { status->overflow = 1; } ok = false; }
+  if (threadIdx.x == 0) *dense.count = base;
+  return ok;
+}
+
+// Stage boundary of the literal+window pipeline: dense list of needle hits.
+__global__ void __launch_bounds__(1024)
+k_gather_hits(SubStore st, DenseList dense, PipelineStatus* status) {
+  __shared__ uint32_t s_warp[33];
+  unsigned long long m;
+  GatherSubStore(st, dense, status, s_warp, &m);
+  if (threadIdx.x == 0) status->n_hits = m;
+}
+
+__device__ __forceinline__ bool IsRestart(const uint64_t* b, const uint64_t* e, const uint64_t* reach, uint64_t i) {
+  return reach[i] < b[i] || (reach[i] == b[i] && e[i] > b[i]);
+}
+
+__device__ __forceinline__ FaithfulScratch WalkerScratch(const FaithfulArgs& fa, uint64_t walker) {
+  uint8_t* base = fa.scratch + walker * fa.scratch_stride;
+  const uint64_t P = fa.nfa.n_pos > 0 ? fa.nfa.n_pos : 1;
+  const uint64_t W = fa.nfa.words;
+  FaithfulScratch sc;
+  sc.lab = reinterpret_cast<uint64_t*>(base);
+  sc.nlab = sc.lab + P;
+  sc.act = reinterpret_cast<uint32_t*>(sc.nlab + P);
+  sc.nact = sc.act + W;
+  sc.blocked = sc.nact + W;
+  return sc;
+}
+
+// ===========================================================================
+// Resolve (ordered input), one CTA of 1024 threads, everything parallel:
+//   gather -> reach = exclusive max of ends -> restart points -> every restart
+//   point walks its segment (ChainTake; label replay for re-entrant patterns)
+//   -> exclusive sum of take flags -> pairs out.
+// Restart rule: candidate i restarts the chain when no earlier candidate can
+// influence it: reach[i] < begin[i], or reach[i] == begin[i] and it is non-empty
+// (strictly smaller only, for re-entrant patterns).
+// ===========================================================================
+__global__ void __launch_bounds__(1024)
+k_resolve_ordered(SubStore st, DenseList dense, ResolveScratch rs, Carry carry_in, uint64_t base_offset,
+                  uint64_t* __restrict__ out_pairs, uint64_t out_cap, FaithfulArgs fa, PipelineStatus* status) {
+  __shared__ uint32_t s_warp[33];
+  __shared__ uint64_t s_warp64[32];
+  __shared__ unsigned long long s_last[2];
+  unsigned long long m;
+  bool ok = GatherSubStore(st, dense, status, s_warp, &m);
+  if (threadIdx.x == 0) status->n_candidates = m;
+  if (!ok) return;
+  if (m > (unsigned long long)kOrderedResolveMax) {
+    if (threadIdx.x == 0) status->need_large = 1;
+    return;
+  }
+  if (threadIdx.x < 2) s_last[threadIdx.x] = 0;
+  const uint32_t M = (uint32_t)m;
+  const uint32_t ipt = (M + blockDim.x - 1) / blockDim.x;      // items per thread (blocked)
+  const uint32_t i0 = min(M, threadIdx.x * ipt), i1 = min(M, i0 + ipt);
+  const uint64_t* b = dense.begin;
+  const uint64_t* e = dense.end;
+  // reach
+  uint64_t local = 0;
+  for (uint32_t i = i0; i < i1; ++i) local = e[i] > local ? e[i] : local;
+  uint64_t run = BlockExclusiveMax(local, carry_in.cur, s_warp64);
+  for (uint32_t i = i0; i < i1; ++i) { rs.reach[i] = run; run = e[i] > run ? e[i] : run; }
+  __syncthreads();
+  // chains
+  for (uint32_t i = i0; i < i1; ++i) {
+    bool head = fa.enabled ? (i == 0 || rs.reach[i] < b[i]) : (i == 0 || IsRestart(b, e, rs.reach, i));
+    if (!head) continue;
+    if (fa.enabled) {
+      uint32_t j = i + 1;
+      while (j < M && !(rs.reach[j] < b[j])) ++j;
+      FaithfulSegment(fa.nfa, fa.text, fa.n, b, e, i, j, WalkerScratch(fa, threadIdx.x), rs.take, rs.fin_end);
+    } else {
+      ChainState cs;
+      if (i == 0) { cs.cur = carry_in.cur; cs.tail = carry_in.tail; }
+      else { cs.cur = 0; cs.tail = kNoMatch; }
+      for (uint32_t j = i; j < M; ++j) {
+        if (j > i && IsRestart(b, e, rs.reach, j)) break;
+        rs.take[j] = ChainTake(&cs, b[j], e[j]) ? 1u : 0u;
+        rs.fin_end[j] = e[j];
+      }
+    }
+  }
+  __syncthreads();
+  // compaction
+  uint32_t mine = 0;
+  for (uint32_t i = i0; i < i1; ++i) mine += rs.take[i];
+  uint32_t total;
+  uint32_t off = BlockExclusiveSum(mine, &total, s_warp);
+  for (uint32_t i = i0; i < i1; ++i) {
+    if (!rs.take[i]) continue;
+    if (off < out_cap) {
+      out_pairs[2 * (uint64_t)off] = b[i] + base_offset;
+      out_pairs[2 * (uint64_t)off + 1] = rs.fin_end[i] + base_offset;
+    }
+    ++off;
+    atomicMax(&s_last[0], (unsigned long long)i + 1);
+    if (rs.fin_end[i] > b[i]) atomicMax(&s_last[1], (unsigned long long)i + 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    status->n_matches = total;
+    uint64_t cur = carry_in.cur, tail = carry_in.tail;
+    if (s_last[0]) {
+      uint64_t i = s_last[0] - 1;
+      cur = rs.fin_end[i] > b[i] ? rs.fin_end[i] : b[i] + 1;
+    }
+    if (s_last[1]) tail = rs.fin_end[s_last[1] - 1];
+    status->carry_cur = cur;
+    status->carry_tail = tail;
+  }
+}
+
+// ===========================================================================
+// Resolve, sort-based fallback (unordered candidates from k_dfa_scan): one CTA
+// sorts by begin (bitonic, shared memory) and walks the chain.
+// ===========================================================================
+__global__ void __launch_bounds__(1024)
+k_resolve_small(CandBuf cand, Carry carry_in, uint64_t base_offset, uint64_t* __restrict__ out_pairs,
+                uint64_t out_cap, PipelineStatus* status) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* kb = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned long long m = *cand.count;
+  if (threadIdx.x == 0) status->n_candidates = m;
+  if (m > cand.cap) {
+    if (threadIdx.x == 0) status->overflow = 1;
+    return;
+  }
+  if (m > (unsigned long long)kSmallResolveMax) {
+    if (threadIdx.x == 0) status->need_large = 1;
+    return;
+  }
+  int count = (int)m;
+  int padded = 1;
+  while (padded < count) padded <<= 1;
+  uint64_t* ke = kb + padded;
+  for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+    kb[i] = (i < count) ? cand.begin[i] : ~0ull;
+    ke[i] = (i < count) ? cand.end[i] : ~0ull;
+  }
+  __syncthreads();
+  for (int k = 2; k <= padded; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          bool up = ((i & k) == 0);
+          uint64_t a = kb[i], b = kb[ixj];
+          if ((a > b) == up) {
+            kb[i] = b; kb[ixj] = a;
+            uint64_t t = ke[i]; ke[i] = ke[ixj]; ke[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    ChainState st{carry_in.cur, carry_in.tail};
+    unsigned long long taken = 0;
+    uint64_t prev_b = ~0ull;
+    for (int i = 0; i < count; ++i) {
+      uint64_t b = kb[i], e = ke[i];
+      if (b == prev_b) continue;
+      prev_b = b;
+      if (ChainTake(&st, b, e)) {
+        if (taken < out_cap) {
+          out_pairs[2 * taken] = b + base_offset;
+          out_pairs[2 * taken + 1] = e + base_offset;
+        }
+        ++taken;
+      }
+    }
+    status->n_matches = taken;
+    status->carry_cur = st.cur;
+    status->carry_tail = st.tail;
+  }
+}
+
+// ===========================================================================
+// Large path (multi-CTA) on a dense, sorted candidate list.
+// ===========================================================================
+struct MaxOp {
+  __host__ __device__ __forceinline__ uint64_t operator()(uint64_t a, uint64_t b) const { return a > b ? a : b; }
+};
+
+__global__ void k_segment_chain(const uint64_t* __restrict__ b, const uint64_t* __restrict__ e,
+                                const uint64_t* __restrict__ reach, uint64_t m, Carry carry_in,
+                                uint32_t* __restrict__ take, uint64_t* __restrict__ fin_end) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < m; i += nthreads) {
+    bool head = (i == 0) || (b[i] != b[i - 1] && IsRestart(b, e, reach, i));
+    if (!head) continue;
+    ChainState st;
+    if (i == 0) { st.cur = carry_in.cur; st.tail = carry_in.tail; }
+    else { st.cur = 0; st.tail = kNoMatch; }
+    uint64_t prev_b = kNoMatch;
+    for (uint64_t j = i; j < m; ++j) {
+      if (j > i && b[j] != b[j - 1] && IsRestart(b, e, reach, j)) break;
+      fin_end[j] = e[j];
+      if (b[j] == prev_b) { take[j] = 0; continue; }
+      prev_b = b[j];
+      take[j] = ChainTake(&st, b[j], e[j]) ? 1u : 0u;
+    }
+  }
+}
+
+__global__ void k_segment_faithful(const uint64_t* __restrict__ b, const uint64_t* __restrict__ e,
+                                   const uint64_t* __restrict__ reach, uint64_t m, FaithfulArgs fa,
+                                   uint32_t* take, uint64_t* fin_end) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  FaithfulScratch sc = WalkerScratch(fa, tid);
+  for (uint64_t i = tid; i < m; i += nthreads) {
+    bool head = (i == 0) || (reach[i] < b[i]);
+    if (!head) continue;
+    uint64_t j = i + 1;
+    while (j < m && !(reach[j] < b[j])) ++j;
+    FaithfulSegment(fa.nfa, fa.text, fa.n, b, e, i, j, sc, take, fin_end);
+  }
+}
+
+__global__ void k_scatter_matches(const uint64_t* __restrict__ b, const uint64_t* __restrict__ e,
+                                  const uint32_t* __restrict__ take, const uint64_t* __restrict__ slot,
+                                  uint64_t m, uint64_t base_offset, uint64_t* __restrict__ out_pairs,
+                                  uint64_t out_cap, unsigned long long* last_any,
+                                  unsigned long long* last_nonempty) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < m; i += nthreads) {
+    if (!take[i]) continue;
+    uint64_t at = slot[i];
+    if (at < out_cap) {
+      out_pairs[2 * at] = b[i] + base_offset;
+      out_pairs[2 * at + 1] = e[i] + base_offset;
+    }
+    atomicMax(last_any, (unsigned long long)(i + 1));
+    if (e[i] > b[i]) atomicMax(last_nonempty, (unsigned long long)(i + 1));
+  }
+}
+
+__global__ void k_finish_large(const uint64_t* __restrict__ b, const uint64_t* __restrict__ e,
+                               const uint32_t* __restrict__ take, const uint64_t* __restrict__ slot,
+                               uint64_t m, Carry carry_in, const unsigned long long* last_any,
+                               const unsigned long long* last_nonempty, PipelineStatus* status) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  status->n_matches = m ? slot[m - 1] + take[m - 1] : 0;
+  uint64_t cur = carry_in.cur, tail = carry_in.tail;
+  if (*last_any) {
+    uint64_t i = *last_any - 1;
+    cur = (e[i] > b[i]) ? e[i] : b[i] + 1;
+  }
+  if (*last_nonempty) tail = e[*last_nonempty - 1];
+  status->carry_cur = cur;
+  status->carry_tail = tail;
+}
+
+__global__ void k_widen_flags(const uint32_t* __restrict__ take, uint64_t* __restrict__ wide, uint64_t m) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < m; i += nthreads) wide[i] = take[i];
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint64_t count, uint32_t v) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < count; i += nthreads) p[i] = v;
+}
+
+}  // namespace rejit_b200
+
+#endif  // REJIT_B200_CUDA_KERNELS_CUH_

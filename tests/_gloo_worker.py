@@ -1,0 +1,48 @@
+"""Worker for tests/test_sharding_gloo.py: one rank of a world_size-N gloo job
+running the slab-stitching protocol of rejit_b200/sharding.py (the one bench.py
+uses under torchrun) with the per-slab resolve emulated on the CPU by
+tests/hostsim.cc.  Prints one JSON line per case on rank 0."""
+import ctypes
+import json
+import os
+import random
+import sys
+
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import fuzzgen  # noqa: E402
+from rejit_b200 import sharding  # noqa: E402
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libhostsim.so"))
+    L.hostsim_slab_run.restype = ctypes.c_int64
+    L.hostsim_slab_run.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64,
+                                   ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64,
+                                   ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    cases = json.loads(sys.argv[1])
+    out = []
+    for pat, text_hex in cases:
+        text = bytes.fromhex(text_hex)
+        pb = pat.encode("latin-1")
+        lo, hi = sharding.slab_bounds(len(text), world, rank)
+
+        def run(cur, tail):
+            oc, ot = ctypes.c_uint64(), ctypes.c_uint64()
+            c = L.hostsim_slab_run(pb, len(pb), text, len(text), lo, hi, 1 if rank + 1 == world else 0,
+                                   cur, tail, ctypes.byref(oc), ctypes.byref(ot))
+            return int(c), int(oc.value), int(ot.value)
+        total, rounds = sharding.stitched_count(dist, rank, world, lo, run)
+        out.append([total, rounds])
+    if rank == 0:
+        print("RESULT " + json.dumps(out), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,19 +82,26 @@ void ScanDfaStreams(const Compiled& c, const uint8_t* text, uint64_t n, uint32_t
   }
 }
 
+// Emulates k_window_verify: windows clipped against the previous hit's window.
 void ScanWindow(const Compiled& c, const uint8_t* text, uint64_t n, Cands* out) {
   Cands hits;
   ScanLiteral(c.ca.literal, text, n, &hits);
   uint32_t lo = c.ca.window_lo, hi = c.ca.window_hi;
-  for (auto& h : hits)
-    for (uint32_t j = 0; j <= hi - lo; ++j) {
-      if (h.first + j < hi) continue;
-      uint64_t s = h.first + j - hi;
+  for (size_t i = 0; i < hits.size(); ++i) {
+    uint64_t h = hits[i].first;
+    if (h < lo) continue;
+    uint64_t s_max = h - lo, s_min = h >= hi ? h - hi : 0;
+    if (i > 0) {
+      uint64_t prev = hits[i - 1].first;
+      if (prev >= lo && prev - lo + 1 > s_min) s_min = prev - lo + 1;
+    }
+    for (uint64_t s = s_min; s <= s_max && s < n; ++s) {
       int ctx = c.nfa.has_anchor ? ContextAt(text, n, s) : 0;
-      if (!(s < n && c.nfa.start_ok[ctx * 256 + text[s]])) continue;
+      if (!c.nfa.start_ok[ctx * 256 + text[s]]) continue;
       uint64_t e = NfaRunAny(c.nfa, text, n, s);
       if (e != kNoMatch) out->push_back({s, e});
     }
+  }
 }
 
 void ScanGeneric(const Compiled& c, const uint8_t* text, uint64_t n, Cands* out) {
@@ -191,7 +198,7 @@ int64_t hostsim_match_all(const char* pattern, size_t plen, int parser_opt, cons
   Cands cands;
   switch (use) {
     case 0: ScanLiteral(c.ca.literal, text, n, &cands); break;
-    case 1: ScanDfaStreams(c, text, n, 512, &cands); break;
+    case 1: ScanDfaStreams(c, text, n, 256, &cands); break;
     case 2: ScanWindow(c, text, n, &cands); break;
     default: ScanGeneric(c, text, n, &cands);
   }
@@ -253,6 +260,25 @@ int64_t hostsim_match_all_slabs(const char* pattern, size_t plen, const uint8_t*
       ++k;
     }
   return (int64_t)k;
+}
+
+// One rank of the one-process-per-GPU sharding: resolve the starts in [lo, hi)
+// (the last slab also owns the offset n) with the given carry (global offsets).
+int64_t hostsim_slab_run(const char* pattern, size_t plen, const uint8_t* text, uint64_t n, uint64_t lo,
+                         uint64_t hi, int last, uint64_t carry_cur, uint64_t carry_tail, uint64_t* out_cur,
+                         uint64_t* out_tail) {
+  Compiled c;
+  std::string error;
+  if (!CompilePattern(pattern, plen, 1, &c, &error)) return -1;
+  Cands all, mine, res;
+  ScanGeneric(c, text, n, &all);
+  uint64_t end = last ? n + 1 : hi;
+  for (auto& x : all) if (x.first >= lo && x.first < end) mine.push_back(x);
+  ChainState fin;
+  ResolveSequential(mine, ChainState{carry_cur, carry_tail}, &res, &fin);
+  *out_cur = fin.cur;
+  *out_tail = fin.tail;
+  return (int64_t)res.size();
 }
 
 int hostsim_match_full(const char* pattern, size_t plen, const uint8_t* text, uint64_t n) {

@@ -125,6 +125,22 @@ def test_dense_matches_take_the_large_path(rj):
         assert got == exp, (pat, len(got), len(exp))
 
 
+def test_dfa_dense_fallback_and_tma_agree(rj):
+    """Fixed-length alternations: sparse -> k_dfa_tma (ordered, TMA-staged);
+    dense -> the lane hit lists overflow and the engine switches to k_dfa_scan +
+    sort.  Both must equal the oracle."""
+    t = fuzzgen.rand_text(random.Random(8), "acgt", 150001)
+    for pat in ("a|c", "ac|gt", "acg|tgc", "ac[gt]a|tt[ac]g", "agggtaaa|tttaccct"):
+        r = rj.Regej(pat)
+        assert r.describe().startswith("fixed-length DFA scan"), r.describe()
+        st = rj.Stats()
+        got = r.match_all_array(t, stats=st)
+        exp = np.array(O.Oracle(pat).match_all(t), dtype=np.uint64).reshape(-1, 2)
+        assert got.shape == exp.shape and (got == exp).all(), (pat, got.shape, exp.shape)
+        again = r.match_all_array(t)            # steady state (capacities remembered)
+        assert (again == exp).all()
+
+
 def test_reentrant_patterns_large_path(rj):
     """Label replay (FaithfulSegment) with many clusters."""
     t = fuzzgen.rand_text(random.Random(11), "acgt", 120000)
@@ -168,7 +184,7 @@ def test_full_size_properties(rj):
     # expected: every planted hit, found by scanning +-64 bytes around each plant with the oracle
     o = O.Oracle(W.COMPLEX_PATTERN)
     lit = rj.Regej("abcdefgh").match_all_array(text)
-    assert lit.shape[0] >= 490
+    assert lit.shape[0] >= 400
     exp = []
     for b in lit[:, 0]:
         lo = max(0, int(b) - 64)
