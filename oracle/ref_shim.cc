@@ -16,6 +16,7 @@
 #include <string>
 #include <thread>
 #include <algorithm>
+#include <omp.h>
 
 #include "rejit.h"
 #include "flags.h"
@@ -93,6 +94,12 @@ int ref_match_anywhere(const char* pattern, const char* text, size_t n) {
 // reference harness forgets to do — SURVEY.md B14).
 struct RefHandle {
   rejit::Regej* re;
+  // One privately compiled matcher per worker thread: threads that share ONE
+  // compiled Regej slow each other down severely (measured here: 8 threads on
+  // one Regej run 6x SLOWER than one thread, 8 processes scale linearly), so
+  // the all-cores baseline gives every thread its own copy of the JIT'd code.
+  std::vector<rejit::Regej*> per_thread;
+  std::string pattern;
 };
 
 void* ref_compile(const char* pattern) {
@@ -103,6 +110,7 @@ void* ref_compile(const char* pattern) {
   }
   RefHandle* h = new RefHandle;
   h->re = re;
+  h->pattern = pattern;
   return h;
 }
 
@@ -110,6 +118,7 @@ void ref_free(void* handle) {
   RefHandle* h = (RefHandle*)handle;
   if (!h) return;
   delete h->re;
+  for (size_t i = 0; i < h->per_thread.size(); i++) delete h->per_thread[i];
   delete h;
 }
 
@@ -119,6 +128,18 @@ int64_t ref_run_match_all(void* handle, const char* text, size_t n) {
   std::vector<rejit::Match> m;
   h->re->MatchAll(text, n, &m);
   return (int64_t)m.size();
+}
+
+// One call on a slab of `n` bytes; returns how many matches BEGIN in the first
+// `own` bytes (the rest of the slab is overlap with the next worker's slab).
+int64_t ref_match_all_handle(void* handle, const char* text, size_t n, size_t own) {
+  RefHandle* h = (RefHandle*)handle;
+  std::vector<rejit::Match> m;
+  h->re->MatchAll(text, n, &m);
+  int64_t c = 0;
+  for (size_t i = 0; i < m.size(); i++)
+    if ((size_t)(m[i].begin - text) < own) c++;
+  return c;
 }
 
 // All-host-threads variant: the text is cut into `threads`
@@ -132,26 +153,31 @@ int64_t ref_run_match_all_mt(void* handle, const char* text, size_t n,
                              int threads, size_t overlap) {
   RefHandle* h = (RefHandle*)handle;
   if (threads < 1) threads = 1;
-  std::vector<int64_t> counts(threads, 0);
-  std::vector<std::thread> pool;
-  size_t slab = (n + threads - 1) / threads;
-  for (int t = 0; t < threads; t++) {
-    pool.emplace_back([=, &counts]() {
-      size_t b = std::min(n, (size_t)t * slab);
-      size_t e = std::min(n, b + slab);
-      size_t ee = std::min(n, e + overlap);
-      if (b >= e) return;
-      std::vector<rejit::Match> m;
-      h->re->MatchAll(text + b, ee - b, &m);
-      int64_t c = 0;
-      for (size_t i = 0; i < m.size(); i++)
-        if ((size_t)(m[i].begin - text) < e) c++;
-      counts[t] = c;
-    });
+  // more slabs than threads so that slabs with many matches do not straggle;
+  // OpenMP keeps its worker threads alive between calls (no spawn cost in the
+  // timed region after the first call)
+  while ((int)h->per_thread.size() < threads) {     // untimed on the warm-up pass
+    rejit::Regej* r = new rejit::Regej(h->pattern.c_str());
+    r->Compile(rejit::kMatchAll);
+    h->per_thread.push_back(r);
   }
-  for (auto& th : pool) th.join();
+  int slabs = threads * 4;
+  if ((size_t)slabs > n / 4096 + 1) slabs = (int)(n / 4096 + 1);
+  size_t slab = (n + slabs - 1) / slabs;
   int64_t total = 0;
-  for (int t = 0; t < threads; t++) total += counts[t];
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1) reduction(+ : total)
+  for (int t = 0; t < slabs; t++) {
+    size_t b = std::min(n, (size_t)t * slab);
+    size_t e = std::min(n, b + slab);
+    size_t ee = std::min(n, e + overlap);
+    if (b >= e) continue;
+    std::vector<rejit::Match> m;
+    h->per_thread[omp_get_thread_num()]->MatchAll(text + b, ee - b, &m);
+    int64_t c = 0;
+    for (size_t i = 0; i < m.size(); i++)
+      if ((size_t)(m[i].begin - text) < e) c++;
+    total += c;
+  }
   return total;
 }
 

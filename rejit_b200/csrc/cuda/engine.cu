@@ -103,8 +103,10 @@ class DeviceContext {
     RJ_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) RJ_TRY(cudaEventCreate(&e));
     RJ_TRY(cudaMallocHost(&h_status, sizeof(PipelineStatus)));
-    if (!counters.Reserve(64, error)) return false;
-    if (!status.Reserve(sizeof(PipelineStatus), error)) return false;
+    // status and the counters share one allocation so that one memset clears both
+    if (!status.Reserve(sizeof(PipelineStatus) + 64, error)) return false;
+    counters.p = static_cast<uint8_t*>(status.p) + ((sizeof(PipelineStatus) + 15) & ~size_t(15));
+    counters.bytes = 0;                 // not owned
     return true;
   }
   bool ReserveDense(uint64_t cap, std::string* error) {
@@ -182,7 +184,9 @@ class DeviceProgram {
     }
     if (ca.strategy == ScanStrategy::DfaFixed) {
       const ScanDfa& d = ca.dfa;
-      if (!Upload(ft.dfa_next, &dfa.next, error) || !Upload(ft.dfa_class, &dfa.byte_class, error)) return false;
+      if (!Upload(ft.dfa_next, &dfa.next, error) || !Upload(ft.dfa_class, &dfa.byte_class, error) ||
+          !Upload(ft.dfa_pair, &dfa.pair, error)) return false;
+      dfa.first_accept = d.first_accept;
       dfa.n_states = d.n_states;
       dfa.n_classes = d.n_classes;
       dfa.first_accept_scaled = d.first_accept * d.n_classes;
@@ -369,11 +373,17 @@ bool ReserveStore(Buffer* b, Buffer* e, Buffer* cnt, const StoreDims& d, std::st
 }
 
 // how many warps of k_dfa_tma fit next to the replicated table
+size_t DfaTmaFixedSmem(const DfaTables& dfa) {
+  return (size_t)dfa.n_states * dfa.n_classes * dfa.n_classes * 128 + (size_t)dfa.n_states * dfa.n_classes * 2 + 16 +
+         256 + 8 * 32 + 256;
+}
 int DfaTmaWarps(const DeviceContext* c, const DfaTables& dfa) {
-  size_t fixed = (size_t)dfa.n_states * dfa.n_classes * 128 + 256 + 8 * 32 + 256;
+  size_t fixed = DfaTmaFixedSmem(dfa);
   if (fixed + 4 * 32 * kDfaRowPitch > c->smem_optin) return 0;
   size_t w = (c->smem_optin - fixed) / (32 * kDfaRowPitch);
-  return (int)std::min<size_t>(w, 24);
+  int cap = 18;
+  if (const char* env = getenv("RJ_DFA_WARPS")) cap = std::max(4, std::min(18, atoi(env)));
+  return (int)std::min<size_t>(w, (size_t)cap);
 }
 
 // Runs scan (+verify) + resolve for one slab whose text is at d_text[0..n).
@@ -401,8 +411,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
   for (int attempt = 0; attempt < 48; ++attempt) {
     unsigned long long* ctr = c->counters.as<unsigned long long>();
     PipelineStatus* d_status = c->status.as<PipelineStatus>();
-    RJ_TRY(cudaMemsetAsync(ctr, 0, 40, s));
-    RJ_TRY(cudaMemsetAsync(d_status, 0, sizeof(PipelineStatus), s));
+    RJ_TRY(cudaMemsetAsync(d_status, 0, ((sizeof(PipelineStatus) + 15) & ~size_t(15)) + 40, s));
     const bool use_fallback = ca.strategy == ScanStrategy::DfaFixed && (dp->dense_mode || tma_warps < 4);
     if (use_fallback && c->cand_cap == 0 && !c->ReserveUnordered(1u << 16, error)) return false;
     uint64_t ocap = d_out ? out_cap : c->out_pairs.bytes / 16;
@@ -465,8 +474,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
           cand.nsub = std::max<uint64_t>(1, (n + kDfaSubBytes - 1) / kDfaSubBytes);
           if (!ReserveStore(&c->sub_b, &c->sub_e, &c->sub_count, {cand.nsub, cand.cap}, error)) return false;
           cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
-          size_t smem = (size_t)dp->dfa.n_states * dp->dfa.n_classes * 128 + 256 + 8 * tma_warps + 256 +
-                        (size_t)tma_warps * 32 * kDfaRowPitch;
+          size_t smem = DfaTmaFixedSmem(dp->dfa) + (size_t)tma_warps * 32 * kDfaRowPitch;
           int blocks = (int)std::min<uint64_t>((cand.nsub + tma_warps - 1) / tma_warps, (uint64_t)c->sm_count);
           k_dfa_tma<<<blocks, tma_warps * 32, smem, s>>>(d_text, n, dp->dfa, slab.own, cand, &d_status->dense);
         } else {

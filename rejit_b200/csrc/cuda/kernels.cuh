@@ -82,8 +82,10 @@ struct PipelineStatus {                // one per call, read back by the host
 struct DfaTables {
   const uint16_t* next;                // [n_states * n_classes], entries pre-multiplied by n_classes
   const uint8_t* byte_class;           // [256]
+  const uint32_t* pair;                // [n_states * n_classes^2]: state after two bytes | bit31 mid-accept
   int n_states, n_classes;
   int first_accept_scaled;             // first accepting state * n_classes
+  int first_accept;                    // first accepting state
   uint32_t match_len;
 };
 
@@ -112,7 +114,6 @@ constexpr uint32_t kWinSubHits = 8;          // needle hits per sub-region of th
 constexpr uint32_t kDfaStreamBytes = 256;    // bytes per lane sub-stream (k_dfa_tma)
 constexpr uint32_t kDfaRowPitch = kDfaStreamBytes + 16;   // 272 = 17 * 16: conflict-free 16-byte rows
 constexpr uint32_t kDfaSubBytes = 32 * kDfaStreamBytes;   // sub-region of one warp
-constexpr int kDfaLaneHits = 4;
 
 // ===========================================================================
 // small device helpers
@@ -293,40 +294,94 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
 // ===========================================================================
 // K2: exact DFA scan for fixed-length, anchor-free patterns (regex-dna).
 // A warp owns a sub-region of 32 x 256 bytes.  Every lane stages ITS OWN row —
-// its 256-byte sub-stream preceded by the 16 bytes before it (the automaton's
-// warm-up: a fixed-length-L automaton entered >= L-1 bytes early is in the same
-// state as one sequential pass) — into shared memory with one TMA bulk copy
-// (cp.async.bulk, completion on the warp's mbarrier).  Rows are 272 bytes apart
-// (17 x 16), so the lanes' 16-byte shared loads are conflict free.  The
-// transition table is replicated per lane (entry e of lane l lives in bank l)
-// and its entries are the shared-memory ADDRESS of the next row, so one step is
-//     class = s_class[byte];  row = *(row + class*128)
-// Accepting rows are the highest addresses; a 16-byte group is replayed only
-// when its running maximum crosses that threshold.  Each lane keeps its (at
-// most four) match ends in registers; at the end of the sub-region a warp scan
-// places them, which yields candidates sorted by construction.
+// its 256-byte sub-stream preceded by the 16 bytes before it — into shared
+// memory with one TMA bulk copy (cp.async.bulk, completion on the warp's
+// mbarrier).  Rows are 272 bytes apart (17 x 16), so the lanes' 16-byte shared
+// loads are conflict free.
+//
+// Each lane runs TWO independent automaton chains (the two 128-byte halves of
+// its row, each entered 16 bytes early: a fixed-length-L automaton entered
+// >= L-1 bytes early is in the same state as one sequential pass), and every
+// chain advances TWO bytes per table lookup: the pair table
+//     entry(state, c1*C + c2) = row address of the state after both bytes,
+//                               bit 31 = "the state in between accepts"
+// is replicated per lane (entry e of lane l lives in bank l: conflict free) and
+// holds shared-memory addresses, so one step is
+//     p = class[b0] * C + class[b1];   row = *(row + p*128)
+// Accepting rows are the highest addresses; a 16-byte group is replayed byte by
+// byte (plain 1-byte table) only when its running maximum crosses that
+// threshold.  Match ends are kept in registers (3 per chain) and placed with a
+// warp scan at the end of the sub-region, so candidates come out sorted.
 // Algorithmic traffic: N bytes read + 16 bytes per match.
 // ===========================================================================
-__global__ void __launch_bounds__(768, 1)
+constexpr int kDfaChainHits = 3;
+
+__device__ __forceinline__ uint32_t Lds32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t Lds8(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 Lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// byte-wise replay of one 16-byte group with the 1-byte table; records the
+// match ends (relative to sub_lo) that fall in (lo_excl, hi_incl]
+__device__ __forceinline__ void DfaReplay(const uint4& v, uint32_t st1, const uint16_t* s_next, const uint8_t* s_class,
+                                          uint32_t acc1, uint64_t p0, uint64_t limit, uint32_t L, uint64_t sub_lo,
+                                          const ScanRange& range, uint32_t* hit, uint32_t& cnt) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  for (int i = 0; i < 16 && p0 + i < limit; ++i) {
+    uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+    st1 = s_next[st1 + s_class[c]];
+    if (st1 >= acc1) {
+      uint64_t e = p0 + i + 1;
+      if (e >= L) {
+        uint64_t s = e - L;
+        if (s >= range.own_begin && s < range.own_end) {
+#pragma unroll
+          for (int q = 0; q < kDfaChainHits; ++q)
+            if (cnt == (uint32_t)q) hit[q] = (uint32_t)(e - sub_lo);
+          ++cnt;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(576, 1)
 k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange range, SubStore out,
           unsigned int* dense_flag) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
-  const int entries = dfa.n_states * dfa.n_classes;
-  // layout: [replicated rows: entries*128][class map: 256][barriers: 8*warps][tiles: warps*32*272]
+  const uint32_t C = (uint32_t)dfa.n_classes;
+  const uint32_t C2 = C * C;
+  const int pair_entries = dfa.n_states * (int)C2;
+  const int next_entries = dfa.n_states * (int)C;
+  // layout: [pair rows: pair_entries*128][1-byte table u16][class map 256][barriers][tiles]
   uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem_raw);
-  uint8_t* s_class = smem_raw + (size_t)entries * 128;
+  uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw + (size_t)pair_entries * 128);
+  uint8_t* s_class = reinterpret_cast<uint8_t*>(s_next) + (((size_t)next_entries * 2 + 15) & ~(size_t)15);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_class + 256);
   uint8_t* s_tiles = reinterpret_cast<uint8_t*>(s_bar + warps_per_cta);
   s_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tiles) + 127) & ~(uintptr_t)127);
   const uint32_t rows_base = SmemAddr(s_rows);
-  for (int i = threadIdx.x; i < entries * 32; i += blockDim.x) {
+  const uint32_t row_stride = C2 * 128u;                               // bytes between the rows of two states
+  for (int i = threadIdx.x; i < pair_entries * 32; i += blockDim.x) {
     int e = i >> 5, l = i & 31;
-    // dfa.next[e] is the next state's row index (state * n_classes)
-    s_rows[e * 32 + l] = rows_base + (uint32_t)dfa.next[e] * 128u + (uint32_t)l * 4u;
+    uint32_t v = dfa.pair[e];
+    s_rows[i] = (rows_base + (v & 0x7FFFFFFFu) * row_stride + (uint32_t)l * 4u) | (v & 0x80000000u);
   }
+  for (int i = threadIdx.x; i < next_entries; i += blockDim.x) s_next[i] = dfa.next[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_class[i] = dfa.byte_class[i];
   uint64_t* bar = s_bar + warp_in_cta;
   if (lane == 0) MbarInit(bar, 1);
@@ -337,7 +392,8 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
   uint8_t* my_row = tile + (size_t)lane * kDfaRowPitch;
   const uint32_t my_row_addr = SmemAddr(my_row);
   const uint32_t lane_base = rows_base + (uint32_t)lane * 4u;          // row of state 0 for this lane
-  const uint32_t acc_addr = lane_base + (uint32_t)dfa.first_accept_scaled * 128u;
+  const uint32_t acc_addr = lane_base + (uint32_t)dfa.first_accept * row_stride;
+  const uint32_t acc1 = (uint32_t)dfa.first_accept_scaled;
   const uint32_t class_base = SmemAddr(s_class);
   const uint32_t L = dfa.match_len;
   const uint64_t gwarp = (uint64_t)blockIdx.x * warps_per_cta + warp_in_cta;
@@ -347,8 +403,8 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
   for (uint64_t sub = gwarp; sub < out.nsub; sub += nwarps) {
     const uint64_t sub_lo = sub * kDfaSubBytes;
     const bool live = sub_lo < n && sub_lo + kDfaSubBytes + L > range.own_begin && sub_lo < range.own_end + L;
-    uint32_t my_cnt = 0;
-    uint32_t hit[kDfaLaneHits] = {0, 0, 0, 0};
+    uint32_t cntA = 0, cntB = 0;
+    uint32_t hitA[kDfaChainHits] = {0, 0, 0}, hitB[kDfaChainHits] = {0, 0, 0};
     if (live) {
       // ---- stage the rows -------------------------------------------------
       const uint64_t a = sub_lo + (uint64_t)lane * kDfaStreamBytes;        // my sub-stream [a, b)
@@ -369,81 +425,94 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
       if (have) TmaLoad1D(my_row + (warm ? 0 : 16), text + src, bytes, bar);
       MbarWait(bar, phase);
       phase ^= 1;
-      // ---- walk my row ------------------------------------------------------
-      if (have) {
-        uint32_t row = lane_base;                 // state 0
-        const uint32_t first_chunk = warm ? 0 : 1;
-        const uint32_t n_chunks = 1 + (uint32_t)((b - a + 15) >> 4);        // warm-up chunk + data chunks
-        for (uint32_t ch = first_chunk; ch < n_chunks; ++ch) {
-          uint4 v;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                       : "r"(my_row_addr + ch * 16));
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-          const uint64_t p0 = a - 16 + (uint64_t)ch * 16;                     // text offset of byte 0 of the chunk
-          const uint32_t row0 = row;
-          uint32_t peak = 0;
-          const bool tail = p0 + 16 > b;
-          if (!tail) {
-            uint32_t cls[16];
+      const bool full = (sub_lo + kDfaSubBytes <= n);                        // warp-uniform
+      if (full) {
+        // ---- two chains, two bytes per lookup ---------------------------------
+        uint32_t rowA = lane_base, rowB = lane_base;
+#pragma unroll 1
+        for (uint32_t ch = 0; ch < 9; ++ch) {
+          const uint4 vA = Lds128(my_row_addr + ch * 16);
+          const uint4 vB = Lds128(my_row_addr + 128 + ch * 16);
+          const uint32_t wA[4] = {vA.x, vA.y, vA.z, vA.w};
+          const uint32_t wB[4] = {vB.x, vB.y, vB.z, vB.w};
+          uint32_t pA[8], pB[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-              asm("ld.shared.u8 %0, [%1];" : "=r"(cls[i]) : "r"(class_base + c));
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              asm("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(row + cls[i] * 128u));
-              peak = max(peak, row);
-            }
-          } else {
-            for (int i = 0; i < 16 && p0 + i < b; ++i) {
-              uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-              uint32_t cls = s_class[c];
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(row + cls * 128u));
-              peak = max(peak, row);
-            }
+          for (int k = 0; k < 8; ++k) {
+            uint32_t a0 = Lds8(class_base + ((wA[k >> 1] >> (16 * (k & 1))) & 0xFFu));
+            uint32_t a1 = Lds8(class_base + ((wA[k >> 1] >> (16 * (k & 1) + 8)) & 0xFFu));
+            uint32_t b0 = Lds8(class_base + ((wB[k >> 1] >> (16 * (k & 1))) & 0xFFu));
+            uint32_t b1 = Lds8(class_base + ((wB[k >> 1] >> (16 * (k & 1) + 8)) & 0xFFu));
+            pA[k] = (a0 * C + a1) * 128u;
+            pB[k] = (b0 * C + b1) * 128u;
           }
-          if (peak >= acc_addr && ch > 0) {
-            // rare: replay the group to find the exact end offsets
-            uint32_t r2 = row0;
-            for (int i = 0; i < 16 && p0 + i < b; ++i) {
-              uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-              uint32_t cls = s_class[c];
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r2) : "r"(r2 + cls * 128u));
-              if (r2 >= acc_addr) {
-                uint64_t e = p0 + i + 1;
-                if (e >= L) {
-                  uint64_t s = e - L;
-                  if (s >= range.own_begin && s < range.own_end) {
+          const uint32_t rowA0 = rowA, rowB0 = rowB;
+          uint32_t peakA = 0, peakB = 0;
 #pragma unroll
-                    for (int q = 0; q < kDfaLaneHits; ++q)
-                      if (my_cnt == (uint32_t)q) hit[q] = (uint32_t)(e - sub_lo);
-                    ++my_cnt;
-                  }
-                }
-              }
-            }
+          for (int k = 0; k < 8; ++k) {
+            uint32_t eA = Lds32(rowA + pA[k]);
+            uint32_t eB = Lds32(rowB + pB[k]);
+            peakA = max(peakA, eA);
+            peakB = max(peakB, eB);
+            rowA = eA & 0x7FFFFFFFu;
+            rowB = eB & 0x7FFFFFFFu;
+          }
+          if (ch == 0) {
+            if (!warm) rowA = lane_base;              // no bytes before the text: chain A starts at its data
+          } else {
+            if (peakA >= acc_addr)
+              DfaReplay(vA, ((rowA0 - lane_base) / row_stride) * C, s_next, s_class, acc1,
+                        a - 16 + (uint64_t)ch * 16, b, L, sub_lo, range, hitA, cntA);
+            if (peakB >= acc_addr)
+              DfaReplay(vB, ((rowB0 - lane_base) / row_stride) * C, s_next, s_class, acc1,
+                        a + 112 + (uint64_t)ch * 16, b, L, sub_lo, range, hitB, cntB);
+          }
+        }
+      } else if (have) {
+        // ---- ragged tail of the text: one chain, one byte per lookup ------------
+        uint32_t st1 = 0;
+        const uint32_t first_chunk = warm ? 0 : 1;
+        const uint32_t n_chunks = 1 + (uint32_t)((b - a + 15) >> 4);
+        for (uint32_t ch = first_chunk; ch < n_chunks; ++ch) {
+          const uint4 v = Lds128(my_row_addr + ch * 16);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          const uint64_t p0 = a - 16 + (uint64_t)ch * 16;
+          if (ch == 0) {
+            for (int i = 0; i < 16; ++i) st1 = s_next[st1 + s_class[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu]];
+          } else {
+            uint32_t before = st1;
+            for (int i = 0; i < 16 && p0 + i < b; ++i) st1 = s_next[st1 + s_class[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu]];
+            // ends in the first half belong to list A, the rest to list B
+            if (p0 + 16 <= a + 128) DfaReplay(v, before, s_next, s_class, acc1, p0, b, L, sub_lo, range, hitA, cntA);
+            else DfaReplay(v, before, s_next, s_class, acc1, p0, b, L, sub_lo, range, hitB, cntB);
           }
         }
       }
       __syncwarp();      // everyone is done with the tile before the next TMA overwrites it
     }
-    // ---- ordered emission: lanes cover increasing offsets ---------------------
+    // ---- ordered emission: lanes cover increasing offsets, A before B ---------
+    const uint32_t my_cnt = cntA + cntB;
     if (__any_sync(kFullMask, my_cnt != 0)) {
-      bool over = __any_sync(kFullMask, my_cnt > kDfaLaneHits);
-      uint32_t c = my_cnt > kDfaLaneHits ? kDfaLaneHits : my_cnt;
+      bool over = __any_sync(kFullMask, cntA > kDfaChainHits || cntB > kDfaChainHits);
+      uint32_t cA = cntA > kDfaChainHits ? kDfaChainHits : cntA;
+      uint32_t cB = cntB > kDfaChainHits ? kDfaChainHits : cntB;
+      uint32_t c = cA + cB;
       uint32_t incl = WarpInclusiveScan(c);
       uint32_t total = __shfl_sync(kFullMask, incl, 31);
       uint32_t idx = incl - c;
 #pragma unroll
-      for (int q = 0; q < kDfaLaneHits; ++q) {
-        if (q < (int)c) {
-          if (idx + q < out.cap) {
-            uint64_t e = sub_lo + hit[q];
-            out.begin[sub * out.cap + idx + q] = e - L;
-            out.end[sub * out.cap + idx + q] = e;
-          }
+      for (int q = 0; q < kDfaChainHits; ++q) {
+        if (q < (int)cA && idx + q < out.cap) {
+          uint64_t e = sub_lo + hitA[q];
+          out.begin[sub * out.cap + idx + q] = e - L;
+          out.end[sub * out.cap + idx + q] = e;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kDfaChainHits; ++q) {
+        if (q < (int)cB && idx + cA + q < out.cap) {
+          uint64_t e = sub_lo + hitB[q];
+          out.begin[sub * out.cap + idx + cA + q] = e - L;
+          out.end[sub * out.cap + idx + cA + q] = e;
         }
       }
       if (lane == 0) {
@@ -650,30 +719,41 @@ __device__ __forceinline__ uint64_t BlockExclusiveMax(uint64_t v, uint64_t init,
 
 // Concatenates the sub-regions' slot ranges into a dense (sorted) list.
 // Returns false (uniformly) on overflow / dense marker; *m_out = total.
+// The counts of kGatherBatch blocks of 1024 sub-regions are loaded up front so
+// that their global-memory latency is paid once per batch.
+constexpr int kGatherBatch = 8;
+
 __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseList& dense, PipelineStatus* status,
                                                uint32_t* s_warp, unsigned long long* m_out) {
-  __shared__ unsigned int s_flags[3];          // [0] max count, [1] dense marker, [2] unused
-  if (threadIdx.x < 3) s_flags[threadIdx.x] = 0;
+  __shared__ unsigned int s_flags[2];          // [0] max count, [1] dense marker
+  if (threadIdx.x < 2) s_flags[threadIdx.x] = 0;
   __syncthreads();
   unsigned long long base = 0;
-  for (uint64_t blk = 0; blk < st.nsub; blk += blockDim.x) {
-    uint64_t sub = blk + threadIdx.x;
-    uint32_t c = 0;
-    if (sub < st.nsub) {
-      c = st.count[sub];
-      if (c == kLaneListOverflow) { atomicOr(&s_flags[1], 1u); c = 0; }
-      else if (c > st.cap) { atomicMax(&s_flags[0], c); c = st.cap; }
+  for (uint64_t blk0 = 0; blk0 < st.nsub; blk0 += (uint64_t)kGatherBatch * blockDim.x) {
+    uint32_t c[kGatherBatch];
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) {
+      uint64_t sub = blk0 + (uint64_t)u * blockDim.x + threadIdx.x;
+      c[u] = (sub < st.nsub) ? st.count[sub] : 0u;
     }
-    uint32_t total;
-    uint32_t off = BlockExclusiveSum(c, &total, s_warp);
-    for (uint32_t i = 0; i < c; ++i) {
-      unsigned long long at = base + off + i;
-      if (at < dense.cap) {
-        dense.begin[at] = st.begin[sub * st.cap + i];
-        dense.end[at] = st.end[sub * st.cap + i];
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) {
+      if (blk0 + (uint64_t)u * blockDim.x >= st.nsub) break;            // uniform
+      uint64_t sub = blk0 + (uint64_t)u * blockDim.x + threadIdx.x;
+      uint32_t cu = c[u];
+      if (cu == kLaneListOverflow) { atomicOr(&s_flags[1], 1u); cu = 0; }
+      else if (cu > st.cap) { atomicMax(&s_flags[0], cu); cu = st.cap; }
+      uint32_t total;
+      uint32_t off = BlockExclusiveSum(cu, &total, s_warp);
+      for (uint32_t i = 0; i < cu; ++i) {
+        unsigned long long at = base + off + i;
+        if (at < dense.cap) {
+          dense.begin[at] = st.begin[sub * st.cap + i];
+          dense.end[at] = st.end[sub * st.cap + i];
+        }
       }
+      base += total;
     }
-    base += total;
   }
   __syncthreads();
   *m_out = base;
@@ -740,6 +820,31 @@ k_resolve_ordered(SubStore st, DenseList dense, ResolveScratch rs, Carry carry_i
   const uint32_t i0 = min(M, threadIdx.x * ipt), i1 = min(M, i0 + ipt);
   const uint64_t* b = dense.begin;
   const uint64_t* e = dense.end;
+  if (!fa.enabled) {
+    // Fast path: when no candidate begins before its predecessor ends (and none
+    // is empty), every candidate restarts the chain, i.e. the matches ARE the
+    // candidates.  This is the common case (sparse, fixed-length matches).
+    int bad = 0;
+    for (uint32_t i = i0; i < i1; ++i) {
+      uint64_t prev_end = (i == 0) ? carry_in.cur : e[i - 1];
+      bad |= (prev_end > b[i]) | (e[i] <= b[i]);
+      if (i + 1 < M && e[i] > e[i + 1]) bad = 1;               // ends not monotone: need the max-scan
+    }
+    if (!__syncthreads_or(bad)) {
+      for (uint32_t i = i0; i < i1; ++i) {
+        if (i < out_cap) {
+          out_pairs[2 * (uint64_t)i] = b[i] + base_offset;
+          out_pairs[2 * (uint64_t)i + 1] = e[i] + base_offset;
+        }
+      }
+      if (threadIdx.x == 0) {
+        status->n_matches = M;
+        status->carry_cur = M ? e[M - 1] : carry_in.cur;
+        status->carry_tail = M ? e[M - 1] : carry_in.tail;
+      }
+      return;
+    }
+  }
   // reach
   uint64_t local = 0;
   for (uint32_t i = i0; i < i1; ++i) local = e[i] > local ? e[i] : local;

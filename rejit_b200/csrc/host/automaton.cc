@@ -468,6 +468,17 @@ void FlattenTables(const CompiledAutomaton& ca, FlatTables* out) {
     for (size_t i = 0; i < d.next.size(); ++i)
       out->dfa_next[i] = static_cast<uint16_t>(d.next[i] * d.n_classes);
     out->dfa_class.assign(d.byte_class.begin(), d.byte_class.end());
+    const int C = d.n_classes;
+    out->dfa_pair.assign(static_cast<size_t>(d.n_states) * C * C, 0);
+    for (int s = 0; s < d.n_states; ++s)
+      for (int c1 = 0; c1 < C; ++c1) {
+        int mid = d.next[static_cast<size_t>(s) * C + c1];
+        for (int c2 = 0; c2 < C; ++c2) {
+          uint32_t fin = d.next[static_cast<size_t>(mid) * C + c2];
+          if (mid >= d.first_accept) fin |= 0x80000000u;
+          out->dfa_pair[(static_cast<size_t>(s) * C + c1) * C + c2] = fin;
+        }
+      }
   }
 }
 

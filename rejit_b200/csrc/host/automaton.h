@@ -100,6 +100,10 @@ struct FlatTables {
   uint8_t accept_empty[4] = {0, 0, 0, 0};
   std::vector<uint16_t> dfa_next;    // [states*classes], entries pre-multiplied by classes
   std::vector<uint8_t> dfa_class;    // [256]
+  // two-byte steps: [state][c1 * classes + c2] = state after both bytes, bit 31
+  // set when the state after the FIRST byte is accepting (a match ends between
+  // the two bytes)
+  std::vector<uint32_t> dfa_pair;
 };
 void FlattenTables(const CompiledAutomaton& ca, FlatTables* out);
 

@@ -11,12 +11,15 @@ echo "== pytest gpu" ; timeout 2400 python -m pytest tests -m gpu -q -x --timeou
 echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench_ours.json
 tail -5 gpurun_out/bench.err
 echo "== bench reference" ; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>> gpurun_out/bench.err | tee gpurun_out/bench_reference.json
+if [ "${RJ_SWEEP:-0}" = "1" ]; then
+for w in 6 10 14 18; do echo "== sweep RJ_DFA_WARPS=$w"; RJ_DFA_WARPS=$w timeout 300 python bench.py --steps 3 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['frac'])"; done
+fi
 if [ "${RJ_PROFILE:-1}" = "1" ]; then
 echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_bench.log 2>&1
 tail -3 gpurun_out/ncu_bench.log
 echo "== ncu full dfa"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dfa_scan -s 9 -c 2 -o gpurun_out/prof_dfa -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dfa_tma -s 9 -c 2 -o gpurun_out/prof_dfa -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 fi
 ls -la gpurun_out
