@@ -141,6 +141,17 @@ int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, con
                                     const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
                                     rejit_b200_stats* stats, char* err, size_t err_length);
 
+/* Upload-once text: one host-to-device copy, then any number of patterns are
+ * matched against the resident copy (regex-dna counts nine patterns over one
+ * sequence); each match call copies only its match list back.                 */
+typedef struct rejit_b200_text rejit_b200_text;
+rejit_b200_text* rejit_b200_text_upload(int device, const char* text, size_t text_length,
+                                        char* err, size_t err_length);
+void rejit_b200_text_free(rejit_b200_text* text);
+int64_t rejit_b200_match_all_text(rejit_b200_program* program, const rejit_b200_text* text,
+                                  uint64_t** out_pairs, rejit_b200_stats* stats,
+                                  char* err, size_t err_length);
+
 /* Slab variant for one-process-per-GPU sharding: only matches that BEGIN in
  * [own_begin, own_end) of the buffer are reported (own_end > text_length means
  * "to the end, including the empty match at text_length"); the buffer should

@@ -49,6 +49,7 @@ EXPORTED = [
     "rejit_b200_device_alloc", "rejit_b200_device_free", "rejit_b200_pinned_alloc",
     "rejit_b200_pinned_free", "rejit_b200_copy_to_device", "rejit_b200_copy_from_device",
     "rejit_b200_flush_l2", "rejit_b200_match_all_device", "rejit_b200_match_all_device_slab", "rejit_b200_free",
+    "rejit_b200_text_upload", "rejit_b200_text_free", "rejit_b200_match_all_text",
 ]
 
 
@@ -101,6 +102,11 @@ def lib():
                                                    ctypes.POINTER(Carry), ctypes.POINTER(Stats), cp, sz]
     L.rejit_b200_match_all_device_slab.restype = ctypes.c_int64
     L.rejit_b200_free.argtypes = [vp]
+    L.rejit_b200_text_upload.argtypes = [ctypes.c_int, vp, sz, cp, sz]
+    L.rejit_b200_text_upload.restype = vp
+    L.rejit_b200_text_free.argtypes = [vp]
+    L.rejit_b200_match_all_text.argtypes = [vp, vp, ctypes.POINTER(u64p), ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_match_all_text.restype = ctypes.c_int64
     _lib = L
     return L
 

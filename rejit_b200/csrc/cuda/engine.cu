@@ -379,8 +379,8 @@ size_t DfaTmaFixedSmem(const DfaTables& dfa) {
 }
 int DfaTmaWarps(const DeviceContext* c, const DfaTables& dfa) {
   size_t fixed = DfaTmaFixedSmem(dfa);
-  if (fixed + 4 * 32 * kDfaRowPitch > c->smem_optin) return 0;
-  size_t w = (c->smem_optin - fixed) / (32 * kDfaRowPitch);
+  if (fixed + 4 * kDfaTileBytes > c->smem_optin) return 0;
+  size_t w = (c->smem_optin - fixed) / kDfaTileBytes;
   int cap = 18;
   if (const char* env = getenv("RJ_DFA_WARPS")) cap = std::max(4, std::min(18, atoi(env)));
   return (int)std::min<size_t>(w, (size_t)cap);
@@ -474,9 +474,9 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
           cand.nsub = std::max<uint64_t>(1, (n + kDfaSubBytes - 1) / kDfaSubBytes);
           if (!ReserveStore(&c->sub_b, &c->sub_e, &c->sub_count, {cand.nsub, cand.cap}, error)) return false;
           cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
-          size_t smem = DfaTmaFixedSmem(dp->dfa) + (size_t)tma_warps * 32 * kDfaRowPitch;
+          size_t smem = DfaTmaFixedSmem(dp->dfa) + (size_t)tma_warps * kDfaTileBytes;
           int blocks = (int)std::min<uint64_t>((cand.nsub + tma_warps - 1) / tma_warps, (uint64_t)c->sm_count);
-          k_dfa_tma<<<blocks, tma_warps * 32, smem, s>>>(d_text, n, dp->dfa, slab.own, cand, &d_status->dense);
+          k_dfa_tma<<<blocks, tma_warps * 32, smem, s>>>(d_text, n, dp->dfa, slab.own, cand, &d_status->dense, ctr + 0);
         } else {
           ordered = false;
           CandBuf un{c->cand_b.as<uint64_t>(), c->cand_e.as<uint64_t>(), ctr, c->cand_cap};
@@ -645,6 +645,30 @@ int64_t MatchAllHost(int device, Program* prog, const uint8_t* text, uint64_t n,
   uint64_t cnt = v.size() / 2;
   *pairs = static_cast<uint64_t*>(malloc(std::max<size_t>(v.size() * 8, 8)));
   if (cnt) memcpy(*pairs, v.data(), v.size() * 8);
+  return (int64_t)cnt;
+}
+
+int64_t MatchAllResident(int device, Program* prog, const uint8_t* d_text, uint64_t n, uint64_t** pairs,
+                         RunStats* stats, std::string* error) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return -1;
+  DeviceProgram* dp = prog->OnDevice(device, error);
+  if (!dp) return -1;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slab slab{{0, n + 1}, 0};
+  PipelineStatus st;
+  Carry in;
+  if (!RunPipeline(c, prog, dp, d_text, n, slab, in, nullptr, 0, &st, stats, error)) return -1;
+  uint64_t cnt = st.n_matches;
+  *pairs = static_cast<uint64_t*>(malloc(std::max<size_t>(cnt * 16, 8)));
+  if (cnt) {
+    if (!Check(cudaMemcpyAsync(*pairs, c->out_pairs.p, cnt * 16, cudaMemcpyDeviceToHost, c->stream), "D2H", error) ||
+        !Check(cudaStreamSynchronize(c->stream), "sync", error)) {
+      free(*pairs);
+      *pairs = nullptr;
+      return -1;
+    }
+  }
   return (int64_t)cnt;
 }
 

@@ -76,6 +76,11 @@ int64_t MatchAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_
 int64_t MatchAllHost(int device, Program* prog, const uint8_t* text, uint64_t n,
                      uint64_t** pairs, RunStats* stats, std::string* error);
 
+// MatchAll over text already resident on `device` (uploaded once, searched by
+// several patterns); only the match list travels back.
+int64_t MatchAllResident(int device, Program* prog, const uint8_t* d_text, uint64_t n, uint64_t** pairs,
+                         RunStats* stats, std::string* error);
+
 // Same, with the text cut into `n_gpus` contiguous slabs, one per device, each
 // scanned with a right halo; chains are stitched at the slab edges (§8e).
 int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int n_gpus,

@@ -111,9 +111,10 @@ constexpr int kOrderedResolveMax = 16384;    // one-CTA ordered resolve
 constexpr uint32_t kLitSubBytes = 16384;     // sub-region of the literal scan (32 pieces)
 constexpr uint32_t kGenSubOffsets = 2048;    // sub-region of the generic scan
 constexpr uint32_t kWinSubHits = 8;          // needle hits per sub-region of the window verify
-constexpr uint32_t kDfaStreamBytes = 256;    // bytes per lane sub-stream (k_dfa_tma)
-constexpr uint32_t kDfaRowPitch = kDfaStreamBytes + 16;   // 272 = 17 * 16: conflict-free 16-byte rows
-constexpr uint32_t kDfaSubBytes = 32 * kDfaStreamBytes;   // sub-region of one warp
+constexpr uint32_t kDfaStreamBytes = 272;    // bytes per lane sub-stream (k_dfa_tma): 17 * 16, so that the
+                                             // lanes' 16-byte shared loads from a DENSE tile are conflict free
+constexpr uint32_t kDfaSubBytes = 32 * kDfaStreamBytes;   // sub-region of one warp (8704 bytes)
+constexpr uint32_t kDfaTileBytes = kDfaSubBytes + 16 + 112;   // + the 16 bytes before it, padded to 128
 
 // ===========================================================================
 // small device helpers
@@ -293,14 +294,14 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
 
 // ===========================================================================
 // K2: exact DFA scan for fixed-length, anchor-free patterns (regex-dna).
-// A warp owns a sub-region of 32 x 256 bytes.  Every lane stages ITS OWN row —
-// its 256-byte sub-stream preceded by the 16 bytes before it — into shared
-// memory with one TMA bulk copy (cp.async.bulk, completion on the warp's
-// mbarrier).  Rows are 272 bytes apart (17 x 16), so the lanes' 16-byte shared
-// loads are conflict free.
+// A warp owns a sub-region of 32 x 272 bytes, handed out dynamically in order.
+// The sub-region and the 16 bytes before it are staged into shared memory with
+// ONE TMA bulk copy (cp.async.bulk, completion on the warp's mbarrier); lane l
+// walks bytes [272 l, 272 l + 272) of it.  272 = 17 x 16, so the lanes' 16-byte
+// shared loads from the dense tile are conflict free.
 //
-// Each lane runs TWO independent automaton chains (the two 128-byte halves of
-// its row, each entered 16 bytes early: a fixed-length-L automaton entered
+// Each lane runs TWO independent automaton chains (144 + 128 bytes of its
+// sub-stream, each entered 16 bytes early: a fixed-length-L automaton entered
 // >= L-1 bytes early is in the same state as one sequential pass), and every
 // chain advances TWO bytes per table lookup: the pair table
 //     entry(state, c1*C + c2) = row address of the state after both bytes,
@@ -358,7 +359,7 @@ __device__ __forceinline__ void DfaReplay(const uint4& v, uint32_t st1, const ui
 
 __global__ void __launch_bounds__(576, 1)
 k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange range, SubStore out,
-          unsigned int* dense_flag) {
+          unsigned int* dense_flag, unsigned long long* work_counter) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -376,72 +377,77 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
   s_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tiles) + 127) & ~(uintptr_t)127);
   const uint32_t rows_base = SmemAddr(s_rows);
   const uint32_t row_stride = C2 * 128u;                               // bytes between the rows of two states
-  for (int i = threadIdx.x; i < pair_entries * 32; i += blockDim.x) {
-    int e = i >> 5, l = i & 31;
-    uint32_t v = dfa.pair[e];
-    s_rows[i] = (rows_base + (v & 0x7FFFFFFFu) * row_stride + (uint32_t)l * 4u) | (v & 0x80000000u);
-  }
+  // the compact pair table is first copied (coalesced, one round trip) into the
+  // not-yet-used tile area, then expanded into the per-lane replicated rows
+  uint32_t* s_tmp = reinterpret_cast<uint32_t*>(s_tiles);
+  for (int i = threadIdx.x; i < pair_entries; i += blockDim.x) s_tmp[i] = dfa.pair[i];
   for (int i = threadIdx.x; i < next_entries; i += blockDim.x) s_next[i] = dfa.next[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_class[i] = dfa.byte_class[i];
   uint64_t* bar = s_bar + warp_in_cta;
   if (lane == 0) MbarInit(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
+  for (int i = threadIdx.x; i < pair_entries * 32; i += blockDim.x) {
+    uint32_t v = s_tmp[i >> 5];
+    s_rows[i] = (rows_base + (v & 0x7FFFFFFFu) * row_stride + (uint32_t)(i & 31) * 4u) | (v & 0x80000000u);
+  }
+  __syncthreads();
 
-  uint8_t* tile = s_tiles + (size_t)warp_in_cta * (32 * kDfaRowPitch);
-  uint8_t* my_row = tile + (size_t)lane * kDfaRowPitch;
-  const uint32_t my_row_addr = SmemAddr(my_row);
+  // tile of this warp: [16 bytes before the sub-region][32 x 272 bytes]; lane l's
+  // sub-stream starts at byte 16 + 272*l, its warm-up chunk at 272*l
+  uint8_t* tile = s_tiles + (size_t)warp_in_cta * kDfaTileBytes;
+  const uint32_t my_warm_addr = SmemAddr(tile) + (uint32_t)lane * kDfaStreamBytes;
   const uint32_t lane_base = rows_base + (uint32_t)lane * 4u;          // row of state 0 for this lane
   const uint32_t acc_addr = lane_base + (uint32_t)dfa.first_accept * row_stride;
   const uint32_t acc1 = (uint32_t)dfa.first_accept_scaled;
   const uint32_t class_base = SmemAddr(s_class);
   const uint32_t L = dfa.match_len;
-  const uint64_t gwarp = (uint64_t)blockIdx.x * warps_per_cta + warp_in_cta;
-  const uint64_t nwarps = (uint64_t)gridDim.x * warps_per_cta;
   uint32_t phase = 0;
 
-  for (uint64_t sub = gwarp; sub < out.nsub; sub += nwarps) {
+  for (;;) {
+    // dynamic scheduling: sub-regions are handed out in order, one per request
+    unsigned long long sub = 0;
+    if (lane == 0) sub = atomicAdd(work_counter, 1ull);
+    sub = __shfl_sync(kFullMask, sub, 0);
+    if (sub >= out.nsub) break;
     const uint64_t sub_lo = sub * kDfaSubBytes;
     const bool live = sub_lo < n && sub_lo + kDfaSubBytes + L > range.own_begin && sub_lo < range.own_end + L;
     uint32_t cntA = 0, cntB = 0;
     uint32_t hitA[kDfaChainHits] = {0, 0, 0}, hitB[kDfaChainHits] = {0, 0, 0};
     if (live) {
-      // ---- stage the rows -------------------------------------------------
-      const uint64_t a = sub_lo + (uint64_t)lane * kDfaStreamBytes;        // my sub-stream [a, b)
-      const uint64_t b = (a + kDfaStreamBytes < n) ? a + kDfaStreamBytes : n;
-      const bool have = a < n;
-      const bool warm = have && a >= 16;
-      const uint64_t src = warm ? a - 16 : a;
-      uint32_t bytes = 0;
-      if (have) {
-        uint64_t end16 = (b + 15) & ~15ull;                                  // stays inside the last 16-byte block
-        bytes = (uint32_t)(end16 - src);
+      // ---- stage the tile: ONE bulk copy per warp ---------------------------
+      const bool sub_warm = sub_lo >= 16;
+      if (lane == 0) {
+        const uint64_t src = sub_warm ? sub_lo - 16 : 0;
+        uint64_t end = sub_lo + kDfaSubBytes;
+        if (end > n) end = (n + 15) & ~15ull;                              // stays inside the last 16-byte block
+        const uint32_t bytes = (uint32_t)(end - src);
+        MbarExpectTx(bar, bytes);
+        TmaLoad1D(tile + (sub_warm ? 0 : 16), text + src, bytes, bar);
       }
-      uint32_t total = bytes;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(kFullMask, total, d);
-      if (lane == 0) MbarExpectTx(bar, total);
-      __syncwarp();
-      if (have) TmaLoad1D(my_row + (warm ? 0 : 16), text + src, bytes, bar);
       MbarWait(bar, phase);
       phase ^= 1;
-      const bool full = (sub_lo + kDfaSubBytes <= n);                        // warp-uniform
-      if (full) {
-        // ---- two chains, two bytes per lookup ---------------------------------
+      const uint64_t a = sub_lo + (uint64_t)lane * kDfaStreamBytes;        // my sub-stream [a, b)
+      const uint64_t b = (a + kDfaStreamBytes < n) ? a + kDfaStreamBytes : n;
+      if (a < n) {
+        // ---- two chains (144 + 128 bytes), two bytes per lookup ----------------
+        // bytes past the end of the text are stale shared memory: they can only
+        // produce "ends" beyond b, which the replay discards
+        const bool warm = a >= 16;
         uint32_t rowA = lane_base, rowB = lane_base;
 #pragma unroll 1
-        for (uint32_t ch = 0; ch < 9; ++ch) {
-          const uint4 vA = Lds128(my_row_addr + ch * 16);
-          const uint4 vB = Lds128(my_row_addr + 128 + ch * 16);
+        for (uint32_t it = 0; it < 10; ++it) {
+          const uint4 vA = Lds128(my_warm_addr + it * 16);
+          const uint4 vB = Lds128(my_warm_addr + (it < 9 ? (9 + it) * 16 : 0));
           const uint32_t wA[4] = {vA.x, vA.y, vA.z, vA.w};
           const uint32_t wB[4] = {vB.x, vB.y, vB.z, vB.w};
           uint32_t pA[8], pB[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            uint32_t a0 = Lds8(class_base + ((wA[k >> 1] >> (16 * (k & 1))) & 0xFFu));
-            uint32_t a1 = Lds8(class_base + ((wA[k >> 1] >> (16 * (k & 1) + 8)) & 0xFFu));
-            uint32_t b0 = Lds8(class_base + ((wB[k >> 1] >> (16 * (k & 1))) & 0xFFu));
-            uint32_t b1 = Lds8(class_base + ((wB[k >> 1] >> (16 * (k & 1) + 8)) & 0xFFu));
+            uint32_t a0 = Lds8(class_base + __byte_perm(wA[k >> 1], 0, 0x4440 + 2 * (k & 1)));
+            uint32_t a1 = Lds8(class_base + __byte_perm(wA[k >> 1], 0, 0x4441 + 2 * (k & 1)));
+            uint32_t b0 = Lds8(class_base + __byte_perm(wB[k >> 1], 0, 0x4440 + 2 * (k & 1)));
+            uint32_t b1 = Lds8(class_base + __byte_perm(wB[k >> 1], 0, 0x4441 + 2 * (k & 1)));
             pA[k] = (a0 * C + a1) * 128u;
             pB[k] = (b0 * C + b1) * 128u;
           }
@@ -456,34 +462,15 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
             rowA = eA & 0x7FFFFFFFu;
             rowB = eB & 0x7FFFFFFFu;
           }
-          if (ch == 0) {
+          if (it == 0) {
             if (!warm) rowA = lane_base;              // no bytes before the text: chain A starts at its data
           } else {
             if (peakA >= acc_addr)
               DfaReplay(vA, ((rowA0 - lane_base) / row_stride) * C, s_next, s_class, acc1,
-                        a - 16 + (uint64_t)ch * 16, b, L, sub_lo, range, hitA, cntA);
-            if (peakB >= acc_addr)
+                        a - 16 + (uint64_t)it * 16, b, L, sub_lo, range, hitA, cntA);
+            if (it < 9 && peakB >= acc_addr)
               DfaReplay(vB, ((rowB0 - lane_base) / row_stride) * C, s_next, s_class, acc1,
-                        a + 112 + (uint64_t)ch * 16, b, L, sub_lo, range, hitB, cntB);
-          }
-        }
-      } else if (have) {
-        // ---- ragged tail of the text: one chain, one byte per lookup ------------
-        uint32_t st1 = 0;
-        const uint32_t first_chunk = warm ? 0 : 1;
-        const uint32_t n_chunks = 1 + (uint32_t)((b - a + 15) >> 4);
-        for (uint32_t ch = first_chunk; ch < n_chunks; ++ch) {
-          const uint4 v = Lds128(my_row_addr + ch * 16);
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-          const uint64_t p0 = a - 16 + (uint64_t)ch * 16;
-          if (ch == 0) {
-            for (int i = 0; i < 16; ++i) st1 = s_next[st1 + s_class[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu]];
-          } else {
-            uint32_t before = st1;
-            for (int i = 0; i < 16 && p0 + i < b; ++i) st1 = s_next[st1 + s_class[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu]];
-            // ends in the first half belong to list A, the rest to list B
-            if (p0 + 16 <= a + 128) DfaReplay(v, before, s_next, s_class, acc1, p0, b, L, sub_lo, range, hitA, cntA);
-            else DfaReplay(v, before, s_next, s_class, acc1, p0, b, L, sub_lo, range, hitB, cntB);
+                        a + 128 + (uint64_t)it * 16, b, L, sub_lo, range, hitB, cntB);
           }
         }
       }

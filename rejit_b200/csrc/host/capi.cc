@@ -114,6 +114,12 @@ struct rejit_b200_program {
   Program* prog;
 };
 
+struct rejit_b200_text {
+  int device;
+  void* d_ptr;
+  size_t length;
+};
+
 extern "C" {
 
 int rejit_b200_parse(const char* pattern, size_t pattern_length, int parser_opt,
@@ -294,6 +300,42 @@ int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, con
   if (r < 0) { SetErr(err, err_length, error); return -1; }
   if (carry_out) { carry_out->cur = out.cur; carry_out->tail = out.tail; }
   FillStats(rs, stats);
+  return r;
+}
+
+rejit_b200_text* rejit_b200_text_upload(int device, const char* text, size_t text_length, char* err,
+                                        size_t err_length) {
+  std::string error;
+  void* d = DeviceAlloc(device, text_length ? text_length : 1, &error);
+  if (!d) { SetErr(err, err_length, error); return nullptr; }
+  if (text_length && !CopyToDevice(device, d, text, text_length, &error)) {
+    DeviceFree(device, d);
+    SetErr(err, err_length, error);
+    return nullptr;
+  }
+  rejit_b200_text* t = new rejit_b200_text;
+  t->device = device;
+  t->d_ptr = d;
+  t->length = text_length;
+  return t;
+}
+
+void rejit_b200_text_free(rejit_b200_text* text) {
+  if (!text) return;
+  DeviceFree(text->device, text->d_ptr);
+  delete text;
+}
+
+int64_t rejit_b200_match_all_text(rejit_b200_program* program, const rejit_b200_text* text, uint64_t** out_pairs,
+                                  rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  RunStats rs;
+  uint64_t* pairs = nullptr;
+  int64_t r = MatchAllResident(text->device, program->prog, static_cast<const uint8_t*>(text->d_ptr), text->length,
+                               &pairs, stats ? &rs : nullptr, &error);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  FillStats(rs, stats);
+  if (out_pairs) *out_pairs = pairs; else free(pairs);
   return r;
 }
 

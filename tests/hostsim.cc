@@ -60,23 +60,43 @@ void ScanLiteral(const std::vector<uint8_t>& needle, const uint8_t* text, uint64
     if (memcmp(text + p, needle.data(), m) == 0) out->push_back({p, p + m});
 }
 
-// Emulates k_dfa_scan: independent sub-streams with a rounded-up warm-up.
-void ScanDfaStreams(const Compiled& c, const uint8_t* text, uint64_t n, uint32_t stream_bytes, Cands* out) {
+// Emulates k_dfa_tma: every 272-byte lane stream is walked as two chains
+// (144 + 128 bytes), each entered 16 bytes early from the start state, two
+// bytes per step through the pair table (bit 31 = accept between the bytes).
+void ScanDfaStreams(const Compiled& c, const uint8_t* text, uint64_t n, uint32_t, Cands* out) {
   const ScanDfa& d = c.ca.dfa;
   const uint32_t L = (uint32_t)d.match_len;
-  const uint32_t warm = (L - 1 + 15) & ~15u;
+  const uint32_t C = (uint32_t)d.n_classes;
   const uint32_t acc = (uint32_t)(d.first_accept * d.n_classes);
-  uint64_t n_streams = (n + stream_bytes - 1) / stream_bytes;
-  for (uint64_t sidx = 0; sidx < n_streams; ++sidx) {
-    uint64_t a = sidx * stream_bytes;
-    uint64_t b = std::min<uint64_t>(n, a + stream_bytes);
-    uint64_t p = (a >= warm) ? a - warm : 0;
-    uint32_t state = 0;
-    for (; p < b; ++p) {
-      state = c.ft.dfa_next[state + c.ft.dfa_class[text[p]]];
-      if (state >= acc) {
-        uint64_t e = p + 1;
-        if (e > a && e >= L) out->push_back({e - L, e});
+  const uint64_t kStream = 272;
+  for (uint64_t a0 = 0; a0 < n; a0 += kStream) {
+    const uint64_t seg[3] = {a0, a0 + 144, a0 + kStream};
+    for (int h = 0; h < 2; ++h) {
+      uint64_t a = seg[h], b = std::min<uint64_t>(n, seg[h + 1]);
+      if (a >= n) break;
+      uint64_t p = a >= 16 ? a - 16 : 0;
+      // the kernel steps in byte PAIRS from a 16-byte aligned start; emulate the
+      // pair table and cross-check it against the single-byte table
+      uint32_t state = 0;          // state id
+      while (p < b) {
+        uint32_t c1 = c.ft.dfa_class[text[p]];
+        uint32_t c2 = (p + 1 < n) ? c.ft.dfa_class[text[p + 1]] : 0;
+        uint32_t one = c.ft.dfa_next[state * C + c1];                 // pre-multiplied
+        uint32_t ent = c.ft.dfa_pair[(state * C + c1) * C + c2];
+        bool mid_acc = one >= acc;
+        if (mid_acc != ((ent & 0x80000000u) != 0)) { out->push_back({~0ull, ~0ull}); return; }
+        if (mid_acc) {
+          uint64_t e = p + 1;
+          if (e > a && e <= b && e >= L) out->push_back({e - L, e});
+        }
+        uint32_t two = c.ft.dfa_next[one + c2];
+        if ((two / C) != (ent & 0x7FFFFFFFu) && p + 1 < n) { out->push_back({~0ull, ~0ull}); return; }
+        if (two >= acc) {
+          uint64_t e = p + 2;
+          if (e > a && e <= b && e >= L) out->push_back({e - L, e});
+        }
+        state = two / C;
+        p += 2;
       }
     }
   }
