@@ -22,6 +22,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -90,7 +91,9 @@ class DeviceContext {
   uint64_t scratch_cap = 0;
   Buffer fscratch;                    // label scratch for re-entrant patterns
   Buffer flush;
-  PipelineStatus* h_status = nullptr; // pinned
+  PipelineStatus* h_status = nullptr; // pinned + mapped: the resolve kernel writes it, the host spins on seq
+  PipelineStatus* h_status_dev = nullptr;   // device view of h_status
+  unsigned int call_seq = 0;
   bool attr_done = false;
 
   bool Init(int dev, std::string* error) {
@@ -102,7 +105,9 @@ class DeviceContext {
     smem_optin = prop.sharedMemPerBlockOptin;
     RJ_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) RJ_TRY(cudaEventCreate(&e));
-    RJ_TRY(cudaMallocHost(&h_status, sizeof(PipelineStatus)));
+    RJ_TRY(cudaHostAlloc(&h_status, sizeof(PipelineStatus), cudaHostAllocMapped));
+    memset(h_status, 0, sizeof(PipelineStatus));
+    RJ_TRY(cudaHostGetDevicePointer(&h_status_dev, h_status, 0));
     // status and the counters share one allocation so that one memset clears both
     if (!status.Reserve(sizeof(PipelineStatus) + 64, error)) return false;
     counters.p = static_cast<uint8_t*>(status.p) + ((sizeof(PipelineStatus) + 15) & ~size_t(15));
@@ -459,7 +464,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         int blocks = (int)std::min<uint64_t>((hs.nsub + 7) / 8, (uint64_t)grid_full);
         k_lit_scan<4><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, hit_range, hs);
         if (stats) cudaEventRecord(c->ev[1], s);
-        k_gather_hits<<<1, 1024, 0, s>>>(hs, hits, d_status);
+        k_gather_hits<<<1, 512, 0, s>>>(hs, hits, d_status);
         cand.cap = kWinSubHits * wsize;
         cand.nsub = (c->hits_cap + kWinSubHits - 1) / kWinSubHits;
         if (!ReserveStore(&c->sub_b, &c->sub_e, &c->sub_count, {cand.nsub, cand.cap}, error)) return false;
@@ -500,17 +505,35 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       }
     }
     if (stats && ca.strategy != ScanStrategy::LiteralWindow) cudaEventRecord(c->ev[1], s);
+    PipelineStatus st;
     if (ordered) {
-      k_resolve_ordered<<<1, 1024, 0, s>>>(cand, dense, rs, carry_in, slab.base_offset, outp, ocap, fa, d_status);
+      const unsigned int seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+      k_resolve_ordered<<<1, 512, 0, s>>>(cand, dense, rs, carry_in, slab.base_offset, outp, ocap, fa, d_status,
+                                          c->h_status_dev, seq);
+      if (stats) stats->launches += 1;
+      RJ_TRY(cudaGetLastError());
+      // spin on the mapped status block; fall back to the stream state if the
+      // kernel cannot have run (launch failure, sticky error)
+      volatile unsigned int* vseq = &c->h_status->seq;
+      uint64_t spins = 0;
+      while (*vseq != seq) {
+        if ((++spins & 0x3FFF) == 0) {
+          cudaError_t q = cudaStreamQuery(s);
+          if (q == cudaSuccess) { if (*vseq == seq) break; if (error) *error = "rejit_b200: resolve kernel did not report"; return false; }
+          if (q != cudaErrorNotReady) { Check(q, "cudaStreamQuery", error); return false; }
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      st = *c->h_status;
     } else {
       CandBuf un{c->cand_b.as<uint64_t>(), c->cand_e.as<uint64_t>(), ctr, c->cand_cap};
       k_resolve_small<<<1, 1024, kSmallResolveMax * 16, s>>>(un, carry_in, slab.base_offset, outp, ocap, d_status);
+      if (stats) stats->launches += 1;
+      RJ_TRY(cudaGetLastError());
+      RJ_TRY(cudaMemcpyAsync(c->h_status, d_status, sizeof(PipelineStatus), cudaMemcpyDeviceToHost, s));
+      RJ_TRY(cudaStreamSynchronize(s));
+      st = *c->h_status;
     }
-    if (stats) stats->launches += 1;
-    RJ_TRY(cudaGetLastError());
-    RJ_TRY(cudaMemcpyAsync(c->h_status, d_status, sizeof(PipelineStatus), cudaMemcpyDeviceToHost, s));
-    RJ_TRY(cudaStreamSynchronize(s));
-    PipelineStatus st = *c->h_status;
 
     // ---- capacity protocol: grow what overflowed and run again -----------------
     bool rerun = false;

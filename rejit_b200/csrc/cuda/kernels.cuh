@@ -76,7 +76,7 @@ struct PipelineStatus {                // one per call, read back by the host
   unsigned int need_large;             // too many candidates for the one-CTA resolve
   unsigned int dense;                  // lane hit list overflowed: use the fallback kernel
   unsigned int full_result;            // MatchFull answer
-  unsigned int pad;
+  unsigned int seq;                    // call id, written last (host polls the mapped copy)
 };
 
 struct DfaTables {
@@ -706,18 +706,25 @@ __device__ __forceinline__ uint64_t BlockExclusiveMax(uint64_t v, uint64_t init,
 
 // Concatenates the sub-regions' slot ranges into a dense (sorted) list.
 // Returns false (uniformly) on overflow / dense marker; *m_out = total.
-// The counts of kGatherBatch blocks of 1024 sub-regions are loaded up front so
-// that their global-memory latency is paid once per batch.
-constexpr int kGatherBatch = 8;
+// Per batch of kGatherBatch x 1024 sub-regions: (1) all counts are loaded up
+// front, (2) the block scans run back to back on registers, (3) every thread
+// then issues the loads of all its entries before storing any of them, so the
+// global-memory latency is paid about once per batch instead of once per entry.
+// If `spec_out` is non-null the pairs are also written there (offset by
+// `base_offset`) — the speculative output of k_resolve_ordered's fast path.
+constexpr int kGatherBatch = 4;
 
 __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseList& dense, PipelineStatus* status,
-                                               uint32_t* s_warp, unsigned long long* m_out) {
+                                               uint32_t* s_warp, unsigned long long* m_out,
+                                               uint64_t* spec_out = nullptr, uint64_t spec_cap = 0,
+                                               uint64_t base_offset = 0) {
   __shared__ unsigned int s_flags[2];          // [0] max count, [1] dense marker
   if (threadIdx.x < 2) s_flags[threadIdx.x] = 0;
   __syncthreads();
   unsigned long long base = 0;
   for (uint64_t blk0 = 0; blk0 < st.nsub; blk0 += (uint64_t)kGatherBatch * blockDim.x) {
     uint32_t c[kGatherBatch];
+    unsigned long long at[kGatherBatch];
 #pragma unroll
     for (int u = 0; u < kGatherBatch; ++u) {
       uint64_t sub = blk0 + (uint64_t)u * blockDim.x + threadIdx.x;
@@ -725,21 +732,31 @@ __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseLi
     }
 #pragma unroll
     for (int u = 0; u < kGatherBatch; ++u) {
-      if (blk0 + (uint64_t)u * blockDim.x >= st.nsub) break;            // uniform
-      uint64_t sub = blk0 + (uint64_t)u * blockDim.x + threadIdx.x;
-      uint32_t cu = c[u];
-      if (cu == kLaneListOverflow) { atomicOr(&s_flags[1], 1u); cu = 0; }
-      else if (cu > st.cap) { atomicMax(&s_flags[0], cu); cu = st.cap; }
+      if (c[u] == kLaneListOverflow) { atomicOr(&s_flags[1], 1u); c[u] = 0; }
+      else if (c[u] > st.cap) { atomicMax(&s_flags[0], c[u]); c[u] = st.cap; }
       uint32_t total;
-      uint32_t off = BlockExclusiveSum(cu, &total, s_warp);
-      for (uint32_t i = 0; i < cu; ++i) {
-        unsigned long long at = base + off + i;
-        if (at < dense.cap) {
-          dense.begin[at] = st.begin[sub * st.cap + i];
-          dense.end[at] = st.end[sub * st.cap + i];
-        }
-      }
+      uint32_t off = BlockExclusiveSum(c[u], &total, s_warp);
+      at[u] = base + off;
       base += total;
+    }
+    // first two entries of every sub-region: loads issued together
+    uint64_t b0[kGatherBatch], e0[kGatherBatch], b1[kGatherBatch], e1[kGatherBatch];
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) {
+      uint64_t sub = blk0 + (uint64_t)u * blockDim.x + threadIdx.x;
+      if (c[u] > 0) { b0[u] = st.begin[sub * st.cap]; e0[u] = st.end[sub * st.cap]; }
+      if (c[u] > 1) { b1[u] = st.begin[sub * st.cap + 1]; e1[u] = st.end[sub * st.cap + 1]; }
+    }
+    auto put = [&](unsigned long long k, uint64_t bb, uint64_t ee) {
+      if (k < dense.cap) { dense.begin[k] = bb; dense.end[k] = ee; }
+      if (spec_out && k < spec_cap) { spec_out[2 * k] = bb + base_offset; spec_out[2 * k + 1] = ee + base_offset; }
+    };
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) {
+      uint64_t sub = blk0 + (uint64_t)u * blockDim.x + threadIdx.x;
+      if (c[u] > 0) put(at[u], b0[u], e0[u]);
+      if (c[u] > 1) put(at[u] + 1, b1[u], e1[u]);
+      for (uint32_t i = 2; i < c[u]; ++i) put(at[u] + i, st.begin[sub * st.cap + i], st.end[sub * st.cap + i]);
     }
   }
   __syncthreads();
@@ -753,7 +770,7 @@ __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseLi
 }
 
 // Stage boundary of the literal+window pipeline: dense list of needle hits.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512, 1)
 k_gather_hits(SubStore st, DenseList dense, PipelineStatus* status) {
   __shared__ uint32_t s_warp[33];
   unsigned long long m;
@@ -787,14 +804,18 @@ __device__ __forceinline__ FaithfulScratch WalkerScratch(const FaithfulArgs& fa,
 // influence it: reach[i] < begin[i], or reach[i] == begin[i] and it is non-empty
 // (strictly smaller only, for re-entrant patterns).
 // ===========================================================================
-__global__ void __launch_bounds__(1024)
-k_resolve_ordered(SubStore st, DenseList dense, ResolveScratch rs, Carry carry_in, uint64_t base_offset,
-                  uint64_t* __restrict__ out_pairs, uint64_t out_cap, FaithfulArgs fa, PipelineStatus* status) {
+__device__ __forceinline__ void ResolveOrderedBody(const SubStore& st, const DenseList& dense, const ResolveScratch& rs,
+                                                   const Carry& carry_in, uint64_t base_offset,
+                                                   uint64_t* __restrict__ out_pairs, uint64_t out_cap,
+                                                   const FaithfulArgs& fa, PipelineStatus* status) {
   __shared__ uint32_t s_warp[33];
   __shared__ uint64_t s_warp64[32];
   __shared__ unsigned long long s_last[2];
   unsigned long long m;
-  bool ok = GatherSubStore(st, dense, status, s_warp, &m);
+  // the gather also writes the candidates straight to the output: if the fast
+  // path below holds they ARE the matches; otherwise the general path
+  // overwrites the output
+  bool ok = GatherSubStore(st, dense, status, s_warp, &m, fa.enabled ? nullptr : out_pairs, out_cap, base_offset);
   if (threadIdx.x == 0) status->n_candidates = m;
   if (!ok) return;
   if (m > (unsigned long long)kOrderedResolveMax) {
@@ -818,12 +839,6 @@ k_resolve_ordered(SubStore st, DenseList dense, ResolveScratch rs, Carry carry_i
       if (i + 1 < M && e[i] > e[i + 1]) bad = 1;               // ends not monotone: need the max-scan
     }
     if (!__syncthreads_or(bad)) {
-      for (uint32_t i = i0; i < i1; ++i) {
-        if (i < out_cap) {
-          out_pairs[2 * (uint64_t)i] = b[i] + base_offset;
-          out_pairs[2 * (uint64_t)i + 1] = e[i] + base_offset;
-        }
-      }
       if (threadIdx.x == 0) {
         status->n_matches = M;
         status->carry_cur = M ? e[M - 1] : carry_in.cur;
@@ -884,6 +899,33 @@ k_resolve_ordered(SubStore st, DenseList dense, ResolveScratch rs, Carry carry_i
     if (s_last[1]) tail = rs.fin_end[s_last[1] - 1];
     status->carry_cur = cur;
     status->carry_tail = tail;
+  }
+}
+
+// The kernel proper: resolve, then publish the status block to mapped host
+// memory (the host spins on `seq` instead of paying a stream synchronisation).
+__global__ void __launch_bounds__(512, 1)
+k_resolve_ordered(SubStore st, DenseList dense, ResolveScratch rs, Carry carry_in, uint64_t base_offset,
+                  uint64_t* __restrict__ out_pairs, uint64_t out_cap, FaithfulArgs fa, PipelineStatus* status,
+                  volatile PipelineStatus* host_status, unsigned int seq) {
+  ResolveOrderedBody(st, dense, rs, carry_in, base_offset, out_pairs, out_cap, fa, status);
+  __syncthreads();
+  if (threadIdx.x == 0 && host_status) {
+    __threadfence();
+    PipelineStatus v = *status;
+    host_status->n_candidates = v.n_candidates;
+    host_status->n_hits = v.n_hits;
+    host_status->n_matches = v.n_matches;
+    host_status->carry_cur = v.carry_cur;
+    host_status->carry_tail = v.carry_tail;
+    host_status->overflow = v.overflow;
+    host_status->need_cap = v.need_cap;
+    host_status->need_large = v.need_large;
+    host_status->dense = v.dense;
+    host_status->full_result = v.full_result;
+    __threadfence_system();
+    host_status->seq = seq;
+    __threadfence_system();
   }
 }
 

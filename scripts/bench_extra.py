@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""Secondary measurements (not the contract line of bench.py): the other
+BASELINE.json configurations with the text resident in HBM, one JSON line per
+case — device pipeline time, scan-kernel time, GB/s and fraction of the measured
+HBM bandwidth.  Used to fill the table in DESIGN.md / profiles/."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import rejit_b200 as rj  # noqa: E402
+from rejit_b200 import workloads as W  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def run(name, pattern, text, reps=10, flush=True):
+    r = rj.Regej(pattern)
+    dt = rj.DeviceText(text)
+    st = rj.Stats()
+    for _ in range(3):
+        r.match_all_device(dt, stats=st)
+    tot = scan = 0.0
+    for _ in range(reps):
+        if flush:
+            rj.lib().rejit_b200_flush_l2(0)
+        cnt = r.match_all_device(dt, stats=st)
+        tot += st.total_ms
+        scan += st.scan_ms
+    n = len(text)
+    line = {"case": name, "pattern": pattern if len(pattern) < 70 else pattern[:67] + "...", "bytes": n,
+            "matches": cnt, "strategy": r.describe().split(";")[0],
+            "pipeline_ms": round(tot / reps, 4), "scan_ms": round(scan / reps, 4),
+            "pipeline_gbs": round(n / (tot / reps) / 1e6, 1), "scan_gbs": round(n / (scan / reps) / 1e6, 1),
+            "scan_frac_of_hbm": round(n / (scan / reps) / 1e6 / peak(), 4), "launches": st.launches}
+    print(json.dumps(line), flush=True)
+    dt.free()
+
+
+def main():
+    big = int(os.environ.get("RJ_EXTRA_BYTES", "500000000"))
+    t = W.random_ascii(1 << 20, seed=1)
+    run("C1 literal, 1 MiB random ASCII (L2 resident)", W.LITERAL_PATTERN, t, flush=False)
+    text = W.random_ascii(big, seed=21)
+    run("C3 complex regex, random text, no hits", W.COMPLEX_PATTERN, text)
+    run("literal 'regexp', same text", W.LITERAL_PATTERN, text)
+    W.plant(text, W.COMPLEX_HITS, every=10_007)
+    run("C3 complex regex, hits every ~10 kB", W.COMPLEX_PATTERN, text)
+    blob = W.source_blob(big, seed=3)
+    run("C4 jrep literal ';\\n}' over source blob", W.JREP_PATTERN, blob)
+    run("jrep line index '^'", "^", blob[:100_000_000])
+    seq = W.fasta_sequence(5_000_000)
+    run("C2 dna #1", W.DNA_PATTERNS[0], seq)
+    run("C5 IUB 'B'", "B", seq)
+    fa = np.frombuffer(W.fasta_file(2_000_000), dtype=np.uint8)
+    run("C5 strip '>.*\\n|\\n' over 20 MB FASTA file", W.STRIP_PATTERN, fa)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,9 @@ echo "== pytest gpu" ; timeout 2400 python -m pytest tests -m gpu -q -x --timeou
 echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench_ours.json
 tail -5 gpurun_out/bench.err
 echo "== bench reference" ; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>> gpurun_out/bench.err | tee gpurun_out/bench_reference.json
+if [ "${RJ_EXTRA:-0}" = "1" ]; then
+echo "== bench_extra"; timeout 1200 python scripts/bench_extra.py 2>&1 | tee gpurun_out/bench_extra.jsonl | cut -c1-400
+fi
 if [ "${RJ_SWEEP:-0}" = "1" ]; then
 for w in 6 10 14 18; do echo "== sweep RJ_DFA_WARPS=$w"; RJ_DFA_WARPS=$w timeout 300 python bench.py --steps 3 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['frac'])"; done
 fi
