@@ -70,6 +70,13 @@ class Regej {
   bool ReplaceFirst(string& text, const string& with);
   size_t ReplaceAll(string& text, const string& with);
 
+  // Several patterns over the same text (new in rejit_b200): the text is copied
+  // to the device once; fixed-length alternation sets (regex-dna's variants) are
+  // fused into a single scan.  (*matches)[i] receives what
+  // patterns[i]->MatchAll(text, text_size, ...) would append.  Returns the total.
+  static size_t MatchAllSet(const std::vector<Regej*>& patterns, const char* text, size_t text_size,
+                            std::vector<std::vector<struct Match> >* matches);
+
   // Builds the matcher eagerly (it is otherwise built on first use).
   bool Compile(MatchType match_type);
 

@@ -152,6 +152,29 @@ int64_t rejit_b200_match_all_text(rejit_b200_program* program, const rejit_b200_
                                   uint64_t** out_pairs, rejit_b200_stats* stats,
                                   char* err, size_t err_length);
 
+/* Pattern sets: several compiled patterns matched
+ * against the same text.  When every member is a fixed-length, anchor-free
+ * alternation (regex-dna's nine variants) they are fused into ONE automaton and
+ * the text is scanned once for all of them; other sets are run member by member.
+ * Results are identical to calling rejit_b200_match_all per member.
+ * out_counts[j] = matches of member j; out_pairs (may be NULL) receives one
+ * malloc'ed (begin,end) array per member (free each with rejit_b200_free).      */
+typedef struct rejit_b200_set rejit_b200_set;
+rejit_b200_set* rejit_b200_set_create(rejit_b200_program* const* programs, int count);
+void rejit_b200_set_free(rejit_b200_set* set);
+const char* rejit_b200_set_describe(const rejit_b200_set* set);
+int rejit_b200_match_all_set_text(rejit_b200_set* set, const rejit_b200_text* text, int64_t* out_counts,
+                                  uint64_t** out_pairs, rejit_b200_stats* stats, char* err, size_t err_length);
+int rejit_b200_match_all_set_device(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
+                                    int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length);
+
+/* Slab variant of the set call (one-process-per-GPU sharding): ownership range,
+ * base offset and one carry per member, as for rejit_b200_match_all_device_slab. */
+int rejit_b200_match_all_set_device_slab(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
+                                         uint64_t own_begin, uint64_t own_end, uint64_t base_offset,
+                                         const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
+                                         int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length);
+
 /* Slab variant for one-process-per-GPU sharding: only matches that BEGIN in
  * [own_begin, own_end) of the buffer are reported (own_end > text_length means
  * "to the end, including the empty match at text_length"); the buffer should

@@ -50,6 +50,8 @@ EXPORTED = [
     "rejit_b200_pinned_free", "rejit_b200_copy_to_device", "rejit_b200_copy_from_device",
     "rejit_b200_flush_l2", "rejit_b200_match_all_device", "rejit_b200_match_all_device_slab", "rejit_b200_free",
     "rejit_b200_text_upload", "rejit_b200_text_free", "rejit_b200_match_all_text",
+    "rejit_b200_set_create", "rejit_b200_set_free", "rejit_b200_set_describe",
+    "rejit_b200_match_all_set_text", "rejit_b200_match_all_set_device", "rejit_b200_match_all_set_device_slab",
 ]
 
 
@@ -107,6 +109,18 @@ def lib():
     L.rejit_b200_text_free.argtypes = [vp]
     L.rejit_b200_match_all_text.argtypes = [vp, vp, ctypes.POINTER(u64p), ctypes.POINTER(Stats), cp, sz]
     L.rejit_b200_match_all_text.restype = ctypes.c_int64
+    L.rejit_b200_set_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    L.rejit_b200_set_create.restype = vp
+    L.rejit_b200_set_free.argtypes = [vp]
+    L.rejit_b200_set_describe.argtypes = [vp]
+    L.rejit_b200_set_describe.restype = cp
+    L.rejit_b200_match_all_set_text.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(u64p),
+                                                ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_match_all_set_device.argtypes = [vp, ctypes.c_int, vp, sz, ctypes.POINTER(ctypes.c_int64),
+                                                  ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_match_all_set_device_slab.argtypes = [vp, ctypes.c_int, vp, sz, ctypes.c_uint64, ctypes.c_uint64,
+                                                       ctypes.c_uint64, ctypes.POINTER(Carry), ctypes.POINTER(Carry),
+                                                       ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(Stats), cp, sz]
     _lib = L
     return L
 
@@ -314,6 +328,75 @@ class Regej:
         if n < 0:
             raise RejitError(err.value.decode("latin-1"))
         return int(n)
+
+
+class RegejSet:
+    """Several patterns matched against the same text; fused into one scan when
+    every member is a fixed-length, anchor-free alternation."""
+
+    def __init__(self, patterns):
+        self.members = [p if isinstance(p, Regej) else Regej(p) for p in patterns]
+        for m in self.members:
+            if not m.compile():
+                raise ParserError(m.status_string)
+        arr = (ctypes.c_void_p * len(self.members))(*[m._prog for m in self.members])
+        self._set = ctypes.c_void_p(lib().rejit_b200_set_create(arr, len(self.members)))
+
+    def describe(self) -> str:
+        return lib().rejit_b200_set_describe(self._set).decode("latin-1")
+
+    def __del__(self):
+        try:
+            if self._set:
+                lib().rejit_b200_set_free(self._set)
+        except Exception:
+            pass
+
+    def match_all_device(self, dtext: "DeviceText", stats: Optional[Stats] = None, own=None, base_offset: int = 0,
+                         carry_in=None, carry_out=None) -> List[int]:
+        counts = (ctypes.c_int64 * len(self.members))()
+        err = ctypes.create_string_buffer(512)
+        if own is not None:
+            r = lib().rejit_b200_match_all_set_device_slab(
+                self._set, dtext.device, dtext.ptr, dtext.nbytes, own[0], own[1], base_offset, carry_in, carry_out,
+                counts, ctypes.byref(stats) if stats is not None else None, err, len(err))
+            if r < 0:
+                raise RejitError(err.value.decode("latin-1"))
+            return list(counts)
+        r = lib().rejit_b200_match_all_set_device(self._set, dtext.device, dtext.ptr, dtext.nbytes, counts,
+                                                  ctypes.byref(stats) if stats is not None else None, err, len(err))
+        if r < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        return list(counts)
+
+    def match_all(self, data) -> List[List[Tuple[int, int]]]:
+        """Uploads `data` once and returns one match list per member."""
+        L = lib()
+        t = _as_bytes(data) if not hasattr(data, "ctypes") else data
+        err = ctypes.create_string_buffer(512)
+        if hasattr(t, "ctypes"):
+            import numpy as np
+            keep = np.ascontiguousarray(t, dtype=np.uint8)
+            ptr, n = ctypes.c_void_p(keep.ctypes.data), keep.size
+        else:
+            ptr, n = ctypes.cast(ctypes.c_char_p(t), ctypes.c_void_p), len(t)
+        h = L.rejit_b200_text_upload(0, ptr, n, err, len(err))
+        if not h:
+            raise RejitError(err.value.decode("latin-1"))
+        try:
+            k = len(self.members)
+            counts = (ctypes.c_int64 * k)()
+            pairs = (ctypes.POINTER(ctypes.c_uint64) * k)()
+            r = L.rejit_b200_match_all_set_text(self._set, h, counts, pairs, None, err, len(err))
+            if r < 0:
+                raise RejitError(err.value.decode("latin-1"))
+            out = []
+            for j in range(k):
+                out.append([(pairs[j][2 * i], pairs[j][2 * i + 1]) for i in range(counts[j])])
+                L.rejit_b200_free(pairs[j])
+            return out
+        finally:
+            L.rejit_b200_text_free(h)
 
 
 def match_all(pattern, text):

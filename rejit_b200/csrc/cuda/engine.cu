@@ -90,6 +90,11 @@ class DeviceContext {
   Buffer sorted_b, sorted_e, reach, take, wide, slot, fin_end, cub_tmp;
   uint64_t scratch_cap = 0;
   Buffer fscratch;                    // label scratch for re-entrant patterns
+  // fused pattern sets
+  Buffer set_sub_b, set_sub_e, set_sub_count, set_dense_b, set_dense_e, set_reach, set_take, set_fin, set_slot,
+      set_out, set_status, set_counts;
+  PipelineStatus* h_set_status = nullptr;      // pinned + mapped, 32 entries
+  PipelineStatus* h_set_status_dev = nullptr;
   Buffer flush;
   PipelineStatus* h_status = nullptr; // pinned + mapped: the resolve kernel writes it, the host spins on seq
   PipelineStatus* h_status_dev = nullptr;   // device view of h_status
@@ -108,6 +113,9 @@ class DeviceContext {
     RJ_TRY(cudaHostAlloc(&h_status, sizeof(PipelineStatus), cudaHostAllocMapped));
     memset(h_status, 0, sizeof(PipelineStatus));
     RJ_TRY(cudaHostGetDevicePointer(&h_status_dev, h_status, 0));
+    RJ_TRY(cudaHostAlloc(&h_set_status, 32 * sizeof(PipelineStatus), cudaHostAllocMapped));
+    memset(h_set_status, 0, 32 * sizeof(PipelineStatus));
+    RJ_TRY(cudaHostGetDevicePointer(&h_set_status_dev, h_set_status, 0));
     // status and the counters share one allocation so that one memset clears both
     if (!status.Reserve(sizeof(PipelineStatus) + 64, error)) return false;
     counters.p = static_cast<uint8_t*>(status.p) + ((sizeof(PipelineStatus) + 15) & ~size_t(15));
@@ -407,6 +415,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     RJ_TRY(cudaFuncSetAttribute(k_resolve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallResolveMax * 16));
     RJ_TRY(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     RJ_TRY(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    RJ_TRY(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     c->attr_done = true;
   }
   if (c->dense_cap == 0 && !c->ReserveDense(1u << 16, error)) return false;
@@ -693,6 +702,216 @@ int64_t MatchAllResident(int device, Program* prog, const uint8_t* d_text, uint6
     }
   }
   return (int64_t)cnt;
+}
+
+// ===========================================================================
+// fused pattern sets
+// ===========================================================================
+class DeviceSet {
+ public:
+  SetTables tb{};
+  std::vector<void*> allocs;
+  size_t fixed_smem = 0;
+  uint32_t sub_cap = 16;
+  uint64_t per_cap = 1u << 14;        // dense / output capacity per pattern
+  bool dense_mode = false;
+  ~DeviceSet() { for (void* p : allocs) cudaFree(p); }
+  template <class T>
+  bool Upload(const T* host, size_t count, const T** dev, std::string* error) {
+    void* p = nullptr;
+    RJ_TRY(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    allocs.push_back(p);
+    RJ_TRY(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<const T*>(p);
+    return true;
+  }
+};
+
+SetProgram* SetProgram::Create(const std::vector<Program*>& members) {
+  SetProgram* sp = new SetProgram();
+  sp->members_ = members;
+  std::vector<const CompiledAutomaton*> autos;
+  for (Program* p : members) autos.push_back(&p->automaton());
+  sp->fused_ = BuildSetDfa(autos, &sp->dfa_);
+  if (sp->fused_) {
+    sp->describe_ = "fused set: " + std::to_string(members.size()) + " patterns, one DFA of " +
+                    std::to_string(sp->dfa_.n_states) + " states x " + std::to_string(sp->dfa_.n_classes) + " classes";
+  } else {
+    sp->describe_ = "set of " + std::to_string(members.size()) + " patterns run one by one (not fusable)";
+  }
+  return sp;
+}
+SetProgram::~SetProgram() { for (auto* d : per_device_) delete d; }
+
+DeviceSet* SetProgram::OnDevice(int device, std::string* error) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!per_device_[device]) {
+    if (!Check(cudaSetDevice(device), "cudaSetDevice", error)) return nullptr;
+    DeviceSet* d = new DeviceSet();
+    const SetDfa& f = dfa_;
+    if (!d->Upload(f.t1.data(), f.t1.size(), &d->tb.t1, error) || !d->Upload(f.t2.data(), f.t2.size(), &d->tb.t2, error) ||
+        !d->Upload(f.byte_class.data(), 256, &d->tb.byte_class, error) ||
+        !d->Upload(f.accept_mask.data(), f.accept_mask.size(), &d->tb.accept_mask, error)) { delete d; return nullptr; }
+    for (int j = 0; j < f.n_patterns; ++j) d->tb.match_len[j] = f.match_len[j];
+    d->tb.n_patterns = f.n_patterns;
+    d->tb.n_states = f.n_states;
+    d->tb.n_classes = f.n_classes;
+    d->tb.first_accept = f.first_accept;
+    d->fixed_smem = f.t2.size() * 4 + f.accept_mask.size() * 4 + f.t1.size() * 2 + 16 + 256 + 8 * 32 + 512;
+    per_device_[device] = d;
+  }
+  return per_device_[device];
+}
+
+int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint64_t n, int64_t* counts,
+                        uint64_t** pairs, RunStats* stats, std::string* error, const SlabView* own_view,
+                        const Carry* carry_in, Carry* carry_out) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return -1;
+  const int K = set->size();
+  auto one_by_one = [&]() -> int {
+    RunStats acc;
+    for (int j = 0; j < K; ++j) {
+      RunStats rs;
+      uint64_t* pj = nullptr;
+      int64_t r;
+      if (own_view || carry_in || carry_out) {
+        Carry in = carry_in ? carry_in[j] : Carry();
+        Carry out;
+        r = MatchAllDevice(device, set->members()[j], d_text, n, nullptr, 0, in, &out, stats ? &rs : nullptr, error, own_view);
+        if (carry_out) carry_out[j] = out;
+        pj = nullptr;
+      } else {
+        r = MatchAllResident(device, set->members()[j], d_text, n, &pj, stats ? &rs : nullptr, error);
+      }
+      if (r < 0) return -1;
+      counts[j] = r;
+      if (pairs) pairs[j] = pj; else free(pj);
+      acc.scan_ms += rs.scan_ms; acc.total_ms += rs.total_ms; acc.launches += rs.launches;
+      acc.candidates += rs.candidates; acc.matches += rs.matches; acc.reruns += rs.reruns;
+    }
+    if (stats) { *stats = acc; stats->strategy = -1; }
+    return 0;
+  };
+  if (!set->fused()) return one_by_one();
+  DeviceSet* ds = set->OnDevice(device, error);
+  if (!ds) return -1;
+  if (ds->dense_mode) return one_by_one();
+  if (ds->fixed_smem + 4 * kDfaTileBytes > c->smem_optin) { ds->dense_mode = true; return one_by_one(); }
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!Check(cudaSetDevice(c->device), "cudaSetDevice", error)) return -1;
+    if ((reinterpret_cast<uintptr_t>(d_text) & 15) != 0) { if (error) *error = "rejit_b200: device text must be 16-byte aligned"; return -1; }
+    cudaStream_t s = c->stream;
+    if (!c->attr_done) {
+      if (!Check(cudaFuncSetAttribute(k_resolve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallResolveMax * 16), "attr", error) ||
+          !Check(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error) ||
+          !Check(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "attr", error) ||
+          !Check(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error)) return -1;
+      c->attr_done = true;
+    }
+    int warps = (int)std::min<size_t>((c->smem_optin - ds->fixed_smem) / kDfaTileBytes, 18);
+    if (const char* env = getenv("RJ_DFA_WARPS")) warps = std::max(4, std::min(warps, atoi(env)));
+    const uint64_t nsub = std::max<uint64_t>(1, (n + kDfaSubBytes - 1) / kDfaSubBytes);
+    bool fallback = false;
+    for (int attempt = 0; attempt < 40 && !fallback; ++attempt) {
+      const uint64_t per_cap = ds->per_cap;
+      if (!c->set_sub_b.Reserve((uint64_t)K * nsub * ds->sub_cap * 8, error) ||
+          !c->set_sub_e.Reserve((uint64_t)K * nsub * ds->sub_cap * 8, error) ||
+          !c->set_sub_count.Reserve((uint64_t)K * nsub * 4 + 16, error) ||
+          !c->set_dense_b.Reserve(K * per_cap * 8, error) || !c->set_dense_e.Reserve(K * per_cap * 8, error) ||
+          !c->set_reach.Reserve(K * per_cap * 8, error) || !c->set_take.Reserve(K * per_cap * 4, error) ||
+          !c->set_fin.Reserve(K * per_cap * 8, error) || !c->set_slot.Reserve(K * per_cap * 8, error) ||
+          !c->set_out.Reserve(K * per_cap * 16, error) || !c->set_status.Reserve(32 * sizeof(PipelineStatus), error) ||
+          !c->set_counts.Reserve(64 * 8, error)) return -1;
+      PipelineStatus* d_status = c->set_status.as<PipelineStatus>();
+      unsigned long long* d_counts = c->set_counts.as<unsigned long long>();     // [0..K) dense counts, [40] work counter
+      if (!Check(cudaMemsetAsync(d_status, 0, 32 * sizeof(PipelineStatus), s), "memset", error) ||
+          !Check(cudaMemsetAsync(d_counts, 0, 64 * 8, s), "memset", error)) return -1;
+      SubStore st{};
+      st.begin = c->set_sub_b.as<uint64_t>(); st.end = c->set_sub_e.as<uint64_t>(); st.count = c->set_sub_count.as<uint32_t>();
+      st.cap = ds->sub_cap; st.nsub = (uint64_t)K * nsub;
+      DenseList dense{c->set_dense_b.as<uint64_t>(), c->set_dense_e.as<uint64_t>(), d_counts, per_cap};
+      ResolveScratch rs{c->set_reach.as<uint64_t>(), c->set_take.as<uint32_t>(), c->set_fin.as<uint64_t>(), c->set_slot.as<uint64_t>()};
+      ScanRange own{0, n + 1};
+      uint64_t base_offset = 0;
+      if (own_view) {
+        own.own_begin = std::min<uint64_t>(own_view->own_begin, n + 1);
+        own.own_end = std::min<uint64_t>(own_view->own_end, n + 1);
+        base_offset = own_view->base_offset;
+      }
+      CarrySet carries;
+      for (int j = 0; j < 32; ++j) carries.c[j] = (carry_in && j < K) ? carry_in[j] : Carry();
+      if (stats) cudaEventRecord(c->ev[0], s);
+      size_t smem = ds->fixed_smem + (size_t)warps * kDfaTileBytes;
+      int blocks = (int)std::min<uint64_t>((nsub + warps - 1) / warps, (uint64_t)c->sm_count);
+      k_set_tma<<<blocks, warps * 32, smem, s>>>(d_text, n, ds->tb, own, st, nsub, &d_status->dense, d_counts + 40);
+      if (stats) cudaEventRecord(c->ev[1], s);
+      const unsigned int seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+      k_resolve_set<<<K, 512, 0, s>>>(st, nsub, dense, rs, per_cap, c->set_out.as<uint64_t>(), d_status,
+                                      c->h_set_status_dev, d_counts, seq, carries, base_offset);
+      if (stats) stats->launches += 2;
+      if (!Check(cudaGetLastError(), "launch", error)) return -1;
+      uint64_t spins = 0;
+      for (int j = 0; j < K; ++j) {
+        volatile unsigned int* vseq = &c->h_set_status[j].seq;
+        while (*vseq != seq) {
+          if ((++spins & 0x3FFF) == 0) {
+            cudaError_t q = cudaStreamQuery(s);
+            if (q == cudaSuccess) { if (*vseq == seq) break; if (error) *error = "rejit_b200: set resolve did not report"; return -1; }
+            if (q != cudaErrorNotReady) { Check(q, "cudaStreamQuery", error); return -1; }
+          }
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      bool rerun = false;
+      uint32_t need_cap = 0;
+      uint64_t need_dense = 0;
+      for (int j = 0; j < K; ++j) {
+        const PipelineStatus& h = c->h_set_status[j];
+        if (h.dense || h.need_large) fallback = true;
+        if (h.overflow && h.need_cap) { need_cap = std::max(need_cap, h.need_cap); rerun = true; }
+        if (h.n_candidates > per_cap) { need_dense = std::max<uint64_t>(need_dense, h.n_candidates); rerun = true; }
+        else if (h.overflow && !h.need_cap) rerun = true;
+      }
+      if (fallback) break;
+      if (rerun) {
+        if (need_cap) ds->sub_cap = std::max<uint32_t>(need_cap, 2 * ds->sub_cap);
+        if (need_dense) ds->per_cap = need_dense + need_dense / 4 + 1024;
+        if (stats) stats->reruns += 1;
+        continue;
+      }
+      uint64_t total_m = 0, total_c = 0;
+      for (int j = 0; j < K; ++j) {
+        const PipelineStatus& h = c->h_set_status[j];
+        counts[j] = (int64_t)h.n_matches;
+        if (carry_out) { carry_out[j].cur = h.carry_cur; carry_out[j].tail = h.carry_tail; }
+        total_m += h.n_matches;
+        total_c += h.n_candidates;
+      }
+      if (stats) {
+        cudaEventRecord(c->ev[2], s);
+        cudaEventSynchronize(c->ev[2]);
+        cudaEventElapsedTime(&stats->scan_ms, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&stats->total_ms, c->ev[0], c->ev[2]);
+        stats->candidates = total_c;
+        stats->matches = total_m;
+        stats->strategy = 4;
+      }
+      if (pairs) {
+        for (int j = 0; j < K; ++j) {
+          pairs[j] = static_cast<uint64_t*>(malloc(std::max<size_t>((size_t)counts[j] * 16, 8)));
+          if (counts[j] && !Check(cudaMemcpyAsync(pairs[j], c->set_out.as<uint64_t>() + (uint64_t)j * 2 * per_cap,
+                                                  (size_t)counts[j] * 16, cudaMemcpyDeviceToHost, s), "D2H", error)) return -1;
+        }
+        if (!Check(cudaStreamSynchronize(s), "sync", error)) return -1;
+      }
+      return 0;
+    }
+    ds->dense_mode = true;
+  }
+  return one_by_one();
 }
 
 int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int n_gpus, uint64_t** pairs,

@@ -5,6 +5,7 @@
 
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../host/automaton.h"
 
@@ -85,6 +86,37 @@ int64_t MatchAllResident(int device, Program* prog, const uint8_t* d_text, uint6
 // scanned with a right halo; chains are stitched at the slab edges (§8e).
 int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int n_gpus,
                              uint64_t** pairs, RunStats* stats, std::string* error);
+
+// A set of compiled patterns matched against the same text in ONE fused pass
+// when every member is a fixed-length anchor-free DFA pattern (otherwise the
+// members are simply run one after the other).
+class DeviceSet;
+class SetProgram {
+ public:
+  static SetProgram* Create(const std::vector<Program*>& members);
+  ~SetProgram();
+  int size() const { return (int)members_.size(); }
+  bool fused() const { return fused_; }
+  const std::string& describe() const { return describe_; }
+  const std::vector<Program*>& members() const { return members_; }
+  const SetDfa& dfa() const { return dfa_; }
+  DeviceSet* OnDevice(int device, std::string* error);
+
+ private:
+  std::vector<Program*> members_;
+  bool fused_ = false;
+  SetDfa dfa_;
+  std::string describe_;
+  DeviceSet* per_device_[16] = {nullptr};
+};
+
+// MatchAll of every member over device-resident text.  counts[j] = number of
+// matches of member j; if pairs != nullptr, pairs[j] receives a malloc'ed array
+// of counts[j] (begin,end) pairs.  Returns 0, or -1 with *error set.
+// `own`, `carry_in` (one per member) and `carry_out` are optional: slab sharding.
+int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint64_t n, int64_t* counts,
+                        uint64_t** pairs, RunStats* stats, std::string* error, const SlabView* own = nullptr,
+                        const Carry* carry_in = nullptr, Carry* carry_out = nullptr);
 
 // MatchFull: 1 / 0, or -1 on error.
 int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error);

@@ -512,6 +512,216 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
   }
 }
 
+// ===========================================================================
+// K2-set: the same scan for a SET of fixed-length patterns fused into one
+// automaton (regex-dna counts nine patterns over one text): one pass over the
+// text advances all of them.  Same tile staging, chain geometry and two-byte
+// steps as k_dfa_tma; the union automaton is too large to replicate per lane, so
+// its pair table is shared (entry = byte offset of the next state's row, bit 31
+// = accept in between).  An accepting state carries a bitmask of the patterns
+// ending there; the replay fans the ends out per pattern, and the emission
+// writes every pattern's ends, in order, into that pattern's own slot range
+// (slot index = pattern * nsub + sub-region).
+// Algorithmic traffic: N bytes read (once for all patterns) + 16 bytes per match.
+// ===========================================================================
+struct SetTables {
+  const uint16_t* t1;                  // [S*C] next state * C
+  const uint32_t* t2;                  // [S*C*C]
+  const uint8_t* byte_class;           // [256]
+  const uint32_t* accept_mask;         // [S]
+  uint32_t match_len[32];
+  int n_patterns;
+  int n_states, n_classes, first_accept;
+};
+
+constexpr int kSetChainHits = 4;
+
+__device__ __forceinline__ void SetReplay(const uint4& v, uint32_t st1, const uint16_t* s_t1, const uint8_t* s_class,
+                                          const uint32_t* s_mask, const SetTables& tb, uint32_t acc1, uint64_t p0,
+                                          uint64_t limit, uint64_t sub_lo, const ScanRange& range, uint32_t* hit,
+                                          uint32_t& cnt) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const uint32_t C = (uint32_t)tb.n_classes;
+  for (int i = 0; i < 16 && p0 + i < limit; ++i) {
+    uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+    st1 = s_t1[st1 + s_class[c]];
+    if (st1 >= acc1) {
+      uint64_t e = p0 + i + 1;
+      uint32_t m = s_mask[st1 / C];
+      while (m) {
+        int j = __ffs(m) - 1;
+        m &= m - 1;
+        uint32_t L = tb.match_len[j];
+        if (e >= L) {
+          uint64_t s = e - L;
+          if (s >= range.own_begin && s < range.own_end) {
+#pragma unroll
+            for (int q = 0; q < kSetChainHits; ++q)
+              if (cnt == (uint32_t)q) hit[q] = (uint32_t)(e - sub_lo) | ((uint32_t)j << 16);
+            ++cnt;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(576, 1)
+k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange range, SubStore out,
+          uint64_t nsub_pat, unsigned int* dense_flag, unsigned long long* work_counter) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const uint32_t C = (uint32_t)tb.n_classes;
+  const uint32_t C2 = C * C;
+  const int t2_entries = tb.n_states * (int)C2;
+  const int t1_entries = tb.n_states * (int)C;
+  // layout: [t2 u32][accept masks u32][t1 u16][class map 256][barriers][tiles]
+  uint32_t* s_t2 = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* s_mask = s_t2 + t2_entries;
+  uint16_t* s_t1 = reinterpret_cast<uint16_t*>(s_mask + tb.n_states);
+  uint8_t* s_class = reinterpret_cast<uint8_t*>(s_t1) + (((size_t)t1_entries * 2 + 15) & ~(size_t)15);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_class + 256) + 7) & ~(uintptr_t)7);
+  uint8_t* s_tiles = reinterpret_cast<uint8_t*>(s_bar + warps_per_cta);
+  s_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tiles) + 127) & ~(uintptr_t)127);
+  for (int i = threadIdx.x; i < t2_entries; i += blockDim.x) s_t2[i] = tb.t2[i];
+  for (int i = threadIdx.x; i < tb.n_states; i += blockDim.x) s_mask[i] = tb.accept_mask[i];
+  for (int i = threadIdx.x; i < t1_entries; i += blockDim.x) s_t1[i] = tb.t1[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_class[i] = tb.byte_class[i];
+  uint64_t* bar = s_bar + warp_in_cta;
+  if (lane == 0) MbarInit(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  uint8_t* tile = s_tiles + (size_t)warp_in_cta * kDfaTileBytes;
+  const uint32_t my_warm_addr = SmemAddr(tile) + (uint32_t)lane * kDfaStreamBytes;
+  const uint32_t t2_base = SmemAddr(s_t2);
+  const uint32_t row_stride = C2 * 4u;
+  const uint32_t acc_row = (uint32_t)tb.first_accept * row_stride;
+  const uint32_t acc1 = (uint32_t)tb.first_accept * C;
+  const uint32_t class_base = SmemAddr(s_class);
+  const int K = tb.n_patterns;
+  uint32_t phase = 0;
+
+  for (;;) {
+    unsigned long long sub = 0;
+    if (lane == 0) sub = atomicAdd(work_counter, 1ull);
+    sub = __shfl_sync(kFullMask, sub, 0);
+    if (sub >= nsub_pat) break;
+    const uint64_t sub_lo = sub * kDfaSubBytes;
+    const bool live = sub_lo < n && sub_lo + kDfaSubBytes + 32 > range.own_begin && sub_lo < range.own_end + 32;
+    uint32_t cntA = 0, cntB = 0;
+    uint32_t hitA[kSetChainHits] = {0, 0, 0, 0}, hitB[kSetChainHits] = {0, 0, 0, 0};
+    if (live) {
+      const bool sub_warm = sub_lo >= 16;
+      if (lane == 0) {
+        const uint64_t src = sub_warm ? sub_lo - 16 : 0;
+        uint64_t end = sub_lo + kDfaSubBytes;
+        if (end > n) end = (n + 15) & ~15ull;
+        const uint32_t bytes = (uint32_t)(end - src);
+        MbarExpectTx(bar, bytes);
+        TmaLoad1D(tile + (sub_warm ? 0 : 16), text + src, bytes, bar);
+      }
+      MbarWait(bar, phase);
+      phase ^= 1;
+      const uint64_t a = sub_lo + (uint64_t)lane * kDfaStreamBytes;
+      const uint64_t b = (a + kDfaStreamBytes < n) ? a + kDfaStreamBytes : n;
+      if (a < n) {
+        const bool warm = a >= 16;
+        uint32_t rowA = 0, rowB = 0;            // byte offset of the state's row in the pair table
+#pragma unroll 1
+        for (uint32_t it = 0; it < 10; ++it) {
+          const uint4 vA = Lds128(my_warm_addr + it * 16);
+          const uint4 vB = Lds128(my_warm_addr + (it < 9 ? (9 + it) * 16 : 0));
+          const uint32_t wA[4] = {vA.x, vA.y, vA.z, vA.w};
+          const uint32_t wB[4] = {vB.x, vB.y, vB.z, vB.w};
+          uint32_t pA[8], pB[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint32_t a0 = Lds8(class_base + __byte_perm(wA[k >> 1], 0, 0x4440 + 2 * (k & 1)));
+            uint32_t a1 = Lds8(class_base + __byte_perm(wA[k >> 1], 0, 0x4441 + 2 * (k & 1)));
+            uint32_t b0 = Lds8(class_base + __byte_perm(wB[k >> 1], 0, 0x4440 + 2 * (k & 1)));
+            uint32_t b1 = Lds8(class_base + __byte_perm(wB[k >> 1], 0, 0x4441 + 2 * (k & 1)));
+            pA[k] = t2_base + (a0 * C + a1) * 4u;
+            pB[k] = t2_base + (b0 * C + b1) * 4u;
+          }
+          const uint32_t rowA0 = rowA, rowB0 = rowB;
+          uint32_t peakA = 0, peakB = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint32_t eA = Lds32(rowA + pA[k]);
+            uint32_t eB = Lds32(rowB + pB[k]);
+            peakA = max(peakA, eA);
+            peakB = max(peakB, eB);
+            rowA = eA & 0x7FFFFFFFu;
+            rowB = eB & 0x7FFFFFFFu;
+          }
+          if (it == 0) {
+            if (!warm) rowA = 0;
+          } else {
+            if (peakA >= acc_row)
+              SetReplay(vA, (rowA0 / row_stride) * C, s_t1, s_class, s_mask, tb, acc1, a - 16 + (uint64_t)it * 16, b,
+                        sub_lo, range, hitA, cntA);
+            if (it < 9 && peakB >= acc_row)
+              SetReplay(vB, (rowB0 / row_stride) * C, s_t1, s_class, s_mask, tb, acc1, a + 128 + (uint64_t)it * 16, b,
+                        sub_lo, range, hitB, cntB);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- ordered emission, one slot range per pattern --------------------------
+    const uint32_t cA = cntA > kSetChainHits ? kSetChainHits : cntA;
+    const uint32_t cB = cntB > kSetChainHits ? kSetChainHits : cntB;
+    uint32_t pm = 0;
+#pragma unroll
+    for (int q = 0; q < kSetChainHits; ++q) {
+      if (q < (int)cA) pm |= 1u << (hitA[q] >> 16);
+      if (q < (int)cB) pm |= 1u << (hitB[q] >> 16);
+    }
+    uint32_t warp_pm = pm;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) warp_pm |= __shfl_xor_sync(kFullMask, warp_pm, d);
+    if (lane < K && !((warp_pm >> lane) & 1u)) out.count[(uint64_t)lane * nsub_pat + sub] = 0;
+    if (warp_pm) {
+      bool over = __any_sync(kFullMask, cntA > kSetChainHits || cntB > kSetChainHits);
+      uint32_t todo = warp_pm;
+      while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        uint32_t c = 0;
+#pragma unroll
+        for (int q = 0; q < kSetChainHits; ++q) {
+          if (q < (int)cA && (int)(hitA[q] >> 16) == j) ++c;
+          if (q < (int)cB && (int)(hitB[q] >> 16) == j) ++c;
+        }
+        uint32_t incl = WarpInclusiveScan(c);
+        uint32_t total = __shfl_sync(kFullMask, incl, 31);
+        uint32_t idx = incl - c;
+        const uint64_t slot0 = ((uint64_t)j * nsub_pat + sub) * out.cap;
+        const uint32_t L = tb.match_len[j];
+#pragma unroll
+        for (int q = 0; q < kSetChainHits; ++q) {
+          if (q < (int)cA && (int)(hitA[q] >> 16) == j) {
+            if (idx < out.cap) { uint64_t e = sub_lo + (hitA[q] & 0xFFFFu); out.begin[slot0 + idx] = e - L; out.end[slot0 + idx] = e; }
+            ++idx;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kSetChainHits; ++q) {
+          if (q < (int)cB && (int)(hitB[q] >> 16) == j) {
+            if (idx < out.cap) { uint64_t e = sub_lo + (hitB[q] & 0xFFFFu); out.begin[slot0 + idx] = e - L; out.end[slot0 + idx] = e; }
+            ++idx;
+          }
+        }
+        if (lane == 0) out.count[(uint64_t)j * nsub_pat + sub] = over ? kLaneListOverflow : total;
+      }
+      if (over && lane == 0) *dense_flag = 1u;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K2 fallback: same automaton, 16-byte global loads, non-replicated table,
 // unordered append (dense matches / tables too large for k_dfa_tma).
@@ -925,6 +1135,54 @@ k_resolve_ordered(SubStore st, DenseList dense, ResolveScratch rs, Carry carry_i
     host_status->full_result = v.full_result;
     __threadfence_system();
     host_status->seq = seq;
+    __threadfence_system();
+  }
+}
+
+// One CTA per pattern of a fused set: the same resolve, on that pattern's slice
+// of the stores / scratch / output / status arrays.
+struct CarrySet { Carry c[32]; };
+
+__global__ void __launch_bounds__(512, 1)
+k_resolve_set(SubStore st, uint64_t nsub_pat, DenseList dense, ResolveScratch rs, uint64_t per_cap,
+              uint64_t* __restrict__ out_pairs, PipelineStatus* status, volatile PipelineStatus* host_status,
+              unsigned long long* dense_counts, unsigned int seq, CarrySet carries, uint64_t base_offset) {
+  const uint64_t j = blockIdx.x;
+  SubStore mine = st;
+  mine.begin += j * nsub_pat * st.cap;
+  mine.end += j * nsub_pat * st.cap;
+  mine.count += j * nsub_pat;
+  mine.nsub = nsub_pat;
+  DenseList d = dense;
+  d.begin += j * per_cap;
+  d.end += j * per_cap;
+  d.count = dense_counts + j;
+  d.cap = per_cap;
+  ResolveScratch r = rs;
+  r.reach += j * per_cap;
+  r.take += j * per_cap;
+  r.fin_end += j * per_cap;
+  r.slot += j * per_cap;
+  FaithfulArgs fa{};
+  fa.enabled = 0;
+  const Carry carry = carries.c[j];
+  PipelineStatus* my_status = status + j;
+  ResolveOrderedBody(mine, d, r, carry, base_offset, out_pairs + j * 2 * per_cap, per_cap, fa, my_status);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    PipelineStatus v = *my_status;
+    volatile PipelineStatus* h = host_status + j;
+    h->n_candidates = v.n_candidates;
+    h->n_matches = v.n_matches;
+    h->carry_cur = v.carry_cur;
+    h->carry_tail = v.carry_tail;
+    h->overflow = v.overflow;
+    h->need_cap = v.need_cap;
+    h->need_large = v.need_large;
+    h->dense = v.dense;
+    __threadfence_system();
+    h->seq = seq;
     __threadfence_system();
   }
 }

@@ -437,6 +437,113 @@ bool BuildAutomaton(const LoweredRegexp& lr, CompiledAutomaton* out, std::string
   return true;
 }
 
+bool BuildSetDfa(const std::vector<const CompiledAutomaton*>& members, SetDfa* out) {
+  const int k = static_cast<int>(members.size());
+  if (k < 2 || k > 32) return false;
+  int total = 0;
+  std::vector<int> base(k);
+  for (int j = 0; j < k; ++j) {
+    const CompiledAutomaton* m = members[j];
+    // any anchor-free pattern all of whose matches have the same length (1..17)
+    if (m->nfa.has_anchor || m->reentrant || m->nfa.n_pos == 0 || m->nfa.max_len == kInfLen ||
+        m->nfa.min_len != m->nfa.max_len || m->nfa.min_len < 1 || m->nfa.min_len > 17) return false;
+    base[j] = total;
+    total += m->nfa.n_pos;
+  }
+  if (total > 2048) return false;
+  const int nbits = ((total + 31) / 32) * 32;
+  auto lift = [&](const BitSet& src, int j) {
+    BitSet r(nbits);
+    for (int q = 0; q < members[j]->nfa.n_pos; ++q) if (src.test(q)) r.set(base[j] + q);
+    return r;
+  };
+  BitSet first(nbits);
+  std::vector<BitSet> follow(total, BitSet(nbits)), byte_mask(256, BitSet(nbits)), accept(k, BitSet(nbits));
+  for (int j = 0; j < k; ++j) {
+    const PositionNfa& a = members[j]->nfa;
+    first.or_with(lift(a.first[0], j));
+    accept[j] = lift(a.accept[0], j);
+    for (int q = 0; q < a.n_pos; ++q) follow[base[j] + q] = lift(a.follow[0][q], j);
+    for (int b = 0; b < 256; ++b) byte_mask[b].or_with(lift(a.byte_mask[b], j));
+  }
+  std::map<std::vector<uint32_t>, int> col_to_class;
+  for (int b = 0; b < 256; ++b) {
+    auto it = col_to_class.find(byte_mask[b].w);
+    if (it == col_to_class.end()) it = col_to_class.emplace(byte_mask[b].w, static_cast<int>(col_to_class.size())).first;
+    out->byte_class[b] = static_cast<uint8_t>(it->second);
+  }
+  const int C = static_cast<int>(col_to_class.size());
+  std::vector<int> rep(C, -1);
+  for (int b = 0; b < 256; ++b) if (rep[out->byte_class[b]] < 0) rep[out->byte_class[b]] = b;
+  std::map<BitSet, int> ids;
+  std::vector<BitSet> sets;
+  std::vector<std::vector<int>> trans;
+  BitSet empty(nbits);
+  ids[empty] = 0;
+  sets.push_back(empty);
+  const size_t kMaxStates = 4096;
+  for (size_t s = 0; s < sets.size(); ++s) {
+    trans.emplace_back(C, 0);
+    BitSet reach = first;
+    for (int q = 0; q < total; ++q) if (sets[s].test(q)) reach.or_with(follow[q]);
+    for (int c = 0; c < C; ++c) {
+      BitSet nx = reach;
+      nx.and_with(byte_mask[rep[c]]);
+      auto it = ids.find(nx);
+      if (it == ids.end()) {
+        if (sets.size() >= kMaxStates) return false;
+        it = ids.emplace(nx, static_cast<int>(sets.size())).first;
+        sets.push_back(nx);
+      }
+      trans[s][c] = it->second;
+    }
+  }
+  const int S = static_cast<int>(sets.size());
+  // budget: 16-bit premultiplied rows and a two-byte table of at most 96 KB
+  if (static_cast<size_t>(S) * C > 65535 || static_cast<size_t>(S) * C * C * 4 > 96 * 1024) return false;
+  auto mask_of = [&](int s) {
+    uint32_t m = 0;
+    for (int j = 0; j < k; ++j) { BitSet t = sets[s]; t.and_with(accept[j]); if (t.any()) m |= 1u << j; }
+    return m;
+  };
+  std::vector<int> renum(S, -1);
+  int next_id = 0;
+  for (int s = 0; s < S; ++s) if (!mask_of(s)) renum[s] = next_id++;
+  out->first_accept = next_id;
+  for (int s = 0; s < S; ++s) if (mask_of(s)) renum[s] = next_id++;
+  if (renum[0] != 0) return false;
+  out->n_patterns = k;
+  out->n_states = S;
+  out->n_classes = C;
+  out->next.assign(static_cast<size_t>(S) * C, 0);
+  out->accept_mask.assign(S, 0);
+  for (int s = 0; s < S; ++s) {
+    out->accept_mask[renum[s]] = mask_of(s);
+    for (int c = 0; c < C; ++c) out->next[static_cast<size_t>(renum[s]) * C + c] = static_cast<uint16_t>(renum[trans[s][c]]);
+  }
+  out->match_len.clear();
+  out->max_len = 0;
+  for (int j = 0; j < k; ++j) {
+    out->match_len.push_back(static_cast<uint32_t>(members[j]->nfa.min_len));
+    out->max_len = std::max<uint32_t>(out->max_len, out->match_len.back());
+  }
+  if (out->max_len > 17) return false;          // the kernel warms every chain up on 16 bytes
+  out->t1.resize(out->next.size());
+  for (size_t i = 0; i < out->next.size(); ++i) out->t1[i] = static_cast<uint16_t>(out->next[i] * C);
+  out->t2.assign(static_cast<size_t>(S) * C * C, 0);
+  for (int s = 0; s < S; ++s)
+    for (int c1 = 0; c1 < C; ++c1) {
+      int mid = out->next[static_cast<size_t>(s) * C + c1];
+      for (int c2 = 0; c2 < C; ++c2) {
+        uint32_t fin = out->next[static_cast<size_t>(mid) * C + c2];
+        uint32_t v = fin * static_cast<uint32_t>(C * C * 4);
+        if (mid >= out->first_accept) v |= 0x80000000u;
+        out->t2[(static_cast<size_t>(s) * C + c1) * C + c2] = v;
+      }
+    }
+  return true;
+}
+
 void FlattenTables(const CompiledAutomaton& ca, FlatTables* out) {
   const PositionNfa& a = ca.nfa;
   const int W = a.words;

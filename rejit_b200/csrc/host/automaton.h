@@ -87,6 +87,27 @@ struct CompiledAutomaton {
 // patterns beyond the engine's static limits.
 bool BuildAutomaton(const LoweredRegexp& lr, CompiledAutomaton* out, std::string* error);
 
+// One DFA for a SET of anchor-free fixed-length patterns (regex-dna's nine
+// variants are counted over the same text): the subset construction runs over
+// the union of the patterns' position automata, so one pass over the text
+// advances all patterns at once; an accepting state carries the bitmask of the
+// patterns that end there.  ("fused multi-pattern".)
+struct SetDfa {
+  int n_patterns = 0;
+  int n_states = 0, n_classes = 0, first_accept = 0;
+  std::array<uint8_t, 256> byte_class{};
+  std::vector<uint16_t> next;            // [n_states * n_classes] -> state id
+  std::vector<uint32_t> accept_mask;     // [n_states] bit j: pattern j ends here
+  std::vector<uint32_t> match_len;       // [n_patterns]
+  uint32_t max_len = 0;
+  // flat device layouts
+  std::vector<uint16_t> t1;              // [S*C]   next state * C
+  std::vector<uint32_t> t2;              // [S*C*C] (state after two bytes) * C*C*4, bit 31: accept in between
+};
+// Returns false when the set cannot be fused (a member is not a fixed-length
+// anchor-free DFA pattern, or the tables exceed the kernel's budget).
+bool BuildSetDfa(const std::vector<const CompiledAutomaton*>& members, SetDfa* out);
+
 // The tables in the flat layouts the kernels index (device_program.h:
 // NfaTables; engine.cu: DfaTables).  The engine uploads these vectors verbatim.
 struct FlatTables {

@@ -114,6 +114,10 @@ struct rejit_b200_program {
   Program* prog;
 };
 
+struct rejit_b200_set {
+  SetProgram* set;
+};
+
 struct rejit_b200_text {
   int device;
   void* d_ptr;
@@ -337,6 +341,66 @@ int64_t rejit_b200_match_all_text(rejit_b200_program* program, const rejit_b200_
   FillStats(rs, stats);
   if (out_pairs) *out_pairs = pairs; else free(pairs);
   return r;
+}
+
+rejit_b200_set* rejit_b200_set_create(rejit_b200_program* const* programs, int count) {
+  if (!programs || count < 1) return nullptr;
+  std::vector<Program*> members;
+  for (int i = 0; i < count; ++i) members.push_back(programs[i]->prog);
+  rejit_b200_set* s = new rejit_b200_set;
+  s->set = SetProgram::Create(members);
+  return s;
+}
+
+void rejit_b200_set_free(rejit_b200_set* set) {
+  if (!set) return;
+  delete set->set;
+  delete set;
+}
+
+const char* rejit_b200_set_describe(const rejit_b200_set* set) { return set ? set->set->describe().c_str() : ""; }
+
+int rejit_b200_match_all_set_device(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
+                                    int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  RunStats rs;
+  int r = MatchAllSetResident(device, set->set, static_cast<const uint8_t*>(d_text), text_length, out_counts, nullptr,
+                              stats ? &rs : nullptr, &error);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  FillStats(rs, stats);
+  return 0;
+}
+
+int rejit_b200_match_all_set_device_slab(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
+                                         uint64_t own_begin, uint64_t own_end, uint64_t base_offset,
+                                         const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
+                                         int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  RunStats rs;
+  const int k = set->set->size();
+  std::vector<Carry> in(k), out(k);
+  if (carry_in) for (int j = 0; j < k; ++j) { in[j].cur = carry_in[j].cur; in[j].tail = carry_in[j].tail; }
+  SlabView view;
+  view.own_begin = own_begin;
+  view.own_end = own_end;
+  view.base_offset = base_offset;
+  int r = MatchAllSetResident(device, set->set, static_cast<const uint8_t*>(d_text), text_length, out_counts, nullptr,
+                              stats ? &rs : nullptr, &error, &view, in.data(), out.data());
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  if (carry_out) for (int j = 0; j < k; ++j) { carry_out[j].cur = out[j].cur; carry_out[j].tail = out[j].tail; }
+  FillStats(rs, stats);
+  return 0;
+}
+
+int rejit_b200_match_all_set_text(rejit_b200_set* set, const rejit_b200_text* text, int64_t* out_counts,
+                                  uint64_t** out_pairs, rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  RunStats rs;
+  int r = MatchAllSetResident(text->device, set->set, static_cast<const uint8_t*>(text->d_ptr), text->length,
+                              out_counts, out_pairs, stats ? &rs : nullptr, &error);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  FillStats(rs, stats);
+  return 0;
 }
 
 int64_t rejit_b200_match_all_device_slab(rejit_b200_program* program, int device, const void* d_text,

@@ -140,6 +140,39 @@ size_t Regej::MatchAllParallel(const char* text, size_t text_size, vector<Match>
   return matches ? matches->size() : static_cast<size_t>(n);
 }
 
+size_t Regej::MatchAllSet(const std::vector<Regej*>& patterns, const char* text, size_t text_size,
+                          std::vector<std::vector<Match> >* matches) {
+  std::vector<rejit_b200_program*> progs;
+  for (Regej* r : patterns) {
+    if (!r->Compile(kMatchAll)) return 0;
+    progs.push_back(r->rinfo_->program);
+  }
+  if (progs.empty()) return 0;
+  char err[256];
+  err[0] = 0;
+  rejit_b200_set* set = rejit_b200_set_create(progs.data(), static_cast<int>(progs.size()));
+  rejit_b200_text* dtext = rejit_b200_text_upload(0, text, text_size, err, sizeof err);
+  if (!set || !dtext) Fatal("MatchAllSet", err);
+  std::vector<int64_t> counts(progs.size(), 0);
+  std::vector<uint64_t*> pairs(progs.size(), nullptr);
+  if (rejit_b200_match_all_set_text(set, dtext, counts.data(), pairs.data(), nullptr, err, sizeof err) != 0)
+    Fatal("MatchAllSet", err);
+  size_t total = 0;
+  if (matches) matches->resize(progs.size());
+  for (size_t j = 0; j < progs.size(); ++j) {
+    if (matches) {
+      std::vector<Match>& out = (*matches)[j];
+      out.reserve(out.size() + static_cast<size_t>(counts[j]));
+      for (int64_t i = 0; i < counts[j]; ++i) out.push_back(Match{text + pairs[j][2 * i], text + pairs[j][2 * i + 1]});
+    }
+    total += static_cast<size_t>(counts[j]);
+    rejit_b200_free(pairs[j]);
+  }
+  rejit_b200_text_free(dtext);
+  rejit_b200_set_free(set);
+  return total;
+}
+
 size_t Regej::MatchAllCount(const string& text) { return MatchAllCount(text.c_str(), text.size()); }
 size_t Regej::MatchAllCount(const char* text, size_t text_size) {
   vector<Match> found;

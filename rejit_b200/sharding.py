@@ -60,3 +60,40 @@ def stitched_count(dist, rank: int, world: int, slab_lo: int,
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         if int(flag.item()) == 0:
             return sum(int(r[2]) for r in rows), rounds
+
+
+def stitched_counts_set(dist, rank: int, world: int, slab_lo: int, k: int, run, device=None):
+    """Set version: run(carries) -> (counts[k], carries_out[k]) with carries as
+    lists of (cur, tail) in global offsets.  One all-gather of a [k, 3] block per
+    rank; a rank resolves again only if some member's arriving chain differs.
+    Returns (global counts[k], collective rounds)."""
+    import torch
+    used = [(slab_lo, NO_TAIL)] * k
+    counts, couts = run(used)
+    rounds = 0
+    while True:
+        rec = torch.tensor([[couts[j][0], couts[j][1] if couts[j][1] != NO_TAIL else -1, counts[j]] for j in range(k)] +
+                           [[slab_lo, 0, 0]], dtype=torch.int64, device=device)
+        if world > 1:
+            gathered = [torch.zeros_like(rec) for _ in range(world)]
+            dist.all_gather(gathered, rec)
+            rows = [g.tolist() for g in gathered]
+        else:
+            rows = [rec.tolist()]
+        rounds += 1
+        changed = False
+        if rank > 0:
+            lo_r = rows[rank][k][0]
+            want = []
+            for j in range(k):
+                left_cur, left_tail = rows[rank - 1][j][0], rows[rank - 1][j][1]
+                want.append((max(left_cur, lo_r), left_tail if left_tail == lo_r else NO_TAIL))
+            if want != used:
+                used = want
+                counts, couts = run(used)
+                changed = True
+        flag = torch.tensor([1 if changed else 0], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) == 0:
+            return [sum(int(r[j][2]) for r in rows) for j in range(k)], rounds

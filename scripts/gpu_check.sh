@@ -12,6 +12,7 @@ echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out
 tail -5 gpurun_out/bench.err
 echo "== bench reference" ; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>> gpurun_out/bench.err | tee gpurun_out/bench_reference.json
 if [ "${RJ_EXTRA:-0}" = "1" ]; then
+echo "== e2e probe"; timeout 300 python scripts/e2e_probe.py 2>&1 | tail -12 | cut -c1-300
 echo "== bench_extra"; timeout 1200 python scripts/bench_extra.py 2>&1 | tee gpurun_out/bench_extra.jsonl | cut -c1-400
 fi
 if [ "${RJ_SWEEP:-0}" = "1" ]; then
@@ -22,7 +23,7 @@ echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_bench.log 2>&1
 tail -3 gpurun_out/ncu_bench.log
 echo "== ncu full dfa"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dfa_tma -s 9 -c 2 -o gpurun_out/prof_dfa -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_set_tma -s 3 -c 2 -o gpurun_out/prof_dfa -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 fi
 ls -la gpurun_out

@@ -301,6 +301,64 @@ int64_t hostsim_slab_run(const char* pattern, size_t plen, const uint8_t* text, 
   return (int64_t)res.size();
 }
 
+// Fused pattern set: emulates k_set_tma (same chain geometry as k_dfa_tma, the
+// union DFA's pair table) and resolves pattern `which`.  -1: parse error,
+// -5: the set cannot be fused.
+int64_t hostsim_set_match_all(const char* joined, size_t len, char sep, const uint8_t* text, uint64_t n, int which,
+                              uint64_t* out_pairs, uint64_t cap) {
+  std::vector<std::string> pats;
+  std::string cur;
+  for (size_t i = 0; i < len; ++i) { if (joined[i] == sep) { pats.push_back(cur); cur.clear(); } else cur.push_back(joined[i]); }
+  pats.push_back(cur);
+  std::vector<Compiled> comp(pats.size());
+  std::vector<const CompiledAutomaton*> members;
+  std::string error;
+  for (size_t j = 0; j < pats.size(); ++j) {
+    if (!CompilePattern(pats[j].data(), pats[j].size(), 1, &comp[j], &error)) return -1;
+    members.push_back(&comp[j].ca);
+  }
+  SetDfa d;
+  if (!BuildSetDfa(members, &d)) return -5;
+  const uint32_t C = (uint32_t)d.n_classes, C2 = C * C;
+  const uint32_t acc_row = (uint32_t)d.first_accept * C2 * 4;
+  std::vector<Cands> per(pats.size());
+  auto report = [&](uint32_t state, uint64_t e, uint64_t a, uint64_t b) {
+    uint32_t m = d.accept_mask[state];
+    for (int j = 0; m; ++j, m >>= 1)
+      if ((m & 1u) && e > a && e <= b && e >= d.match_len[j]) per[j].push_back({e - d.match_len[j], e});
+  };
+  const uint64_t kStream = 272;
+  for (uint64_t a0 = 0; a0 < n; a0 += kStream) {
+    const uint64_t seg[3] = {a0, a0 + 144, a0 + kStream};
+    for (int h = 0; h < 2; ++h) {
+      uint64_t a = seg[h], b = std::min<uint64_t>(n, seg[h + 1]);
+      if (a >= n) break;
+      uint64_t p = a >= 16 ? a - 16 : 0;
+      uint32_t row = 0;                       // state * C2 * 4
+      while (p < b) {
+        uint32_t state = row / (C2 * 4);
+        uint32_t c1 = d.byte_class[text[p]];
+        uint32_t c2 = (p + 1 < n) ? d.byte_class[text[p + 1]] : 0;
+        uint32_t ent = d.t2[(state * C + c1) * C + c2];
+        uint32_t mid = d.t1[state * C + c1] / C;
+        if (((ent & 0x80000000u) != 0) != ((int)mid >= d.first_accept)) return -6;
+        if ((int)mid >= d.first_accept) report(mid, p + 1, a, b);
+        row = ent & 0x7FFFFFFFu;
+        if (p + 1 < n) {
+          uint32_t fin = d.t1[mid * C + c2] / C;
+          if (fin * C2 * 4 != row) return -6;
+          if (row >= acc_row) report(fin, p + 2, a, b);
+        }
+        p += 2;
+      }
+    }
+  }
+  Cands res;
+  ResolveSequential(per[which], ChainState{0, kNoMatch}, &res, nullptr);
+  for (size_t i = 0; i < res.size() && i < cap; ++i) { out_pairs[2 * i] = res[i].first; out_pairs[2 * i + 1] = res[i].second; }
+  return (int64_t)res.size();
+}
+
 int hostsim_match_full(const char* pattern, size_t plen, const uint8_t* text, uint64_t n) {
   Compiled c;
   std::string error;

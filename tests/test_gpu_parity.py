@@ -211,6 +211,35 @@ def test_full_size_properties(rj):
         assert got.shape == exp.shape and (got == exp).all(), p
 
 
+def test_fused_pattern_set(rj):
+    """the nine regex-dna patterns fused into one scan must
+    give, per pattern, exactly the per-pattern MatchAll result."""
+    from rejit_b200 import workloads as W
+    seq = W.fasta_sequence(300000)                  # 3 MB
+    data = seq.tobytes()
+    rs = rj.RegejSet(W.DNA_PATTERNS)
+    assert rs.describe().startswith("fused set: 9 patterns"), rs.describe()
+    fused = rs.match_all(seq)
+    for p, got in zip(W.DNA_PATTERNS, fused):
+        assert got == O.Oracle(p).match_all(data), p
+    # counts-only device path, repeated (steady state) and on ragged lengths
+    for cut in (len(seq), 8704 * 3, 8704 * 3 + 5, 100, 17):
+        dt = rj.DeviceText(seq[:cut])
+        try:
+            st = rj.Stats()
+            counts = rs.match_all_device(dt, stats=st)
+            assert counts == [len(O.Oracle(p).match_all(data[:cut])) for p in W.DNA_PATTERNS], cut
+            assert st.strategy == 4 and st.launches == 2
+        finally:
+            dt.free()
+    # mixed lengths and a dense member (falls back to member-by-member runs)
+    t = fuzzgen.rand_text(random.Random(4), "acgt", 50000)
+    for pats in (["acg", "ttgca", "a[ct]g"], ["a", "cg"], ["acgt", "x+"]):
+        got = rj.RegejSet(pats).match_all(t)
+        for p, g in zip(pats, got):
+            assert g == O.Oracle(p).match_all(t), (pats, p)
+
+
 def test_multi_gpu_equals_single(rj):
     if rj.device_count() < 2:
         pytest.skip("needs 2 GPUs")

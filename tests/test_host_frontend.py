@@ -175,6 +175,28 @@ def test_hostsim_slab_stitching(hostsim):
         checked += 1
 
 
+def test_fused_set_tables_on_cpu():
+    """Union DFA of a pattern set (k_set_tma's tables) emulated by tests/hostsim.cc."""
+    import ctypes
+    from rejit_b200 import workloads as W
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libhostsim.so"))
+    L.hostsim_set_match_all.restype = ctypes.c_int64
+    L.hostsim_set_match_all.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char, ctypes.c_char_p,
+                                        ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64]
+    seq = W.fasta_sequence(40000).tobytes()
+    r = random.Random(1)
+    sets = [W.DNA_PATTERNS, ["acg", "ttgca", "a[ct]g"], ["ac|gt", "tgc|aaa", "c[ag]t|ggg"]]
+    for pats in sets:
+        joined = "\x01".join(pats).encode()
+        for j, p in enumerate(pats):
+            out = (ctypes.c_uint64 * 100000)()
+            k = L.hostsim_set_match_all(joined, len(joined), b"\x01", seq, len(seq), j, out, 50000)
+            assert k >= 0, (pats, k)
+            assert [(out[2 * i], out[2 * i + 1]) for i in range(k)] == O.Oracle(p).match_all(seq), (pats, p)
+    joined = b"acgt\x01x+"
+    assert L.hostsim_set_match_all(joined, len(joined), b"\x01", seq, len(seq), 0, None, 0) == -5
+
+
 def test_workload_shaped_parity_on_cpu(hostsim):
     from rejit_b200 import workloads as W
     seq = W.fasta_sequence(20000).tobytes()          # 200 kB
