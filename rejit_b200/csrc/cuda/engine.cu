@@ -456,7 +456,10 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         if (!ReserveStore(&c->sub_b, &c->sub_e, &c->sub_count, {cand.nsub, cand.cap}, error)) return false;
         cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
         int blocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)grid_full);
-        k_lit_scan<4><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, slab.own, cand);
+        if (dp->needle_len >= 4)
+          k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, slab.own, cand);
+        else
+          k_lit_scan<false><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, slab.own, cand);
         if (stats) stats->launches += 1;
         break;
       }
@@ -471,7 +474,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         // the needle may sit up to window_hi bytes after an owned start
         ScanRange hit_range{slab.own.own_begin, slab.own.own_end + ca.window_hi + 1};
         int blocks = (int)std::min<uint64_t>((hs.nsub + 7) / 8, (uint64_t)grid_full);
-        k_lit_scan<4><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, hit_range, hs);
+        k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, hit_range, hs);
         if (stats) cudaEventRecord(c->ev[1], s);
         k_gather_hits<<<1, 512, 0, s>>>(hs, hits, d_status);
         cand.cap = kWinSubHits * wsize;
@@ -758,6 +761,7 @@ DeviceSet* SetProgram::OnDevice(int device, std::string* error) {
     d->tb.n_states = f.n_states;
     d->tb.n_classes = f.n_classes;
     d->tb.first_accept = f.first_accept;
+    d->tb.row_shift = f.row_shift;
     d->fixed_smem = f.t2.size() * 4 + f.accept_mask.size() * 4 + f.t1.size() * 2 + 16 + 256 + 8 * 32 + 512;
     per_device_[device] = d;
   }

@@ -217,7 +217,60 @@ __device__ __forceinline__ void TmaLoad1D(void* smem_dst, const void* gmem_src, 
 // Survivors (rare) compare the rest of the needle from global memory.
 // Algorithmic traffic: N bytes read + 16 bytes written per occurrence.
 // ===========================================================================
-template <int kUnroll>
+// Rare path of k_lit_scan, kept out of line so that the hot loop stays small:
+// validates the survivors of one 16-byte lane group (bounds, ownership, the rest
+// of the needle) and appends them in offset order.  Called by the whole warp.
+__device__ __noinline__ void LitEmit(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restrict__ needle,
+                                     uint32_t m, uint32_t p4, uint32_t pmask, const ScanRange& range,
+                                     const SubStore& out, uint64_t sub, uint32_t& k, uint64_t my, uint4 v, uint32_t nx) {
+  const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
+  uint32_t valid = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t x = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3));
+    if (((x ^ p4) & pmask) == 0) valid |= 1u << j;
+  }
+  uint32_t hh = valid;
+  while (hh) {
+    int j = __ffs(hh) - 1;
+    hh &= hh - 1;
+    uint64_t pos = my + j;
+    bool ok = pos >= range.own_begin && pos < range.own_end && pos + m <= n;
+    for (uint32_t i = 4; i < m && ok; ++i) ok = (text[pos + i] == needle[i]);
+    if (!ok) valid &= ~(1u << j);
+  }
+  __syncwarp();
+  uint32_t c = __popc(valid);
+  uint32_t incl = WarpInclusiveScan(c);
+  uint32_t total = __shfl_sync(kFullMask, incl, 31);
+  uint32_t idx = k + incl - c;
+  while (valid) {
+    int j = __ffs(valid) - 1;
+    valid &= valid - 1;
+    if (idx < out.cap) {
+      out.begin[sub * out.cap + idx] = my + j;
+      out.end[sub * out.cap + idx] = my + j + m;
+    }
+    ++idx;
+  }
+  __syncwarp();
+  k += total;
+}
+
+template <bool kFull4>
+__device__ __forceinline__ bool LitAny(const uint4& v, uint32_t nx, uint32_t p4, uint32_t pmask) {
+  const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t x = (j & 3) ? __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3)) : w[j >> 2];
+    if (kFull4) any |= (x == p4);
+    else any |= (((x ^ p4) & pmask) == 0);
+  }
+  return any;
+}
+
+template <bool kFull4>
 __global__ void __launch_bounds__(256)
 k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restrict__ needle,
            uint32_t m, uint32_t p4, uint32_t pmask, ScanRange range, SubStore out) {
@@ -229,63 +282,47 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
     const uint64_t sub_lo = sub * kLitSubBytes;
     uint32_t k = 0;
     const bool live = sub_lo < n && sub_lo + kLitSubBytes > range.own_begin && sub_lo < range.own_end;
-    if (live) {
-      for (uint32_t pc = 0; pc < kPieces; pc += kUnroll) {
+    if (live && sub_lo + kLitSubBytes + 16 <= n) {
+      // ---- interior sub-region: unguarded 16-byte loads, 4 pieces per step, the
+      // next step's loads are issued before the current step is examined --------
+      const uint4* base = reinterpret_cast<const uint4*>(text + sub_lo) + lane;
+      uint4 nxt[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nxt[u] = __ldg(base + u * 32);
+#pragma unroll 1
+      for (uint32_t pc = 0; pc < kPieces; pc += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = nxt[u];
+        if (pc + 4 < kPieces) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) nxt[u] = __ldg(base + (pc + 4 + u) * 32);
+        } else {
+          // word that follows the sub-region (in bounds: sub_lo + 16 KB + 16 <= n)
+          nxt[0].x = __ldg(reinterpret_cast<const uint32_t*>(text + sub_lo + kLitSubBytes));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          // lane l needs the first word of lane l+1; lane 31 that of lane 0 of the next piece
+          uint32_t up = __shfl_down_sync(kFullMask, v[u].x, 1);
+          uint32_t wrap = __shfl_sync(kFullMask, (u < 3) ? v[u + 1].x : nxt[0].x, 0);
+          uint32_t nx = (lane == 31) ? wrap : up;
+          bool any = LitAny<kFull4>(v[u], nx, p4, pmask);
+          if (__any_sync(kFullMask, any))
+            LitEmit(text, n, needle, m, p4, pmask, range, out, sub, k,
+                    sub_lo + (uint64_t)(pc + u) * 512 + (uint64_t)lane * 16, v[u], nx);
+        }
+      }
+    } else if (live) {
+      // ---- first / last sub-regions of the text: guarded loads ------------------
+      for (uint32_t pc = 0; pc < kPieces; ++pc) {
+        const uint64_t my = sub_lo + (uint64_t)pc * 512 + (uint64_t)lane * 16;
         if (sub_lo + (uint64_t)pc * 512 >= n) break;
-        uint4 v[kUnroll];
-        uint32_t nx[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          uint64_t my = sub_lo + (uint64_t)(pc + u) * 512 + (uint64_t)lane * 16;
-          v[u] = (my < n) ? LoadText16(text, n, my) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          uint64_t my = sub_lo + (uint64_t)(pc + u) * 512 + (uint64_t)lane * 16;
-          nx[u] = __shfl_down_sync(kFullMask, v[u].x, 1);
-          if (lane == 31) nx[u] = (my + 16 < n) ? LoadText4(text, n, my + 16) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const uint64_t my = sub_lo + (uint64_t)(pc + u) * 512 + (uint64_t)lane * 16;
-          const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nx[u]};
-          uint32_t hits = 0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            uint32_t x = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3));
-            if (((x ^ p4) & pmask) == 0) hits |= 1u << j;
-          }
-          if (__any_sync(kFullMask, hits != 0)) {
-            // rare: validate the survivors, then append them in offset order
-            uint32_t valid = 0;
-            uint32_t hh = hits;
-            while (hh) {
-              int j = __ffs(hh) - 1;
-              hh &= hh - 1;
-              uint64_t pos = my + j;
-              if (pos < range.own_begin || pos >= range.own_end || pos + m > n) continue;
-              bool ok = true;
-              for (uint32_t i = 4; i < m && ok; ++i) ok = (text[pos + i] == needle[i]);
-              if (ok) valid |= 1u << j;
-            }
-            __syncwarp();
-            uint32_t c = __popc(valid);
-            uint32_t incl = WarpInclusiveScan(c);
-            uint32_t total = __shfl_sync(kFullMask, incl, 31);
-            uint32_t idx = k + incl - c;
-            while (valid) {
-              int j = __ffs(valid) - 1;
-              valid &= valid - 1;
-              if (idx < out.cap) {
-                out.begin[sub * out.cap + idx] = my + j;
-                out.end[sub * out.cap + idx] = my + j + m;
-              }
-              ++idx;
-            }
-            __syncwarp();
-            k += total;
-          }
-        }
+        uint4 v = (my < n) ? LoadText16(text, n, my) : make_uint4(0, 0, 0, 0);
+        uint32_t nx = __shfl_down_sync(kFullMask, v.x, 1);
+        if (lane == 31) nx = (my + 16 < n) ? LoadText4(text, n, my + 16) : 0u;
+        bool any = LitAny<kFull4>(v, nx, p4, pmask);
+        if (__any_sync(kFullMask, any)) LitEmit(text, n, needle, m, p4, pmask, range, out, sub, k, my, v, nx);
       }
     }
     if (lane == 0) out.count[sub] = k;
@@ -532,35 +569,28 @@ struct SetTables {
   uint32_t match_len[32];
   int n_patterns;
   int n_states, n_classes, first_accept;
+  int row_shift;                       // pair-table rows are 2^row_shift bytes
 };
 
 constexpr int kSetChainHits = 4;
 
-__device__ __forceinline__ void SetReplay(const uint4& v, uint32_t st1, const uint16_t* s_t1, const uint8_t* s_class,
-                                          const uint32_t* s_mask, const SetTables& tb, uint32_t acc1, uint64_t p0,
-                                          uint64_t limit, uint64_t sub_lo, const ScanRange& range, uint32_t* hit,
-                                          uint32_t& cnt) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  const uint32_t C = (uint32_t)tb.n_classes;
-  for (int i = 0; i < 16 && p0 + i < limit; ++i) {
-    uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-    st1 = s_t1[st1 + s_class[c]];
-    if (st1 >= acc1) {
-      uint64_t e = p0 + i + 1;
-      uint32_t m = s_mask[st1 / C];
-      while (m) {
-        int j = __ffs(m) - 1;
-        m &= m - 1;
-        uint32_t L = tb.match_len[j];
-        if (e >= L) {
-          uint64_t s = e - L;
-          if (s >= range.own_begin && s < range.own_end) {
+// records the ends of the patterns accepted in `state` at text offset `e`
+__device__ __forceinline__ void SetRecord(uint32_t state, uint64_t e, uint64_t limit, const uint32_t* s_mask,
+                                          const SetTables& tb, uint64_t sub_lo, const ScanRange& range,
+                                          uint32_t* hit, uint32_t& cnt) {
+  if (e > limit) return;
+  uint32_t m = s_mask[state];
+  while (m) {
+    int j = __ffs(m) - 1;
+    m &= m - 1;
+    uint32_t L = tb.match_len[j];
+    if (e >= L) {
+      uint64_t s = e - L;
+      if (s >= range.own_begin && s < range.own_end) {
 #pragma unroll
-            for (int q = 0; q < kSetChainHits; ++q)
-              if (cnt == (uint32_t)q) hit[q] = (uint32_t)(e - sub_lo) | ((uint32_t)j << 16);
-            ++cnt;
-          }
-        }
+        for (int q = 0; q < kSetChainHits; ++q)
+          if (cnt == (uint32_t)q) hit[q] = (uint32_t)(e - sub_lo) | ((uint32_t)j << 16);
+        ++cnt;
       }
     }
   }
@@ -575,9 +605,10 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
   const int warps_per_cta = blockDim.x >> 5;
   const uint32_t C = (uint32_t)tb.n_classes;
   const uint32_t C2 = C * C;
-  const int t2_entries = tb.n_states * (int)C2;
+  const int t2_entries = tb.n_states << (tb.row_shift - 2);
   const int t1_entries = tb.n_states * (int)C;
-  // layout: [t2 u32][accept masks u32][t1 u16][class map 256][barriers][tiles]
+  (void)C2;
+  // layout: [t2 u32, padded rows][accept masks u32][t1 u16][class map 256][barriers][tiles]
   uint32_t* s_t2 = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* s_mask = s_t2 + t2_entries;
   uint16_t* s_t1 = reinterpret_cast<uint16_t*>(s_mask + tb.n_states);
@@ -597,9 +628,8 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
   uint8_t* tile = s_tiles + (size_t)warp_in_cta * kDfaTileBytes;
   const uint32_t my_warm_addr = SmemAddr(tile) + (uint32_t)lane * kDfaStreamBytes;
   const uint32_t t2_base = SmemAddr(s_t2);
-  const uint32_t row_stride = C2 * 4u;
-  const uint32_t acc_row = (uint32_t)tb.first_accept * row_stride;
-  const uint32_t acc1 = (uint32_t)tb.first_accept * C;
+  const int row_shift = tb.row_shift;
+  const uint32_t acc_row = (uint32_t)tb.first_accept << row_shift;
   const uint32_t class_base = SmemAddr(s_class);
   const int K = tb.n_patterns;
   uint32_t phase = 0;
@@ -648,24 +678,56 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
           }
           const uint32_t rowA0 = rowA, rowB0 = rowB;
           uint32_t peakA = 0, peakB = 0;
+          uint32_t eA[8], eB[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            uint32_t eA = Lds32(rowA + pA[k]);
-            uint32_t eB = Lds32(rowB + pB[k]);
-            peakA = max(peakA, eA);
-            peakB = max(peakB, eB);
-            rowA = eA & 0x7FFFFFFFu;
-            rowB = eB & 0x7FFFFFFFu;
+            eA[k] = Lds32(rowA + pA[k]);
+            eB[k] = Lds32(rowB + pB[k]);
+            peakA = max(peakA, eA[k]);
+            peakB = max(peakB, eB[k]);
+            rowA = eA[k] & 0x7FFFFFFFu;
+            rowB = eB[k] & 0x7FFFFFFFu;
           }
           if (it == 0) {
             if (!warm) rowA = 0;
           } else {
-            if (peakA >= acc_row)
-              SetReplay(vA, (rowA0 / row_stride) * C, s_t1, s_class, s_mask, tb, acc1, a - 16 + (uint64_t)it * 16, b,
-                        sub_lo, range, hitA, cntA);
-            if (it < 9 && peakB >= acc_row)
-              SetReplay(vB, (rowB0 / row_stride) * C, s_t1, s_class, s_mask, tb, acc1, a + 128 + (uint64_t)it * 16, b,
-                        sub_lo, range, hitB, cntB);
+            // rare: some pair of this group accepted — walk the saved entries
+            if (peakA >= acc_row) {
+              uint32_t prev = rowA0;
+              const uint64_t p0 = a - 16 + (uint64_t)it * 16;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t e = eA[k];
+                if (e >= acc_row) {
+                  if (e & 0x80000000u) {
+                    uint32_t c1 = s_class[__byte_perm(wA[k >> 1], 0, 0x4440 + 2 * (k & 1))];
+                    uint32_t mid = s_t1[(prev >> row_shift) * C + c1] / C;
+                    SetRecord(mid, p0 + 2 * k + 1, b, s_mask, tb, sub_lo, range, hitA, cntA);
+                  }
+                  if ((e & 0x7FFFFFFFu) >= acc_row)
+                    SetRecord((e & 0x7FFFFFFFu) >> row_shift, p0 + 2 * k + 2, b, s_mask, tb, sub_lo, range, hitA, cntA);
+                }
+                prev = e & 0x7FFFFFFFu;
+              }
+            }
+            if (it < 9 && peakB >= acc_row) {
+              uint32_t prev = rowB0;
+              const uint64_t p0 = a + 128 + (uint64_t)it * 16;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t e = eB[k];
+                if (e >= acc_row) {
+                  if (e & 0x80000000u) {
+                    uint32_t c1 = s_class[__byte_perm(wB[k >> 1], 0, 0x4440 + 2 * (k & 1))];
+                    uint32_t mid = s_t1[(prev >> row_shift) * C + c1] / C;
+                    SetRecord(mid, p0 + 2 * k + 1, b, s_mask, tb, sub_lo, range, hitB, cntB);
+                  }
+                  if ((e & 0x7FFFFFFFu) >= acc_row)
+                    SetRecord((e & 0x7FFFFFFFu) >> row_shift, p0 + 2 * k + 2, b, s_mask, tb, sub_lo, range, hitB, cntB);
+                }
+                prev = e & 0x7FFFFFFFu;
+              }
+            }
           }
         }
       }

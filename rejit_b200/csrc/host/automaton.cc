@@ -500,7 +500,7 @@ bool BuildSetDfa(const std::vector<const CompiledAutomaton*>& members, SetDfa* o
   }
   const int S = static_cast<int>(sets.size());
   // budget: 16-bit premultiplied rows and a two-byte table of at most 96 KB
-  if (static_cast<size_t>(S) * C > 65535 || static_cast<size_t>(S) * C * C * 4 > 96 * 1024) return false;
+  if (static_cast<size_t>(S) * C > 65535) return false;
   auto mask_of = [&](int s) {
     uint32_t m = 0;
     for (int j = 0; j < k; ++j) { BitSet t = sets[s]; t.and_with(accept[j]); if (t.any()) m |= 1u << j; }
@@ -530,15 +530,22 @@ bool BuildSetDfa(const std::vector<const CompiledAutomaton*>& members, SetDfa* o
   if (out->max_len > 17) return false;          // the kernel warms every chain up on 16 bytes
   out->t1.resize(out->next.size());
   for (size_t i = 0; i < out->next.size(); ++i) out->t1[i] = static_cast<uint16_t>(out->next[i] * C);
-  out->t2.assign(static_cast<size_t>(S) * C * C, 0);
+  // pair-table rows are padded to a power of two so that the state of a row
+  // offset is a shift
+  int row_words = 1;
+  while (row_words < C * C) row_words <<= 1;
+  out->row_shift = 2;
+  while ((1 << out->row_shift) < row_words * 4) ++out->row_shift;
+  if (static_cast<size_t>(S) * row_words * 4 > 128 * 1024) return false;
+  out->t2.assign(static_cast<size_t>(S) * row_words, 0);
   for (int s = 0; s < S; ++s)
     for (int c1 = 0; c1 < C; ++c1) {
       int mid = out->next[static_cast<size_t>(s) * C + c1];
       for (int c2 = 0; c2 < C; ++c2) {
         uint32_t fin = out->next[static_cast<size_t>(mid) * C + c2];
-        uint32_t v = fin * static_cast<uint32_t>(C * C * 4);
+        uint32_t v = fin << out->row_shift;
         if (mid >= out->first_accept) v |= 0x80000000u;
-        out->t2[(static_cast<size_t>(s) * C + c1) * C + c2] = v;
+        out->t2[static_cast<size_t>(s) * row_words + c1 * C + c2] = v;
       }
     }
   return true;

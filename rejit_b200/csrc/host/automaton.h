@@ -102,7 +102,8 @@ struct SetDfa {
   uint32_t max_len = 0;
   // flat device layouts
   std::vector<uint16_t> t1;              // [S*C]   next state * C
-  std::vector<uint32_t> t2;              // [S*C*C] (state after two bytes) * C*C*4, bit 31: accept in between
+  std::vector<uint32_t> t2;              // [S][2^row_shift / 4]: (state after two bytes) << row_shift, bit 31: accept in between
+  int row_shift = 0;                     // log2 of the padded row size in bytes
 };
 // Returns false when the set cannot be fused (a member is not a fixed-length
 // anchor-free DFA pattern, or the tables exceed the kernel's budget).

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -122,7 +123,16 @@ struct rejit_b200_text {
   int device;
   void* d_ptr;
   size_t length;
+  size_t capacity;
 };
+
+namespace {
+// Freed text buffers are kept (two per process) so that a loop of
+// upload / match / free does not pay cudaMalloc + cudaFree every time.
+struct CachedText { int device; void* p; size_t capacity; };
+std::mutex g_text_cache_mu;
+std::vector<CachedText> g_text_cache;
+}  // namespace
 
 extern "C" {
 
@@ -310,8 +320,23 @@ int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, con
 rejit_b200_text* rejit_b200_text_upload(int device, const char* text, size_t text_length, char* err,
                                         size_t err_length) {
   std::string error;
-  void* d = DeviceAlloc(device, text_length ? text_length : 1, &error);
-  if (!d) { SetErr(err, err_length, error); return nullptr; }
+  void* d = nullptr;
+  size_t capacity = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_text_cache_mu);
+    for (size_t i = 0; i < g_text_cache.size(); ++i)
+      if (g_text_cache[i].device == device && g_text_cache[i].capacity >= text_length) {
+        d = g_text_cache[i].p;
+        capacity = g_text_cache[i].capacity;
+        g_text_cache.erase(g_text_cache.begin() + i);
+        break;
+      }
+  }
+  if (!d) {
+    capacity = text_length ? text_length : 1;
+    d = DeviceAlloc(device, capacity, &error);
+    if (!d) { SetErr(err, err_length, error); return nullptr; }
+  }
   if (text_length && !CopyToDevice(device, d, text, text_length, &error)) {
     DeviceFree(device, d);
     SetErr(err, err_length, error);
@@ -321,12 +346,20 @@ rejit_b200_text* rejit_b200_text_upload(int device, const char* text, size_t tex
   t->device = device;
   t->d_ptr = d;
   t->length = text_length;
+  t->capacity = capacity;
   return t;
 }
 
 void rejit_b200_text_free(rejit_b200_text* text) {
   if (!text) return;
-  DeviceFree(text->device, text->d_ptr);
+  {
+    std::lock_guard<std::mutex> lk(g_text_cache_mu);
+    if (g_text_cache.size() < 2) {
+      g_text_cache.push_back({text->device, text->d_ptr, text->capacity});
+      text->d_ptr = nullptr;
+    }
+  }
+  if (text->d_ptr) DeviceFree(text->device, text->d_ptr);
   delete text;
 }
 

@@ -319,8 +319,9 @@ int64_t hostsim_set_match_all(const char* joined, size_t len, char sep, const ui
   }
   SetDfa d;
   if (!BuildSetDfa(members, &d)) return -5;
-  const uint32_t C = (uint32_t)d.n_classes, C2 = C * C;
-  const uint32_t acc_row = (uint32_t)d.first_accept * C2 * 4;
+  const uint32_t C = (uint32_t)d.n_classes;
+  const uint32_t RW = (1u << d.row_shift) / 4;
+  const uint32_t acc_row = (uint32_t)d.first_accept << d.row_shift;
   std::vector<Cands> per(pats.size());
   auto report = [&](uint32_t state, uint64_t e, uint64_t a, uint64_t b) {
     uint32_t m = d.accept_mask[state];
@@ -334,19 +335,19 @@ int64_t hostsim_set_match_all(const char* joined, size_t len, char sep, const ui
       uint64_t a = seg[h], b = std::min<uint64_t>(n, seg[h + 1]);
       if (a >= n) break;
       uint64_t p = a >= 16 ? a - 16 : 0;
-      uint32_t row = 0;                       // state * C2 * 4
+      uint32_t row = 0;                       // state << row_shift
       while (p < b) {
-        uint32_t state = row / (C2 * 4);
+        uint32_t state = row >> d.row_shift;
         uint32_t c1 = d.byte_class[text[p]];
         uint32_t c2 = (p + 1 < n) ? d.byte_class[text[p + 1]] : 0;
-        uint32_t ent = d.t2[(state * C + c1) * C + c2];
+        uint32_t ent = d.t2[state * RW + c1 * C + c2];
         uint32_t mid = d.t1[state * C + c1] / C;
         if (((ent & 0x80000000u) != 0) != ((int)mid >= d.first_accept)) return -6;
         if ((int)mid >= d.first_accept) report(mid, p + 1, a, b);
         row = ent & 0x7FFFFFFFu;
         if (p + 1 < n) {
           uint32_t fin = d.t1[mid * C + c2] / C;
-          if (fin * C2 * 4 != row) return -6;
+          if ((fin << d.row_shift) != row) return -6;
           if (row >= acc_row) report(fin, p + 2, a, b);
         }
         p += 2;
