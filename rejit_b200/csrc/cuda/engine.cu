@@ -159,6 +159,7 @@ class DeviceProgram {
   uint32_t needle_len = 0, p4 = 0, pmask = 0;
   size_t dfa_smem = 0;
   // adaptive capacities (remembered across calls so that steady state never reruns)
+  GenFilter gen_filter{};             // start filter of the generic scan
   uint32_t cand_sub_cap = 16;         // slots per sub-region, candidate store
   uint32_t hit_sub_cap = 16;          // slots per sub-region, needle-hit store
   bool dense_mode = false;            // k_dfa_tma's lane lists overflowed once: use k_dfa_scan
@@ -187,6 +188,14 @@ class DeviceProgram {
         !Upload(ft.follow, &nfa.follow, error) || !Upload(ft.accept, &nfa.accept, error) ||
         !Upload(ft.chain, &nfa.chain, error) || !Upload(ft.start_ok, &nfa.start_ok, error)) return false;
 
+    // start filter: byte c can begin a match (or the empty match is possible) in
+    // the context (sol, eol(c))
+    for (int sol = 0; sol < 2; ++sol)
+      for (int b = 0; b < 256; ++b) {
+        int eol = (b == '\n' || b == '\r') ? 1 : 0;
+        int ctx = ca.nfa.has_anchor ? (sol | (eol << 1)) : 0;
+        if (ca.start_ok[ctx][b] || ca.nfa.accept_empty[ctx]) gen_filter.t[sol][b >> 5] |= 1u << (b & 31);
+      }
     if (ca.strategy == ScanStrategy::Literal || ca.strategy == ScanStrategy::LiteralWindow) {
       if (!Upload(ca.literal, &needle, error)) return false;
       needle_len = (uint32_t)ca.literal.size();
@@ -506,12 +515,12 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         break;
       }
       case ScanStrategy::Generic: {
-        cand.nsub = (n + 1 + kGenSubOffsets - 1) / kGenSubOffsets;
-        cand.cap = std::min<uint32_t>(std::max<uint32_t>(cand.cap, 64), kGenSubOffsets);
+        cand.nsub = (n + 1 + kGenSubBytes - 1) / kGenSubBytes;
+        cand.cap = std::min<uint32_t>(std::max<uint32_t>(cand.cap, 64), kGenSubBytes);
         if (!ReserveStore(&c->sub_b, &c->sub_e, &c->sub_count, {cand.nsub, cand.cap}, error)) return false;
         cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
         int blocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)grid_full);
-        k_generic_scan<<<blocks, 256, 0, s>>>(d_text, n, dp->nfa, slab.own, cand);
+        k_generic_scan<<<blocks, 256, 0, s>>>(d_text, n, dp->nfa, dp->gen_filter, slab.own, cand);
         if (stats) stats->launches += 1;
         break;
       }
@@ -572,6 +581,19 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     if (rerun) {
       if (stats) stats->reruns += 1;
       continue;
+    }
+    if (st.need_large && ordered) {
+      // many candidates: gather the slot ranges with the whole GPU
+      if (!c->wide.Reserve(cand.nsub * 8 + 64, error) || !c->slot.Reserve(cand.nsub * 8 + 64, error)) return false;
+      size_t tmp = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->wide.as<uint64_t>(), c->slot.as<uint64_t>(), (int64_t)cand.nsub, s);
+      if (!c->cub_tmp.Reserve(tmp, error)) return false;
+      int gblocks = (int)std::min<uint64_t>((cand.nsub + 255) / 256, (uint64_t)c->sm_count * 8);
+      k_clamp_counts<<<gblocks, 256, 0, s>>>(cand.count, cand.cap, cand.nsub, c->wide.as<uint64_t>());
+      RJ_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->wide.as<uint64_t>(), c->slot.as<uint64_t>(), (int64_t)cand.nsub, s));
+      int wblocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)c->sm_count * 8);
+      k_gather_multi<<<wblocks, 256, 0, s>>>(cand, c->slot.as<uint64_t>(), dense);
+      if (stats) stats->launches += 4;
     }
     if (st.need_large) {
       outp = d_out ? d_out : c->out_pairs.as<uint64_t>();

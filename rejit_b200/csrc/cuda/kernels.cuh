@@ -109,7 +109,7 @@ constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr int kSmallResolveMax = 4096;       // sort-based fallback resolve
 constexpr int kOrderedResolveMax = 16384;    // one-CTA ordered resolve
 constexpr uint32_t kLitSubBytes = 16384;     // sub-region of the literal scan (32 pieces)
-constexpr uint32_t kGenSubOffsets = 2048;    // sub-region of the generic scan
+constexpr uint32_t kGenSubBytes = 16384;     // sub-region of the generic scan
 constexpr uint32_t kWinSubHits = 8;          // needle hits per sub-region of the window verify
 constexpr uint32_t kDfaStreamBytes = 272;    // bytes per lane sub-stream (k_dfa_tma): 17 * 16, so that the
                                              // lanes' 16-byte shared loads from a DENSE tile are conflict free
@@ -842,29 +842,90 @@ k_dfa_scan(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, uint32_t
 }
 
 // ===========================================================================
-// K3: generic scan (ordered) — a warp owns 2048 consecutive start offsets; per
-// step, one lane per offset: start filter on the first byte, then the NFA run.
+// K3: generic scan (ordered).  A warp owns 16 KB of start offsets; per 512-byte
+// piece a lane holds 16 bytes (one vector load) and tests each of its 16 offsets
+// against a 256-bit start filter — "can a match begin with this byte in this
+// line context?" (the context bit sol comes from the previous byte, eol is a
+// function of the byte itself, so two bitmaps suffice).  Only offsets that pass
+// run the per-start NFA.  Empty-match patterns (^, x*) pass through the same
+// filter (their bitmaps include every byte where the empty match is possible).
 // ===========================================================================
+struct GenFilter {
+  uint32_t t[2][8];      // [sol][byte >> 5] bit (byte & 31)
+};
+
+__device__ __noinline__ void GenEmit(const uint8_t* __restrict__ text, uint64_t n, const NfaTables& nfa,
+                                     const ScanRange& range, const SubStore& out, uint64_t sub, uint32_t& k,
+                                     uint64_t my, uint32_t cand) {
+  uint64_t ends[16];
+  uint32_t valid = 0;
+  uint32_t hh = cand;
+  while (hh) {
+    int j = __ffs(hh) - 1;
+    hh &= hh - 1;
+    uint64_t s = my + j;
+    if (s < range.own_begin || s >= range.own_end || s > n) continue;
+    uint64_t e = NfaRunAny(nfa, text, n, s);
+    if (e != kNoMatch) { ends[j] = e; valid |= 1u << j; }
+  }
+  __syncwarp();
+  uint32_t c = __popc(valid);
+  uint32_t incl = WarpInclusiveScan(c);
+  uint32_t total = __shfl_sync(kFullMask, incl, 31);
+  uint32_t idx = k + incl - c;
+  while (valid) {
+    int j = __ffs(valid) - 1;
+    valid &= valid - 1;
+    if (idx < out.cap) {
+      out.begin[sub * out.cap + idx] = my + j;
+      out.end[sub * out.cap + idx] = ends[j];
+    }
+    ++idx;
+  }
+  __syncwarp();
+  k += total;
+}
+
 __global__ void __launch_bounds__(256)
-k_generic_scan(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, ScanRange range, SubStore out) {
+k_generic_scan(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, GenFilter flt, ScanRange range,
+               SubStore out) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr uint32_t kPieces = kGenSubBytes / 512;
   for (uint64_t sub = warp; sub < out.nsub; sub += nwarps) {
-    const uint64_t lo = sub * kGenSubOffsets;
+    const uint64_t sub_lo = sub * kGenSubBytes;
     uint32_t k = 0;
-    if (lo <= n && lo + kGenSubOffsets > range.own_begin && lo < range.own_end) {
-      for (uint32_t it = 0; it < kGenSubOffsets; it += 32) {
-        uint64_t s = lo + it + lane;
-        uint64_t e = kNoMatch;
-        if (s <= n && s >= range.own_begin && s < range.own_end) {
-          int ctx = nfa.has_anchor ? ContextAt(text, n, s) : 0;
-          bool ok = nfa.accept_empty[ctx] || (s < n && nfa.start_ok[ctx * 256 + text[s]]);
-          if (ok) e = NfaRunAny(nfa, text, n, s);
+    if (sub_lo <= n && sub_lo + kGenSubBytes > range.own_begin && sub_lo < range.own_end) {
+      for (uint32_t pc = 0; pc < kPieces; ++pc) {
+        const uint64_t piece_lo = sub_lo + (uint64_t)pc * 512;
+        if (piece_lo > n) break;
+        const uint64_t my = piece_lo + (uint64_t)lane * 16;
+        uint4 v = (my < n) ? LoadText16(text, n, my) : make_uint4(0, 0, 0, 0);
+        // byte before my chunk: last byte of the previous lane, or of the previous piece
+        uint32_t prev = __shfl_up_sync(kFullMask, v.w >> 24, 1);
+        if (lane == 0) prev = (my == 0) ? 0x0Au : (uint32_t)text[my - 1];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t cand = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          uint32_t sol = (prev == 0x0Au || prev == 0x0Du) ? 1u : 0u;
+          uint32_t bit = (flt.t[sol][c >> 5] >> (c & 31)) & 1u;
+          cand |= bit << j;
+          prev = c;
         }
-        __syncwarp();
-        EmitOrdered(out, sub, k, e != kNoMatch, s, e);
-        if (lo + it + 32 > n) break;
+        // offsets at or beyond n: only the offset n itself can still hold an (empty) match
+        if (my + 16 > n) {
+          uint32_t keep = (my >= n) ? 0u : ((1u << (uint32_t)(n - my)) - 1u);
+          cand &= keep;
+          if (n >= my && n < my + 16) {
+            uint32_t pb = (n == 0) ? 0x0Au : (uint32_t)text[n - 1];
+            int ctx = ((pb == 0x0Au || pb == 0x0Du) ? 1 : 0) | 2;
+            if (nfa.accept_empty[nfa.has_anchor ? ctx : 0]) cand |= 1u << (uint32_t)(n - my);
+          }
+        }
+        if (__any_sync(kFullMask, cand != 0)) GenEmit(text, n, nfa, range, out, sub, k, my, cand);
       }
     }
     if (lane == 0) out.count[sub] = k;
@@ -988,11 +1049,35 @@ constexpr int kGatherBatch = 4;
 
 __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseList& dense, PipelineStatus* status,
                                                uint32_t* s_warp, unsigned long long* m_out,
+                                               unsigned long long gather_limit,
                                                uint64_t* spec_out = nullptr, uint64_t spec_cap = 0,
                                                uint64_t base_offset = 0) {
   __shared__ unsigned int s_flags[2];          // [0] max count, [1] dense marker
+  __shared__ unsigned long long s_total;
   if (threadIdx.x < 2) s_flags[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_total = 0;
   __syncthreads();
+  // pass 1: total and overflow markers only (the counts stay hot in L2)
+  {
+    unsigned long long mine = 0;
+    unsigned int mx = 0, marker = 0;
+    for (uint64_t sub = threadIdx.x; sub < st.nsub; sub += blockDim.x) {
+      uint32_t c = st.count[sub];
+      if (c == kLaneListOverflow) marker = 1;
+      else { if (c > st.cap) { mx = max(mx, c); c = st.cap; } mine += c; }
+    }
+    if (marker) atomicOr(&s_flags[1], 1u);
+    if (mx) atomicMax(&s_flags[0], mx);
+    atomicAdd(&s_total, mine);
+    __syncthreads();
+    *m_out = s_total;
+    bool ok1 = true;
+    if (s_flags[1]) { if (threadIdx.x == 0) status->dense = 1; ok1 = false; }
+    if (s_flags[0]) { if (threadIdx.x == 0) { status->overflow = 1; status->need_cap = s_flags[0]; } ok1 = false; }
+    if (s_total > dense.cap) { if (threadIdx.x == 0) status->overflow = 1; ok1 = false; }
+    if (threadIdx.x == 0) *dense.count = s_total;
+    if (!ok1 || s_total > gather_limit) return ok1;      // too many for one CTA: the host runs the multi-CTA gather
+  }
   unsigned long long base = 0;
   for (uint64_t blk0 = 0; blk0 < st.nsub; blk0 += (uint64_t)kGatherBatch * blockDim.x) {
     uint32_t c[kGatherBatch];
@@ -1004,8 +1089,6 @@ __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseLi
     }
 #pragma unroll
     for (int u = 0; u < kGatherBatch; ++u) {
-      if (c[u] == kLaneListOverflow) { atomicOr(&s_flags[1], 1u); c[u] = 0; }
-      else if (c[u] > st.cap) { atomicMax(&s_flags[0], c[u]); c[u] = st.cap; }
       uint32_t total;
       uint32_t off = BlockExclusiveSum(c[u], &total, s_warp);
       at[u] = base + off;
@@ -1033,12 +1116,7 @@ __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseLi
   }
   __syncthreads();
   *m_out = base;
-  bool ok = true;
-  if (s_flags[1]) { if (threadIdx.x == 0) status->dense = 1; ok = false; }
-  if (s_flags[0]) { if (threadIdx.x == 0) { status->overflow = 1; status->need_cap = s_flags[0]; } ok = false; }
-  if (base > dense.cap) { if (threadIdx.x == 0) { status->overflow = 1; } ok = false; }
-  if (threadIdx.x == 0) *dense.count = base;
-  return ok;
+  return true;
 }
 
 // Stage boundary of the literal+window pipeline: dense list of needle hits.
@@ -1046,7 +1124,7 @@ __global__ void __launch_bounds__(512, 1)
 k_gather_hits(SubStore st, DenseList dense, PipelineStatus* status) {
   __shared__ uint32_t s_warp[33];
   unsigned long long m;
-  GatherSubStore(st, dense, status, s_warp, &m);
+  GatherSubStore(st, dense, status, s_warp, &m, ~0ull);
   if (threadIdx.x == 0) status->n_hits = m;
 }
 
@@ -1087,7 +1165,8 @@ __device__ __forceinline__ void ResolveOrderedBody(const SubStore& st, const Den
   // the gather also writes the candidates straight to the output: if the fast
   // path below holds they ARE the matches; otherwise the general path
   // overwrites the output
-  bool ok = GatherSubStore(st, dense, status, s_warp, &m, fa.enabled ? nullptr : out_pairs, out_cap, base_offset);
+  bool ok = GatherSubStore(st, dense, status, s_warp, &m, (unsigned long long)kOrderedResolveMax,
+                           fa.enabled ? nullptr : out_pairs, out_cap, base_offset);
   if (threadIdx.x == 0) status->n_candidates = m;
   if (!ok) return;
   if (m > (unsigned long long)kOrderedResolveMax) {
@@ -1312,6 +1391,36 @@ k_resolve_small(CandBuf cand, Carry carry_in, uint64_t base_offset, uint64_t* __
     status->n_matches = taken;
     status->carry_cur = st.cur;
     status->carry_tail = st.tail;
+  }
+}
+
+// Multi-CTA gather for large candidate counts: offsets = exclusive sum of the
+// sub-region counts (computed by cub::DeviceScan), one lane per sub-region.
+__global__ void k_clamp_counts(const uint32_t* __restrict__ count, uint32_t cap, uint64_t nsub, uint64_t* __restrict__ wide) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < nsub; i += nthreads) {
+    uint32_t c = count[i];
+    wide[i] = (c == kLaneListOverflow) ? 0 : (c > cap ? cap : c);
+  }
+}
+
+// One warp per sub-region: the slot range is copied with coalesced accesses.
+__global__ void k_gather_multi(SubStore st, const uint64_t* __restrict__ offsets, DenseList dense) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t sub = warp; sub < st.nsub; sub += nwarps) {
+    uint32_t c = st.count[sub];
+    if (c == kLaneListOverflow) c = 0;
+    if (c > st.cap) c = st.cap;
+    const uint64_t at = offsets[sub];
+    for (uint32_t i = lane; i < c; i += 32) {
+      if (at + i < dense.cap) {
+        dense.begin[at + i] = st.begin[sub * st.cap + i];
+        dense.end[at + i] = st.end[sub * st.cap + i];
+      }
+    }
   }
 }
 
