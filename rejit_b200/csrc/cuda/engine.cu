@@ -68,6 +68,9 @@ struct Buffer {
 
 }  // namespace
 
+// finish area inside DeviceContext::status
+constexpr size_t kFinSyncOffset = 128, kFinLastOffset = 160, kFinSegOffset = 168;
+
 class DeviceContext {
  public:
   int device = 0;
@@ -100,6 +103,7 @@ class DeviceContext {
   PipelineStatus* h_status_dev = nullptr;   // device view of h_status
   unsigned int call_seq = 0;
   bool attr_done = false;
+  bool coop = false;                  // cooperative launch available: scans finish in-kernel
 
   bool Init(int dev, std::string* error) {
     device = dev;
@@ -108,6 +112,7 @@ class DeviceContext {
     RJ_TRY(cudaGetDeviceProperties(&prop, dev));
     sm_count = prop.multiProcessorCount;
     smem_optin = prop.sharedMemPerBlockOptin;
+    coop = prop.cooperativeLaunch != 0 && getenv("RJ_NO_FUSED_FINISH") == nullptr;
     RJ_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) RJ_TRY(cudaEventCreate(&e));
     RJ_TRY(cudaHostAlloc(&h_status, sizeof(PipelineStatus), cudaHostAllocMapped));
@@ -117,7 +122,9 @@ class DeviceContext {
     memset(h_set_status, 0, 32 * sizeof(PipelineStatus));
     RJ_TRY(cudaHostGetDevicePointer(&h_set_status_dev, h_set_status, 0));
     // status and the counters share one allocation so that one memset clears both
-    if (!status.Reserve(sizeof(PipelineStatus) + 64, error)) return false;
+    // layout: [PipelineStatus][counters 40 B, at +64][finish: sync 8 x u32 at +128, last_end at +160,
+    //          segcount at +168 (one u32 per scan CTA)]
+    if (!status.Reserve(kFinSegOffset + 4 * (size_t)sm_count + 64, error)) return false;
     counters.p = static_cast<uint8_t*>(status.p) + ((sizeof(PipelineStatus) + 15) & ~size_t(15));
     counters.bytes = 0;                 // not owned
     return true;
@@ -434,7 +441,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
   for (int attempt = 0; attempt < 48; ++attempt) {
     unsigned long long* ctr = c->counters.as<unsigned long long>();
     PipelineStatus* d_status = c->status.as<PipelineStatus>();
-    RJ_TRY(cudaMemsetAsync(d_status, 0, ((sizeof(PipelineStatus) + 15) & ~size_t(15)) + 40, s));
+    RJ_TRY(cudaMemsetAsync(d_status, 0, kFinSegOffset + 4 * (size_t)c->sm_count, s));
     const bool use_fallback = ca.strategy == ScanStrategy::DfaFixed && (dp->dense_mode || tma_warps < 4);
     if (use_fallback && c->cand_cap == 0 && !c->ReserveUnordered(1u << 16, error)) return false;
     uint64_t ocap = d_out ? out_cap : c->out_pairs.bytes / 16;
@@ -458,6 +465,8 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     if (stats) cudaEventRecord(c->ev[0], s);
     const int grid_full = c->sm_count * 8;
     bool ordered = true;
+    bool fused = false;                 // the scan kernel also produced the matches and the status
+    unsigned int fused_seq = 0;
     switch (ca.strategy) {
       case ScanStrategy::Literal: {
         cand.nsub = (n + kLitSubBytes - 1) / kLitSubBytes;
@@ -502,7 +511,36 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
           cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
           size_t smem = DfaTmaFixedSmem(dp->dfa) + (size_t)tma_warps * kDfaTileBytes;
           int blocks = (int)std::min<uint64_t>((cand.nsub + tma_warps - 1) / tma_warps, (uint64_t)c->sm_count);
-          k_dfa_tma<<<blocks, tma_warps * 32, smem, s>>>(d_text, n, dp->dfa, slab.own, cand, &d_status->dense, ctr + 0);
+          FinishArgs fin{};
+          CarrySet cset{};
+          cset.c[0] = carry_in;
+          unsigned int* dense_flag = &d_status->dense;
+          unsigned long long* work = ctr + 0;
+          if (c->coop && !fa.enabled) {
+            // the scan grid finishes the job itself (see FinishFixed)
+            uint8_t* base = static_cast<uint8_t*>(c->status.p);
+            fin.enabled = 1;
+            fin.seg_subs = (uint32_t)((cand.nsub + blocks - 1) / blocks);
+            fin.nseg = (uint32_t)((cand.nsub + fin.seg_subs - 1) / fin.seg_subs);
+            fin.sync = reinterpret_cast<unsigned int*>(base + kFinSyncOffset);
+            fin.last_end = reinterpret_cast<unsigned long long*>(base + kFinLastOffset);
+            fin.segcount = reinterpret_cast<uint32_t*>(base + kFinSegOffset);
+            fin.out_pairs = outp;
+            fin.out_stride = 0;
+            fin.out_cap = ocap;
+            fin.base_offset = slab.base_offset;
+            fin.status = d_status;
+            fin.host_status = c->h_status_dev;
+            fin.seq = fused_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+            dense_flag = fin.sync + 4;
+            ScanRange own = slab.own;
+            void* args[] = {(void*)&d_text, (void*)&n, (void*)&dp->dfa, (void*)&own, (void*)&cand, (void*)&dense_flag,
+                            (void*)&work, (void*)&fin, (void*)&cset};
+            RJ_TRY(cudaLaunchCooperativeKernel((const void*)k_dfa_tma, dim3(blocks), dim3(tma_warps * 32), args, smem, s));
+            fused = true;
+          } else {
+            k_dfa_tma<<<blocks, tma_warps * 32, smem, s>>>(d_text, n, dp->dfa, slab.own, cand, dense_flag, work, fin, cset);
+          }
         } else {
           ordered = false;
           CandBuf un{c->cand_b.as<uint64_t>(), c->cand_e.as<uint64_t>(), ctr, c->cand_cap};
@@ -527,14 +565,9 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     }
     if (stats && ca.strategy != ScanStrategy::LiteralWindow) cudaEventRecord(c->ev[1], s);
     PipelineStatus st;
-    if (ordered) {
-      const unsigned int seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
-      k_resolve_ordered<<<1, 512, 0, s>>>(cand, dense, rs, carry_in, slab.base_offset, outp, ocap, fa, d_status,
-                                          c->h_status_dev, seq);
-      if (stats) stats->launches += 1;
-      RJ_TRY(cudaGetLastError());
-      // spin on the mapped status block; fall back to the stream state if the
-      // kernel cannot have run (launch failure, sticky error)
+    // spin on the mapped status block; fall back to the stream state if the
+    // kernel cannot have run (launch failure, sticky error)
+    auto wait_status = [&](unsigned int seq) -> bool {
       volatile unsigned int* vseq = &c->h_status->seq;
       uint64_t spins = 0;
       while (*vseq != seq) {
@@ -546,6 +579,26 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       }
       std::atomic_thread_fence(std::memory_order_acquire);
       st = *c->h_status;
+      return true;
+    };
+    auto resolve_ordered = [&]() -> bool {
+      const unsigned int seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+      k_resolve_ordered<<<1, 512, 0, s>>>(cand, dense, rs, carry_in, slab.base_offset, outp, ocap, fa, d_status,
+                                          c->h_status_dev, seq);
+      if (stats) stats->launches += 1;
+      RJ_TRY(cudaGetLastError());
+      return wait_status(seq);
+    };
+    if (ordered && fused) {
+      RJ_TRY(cudaGetLastError());
+      if (!wait_status(fused_seq)) return false;
+      if (st.need_large && !st.overflow && !st.dense) {
+        // neighbouring candidates overlap: the general resolve decides
+        RJ_TRY(cudaMemsetAsync(d_status, 0, sizeof(PipelineStatus), s));
+        if (!resolve_ordered()) return false;
+      }
+    } else if (ordered) {
+      if (!resolve_ordered()) return false;
     } else {
       CandBuf un{c->cand_b.as<uint64_t>(), c->cand_e.as<uint64_t>(), ctr, c->cand_cap};
       k_resolve_small<<<1, 1024, kSmallResolveMax * 16, s>>>(un, carry_in, slab.base_offset, outp, ocap, d_status);
@@ -849,12 +902,19 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           !c->set_dense_b.Reserve(K * per_cap * 8, error) || !c->set_dense_e.Reserve(K * per_cap * 8, error) ||
           !c->set_reach.Reserve(K * per_cap * 8, error) || !c->set_take.Reserve(K * per_cap * 4, error) ||
           !c->set_fin.Reserve(K * per_cap * 8, error) || !c->set_slot.Reserve(K * per_cap * 8, error) ||
-          !c->set_out.Reserve(K * per_cap * 16, error) || !c->set_status.Reserve(32 * sizeof(PipelineStatus), error) ||
-          !c->set_counts.Reserve(64 * 8, error)) return -1;
+          !c->set_out.Reserve(K * per_cap * 16, error) || !c->set_status.Reserve(32 * sizeof(PipelineStatus), error)) return -1;
       PipelineStatus* d_status = c->set_status.as<PipelineStatus>();
-      unsigned long long* d_counts = c->set_counts.as<unsigned long long>();     // [0..K) dense counts, [40] work counter
-      if (!Check(cudaMemsetAsync(d_status, 0, 32 * sizeof(PipelineStatus), s), "memset", error) ||
-          !Check(cudaMemsetAsync(d_counts, 0, 64 * 8, s), "memset", error)) return -1;
+      int blocks = (int)std::min<uint64_t>((nsub + warps - 1) / warps, (uint64_t)c->sm_count);
+      // set_counts: [0..K) dense counts, [40] work counter, then the finish area
+      // (sync 8 x u32 at +512, last_end[32] at +544, segcount[K][nseg] at +800)
+      const bool fuse_finish = c->coop;
+      const uint32_t seg_subs = (uint32_t)((nsub + blocks - 1) / blocks);
+      const uint32_t nseg = (uint32_t)((nsub + seg_subs - 1) / seg_subs);
+      const size_t counts_bytes = 800 + (fuse_finish ? (size_t)K * nseg * 4 : 0);
+      if (!c->set_counts.Reserve(counts_bytes, error)) return -1;
+      unsigned long long* d_counts = c->set_counts.as<unsigned long long>();
+      if (!Check(cudaMemsetAsync(d_counts, 0, counts_bytes, s), "memset", error)) return -1;
+      if (!fuse_finish && !Check(cudaMemsetAsync(d_status, 0, 32 * sizeof(PipelineStatus), s), "memset", error)) return -1;
       SubStore st{};
       st.begin = c->set_sub_b.as<uint64_t>(); st.end = c->set_sub_e.as<uint64_t>(); st.count = c->set_sub_count.as<uint32_t>();
       st.cap = ds->sub_cap; st.nsub = (uint64_t)K * nsub;
@@ -871,24 +931,70 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
       for (int j = 0; j < 32; ++j) carries.c[j] = (carry_in && j < K) ? carry_in[j] : Carry();
       if (stats) cudaEventRecord(c->ev[0], s);
       size_t smem = ds->fixed_smem + (size_t)warps * kDfaTileBytes;
-      int blocks = (int)std::min<uint64_t>((nsub + warps - 1) / warps, (uint64_t)c->sm_count);
-      k_set_tma<<<blocks, warps * 32, smem, s>>>(d_text, n, ds->tb, own, st, nsub, &d_status->dense, d_counts + 40);
-      if (stats) cudaEventRecord(c->ev[1], s);
-      const unsigned int seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
-      k_resolve_set<<<K, 512, 0, s>>>(st, nsub, dense, rs, per_cap, c->set_out.as<uint64_t>(), d_status,
-                                      c->h_set_status_dev, d_counts, seq, carries, base_offset);
-      if (stats) stats->launches += 2;
-      if (!Check(cudaGetLastError(), "launch", error)) return -1;
-      uint64_t spins = 0;
-      for (int j = 0; j < K; ++j) {
-        volatile unsigned int* vseq = &c->h_set_status[j].seq;
-        while (*vseq != seq) {
-          if ((++spins & 0x3FFF) == 0) {
-            cudaError_t q = cudaStreamQuery(s);
-            if (q == cudaSuccess) { if (*vseq == seq) break; if (error) *error = "rejit_b200: set resolve did not report"; return -1; }
-            if (q != cudaErrorNotReady) { Check(q, "cudaStreamQuery", error); return -1; }
+      auto wait_all = [&](unsigned int seq) -> bool {
+        uint64_t spins = 0;
+        for (int j = 0; j < K; ++j) {
+          volatile unsigned int* vseq = &c->h_set_status[j].seq;
+          while (*vseq != seq) {
+            if ((++spins & 0x3FFF) == 0) {
+              cudaError_t q = cudaStreamQuery(s);
+              if (q == cudaSuccess) { if (*vseq == seq) break; if (error) *error = "rejit_b200: set resolve did not report"; return false; }
+              if (q != cudaErrorNotReady) { Check(q, "cudaStreamQuery", error); return false; }
+            }
           }
         }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        return true;
+      };
+      auto resolve_set = [&]() -> bool {
+        const unsigned int seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+        k_resolve_set<<<K, 512, 0, s>>>(st, nsub, dense, rs, per_cap, c->set_out.as<uint64_t>(), d_status,
+                                        c->h_set_status_dev, d_counts, seq, carries, base_offset);
+        if (stats) stats->launches += 1;
+        if (!Check(cudaGetLastError(), "launch", error)) return false;
+        return wait_all(seq);
+      };
+      FinishArgs fin{};
+      unsigned int* dense_flag = &d_status->dense;
+      unsigned long long* work = d_counts + 40;
+      if (fuse_finish) {
+        uint8_t* base = c->set_counts.as<uint8_t>();
+        fin.enabled = 1;
+        fin.seg_subs = seg_subs;
+        fin.nseg = nseg;
+        fin.sync = reinterpret_cast<unsigned int*>(base + 512);
+        fin.last_end = reinterpret_cast<unsigned long long*>(base + 544);
+        fin.segcount = reinterpret_cast<uint32_t*>(base + 800);
+        fin.out_pairs = c->set_out.as<uint64_t>();
+        fin.out_stride = per_cap;
+        fin.out_cap = per_cap;
+        fin.base_offset = base_offset;
+        fin.status = d_status;
+        fin.host_status = c->h_set_status_dev;
+        fin.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+        dense_flag = fin.sync + 4;
+        uint64_t n_arg = n, nsub_arg = nsub;
+        void* args[] = {(void*)&d_text, (void*)&n_arg, (void*)&ds->tb, (void*)&own, (void*)&st, (void*)&nsub_arg,
+                        (void*)&dense_flag, (void*)&work, (void*)&fin, (void*)&carries};
+        if (!Check(cudaLaunchCooperativeKernel((const void*)k_set_tma, dim3(blocks), dim3(warps * 32), args, smem, s),
+                   "cooperative launch", error)) return -1;
+        if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
+        if (!Check(cudaGetLastError(), "launch", error) || !wait_all(fin.seq)) return -1;
+        bool overlap = false, clean = true;
+        for (int j = 0; j < K; ++j) {
+          const PipelineStatus& h = c->h_set_status[j];
+          if (h.overflow || h.dense) clean = false;
+          if (h.need_large) overlap = true;
+        }
+        if (overlap && clean) {
+          // some pattern's neighbouring candidates overlap: the general resolve decides
+          if (!Check(cudaMemsetAsync(d_status, 0, 32 * sizeof(PipelineStatus), s), "memset", error)) return -1;
+          if (!resolve_set()) return -1;
+        }
+      } else {
+        k_set_tma<<<blocks, warps * 32, smem, s>>>(d_text, n, ds->tb, own, st, nsub, dense_flag, work, fin, carries);
+        if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
+        if (!resolve_set()) return -1;
       }
       std::atomic_thread_fence(std::memory_order_acquire);
       bool rerun = false;

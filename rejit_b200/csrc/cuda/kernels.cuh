@@ -79,6 +79,26 @@ struct PipelineStatus {                // one per call, read back by the host
   unsigned int seq;                    // call id, written last (host polls the mapped copy)
 };
 
+struct CarrySet { Carry c[32]; };
+
+// In-kernel finish of the fixed-length scans (k_dfa_tma, k_set_tma): the scan
+// grid is one CTA per SM, launched cooperatively, so that after a grid barrier
+// the same CTAs concatenate the slot ranges straight into the output.
+struct FinishArgs {
+  int enabled;
+  uint32_t nseg, seg_subs;             // the sub-regions are cut into nseg segments of seg_subs
+  uint32_t* segcount;                  // [K][nseg] candidates per (pattern, segment); zeroed by the host
+  unsigned int* sync;                  // [0] arrive, [1] done, [2] flags, [3] need_cap; zeroed by the host
+  unsigned long long* last_end;        // [K] end of the last candidate; zeroed by the host
+  uint64_t* out_pairs;                 // pattern j's pairs start at out_pairs + j * 2 * out_stride
+  uint64_t out_stride, out_cap;
+  uint64_t base_offset;
+  PipelineStatus* status;              // [K] device copies
+  volatile PipelineStatus* host_status;  // [K] mapped host copies
+  unsigned int seq;
+};
+constexpr unsigned int kFinOverlap = 1u, kFinDense = 2u, kFinOverflow = 4u;
+
 struct DfaTables {
   const uint16_t* next;                // [n_states * n_classes], entries pre-multiplied by n_classes
   const uint8_t* byte_class;           // [256]
@@ -352,6 +372,156 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
 // warp scan at the end of the sub-region, so candidates come out sorted.
 // Algorithmic traffic: N bytes read + 16 bytes per match.
 // ===========================================================================
+// ---------------------------------------------------------------------------
+// Finish of a fixed-length scan (see FinishArgs).  Matches of one fixed-length
+// pattern come out of the scan sorted and can only interact with their direct
+// neighbour: when no candidate begins before its predecessor ends, the
+// candidates ARE the matches (the common case) and this copy is the whole
+// resolve; otherwise kFinOverlap is raised and the host runs the general resolve
+// kernel on the same slot ranges.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void GridBarrier(unsigned int* ctr, unsigned int expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v < expected) __nanosleep(40);
+    } while (v < expected);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// the scan's bookkeeping for one (pattern, sub-region) count
+__device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_t sub, uint32_t total, bool over,
+                                           uint32_t cap) {
+  if (!fin.enabled) return;
+  if (over) { atomicOr(&fin.sync[2], kFinDense); return; }
+  if (total > cap) { atomicOr(&fin.sync[2], kFinOverflow); atomicMax(&fin.sync[3], total); total = cap; }
+  if (total) atomicAdd(&fin.segcount[(uint64_t)j * fin.nseg + (uint32_t)(sub / fin.seg_subs)], total);
+}
+
+__device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
+                                            const CarrySet& carries) {
+  __shared__ int s_is_last;
+  GridBarrier(&fin.sync[0], gridDim.x);
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const unsigned int flags0 = __ldcg(&fin.sync[2]);
+  if (!(flags0 & (kFinDense | kFinOverflow))) {
+    for (uint32_t seg = blockIdx.x; seg < fin.nseg; seg += gridDim.x) {
+      for (int j = warp_in_cta; j < K; j += nwarps) {
+        unsigned long long pre = 0, mine = 0;
+        for (uint32_t s2 = lane; s2 < fin.nseg; s2 += 32) {
+          uint32_t v = __ldcg(&fin.segcount[(uint64_t)j * fin.nseg + s2]);
+          if (s2 < seg) pre += v;
+          if (s2 == seg) mine = v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          pre += __shfl_xor_sync(kFullMask, pre, d);
+          mine += __shfl_xor_sync(kFullMask, mine, d);
+        }
+        if (mine == 0) continue;
+        const Carry cin = carries.c[j];
+        const uint64_t sub0 = (uint64_t)seg * fin.seg_subs;
+        const uint64_t sub1 = (sub0 + fin.seg_subs < nsub_pat) ? sub0 + fin.seg_subs : nsub_pat;
+        const uint32_t* cnt = st.count + (uint64_t)j * nsub_pat;
+        uint64_t* outp = fin.out_pairs + (uint64_t)j * 2 * fin.out_stride;
+        unsigned long long run = pre;
+        uint64_t last_e = 0;
+        bool bad = false;
+        for (uint64_t base = sub0; base < sub1; base += 32) {
+          const uint64_t sub = base + lane;
+          const uint32_t c = (sub < sub1) ? __ldcg(&cnt[sub]) : 0u;
+          const uint32_t incl = WarpInclusiveScan(c);
+          const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+          if (c) {
+            const unsigned long long at = run + incl - c;
+            const uint64_t slot0 = ((uint64_t)j * nsub_pat + sub) * st.cap;
+            uint64_t prev_end = cin.cur;
+            if (sub > 0) {
+              const uint32_t pc = __ldcg(&cnt[sub - 1]);
+              if (pc) {
+                const uint64_t pe = __ldcg(&st.end[slot0 - st.cap + pc - 1]);
+                prev_end = pe > prev_end ? pe : prev_end;
+              }
+            }
+            for (uint32_t i = 0; i < c; ++i) {
+              const uint64_t b = __ldcg(&st.begin[slot0 + i]);
+              const uint64_t e = __ldcg(&st.end[slot0 + i]);
+              bad |= prev_end > b;
+              prev_end = e;
+              if (at + i < fin.out_cap) {
+                outp[2 * (at + i)] = b + fin.base_offset;
+                outp[2 * (at + i) + 1] = e + fin.base_offset;
+              }
+            }
+            last_e = prev_end;
+          }
+          run += total;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const uint64_t o = __shfl_xor_sync(kFullMask, last_e, d);
+          last_e = o > last_e ? o : last_e;
+        }
+        if (lane == 0 && last_e) atomicMax(&fin.last_end[j], (unsigned long long)last_e);
+        if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(&fin.sync[2], kFinOverlap);
+      }
+    }
+  }
+  // the last CTA to get here publishes the status blocks
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_is_last = (atomicAdd(&fin.sync[1], 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const unsigned int flags = __ldcg(&fin.sync[2]);
+  const unsigned int need_cap = __ldcg(&fin.sync[3]);
+  for (int j = warp_in_cta; j < K; j += nwarps) {
+    unsigned long long tot = 0;
+    for (uint32_t s2 = lane; s2 < fin.nseg; s2 += 32) tot += __ldcg(&fin.segcount[(uint64_t)j * fin.nseg + s2]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(kFullMask, tot, d);
+    if (lane == 0) {
+      const Carry cin = carries.c[j];
+      const unsigned long long le = __ldcg(&fin.last_end[j]);
+      PipelineStatus v{};
+      v.n_candidates = tot;
+      v.n_matches = tot;
+      v.carry_cur = tot ? le : cin.cur;
+      v.carry_tail = tot ? le : cin.tail;
+      v.overflow = (flags & kFinOverflow) ? 1u : 0u;
+      v.need_cap = need_cap;
+      v.need_large = (flags & kFinOverlap) ? 1u : 0u;
+      v.dense = (flags & kFinDense) ? 1u : 0u;
+      fin.status[j] = v;
+      volatile PipelineStatus* h = fin.host_status + j;
+      h->n_candidates = v.n_candidates;
+      h->n_hits = 0;
+      h->n_matches = v.n_matches;
+      h->carry_cur = v.carry_cur;
+      h->carry_tail = v.carry_tail;
+      h->overflow = v.overflow;
+      h->need_cap = v.need_cap;
+      h->need_large = v.need_large;
+      h->dense = v.dense;
+      h->full_result = 0;
+      __threadfence_system();
+      h->seq = fin.seq;
+      __threadfence_system();
+    }
+  }
+}
+
 constexpr int kDfaChainHits = 3;
 
 __device__ __forceinline__ uint32_t Lds32(uint32_t addr) {
@@ -396,7 +566,7 @@ __device__ __forceinline__ void DfaReplay(const uint4& v, uint32_t st1, const ui
 
 __global__ void __launch_bounds__(576, 1)
 k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange range, SubStore out,
-          unsigned int* dense_flag, unsigned long long* work_counter) {
+          unsigned int* dense_flag, unsigned long long* work_counter, FinishArgs fin, CarrySet carries) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -542,11 +712,13 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
       if (lane == 0) {
         out.count[sub] = over ? kLaneListOverflow : total;
         if (over) *dense_flag = 1u;
+        FinishNote(fin, 0, sub, total, over, out.cap);
       }
     } else if (lane == 0) {
       out.count[sub] = 0;
     }
   }
+  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, carries);
 }
 
 // ===========================================================================
@@ -598,7 +770,8 @@ __device__ __forceinline__ void SetRecord(uint32_t state, uint64_t e, uint64_t l
 
 __global__ void __launch_bounds__(576, 1)
 k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange range, SubStore out,
-          uint64_t nsub_pat, unsigned int* dense_flag, unsigned long long* work_counter) {
+          uint64_t nsub_pat, unsigned int* dense_flag, unsigned long long* work_counter, FinishArgs fin,
+          CarrySet carries) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -777,11 +950,15 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
             ++idx;
           }
         }
-        if (lane == 0) out.count[(uint64_t)j * nsub_pat + sub] = over ? kLaneListOverflow : total;
+        if (lane == 0) {
+          out.count[(uint64_t)j * nsub_pat + sub] = over ? kLaneListOverflow : total;
+          FinishNote(fin, j, sub, total, over, out.cap);
+        }
       }
       if (over && lane == 0) *dense_flag = 1u;
     }
   }
+  if (fin.enabled) FinishFixed(out, nsub_pat, K, fin, carries);
 }
 
 // ---------------------------------------------------------------------------
@@ -1061,10 +1238,19 @@ __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseLi
   {
     unsigned long long mine = 0;
     unsigned int mx = 0, marker = 0;
-    for (uint64_t sub = threadIdx.x; sub < st.nsub; sub += blockDim.x) {
-      uint32_t c = st.count[sub];
-      if (c == kLaneListOverflow) marker = 1;
-      else { if (c > st.cap) { mx = max(mx, c); c = st.cap; } mine += c; }
+    for (uint64_t blk0 = 0; blk0 < st.nsub; blk0 += 8ull * blockDim.x) {
+      uint32_t cc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {                  // eight loads in flight per thread
+        uint64_t sub = blk0 + (uint64_t)u * blockDim.x + threadIdx.x;
+        cc[u] = (sub < st.nsub) ? st.count[sub] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint32_t c = cc[u];
+        if (c == kLaneListOverflow) marker = 1;
+        else { if (c > st.cap) { mx = max(mx, c); c = st.cap; } mine += c; }
+      }
     }
     if (marker) atomicOr(&s_flags[1], 1u);
     if (mx) atomicMax(&s_flags[0], mx);
@@ -1282,8 +1468,6 @@ k_resolve_ordered(SubStore st, DenseList dense, ResolveScratch rs, Carry carry_i
 
 // One CTA per pattern of a fused set: the same resolve, on that pattern's slice
 // of the stores / scratch / output / status arrays.
-struct CarrySet { Carry c[32]; };
-
 __global__ void __launch_bounds__(512, 1)
 k_resolve_set(SubStore st, uint64_t nsub_pat, DenseList dense, ResolveScratch rs, uint64_t per_cap,
               uint64_t* __restrict__ out_pairs, PipelineStatus* status, volatile PipelineStatus* host_status,

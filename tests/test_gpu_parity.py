@@ -229,7 +229,7 @@ def test_fused_pattern_set(rj):
             st = rj.Stats()
             counts = rs.match_all_device(dt, stats=st)
             assert counts == [len(O.Oracle(p).match_all(data[:cut])) for p in W.DNA_PATTERNS], cut
-            assert st.strategy == 4 and st.launches == 2
+            assert st.strategy == 4 and st.launches == 1     # scan + in-kernel finish
         finally:
             dt.free()
     # mixed lengths and a dense member (falls back to member-by-member runs)
@@ -238,6 +238,54 @@ def test_fused_pattern_set(rj):
         got = rj.RegejSet(pats).match_all(t)
         for p, g in zip(pats, got):
             assert g == O.Oracle(p).match_all(t), (pats, p)
+
+
+def test_fixed_length_finish_in_kernel_and_overlap_fallback(rj):
+    """k_dfa_tma / k_set_tma finish in-kernel (grid barrier + copy) when no
+    candidate overlaps its predecessor; overlapping neighbours (also across
+    lane, sub-region and segment edges) must fall back to the general resolve."""
+    rng = random.Random(12)
+    t = fuzzgen.rand_text(rng, "xxxxxxxxxxxxxxxxxxxxab", 400000)
+    pats = ["a[ab]", "[ab]b", "a[ab]a|b[ab]b", "ab[ab]|ba[ab]"]
+    for p in pats:
+        r = rj.Regej(p)
+        assert r.describe().startswith("fixed-length DFA scan"), r.describe()
+        exp = O.Oracle(p).match_all(t)
+        assert r.match_all(t) == exp, p
+        assert r.match_all(t) == exp, p             # steady state
+    got = rj.RegejSet(pats).match_all(t)
+    for p, g in zip(pats, got):
+        assert g == O.Oracle(p).match_all(t), p
+    # no overlaps at all: one launch per call
+    t2 = fuzzgen.rand_text(rng, "acgt", 300000)
+    r = rj.Regej("acgtac|gtgtca")
+    st = rj.Stats()
+    dt = rj.DeviceText(np.frombuffer(t2, dtype=np.uint8))
+    try:
+        r.match_all_device(dt, stats=st)
+        cnt = r.match_all_device(dt, stats=st)
+        assert cnt == len(O.Oracle("acgtac|gtgtca").match_all(t2)) and st.launches == 1
+    finally:
+        dt.free()
+    # slab calls with a carry reaching into the slab
+    for p, text in (("ab[ab]|ba[ab]", t), ("acgtac|gtgtca", t2), ("a[ab]", b"x" * 8703 + b"aaaa" + b"x" * 9000)):
+        r = rj.Regej(p)
+        exp = len(O.Oracle(p).match_all(text))
+        n = len(text)
+        dt = rj.DeviceText(np.frombuffer(text, dtype=np.uint8))
+        try:
+            for k in (1, 2, 3, 7):
+                carry = rj.Carry(0, 0xFFFFFFFFFFFFFFFF)
+                total = 0
+                for i in range(k):
+                    lo = n * i // k
+                    hi = n * (i + 1) // k if i + 1 < k else n + 1
+                    nxt = rj.Carry()
+                    total += r.match_all_device(dt, own=(lo, hi), carry_in=carry, carry_out=nxt)
+                    carry = nxt
+                assert total == exp, (p, k, total, exp)
+        finally:
+            dt.free()
 
 
 def test_multi_gpu_equals_single(rj):
