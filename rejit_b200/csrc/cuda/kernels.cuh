@@ -406,7 +406,6 @@ __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_
 
 __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
                                             const CarrySet& carries) {
-  __shared__ int s_is_last;
   GridBarrier(&fin.sync[0], gridDim.x);
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -476,13 +475,14 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
     }
   }
   // the last CTA to get here publishes the status blocks
+  // (no static shared memory here: the scan kernels use the whole opt-in carve-out)
   __syncthreads();
+  int is_last = 0;
   if (threadIdx.x == 0) {
     __threadfence();
-    s_is_last = (atomicAdd(&fin.sync[1], 1u) == gridDim.x - 1) ? 1 : 0;
+    is_last = (atomicAdd(&fin.sync[1], 1u) == gridDim.x - 1) ? 1 : 0;
   }
-  __syncthreads();
-  if (!s_is_last) return;
+  if (!__syncthreads_or(is_last)) return;
   __threadfence();
   const unsigned int flags = __ldcg(&fin.sync[2]);
   const unsigned int need_cap = __ldcg(&fin.sync[3]);
@@ -1659,16 +1659,30 @@ __global__ void k_scatter_matches(const uint64_t* __restrict__ b, const uint64_t
                                   unsigned long long* last_nonempty) {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = tid; i < m; i += nthreads) {
-    if (!take[i]) continue;
-    uint64_t at = slot[i];
-    if (at < out_cap) {
-      out_pairs[2 * at] = b[i] + base_offset;
-      out_pairs[2 * at + 1] = e[i] + base_offset;
+  const int lane = threadIdx.x & 31;
+  // the last taken candidate is the one whose slot is total-1 (one writer, no
+  // atomic); the last NON-EMPTY one needs a maximum, reduced per warp first
+  const uint64_t total = m ? slot[m - 1] + take[m - 1] : 0;
+  unsigned long long best = 0;
+  for (uint64_t i0 = tid - lane; i0 < m; i0 += nthreads) {
+    const uint64_t i = i0 + lane;
+    if (i < m && take[i]) {
+      const uint64_t at = slot[i];
+      const uint64_t bi = b[i], ei = e[i];
+      if (at < out_cap) {
+        out_pairs[2 * at] = bi + base_offset;
+        out_pairs[2 * at + 1] = ei + base_offset;
+      }
+      if (at + 1 == total) *last_any = (unsigned long long)(i + 1);
+      if (ei > bi) best = (unsigned long long)(i + 1);      // i grows along the loop
     }
-    atomicMax(last_any, (unsigned long long)(i + 1));
-    if (e[i] > b[i]) atomicMax(last_nonempty, (unsigned long long)(i + 1));
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(kFullMask, best, d);
+    best = o > best ? o : best;
+  }
+  if (lane == 0 && best) atomicMax(last_nonempty, best);
 }
 
 __global__ void k_finish_large(const uint64_t* __restrict__ b, const uint64_t* __restrict__ e,
