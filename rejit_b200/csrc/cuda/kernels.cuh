@@ -388,7 +388,6 @@ __device__ __forceinline__ void GridBarrier(unsigned int* ctr, unsigned int expe
     unsigned int v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-      if (v < expected) __nanosleep(40);
     } while (v < expected);
     __threadfence();
   }
