@@ -409,10 +409,18 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  const unsigned int flags0 = __ldcg(&fin.sync[2]);
-  if (!(flags0 & (kFinDense | kFinOverflow))) {
+  // Latency matters here, not bandwidth (a few thousand matches): loads that do
+  // not depend on each other are issued together, and the counts of the next 32
+  // sub-regions are fetched while the current ones are copied.
+  const unsigned int flags0 = __ldcg(&fin.sync[2]);      // consumed after the loads below are in flight
+  {
     for (uint32_t seg = blockIdx.x; seg < fin.nseg; seg += gridDim.x) {
       for (int j = warp_in_cta; j < K; j += nwarps) {
+        const uint64_t sub0 = (uint64_t)seg * fin.seg_subs;
+        const uint64_t sub1 = (sub0 + fin.seg_subs < nsub_pat) ? sub0 + fin.seg_subs : nsub_pat;
+        const uint32_t* cnt = st.count + (uint64_t)j * nsub_pat;
+        uint32_t c_next = (sub0 + lane < sub1) ? __ldcg(&cnt[sub0 + lane]) : 0u;
+        uint32_t edge = (lane == 0 && sub0 > 0) ? __ldcg(&cnt[sub0 - 1]) : 0u;   // the sub-region before the chunk
         unsigned long long pre = 0, mine = 0;
         for (uint32_t s2 = lane; s2 < fin.nseg; s2 += 32) {
           uint32_t v = __ldcg(&fin.segcount[(uint64_t)j * fin.nseg + s2]);
@@ -424,40 +432,38 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
           pre += __shfl_xor_sync(kFullMask, pre, d);
           mine += __shfl_xor_sync(kFullMask, mine, d);
         }
-        if (mine == 0) continue;
+        if (mine == 0 || (flags0 & (kFinDense | kFinOverflow))) continue;
         const Carry cin = carries.c[j];
-        const uint64_t sub0 = (uint64_t)seg * fin.seg_subs;
-        const uint64_t sub1 = (sub0 + fin.seg_subs < nsub_pat) ? sub0 + fin.seg_subs : nsub_pat;
-        const uint32_t* cnt = st.count + (uint64_t)j * nsub_pat;
         uint64_t* outp = fin.out_pairs + (uint64_t)j * 2 * fin.out_stride;
         unsigned long long run = pre;
         uint64_t last_e = 0;
         bool bad = false;
         for (uint64_t base = sub0; base < sub1; base += 32) {
           const uint64_t sub = base + lane;
-          const uint32_t c = (sub < sub1) ? __ldcg(&cnt[sub]) : 0u;
+          const uint32_t c = c_next;
+          if (base + 32 < sub1) c_next = (sub + 32 < sub1) ? __ldcg(&cnt[sub + 32]) : 0u;
+          uint32_t pc = __shfl_up_sync(kFullMask, c, 1);
+          if (lane == 0) pc = edge;
+          edge = __shfl_sync(kFullMask, c, 31);
           const uint32_t incl = WarpInclusiveScan(c);
           const uint32_t total = __shfl_sync(kFullMask, incl, 31);
           if (c) {
             const unsigned long long at = run + incl - c;
             const uint64_t slot0 = ((uint64_t)j * nsub_pat + sub) * st.cap;
-            uint64_t prev_end = cin.cur;
-            if (sub > 0) {
-              const uint32_t pc = __ldcg(&cnt[sub - 1]);
-              if (pc) {
-                const uint64_t pe = __ldcg(&st.end[slot0 - st.cap + pc - 1]);
-                prev_end = pe > prev_end ? pe : prev_end;
-              }
-            }
-            for (uint32_t i = 0; i < c; ++i) {
-              const uint64_t b = __ldcg(&st.begin[slot0 + i]);
-              const uint64_t e = __ldcg(&st.end[slot0 + i]);
+            uint64_t b = __ldcg(&st.begin[slot0]);
+            uint64_t e = __ldcg(&st.end[slot0]);
+            uint64_t prev_end = pc ? __ldcg(&st.end[slot0 - st.cap + pc - 1]) : 0;
+            prev_end = cin.cur > prev_end ? cin.cur : prev_end;
+            for (uint32_t i = 0;;) {
               bad |= prev_end > b;
               prev_end = e;
               if (at + i < fin.out_cap) {
                 outp[2 * (at + i)] = b + fin.base_offset;
                 outp[2 * (at + i) + 1] = e + fin.base_offset;
               }
+              if (++i >= c) break;
+              b = __ldcg(&st.begin[slot0 + i]);
+              e = __ldcg(&st.end[slot0 + i]);
             }
             last_e = prev_end;
           }
@@ -487,12 +493,12 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
   const unsigned int need_cap = __ldcg(&fin.sync[3]);
   for (int j = warp_in_cta; j < K; j += nwarps) {
     unsigned long long tot = 0;
+    const unsigned long long le = __ldcg(&fin.last_end[j]);
     for (uint32_t s2 = lane; s2 < fin.nseg; s2 += 32) tot += __ldcg(&fin.segcount[(uint64_t)j * fin.nseg + s2]);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(kFullMask, tot, d);
     if (lane == 0) {
       const Carry cin = carries.c[j];
-      const unsigned long long le = __ldcg(&fin.last_end[j]);
       PipelineStatus v{};
       v.n_candidates = tot;
       v.n_matches = tot;
