@@ -83,7 +83,7 @@ class DeviceContext {
   // ordered stores (slot ranges per sub-region): candidates and needle hits
   Buffer sub_b, sub_e, sub_count, hsub_b, hsub_e, hsub_count;
   // dense (gathered, sorted) lists
-  Buffer dense_b, dense_e, hits_b, hits_e, out_pairs;
+  Buffer dense_b, dense_e, hits_b, hits_e, out_pairs, fin_trace;
   uint64_t dense_cap = 0, hits_cap = 0;
   // unordered fallback (k_dfa_scan)
   Buffer cand_b, cand_e;
@@ -813,7 +813,8 @@ SetProgram* SetProgram::Create(const std::vector<Program*>& members) {
   sp->fused_ = BuildSetDfa(autos, &sp->dfa_);
   if (sp->fused_) {
     sp->describe_ = "fused set: " + std::to_string(members.size()) + " patterns, one DFA of " +
-                    std::to_string(sp->dfa_.n_states) + " states x " + std::to_string(sp->dfa_.n_classes) + " classes";
+                    std::to_string(sp->dfa_.n_states) + " states (+" + std::to_string(sp->dfa_.n_rows - sp->dfa_.n_states) +
+                    " shadow rows) x " + std::to_string(sp->dfa_.n_classes) + " classes";
   } else {
     sp->describe_ = "set of " + std::to_string(members.size()) + " patterns run one by one (not fusable)";
   }
@@ -833,11 +834,11 @@ DeviceSet* SetProgram::OnDevice(int device, std::string* error) {
         !d->Upload(f.accept_mask.data(), f.accept_mask.size(), &d->tb.accept_mask, error)) { delete d; return nullptr; }
     for (int j = 0; j < f.n_patterns; ++j) d->tb.match_len[j] = f.match_len[j];
     d->tb.n_patterns = f.n_patterns;
-    d->tb.n_states = f.n_states;
+    d->tb.n_rows = f.n_rows;
     d->tb.n_classes = f.n_classes;
     d->tb.first_accept = f.first_accept;
     d->tb.row_shift = f.row_shift;
-    d->fixed_smem = f.t2.size() * 4 + f.accept_mask.size() * 4 + f.t1.size() * 2 + 16 + 256 + 8 * 32 + 512;
+    d->fixed_smem = f.t2.size() * 4 + f.accept_mask.size() * 4 + f.t1.size() * 2 + 16 + 3 * 256 + 8 * 32 + 512;
     per_device_[device] = d;
   }
   return per_device_[device];
@@ -973,6 +974,12 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         fin.host_status = c->h_set_status_dev;
         fin.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
         dense_flag = fin.sync + 4;
+        static const bool want_trace = getenv("RJ_FIN_TRACE") != nullptr;
+        if (want_trace) {
+          if (!c->fin_trace.Reserve((size_t)blocks * 5 * 8 + 8 * 8, error)) return -1;
+          cudaMemsetAsync(c->fin_trace.p, 0, (size_t)blocks * 5 * 8 + 64, s);
+          fin.trace = c->fin_trace.as<unsigned long long>();
+        }
         uint64_t n_arg = n, nsub_arg = nsub;
         void* args[] = {(void*)&d_text, (void*)&n_arg, (void*)&ds->tb, (void*)&own, (void*)&st, (void*)&nsub_arg,
                         (void*)&dense_flag, (void*)&work, (void*)&fin, (void*)&carries};
@@ -980,6 +987,23 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
                    "cooperative launch", error)) return -1;
         if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
         if (!Check(cudaGetLastError(), "launch", error) || !wait_all(fin.seq)) return -1;
+        if (fin.trace) {
+          // debugging aid: phase times of the in-kernel finish (ns, relative to the earliest scan end)
+          std::vector<unsigned long long> tr((size_t)blocks * 5);
+          cudaStreamSynchronize(s);
+          cudaMemcpy(tr.data(), fin.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
+          unsigned long long t0 = ~0ull, mx[5] = {0, 0, 0, 0, 0}, mn[5] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull};
+          for (int b2 = 0; b2 < blocks; ++b2) t0 = std::min(t0, tr[(size_t)b2 * 5]);
+          for (int b2 = 0; b2 < blocks; ++b2)
+            for (int q = 0; q < 5; ++q) {
+              unsigned long long v = tr[(size_t)b2 * 5 + q];
+              if (!v) continue;
+              mx[q] = std::max(mx[q], v - t0);
+              mn[q] = std::min(mn[q], v - t0);
+            }
+          fprintf(stderr, "[fin trace] scan_end %llu..%llu  barrier_out %llu..%llu  copied %llu..%llu  last_in %llu  published %llu (ns)\n",
+                  mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mx[3], mx[4]);
+        }
         bool overlap = false, clean = true;
         for (int j = 0; j < K; ++j) {
           const PipelineStatus& h = c->h_set_status[j];

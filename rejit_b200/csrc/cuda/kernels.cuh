@@ -96,6 +96,7 @@ struct FinishArgs {
   PipelineStatus* status;              // [K] device copies
   volatile PipelineStatus* host_status;  // [K] mapped host copies
   unsigned int seq;
+  unsigned long long* trace;           // optional (RJ_FIN_TRACE): 5 globaltimer stamps per CTA
 };
 constexpr unsigned int kFinOverlap = 1u, kFinDense = 2u, kFinOverflow = 4u;
 
@@ -394,6 +395,14 @@ __device__ __forceinline__ void GridBarrier(unsigned int* ctr, unsigned int expe
   __syncthreads();
 }
 
+__device__ __forceinline__ void FinTrace(const FinishArgs& fin, int slot) {
+  if (fin.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    fin.trace[(size_t)blockIdx.x * 5 + slot] = t;
+  }
+}
+
 // the scan's bookkeeping for one (pattern, sub-region) count
 __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_t sub, uint32_t total, bool over,
                                            uint32_t cap) {
@@ -405,7 +414,9 @@ __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_
 
 __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
                                             const CarrySet& carries) {
+  FinTrace(fin, 0);
   GridBarrier(&fin.sync[0], gridDim.x);
+  FinTrace(fin, 1);
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
@@ -482,12 +493,14 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
   // the last CTA to get here publishes the status blocks
   // (no static shared memory here: the scan kernels use the whole opt-in carve-out)
   __syncthreads();
+  FinTrace(fin, 2);
   int is_last = 0;
   if (threadIdx.x == 0) {
     __threadfence();
     is_last = (atomicAdd(&fin.sync[1], 1u) == gridDim.x - 1) ? 1 : 0;
   }
   if (!__syncthreads_or(is_last)) return;
+  FinTrace(fin, 3);
   __threadfence();
   const unsigned int flags = __ldcg(&fin.sync[2]);
   const unsigned int need_cap = __ldcg(&fin.sync[3]);
@@ -521,10 +534,11 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
       h->dense = v.dense;
       h->full_result = 0;
       __threadfence_system();
-      h->seq = fin.seq;
-      __threadfence_system();
+      h->seq = fin.seq;                  // (the end of the kernel flushes it)
     }
   }
+  __syncthreads();
+  FinTrace(fin, 4);
 }
 
 constexpr int kDfaChainHits = 3;
@@ -739,13 +753,13 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
 // Algorithmic traffic: N bytes read (once for all patterns) + 16 bytes per match.
 // ===========================================================================
 struct SetTables {
-  const uint16_t* t1;                  // [S*C] next state * C
-  const uint32_t* t2;                  // [S*C*C]
+  const uint16_t* t1;                  // [R*C] next state * C           (R rows = states + shadow rows)
+  const uint32_t* t2;                  // [R << (row_shift-2)] row offset after two bytes
   const uint8_t* byte_class;           // [256]
-  const uint32_t* accept_mask;         // [S]
+  const uint32_t* accept_mask;         // [R]
   uint32_t match_len[32];
   int n_patterns;
-  int n_states, n_classes, first_accept;
+  int n_rows, n_classes, first_accept;
   int row_shift;                       // pair-table rows are 2^row_shift bytes
 };
 
@@ -773,6 +787,11 @@ __device__ __forceinline__ void SetRecord(uint32_t state, uint64_t e, uint64_t l
   }
 }
 
+// Entries of the pair table are shared-memory ADDRESSES of the next row (the
+// kernel adds the table base while staging it); rows at or above the first
+// accepting row mean "an accept happened in this pair" (shadow rows: only in
+// between), so one step of a chain is   row = *(row + hi[b0] + lo[b1])   with
+// hi = class*C*4 and lo = class*4 looked up per byte.
 __global__ void __launch_bounds__(576, 1)
 k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange range, SubStore out,
           uint64_t nsub_pat, unsigned int* dense_flag, unsigned long long* work_counter, FinishArgs fin,
@@ -782,22 +801,28 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
   const int warp_in_cta = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const uint32_t C = (uint32_t)tb.n_classes;
-  const uint32_t C2 = C * C;
-  const int t2_entries = tb.n_states << (tb.row_shift - 2);
-  const int t1_entries = tb.n_states * (int)C;
-  (void)C2;
-  // layout: [t2 u32, padded rows][accept masks u32][t1 u16][class map 256][barriers][tiles]
+  const int t2_entries = tb.n_rows << (tb.row_shift - 2);
+  const int t1_entries = tb.n_rows * (int)C;
+  // layout: [t2 u32, padded rows][accept masks u32][t1 u16][class 256][hi 256][lo 256][barriers][tiles]
   uint32_t* s_t2 = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* s_mask = s_t2 + t2_entries;
-  uint16_t* s_t1 = reinterpret_cast<uint16_t*>(s_mask + tb.n_states);
+  uint16_t* s_t1 = reinterpret_cast<uint16_t*>(s_mask + tb.n_rows);
   uint8_t* s_class = reinterpret_cast<uint8_t*>(s_t1) + (((size_t)t1_entries * 2 + 15) & ~(size_t)15);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_class + 256) + 7) & ~(uintptr_t)7);
+  uint8_t* s_hi = s_class + 256;
+  uint8_t* s_lo = s_hi + 256;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_lo + 256) + 7) & ~(uintptr_t)7);
   uint8_t* s_tiles = reinterpret_cast<uint8_t*>(s_bar + warps_per_cta);
   s_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tiles) + 127) & ~(uintptr_t)127);
-  for (int i = threadIdx.x; i < t2_entries; i += blockDim.x) s_t2[i] = tb.t2[i];
-  for (int i = threadIdx.x; i < tb.n_states; i += blockDim.x) s_mask[i] = tb.accept_mask[i];
+  const uint32_t t2_base = SmemAddr(s_t2);
+  for (int i = threadIdx.x; i < t2_entries; i += blockDim.x) s_t2[i] = tb.t2[i] + t2_base;
+  for (int i = threadIdx.x; i < tb.n_rows; i += blockDim.x) s_mask[i] = tb.accept_mask[i];
   for (int i = threadIdx.x; i < t1_entries; i += blockDim.x) s_t1[i] = tb.t1[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_class[i] = tb.byte_class[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const uint32_t c = tb.byte_class[i];
+    s_class[i] = (uint8_t)c;
+    s_hi[i] = (uint8_t)(c * C * 4u);
+    s_lo[i] = (uint8_t)(c * 4u);
+  }
   uint64_t* bar = s_bar + warp_in_cta;
   if (lane == 0) MbarInit(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -805,10 +830,10 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
 
   uint8_t* tile = s_tiles + (size_t)warp_in_cta * kDfaTileBytes;
   const uint32_t my_warm_addr = SmemAddr(tile) + (uint32_t)lane * kDfaStreamBytes;
-  const uint32_t t2_base = SmemAddr(s_t2);
   const int row_shift = tb.row_shift;
-  const uint32_t acc_row = (uint32_t)tb.first_accept << row_shift;
-  const uint32_t class_base = SmemAddr(s_class);
+  const uint32_t acc_row = t2_base + ((uint32_t)tb.first_accept << row_shift);
+  const uint32_t hi_base = SmemAddr(s_hi);
+  const uint32_t lo_base = SmemAddr(s_lo);
   const int K = tb.n_patterns;
   uint32_t phase = 0;
 
@@ -837,7 +862,7 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
       const uint64_t b = (a + kDfaStreamBytes < n) ? a + kDfaStreamBytes : n;
       if (a < n) {
         const bool warm = a >= 16;
-        uint32_t rowA = 0, rowB = 0;            // byte offset of the state's row in the pair table
+        uint32_t rowA = t2_base, rowB = t2_base;        // shared-memory address of the state's row
 #pragma unroll 1
         for (uint32_t it = 0; it < 10; ++it) {
           const uint4 vA = Lds128(my_warm_addr + it * 16);
@@ -847,12 +872,12 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
           uint32_t pA[8], pB[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            uint32_t a0 = Lds8(class_base + __byte_perm(wA[k >> 1], 0, 0x4440 + 2 * (k & 1)));
-            uint32_t a1 = Lds8(class_base + __byte_perm(wA[k >> 1], 0, 0x4441 + 2 * (k & 1)));
-            uint32_t b0 = Lds8(class_base + __byte_perm(wB[k >> 1], 0, 0x4440 + 2 * (k & 1)));
-            uint32_t b1 = Lds8(class_base + __byte_perm(wB[k >> 1], 0, 0x4441 + 2 * (k & 1)));
-            pA[k] = t2_base + (a0 * C + a1) * 4u;
-            pB[k] = t2_base + (b0 * C + b1) * 4u;
+            uint32_t a0 = Lds8(hi_base + __byte_perm(wA[k >> 1], 0, 0x4440 + 2 * (k & 1)));
+            uint32_t a1 = Lds8(lo_base + __byte_perm(wA[k >> 1], 0, 0x4441 + 2 * (k & 1)));
+            uint32_t b0 = Lds8(hi_base + __byte_perm(wB[k >> 1], 0, 0x4440 + 2 * (k & 1)));
+            uint32_t b1 = Lds8(lo_base + __byte_perm(wB[k >> 1], 0, 0x4441 + 2 * (k & 1)));
+            pA[k] = a0 + a1;
+            pB[k] = b0 + b1;
           }
           const uint32_t rowA0 = rowA, rowB0 = rowB;
           uint32_t peakA = 0, peakB = 0;
@@ -863,48 +888,37 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
             eB[k] = Lds32(rowB + pB[k]);
             peakA = max(peakA, eA[k]);
             peakB = max(peakB, eB[k]);
-            rowA = eA[k] & 0x7FFFFFFFu;
-            rowB = eB[k] & 0x7FFFFFFFu;
+            rowA = eA[k];
+            rowB = eB[k];
           }
           if (it == 0) {
-            if (!warm) rowA = 0;
-          } else {
+            if (!warm) rowA = t2_base;
+          } else if (peakA >= acc_row || (it < 9 && peakB >= acc_row)) {
             // rare: some pair of this group accepted — walk the saved entries
-            if (peakA >= acc_row) {
-              uint32_t prev = rowA0;
-              const uint64_t p0 = a - 16 + (uint64_t)it * 16;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+              if (ch == 0 ? (peakA < acc_row) : (it >= 9 || peakB < acc_row)) continue;
+              uint32_t prev = ch ? rowB0 : rowA0;
+              const uint64_t p0 = (ch ? a + 128 : a - 16) + (uint64_t)it * 16;
+              uint32_t cnt = ch ? cntB : cntA;
+              uint32_t hit[kSetChainHits];
+#pragma unroll
+              for (int q = 0; q < kSetChainHits; ++q) hit[q] = ch ? hitB[q] : hitA[q];
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                const uint32_t e = eA[k];
+                const uint32_t e = ch ? eB[k] : eA[k];
                 if (e >= acc_row) {
-                  if (e & 0x80000000u) {
-                    uint32_t c1 = s_class[__byte_perm(wA[k >> 1], 0, 0x4440 + 2 * (k & 1))];
-                    uint32_t mid = s_t1[(prev >> row_shift) * C + c1] / C;
-                    SetRecord(mid, p0 + 2 * k + 1, b, s_mask, tb, sub_lo, range, hitA, cntA);
-                  }
-                  if ((e & 0x7FFFFFFFu) >= acc_row)
-                    SetRecord((e & 0x7FFFFFFFu) >> row_shift, p0 + 2 * k + 2, b, s_mask, tb, sub_lo, range, hitA, cntA);
+                  const uint32_t w = ch ? wB[k >> 1] : wA[k >> 1];
+                  const uint32_t c1 = s_class[__byte_perm(w, 0, 0x4440 + 2 * (k & 1))];
+                  const uint32_t mid = s_t1[((prev - t2_base) >> row_shift) * C + c1] / C;
+                  SetRecord(mid, p0 + 2 * k + 1, b, s_mask, tb, sub_lo, range, hit, cnt);
+                  SetRecord((e - t2_base) >> row_shift, p0 + 2 * k + 2, b, s_mask, tb, sub_lo, range, hit, cnt);
                 }
-                prev = e & 0x7FFFFFFFu;
+                prev = e;
               }
-            }
-            if (it < 9 && peakB >= acc_row) {
-              uint32_t prev = rowB0;
-              const uint64_t p0 = a + 128 + (uint64_t)it * 16;
+              if (ch) { cntB = cnt; } else { cntA = cnt; }
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const uint32_t e = eB[k];
-                if (e >= acc_row) {
-                  if (e & 0x80000000u) {
-                    uint32_t c1 = s_class[__byte_perm(wB[k >> 1], 0, 0x4440 + 2 * (k & 1))];
-                    uint32_t mid = s_t1[(prev >> row_shift) * C + c1] / C;
-                    SetRecord(mid, p0 + 2 * k + 1, b, s_mask, tb, sub_lo, range, hitB, cntB);
-                  }
-                  if ((e & 0x7FFFFFFFu) >= acc_row)
-                    SetRecord((e & 0x7FFFFFFFu) >> row_shift, p0 + 2 * k + 2, b, s_mask, tb, sub_lo, range, hitB, cntB);
-                }
-                prev = e & 0x7FFFFFFFu;
-              }
+              for (int q = 0; q < kSetChainHits; ++q) { if (ch) hitB[q] = hit[q]; else hitA[q] = hit[q]; }
             }
           }
         }

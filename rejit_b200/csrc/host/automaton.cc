@@ -528,26 +528,49 @@ bool BuildSetDfa(const std::vector<const CompiledAutomaton*>& members, SetDfa* o
     out->max_len = std::max<uint32_t>(out->max_len, out->match_len.back());
   }
   if (out->max_len > 17) return false;          // the kernel warms every chain up on 16 bytes
-  out->t1.resize(out->next.size());
-  for (size_t i = 0; i < out->next.size(); ++i) out->t1[i] = static_cast<uint16_t>(out->next[i] * C);
-  // pair-table rows are padded to a power of two so that the state of a row
-  // offset is a shift
+  // the kernel's class tables hold class*C*4 and class*4 in one byte each
+  if ((C - 1) * C * 4 > 255) return false;
+  // shadow rows (see automaton.h)
+  std::vector<int> shadow_of_state(S, -1);
+  out->row_state.resize(S);
+  for (int s = 0; s < S; ++s) out->row_state[s] = static_cast<uint16_t>(s);
+  for (int s = 0; s < S; ++s)
+    for (int c1 = 0; c1 < C; ++c1) {
+      int mid = out->next[static_cast<size_t>(s) * C + c1];
+      if (mid < out->first_accept) continue;
+      for (int c2 = 0; c2 < C; ++c2) {
+        int fin = out->next[static_cast<size_t>(mid) * C + c2];
+        if (fin < out->first_accept && shadow_of_state[fin] < 0) {
+          shadow_of_state[fin] = static_cast<int>(out->row_state.size());
+          out->row_state.push_back(static_cast<uint16_t>(fin));
+        }
+      }
+    }
+  const int R = static_cast<int>(out->row_state.size());
+  out->n_rows = R;
+  out->accept_mask.resize(R, 0);
+  out->t1.assign(static_cast<size_t>(R) * C, 0);
+  for (int r = 0; r < R; ++r)
+    for (int c = 0; c < C; ++c)
+      out->t1[static_cast<size_t>(r) * C + c] = static_cast<uint16_t>(out->next[static_cast<size_t>(out->row_state[r]) * C + c] * C);
+  // pair-table rows are padded to a power of two so that the row of an entry is a shift
   int row_words = 1;
   while (row_words < C * C) row_words <<= 1;
   out->row_shift = 2;
   while ((1 << out->row_shift) < row_words * 4) ++out->row_shift;
-  if (static_cast<size_t>(S) * row_words * 4 > 128 * 1024) return false;
-  out->t2.assign(static_cast<size_t>(S) * row_words, 0);
-  for (int s = 0; s < S; ++s)
+  if (static_cast<size_t>(R) * row_words * 4 > 128 * 1024) return false;
+  out->t2.assign(static_cast<size_t>(R) * row_words, 0);
+  for (int r = 0; r < R; ++r) {
+    const int s = out->row_state[r];
     for (int c1 = 0; c1 < C; ++c1) {
       int mid = out->next[static_cast<size_t>(s) * C + c1];
       for (int c2 = 0; c2 < C; ++c2) {
-        uint32_t fin = out->next[static_cast<size_t>(mid) * C + c2];
-        uint32_t v = fin << out->row_shift;
-        if (mid >= out->first_accept) v |= 0x80000000u;
-        out->t2[static_cast<size_t>(s) * row_words + c1 * C + c2] = v;
+        int fin = out->next[static_cast<size_t>(mid) * C + c2];
+        int row = (mid >= out->first_accept && fin < out->first_accept) ? shadow_of_state[fin] : fin;
+        out->t2[static_cast<size_t>(r) * row_words + c1 * C + c2] = static_cast<uint32_t>(row) << out->row_shift;
       }
     }
+  }
   return true;
 }
 

@@ -97,12 +97,17 @@ struct SetDfa {
   int n_states = 0, n_classes = 0, first_accept = 0;
   std::array<uint8_t, 256> byte_class{};
   std::vector<uint16_t> next;            // [n_states * n_classes] -> state id
-  std::vector<uint32_t> accept_mask;     // [n_states] bit j: pattern j ends here
+  std::vector<uint32_t> accept_mask;     // [n_rows] bit j: pattern j ends here (0 for shadow rows)
   std::vector<uint32_t> match_len;       // [n_patterns]
   uint32_t max_len = 0;
-  // flat device layouts
-  std::vector<uint16_t> t1;              // [S*C]   next state * C
-  std::vector<uint32_t> t2;              // [S][2^row_shift / 4]: (state after two bytes) << row_shift, bit 31: accept in between
+  // flat device layouts.  Rows = the states, followed by SHADOW rows: a copy of a
+  // non-accepting state's row, entered when the state in between two bytes
+  // accepted, so that "some accept happened" is visible in the row address alone
+  // (rows >= first_accept) and the scan needs no flag bit in the entries.
+  int n_rows = 0;
+  std::vector<uint16_t> row_state;       // [n_rows] the state a row stands for
+  std::vector<uint16_t> t1;              // [n_rows*C]   next state * C
+  std::vector<uint32_t> t2;              // [n_rows][2^row_shift / 4]: (row after two bytes) << row_shift
   int row_shift = 0;                     // log2 of the padded row size in bytes
 };
 // Returns false when the set cannot be fused (a member is not a fixed-length

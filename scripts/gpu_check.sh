@@ -12,7 +12,7 @@ echo "== bench" ; timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out
 tail -5 gpurun_out/bench.err
 echo "== bench reference" ; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>> gpurun_out/bench.err | tee gpurun_out/bench_reference.json
 if [ "${RJ_EXTRA:-0}" = "1" ]; then
-echo "== e2e probe"; timeout 300 python scripts/e2e_probe.py 2>&1 | tail -12 | cut -c1-300
+echo "== finish trace"; timeout 300 python scripts/fin_trace.py 2>&1 | tail -8 | tee gpurun_out/fin_trace.txt | cut -c1-300
 echo "== bench_extra"; timeout 1200 python scripts/bench_extra.py 2>&1 | tee gpurun_out/bench_extra.jsonl | cut -c1-400
 fi
 if [ "${RJ_SWEEP:-0}" = "1" ]; then

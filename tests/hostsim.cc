@@ -337,18 +337,23 @@ int64_t hostsim_set_match_all(const char* joined, size_t len, char sep, const ui
       uint64_t p = a >= 16 ? a - 16 : 0;
       uint32_t row = 0;                       // state << row_shift
       while (p < b) {
-        uint32_t state = row >> d.row_shift;
+        uint32_t state = row >> d.row_shift;            // a row: a state or the shadow of one
+        if ((int)state >= d.n_rows) return -6;
         uint32_t c1 = d.byte_class[text[p]];
         uint32_t c2 = (p + 1 < n) ? d.byte_class[text[p + 1]] : 0;
         uint32_t ent = d.t2[state * RW + c1 * C + c2];
         uint32_t mid = d.t1[state * C + c1] / C;
-        if (((ent & 0x80000000u) != 0) != ((int)mid >= d.first_accept)) return -6;
+        if (mid != d.next[(size_t)d.row_state[state] * C + c1]) return -6;
         if ((int)mid >= d.first_accept) report(mid, p + 1, a, b);
-        row = ent & 0x7FFFFFFFu;
+        row = ent;
         if (p + 1 < n) {
-          uint32_t fin = d.t1[mid * C + c2] / C;
-          if ((fin << d.row_shift) != row) return -6;
-          if (row >= acc_row) report(fin, p + 2, a, b);
+          uint32_t fin = d.next[(size_t)mid * C + c2];
+          uint32_t r2 = row >> d.row_shift;
+          if ((int)r2 >= d.n_rows || d.row_state[r2] != fin) return -6;
+          // an accept in between must be visible in the row address
+          if ((int)mid >= d.first_accept && row < acc_row) return -6;
+          if ((int)r2 >= d.n_states && !((int)mid >= d.first_accept && (int)fin < d.first_accept)) return -6;
+          if (row >= acc_row) report(r2, p + 2, a, b);      // shadow rows carry an empty mask
         }
         p += 2;
       }
