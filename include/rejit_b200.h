@@ -152,6 +152,22 @@ int64_t rejit_b200_match_all_text(rejit_b200_program* program, const rejit_b200_
                                   uint64_t** out_pairs, rejit_b200_stats* stats,
                                   char* err, size_t err_length);
 
+/* Regej::ReplaceAll (reference include/rejit.h:131, src/rejit.cc:221-226 and
+ * Replace, src/rejit.cc:97-112) with the rebuild done on the device (SURVEY.md
+ * §8f rank 2): every match is replaced by with[0..with_length).  Returns the
+ * number of matches replaced; *out is malloc'ed (rejit_b200_free).              */
+int64_t rejit_b200_replace_all(rejit_b200_program* program, const char* text, size_t text_length,
+                               const char* with, size_t with_length, char** out, size_t* out_length,
+                               rejit_b200_stats* stats, char* err, size_t err_length);
+/* The same on an uploaded text; the result stays on the device as a new text, so
+ * that substitutions chain without host round trips (regex-dna: the header /
+ * newline strip followed by the eleven IUB substitutions, sample/regexdna.cc:49,69-85). */
+rejit_b200_text* rejit_b200_replace_all_text(rejit_b200_program* program, const rejit_b200_text* text,
+                                             const char* with, size_t with_length, int64_t* n_matches,
+                                             rejit_b200_stats* stats, char* err, size_t err_length);
+size_t rejit_b200_text_length(const rejit_b200_text* text);
+int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capacity, char* err, size_t err_length);
+
 /* Pattern sets: several compiled patterns matched
  * against the same text.  When every member is a fixed-length, anchor-free
  * alternation (regex-dna's nine variants) they are fused into ONE automaton and

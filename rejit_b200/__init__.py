@@ -52,6 +52,7 @@ EXPORTED = [
     "rejit_b200_text_upload", "rejit_b200_text_free", "rejit_b200_match_all_text",
     "rejit_b200_set_create", "rejit_b200_set_free", "rejit_b200_set_describe",
     "rejit_b200_match_all_set_text", "rejit_b200_match_all_set_device", "rejit_b200_match_all_set_device_slab",
+    "rejit_b200_replace_all", "rejit_b200_replace_all_text", "rejit_b200_text_length", "rejit_b200_text_download",
 ]
 
 
@@ -121,6 +122,15 @@ def lib():
     L.rejit_b200_match_all_set_device_slab.argtypes = [vp, ctypes.c_int, vp, sz, ctypes.c_uint64, ctypes.c_uint64,
                                                        ctypes.c_uint64, ctypes.POINTER(Carry), ctypes.POINTER(Carry),
                                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_replace_all.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz),
+                                         ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_replace_all.restype = ctypes.c_int64
+    L.rejit_b200_replace_all_text.argtypes = [vp, vp, vp, sz, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(Stats),
+                                              cp, sz]
+    L.rejit_b200_replace_all_text.restype = vp
+    L.rejit_b200_text_length.argtypes = [vp]
+    L.rejit_b200_text_length.restype = sz
+    L.rejit_b200_text_download.argtypes = [vp, vp, sz, cp, sz]
     _lib = L
     return L
 
@@ -164,6 +174,51 @@ class DeviceText:
         if self.ptr:
             lib().rejit_b200_device_free(self.device, self.ptr)
             self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Text:
+    """An uploaded text (rejit_b200_text): searched and rewritten on the device;
+    `replace_all` returns a new Text, so substitutions chain without host copies."""
+
+    def __init__(self, data=None, device: int = 0, _handle=None):
+        L = lib()
+        if _handle is not None:
+            self._h = ctypes.c_void_p(_handle)
+            return
+        if hasattr(data, "ctypes"):
+            import numpy as np
+            keep = np.ascontiguousarray(data, dtype=np.uint8)
+            ptr, n = ctypes.c_void_p(keep.ctypes.data), keep.size
+        else:
+            keep = _as_bytes(data)
+            ptr, n = ctypes.cast(ctypes.c_char_p(keep), ctypes.c_void_p), len(keep)
+        err = ctypes.create_string_buffer(512)
+        h = L.rejit_b200_text_upload(device, ptr, n, err, len(err))
+        if not h:
+            raise RejitError(err.value.decode("latin-1"))
+        self._h = ctypes.c_void_p(h)
+
+    def __len__(self) -> int:
+        return int(lib().rejit_b200_text_length(self._h))
+
+    def download(self) -> bytes:
+        n = len(self)
+        buf = ctypes.create_string_buffer(max(n, 1))
+        err = ctypes.create_string_buffer(512)
+        if lib().rejit_b200_text_download(self._h, buf, n, err, len(err)) != 0:
+            raise RejitError(err.value.decode("latin-1"))
+        return buf.raw[:n]
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib().rejit_b200_text_free(self._h)
+            self._h = None
 
     def __del__(self):
         try:
@@ -300,6 +355,53 @@ class Regej:
         if r < 0:
             raise RejitError(err.value.decode("latin-1"))
         return r == 1
+
+    # -- ReplaceAll (rebuilt on the device) ---------------------------------------
+    def replace_all(self, text, with_, stats: Optional[Stats] = None):
+        """Regej::ReplaceAll: returns (rebuilt bytes, number of matches)."""
+        if not self.compile():
+            return _as_bytes(text), 0
+        t, w = _as_bytes(text), _as_bytes(with_)
+        out, n_out = ctypes.c_void_p(), ctypes.c_size_t()
+        err = ctypes.create_string_buffer(512)
+        r = lib().rejit_b200_replace_all(self._prog, ctypes.cast(ctypes.c_char_p(t), ctypes.c_void_p), len(t),
+                                         ctypes.cast(ctypes.c_char_p(w), ctypes.c_void_p), len(w),
+                                         ctypes.byref(out), ctypes.byref(n_out),
+                                         ctypes.byref(stats) if stats is not None else None, err, len(err))
+        if r < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        try:
+            return ctypes.string_at(out.value, n_out.value), int(r)
+        finally:
+            lib().rejit_b200_free(out)
+
+    def replace_all_text(self, text: "Text", with_, stats: Optional[Stats] = None):
+        """The same on an uploaded Text; returns (new Text, number of matches)."""
+        if not self.compile():
+            raise ParserError(self.status_string)
+        w = _as_bytes(with_)
+        n = ctypes.c_int64()
+        err = ctypes.create_string_buffer(512)
+        h = lib().rejit_b200_replace_all_text(self._prog, text._h, ctypes.cast(ctypes.c_char_p(w), ctypes.c_void_p),
+                                              len(w), ctypes.byref(n),
+                                              ctypes.byref(stats) if stats is not None else None, err, len(err))
+        if not h:
+            raise RejitError(err.value.decode("latin-1"))
+        return Text(_handle=h), int(n.value)
+
+    def match_all_text(self, text: "Text", stats: Optional[Stats] = None) -> List[Tuple[int, int]]:
+        if not self.compile():
+            return []
+        pairs = ctypes.POINTER(ctypes.c_uint64)()
+        err = ctypes.create_string_buffer(512)
+        n = lib().rejit_b200_match_all_text(self._prog, text._h, ctypes.byref(pairs),
+                                            ctypes.byref(stats) if stats is not None else None, err, len(err))
+        if n < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        try:
+            return [(int(pairs[2 * i]), int(pairs[2 * i + 1])) for i in range(n)]
+        finally:
+            lib().rejit_b200_free(pairs)
 
     # -- device-resident text --------------------------------------------------
     def match_all_device(self, dtext: DeviceText, length: Optional[int] = None, out_ptr=None,

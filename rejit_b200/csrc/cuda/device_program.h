@@ -344,6 +344,77 @@ RJ_HD void FaithfulSegment(const NfaTables& t, const uint8_t* text, uint64_t n, 
   }
 }
 
+// ---------------------------------------------------------------------------
+// ReplaceAll placement (k_replace_tiles; also driven on the CPU by
+// tests/hostsim.cc).  `pairs` = the (begin,end) matches, `removed[i]` = total
+// length of the matches before match i.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kReplaceTile = 4096;
+
+struct ReplaceTileHead {
+  uint64_t m0, m1;          // the tile's own matches: begin in [tile_lo, tile_hi) (+ end of text for the last tile)
+  uint64_t removed_before;  // bytes removed before tile_lo
+  uint64_t skip_end;        // end of the match straddling tile_lo (>= tile_lo)
+  uint64_t r0;              // removed[m0]
+};
+
+RJ_HD uint64_t ReplaceLowerBound(const uint64_t* pairs, uint64_t m, uint64_t key) {
+  uint64_t lo = 0, hi = m;                 // first i with begin[i] >= key
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (pairs[2 * mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+RJ_HD void ReplaceHead(const uint64_t* pairs, const uint64_t* removed, uint64_t m, uint64_t tile_lo,
+                              ReplaceTileHead* h) {
+  const uint64_t m0 = h->m0;
+  h->removed_before = 0;
+  h->skip_end = tile_lo;
+  h->r0 = (m0 < m) ? removed[m0] : 0;
+  if (m0 > 0) {
+    const uint64_t pb = pairs[2 * (m0 - 1)], pe = pairs[2 * (m0 - 1) + 1];
+    h->removed_before = removed[m0 - 1] + ((pe < tile_lo ? pe : tile_lo) - pb);
+    if (pe > h->skip_end) h->skip_end = pe;
+  }
+}
+
+// One thread places input bytes [tile_lo + 16*thread, +16) of the tile and the
+// replacements of the matches beginning there.  s_b / s_e: begin / clipped end of
+// the own matches relative to tile_lo; s_r: removed[m0+i] - removed[m0].
+RJ_HD void ReplacePlace(uint32_t thread, const uint8_t* text, uint64_t tile_lo, uint64_t tile_hi, bool last,
+                               const ReplaceTileHead& h, uint32_t cnt, const uint16_t* s_b, const uint16_t* s_e,
+                               const uint16_t* s_r, const uint8_t* with, uint32_t w, uint8_t* out) {
+  const uint32_t span = (uint32_t)(tile_hi - tile_lo);
+  const uint32_t p = thread * 16;
+  if (p > span) return;
+  const uint64_t out_base = tile_lo - h.removed_before + (uint64_t)w * h.m0;
+  const uint32_t head_skip = (uint32_t)((h.skip_end < tile_hi ? h.skip_end : tile_hi) - tile_lo);
+  uint32_t lo = 0, hi = cnt;                // i = own matches beginning before p
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_b[mid] < p) lo = mid + 1; else hi = mid; }
+  uint32_t i = lo;
+  uint32_t rem = head_skip < p ? head_skip : p;        // removed inside the tile before p
+  uint32_t cur_skip = head_skip;
+  if (i > 0) {
+    const uint32_t pe = s_e[i - 1];
+    rem += s_r[i - 1] + ((pe < p ? pe : p) - s_b[i - 1]);
+    if (pe > cur_skip) cur_skip = pe;
+  }
+  uint64_t q = out_base + p - rem + (uint64_t)w * i;
+  // the thread whose range holds the end of the text also places the matches that begin there
+  const uint32_t stop = (p + 16 < span) ? p + 16 : span + ((last && p + 16 > span) ? 1u : 0u);
+  for (uint32_t pos = p; pos < stop; ++pos) {
+    if (i < cnt && s_b[i] == pos) {
+      for (uint32_t k = 0; k < w; ++k) out[q + k] = with[k];
+      q += w;
+      if (s_e[i] > cur_skip) cur_skip = s_e[i];
+      ++i;
+    }
+    if (pos < span && pos >= cur_skip) out[q++] = text[tile_lo + pos];
+  }
+}
+
 }  // namespace rejit_b200
 
 #endif  // REJIT_B200_CUDA_DEVICE_PROGRAM_H_

@@ -83,7 +83,7 @@ class DeviceContext {
   // ordered stores (slot ranges per sub-region): candidates and needle hits
   Buffer sub_b, sub_e, sub_count, hsub_b, hsub_e, hsub_count;
   // dense (gathered, sorted) lists
-  Buffer dense_b, dense_e, hits_b, hits_e, out_pairs, fin_trace;
+  Buffer dense_b, dense_e, hits_b, hits_e, out_pairs, fin_trace, with_buf;
   uint64_t dense_cap = 0, hits_cap = 0;
   // unordered fallback (k_dfa_scan)
   Buffer cand_b, cand_e;
@@ -101,6 +101,8 @@ class DeviceContext {
   Buffer flush;
   PipelineStatus* h_status = nullptr; // pinned + mapped: the resolve kernel writes it, the host spins on seq
   PipelineStatus* h_status_dev = nullptr;   // device view of h_status
+  FinRecord* h_fin = nullptr;               // mapped: records of the in-kernel finish (one per pattern)
+  FinRecord* h_fin_dev = nullptr;
   unsigned int call_seq = 0;
   bool attr_done = false;
   bool coop = false;                  // cooperative launch available: scans finish in-kernel
@@ -118,6 +120,9 @@ class DeviceContext {
     RJ_TRY(cudaHostAlloc(&h_status, sizeof(PipelineStatus), cudaHostAllocMapped));
     memset(h_status, 0, sizeof(PipelineStatus));
     RJ_TRY(cudaHostGetDevicePointer(&h_status_dev, h_status, 0));
+    RJ_TRY(cudaHostAlloc(&h_fin, 32 * sizeof(FinRecord), cudaHostAllocMapped));
+    memset(h_fin, 0, 32 * sizeof(FinRecord));
+    RJ_TRY(cudaHostGetDevicePointer(&h_fin_dev, h_fin, 0));
     RJ_TRY(cudaHostAlloc(&h_set_status, 32 * sizeof(PipelineStatus), cudaHostAllocMapped));
     memset(h_set_status, 0, 32 * sizeof(PipelineStatus));
     RJ_TRY(cudaHostGetDevicePointer(&h_set_status_dev, h_set_status, 0));
@@ -328,6 +333,41 @@ DeviceProgram* Program::OnDevice(int device, std::string* error) {
 // ===========================================================================
 namespace {
 
+// Waits until the in-kernel finish has published its K records for call `seq`
+// (both halves of every record), then turns record j into a PipelineStatus.
+bool WaitFinRecords(DeviceContext* c, int K, unsigned int seq, std::string* error) {
+  uint64_t spins = 0;
+  for (int j = 0; j < K; ++j) {
+    volatile FinRecord* r = c->h_fin + j;
+    while (r->seq0 != seq || r->seq1 != seq) {
+      if ((++spins & 0x3FFF) == 0) {
+        cudaError_t q = cudaStreamQuery(c->stream);
+        if (q == cudaSuccess) {
+          if (r->seq0 == seq && r->seq1 == seq) break;
+          if (error) *error = "rejit_b200: the scan kernel did not report";
+          return false;
+        }
+        if (q != cudaErrorNotReady) { Check(q, "cudaStreamQuery", error); return false; }
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return true;
+}
+
+PipelineStatus StatusFromRecord(const FinRecord& r, const Carry& carry_in) {
+  PipelineStatus st{};
+  st.n_candidates = r.n_matches;
+  st.n_matches = r.n_matches;
+  st.carry_cur = r.n_matches ? r.last_end : carry_in.cur;
+  st.carry_tail = r.n_matches ? r.last_end : carry_in.tail;
+  st.overflow = (r.flags & kFinOverflow) ? 1u : 0u;
+  st.need_cap = r.need_cap;
+  st.need_large = (r.flags & kFinOverlap) ? 1u : 0u;
+  st.dense = (r.flags & kFinDense) ? 1u : 0u;
+  return st;
+}
+
 struct Slab {                 // how a launch maps local offsets to the whole text
   ScanRange own;
   uint64_t base_offset;       // added to every reported offset
@@ -529,8 +569,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
             fin.out_stride = 0;
             fin.out_cap = ocap;
             fin.base_offset = slab.base_offset;
-            fin.status = d_status;
-            fin.host_status = c->h_status_dev;
+            fin.host_records = c->h_fin_dev;
             fin.seq = fused_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
             dense_flag = fin.sync + 4;
             ScanRange own = slab.own;
@@ -591,7 +630,8 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     };
     if (ordered && fused) {
       RJ_TRY(cudaGetLastError());
-      if (!wait_status(fused_seq)) return false;
+      if (!WaitFinRecords(c, 1, fused_seq, error)) return false;
+      st = StatusFromRecord(c->h_fin[0], carry_in);
       if (st.need_large && !st.overflow && !st.dense) {
         // neighbouring candidates overlap: the general resolve decides
         RJ_TRY(cudaMemsetAsync(d_status, 0, sizeof(PipelineStatus), s));
@@ -970,8 +1010,7 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         fin.out_stride = per_cap;
         fin.out_cap = per_cap;
         fin.base_offset = base_offset;
-        fin.status = d_status;
-        fin.host_status = c->h_set_status_dev;
+        fin.host_records = c->h_fin_dev;
         fin.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
         dense_flag = fin.sync + 4;
         static const bool want_trace = getenv("RJ_FIN_TRACE") != nullptr;
@@ -986,7 +1025,8 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         if (!Check(cudaLaunchCooperativeKernel((const void*)k_set_tma, dim3(blocks), dim3(warps * 32), args, smem, s),
                    "cooperative launch", error)) return -1;
         if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
-        if (!Check(cudaGetLastError(), "launch", error) || !wait_all(fin.seq)) return -1;
+        if (!Check(cudaGetLastError(), "launch", error) || !WaitFinRecords(c, K, fin.seq, error)) return -1;
+        for (int j = 0; j < K; ++j) c->h_set_status[j] = StatusFromRecord(c->h_fin[j], carries.c[j]);
         if (fin.trace) {
           // debugging aid: phase times of the in-kernel finish (ns, relative to the earliest scan end)
           std::vector<unsigned long long> tr((size_t)blocks * 5);
@@ -1131,6 +1171,96 @@ int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int
     stats->strategy = (int)prog->automaton().strategy;
   }
   return (int64_t)(total / 2);
+}
+
+// ===========================================================================
+// ReplaceAll
+// ===========================================================================
+int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_t n, const uint8_t* with,
+                         uint64_t with_len, void** d_out, uint64_t* out_len, uint64_t* out_capacity,
+                         RunStats* stats, std::string* error) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return -1;
+  DeviceProgram* dp = prog->OnDevice(device, error);
+  if (!dp) return -1;
+  if (with_len > 0xFFFFFFFFull) { if (error) *error = "rejit_b200: replacement too long"; return -1; }
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slab slab{{0, n + 1}, 0};
+  PipelineStatus st;
+  Carry in;
+  if (!RunPipeline(c, prog, dp, d_text, n, slab, in, nullptr, 0, &st, stats, error)) return -1;
+  cudaStream_t s = c->stream;
+  const uint64_t m = st.n_matches;
+  const uint64_t* pairs = c->out_pairs.as<uint64_t>();
+  if (stats) cudaEventRecord(c->ev[0], s);
+  uint64_t total_removed = 0;
+  if (m) {
+    if (!c->ReserveScratch(m, error)) return -1;
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->wide.as<uint64_t>(), c->slot.as<uint64_t>(), (int64_t)m, s);
+    if (!c->cub_tmp.Reserve(tmp, error)) return -1;
+    int blocks = (int)std::min<uint64_t>((m + 255) / 256, (uint64_t)c->sm_count * 8);
+    k_match_lengths<<<blocks, 256, 0, s>>>(pairs, m, c->wide.as<uint64_t>());
+    RJ_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->wide.as<uint64_t>(), c->slot.as<uint64_t>(), (int64_t)m, s));
+    uint64_t tail[2] = {0, 0};
+    RJ_TRY(cudaMemcpyAsync(&tail[0], c->slot.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, s));
+    RJ_TRY(cudaMemcpyAsync(&tail[1], c->wide.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, s));
+    RJ_TRY(cudaStreamSynchronize(s));
+    total_removed = tail[0] + tail[1];
+    if (stats) stats->launches += 3;
+  }
+  const uint64_t len = n - total_removed + m * with_len;
+  const uint64_t cap = len + 64;
+  void* out = DeviceAlloc(device, cap, error);
+  if (!out) return -1;
+  bool ok = true;
+  if (m == 0) {
+    if (n) ok = Check(cudaMemcpyAsync(out, d_text, n, cudaMemcpyDeviceToDevice, s), "D2D", error);
+  } else {
+    ok = c->with_buf.Reserve(with_len + 16, error);
+    if (ok && with_len) ok = Check(cudaMemcpyAsync(c->with_buf.p, with, with_len, cudaMemcpyHostToDevice, s), "H2D", error);
+    if (ok) {
+      const uint64_t n_tiles = n / kReplaceTile + 1;
+      int blocks = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 8);
+      k_replace_tiles<<<blocks, 256, 0, s>>>(d_text, n, pairs, c->slot.as<uint64_t>(), m, c->with_buf.as<uint8_t>(),
+                                             (uint32_t)with_len, static_cast<uint8_t*>(out), n_tiles);
+      ok = Check(cudaGetLastError(), "k_replace_tiles", error);
+      if (stats) stats->launches += 1;
+    }
+  }
+  if (ok && stats) {
+    cudaEventRecord(c->ev[1], s);
+    ok = Check(cudaEventSynchronize(c->ev[1]), "sync", error);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    stats->total_ms += ms;
+  } else if (ok) {
+    ok = Check(cudaStreamSynchronize(s), "sync", error);
+  }
+  if (!ok) { DeviceFree(device, out); return -1; }
+  *d_out = out;
+  *out_len = len;
+  if (out_capacity) *out_capacity = cap;
+  return (int64_t)m;
+}
+
+int64_t ReplaceAllHost(int device, Program* prog, const uint8_t* text, uint64_t n, const uint8_t* with,
+                       uint64_t with_len, uint8_t** out, uint64_t* out_len, RunStats* stats, std::string* error) {
+  void* d_text = DeviceAlloc(device, n + 64, error);
+  if (!d_text) return -1;
+  if (n && !CopyToDevice(device, d_text, text, n, error)) { DeviceFree(device, d_text); return -1; }
+  void* d_out = nullptr;
+  uint64_t len = 0;
+  int64_t m = ReplaceAllDevice(device, prog, static_cast<const uint8_t*>(d_text), n, with, with_len, &d_out, &len, nullptr,
+                               stats, error);
+  DeviceFree(device, d_text);
+  if (m < 0) return -1;
+  *out = static_cast<uint8_t*>(malloc(std::max<uint64_t>(len, 1)));
+  bool ok = *out != nullptr && (len == 0 || CopyFromDevice(device, *out, d_out, len, error));
+  DeviceFree(device, d_out);
+  if (!ok) { free(*out); *out = nullptr; if (error && error->empty()) *error = "rejit_b200: out of memory"; return -1; }
+  *out_len = len;
+  return m;
 }
 
 int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error) {

@@ -118,6 +118,17 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
                         uint64_t** pairs, RunStats* stats, std::string* error, const SlabView* own = nullptr,
                         const Carry* carry_in = nullptr, Carry* carry_out = nullptr);
 
+// Regej::ReplaceAll on the device (reference
+// src/rejit.cc:221-226, 97-112): every match in d_text[0..n) is replaced by
+// with[0..with_len) (host bytes).  *d_out receives a DeviceAlloc'ed buffer holding
+// the *out_len rebuilt bytes; returns the number of matches, or -1.
+int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_t n, const uint8_t* with,
+                         uint64_t with_len, void** d_out, uint64_t* out_len, uint64_t* out_capacity,
+                         RunStats* stats, std::string* error);
+// Host-pointer convenience: uploads, replaces, downloads (*out is malloc'ed).
+int64_t ReplaceAllHost(int device, Program* prog, const uint8_t* text, uint64_t n, const uint8_t* with,
+                       uint64_t with_len, uint8_t** out, uint64_t* out_len, RunStats* stats, std::string* error);
+
 // MatchFull: 1 / 0, or -1 on error.
 int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error);
 

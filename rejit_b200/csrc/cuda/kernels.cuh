@@ -81,6 +81,19 @@ struct PipelineStatus {                // one per call, read back by the host
 
 struct CarrySet { Carry c[32]; };
 
+// What the in-kernel finish reports per pattern, in mapped host memory.  Two
+// 16-byte halves, each written with ONE store (one PCIe write, so each half is
+// seen whole) and each carrying the call's sequence number: the host waits until
+// both match — no system-scope fence on the device.
+struct __align__(16) FinRecord {
+  unsigned long long n_matches;
+  unsigned int flags;                  // kFin* bits
+  unsigned int seq0;
+  unsigned long long last_end;         // end of the last match (0 if none)
+  unsigned int need_cap;
+  unsigned int seq1;
+};
+
 // In-kernel finish of the fixed-length scans (k_dfa_tma, k_set_tma): the scan
 // grid is one CTA per SM, launched cooperatively, so that after a grid barrier
 // the same CTAs concatenate the slot ranges straight into the output.
@@ -93,8 +106,7 @@ struct FinishArgs {
   uint64_t* out_pairs;                 // pattern j's pairs start at out_pairs + j * 2 * out_stride
   uint64_t out_stride, out_cap;
   uint64_t base_offset;
-  PipelineStatus* status;              // [K] device copies
-  volatile PipelineStatus* host_status;  // [K] mapped host copies
+  FinRecord* host_records;             // [K] mapped host memory (see FinRecord)
   unsigned int seq;
   unsigned long long* trace;           // optional (RJ_FIN_TRACE): 5 globaltimer stamps per CTA
 };
@@ -413,7 +425,7 @@ __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_
 }
 
 __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
-                                            const CarrySet& carries) {
+                                            const CarrySet& carries, uint32_t* scratch /* >= 32 words of this warp's shared memory */) {
   FinTrace(fin, 0);
   GridBarrier(&fin.sync[0], gridDim.x);
   FinTrace(fin, 1);
@@ -490,55 +502,48 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
       }
     }
   }
-  // the last CTA to get here publishes the status blocks
-  // (no static shared memory here: the scan kernels use the whole opt-in carve-out)
-  __syncthreads();
+  // the last WARP of the grid to get here publishes the records (every warp
+  // counts once; its atomics above are ordered before the count by the fence)
   FinTrace(fin, 2);
+  __syncwarp();
   int is_last = 0;
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     __threadfence();
-    is_last = (atomicAdd(&fin.sync[1], 1u) == gridDim.x - 1) ? 1 : 0;
+    is_last = (atomicAdd(&fin.sync[1], 1u) == gridDim.x * (unsigned)nwarps - 1u) ? 1 : 0;
   }
-  if (!__syncthreads_or(is_last)) return;
-  FinTrace(fin, 3);
+  if (!__shfl_sync(kFullMask, is_last, 0)) return;
   __threadfence();
+  if (fin.trace && lane == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    fin.trace[(size_t)blockIdx.x * 5 + 3] = t;
+  }
   const unsigned int flags = __ldcg(&fin.sync[2]);
   const unsigned int need_cap = __ldcg(&fin.sync[3]);
-  for (int j = warp_in_cta; j < K; j += nwarps) {
-    unsigned long long tot = 0;
-    const unsigned long long le = __ldcg(&fin.last_end[j]);
-    for (uint32_t s2 = lane; s2 < fin.nseg; s2 += 32) tot += __ldcg(&fin.segcount[(uint64_t)j * fin.nseg + s2]);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(kFullMask, tot, d);
-    if (lane == 0) {
-      const Carry cin = carries.c[j];
-      PipelineStatus v{};
-      v.n_candidates = tot;
-      v.n_matches = tot;
-      v.carry_cur = tot ? le : cin.cur;
-      v.carry_tail = tot ? le : cin.tail;
-      v.overflow = (flags & kFinOverflow) ? 1u : 0u;
-      v.need_cap = need_cap;
-      v.need_large = (flags & kFinOverlap) ? 1u : 0u;
-      v.dense = (flags & kFinDense) ? 1u : 0u;
-      fin.status[j] = v;
-      volatile PipelineStatus* h = fin.host_status + j;
-      h->n_candidates = v.n_candidates;
-      h->n_hits = 0;
-      h->n_matches = v.n_matches;
-      h->carry_cur = v.carry_cur;
-      h->carry_tail = v.carry_tail;
-      h->overflow = v.overflow;
-      h->need_cap = v.need_cap;
-      h->need_large = v.need_large;
-      h->dense = v.dense;
-      h->full_result = 0;
-      __threadfence_system();
-      h->seq = fin.seq;                  // (the end of the kernel flushes it)
-    }
+  // totals: scratch[j] = sum of pattern j's segment counters (the warp's tile is free by now)
+  for (int j = lane; j < K; j += 32) scratch[j] = 0;
+  __syncwarp();
+  const uint32_t cells = (uint32_t)K * fin.nseg;
+  for (uint32_t i = lane; i < cells; i += 32) {
+    const uint32_t v = __ldcg(&fin.segcount[i]);
+    if (v) atomicAdd(&scratch[i / fin.nseg], v);
   }
-  __syncthreads();
-  FinTrace(fin, 4);
+  __syncwarp();
+  for (int j = lane; j < K; j += 32) {
+    const unsigned long long tot = scratch[j];
+    const unsigned long long le = __ldcg(&fin.last_end[j]);
+    uint4 h0, h1;
+    h0.x = (unsigned int)tot; h0.y = (unsigned int)(tot >> 32); h0.z = flags; h0.w = fin.seq;
+    h1.x = (unsigned int)le; h1.y = (unsigned int)(le >> 32); h1.z = need_cap; h1.w = fin.seq;
+    volatile uint4* dst = reinterpret_cast<volatile uint4*>(fin.host_records + j);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
+  }
+  if (fin.trace && lane == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    fin.trace[(size_t)blockIdx.x * 5 + 4] = t;
+  }
 }
 
 constexpr int kDfaChainHits = 3;
@@ -737,7 +742,7 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
       out.count[sub] = 0;
     }
   }
-  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, carries);
+  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, carries, reinterpret_cast<uint32_t*>(tile));
 }
 
 // ===========================================================================
@@ -977,7 +982,7 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
       if (over && lane == 0) *dense_flag = 1u;
     }
   }
-  if (fin.enabled) FinishFixed(out, nsub_pat, K, fin, carries);
+  if (fin.enabled) FinishFixed(out, nsub_pat, K, fin, carries, reinterpret_cast<uint32_t*>(tile));
 }
 
 // ---------------------------------------------------------------------------
@@ -1730,6 +1735,55 @@ __global__ void k_fill_u32(uint32_t* p, uint64_t count, uint32_t v) {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = tid; i < count; i += nthreads) p[i] = v;
+}
+
+// ===========================================================================
+// ReplaceAll on the device (reference: Regej::ReplaceAll
+// src/rejit.cc:221-226 and Replace :97-112): the matches are already in device
+// memory, so the rebuilt text is a prefix sum plus a gather.
+//   removed[i] = sum of the lengths of the matches before match i (CUB scan);
+// an input byte p outside every match lands at
+//   p - (removed bytes before p) + with_len * (matches beginning at or before p)
+// and the replacement of match i right before the byte that follows it.
+// One CTA per 4 KB input tile: two binary searches find the tile's matches,
+// their begins/ends/prefixes are staged in shared memory, every thread then
+// places its own 16 input bytes.
+// ===========================================================================
+__global__ void k_match_lengths(const uint64_t* __restrict__ pairs, uint64_t m, uint64_t* __restrict__ len) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < m; i += nthreads) len[i] = pairs[2 * i + 1] - pairs[2 * i];
+}
+
+__global__ void __launch_bounds__(256)
+k_replace_tiles(const uint8_t* __restrict__ text, uint64_t n, const uint64_t* __restrict__ pairs,
+                const uint64_t* __restrict__ removed, uint64_t m, const uint8_t* __restrict__ with, uint32_t w,
+                uint8_t* __restrict__ out, uint64_t n_tiles) {
+  __shared__ uint16_t s_b[kReplaceTile + 2];        // begin - tile_lo of the tile's own matches
+  __shared__ uint16_t s_e[kReplaceTile + 2];        // end - tile_lo, clipped to the tile
+  __shared__ uint16_t s_r[kReplaceTile + 2];        // removed[m0 + i] - removed[m0]
+  __shared__ ReplaceTileHead s_head;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t tile_lo = tile * kReplaceTile;
+    const bool last = tile + 1 == n_tiles;
+    const uint64_t tile_hi = last ? n : tile_lo + kReplaceTile;
+    if (threadIdx.x == 0) s_head.m0 = ReplaceLowerBound(pairs, m, tile_lo);
+    if (threadIdx.x == 32) s_head.m1 = last ? m : ReplaceLowerBound(pairs, m, tile_hi);
+    __syncthreads();
+    if (threadIdx.x == 0) ReplaceHead(pairs, removed, m, tile_lo, &s_head);
+    __syncthreads();
+    const ReplaceTileHead h = s_head;
+    const uint32_t cnt = (uint32_t)(h.m1 - h.m0);
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const uint64_t b = pairs[2 * (h.m0 + i)], e = pairs[2 * (h.m0 + i) + 1];
+      s_b[i] = (uint16_t)(b - tile_lo);
+      s_e[i] = (uint16_t)((e < tile_hi ? e : tile_hi) - tile_lo);
+      s_r[i] = (uint16_t)(removed[h.m0 + i] - h.r0);
+    }
+    __syncthreads();
+    ReplacePlace(threadIdx.x, text, tile_lo, tile_hi, last, h, cnt, s_b, s_e, s_r, with, w, out);
+    __syncthreads();
+  }
 }
 
 }  // namespace rejit_b200

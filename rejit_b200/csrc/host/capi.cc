@@ -457,6 +457,60 @@ int64_t rejit_b200_match_all_device_slab(rejit_b200_program* program, int device
   return r;
 }
 
+int64_t rejit_b200_replace_all(rejit_b200_program* program, const char* text, size_t text_length, const char* with,
+                               size_t with_length, char** out, size_t* out_length, rejit_b200_stats* stats,
+                               char* err, size_t err_length) {
+  std::string error;
+  if (!program || !out || !out_length) { SetErr(err, err_length, "rejit_b200: null argument"); return -1; }
+  if (!CudaOk(&error)) { SetErr(err, err_length, error); return -1; }
+  RunStats rs;
+  uint8_t* rebuilt = nullptr;
+  uint64_t len = 0;
+  int64_t r = ReplaceAllHost(0, program->prog, reinterpret_cast<const uint8_t*>(text), text_length,
+                             reinterpret_cast<const uint8_t*>(with), with_length, &rebuilt, &len, stats ? &rs : nullptr,
+                             &error);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  FillStats(rs, stats);
+  *out = reinterpret_cast<char*>(rebuilt);
+  *out_length = len;
+  return r;
+}
+
+rejit_b200_text* rejit_b200_replace_all_text(rejit_b200_program* program, const rejit_b200_text* text, const char* with,
+                                             size_t with_length, int64_t* n_matches, rejit_b200_stats* stats,
+                                             char* err, size_t err_length) {
+  std::string error;
+  if (!program || !text) { SetErr(err, err_length, "rejit_b200: null argument"); return nullptr; }
+  RunStats rs;
+  void* d_out = nullptr;
+  uint64_t len = 0, cap = 0;
+  int64_t r = ReplaceAllDevice(text->device, program->prog, static_cast<const uint8_t*>(text->d_ptr), text->length,
+                               reinterpret_cast<const uint8_t*>(with), with_length, &d_out, &len, &cap,
+                               stats ? &rs : nullptr, &error);
+  if (r < 0) { SetErr(err, err_length, error); return nullptr; }
+  FillStats(rs, stats);
+  if (n_matches) *n_matches = r;
+  rejit_b200_text* t = new rejit_b200_text;
+  t->device = text->device;
+  t->d_ptr = d_out;
+  t->length = len;
+  t->capacity = cap;
+  return t;
+}
+
+size_t rejit_b200_text_length(const rejit_b200_text* text) { return text ? text->length : 0; }
+
+int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capacity, char* err, size_t err_length) {
+  std::string error;
+  if (!text || (!dst && text->length)) { SetErr(err, err_length, "rejit_b200: null argument"); return -1; }
+  if (capacity < text->length) { SetErr(err, err_length, "rejit_b200: destination too small"); return -1; }
+  if (text->length && !CopyFromDevice(text->device, dst, text->d_ptr, text->length, &error)) {
+    SetErr(err, err_length, error);
+    return -1;
+  }
+  return 0;
+}
+
 void rejit_b200_free(void* ptr) { free(ptr); }
 
 }  // extern "C"

@@ -187,10 +187,17 @@ bool Regej::ReplaceFirst(string& text, const string& with) {
 }
 
 size_t Regej::ReplaceAll(string& text, const string& with) {
-  vector<Match> found;
-  MatchAll(text, &found);
-  Replace(&found, text, with);
-  return found.size();
+  // the rebuild (src/rejit.cc:97-112) runs on the device too
+  if (!Compile(kMatchAll)) return 0;
+  char err[256];
+  char* rebuilt = nullptr;
+  size_t len = 0;
+  int64_t n = rejit_b200_replace_all(rinfo_->program, text.data(), text.size(), with.data(), with.size(), &rebuilt, &len,
+                                     nullptr, err, sizeof err);
+  if (n < 0) Fatal("ReplaceAll", err);
+  text.assign(rebuilt, len);
+  rejit_b200_free(rebuilt);
+  return static_cast<size_t>(n);
 }
 
 // ---- free helpers ------------------------------------------------------------

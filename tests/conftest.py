@@ -67,7 +67,22 @@ def hostsim():
                                           ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64]
     L.hostsim_match_full.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64]
 
+    L.hostsim_replace_all.restype = ctypes.c_int64
+    L.hostsim_replace_all.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64,
+                                      ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64,
+                                      ctypes.POINTER(ctypes.c_uint64)]
+
     class Sim:
+        def replace_all(self, pat, text, with_):
+            pb = pat.encode("latin-1") if isinstance(pat, str) else pat
+            cap = len(text) + (len(text) + 2) * len(with_) + 64
+            out = ctypes.create_string_buffer(cap)
+            n_out = ctypes.c_uint64()
+            r = L.hostsim_replace_all(pb, len(pb), text, len(text), with_, len(with_), out, cap, ctypes.byref(n_out))
+            if r < 0:
+                return int(r), b""
+            return int(r), out.raw[:n_out.value]
+
         def match_all(self, pat, text, strategy=-1, parser_opt=1):
             pb = pat.encode("latin-1") if isinstance(pat, str) else pat
             cap = len(text) + 2

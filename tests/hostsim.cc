@@ -365,6 +365,51 @@ int64_t hostsim_set_match_all(const char* joined, size_t len, char sep, const ui
   return (int64_t)res.size();
 }
 
+// ReplaceAll: the kernel's placement functions (device_program.h) driven tile by
+// tile, thread by thread, over the matches of the sequential resolve.
+int64_t hostsim_replace_all(const char* pattern, size_t plen, const uint8_t* text, uint64_t n, const uint8_t* with,
+                            uint32_t w, uint8_t* out, uint64_t cap, uint64_t* out_len) {
+  Compiled c;
+  std::string error;
+  if (!CompilePattern(pattern, plen, 1, &c, &error)) return -1;
+  Cands cands, res;
+  ScanGeneric(c, text, n, &cands);
+  if (c.ca.reentrant) ResolveFaithful(c, text, n, cands, &res);
+  else ResolveSequential(cands, ChainState{0, kNoMatch}, &res, nullptr);
+  const uint64_t m = res.size();
+  std::vector<uint64_t> pairs(2 * m + 2), removed(m + 1, 0);
+  for (uint64_t i = 0; i < m; ++i) { pairs[2 * i] = res[i].first; pairs[2 * i + 1] = res[i].second; }
+  for (uint64_t i = 0; i < m; ++i) removed[i + 1] = removed[i] + (res[i].second - res[i].first);
+  const uint64_t len = n - removed[m] + m * w;
+  *out_len = len;
+  if (len > cap) return -2;
+  std::vector<uint8_t> canary(len + 64, 0xEE);
+  const uint64_t n_tiles = n / kReplaceTile + 1;
+  std::vector<uint16_t> s_b(kReplaceTile + 2), s_e(kReplaceTile + 2), s_r(kReplaceTile + 2);
+  for (uint64_t tile = 0; tile < n_tiles; ++tile) {
+    const uint64_t tile_lo = tile * kReplaceTile;
+    const bool last = tile + 1 == n_tiles;
+    const uint64_t tile_hi = last ? n : tile_lo + kReplaceTile;
+    ReplaceTileHead h;
+    h.m0 = ReplaceLowerBound(pairs.data(), m, tile_lo);
+    h.m1 = last ? m : ReplaceLowerBound(pairs.data(), m, tile_hi);
+    ReplaceHead(pairs.data(), removed.data(), m, tile_lo, &h);
+    const uint32_t cnt = (uint32_t)(h.m1 - h.m0);
+    if (cnt > kReplaceTile + 1) return -7;
+    for (uint32_t i = 0; i < cnt; ++i) {
+      const uint64_t b = pairs[2 * (h.m0 + i)], e = pairs[2 * (h.m0 + i) + 1];
+      s_b[i] = (uint16_t)(b - tile_lo);
+      s_e[i] = (uint16_t)((e < tile_hi ? e : tile_hi) - tile_lo);
+      s_r[i] = (uint16_t)(removed[h.m0 + i] - h.r0);
+    }
+    for (uint32_t t = 0; t < 256; ++t)
+      ReplacePlace(t, text, tile_lo, tile_hi, last, h, cnt, s_b.data(), s_e.data(), s_r.data(), with, w, canary.data());
+  }
+  for (uint64_t i = len; i < len + 64; ++i) if (canary[i] != 0xEE) return -8;     // wrote past the end
+  memcpy(out, canary.data(), len);
+  return (int64_t)m;
+}
+
 int hostsim_match_full(const char* pattern, size_t plen, const uint8_t* text, uint64_t n) {
   Compiled c;
   std::string error;

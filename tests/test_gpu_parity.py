@@ -288,6 +288,54 @@ def test_fixed_length_finish_in_kernel_and_overlap_fallback(rj):
             dt.free()
 
 
+def _replace_expected(pat, text, w):
+    out, at = bytearray(), 0
+    ms = O.Oracle(pat).match_all(text)
+    for b, e in ms:
+        out += text[at:b] + w
+        at = e
+    out += text[at:]
+    return bytes(out), len(ms)
+
+
+def test_replace_all_on_device(rj):
+    """SURVEY §8f rank 2: Regej::ReplaceAll with the rebuild on the device
+    (k_match_lengths + scan + k_replace_tiles) == the reference's Replace
+    (src/rejit.cc:97-112) applied to the oracle's matches."""
+    rng = random.Random(21)
+    cases = [("a", b"", b"X"), ("x*", b"aaxa", b"-"), ("$", b"ab\ncd", b"<EOL>"), ("^", b"a\nb\n", b"> "),
+             ("abc", b"abc" * 3000, b""), ("abc", b"abc" * 3000, b"abcabc"), (".*", b"x" * 9000, b"y"),
+             ("x{2,}", b"ab" + b"x" * 12000 + b"cd", b"_")]
+    for n in (1, 16, 17, 4095, 4096, 4097, 12289, 70001):
+        t = fuzzgen.rand_text(rng, "abx\n", n)
+        for pat in ("a", "ab|ba", "x*", "a.*", "(^|$|[x])", "b+", "\n"):
+            cases.append((pat, t, rng.choice([b"", b"Q", b"(c|g|t)"])))
+    for pat, t, w in cases:
+        assert rj.Regej(pat).replace_all(t, w) == _replace_expected(pat, t, w), (pat, len(t), w)
+    # regex-dna's front: strip headers and newlines, then chained IUB substitutions
+    # on the device-resident result (sample/regexdna.cc:49, 69-85)
+    from rejit_b200 import workloads as W
+    fa = W.fasta_file(30000)                         # ~300 KB FASTA file
+    exp, n_strip = _replace_expected(W.STRIP_PATTERN, fa, b"")
+    cur = rj.Text(fa)
+    try:
+        nxt, n = rj.Regej(W.STRIP_PATTERN).replace_all_text(cur, b"")
+        cur.free()
+        cur = nxt
+        assert n == n_strip and len(cur) == len(exp) and cur.download() == exp
+        for code, alt in W.IUB_SUBSTITUTIONS[:4]:
+            exp, n_e = _replace_expected(code, exp, alt.encode())
+            nxt, n = rj.Regej(code).replace_all_text(cur, alt.encode())
+            cur.free()
+            cur = nxt
+            assert n == n_e and cur.download() == exp, code
+        # the rebuilt text is an ordinary device text: it can be searched
+        p = W.DNA_PATTERNS[3]
+        assert rj.Regej(p).match_all_text(cur) == O.Oracle(p).match_all(exp)
+    finally:
+        cur.free()
+
+
 def test_multi_gpu_equals_single(rj):
     if rj.device_count() < 2:
         pytest.skip("needs 2 GPUs")

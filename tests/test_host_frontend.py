@@ -211,3 +211,37 @@ def test_workload_shaped_parity_on_cpu(hostsim):
     fa = W.fasta_file(2000)
     got, desc = hostsim.match_all(W.STRIP_PATTERN, fa)
     assert got == O.Oracle(W.STRIP_PATTERN).match_all(fa)
+
+
+def test_replace_all_placement(hostsim):
+    """ReplaceAll: the kernel's placement arithmetic
+    (device_program.h: ReplaceHead / ReplacePlace) driven on the CPU, against the
+    reference's Replace semantics (src/rejit.cc:97-112) applied to the oracle's
+    matches: texts around the 4096-byte tile size, matches straddling tiles,
+    empty matches (also at the end of the text), empty and long replacements."""
+    import random
+    import rejit_oracle as O
+    import fuzzgen
+    rng = random.Random(5)
+
+    def expected(pat, text, w):
+        out, at = bytearray(), 0
+        ms = O.Oracle(pat).match_all(text)
+        for b, e in ms:
+            out += text[at:b] + w
+            at = e
+        out += text[at:]
+        return len(ms), bytes(out)
+
+    cases = [("a", b"", b"X"), ("x*", b"aaxa", b"-"), ("$", b"ab\ncd", b"<EOL>"), ("^", b"a\nb\n", b"> "),
+             ("abc", b"abc" * 3000, b""), ("abc", b"abc" * 3000, b"abcabc"), (".*", b"x" * 9000, b"y"),
+             ("x{2,}", b"ab" + b"x" * 12000 + b"cd", b"_")]
+    for n in (1, 15, 16, 17, 4095, 4096, 4097, 8192, 12289):
+        t = fuzzgen.rand_text(rng, "abx\n", n)
+        for pat in ("a", "ab|ba", "x*", "a.*", "(^|$|[x])", "b+", "\n"):
+            for w in (b"", b"Q", b"(c|g|t)"):
+                cases.append((pat, t, w))
+    for pat, t, w in cases:
+        exp = expected(pat, t, w)
+        got = hostsim.replace_all(pat, t, w)
+        assert got == exp, (pat, len(t), w, got[0], exp[0])
