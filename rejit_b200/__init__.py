@@ -471,6 +471,17 @@ class RegejSet:
             raise RejitError(err.value.decode("latin-1"))
         return list(counts)
 
+    def match_all_text(self, text: "Text", stats: Optional[Stats] = None) -> List[int]:
+        """Counts per member over an uploaded Text (no match lists copied back)."""
+        k = len(self.members)
+        counts = (ctypes.c_int64 * k)()
+        err = ctypes.create_string_buffer(512)
+        r = lib().rejit_b200_match_all_set_text(self._set, text._h, counts, None,
+                                                ctypes.byref(stats) if stats is not None else None, err, len(err))
+        if r < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        return list(counts)
+
     def match_all(self, data) -> List[List[Tuple[int, int]]]:
         """Uploads `data` once and returns one match list per member."""
         L = lib()

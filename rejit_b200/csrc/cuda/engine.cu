@@ -69,7 +69,7 @@ struct Buffer {
 }  // namespace
 
 // finish area inside DeviceContext::status
-constexpr size_t kFinSyncOffset = 128, kFinLastOffset = 160, kFinSegOffset = 168;
+constexpr size_t kFinSyncOffset = 128, kFinLastOffset = 160, kFinTotalOffset = 168, kFinSegOffset = 176;
 
 class DeviceContext {
  public:
@@ -128,7 +128,7 @@ class DeviceContext {
     RJ_TRY(cudaHostGetDevicePointer(&h_set_status_dev, h_set_status, 0));
     // status and the counters share one allocation so that one memset clears both
     // layout: [PipelineStatus][counters 40 B, at +64][finish: sync 8 x u32 at +128, last_end at +160,
-    //          segcount at +168 (one u32 per scan CTA)]
+    //          total at +168, segcount at +176 (one u32 per scan CTA)]
     if (!status.Reserve(kFinSegOffset + 4 * (size_t)sm_count + 64, error)) return false;
     counters.p = static_cast<uint8_t*>(status.p) + ((sizeof(PipelineStatus) + 15) & ~size_t(15));
     counters.bytes = 0;                 // not owned
@@ -564,6 +564,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
             fin.nseg = (uint32_t)((cand.nsub + fin.seg_subs - 1) / fin.seg_subs);
             fin.sync = reinterpret_cast<unsigned int*>(base + kFinSyncOffset);
             fin.last_end = reinterpret_cast<unsigned long long*>(base + kFinLastOffset);
+            fin.totals = reinterpret_cast<unsigned long long*>(base + kFinTotalOffset);
             fin.segcount = reinterpret_cast<uint32_t*>(base + kFinSegOffset);
             fin.out_pairs = outp;
             fin.out_stride = 0;
@@ -798,6 +799,37 @@ int64_t MatchAllHost(int device, Program* prog, const uint8_t* text, uint64_t n,
   return (int64_t)cnt;
 }
 
+// MatchFirst / MatchAnywhere with early exit (the reference
+// returns at the first registered match, x64/codegen-x64.cc:427-431, 481-486):
+// the text is searched in growing slabs — only the slab (plus halo) is copied to
+// the device and scanned — and the search stops at the first slab that holds a
+// match.  With no match before a slab, the first match found in it is
+// MatchAll()[0] (the first candidate of a chain is always selected).
+int MatchFirstHost(int device, Program* prog, const uint8_t* text, uint64_t n, uint64_t pair[2], std::string* error) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return -1;
+  DeviceProgram* dp = prog->OnDevice(device, error);
+  if (!dp) return -1;
+  const CompiledAutomaton& ca = prog->automaton();
+  uint64_t step = 1ull << 18;
+  if (ca.reentrant || ca.nfa.max_len == kInfLen) step = n + 1;      // one pass (the halo would be the whole text)
+  uint64_t lo = 0;
+  for (;;) {
+    const uint64_t hi = (n - lo <= step) ? n : lo + step;
+    const bool last = hi == n;
+    Carry in{lo, kNoMatch}, out;
+    std::vector<uint64_t> found;
+    if (!MatchSlabFromHost(c, prog, dp, text, n, lo, hi, last, in, &out, &found, nullptr, error)) return -1;
+    if (!found.empty()) {
+      if (pair) { pair[0] = found[0]; pair[1] = found[1]; }
+      return 1;
+    }
+    if (last) return 0;
+    lo = hi;
+    step *= 8;
+  }
+}
+
 int64_t MatchAllResident(int device, Program* prog, const uint8_t* d_text, uint64_t n, uint64_t** pairs,
                          RunStats* stats, std::string* error) {
   DeviceContext* c = ContextFor(device, error);
@@ -947,11 +979,11 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
       PipelineStatus* d_status = c->set_status.as<PipelineStatus>();
       int blocks = (int)std::min<uint64_t>((nsub + warps - 1) / warps, (uint64_t)c->sm_count);
       // set_counts: [0..K) dense counts, [40] work counter, then the finish area
-      // (sync 8 x u32 at +512, last_end[32] at +544, segcount[K][nseg] at +800)
+      // (sync 8 x u32 at +512, last_end[32] at +544, totals[32] at +800, segcount[K][nseg] at +1056)
       const bool fuse_finish = c->coop;
       const uint32_t seg_subs = (uint32_t)((nsub + blocks - 1) / blocks);
       const uint32_t nseg = (uint32_t)((nsub + seg_subs - 1) / seg_subs);
-      const size_t counts_bytes = 800 + (fuse_finish ? (size_t)K * nseg * 4 : 0);
+      const size_t counts_bytes = 1056 + (fuse_finish ? (size_t)K * nseg * 4 : 0);
       if (!c->set_counts.Reserve(counts_bytes, error)) return -1;
       unsigned long long* d_counts = c->set_counts.as<unsigned long long>();
       if (!Check(cudaMemsetAsync(d_counts, 0, counts_bytes, s), "memset", error)) return -1;
@@ -1005,7 +1037,8 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         fin.nseg = nseg;
         fin.sync = reinterpret_cast<unsigned int*>(base + 512);
         fin.last_end = reinterpret_cast<unsigned long long*>(base + 544);
-        fin.segcount = reinterpret_cast<uint32_t*>(base + 800);
+        fin.totals = reinterpret_cast<unsigned long long*>(base + 800);
+        fin.segcount = reinterpret_cast<uint32_t*>(base + 1056);
         fin.out_pairs = c->set_out.as<uint64_t>();
         fin.out_stride = per_cap;
         fin.out_cap = per_cap;

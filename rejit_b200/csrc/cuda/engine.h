@@ -129,6 +129,9 @@ int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint6
 int64_t ReplaceAllHost(int device, Program* prog, const uint8_t* text, uint64_t n, const uint8_t* with,
                        uint64_t with_len, uint8_t** out, uint64_t* out_len, RunStats* stats, std::string* error);
 
+// MatchFirst (pair != nullptr) / MatchAnywhere with early exit: 1 / 0, or -1 on error.
+int MatchFirstHost(int device, Program* prog, const uint8_t* text, uint64_t n, uint64_t pair[2], std::string* error);
+
 // MatchFull: 1 / 0, or -1 on error.
 int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error);
 

@@ -103,6 +103,7 @@ struct FinishArgs {
   uint32_t* segcount;                  // [K][nseg] candidates per (pattern, segment); zeroed by the host
   unsigned int* sync;                  // [0] arrive, [1] done, [2] flags, [3] need_cap; zeroed by the host
   unsigned long long* last_end;        // [K] end of the last candidate; zeroed by the host
+  unsigned long long* totals;          // [K] candidates per pattern (written by the warp of the last segment)
   uint64_t* out_pairs;                 // pattern j's pairs start at out_pairs + j * 2 * out_stride
   uint64_t out_stride, out_cap;
   uint64_t base_offset;
@@ -425,7 +426,7 @@ __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_
 }
 
 __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
-                                            const CarrySet& carries, uint32_t* scratch /* >= 32 words of this warp's shared memory */) {
+                                            const CarrySet& carries) {
   FinTrace(fin, 0);
   GridBarrier(&fin.sync[0], gridDim.x);
   FinTrace(fin, 1);
@@ -455,6 +456,7 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
           pre += __shfl_xor_sync(kFullMask, pre, d);
           mine += __shfl_xor_sync(kFullMask, mine, d);
         }
+        if (seg + 1 == fin.nseg && lane == 0) fin.totals[j] = pre + mine;
         if (mine == 0 || (flags0 & (kFinDense | kFinOverflow))) continue;
         const Carry cin = carries.c[j];
         uint64_t* outp = fin.out_pairs + (uint64_t)j * 2 * fin.out_stride;
@@ -520,17 +522,8 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
   }
   const unsigned int flags = __ldcg(&fin.sync[2]);
   const unsigned int need_cap = __ldcg(&fin.sync[3]);
-  // totals: scratch[j] = sum of pattern j's segment counters (the warp's tile is free by now)
-  for (int j = lane; j < K; j += 32) scratch[j] = 0;
-  __syncwarp();
-  const uint32_t cells = (uint32_t)K * fin.nseg;
-  for (uint32_t i = lane; i < cells; i += 32) {
-    const uint32_t v = __ldcg(&fin.segcount[i]);
-    if (v) atomicAdd(&scratch[i / fin.nseg], v);
-  }
-  __syncwarp();
   for (int j = lane; j < K; j += 32) {
-    const unsigned long long tot = scratch[j];
+    const unsigned long long tot = __ldcg(&fin.totals[j]);
     const unsigned long long le = __ldcg(&fin.last_end[j]);
     uint4 h0, h1;
     h0.x = (unsigned int)tot; h0.y = (unsigned int)(tot >> 32); h0.z = flags; h0.w = fin.seq;
@@ -742,7 +735,7 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
       out.count[sub] = 0;
     }
   }
-  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, carries, reinterpret_cast<uint32_t*>(tile));
+  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, carries);
 }
 
 // ===========================================================================
@@ -982,7 +975,7 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
       if (over && lane == 0) *dense_flag = 1u;
     }
   }
-  if (fin.enabled) FinishFixed(out, nsub_pat, K, fin, carries, reinterpret_cast<uint32_t*>(tile));
+  if (fin.enabled) FinishFixed(out, nsub_pat, K, fin, carries);
 }
 
 // ---------------------------------------------------------------------------

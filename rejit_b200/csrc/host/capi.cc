@@ -235,13 +235,14 @@ int64_t rejit_b200_match_all(rejit_b200_program* program, const char* text, size
 
 int rejit_b200_match_first(rejit_b200_program* program, const char* text, size_t text_length,
                            uint64_t out_pair[2], char* err, size_t err_length) {
-  // MatchFirst := first element of MatchAll
-  uint64_t* pairs = nullptr;
-  int64_t r = rejit_b200_match_all_alloc(program, text, text_length, &pairs, nullptr, err, err_length);
-  if (r < 0) return -1;
-  if (r > 0 && out_pair) { out_pair[0] = pairs[0]; out_pair[1] = pairs[1]; }
-  free(pairs);
-  return r > 0 ? 1 : 0;
+  // MatchFirst := first element of MatchAll, found slab by slab with early exit
+  std::string error;
+  if (!CudaOk(&error)) { SetErr(err, err_length, error); return -1; }
+  uint64_t pair[2] = {0, 0};
+  int r = MatchFirstHost(0, program->prog, reinterpret_cast<const uint8_t*>(text), text_length, pair, &error);
+  if (r < 0) { SetErr(err, err_length, error); return -1; }
+  if (r > 0 && out_pair) { out_pair[0] = pair[0]; out_pair[1] = pair[1]; }
+  return r;
 }
 
 int rejit_b200_match_full(rejit_b200_program* program, const char* text, size_t text_length,
@@ -254,11 +255,11 @@ int rejit_b200_match_full(rejit_b200_program* program, const char* text, size_t 
 
 int rejit_b200_match_anywhere(rejit_b200_program* program, const char* text, size_t text_length,
                               char* err, size_t err_length) {
-  uint64_t* pairs = nullptr;
-  int64_t r = rejit_b200_match_all_alloc(program, text, text_length, &pairs, nullptr, err, err_length);
-  if (r < 0) return -1;
-  free(pairs);
-  return r > 0 ? 1 : 0;
+  std::string error;
+  if (!CudaOk(&error)) { SetErr(err, err_length, error); return -1; }
+  int r = MatchFirstHost(0, program->prog, reinterpret_cast<const uint8_t*>(text), text_length, nullptr, &error);
+  if (r < 0) SetErr(err, err_length, error);
+  return r;
 }
 
 int64_t rejit_b200_match_all_multi_gpu(rejit_b200_program* program, const char* text, size_t text_length,

@@ -66,5 +66,40 @@ def main():
     run("C5 strip '>.*\\n|\\n' over 20 MB FASTA file", W.STRIP_PATTERN, fa)
 
 
+def regexdna_chain(n_lines=2_000_000):
+    """C5 shape (sample/regexdna.cc:49-91) with everything on the device: upload the
+    FASTA file once, strip headers/newlines, count the nine variants in one fused
+    scan, apply the eleven IUB substitutions; only counts and lengths come back."""
+    fa = W.fasta_file(n_lines)
+    strip = rj.Regej(W.STRIP_PATTERN)
+    iub = [(rj.Regej(c), a.encode()) for c, a in W.IUB_SUBSTITUTIONS]
+    rs = rj.RegejSet(W.DNA_PATTERNS)
+    best = None
+    for rep in range(3):
+        t0 = time.perf_counter()
+        cur = rj.Text(fa)
+        t1 = time.perf_counter()
+        nxt, n_strip = strip.replace_all_text(cur, b"")
+        cur.free(); cur = nxt
+        stripped = len(cur)
+        t2 = time.perf_counter()
+        counts = rs.match_all_text(cur)
+        t3 = time.perf_counter()
+        for r, a in iub:
+            nxt, _ = r.replace_all_text(cur, a)
+            cur.free(); cur = nxt
+        final = len(cur)
+        t4 = time.perf_counter()
+        cur.free()
+        line = {"case": "C5 regex-dna chain on device", "bytes": len(fa), "stripped": stripped, "final": final,
+                "counts": counts, "upload_ms": round((t1 - t0) * 1e3, 3), "strip_ms": round((t2 - t1) * 1e3, 3),
+                "count9_ms": round((t3 - t2) * 1e3, 3), "iub11_ms": round((t4 - t3) * 1e3, 3),
+                "total_ms": round((t4 - t0) * 1e3, 3), "gbs_of_input": round(len(fa) / (t4 - t0) / 1e9, 2)}
+        if best is None or line["total_ms"] < best["total_ms"]:
+            best = line
+    print(json.dumps(best), flush=True)
+
+
 if __name__ == "__main__":
     main()
+    regexdna_chain()

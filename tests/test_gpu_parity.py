@@ -288,6 +288,25 @@ def test_fixed_length_finish_in_kernel_and_overlap_fallback(rj):
             dt.free()
 
 
+def test_match_first_early_exit(rj):
+    """MatchFirst / MatchAnywhere search growing slabs and stop
+    at the first one that holds a match; the answer is MatchAll()[0]."""
+    rng = random.Random(31)
+    n = 3_000_000
+    base = bytearray(fuzzgen.rand_text(rng, "0123456789\n", n))
+    for pat, hit in (("abcdefgh", b"abcdefgh"), ("ab[cd]e|xyz", b"abde"), ("^qq$", b"\nqq\n"), ("r+s", b"rrrrs")):
+        o = O.Oracle(pat)
+        for where in (5, 262140, 262144, 300000, 2_359_290, n - len(hit)):
+            t = bytearray(base)
+            t[where:where + len(hit)] = hit
+            t[n - 20:n - 20 + len(hit)] = hit            # a later one that must not win
+            t = bytes(t)
+            r = rj.Regej(pat)
+            assert r.match_first(t) == o.match_first(t), (pat, where)
+            assert r.match_anywhere(t) is True
+        assert rj.Regej(pat).match_first(bytes(base)) is None and rj.Regej(pat).match_anywhere(bytes(base)) is False
+
+
 def _replace_expected(pat, text, w):
     out, at = bytearray(), 0
     ms = O.Oracle(pat).match_all(text)
