@@ -106,6 +106,7 @@ class DeviceContext {
   unsigned int call_seq = 0;
   bool attr_done = false;
   bool coop = false;                  // cooperative launch available: scans finish in-kernel
+  int lit_blocks_per_sm = 0;          // co-resident CTAs of k_lit_scan (occupancy query, cached)
 
   bool Init(int dev, std::string* error) {
     device = dev;
@@ -507,6 +508,26 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     bool ordered = true;
     bool fused = false;                 // the scan kernel also produced the matches and the status
     unsigned int fused_seq = 0;
+    // arguments of the in-kernel finish (FinishFixed) for a scan grid of `blocks` CTAs
+    auto make_fin = [&](int blocks, uint64_t nsub) {
+      FinishArgs fin{};
+      uint8_t* base = static_cast<uint8_t*>(c->status.p);
+      fin.enabled = 1;
+      const int segs = std::min(blocks, c->sm_count);            // the counter array holds sm_count segments
+      fin.seg_subs = (uint32_t)((nsub + segs - 1) / segs);
+      fin.nseg = (uint32_t)((nsub + fin.seg_subs - 1) / fin.seg_subs);
+      fin.sync = reinterpret_cast<unsigned int*>(base + kFinSyncOffset);
+      fin.last_end = reinterpret_cast<unsigned long long*>(base + kFinLastOffset);
+      fin.totals = reinterpret_cast<unsigned long long*>(base + kFinTotalOffset);
+      fin.segcount = reinterpret_cast<uint32_t*>(base + kFinSegOffset);
+      fin.out_pairs = outp;
+      fin.out_stride = 0;
+      fin.out_cap = ocap;
+      fin.base_offset = slab.base_offset;
+      fin.host_records = c->h_fin_dev;
+      fin.seq = fused_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+      return fin;
+    };
     switch (ca.strategy) {
       case ScanStrategy::Literal: {
         cand.nsub = (n + kLitSubBytes - 1) / kLitSubBytes;
@@ -514,10 +535,33 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         if (!ReserveStore(&c->sub_b, &c->sub_e, &c->sub_count, {cand.nsub, cand.cap}, error)) return false;
         cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
         int blocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)grid_full);
-        if (dp->needle_len >= 4)
-          k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, slab.own, cand);
-        else
-          k_lit_scan<false><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, slab.own, cand);
+        const bool full4 = dp->needle_len >= 4;
+        FinishArgs fin{};
+        if (c->coop && !fa.enabled && dp->needle_len + 64 < kLitSubBytes) {
+          // finish in-kernel: the grid must be co-resident for the barrier
+          if (c->lit_blocks_per_sm == 0) {
+            int nb = 0;
+            RJ_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lit_scan<true>, 256, 0));
+            int nb2 = 0;
+            RJ_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_lit_scan<false>, 256, 0));
+            c->lit_blocks_per_sm = std::max(1, std::min(nb, nb2));
+          }
+          blocks = std::min(blocks, c->lit_blocks_per_sm * c->sm_count);
+          fin = make_fin(blocks, cand.nsub);
+          fused = true;
+          const uint8_t* needle = dp->needle;
+          uint32_t nl = dp->needle_len, p4 = dp->p4, pmask = dp->pmask;
+          ScanRange own = slab.own;
+          Carry c0 = carry_in;
+          void* args[] = {(void*)&d_text, (void*)&n, (void*)&needle, (void*)&nl, (void*)&p4, (void*)&pmask,
+                          (void*)&own, (void*)&cand, (void*)&fin, (void*)&c0};
+          const void* fn = full4 ? (const void*)k_lit_scan<true> : (const void*)k_lit_scan<false>;
+          RJ_TRY(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, s));
+        } else if (full4) {
+          k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, slab.own, cand, fin, carry_in);
+        } else {
+          k_lit_scan<false><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, slab.own, cand, fin, carry_in);
+        }
         if (stats) stats->launches += 1;
         break;
       }
@@ -532,7 +576,8 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         // the needle may sit up to window_hi bytes after an owned start
         ScanRange hit_range{slab.own.own_begin, slab.own.own_end + ca.window_hi + 1};
         int blocks = (int)std::min<uint64_t>((hs.nsub + 7) / 8, (uint64_t)grid_full);
-        k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, hit_range, hs);
+        k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, hit_range, hs,
+                                                FinishArgs{}, Carry());
         if (stats) cudaEventRecord(c->ev[1], s);
         k_gather_hits<<<1, 512, 0, s>>>(hs, hits, d_status);
         cand.cap = kWinSubHits * wsize;
@@ -558,20 +603,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
           unsigned long long* work = ctr + 0;
           if (c->coop && !fa.enabled) {
             // the scan grid finishes the job itself (see FinishFixed)
-            uint8_t* base = static_cast<uint8_t*>(c->status.p);
-            fin.enabled = 1;
-            fin.seg_subs = (uint32_t)((cand.nsub + blocks - 1) / blocks);
-            fin.nseg = (uint32_t)((cand.nsub + fin.seg_subs - 1) / fin.seg_subs);
-            fin.sync = reinterpret_cast<unsigned int*>(base + kFinSyncOffset);
-            fin.last_end = reinterpret_cast<unsigned long long*>(base + kFinLastOffset);
-            fin.totals = reinterpret_cast<unsigned long long*>(base + kFinTotalOffset);
-            fin.segcount = reinterpret_cast<uint32_t*>(base + kFinSegOffset);
-            fin.out_pairs = outp;
-            fin.out_stride = 0;
-            fin.out_cap = ocap;
-            fin.base_offset = slab.base_offset;
-            fin.host_records = c->h_fin_dev;
-            fin.seq = fused_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+            fin = make_fin(blocks, cand.nsub);
             dense_flag = fin.sync + 4;
             ScanRange own = slab.own;
             void* args[] = {(void*)&d_text, (void*)&n, (void*)&dp->dfa, (void*)&own, (void*)&cand, (void*)&dense_flag,

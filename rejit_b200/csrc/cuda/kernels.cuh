@@ -304,10 +304,16 @@ __device__ __forceinline__ bool LitAny(const uint4& v, uint32_t nx, uint32_t p4,
   return any;
 }
 
+// (defined below, next to the DFA scans)
+__device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_t sub, uint32_t total, bool over,
+                                           uint32_t cap);
+__device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
+                                            const Carry* carries);
+
 template <bool kFull4>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restrict__ needle,
-           uint32_t m, uint32_t p4, uint32_t pmask, ScanRange range, SubStore out) {
+           uint32_t m, uint32_t p4, uint32_t pmask, ScanRange range, SubStore out, FinishArgs fin, Carry carry0) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -359,8 +365,13 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
         if (__any_sync(kFullMask, any)) LitEmit(text, n, needle, m, p4, pmask, range, out, sub, k, my, v, nx);
       }
     }
-    if (lane == 0) out.count[sub] = k;
+    if (lane == 0) {
+      out.count[sub] = k;
+      FinishNote(fin, 0, sub, k, false, out.cap);
+    }
   }
+  // whole-literal patterns finish in-kernel like the DFA scans (cooperative launch)
+  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, &carry0);
 }
 
 // ===========================================================================
@@ -426,7 +437,7 @@ __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_
 }
 
 __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
-                                            const CarrySet& carries) {
+                                            const Carry* carries) {
   FinTrace(fin, 0);
   GridBarrier(&fin.sync[0], gridDim.x);
   FinTrace(fin, 1);
@@ -458,7 +469,7 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
         }
         if (seg + 1 == fin.nseg && lane == 0) fin.totals[j] = pre + mine;
         if (mine == 0 || (flags0 & (kFinDense | kFinOverflow))) continue;
-        const Carry cin = carries.c[j];
+        const Carry cin = carries[j];
         uint64_t* outp = fin.out_pairs + (uint64_t)j * 2 * fin.out_stride;
         unsigned long long run = pre;
         uint64_t last_e = 0;
@@ -735,7 +746,7 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
       out.count[sub] = 0;
     }
   }
-  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, carries);
+  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, carries.c);
 }
 
 // ===========================================================================
@@ -975,7 +986,7 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
       if (over && lane == 0) *dense_flag = 1u;
     }
   }
-  if (fin.enabled) FinishFixed(out, nsub_pat, K, fin, carries);
+  if (fin.enabled) FinishFixed(out, nsub_pat, K, fin, carries.c);
 }
 
 // ---------------------------------------------------------------------------

@@ -256,6 +256,19 @@ def test_fixed_length_finish_in_kernel_and_overlap_fallback(rj):
     got = rj.RegejSet(pats).match_all(t)
     for p, g in zip(pats, got):
         assert g == O.Oracle(p).match_all(t), p
+    # whole-literal patterns finish in-kernel too; self-overlapping occurrences fall back
+    for p in ("aa", "aba", "ab", "bxa"):
+        r = rj.Regej(p)
+        assert r.describe().startswith("literal scan"), r.describe()
+        exp = O.Oracle(p).match_all(t)
+        assert r.match_all(t) == exp and r.match_all(t) == exp, p
+    st = rj.Stats()
+    dt = rj.DeviceText(np.frombuffer(t, dtype=np.uint8))
+    try:
+        assert rj.Regej("ab").match_all_device(dt, stats=st) == len(O.Oracle("ab").match_all(t)) and st.launches == 1
+        assert rj.Regej("aa").match_all_device(dt, stats=st) == len(O.Oracle("aa").match_all(t)) and st.launches == 2
+    finally:
+        dt.free()
     # no overlaps at all: one launch per call
     t2 = fuzzgen.rand_text(rng, "acgt", 300000)
     r = rj.Regej("aacgtc|ggtgtc")
@@ -268,7 +281,8 @@ def test_fixed_length_finish_in_kernel_and_overlap_fallback(rj):
     finally:
         dt.free()
     # slab calls with a carry reaching into the slab
-    for p, text in (("ab[ab]|ba[ab]", t), ("aacgtc|ggtgtc", t2), ("a[ab]", b"x" * 8703 + b"aaaa" + b"x" * 9000)):
+    for p, text in (("ab[ab]|ba[ab]", t), ("aacgtc|ggtgtc", t2), ("a[ab]", b"x" * 8703 + b"aaaa" + b"x" * 9000),
+                    ("aa", b"x" * 16383 + b"aaaaa" + b"x" * 20000), ("ab", t)):
         r = rj.Regej(p)
         exp = len(O.Oracle(p).match_all(text))
         n = len(text)
