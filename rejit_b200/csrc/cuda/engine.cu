@@ -69,7 +69,8 @@ struct Buffer {
 }  // namespace
 
 // finish area inside DeviceContext::status
-constexpr size_t kFinSyncOffset = 128, kFinLastOffset = 160, kFinTotalOffset = 168, kFinSegOffset = 176;
+constexpr size_t kFinSyncOffset = 128, kFinLastOffset = 160, kFinTotalOffset = 168, kFinLastNeOffset = 176,
+                 kFinSegOffset = 184;
 
 class DeviceContext {
  public:
@@ -107,6 +108,7 @@ class DeviceContext {
   bool attr_done = false;
   bool coop = false;                  // cooperative launch available: scans finish in-kernel
   int lit_blocks_per_sm = 0;          // co-resident CTAs of k_lit_scan (occupancy query, cached)
+  int gen_blocks_per_sm = 0, win_blocks_per_sm = 0;
 
   bool Init(int dev, std::string* error) {
     device = dev;
@@ -129,7 +131,7 @@ class DeviceContext {
     RJ_TRY(cudaHostGetDevicePointer(&h_set_status_dev, h_set_status, 0));
     // status and the counters share one allocation so that one memset clears both
     // layout: [PipelineStatus][counters 40 B, at +64][finish: sync 8 x u32 at +128, last_end at +160,
-    //          total at +168, segcount at +176 (one u32 per scan CTA)]
+    //          total at +168, last non-empty end at +176, segcount at +184 (one u32 per segment)]
     if (!status.Reserve(kFinSegOffset + 4 * (size_t)sm_count + 64, error)) return false;
     counters.p = static_cast<uint8_t*>(status.p) + ((sizeof(PipelineStatus) + 15) & ~size_t(15));
     counters.bytes = 0;                 // not owned
@@ -340,11 +342,11 @@ bool WaitFinRecords(DeviceContext* c, int K, unsigned int seq, std::string* erro
   uint64_t spins = 0;
   for (int j = 0; j < K; ++j) {
     volatile FinRecord* r = c->h_fin + j;
-    while (r->seq0 != seq || r->seq1 != seq) {
+    while (r->seq0 != seq || r->seq1 != seq || r->seq2 != seq) {
       if ((++spins & 0x3FFF) == 0) {
         cudaError_t q = cudaStreamQuery(c->stream);
         if (q == cudaSuccess) {
-          if (r->seq0 == seq && r->seq1 == seq) break;
+          if (r->seq0 == seq && r->seq1 == seq && r->seq2 == seq) break;
           if (error) *error = "rejit_b200: the scan kernel did not report";
           return false;
         }
@@ -360,8 +362,15 @@ PipelineStatus StatusFromRecord(const FinRecord& r, const Carry& carry_in) {
   PipelineStatus st{};
   st.n_candidates = r.n_matches;
   st.n_matches = r.n_matches;
-  st.carry_cur = r.n_matches ? r.last_end : carry_in.cur;
-  st.carry_tail = r.n_matches ? r.last_end : carry_in.tail;
+  // the chain state after the last match (ChainTake): a non-empty match [b,e) leaves (e, e); an empty
+  // one at b leaves (b + 1, end of the last non-empty match)
+  st.carry_cur = carry_in.cur;
+  st.carry_tail = carry_in.tail;
+  if (r.n_matches) {
+    const bool last_is_empty = r.last_nonempty != r.last_end;
+    st.carry_cur = last_is_empty ? r.last_end + 1 : r.last_end;
+    if (r.last_nonempty) st.carry_tail = r.last_nonempty;
+  }
   st.overflow = (r.flags & kFinOverflow) ? 1u : 0u;
   st.need_cap = r.need_cap;
   st.need_large = (r.flags & kFinOverlap) ? 1u : 0u;
@@ -507,8 +516,17 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     const int grid_full = c->sm_count * 8;
     bool ordered = true;
     bool fused = false;                 // the scan kernel also produced the matches and the status
-    unsigned int fused_seq = 0;
-    // arguments of the in-kernel finish (FinishFixed) for a scan grid of `blocks` CTAs
+    unsigned int fused_seq = 0, hits_seq = 0;
+    // largest co-resident grid of a 256-thread kernel with the finish scratch (cached occupancy query)
+    auto coop_blocks = [&](const void* fn, int* cache) -> int {
+      if (*cache == 0) {
+        int nb = 0;
+        if (!Check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 256, kFinScratchWords * 4), "occupancy", error)) return 0;
+        *cache = std::max(1, nb);
+      }
+      return *cache * c->sm_count;
+    };
+    // arguments of the in-kernel finish (FinishOrdered) for a scan grid of `blocks` CTAs
     auto make_fin = [&](int blocks, uint64_t nsub) {
       FinishArgs fin{};
       uint8_t* base = static_cast<uint8_t*>(c->status.p);
@@ -519,7 +537,11 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       fin.sync = reinterpret_cast<unsigned int*>(base + kFinSyncOffset);
       fin.last_end = reinterpret_cast<unsigned long long*>(base + kFinLastOffset);
       fin.totals = reinterpret_cast<unsigned long long*>(base + kFinTotalOffset);
+      fin.last_ne = reinterpret_cast<unsigned long long*>(base + kFinLastNeOffset);
       fin.segcount = reinterpret_cast<uint32_t*>(base + kFinSegOffset);
+      // a candidate can only touch a predecessor in the 32 preceding sub-regions when matches are
+      // shorter than one sub-region (all scans here cut sub-regions by text offset)
+      fin.local_pred = (ca.nfa.max_len != kInfLen && ca.nfa.max_len + 64 < kDfaSubBytes) ? 1 : 0;
       fin.out_pairs = outp;
       fin.out_stride = 0;
       fin.out_cap = ocap;
@@ -541,9 +563,9 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
           // finish in-kernel: the grid must be co-resident for the barrier
           if (c->lit_blocks_per_sm == 0) {
             int nb = 0;
-            RJ_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lit_scan<true>, 256, 0));
+            RJ_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lit_scan<true>, 256, kFinScratchWords * 4));
             int nb2 = 0;
-            RJ_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_lit_scan<false>, 256, 0));
+            RJ_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_lit_scan<false>, 256, kFinScratchWords * 4));
             c->lit_blocks_per_sm = std::max(1, std::min(nb, nb2));
           }
           blocks = std::min(blocks, c->lit_blocks_per_sm * c->sm_count);
@@ -556,7 +578,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
           void* args[] = {(void*)&d_text, (void*)&n, (void*)&needle, (void*)&nl, (void*)&p4, (void*)&pmask,
                           (void*)&own, (void*)&cand, (void*)&fin, (void*)&c0};
           const void* fn = full4 ? (const void*)k_lit_scan<true> : (const void*)k_lit_scan<false>;
-          RJ_TRY(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, s));
+          RJ_TRY(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, kFinScratchWords * 4, s));
         } else if (full4) {
           k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, slab.own, cand, fin, carry_in);
         } else {
@@ -579,13 +601,30 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, hit_range, hs,
                                                 FinishArgs{}, Carry());
         if (stats) cudaEventRecord(c->ev[1], s);
-        k_gather_hits<<<1, 512, 0, s>>>(hs, hits, d_status);
+        const bool win_fused = c->coop && !fa.enabled;
+        if (win_fused) hits_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+        k_gather_hits<<<1, 512, 0, s>>>(hs, hits, d_status, win_fused ? c->h_fin_dev + 31 : nullptr, hits_seq);
         cand.cap = kWinSubHits * wsize;
         cand.nsub = (c->hits_cap + kWinSubHits - 1) / kWinSubHits;
         if (!ReserveStore(&c->sub_b, &c->sub_e, &c->sub_count, {cand.nsub, cand.cap}, error)) return false;
         cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
         int wblocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)c->sm_count * 4);
-        k_window_verify<<<wblocks, 256, 0, s>>>(d_text, n, dp->nfa, hits, ca.window_lo, ca.window_hi, slab.own, cand);
+        FinishArgs fin{};
+        if (c->coop && !fa.enabled) {
+          wblocks = std::min(wblocks, coop_blocks((const void*)k_window_verify, &c->win_blocks_per_sm));
+          if (wblocks < 1) return false;
+          fin = make_fin(wblocks, cand.nsub);
+          fin.local_pred = 0;                    // sub-regions of this store are cut by hit index, not by offset
+          fused = true;
+          uint32_t wlo = ca.window_lo, whi = ca.window_hi;
+          ScanRange own = slab.own;
+          Carry c0 = carry_in;
+          void* args[] = {(void*)&d_text, (void*)&n, (void*)&dp->nfa, (void*)&hits, (void*)&wlo, (void*)&whi, (void*)&own,
+                          (void*)&cand, (void*)&fin, (void*)&c0};
+          RJ_TRY(cudaLaunchCooperativeKernel((const void*)k_window_verify, dim3(wblocks), dim3(256), args, kFinScratchWords * 4, s));
+        } else {
+          k_window_verify<<<wblocks, 256, 0, s>>>(d_text, n, dp->nfa, hits, ca.window_lo, ca.window_hi, slab.own, cand, fin, carry_in);
+        }
         if (stats) stats->launches += 3;
         break;
       }
@@ -630,7 +669,21 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         if (!ReserveStore(&c->sub_b, &c->sub_e, &c->sub_count, {cand.nsub, cand.cap}, error)) return false;
         cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
         int blocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)grid_full);
-        k_generic_scan<<<blocks, 256, 0, s>>>(d_text, n, dp->nfa, dp->gen_filter, slab.own, cand);
+        FinishArgs fin{};
+        if (c->coop && !fa.enabled) {
+          blocks = std::min(blocks, coop_blocks((const void*)k_generic_scan, &c->gen_blocks_per_sm));
+          if (blocks < 1) return false;
+          fin = make_fin(blocks, cand.nsub);
+          fin.local_pred = (ca.nfa.max_len != kInfLen && ca.nfa.max_len + 64 < kGenSubBytes) ? 1 : 0;
+          fused = true;
+          ScanRange own = slab.own;
+          Carry c0 = carry_in;
+          void* args[] = {(void*)&d_text, (void*)&n, (void*)&dp->nfa, (void*)&dp->gen_filter, (void*)&own, (void*)&cand,
+                          (void*)&fin, (void*)&c0};
+          RJ_TRY(cudaLaunchCooperativeKernel((const void*)k_generic_scan, dim3(blocks), dim3(256), args, kFinScratchWords * 4, s));
+        } else {
+          k_generic_scan<<<blocks, 256, 0, s>>>(d_text, n, dp->nfa, dp->gen_filter, slab.own, cand, fin, carry_in);
+        }
         if (stats) stats->launches += 1;
         break;
       }
@@ -665,6 +718,16 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       RJ_TRY(cudaGetLastError());
       if (!WaitFinRecords(c, 1, fused_seq, error)) return false;
       st = StatusFromRecord(c->h_fin[0], carry_in);
+      if (ca.strategy == ScanStrategy::LiteralWindow) {
+        // outcome of the hit stage (k_gather_hits), published the same way in slot 31
+        volatile FinRecord* hr = c->h_fin + 31;
+        uint64_t spins = 0;
+        while (hr->seq0 != hits_seq || hr->seq1 != hits_seq || hr->seq2 != hits_seq)
+          if ((++spins & 0x3FFFFF) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;
+        if (hr->seq0 != hits_seq) { if (error) *error = "rejit_b200: the hit stage did not report"; return false; }
+        st.n_hits = hr->n_matches;
+        if (hr->flags & kFinOverflow) { st.overflow = 1; st.need_cap = std::max(st.need_cap, (unsigned int)hr->need_cap); }
+      }
       if (st.need_large && !st.overflow && !st.dense) {
         // neighbouring candidates overlap: the general resolve decides
         RJ_TRY(cudaMemsetAsync(d_status, 0, sizeof(PipelineStatus), s));
@@ -1011,11 +1074,12 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
       PipelineStatus* d_status = c->set_status.as<PipelineStatus>();
       int blocks = (int)std::min<uint64_t>((nsub + warps - 1) / warps, (uint64_t)c->sm_count);
       // set_counts: [0..K) dense counts, [40] work counter, then the finish area
-      // (sync 8 x u32 at +512, last_end[32] at +544, totals[32] at +800, segcount[K][nseg] at +1056)
+      // (sync 8 x u32 at +512, last_end[32] at +544, totals[32] at +800, last_ne[32] at +1056,
+      //  segcount[K][nseg] at +1312)
       const bool fuse_finish = c->coop;
       const uint32_t seg_subs = (uint32_t)((nsub + blocks - 1) / blocks);
       const uint32_t nseg = (uint32_t)((nsub + seg_subs - 1) / seg_subs);
-      const size_t counts_bytes = 1056 + (fuse_finish ? (size_t)K * nseg * 4 : 0);
+      const size_t counts_bytes = 1312 + (fuse_finish ? (size_t)K * nseg * 4 : 0);
       if (!c->set_counts.Reserve(counts_bytes, error)) return -1;
       unsigned long long* d_counts = c->set_counts.as<unsigned long long>();
       if (!Check(cudaMemsetAsync(d_counts, 0, counts_bytes, s), "memset", error)) return -1;
@@ -1070,7 +1134,9 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         fin.sync = reinterpret_cast<unsigned int*>(base + 512);
         fin.last_end = reinterpret_cast<unsigned long long*>(base + 544);
         fin.totals = reinterpret_cast<unsigned long long*>(base + 800);
-        fin.segcount = reinterpret_cast<uint32_t*>(base + 1056);
+        fin.last_ne = reinterpret_cast<unsigned long long*>(base + 1056);
+        fin.segcount = reinterpret_cast<uint32_t*>(base + 1312);
+        fin.local_pred = 1;                      // members are at most 17 bytes long
         fin.out_pairs = c->set_out.as<uint64_t>();
         fin.out_stride = per_cap;
         fin.out_cap = per_cap;

@@ -92,6 +92,9 @@ struct __align__(16) FinRecord {
   unsigned long long last_end;         // end of the last match (0 if none)
   unsigned int need_cap;
   unsigned int seq1;
+  unsigned long long last_nonempty;    // end of the last non-empty match (0 if none)
+  unsigned int pad;
+  unsigned int seq2;
 };
 
 // In-kernel finish of the fixed-length scans (k_dfa_tma, k_set_tma): the scan
@@ -104,6 +107,9 @@ struct FinishArgs {
   unsigned int* sync;                  // [0] arrive, [1] done, [2] flags, [3] need_cap; zeroed by the host
   unsigned long long* last_end;        // [K] end of the last candidate; zeroed by the host
   unsigned long long* totals;          // [K] candidates per pattern (written by the warp of the last segment)
+  unsigned long long* last_ne;         // [K] end of the last non-empty candidate; zeroed by the host
+  int local_pred;                      // geometry: a candidate can only touch a predecessor that lives in
+                                       // one of the 32 preceding sub-regions (bounded match length)
   uint64_t* out_pairs;                 // pattern j's pairs start at out_pairs + j * 2 * out_stride
   uint64_t out_stride, out_cap;
   uint64_t base_offset;
@@ -112,6 +118,7 @@ struct FinishArgs {
   unsigned long long* trace;           // optional (RJ_FIN_TRACE): 5 globaltimer stamps per CTA
 };
 constexpr unsigned int kFinOverlap = 1u, kFinDense = 2u, kFinOverflow = 4u;
+constexpr uint32_t kFinScratchWords = 2048;   // dynamic shared memory of the non-TMA scans (8 KB)
 
 struct DfaTables {
   const uint16_t* next;                // [n_states * n_classes], entries pre-multiplied by n_classes
@@ -307,8 +314,8 @@ __device__ __forceinline__ bool LitAny(const uint4& v, uint32_t nx, uint32_t p4,
 // (defined below, next to the DFA scans)
 __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_t sub, uint32_t total, bool over,
                                            uint32_t cap);
-__device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
-                                            const Carry* carries);
+__device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
+                                              const Carry* carries, uint32_t* scratch, uint32_t scratch_words);
 
 template <bool kFull4>
 __global__ void __launch_bounds__(256, 4)
@@ -371,7 +378,10 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
     }
   }
   // whole-literal patterns finish in-kernel like the DFA scans (cooperative launch)
-  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, &carry0);
+  if (fin.enabled) {
+    extern __shared__ __align__(16) uint32_t lit_scratch[];
+    FinishOrdered(out, out.nsub, 1, fin, &carry0, lit_scratch, kFinScratchWords);
+  }
 }
 
 // ===========================================================================
@@ -436,84 +446,225 @@ __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_
   if (total) atomicAdd(&fin.segcount[(uint64_t)j * fin.nseg + (uint32_t)(sub / fin.seg_subs)], total);
 }
 
-__device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
-                                            const Carry* carries) {
+__device__ __forceinline__ uint64_t WarpMax64(uint64_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const uint64_t o = __shfl_xor_sync(kFullMask, v, d);
+    v = o > v ? o : v;
+  }
+  return v;
+}
+
+// End + 1 of the last candidate stored in the sub-regions before `sub_end` of one
+// pattern's slice (cnt = its counts, row0 = index of its first sub-region), 0 if none.
+__device__ __forceinline__ uint64_t FinPrevBefore(const SubStore& st, const uint32_t* cnt, uint64_t row0,
+                                                  uint64_t sub_end, int local_pred, int lane) {
+  uint64_t s2 = sub_end;
+  while (s2 > 0) {
+    const uint64_t base = s2 >= 32 ? s2 - 32 : 0;
+    const uint64_t sub = base + lane;
+    uint32_t c = (sub < s2) ? __ldcg(&cnt[sub]) : 0u;
+    if (c == kLaneListOverflow) c = 0;
+    if (c > st.cap) c = st.cap;
+    const unsigned has = __ballot_sync(kFullMask, c != 0);
+    if (has) {
+      const int top = 31 - __clz(has);
+      const uint32_t ct = __shfl_sync(kFullMask, c, top);
+      return __ldcg(&st.end[(row0 + base + top) * st.cap + ct - 1]) + 1;
+    }
+    if (local_pred) return 0;
+    s2 = base;
+  }
+  return 0;
+}
+
+// One candidate against its predecessor (P = predecessor's end + 1, 0 = none):
+// the chain takes it iff it restarts the chain (ChainTake, device_program.h).
+__device__ __forceinline__ bool FinTaken(uint64_t b, uint64_t e, uint64_t P, const Carry& cin) {
+  bool ok = P == 0 || P <= b || (P == b + 1 && e > b);
+  if (b < cin.cur || (e == b && b == cin.tail)) ok = false;
+  return ok;
+}
+
+// ---------------------------------------------------------------------------
+// FinishOrdered: the in-kernel finish of an ordered candidate store.
+//   grid barrier -> every CTA takes one segment of sub-regions; its warps share
+//   the (pattern, chunk of 32 sub-regions) items:
+//     pass 1: counts and last ends of the item -> shared scratch
+//     pass 2: offset of the item (segment prefix from the scan's atomic counters
+//             + the chunk sums before it), its predecessor (last end before it),
+//             then the copy to the output with the "every candidate restarts the
+//             chain" check.
+//   The last warp of the grid publishes the records.
+// Latency matters here, not bandwidth: loads that do not depend on each other are
+// issued together; sparse chunks are copied lane-per-sub-region, dense ones
+// warp-per-sub-region (coalesced).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
+                                              const Carry* carries, uint32_t* scratch, uint32_t scratch_words) {
   FinTrace(fin, 0);
   GridBarrier(&fin.sync[0], gridDim.x);
   FinTrace(fin, 1);
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  // Latency matters here, not bandwidth (a few thousand matches): loads that do
-  // not depend on each other are issued together, and the counts of the next 32
-  // sub-regions are fetched while the current ones are copied.
   const unsigned int flags0 = __ldcg(&fin.sync[2]);      // consumed after the loads below are in flight
-  {
-    for (uint32_t seg = blockIdx.x; seg < fin.nseg; seg += gridDim.x) {
-      for (int j = warp_in_cta; j < K; j += nwarps) {
-        const uint64_t sub0 = (uint64_t)seg * fin.seg_subs;
-        const uint64_t sub1 = (sub0 + fin.seg_subs < nsub_pat) ? sub0 + fin.seg_subs : nsub_pat;
-        const uint32_t* cnt = st.count + (uint64_t)j * nsub_pat;
-        uint32_t c_next = (sub0 + lane < sub1) ? __ldcg(&cnt[sub0 + lane]) : 0u;
-        uint32_t edge = (lane == 0 && sub0 > 0) ? __ldcg(&cnt[sub0 - 1]) : 0u;   // the sub-region before the chunk
-        unsigned long long pre = 0, mine = 0;
+  for (uint32_t seg = blockIdx.x; seg < fin.nseg; seg += gridDim.x) {
+    const uint64_t sub0 = (uint64_t)seg * fin.seg_subs;
+    const uint64_t sub1 = (sub0 + fin.seg_subs < nsub_pat) ? sub0 + fin.seg_subs : nsub_pat;
+    const uint32_t nch = (uint32_t)((sub1 - sub0 + 31) / 32);
+    const uint32_t items = (uint32_t)K * nch;
+    const uint32_t sum_words = (items + 1) & ~1u;
+    uint32_t* s_sum = scratch;
+    uint64_t* s_last = reinterpret_cast<uint64_t*>(scratch + sum_words);
+    const bool fits = (uint64_t)sum_words + 2ull * items <= scratch_words;
+    if (!fits && threadIdx.x == 0) atomicOr(&fin.sync[2], kFinOverlap);      // the host resolves instead
+    // ---- pass 1 --------------------------------------------------------------
+    uint32_t c_keep = 0;
+    uint64_t P_keep = 0;
+    unsigned long long pre_keep = 0, mine_keep = 0;
+    for (uint32_t it = warp_in_cta, k = 0; it < items; it += nwarps, ++k) {
+      const uint32_t j = it / nch, ci = it - j * nch;
+      const uint64_t sub = sub0 + (uint64_t)ci * 32 + lane;
+      const uint32_t* cnt = st.count + (uint64_t)j * nsub_pat;
+      uint32_t c = (sub < sub1) ? __ldcg(&cnt[sub]) : 0u;
+      unsigned long long pre = 0, mine = 0;
+      if (k == 0) {
         for (uint32_t s2 = lane; s2 < fin.nseg; s2 += 32) {
-          uint32_t v = __ldcg(&fin.segcount[(uint64_t)j * fin.nseg + s2]);
+          const uint32_t v = __ldcg(&fin.segcount[(uint64_t)j * fin.nseg + s2]);
           if (s2 < seg) pre += v;
           if (s2 == seg) mine = v;
         }
+      }
+      if (c == kLaneListOverflow) c = 0;
+      if (c > st.cap) c = st.cap;
+      const uint64_t P = c ? __ldcg(&st.end[((uint64_t)j * nsub_pat + sub) * st.cap + c - 1]) + 1 : 0;
+      uint32_t sum = c;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
+      const uint64_t mx = WarpMax64(P);
+      if (fits && lane == 0) { s_sum[it] = sum; s_last[it] = mx; }
+      if (k == 0) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
           pre += __shfl_xor_sync(kFullMask, pre, d);
           mine += __shfl_xor_sync(kFullMask, mine, d);
         }
-        if (seg + 1 == fin.nseg && lane == 0) fin.totals[j] = pre + mine;
-        if (mine == 0 || (flags0 & (kFinDense | kFinOverflow))) continue;
-        const Carry cin = carries[j];
-        uint64_t* outp = fin.out_pairs + (uint64_t)j * 2 * fin.out_stride;
-        unsigned long long run = pre;
-        uint64_t last_e = 0;
-        bool bad = false;
-        for (uint64_t base = sub0; base < sub1; base += 32) {
-          const uint64_t sub = base + lane;
-          const uint32_t c = c_next;
-          if (base + 32 < sub1) c_next = (sub + 32 < sub1) ? __ldcg(&cnt[sub + 32]) : 0u;
-          uint32_t pc = __shfl_up_sync(kFullMask, c, 1);
-          if (lane == 0) pc = edge;
-          edge = __shfl_sync(kFullMask, c, 31);
-          const uint32_t incl = WarpInclusiveScan(c);
-          const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-          if (c) {
-            const unsigned long long at = run + incl - c;
-            const uint64_t slot0 = ((uint64_t)j * nsub_pat + sub) * st.cap;
-            uint64_t b = __ldcg(&st.begin[slot0]);
-            uint64_t e = __ldcg(&st.end[slot0]);
-            uint64_t prev_end = pc ? __ldcg(&st.end[slot0 - st.cap + pc - 1]) : 0;
-            prev_end = cin.cur > prev_end ? cin.cur : prev_end;
-            for (uint32_t i = 0;;) {
-              bad |= prev_end > b;
-              prev_end = e;
-              if (at + i < fin.out_cap) {
-                outp[2 * (at + i)] = b + fin.base_offset;
-                outp[2 * (at + i) + 1] = e + fin.base_offset;
-              }
-              if (++i >= c) break;
-              b = __ldcg(&st.begin[slot0 + i]);
-              e = __ldcg(&st.end[slot0 + i]);
-            }
-            last_e = prev_end;
-          }
-          run += total;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          const uint64_t o = __shfl_xor_sync(kFullMask, last_e, d);
-          last_e = o > last_e ? o : last_e;
-        }
-        if (lane == 0 && last_e) atomicMax(&fin.last_end[j], (unsigned long long)last_e);
-        if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(&fin.sync[2], kFinOverlap);
+        c_keep = c; P_keep = P; pre_keep = pre; mine_keep = mine;
       }
     }
+    __syncthreads();
+    // ---- pass 2 --------------------------------------------------------------
+    for (uint32_t it = warp_in_cta, k = 0; it < items; it += nwarps, ++k) {
+      const uint32_t j = it / nch, ci = it - j * nch;
+      const uint64_t row0 = (uint64_t)j * nsub_pat;
+      const uint64_t sub = sub0 + (uint64_t)ci * 32 + lane;
+      const uint32_t* cnt = st.count + row0;
+      uint32_t c = c_keep;
+      uint64_t P = P_keep;
+      unsigned long long pre = pre_keep, mine = mine_keep;
+      if (k != 0) {
+        c = (sub < sub1) ? __ldcg(&cnt[sub]) : 0u;
+        pre = 0; mine = 0;
+        for (uint32_t s2 = lane; s2 < fin.nseg; s2 += 32) {
+          const uint32_t v = __ldcg(&fin.segcount[(uint64_t)j * fin.nseg + s2]);
+          if (s2 < seg) pre += v;
+          if (s2 == seg) mine = v;
+        }
+        if (c == kLaneListOverflow) c = 0;
+        if (c > st.cap) c = st.cap;
+        P = c ? __ldcg(&st.end[(row0 + sub) * st.cap + c - 1]) + 1 : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          pre += __shfl_xor_sync(kFullMask, pre, d);
+          mine += __shfl_xor_sync(kFullMask, mine, d);
+        }
+      }
+      if (ci + 1 == nch && seg + 1 == fin.nseg && lane == 0) fin.totals[j] = pre + mine;
+      if (!fits || mine == 0 || (flags0 & (kFinDense | kFinOverflow))) continue;
+      // where the item's candidates go, and who precedes them
+      unsigned long long before = 0;
+      uint64_t prevP = 0;
+      for (uint32_t c2 = lane; c2 < ci; c2 += 32) {
+        before += s_sum[j * nch + c2];
+        const uint64_t q = s_last[j * nch + c2];
+        prevP = q > prevP ? q : prevP;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(kFullMask, before, d);
+      prevP = WarpMax64(prevP);
+      const uint32_t incl = WarpInclusiveScan(c);
+      const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+      if (total == 0) continue;
+      if (prevP == 0) prevP = FinPrevBefore(st, cnt, row0, sub0, fin.local_pred, lane);
+      // predecessor of my sub-region's first candidate: the last end among the lanes before me
+      uint64_t inclP = P;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t o = __shfl_up_sync(kFullMask, inclP, d);
+        if (lane >= d && o > inclP) inclP = o;
+      }
+      uint64_t myprev = __shfl_up_sync(kFullMask, inclP, 1);
+      if (lane == 0) myprev = 0;
+      if (prevP > myprev) myprev = prevP;
+      const unsigned long long at = pre + before + incl - c;
+      const Carry cin = carries[j];
+      uint64_t* outp = fin.out_pairs + (uint64_t)j * 2 * fin.out_stride;
+      bool bad = false;
+      uint64_t ne = 0;                         // last non-empty end seen by this lane
+      uint32_t maxc = c;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(kFullMask, maxc, d));
+      if (maxc <= 2) {
+        if (c) {
+          const uint64_t slot0 = (row0 + sub) * st.cap;
+          const uint64_t b0 = __ldcg(&st.begin[slot0]), e0 = __ldcg(&st.end[slot0]);
+          uint64_t b1 = 0, e1 = 0;
+          if (c > 1) { b1 = __ldcg(&st.begin[slot0 + 1]); e1 = __ldcg(&st.end[slot0 + 1]); }
+          bad |= !FinTaken(b0, e0, myprev, cin);
+          if (e0 > b0) ne = e0;
+          if (at < fin.out_cap) { outp[2 * at] = b0 + fin.base_offset; outp[2 * at + 1] = e0 + fin.base_offset; }
+          if (c > 1) {
+            bad |= !FinTaken(b1, e1, e0 + 1, cin);
+            if (e1 > b1) ne = e1;
+            if (at + 1 < fin.out_cap) { outp[2 * at + 2] = b1 + fin.base_offset; outp[2 * at + 3] = e1 + fin.base_offset; }
+          }
+        }
+      } else {
+        unsigned todo = __ballot_sync(kFullMask, c != 0);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const uint32_t cs = __shfl_sync(kFullMask, c, src);
+          const unsigned long long ats = __shfl_sync(kFullMask, at, src);
+          uint64_t carryP = __shfl_sync(kFullMask, myprev, src);
+          const uint64_t slot0 = (row0 + sub0 + (uint64_t)ci * 32 + src) * st.cap;
+          for (uint32_t i0 = 0; i0 < cs; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool v = i < cs;
+            const uint64_t b = v ? __ldcg(&st.begin[slot0 + i]) : 0;
+            const uint64_t e = v ? __ldcg(&st.end[slot0 + i]) : 0;
+            uint64_t Pp = __shfl_up_sync(kFullMask, e + 1, 1);
+            if (lane == 0) Pp = carryP;
+            if (v) {
+              bad |= !FinTaken(b, e, Pp, cin);
+              if (e > b) ne = e;
+              if (ats + i < fin.out_cap) { outp[2 * (ats + i)] = b + fin.base_offset; outp[2 * (ats + i) + 1] = e + fin.base_offset; }
+            }
+            const uint32_t lastl = (cs - i0 > 32 ? 32u : cs - i0) - 1;
+            carryP = __shfl_sync(kFullMask, e + 1, lastl);
+          }
+        }
+      }
+      const uint64_t lastP = WarpMax64(P);
+      ne = WarpMax64(ne);
+      if (lane == 0) {
+        if (lastP) atomicMax(&fin.last_end[j], (unsigned long long)(lastP - 1));
+        if (ne) atomicMax(&fin.last_ne[j], (unsigned long long)ne);
+      }
+      if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(&fin.sync[2], kFinOverlap);
+    }
+    __syncthreads();
   }
   // the last WARP of the grid to get here publishes the records (every warp
   // counts once; its atomics above are ordered before the count by the fence)
@@ -536,12 +687,14 @@ __device__ __forceinline__ void FinishFixed(const SubStore& st, uint64_t nsub_pa
   for (int j = lane; j < K; j += 32) {
     const unsigned long long tot = __ldcg(&fin.totals[j]);
     const unsigned long long le = __ldcg(&fin.last_end[j]);
-    uint4 h0, h1;
-    h0.x = (unsigned int)tot; h0.y = (unsigned int)(tot >> 32); h0.z = flags; h0.w = fin.seq;
-    h1.x = (unsigned int)le; h1.y = (unsigned int)(le >> 32); h1.z = need_cap; h1.w = fin.seq;
+    const unsigned long long ln = __ldcg(&fin.last_ne[j]);
     volatile uint4* dst = reinterpret_cast<volatile uint4*>(fin.host_records + j);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w) : "memory");
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)tot),
+                 "r"((unsigned int)(tot >> 32)), "r"(flags), "r"(fin.seq) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)le),
+                 "r"((unsigned int)(le >> 32)), "r"(need_cap), "r"(fin.seq) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"((unsigned int)ln),
+                 "r"((unsigned int)(ln >> 32)), "r"(0u), "r"(fin.seq) : "memory");
   }
   if (fin.trace && lane == 0) {
     unsigned long long t;
@@ -746,7 +899,8 @@ k_dfa_tma(const uint8_t* __restrict__ text, uint64_t n, DfaTables dfa, ScanRange
       out.count[sub] = 0;
     }
   }
-  if (fin.enabled) FinishFixed(out, out.nsub, 1, fin, carries.c);
+  if (fin.enabled) FinishOrdered(out, out.nsub, 1, fin, carries.c, reinterpret_cast<uint32_t*>(s_tiles),
+                                 (uint32_t)warps_per_cta * (kDfaTileBytes / 4));
 }
 
 // ===========================================================================
@@ -986,7 +1140,8 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
       if (over && lane == 0) *dense_flag = 1u;
     }
   }
-  if (fin.enabled) FinishFixed(out, nsub_pat, K, fin, carries.c);
+  if (fin.enabled) FinishOrdered(out, nsub_pat, K, fin, carries.c, reinterpret_cast<uint32_t*>(s_tiles),
+                                 (uint32_t)warps_per_cta * (kDfaTileBytes / 4));
 }
 
 // ---------------------------------------------------------------------------
@@ -1093,7 +1248,7 @@ __device__ __noinline__ void GenEmit(const uint8_t* __restrict__ text, uint64_t 
 
 __global__ void __launch_bounds__(256)
 k_generic_scan(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, GenFilter flt, ScanRange range,
-               SubStore out) {
+               SubStore out, FinishArgs fin, Carry carry0) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1133,7 +1288,14 @@ k_generic_scan(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, GenF
         if (__any_sync(kFullMask, cand != 0)) GenEmit(text, n, nfa, range, out, sub, k, my, cand);
       }
     }
-    if (lane == 0) out.count[sub] = k;
+    if (lane == 0) {
+      out.count[sub] = k;
+      FinishNote(fin, 0, sub, k, false, out.cap);
+    }
+  }
+  if (fin.enabled) {
+    extern __shared__ __align__(16) uint32_t gen_scratch[];
+    FinishOrdered(out, out.nsub, 1, fin, &carry0, gen_scratch, kFinScratchWords);
   }
 }
 
@@ -1144,7 +1306,7 @@ k_generic_scan(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, GenF
 // ===========================================================================
 __global__ void __launch_bounds__(256)
 k_window_verify(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, DenseList hits, uint32_t lo,
-                uint32_t hi, ScanRange range, SubStore out) {
+                uint32_t hi, ScanRange range, SubStore out, FinishArgs fin, Carry carry0) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1174,7 +1336,14 @@ k_window_verify(const uint8_t* __restrict__ text, uint64_t n, NfaTables nfa, Den
         EmitOrdered(out, sub, k, e != kNoMatch, s, e);
       }
     }
-    if (lane == 0) out.count[sub] = k;
+    if (lane == 0) {
+      out.count[sub] = k;
+      FinishNote(fin, 0, sub, k, false, out.cap);
+    }
+  }
+  if (fin.enabled) {
+    extern __shared__ __align__(16) uint32_t win_scratch[];
+    FinishOrdered(out, out.nsub, 1, fin, &carry0, win_scratch, kFinScratchWords);
   }
 }
 
@@ -1335,11 +1504,26 @@ __device__ __forceinline__ bool GatherSubStore(const SubStore& st, const DenseLi
 
 // Stage boundary of the literal+window pipeline: dense list of needle hits.
 __global__ void __launch_bounds__(512, 1)
-k_gather_hits(SubStore st, DenseList dense, PipelineStatus* status) {
+k_gather_hits(SubStore st, DenseList dense, PipelineStatus* status, FinRecord* host_rec, unsigned int seq) {
   __shared__ uint32_t s_warp[33];
   unsigned long long m;
   GatherSubStore(st, dense, status, s_warp, &m, ~0ull);
-  if (threadIdx.x == 0) status->n_hits = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    status->n_hits = m;
+    if (host_rec) {
+      // the fused pipeline reads the hit stage's outcome from mapped memory (see FinRecord)
+      const unsigned int flags = (status->overflow ? kFinOverflow : 0u) | (status->dense ? kFinDense : 0u);
+      const unsigned int need_cap = status->need_cap;
+      volatile uint4* dst = reinterpret_cast<volatile uint4*>(host_rec);
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)m),
+                   "r"((unsigned int)(m >> 32)), "r"(flags), "r"(seq) : "memory");
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"(0u), "r"(0u), "r"(need_cap),
+                   "r"(seq) : "memory");
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"(0u), "r"(0u), "r"(0u),
+                   "r"(seq) : "memory");
+    }
+  }
 }
 
 __device__ __forceinline__ bool IsRestart(const uint64_t* b, const uint64_t* e, const uint64_t* reach, uint64_t i) {
