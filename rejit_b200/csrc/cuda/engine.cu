@@ -69,6 +69,7 @@ struct Buffer {
 }  // namespace
 
 // finish area inside DeviceContext::status
+constexpr size_t kFinMaxSegments = 1024;
 constexpr size_t kFinSyncOffset = 128, kFinLastOffset = 160, kFinTotalOffset = 168, kFinLastNeOffset = 176,
                  kFinSegOffset = 184;
 
@@ -132,7 +133,7 @@ class DeviceContext {
     // status and the counters share one allocation so that one memset clears both
     // layout: [PipelineStatus][counters 40 B, at +64][finish: sync 8 x u32 at +128, last_end at +160,
     //          total at +168, last non-empty end at +176, segcount at +184 (one u32 per segment)]
-    if (!status.Reserve(kFinSegOffset + 4 * (size_t)sm_count + 64, error)) return false;
+    if (!status.Reserve(kFinSegOffset + 4 * (size_t)kFinMaxSegments + 64, error)) return false;
     counters.p = static_cast<uint8_t*>(status.p) + ((sizeof(PipelineStatus) + 15) & ~size_t(15));
     counters.bytes = 0;                 // not owned
     return true;
@@ -272,16 +273,76 @@ DeviceContext* ContextFor(int device, std::string* error) {
   return g_ctx[device];
 }
 
+// Text-sized device buffers come and go in chains of ReplaceAll calls and in
+// upload / search / free loops; cudaMalloc + cudaFree cost about a millisecond
+// a pair, so freed buffers are kept (a few per device) and handed out again when
+// the size fits.
+namespace {
+struct PooledBuffer { void* p; size_t bytes; };
+std::mutex g_pool_mu;
+std::vector<PooledBuffer> g_pool[16];
+std::vector<PooledBuffer> g_live[16];          // sizes of the buffers handed out
+constexpr size_t kPoolBuffers = 6;
+}  // namespace
+
 void* DeviceAlloc(int device, size_t bytes, std::string* error) {
   if (!CudaOk(error)) return nullptr;
-  void* p = nullptr;
-  if (!Check(cudaSetDevice(device), "cudaSetDevice", error)) return nullptr;
+  if (device < 0 || device >= 16) { if (error) *error = "rejit_b200: bad device"; return nullptr; }
   // 64 bytes of slack so that 16-byte vector loads near the end never leave
   // the allocation
-  if (!Check(cudaMalloc(&p, bytes + 64), "cudaMalloc", error)) return nullptr;
+  const size_t want = bytes + 64;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto& pool = g_pool[device];
+    size_t best = pool.size();
+    for (size_t i = 0; i < pool.size(); ++i)
+      if (pool[i].bytes >= want && pool[i].bytes <= 2 * want + (1u << 20) &&
+          (best == pool.size() || pool[i].bytes < pool[best].bytes)) best = i;
+    if (best != pool.size()) {
+      PooledBuffer b = pool[best];
+      pool.erase(pool.begin() + best);
+      g_live[device].push_back(b);
+      return b.p;
+    }
+  }
+  void* p = nullptr;
+  if (!Check(cudaSetDevice(device), "cudaSetDevice", error)) return nullptr;
+  const size_t grow = want + want / 8;           // room for a text that grows a little (IUB substitutions)
+  if (cudaMalloc(&p, grow) != cudaSuccess) {
+    cudaGetLastError();
+    // out of memory: drop the pool and try the exact size
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      for (auto& b : g_pool[device]) cudaFree(b.p);
+      g_pool[device].clear();
+    }
+    if (!Check(cudaMalloc(&p, want), "cudaMalloc", error)) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_live[device].push_back({p, want});
+    return p;
+  }
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_live[device].push_back({p, grow});
   return p;
 }
-void DeviceFree(int device, void* p) { if (p) { cudaSetDevice(device); cudaFree(p); } }
+void DeviceFree(int device, void* p) {
+  if (!p || device < 0 || device >= 16) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto& live = g_live[device];
+  size_t bytes = 0;
+  for (size_t i = 0; i < live.size(); ++i)
+    if (live[i].p == p) { bytes = live[i].bytes; live.erase(live.begin() + i); break; }
+  auto& pool = g_pool[device];
+  if (bytes && pool.size() < kPoolBuffers) { pool.push_back({p, bytes}); return; }
+  if (bytes && !pool.empty()) {
+    // keep the larger buffers
+    size_t smallest = 0;
+    for (size_t i = 1; i < pool.size(); ++i) if (pool[i].bytes < pool[smallest].bytes) smallest = i;
+    if (pool[smallest].bytes < bytes) std::swap(pool[smallest].p, p), std::swap(pool[smallest].bytes, bytes);
+  }
+  cudaSetDevice(device);
+  cudaFree(p);
+}
 void* PinnedAlloc(size_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
@@ -491,7 +552,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
   for (int attempt = 0; attempt < 48; ++attempt) {
     unsigned long long* ctr = c->counters.as<unsigned long long>();
     PipelineStatus* d_status = c->status.as<PipelineStatus>();
-    RJ_TRY(cudaMemsetAsync(d_status, 0, kFinSegOffset + 4 * (size_t)c->sm_count, s));
+    RJ_TRY(cudaMemsetAsync(d_status, 0, kFinSegOffset + 4 * (size_t)kFinMaxSegments, s));
     const bool use_fallback = ca.strategy == ScanStrategy::DfaFixed && (dp->dense_mode || tma_warps < 4);
     if (use_fallback && c->cand_cap == 0 && !c->ReserveUnordered(1u << 16, error)) return false;
     uint64_t ocap = d_out ? out_cap : c->out_pairs.bytes / 16;
@@ -531,7 +592,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       FinishArgs fin{};
       uint8_t* base = static_cast<uint8_t*>(c->status.p);
       fin.enabled = 1;
-      const int segs = std::min(blocks, c->sm_count);            // the counter array holds sm_count segments
+      const int segs = std::min(blocks, (int)kFinMaxSegments);   // one segment per CTA
       fin.seg_subs = (uint32_t)((nsub + segs - 1) / segs);
       fin.nseg = (uint32_t)((nsub + fin.seg_subs - 1) / fin.seg_subs);
       fin.sync = reinterpret_cast<unsigned int*>(base + kFinSyncOffset);

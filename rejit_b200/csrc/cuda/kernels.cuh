@@ -118,7 +118,7 @@ struct FinishArgs {
   unsigned long long* trace;           // optional (RJ_FIN_TRACE): 5 globaltimer stamps per CTA
 };
 constexpr unsigned int kFinOverlap = 1u, kFinDense = 2u, kFinOverflow = 4u;
-constexpr uint32_t kFinScratchWords = 2048;   // dynamic shared memory of the non-TMA scans (8 KB)
+constexpr uint32_t kFinScratchWords = 4096;   // dynamic shared memory of the non-TMA scans (16 KB)
 
 struct DfaTables {
   const uint16_t* next;                // [n_states * n_classes], entries pre-multiplied by n_classes
@@ -423,6 +423,10 @@ __device__ __forceinline__ void GridBarrier(unsigned int* ctr, unsigned int expe
     unsigned int v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v < expected) {                       // back off: hundreds of CTAs poll one L2 line
+        const long long t0 = clock64();         // (no __nanosleep: ptxas reserves static shared memory for it)
+        while (clock64() - t0 < 256) {}
+      }
     } while (v < expected);
     __threadfence();
   }
@@ -515,11 +519,19 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
     const uint32_t nch = (uint32_t)((sub1 - sub0 + 31) / 32);
     const uint32_t items = (uint32_t)K * nch;
     const uint32_t sum_words = (items + 1) & ~1u;
+    const uint32_t seg_len = (uint32_t)(sub1 - sub0);
+    const uint32_t cells = (uint32_t)K * seg_len;                  // (pattern, sub-region) pairs of the segment
+    const uint32_t cell_words = (cells + 1) & ~1u;
+    // scratch: [chunk sums u32][cell counts u32][chunk last P u64][cell offsets u64][cell predecessors u64]
     uint32_t* s_sum = scratch;
-    uint64_t* s_last = reinterpret_cast<uint64_t*>(scratch + sum_words);
-    const bool fits = (uint64_t)sum_words + 2ull * items <= scratch_words;
+    uint32_t* s_cnt = scratch + sum_words;
+    uint64_t* s_last = reinterpret_cast<uint64_t*>(scratch + sum_words + cell_words);
+    uint64_t* s_at = s_last + items;
+    uint64_t* s_prev = s_at + cells;
+    const bool fits = (uint64_t)sum_words + cell_words + 2ull * items + 4ull * cells <= scratch_words;
     if (!fits && threadIdx.x == 0) atomicOr(&fin.sync[2], kFinOverlap);      // the host resolves instead
-    // ---- pass 1 --------------------------------------------------------------
+    const bool usable = fits && !(flags0 & (kFinDense | kFinOverflow));
+    // ---- pass 1: counts and last ends of every item ------------------------------
     uint32_t c_keep = 0;
     uint64_t P_keep = 0;
     unsigned long long pre_keep = 0, mine_keep = 0;
@@ -554,7 +566,7 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
       }
     }
     __syncthreads();
-    // ---- pass 2 --------------------------------------------------------------
+    // ---- pass 2: where every sub-region's candidates go, and who precedes them ---
     for (uint32_t it = warp_in_cta, k = 0; it < items; it += nwarps, ++k) {
       const uint32_t j = it / nch, ci = it - j * nch;
       const uint64_t row0 = (uint64_t)j * nsub_pat;
@@ -581,8 +593,9 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
         }
       }
       if (ci + 1 == nch && seg + 1 == fin.nseg && lane == 0) fin.totals[j] = pre + mine;
-      if (!fits || mine == 0 || (flags0 & (kFinDense | kFinOverflow))) continue;
-      // where the item's candidates go, and who precedes them
+      if (!usable) continue;
+      const uint32_t cell = j * seg_len + ci * 32 + lane;
+      if (mine == 0) { if (sub < sub1) s_cnt[cell] = 0; continue; }
       unsigned long long before = 0;
       uint64_t prevP = 0;
       for (uint32_t c2 = lane; c2 < ci; c2 += 32) {
@@ -595,8 +608,7 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
       prevP = WarpMax64(prevP);
       const uint32_t incl = WarpInclusiveScan(c);
       const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-      if (total == 0) continue;
-      if (prevP == 0) prevP = FinPrevBefore(st, cnt, row0, sub0, fin.local_pred, lane);
+      if (total != 0 && prevP == 0) prevP = FinPrevBefore(st, cnt, row0, sub0, fin.local_pred, lane);
       // predecessor of my sub-region's first candidate: the last end among the lanes before me
       uint64_t inclP = P;
 #pragma unroll
@@ -607,61 +619,61 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
       uint64_t myprev = __shfl_up_sync(kFullMask, inclP, 1);
       if (lane == 0) myprev = 0;
       if (prevP > myprev) myprev = prevP;
-      const unsigned long long at = pre + before + incl - c;
-      const Carry cin = carries[j];
-      uint64_t* outp = fin.out_pairs + (uint64_t)j * 2 * fin.out_stride;
-      bool bad = false;
-      uint64_t ne = 0;                         // last non-empty end seen by this lane
-      uint32_t maxc = c;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(kFullMask, maxc, d));
-      if (maxc <= 2) {
-        if (c) {
-          const uint64_t slot0 = (row0 + sub) * st.cap;
-          const uint64_t b0 = __ldcg(&st.begin[slot0]), e0 = __ldcg(&st.end[slot0]);
-          uint64_t b1 = 0, e1 = 0;
-          if (c > 1) { b1 = __ldcg(&st.begin[slot0 + 1]); e1 = __ldcg(&st.end[slot0 + 1]); }
-          bad |= !FinTaken(b0, e0, myprev, cin);
-          if (e0 > b0) ne = e0;
-          if (at < fin.out_cap) { outp[2 * at] = b0 + fin.base_offset; outp[2 * at + 1] = e0 + fin.base_offset; }
-          if (c > 1) {
-            bad |= !FinTaken(b1, e1, e0 + 1, cin);
-            if (e1 > b1) ne = e1;
-            if (at + 1 < fin.out_cap) { outp[2 * at + 2] = b1 + fin.base_offset; outp[2 * at + 3] = e1 + fin.base_offset; }
-          }
-        }
-      } else {
-        unsigned todo = __ballot_sync(kFullMask, c != 0);
-        while (todo) {
-          const int src = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const uint32_t cs = __shfl_sync(kFullMask, c, src);
-          const unsigned long long ats = __shfl_sync(kFullMask, at, src);
-          uint64_t carryP = __shfl_sync(kFullMask, myprev, src);
-          const uint64_t slot0 = (row0 + sub0 + (uint64_t)ci * 32 + src) * st.cap;
-          for (uint32_t i0 = 0; i0 < cs; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool v = i < cs;
-            const uint64_t b = v ? __ldcg(&st.begin[slot0 + i]) : 0;
-            const uint64_t e = v ? __ldcg(&st.end[slot0 + i]) : 0;
-            uint64_t Pp = __shfl_up_sync(kFullMask, e + 1, 1);
-            if (lane == 0) Pp = carryP;
-            if (v) {
-              bad |= !FinTaken(b, e, Pp, cin);
-              if (e > b) ne = e;
-              if (ats + i < fin.out_cap) { outp[2 * (ats + i)] = b + fin.base_offset; outp[2 * (ats + i) + 1] = e + fin.base_offset; }
-            }
-            const uint32_t lastl = (cs - i0 > 32 ? 32u : cs - i0) - 1;
-            carryP = __shfl_sync(kFullMask, e + 1, lastl);
-          }
-        }
+      if (sub < sub1) {
+        s_cnt[cell] = c;
+        s_at[cell] = pre + before + incl - c;
+        s_prev[cell] = myprev;
       }
       const uint64_t lastP = WarpMax64(P);
-      ne = WarpMax64(ne);
-      if (lane == 0) {
-        if (lastP) atomicMax(&fin.last_end[j], (unsigned long long)(lastP - 1));
-        if (ne) atomicMax(&fin.last_ne[j], (unsigned long long)ne);
+      if (lane == 0 && lastP) atomicMax(&fin.last_end[j], (unsigned long long)(lastP - 1));
+    }
+    __syncthreads();
+    // ---- pass 3: the copy, one warp per non-empty sub-region, 128 candidates in flight
+    if (usable) {
+      bool bad = false;
+      uint64_t ne = 0;                          // last non-empty end seen by this lane
+      int ne_j = -1;
+      for (uint32_t cell = warp_in_cta; cell < cells; cell += nwarps) {
+        const uint32_t cs = s_cnt[cell];
+        if (cs == 0) continue;
+        const uint32_t j = cell / seg_len;
+        const uint64_t sub = sub0 + (cell - j * seg_len);
+        const uint64_t slot0 = ((uint64_t)j * nsub_pat + sub) * st.cap;
+        const unsigned long long ats = s_at[cell];
+        uint64_t carryP = s_prev[cell];
+        const Carry cin = carries[j];
+        ulonglong2* outp = reinterpret_cast<ulonglong2*>(fin.out_pairs + (uint64_t)j * 2 * fin.out_stride);
+        if (ne_j != (int)j) {
+          // (a warp's cells are visited in increasing pattern order: flush the previous pattern's maximum)
+          if (ne_j >= 0) { const uint64_t m2 = WarpMax64(ne); if (lane == 0 && m2) atomicMax(&fin.last_ne[ne_j], (unsigned long long)m2); }
+          ne = 0; ne_j = (int)j;
+        }
+        for (uint32_t i0 = 0; i0 < cs; i0 += 128) {
+          uint64_t bb[4], ee[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * 32 + lane;
+            bb[u] = (i < cs) ? __ldcg(&st.begin[slot0 + i]) : 0;
+            ee[u] = (i < cs) ? __ldcg(&st.end[slot0 + i]) : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t ib = i0 + u * 32;
+            if (ib >= cs) break;
+            const uint32_t i = ib + lane;
+            uint64_t Pp = __shfl_up_sync(kFullMask, ee[u] + 1, 1);
+            if (lane == 0) Pp = carryP;
+            if (i < cs) {
+              bad |= !FinTaken(bb[u], ee[u], Pp, cin);
+              if (ee[u] > bb[u]) ne = ee[u];
+              if (ats + i < fin.out_cap) outp[ats + i] = make_ulonglong2(bb[u] + fin.base_offset, ee[u] + fin.base_offset);
+            }
+            const uint32_t nvalid = cs - ib > 32 ? 32u : cs - ib;
+            carryP = __shfl_sync(kFullMask, ee[u] + 1, nvalid - 1);
+          }
+        }
       }
+      if (ne_j >= 0) { const uint64_t m2 = WarpMax64(ne); if (lane == 0 && m2) atomicMax(&fin.last_ne[ne_j], (unsigned long long)m2); }
       if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(&fin.sync[2], kFinOverlap);
     }
     __syncthreads();

@@ -14,6 +14,7 @@ echo "== bench reference" ; timeout 900 python bench.py --impl reference --steps
 if [ "${RJ_EXTRA:-0}" = "1" ]; then
 echo "== finish trace"; timeout 300 python scripts/fin_trace.py 2>&1 | tail -8 | tee gpurun_out/fin_trace.txt | cut -c1-300
 echo "== bench_extra"; timeout 1200 python scripts/bench_extra.py 2>&1 | tee gpurun_out/bench_extra.jsonl | cut -c1-400
+echo "== ncu launches of bench_extra"; RJ_EXTRA_REPS=2 RJ_EXTRA_BYTES=500000000 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_extra.csv python scripts/bench_extra.py > gpurun_out/ncu_extra.log 2>&1; tail -2 gpurun_out/ncu_extra.log | cut -c1-200
 fi
 if [ "${RJ_SWEEP:-0}" = "1" ]; then
 for w in 6 10 14 18; do echo "== sweep RJ_DFA_WARPS=$w"; RJ_DFA_WARPS=$w timeout 300 python bench.py --steps 3 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['frac'])"; done
