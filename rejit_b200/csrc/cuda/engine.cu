@@ -179,6 +179,7 @@ class DeviceProgram {
   uint32_t cand_sub_cap = 16;         // slots per sub-region, candidate store
   uint32_t hit_sub_cap = 16;          // slots per sub-region, needle-hit store
   bool dense_mode = false;            // k_dfa_tma's lane lists overflowed once: use k_dfa_scan
+  uint32_t fuse_misses = 0, fuse_skips = 0;   // in-kernel finish: consecutive misses / calls skipped since
   std::vector<void*> allocs;
   ~DeviceProgram() { for (void* p : allocs) cudaFree(p); }
 
@@ -576,6 +577,11 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     if (stats) cudaEventRecord(c->ev[0], s);
     const int grid_full = c->sm_count * 8;
     bool ordered = true;
+    // The in-kernel finish only pays off when the candidates turn out to be the matches.  A pattern whose
+    // candidates overlap by nature (several starts reach the same end) keeps failing the test: after a
+    // miss the finish is skipped, and probed again every 32nd call.
+    const bool try_fuse = c->coop && !fa.enabled && (dp->fuse_misses == 0 || (dp->fuse_skips & 31) == 31);
+    if (c->coop && !fa.enabled && !try_fuse) dp->fuse_skips++;
     bool fused = false;                 // the scan kernel also produced the matches and the status
     unsigned int fused_seq = 0, hits_seq = 0;
     // largest co-resident grid of a 256-thread kernel with the finish scratch (cached occupancy query)
@@ -620,7 +626,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         int blocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)grid_full);
         const bool full4 = dp->needle_len >= 4;
         FinishArgs fin{};
-        if (c->coop && !fa.enabled && dp->needle_len + 64 < kLitSubBytes) {
+        if (try_fuse && dp->needle_len + 64 < kLitSubBytes) {
           // finish in-kernel: the grid must be co-resident for the barrier
           if (c->lit_blocks_per_sm == 0) {
             int nb = 0;
@@ -662,7 +668,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         k_lit_scan<true><<<blocks, 256, 0, s>>>(d_text, n, dp->needle, dp->needle_len, dp->p4, dp->pmask, hit_range, hs,
                                                 FinishArgs{}, Carry());
         if (stats) cudaEventRecord(c->ev[1], s);
-        const bool win_fused = c->coop && !fa.enabled;
+        const bool win_fused = try_fuse;
         if (win_fused) hits_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
         k_gather_hits<<<1, 512, 0, s>>>(hs, hits, d_status, win_fused ? c->h_fin_dev + 31 : nullptr, hits_seq);
         cand.cap = kWinSubHits * wsize;
@@ -671,7 +677,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
         int wblocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)c->sm_count * 4);
         FinishArgs fin{};
-        if (c->coop && !fa.enabled) {
+        if (try_fuse) {
           wblocks = std::min(wblocks, coop_blocks((const void*)k_window_verify, &c->win_blocks_per_sm));
           if (wblocks < 1) return false;
           fin = make_fin(wblocks, cand.nsub);
@@ -701,7 +707,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
           cset.c[0] = carry_in;
           unsigned int* dense_flag = &d_status->dense;
           unsigned long long* work = ctr + 0;
-          if (c->coop && !fa.enabled) {
+          if (try_fuse) {
             // the scan grid finishes the job itself (see FinishFixed)
             fin = make_fin(blocks, cand.nsub);
             dense_flag = fin.sync + 4;
@@ -731,7 +737,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         cand.begin = c->sub_b.as<uint64_t>(); cand.end = c->sub_e.as<uint64_t>(); cand.count = c->sub_count.as<uint32_t>();
         int blocks = (int)std::min<uint64_t>((cand.nsub + 7) / 8, (uint64_t)grid_full);
         FinishArgs fin{};
-        if (c->coop && !fa.enabled) {
+        if (try_fuse) {
           blocks = std::min(blocks, coop_blocks((const void*)k_generic_scan, &c->gen_blocks_per_sm));
           if (blocks < 1) return false;
           fin = make_fin(blocks, cand.nsub);
@@ -788,6 +794,9 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         if (hr->seq0 != hits_seq) { if (error) *error = "rejit_b200: the hit stage did not report"; return false; }
         st.n_hits = hr->n_matches;
         if (hr->flags & kFinOverflow) { st.overflow = 1; st.need_cap = std::max(st.need_cap, (unsigned int)hr->need_cap); }
+      }
+      if (!st.overflow && !st.dense) {
+        if (st.need_large) { dp->fuse_misses++; dp->fuse_skips = 0; } else { dp->fuse_misses = 0; }
       }
       if (st.need_large && !st.overflow && !st.dense) {
         // neighbouring candidates overlap: the general resolve decides
@@ -1235,6 +1244,14 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
             }
           fprintf(stderr, "[fin trace] scan_end %llu..%llu  barrier_out %llu..%llu  copied %llu..%llu  last_in %llu  published %llu (ns)\n",
                   mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mx[3], mx[4]);
+          // the slowest copies
+          std::vector<std::pair<unsigned long long, int>> slow;
+          for (int b2 = 0; b2 < blocks; ++b2) slow.push_back({tr[(size_t)b2 * 5 + 2] - tr[(size_t)b2 * 5 + 1], b2});
+          std::sort(slow.begin(), slow.end());
+          fprintf(stderr, "[fin trace] copy time ns: median %llu; slowest:", slow[slow.size() / 2].first);
+          for (size_t q = 0; q < 6 && q < slow.size(); ++q)
+            fprintf(stderr, " cta%d=%llu", slow[slow.size() - 1 - q].second, slow[slow.size() - 1 - q].first);
+          fprintf(stderr, "\n");
         }
         bool overlap = false, clean = true;
         for (int j = 0; j < K; ++j) {
