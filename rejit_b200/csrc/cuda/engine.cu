@@ -1216,8 +1216,8 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         dense_flag = fin.sync + 4;
         static const bool want_trace = getenv("RJ_FIN_TRACE") != nullptr;
         if (want_trace) {
-          if (!c->fin_trace.Reserve((size_t)blocks * 5 * 8 + 8 * 8, error)) return -1;
-          cudaMemsetAsync(c->fin_trace.p, 0, (size_t)blocks * 5 * 8 + 64, s);
+          if (!c->fin_trace.Reserve((size_t)blocks * 8 * 8 + 8 * 8, error)) return -1;
+          cudaMemsetAsync(c->fin_trace.p, 0, (size_t)blocks * 8 * 8 + 64, s);
           fin.trace = c->fin_trace.as<unsigned long long>();
         }
         uint64_t n_arg = n, nsub_arg = nsub;
@@ -1230,14 +1230,14 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         for (int j = 0; j < K; ++j) c->h_set_status[j] = StatusFromRecord(c->h_fin[j], carries.c[j]);
         if (fin.trace) {
           // debugging aid: phase times of the in-kernel finish (ns, relative to the earliest scan end)
-          std::vector<unsigned long long> tr((size_t)blocks * 5);
+          std::vector<unsigned long long> tr((size_t)blocks * 8);
           cudaStreamSynchronize(s);
           cudaMemcpy(tr.data(), fin.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
           unsigned long long t0 = ~0ull, mx[5] = {0, 0, 0, 0, 0}, mn[5] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull};
-          for (int b2 = 0; b2 < blocks; ++b2) t0 = std::min(t0, tr[(size_t)b2 * 5]);
+          for (int b2 = 0; b2 < blocks; ++b2) t0 = std::min(t0, tr[(size_t)b2 * 8]);
           for (int b2 = 0; b2 < blocks; ++b2)
             for (int q = 0; q < 5; ++q) {
-              unsigned long long v = tr[(size_t)b2 * 5 + q];
+              unsigned long long v = tr[(size_t)b2 * 8 + q];
               if (!v) continue;
               mx[q] = std::max(mx[q], v - t0);
               mn[q] = std::min(mn[q], v - t0);
@@ -1246,12 +1246,26 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
                   mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mx[3], mx[4]);
           // the slowest copies
           std::vector<std::pair<unsigned long long, int>> slow;
-          for (int b2 = 0; b2 < blocks; ++b2) slow.push_back({tr[(size_t)b2 * 5 + 2] - tr[(size_t)b2 * 5 + 1], b2});
+          for (int b2 = 0; b2 < blocks; ++b2) slow.push_back({tr[(size_t)b2 * 8 + 2] - tr[(size_t)b2 * 8 + 1], b2});
           std::sort(slow.begin(), slow.end());
           fprintf(stderr, "[fin trace] copy time ns: median %llu; slowest:", slow[slow.size() / 2].first);
           for (size_t q = 0; q < 6 && q < slow.size(); ++q)
             fprintf(stderr, " cta%d=%llu", slow[slow.size() - 1 - q].second, slow[slow.size() - 1 - q].first);
           fprintf(stderr, "\n");
+          {
+            // medians of the three passes
+            std::vector<unsigned long long> p1, p2, p3;
+            for (int b2 = 0; b2 < blocks; ++b2) {
+              const unsigned long long* r = &tr[(size_t)b2 * 8];
+              if (!r[5] || !r[6]) continue;
+              p1.push_back(r[5] - r[1]); p2.push_back(r[6] - r[5]); p3.push_back(r[7] - r[6]);
+            }
+            if (!p1.empty()) {
+              std::sort(p1.begin(), p1.end()); std::sort(p2.begin(), p2.end()); std::sort(p3.begin(), p3.end());
+              fprintf(stderr, "[fin trace] pass medians ns: %llu %llu %llu  (max %llu %llu %llu)\n", p1[p1.size() / 2],
+                      p2[p2.size() / 2], p3[p3.size() / 2], p1.back(), p2.back(), p3.back());
+            }
+          }
         }
         bool overlap = false, clean = true;
         for (int j = 0; j < K; ++j) {

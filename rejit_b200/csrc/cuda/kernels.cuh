@@ -437,7 +437,7 @@ __device__ __forceinline__ void FinTrace(const FinishArgs& fin, int slot) {
   if (fin.trace && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    fin.trace[(size_t)blockIdx.x * 5 + slot] = t;
+    fin.trace[(size_t)blockIdx.x * 8 + slot] = t;
   }
 }
 
@@ -528,7 +528,9 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
     uint64_t* s_last = reinterpret_cast<uint64_t*>(scratch + sum_words + cell_words);
     uint64_t* s_at = s_last + items;
     uint64_t* s_prev = s_at + cells;
-    const bool fits = (uint64_t)sum_words + cell_words + 2ull * items + 4ull * cells <= scratch_words;
+    unsigned long long* s_ne = reinterpret_cast<unsigned long long*>(s_prev + cells);   // [K] last non-empty end
+    const bool fits = (uint64_t)sum_words + cell_words + 2ull * items + 4ull * cells + 2ull * K <= scratch_words;
+    if (fits) for (int j = threadIdx.x; j < K; j += blockDim.x) s_ne[j] = 0;
     if (!fits && threadIdx.x == 0) atomicOr(&fin.sync[2], kFinOverlap);      // the host resolves instead
     const bool usable = fits && !(flags0 & (kFinDense | kFinOverflow));
     // ---- pass 1: counts and last ends of every item ------------------------------
@@ -566,6 +568,7 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
       }
     }
     __syncthreads();
+    FinTrace(fin, 5);
     // ---- pass 2: where every sub-region's candidates go, and who precedes them ---
     for (uint32_t it = warp_in_cta, k = 0; it < items; it += nwarps, ++k) {
       const uint32_t j = it / nch, ci = it - j * nch;
@@ -624,58 +627,97 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
         s_at[cell] = pre + before + incl - c;
         s_prev[cell] = myprev;
       }
-      const uint64_t lastP = WarpMax64(P);
-      if (lane == 0 && lastP) atomicMax(&fin.last_end[j], (unsigned long long)(lastP - 1));
     }
     __syncthreads();
-    // ---- pass 3: the copy, one warp per non-empty sub-region, 128 candidates in flight
+    // the segment's last end per pattern: one global atomic per (CTA, pattern)
+    if (usable)
+      for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        uint64_t m2 = 0;
+        for (uint32_t c2 = 0; c2 < nch; ++c2) { const uint64_t q = s_last[j * nch + c2]; m2 = q > m2 ? q : m2; }
+        if (m2) atomicMax(&fin.last_end[j], (unsigned long long)(m2 - 1));
+      }
+    FinTrace(fin, 6);
+    // ---- pass 3: the copy.  Cells with at most 4 candidates: one LANE per cell (all
+    // loads of 32 cells in flight at once); larger cells: the whole warp per cell,
+    // 128 candidates in flight.
     if (usable) {
       bool bad = false;
-      uint64_t ne = 0;                          // last non-empty end seen by this lane
-      int ne_j = -1;
-      for (uint32_t cell = warp_in_cta; cell < cells; cell += nwarps) {
-        const uint32_t cs = s_cnt[cell];
-        if (cs == 0) continue;
-        const uint32_t j = cell / seg_len;
-        const uint64_t sub = sub0 + (cell - j * seg_len);
-        const uint64_t slot0 = ((uint64_t)j * nsub_pat + sub) * st.cap;
-        const unsigned long long ats = s_at[cell];
-        uint64_t carryP = s_prev[cell];
-        const Carry cin = carries[j];
-        ulonglong2* outp = reinterpret_cast<ulonglong2*>(fin.out_pairs + (uint64_t)j * 2 * fin.out_stride);
-        if (ne_j != (int)j) {
-          // (a warp's cells are visited in increasing pattern order: flush the previous pattern's maximum)
-          if (ne_j >= 0) { const uint64_t m2 = WarpMax64(ne); if (lane == 0 && m2) atomicMax(&fin.last_ne[ne_j], (unsigned long long)m2); }
-          ne = 0; ne_j = (int)j;
-        }
-        for (uint32_t i0 = 0; i0 < cs; i0 += 128) {
+      for (uint32_t base = warp_in_cta * 32; base < cells; base += nwarps * 32) {
+        const uint32_t cell = base + lane;
+        const uint32_t cs = cell < cells ? s_cnt[cell] : 0u;
+        if (cs > 0 && cs <= 4) {
+          const uint32_t j = cell / seg_len;
+          const uint64_t slot0 = ((uint64_t)j * nsub_pat + sub0 + (cell - j * seg_len)) * st.cap;
+          const unsigned long long ats = s_at[cell];
+          uint64_t P = s_prev[cell];
+          const Carry cin = carries[j];
+          ulonglong2* outp = reinterpret_cast<ulonglong2*>(fin.out_pairs + (uint64_t)j * 2 * fin.out_stride);
           uint64_t bb[4], ee[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const uint32_t i = i0 + u * 32 + lane;
-            bb[u] = (i < cs) ? __ldcg(&st.begin[slot0 + i]) : 0;
-            ee[u] = (i < cs) ? __ldcg(&st.end[slot0 + i]) : 0;
+            bb[u] = ((uint32_t)u < cs) ? __ldcg(&st.begin[slot0 + u]) : 0;
+            ee[u] = ((uint32_t)u < cs) ? __ldcg(&st.end[slot0 + u]) : 0;
           }
+          uint64_t ne = 0;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const uint32_t ib = i0 + u * 32;
-            if (ib >= cs) break;
-            const uint32_t i = ib + lane;
-            uint64_t Pp = __shfl_up_sync(kFullMask, ee[u] + 1, 1);
-            if (lane == 0) Pp = carryP;
-            if (i < cs) {
-              bad |= !FinTaken(bb[u], ee[u], Pp, cin);
+            if ((uint32_t)u < cs) {
+              bad |= !FinTaken(bb[u], ee[u], P, cin);
+              P = ee[u] + 1;
               if (ee[u] > bb[u]) ne = ee[u];
-              if (ats + i < fin.out_cap) outp[ats + i] = make_ulonglong2(bb[u] + fin.base_offset, ee[u] + fin.base_offset);
+              if (ats + u < fin.out_cap) outp[ats + u] = make_ulonglong2(bb[u] + fin.base_offset, ee[u] + fin.base_offset);
             }
-            const uint32_t nvalid = cs - ib > 32 ? 32u : cs - ib;
-            carryP = __shfl_sync(kFullMask, ee[u] + 1, nvalid - 1);
           }
+          if (ne) atomicMax(&s_ne[j], (unsigned long long)ne);
+        }
+        unsigned big = __ballot_sync(kFullMask, cs > 4);
+        while (big) {
+          const int src = __ffs(big) - 1;
+          big &= big - 1;
+          const uint32_t bcell = base + src;
+          const uint32_t bcs = __shfl_sync(kFullMask, cs, src);
+          const uint32_t j = bcell / seg_len;
+          const uint64_t slot0 = ((uint64_t)j * nsub_pat + sub0 + (bcell - j * seg_len)) * st.cap;
+          const unsigned long long ats = s_at[bcell];
+          uint64_t carryP = s_prev[bcell];
+          const Carry cin = carries[j];
+          ulonglong2* outp = reinterpret_cast<ulonglong2*>(fin.out_pairs + (uint64_t)j * 2 * fin.out_stride);
+          uint64_t ne = 0;
+          for (uint32_t i0 = 0; i0 < bcs; i0 += 128) {
+            uint64_t bb[4], ee[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t i = i0 + u * 32 + lane;
+              bb[u] = (i < bcs) ? __ldcg(&st.begin[slot0 + i]) : 0;
+              ee[u] = (i < bcs) ? __ldcg(&st.end[slot0 + i]) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t ib = i0 + u * 32;
+              if (ib >= bcs) break;
+              const uint32_t i = ib + lane;
+              uint64_t Pp = __shfl_up_sync(kFullMask, ee[u] + 1, 1);
+              if (lane == 0) Pp = carryP;
+              if (i < bcs) {
+                bad |= !FinTaken(bb[u], ee[u], Pp, cin);
+                if (ee[u] > bb[u]) ne = ee[u];
+                if (ats + i < fin.out_cap) outp[ats + i] = make_ulonglong2(bb[u] + fin.base_offset, ee[u] + fin.base_offset);
+              }
+              const uint32_t nvalid = bcs - ib > 32 ? 32u : bcs - ib;
+              carryP = __shfl_sync(kFullMask, ee[u] + 1, nvalid - 1);
+            }
+          }
+          ne = WarpMax64(ne);
+          if (lane == 0 && ne) atomicMax(&s_ne[j], (unsigned long long)ne);
         }
       }
-      if (ne_j >= 0) { const uint64_t m2 = WarpMax64(ne); if (lane == 0 && m2) atomicMax(&fin.last_ne[ne_j], (unsigned long long)m2); }
       if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(&fin.sync[2], kFinOverlap);
     }
+    FinTrace(fin, 7);
+    __syncthreads();
+    if (usable)
+      for (int j = threadIdx.x; j < K; j += blockDim.x)
+        if (s_ne[j]) atomicMax(&fin.last_ne[j], s_ne[j]);
     __syncthreads();
   }
   // the last WARP of the grid to get here publishes the records (every warp
@@ -692,7 +734,7 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
   if (fin.trace && lane == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    fin.trace[(size_t)blockIdx.x * 5 + 3] = t;
+    fin.trace[(size_t)blockIdx.x * 8 + 3] = t;
   }
   const unsigned int flags = __ldcg(&fin.sync[2]);
   const unsigned int need_cap = __ldcg(&fin.sync[3]);
@@ -711,7 +753,7 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
   if (fin.trace && lane == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    fin.trace[(size_t)blockIdx.x * 5 + 4] = t;
+    fin.trace[(size_t)blockIdx.x * 8 + 4] = t;
   }
 }
 
