@@ -50,7 +50,7 @@ EXPORTED = [
     "rejit_b200_pinned_free", "rejit_b200_copy_to_device", "rejit_b200_copy_from_device",
     "rejit_b200_flush_l2", "rejit_b200_match_all_device", "rejit_b200_match_all_device_slab", "rejit_b200_free",
     "rejit_b200_text_upload", "rejit_b200_text_free", "rejit_b200_match_all_text",
-    "rejit_b200_set_create", "rejit_b200_set_free", "rejit_b200_set_describe",
+    "rejit_b200_set_create", "rejit_b200_set_free", "rejit_b200_set_describe", "rejit_b200_set_kmer_tables",
     "rejit_b200_match_all_set_text", "rejit_b200_match_all_set_device", "rejit_b200_match_all_set_device_slab",
     "rejit_b200_replace_all", "rejit_b200_replace_all_text", "rejit_b200_text_length", "rejit_b200_text_download",
 ]
@@ -114,6 +114,8 @@ def lib():
     L.rejit_b200_set_create.restype = vp
     L.rejit_b200_set_free.argtypes = [vp]
     L.rejit_b200_set_describe.argtypes = [vp]
+    L.rejit_b200_set_kmer_tables.argtypes = [vp, vp, vp, vp]
+    L.rejit_b200_set_kmer_tables.restype = ctypes.c_int
     L.rejit_b200_set_describe.restype = cp
     L.rejit_b200_match_all_set_text.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(u64p),
                                                 ctypes.POINTER(Stats), cp, sz]
@@ -446,6 +448,16 @@ class RegejSet:
 
     def describe(self) -> str:
         return lib().rejit_b200_set_describe(self._set).decode("latin-1")
+
+    def kmer_tables(self):
+        """(info, bitmap, mask16) of the set's k-mer index as numpy arrays, or None
+        (rejit_b200_set_kmer_tables; tests emulate the kernel's arithmetic with it)."""
+        import numpy as np
+        info = np.zeros(14, dtype=np.uint32)
+        bitmap = np.zeros(8192, dtype=np.uint32)
+        mask16 = np.zeros(65536, dtype=np.uint32)
+        ok = lib().rejit_b200_set_kmer_tables(self._set, info.ctypes.data, bitmap.ctypes.data, mask16.ctypes.data)
+        return (info, bitmap, mask16) if ok else None
 
     def __del__(self):
         try:

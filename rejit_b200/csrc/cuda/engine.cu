@@ -97,7 +97,7 @@ class DeviceContext {
   Buffer fscratch;                    // label scratch for re-entrant patterns
   // fused pattern sets
   Buffer set_sub_b, set_sub_e, set_sub_count, set_dense_b, set_dense_e, set_reach, set_take, set_fin, set_slot,
-      set_out, set_status, set_counts;
+      set_out, set_status, set_counts, kmer_xchg;
   PipelineStatus* h_set_status = nullptr;      // pinned + mapped, 32 entries
   PipelineStatus* h_set_status_dev = nullptr;
   Buffer flush;
@@ -544,6 +544,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     RJ_TRY(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     RJ_TRY(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RJ_TRY(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    RJ_TRY(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmerSmemBytes));
     c->attr_done = true;
   }
   if (c->dense_cap == 0 && !c->ReserveDense(1u << 16, error)) return false;
@@ -1025,6 +1026,10 @@ int64_t MatchAllResident(int device, Program* prog, const uint8_t* d_text, uint6
 class DeviceSet {
  public:
   SetTables tb{};
+  KmerTables km{};
+  bool kmer = false;                  // k_set_kmer instead of k_set_tma (SetDfa::Kmer)
+  bool kmer_off = false;              // ... until hits were too dense for it twice in a row
+  int kmer_dense = 0;
   std::vector<void*> allocs;
   size_t fixed_smem = 0;
   uint32_t sub_cap = 16;
@@ -1052,6 +1057,7 @@ SetProgram* SetProgram::Create(const std::vector<Program*>& members) {
     sp->describe_ = "fused set: " + std::to_string(members.size()) + " patterns, one DFA of " +
                     std::to_string(sp->dfa_.n_states) + " states (+" + std::to_string(sp->dfa_.n_rows - sp->dfa_.n_states) +
                     " shadow rows) x " + std::to_string(sp->dfa_.n_classes) + " classes";
+    if (sp->dfa_.kmer.ok) sp->describe_ += "; k-mer index (2-bit codes, (byte >> " + std::to_string(sp->dfa_.kmer.shift) + ") & 3)";
   } else {
     sp->describe_ = "set of " + std::to_string(members.size()) + " patterns run one by one (not fusable)";
   }
@@ -1076,6 +1082,20 @@ DeviceSet* SetProgram::OnDevice(int device, std::string* error) {
     d->tb.first_accept = f.first_accept;
     d->tb.row_shift = f.row_shift;
     d->fixed_smem = f.t2.size() * 4 + f.accept_mask.size() * 4 + f.t1.size() * 2 + 16 + 3 * 256 + 8 * 32 + 512;
+    static const bool no_kmer = getenv("RJ_NO_KMER") != nullptr;
+    if (f.kmer.ok && !no_kmer) {
+      if (!d->Upload(f.kmer.bitmap.data(), f.kmer.bitmap.size(), &d->km.bitmap, error) ||
+          !d->Upload(f.kmer.mask16.data(), f.kmer.mask16.size(), &d->km.mask16, error)) { delete d; return nullptr; }
+      d->km.shift = f.kmer.shift;
+      d->km.field_mask = 0x03030303u << f.kmer.shift;
+      d->km.mult = 0x01041040u >> f.kmer.shift;
+      // a code without a live byte gets a byte that has ANOTHER code: never equal to a text byte with this code
+      d->km.canon = f.kmer.canon;
+      for (uint32_t cd = 0; cd < 4; ++cd)
+        if (!((f.kmer.canon_ok >> cd) & 1u)) d->km.canon |= ((((cd + 1) & 3u) << f.kmer.shift) & 0xFFu) << (8 * cd);
+      for (int v = 0; v <= 8; ++v) d->km.len_le[v] = f.kmer.len_le[v];
+      d->kmer = true;
+    }
     per_device_[device] = d;
   }
   return per_device_[device];
@@ -1125,8 +1145,128 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
       if (!Check(cudaFuncSetAttribute(k_resolve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallResolveMax * 16), "attr", error) ||
           !Check(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error) ||
           !Check(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "attr", error) ||
-          !Check(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error)) return -1;
+          !Check(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error) ||
+          !Check(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmerSmemBytes), "attr", error)) return -1;
       c->attr_done = true;
+    }
+    // what a finished call hands back (statuses in c->h_set_status, pairs in c->set_out)
+    auto deliver = [&](uint64_t per_cap, int strategy) -> int {
+      uint64_t total_m = 0, total_c = 0;
+      for (int j = 0; j < K; ++j) {
+        const PipelineStatus& h = c->h_set_status[j];
+        counts[j] = (int64_t)h.n_matches;
+        if (carry_out) { carry_out[j].cur = h.carry_cur; carry_out[j].tail = h.carry_tail; }
+        total_m += h.n_matches;
+        total_c += h.n_candidates;
+      }
+      if (stats) {
+        cudaEventRecord(c->ev[2], s);
+        cudaEventSynchronize(c->ev[2]);
+        cudaEventElapsedTime(&stats->scan_ms, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&stats->total_ms, c->ev[0], c->ev[2]);
+        stats->candidates = total_c;
+        stats->matches = total_m;
+        stats->strategy = strategy;
+      }
+      if (pairs) {
+        for (int j = 0; j < K; ++j) {
+          pairs[j] = static_cast<uint64_t*>(malloc(std::max<size_t>((size_t)counts[j] * 16, 8)));
+          if (counts[j] && !Check(cudaMemcpyAsync(pairs[j], c->set_out.as<uint64_t>() + (uint64_t)j * 2 * per_cap,
+                                                  (size_t)counts[j] * 16, cudaMemcpyDeviceToHost, s), "D2H", error)) return -1;
+        }
+        if (!Check(cudaStreamSynchronize(s), "sync", error)) return -1;
+      }
+      return 0;
+    };
+    // ---- k-mer index: one kernel, scan + finish (k_set_kmer) ---------------------------------------
+    if (ds->kmer && !ds->kmer_off && c->coop) {
+      ScanRange own{0, n + 1};
+      uint64_t base_offset = 0;
+      if (own_view) {
+        own.own_begin = std::min<uint64_t>(own_view->own_begin, n + 1);
+        own.own_end = std::min<uint64_t>(own_view->own_end, n + 1);
+        base_offset = own_view->base_offset;
+      }
+      const uint64_t n16 = (n + 15) & ~15ull;
+      const uint64_t row_lo = own.own_begin >> 9;
+      const uint64_t last_end = std::min<uint64_t>(n, own.own_end + 8);          // an owned match ends at most here
+      const uint64_t row_hi = std::max<uint64_t>(std::min<uint64_t>((last_end + 511) >> 9, (n16 + 511) >> 9), row_lo + 1);
+      const uint64_t rows = row_hi - row_lo;
+      const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 31) / 32, (uint64_t)c->sm_count));
+      const uint64_t rows_per_cta = (rows + blocks - 1) / blocks;
+      if (rows_per_cta <= kKmerMaxRows) {
+        for (int attempt = 0; attempt < 8; ++attempt) {
+          const uint64_t per_cap = ds->per_cap;
+          if (!c->set_out.Reserve(K * per_cap * 16, error)) return -1;
+          if (!c->kmer_xchg.p) {
+            if (!c->kmer_xchg.Reserve((size_t)c->sm_count * 32 * sizeof(KmerXchg), error) ||
+                !Check(cudaMemsetAsync(c->kmer_xchg.p, 0, (size_t)c->sm_count * 32 * sizeof(KmerXchg), s), "memset", error)) return -1;
+          }
+          KmerRun run{};
+          run.row_lo = row_lo;
+          run.rows_per_cta = (uint32_t)rows_per_cta;
+          run.rows_per_warp = (uint32_t)((rows_per_cta + 31) / 32);
+          run.xchg = c->kmer_xchg.as<KmerXchg>();
+          run.out_pairs = c->set_out.as<uint64_t>();
+          run.out_stride = per_cap;
+          run.out_cap = per_cap;
+          run.base_offset = base_offset;
+          run.host_records = c->h_fin_dev;
+          run.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+          static const bool want_trace = getenv("RJ_FIN_TRACE") != nullptr;
+          if (want_trace) {
+            if (!c->fin_trace.Reserve((size_t)blocks * 16 * 8 + 64, error)) return -1;
+            cudaMemsetAsync(c->fin_trace.p, 0, (size_t)blocks * 16 * 8 + 64, s);
+            run.trace = c->fin_trace.as<unsigned long long>();
+          }
+          CarrySet carries;
+          for (int j = 0; j < 32; ++j) carries.c[j] = (carry_in && j < K) ? carry_in[j] : Carry();
+          uint64_t n_arg = n;
+          if (stats) cudaEventRecord(c->ev[0], s);
+          void* kargs[] = {(void*)&d_text, (void*)&n_arg, (void*)&ds->tb, (void*)&ds->km, (void*)&own, (void*)&run, (void*)&carries};
+          if (!Check(cudaLaunchCooperativeKernel((const void*)k_set_kmer, dim3(blocks), dim3(kKmerThreads), kargs, kKmerSmemBytes, s),
+                     "cooperative launch", error)) return -1;
+          if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
+          if (!Check(cudaGetLastError(), "launch", error) || !WaitFinRecords(c, K, run.seq, error)) return -1;
+          bool redo = false, give_up = false, dense = false;
+          uint64_t need = 0;
+          for (int j = 0; j < K; ++j) {
+            c->h_set_status[j] = StatusFromRecord(c->h_fin[j], carries.c[j]);
+            const PipelineStatus& h = c->h_set_status[j];
+            if (h.overflow || h.dense || h.need_large) give_up = true;
+            if (h.dense) dense = true;
+            if (h.n_matches > per_cap) { need = std::max<uint64_t>(need, h.n_matches); redo = true; }
+          }
+          if (run.trace) {
+            // debugging aid: phase times (ns, relative to the earliest CTA start): min..max over the CTAs
+            std::vector<unsigned long long> tr((size_t)blocks * 16);
+            cudaStreamSynchronize(s);
+            cudaMemcpy(tr.data(), run.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
+            static const char* names[9] = {"start", "tables", "scanned", "compacted", "checked", "counted", "exchanged", "written", "reported"};
+            unsigned long long t0 = ~0ull;
+            for (int b2 = 0; b2 < blocks; ++b2) t0 = std::min(t0, tr[(size_t)b2 * 16]);
+            std::string line = "[kmer trace]";
+            for (int q = 0; q < 9; ++q) {
+              unsigned long long mn = ~0ull, mx = 0;
+              for (int b2 = 0; b2 < blocks; ++b2) {
+                const unsigned long long v = tr[(size_t)b2 * 16 + q];
+                if (!v) continue;
+                mx = std::max(mx, v - t0);
+                mn = std::min(mn, v - t0);
+              }
+              if (mx) line += " " + std::string(names[q]) + " " + std::to_string(mn) + ".." + std::to_string(mx);
+            }
+            fprintf(stderr, "%s (ns)\n", line.c_str());
+          }
+          if (!dense) ds->kmer_dense = 0;
+          if (give_up) {                                         // overlapping or too dense: the general path decides
+            if (dense && ++ds->kmer_dense >= 2) ds->kmer_off = true;
+            break;
+          }
+          if (redo) { ds->per_cap = need + need / 4 + 1024; if (stats) stats->reruns += 1; continue; }
+          return deliver(per_cap, 4);
+        }
+      }
     }
     int warps = (int)std::min<size_t>((c->smem_optin - ds->fixed_smem) / kDfaTileBytes, 18);
     if (const char* env = getenv("RJ_DFA_WARPS")) warps = std::max(4, std::min(warps, atoi(env)));
@@ -1301,32 +1441,7 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         if (stats) stats->reruns += 1;
         continue;
       }
-      uint64_t total_m = 0, total_c = 0;
-      for (int j = 0; j < K; ++j) {
-        const PipelineStatus& h = c->h_set_status[j];
-        counts[j] = (int64_t)h.n_matches;
-        if (carry_out) { carry_out[j].cur = h.carry_cur; carry_out[j].tail = h.carry_tail; }
-        total_m += h.n_matches;
-        total_c += h.n_candidates;
-      }
-      if (stats) {
-        cudaEventRecord(c->ev[2], s);
-        cudaEventSynchronize(c->ev[2]);
-        cudaEventElapsedTime(&stats->scan_ms, c->ev[0], c->ev[1]);
-        cudaEventElapsedTime(&stats->total_ms, c->ev[0], c->ev[2]);
-        stats->candidates = total_c;
-        stats->matches = total_m;
-        stats->strategy = 4;
-      }
-      if (pairs) {
-        for (int j = 0; j < K; ++j) {
-          pairs[j] = static_cast<uint64_t*>(malloc(std::max<size_t>((size_t)counts[j] * 16, 8)));
-          if (counts[j] && !Check(cudaMemcpyAsync(pairs[j], c->set_out.as<uint64_t>() + (uint64_t)j * 2 * per_cap,
-                                                  (size_t)counts[j] * 16, cudaMemcpyDeviceToHost, s), "D2H", error)) return -1;
-        }
-        if (!Check(cudaStreamSynchronize(s), "sync", error)) return -1;
-      }
-      return 0;
+      return deliver(per_cap, 4);
     }
     ds->dense_mode = true;
   }

@@ -1198,6 +1198,426 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
                                  (uint32_t)warps_per_cta * (kDfaTileBytes / 4));
 }
 
+// ===========================================================================
+// K2-kmer: the set scan for members of at most 8 bytes over at most four live
+// byte values (SetDfa::Kmer in host/automaton.h; the nine regex-dna variants of
+// sample/regexdna.cc:52-62).  "Does a member end at e" is a function of the
+// eight 2-bit codes before e, so there is no automaton state and no dependent
+// chain.
+//   scan     every CTA owns a contiguous segment of 512-byte rows, every warp a
+//            contiguous run of them.  A lane loads 16 bytes of a row (coalesced
+//            uint4, four rows in flight), packs them into 16 codes (one AND + one
+//            multiply per four bytes), takes the seven codes before them from its
+//            neighbour (shuffle) and looks the two ends after letters 2t, 2t+1 up
+//            in an 18-bit bitmap (32 KB of shared memory, staged by one TMA bulk
+//            copy): eight lookups, whose answers go, as one byte, into a byte
+//            array in shared memory that is indexed by position.  No branch, no
+//            atomic, nothing written to global memory.
+//   finish   (same CTA, no second kernel) the byte array is compacted in position
+//            order (block scan); every hit is checked exactly against the text (a
+//            byte whose code aliases a live byte is not that byte) and fanned out
+//            per member through a 65536-entry mask table (global, L2 resident);
+//            per-member indices by ballot + a prefix over the 32-candidate chunks.
+//   exchange every CTA publishes, per member, {count, first end, last end} as two
+//            16-byte records carrying the call's sequence number and waits for the
+//            CTAs before it (cooperative launch: all resident): this is the only
+//            grid-wide step.  It then writes its matches at their final place;
+//            the last CTA also checks the seams and reports to the host.
+// Candidates that overlap (or a carry reaching into the slab) raise kFinOverlap and
+// the host repeats the call with k_set_tma + the general resolve.
+// Algorithmic traffic: N bytes read (once for all members) + 16 bytes per match.
+// ===========================================================================
+struct KmerTables {
+  const uint32_t* bitmap;              // [8192]
+  const uint32_t* mask16;              // [65536]
+  uint32_t field_mask;                 // 0x03030303 << shift
+  uint32_t mult;                       // 0x01041040 >> shift: packs four fields into the top byte
+  uint32_t shift;
+  uint32_t canon;                      // byte c: the live byte with code c (or a byte with another code)
+  uint32_t len_le[9];
+};
+
+struct __align__(16) KmerXchg {        // one per (CTA, member); each half is one 16-byte store
+  unsigned long long first_end;
+  unsigned int count, seq0;
+  unsigned long long last_end;
+  unsigned int flags, seq1;
+};
+
+struct KmerRun {
+  uint64_t row_lo;                     // first 512-byte row that can hold an owned end
+  uint32_t rows_per_cta, rows_per_warp;
+  KmerXchg* xchg;                      // [gridDim.x][32]
+  uint64_t* out_pairs;                 // member j's pairs start at out_pairs + j * 2 * out_stride
+  uint64_t out_stride, out_cap, base_offset;
+  FinRecord* host_records;
+  unsigned int seq;
+  unsigned long long* trace;           // optional: 16 globaltimer stamps per CTA
+};
+
+constexpr uint32_t kKmerBitmapBytes = 32768;
+constexpr uint32_t kKmerThreads = 1024;
+constexpr uint32_t kKmerMaxRows = 2048;            // rows per CTA (1 MB of text): 64 hit bytes per thread
+constexpr uint32_t kKmerRawCap = 2048;             // hits per CTA
+constexpr uint32_t kKmerChunks = 2 * kKmerRawCap / 32;
+constexpr uint32_t kKmerSmemBytes = kKmerBitmapBytes + kKmerMaxRows * 32 + kKmerRawCap * 4 + 2 * kKmerRawCap * 4 +
+                                    kKmerChunks * 32 * 2 + 2048;
+
+__device__ __forceinline__ uint32_t KmerPack(const uint4& v, uint32_t fm, uint32_t mult) {
+  const uint32_t p0 = (v.x & fm) * mult, p1 = (v.y & fm) * mult, p2 = (v.z & fm) * mult, p3 = (v.w & fm) * mult;
+  return __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);
+}
+
+__device__ __forceinline__ void KmerTrace(const KmerRun& run, int slot) {
+  if (run.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    run.trace[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
+
+// the members that end at text offset e (exact): codes of the eight bytes before e,
+// how many of them, counted back from e, are live bytes, and the mask table
+__device__ __forceinline__ uint32_t KmerVerify(const uint8_t* __restrict__ text, uint64_t e, const KmerTables& km) {
+  uint32_t w0 = 0, w1 = 0;             // bytes e-8..e-5, e-4..e-1 (0 where the text has not begun)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t hi = (e >= (uint64_t)(4 - i)) ? __ldg(text + e - 4 + i) : 0u;
+    const uint32_t lo = (e >= (uint64_t)(8 - i)) ? __ldg(text + e - 8 + i) : 0u;
+    w1 |= hi << (8 * i);
+    w0 |= lo << (8 * i);
+  }
+  // rebuild the canonical bytes from the codes and compare
+  const uint32_t c0 = ((w0 & km.field_mask) * km.mult) >> 24, c1 = ((w1 & km.field_mask) * km.mult) >> 24;
+  uint32_t bad = 0;                    // bit i: byte e-8+i is not the live byte its code stands for
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t byte = ((i < 4 ? w0 : w1) >> (8 * (i & 3))) & 0xFFu;
+    const uint32_t code = ((i < 4 ? c0 : c1) >> (2 * (i & 3))) & 3u;
+    const bool before = e < (uint64_t)(8 - i);
+    if (before || ((km.canon >> (8 * code)) & 0xFFu) != byte) bad |= 1u << i;
+  }
+  const uint32_t v = bad ? (uint32_t)__clz(bad << 24) : 8u;          // valid bytes counted back from e
+  return __ldg(km.mask16 + (c0 | (c1 << 8))) & km.len_le[v];
+}
+
+__global__ void __launch_bounds__(kKmerThreads, 1)
+k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTables km, ScanRange range, KmerRun run,
+           CarrySet carries) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int K = tb.n_patterns;
+  // layout: [bitmap][hit bytes][raw hits u32][candidate masks u32][chunk counts u16][misc]
+  uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(smem_raw);
+  uint8_t* s_hit = smem_raw + kKmerBitmapBytes;
+  uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_hit + kKmerMaxRows * 32);
+  uint32_t* s_mask = s_raw + kKmerRawCap;
+  uint16_t* s_chunk = reinterpret_cast<uint16_t*>(s_mask + 2 * kKmerRawCap);          // [chunk][32]
+  uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_chunk + kKmerChunks * 32);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc);                              // 8 bytes
+  uint32_t* s_warp = s_misc + 2;                                                      // [32] block scan
+  uint32_t* s_total = s_misc + 34;                                                    // [0] raw hits, [1] flags
+  uint32_t* s_first = s_misc + 36;                                                    // [32] first candidate per member
+  uint32_t* s_last = s_first + 32;                                                    // [32] last candidate + 1
+  uint32_t* s_base = s_last + 32;                                                     // [32] matches of the CTAs before me
+  uint32_t* s_count = s_base + 32;                                                    // [32] my matches per member
+
+  if (threadIdx.x == 0) {
+    MbarInit(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    MbarExpectTx(s_bar, kKmerBitmapBytes);
+    TmaLoad1D(s_bitmap, km.bitmap, kKmerBitmapBytes, s_bar);
+  }
+  KmerTrace(run, 0);
+  if (threadIdx.x < 32) { s_first[threadIdx.x] = ~0u; s_last[threadIdx.x] = 0; s_base[threadIdx.x] = 0; s_count[threadIdx.x] = 0; }
+  if (threadIdx.x < 2) s_total[threadIdx.x] = 0;
+
+  // ---- scan --------------------------------------------------------------------
+  const uint64_t cta_row0 = run.row_lo + (uint64_t)blockIdx.x * run.rows_per_cta;
+  const uint64_t n16 = (n + 15) & ~15ull;                   // device texts are padded: whole groups can be read
+  const uint64_t total_rows = (n16 + 511) >> 9;
+  uint64_t cta_rows = 0;
+  if (cta_row0 < total_rows) cta_rows = total_rows - cta_row0 < run.rows_per_cta ? total_rows - cta_row0 : run.rows_per_cta;
+  const uint32_t w_row0 = (uint32_t)warp * run.rows_per_warp;
+  const uint32_t w_row1 = w_row0 + run.rows_per_warp < cta_rows ? w_row0 + run.rows_per_warp : (uint32_t)cta_rows;
+  const uint32_t fm = km.field_mask, mult = km.mult;
+  const uint32_t bm_base = SmemAddr(s_bitmap);
+  auto load_row = [&](uint32_t r) -> uint4 {
+    const uint64_t at = ((cta_row0 + r) << 9) + (uint64_t)lane * 16;
+    if (r < w_row1 && at < n16) return __ldg(reinterpret_cast<const uint4*>(text + at));
+    return make_uint4(0, 0, 0, 0);
+  };
+  uint4 v0 = load_row(w_row0), v1 = load_row(w_row0 + 1), v2 = load_row(w_row0 + 2), v3 = load_row(w_row0 + 3);
+  uint32_t prev31 = 0;                                      // codes of the 16 bytes before my first row
+  if (w_row0 < w_row1 && cta_row0 + w_row0 > 0)
+    prev31 = KmerPack(__ldg(reinterpret_cast<const uint4*>(text + ((cta_row0 + w_row0) << 9) - 16)), fm, mult);
+  __syncthreads();                                          // the barrier is initialised
+  MbarWait(s_bar, 0);
+  KmerTrace(run, 1);
+  for (uint32_t r = w_row0; r < w_row1; ++r) {
+    const uint32_t Q = KmerPack(v0, fm, mult);
+    v0 = v1; v1 = v2; v2 = v3;
+    v3 = load_row(r + 4);
+    uint32_t P = __shfl_up_sync(kFullMask, Q, 1);
+    if (lane == 0) P = prev31;
+    prev31 = __shfl_sync(kFullMask, Q, 31);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      // bits [16 + 4t, ...) of (Q:P): nine codes from bit 2 on = the ends after letters 2t and 2t+1
+      const uint32_t w = t < 4 ? __funnelshift_r(P, Q, 16 + 4 * t) : (Q >> (4 * t - 16));
+      const uint32_t word = Lds32(bm_base + (w & 0x7FFCu));
+      acc = __funnelshift_l(__funnelshift_l(0u, word, w >> 15), acc, 1);
+    }
+    s_hit[r * 32 + lane] = (uint8_t)acc;                    // bit 7 - t: lookup t
+  }
+  __syncthreads();
+  KmerTrace(run, 2);
+
+  // ---- finish: hits in position order --------------------------------------------
+  // thread i owns hit bytes [64 i, 64 i + 64) = rows 2i, 2i+1
+  uint4 hb[4];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    hb[q] = (2u * threadIdx.x + (q >> 1) < cta_rows) ? *reinterpret_cast<const uint4*>(s_hit + 64 * threadIdx.x + 16 * q)
+                                                     : make_uint4(0, 0, 0, 0);
+    mine += __popc(hb[q].x) + __popc(hb[q].y) + __popc(hb[q].z) + __popc(hb[q].w);
+  }
+  const uint32_t incl = WarpInclusiveScan(mine);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t wi = WarpInclusiveScan(s_warp[lane]);
+    s_warp[lane] = wi;
+    if (lane == 31) s_total[0] = wi;
+  }
+  __syncthreads();
+  const uint32_t n_raw = s_total[0];
+  unsigned int flags = 0;
+  if (n_raw > kKmerRawCap) flags |= kFinDense;
+  // my hits, by position: hit byte, then lookup (bit 7 first)
+  if (mine && n_raw <= kKmerRawCap) {
+    uint32_t at = incl - mine + (warp ? s_warp[warp - 1] : 0u);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const uint4 h = hb[q4];
+      if (h.x | h.y | h.z | h.w) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          // bit 8k + t = lookup t of hit byte k: ascending bits = ascending positions
+          uint32_t x = __byte_perm(__brev(k4 == 0 ? h.x : k4 == 1 ? h.y : k4 == 2 ? h.z : h.w), 0, 0x0123);
+          while (x) {
+            const uint32_t bit = __ffs(x) - 1;
+            x &= x - 1;
+            // first of the two ends, relative to the CTA's first byte
+            s_raw[at++] = (64u * threadIdx.x + 16u * q4 + 4u * k4 + (bit >> 3)) * 16u + 2u * (bit & 7u) + 1u;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  KmerTrace(run, 3);
+
+  // ---- exact check: candidate 2h, 2h+1 = the two ends of hit h ---------------------
+  const uint64_t cta_base = cta_row0 << 9;
+  const uint32_t n_cand = n_raw <= kKmerRawCap ? 2 * n_raw : 0;
+  for (uint32_t i = threadIdx.x; i < n_cand; i += kKmerThreads) {
+    const uint64_t e = cta_base + s_raw[i >> 1] + (i & 1u);
+    uint32_t m = 0;
+    if (e <= n) {
+      m = KmerVerify(text, e, km);
+      uint32_t keep = 0;
+      for (uint32_t mm = m; mm; mm &= mm - 1) {
+        const int j = __ffs(mm) - 1;
+        const uint64_t b = e - tb.match_len[j];
+        if (b >= range.own_begin && b < range.own_end) {
+          keep |= 1u << j;
+          if (b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
+        }
+      }
+      m = keep;
+    }
+    s_mask[i] = m;
+  }
+  __syncthreads();
+  KmerTrace(run, 4);
+  // per-member counts of every chunk of 32 candidates (lane j keeps member j's)
+  const uint32_t n_chunks = (n_cand + 31) / 32;
+  for (uint32_t ch = warp; ch < n_chunks; ch += kKmerThreads / 32) {
+    const uint32_t i = ch * 32 + lane;
+    const uint32_t m = i < n_cand ? s_mask[i] : 0u;
+    uint32_t cj = 0;
+    for (int j = 0; j < K; ++j) {
+      const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
+      if (lane == j && bal) {
+        cj = __popc(bal);
+        atomicMin(&s_first[j], ch * 32 + (uint32_t)__ffs(bal) - 1u);
+        atomicMax(&s_last[j], ch * 32 + 32u - (uint32_t)__clz(bal));
+      }
+    }
+    s_chunk[ch * 32 + lane] = (uint16_t)cj;
+    // a candidate overlaps an earlier one of the same member iff that one ends less than a match length before it
+    if (m) {
+      const uint64_t e = s_raw[i >> 1] + (i & 1u);
+      for (uint32_t d = 1; d <= 8 && d <= i; ++d) {
+        const uint32_t m2 = s_mask[i - d] & m;
+        if (!m2) continue;
+        const uint64_t e2 = s_raw[(i - d) >> 1] + ((i - d) & 1u);
+        for (uint32_t mm = m2; mm; mm &= mm - 1)
+          if (e2 + tb.match_len[__ffs(mm) - 1] > e) flags |= kFinOverlap;
+      }
+    }
+  }
+  __syncthreads();
+  // warp j: exclusive prefix of member j's chunk counts (in place), total -> s_count[j]
+  if (warp < K) {
+    uint32_t carry = 0;
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32) {
+      const uint32_t ch = c0 + lane;
+      const uint32_t c = ch < n_chunks ? s_chunk[ch * 32 + warp] : 0u;
+      const uint32_t inc = WarpInclusiveScan(c);
+      if (ch < n_chunks) s_chunk[ch * 32 + warp] = (uint16_t)(carry + inc - c);
+      carry += __shfl_sync(kFullMask, inc, 31);
+    }
+    if (lane == 0) s_count[warp] = carry;
+  }
+  if (flags) atomicOr(&s_total[1], flags);
+  __syncthreads();
+  KmerTrace(run, 5);
+
+  // ---- exchange ------------------------------------------------------------------
+  if (threadIdx.x < K) {
+    const int j = threadIdx.x;
+    const unsigned int c = s_count[j];
+    unsigned long long fe = 0, le = 0;
+    if (c) {
+      const uint32_t i0 = s_first[j], i1 = s_last[j] - 1;
+      fe = cta_base + s_raw[i0 >> 1] + (i0 & 1u);
+      le = cta_base + s_raw[i1 >> 1] + (i1 & 1u);
+    }
+    volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.xchg + (size_t)blockIdx.x * 32 + j);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)fe),
+                 "r"((unsigned int)(fe >> 32)), "r"(c), "r"(run.seq) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)le),
+                 "r"((unsigned int)(le >> 32)), "r"(s_total[1]), "r"(run.seq) : "memory");
+  }
+  const bool last_cta = blockIdx.x + 1 == gridDim.x;
+  // the CTAs before me: warp w reads CTA w, w + 32, ... (lane j = member j), five CTAs' records in flight
+  // at once.  The last CTA keeps what it reads (s_seam, in the hit-byte area) for the seam check below.
+  ulonglong2* s_seam = reinterpret_cast<ulonglong2*>(s_hit);            // [CTA][member] {first end, last end}
+  const bool seam_fits = (uint64_t)gridDim.x * K * sizeof(ulonglong2) <= (uint64_t)kKmerMaxRows * 32;
+  for (uint32_t c0 = warp; c0 < blockIdx.x; c0 += 160) {
+    uint4 a[5], b[5];
+    unsigned pending = 0;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      a[u] = b[u] = make_uint4(0, 0, 0, 0);
+      if (c0 + 32 * u < blockIdx.x && lane < K) pending |= 1u << u;
+    }
+    while (pending) {
+#pragma unroll
+      for (int u = 0; u < 5; ++u)
+        if ((pending >> u) & 1u) {
+          const volatile uint4* src = reinterpret_cast<const volatile uint4*>(run.xchg + (size_t)(c0 + 32 * u) * 32 + lane);
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w) : "l"(src) : "memory");
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b[u].x), "=r"(b[u].y), "=r"(b[u].z), "=r"(b[u].w) : "l"(src + 1) : "memory");
+        }
+#pragma unroll
+      for (int u = 0; u < 5; ++u)
+        if (((pending >> u) & 1u) && a[u].w == run.seq && b[u].w == run.seq) {
+          pending &= ~(1u << u);
+          sum += a[u].z;
+          if (last_cta) {
+            if (b[u].z) atomicOr(&s_total[1], b[u].z);
+            if (seam_fits)
+              s_seam[(size_t)(c0 + 32 * u) * K + lane] =
+                  make_ulonglong2(a[u].z ? ((unsigned long long)a[u].y << 32 | a[u].x) : 0ull,
+                                  a[u].z ? ((unsigned long long)b[u].y << 32 | b[u].x) : 0ull);
+          }
+        }
+    }
+    if (sum) atomicAdd(&s_base[lane], sum);
+  }
+  __syncthreads();
+  KmerTrace(run, 6);
+
+  // ---- my matches, at their final place ------------------------------------------
+  for (uint32_t ch = warp; ch < n_chunks; ch += kKmerThreads / 32) {
+    const uint32_t i = ch * 32 + lane;
+    const uint32_t m = i < n_cand ? s_mask[i] : 0u;
+    const uint64_t e = cta_base + (i < n_cand ? s_raw[i >> 1] + (i & 1u) : 0u);
+    for (int j = 0; j < K; ++j) {
+      const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
+      if ((m >> j) & 1u) {
+        const unsigned long long at = (unsigned long long)s_base[j] + s_chunk[ch * 32 + j] + __popc(bal & ((1u << lane) - 1u));
+        if (at < run.out_cap)
+          reinterpret_cast<ulonglong2*>(run.out_pairs + (uint64_t)j * 2 * run.out_stride)[at] =
+              make_ulonglong2(e - tb.match_len[j] + run.base_offset, e + run.base_offset);
+      }
+    }
+  }
+  KmerTrace(run, 7);
+  if (!last_cta) return;
+  // ---- the last CTA: seams between CTAs, totals, report ----------------------------
+  if (warp < K) {
+    const int j = warp;
+    unsigned long long prev_last = 0;
+    unsigned int bad = 0;
+    for (uint32_t c0 = 0; c0 < gridDim.x; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      unsigned long long fe = 0, le = 0;
+      unsigned int cnt = 0;
+      if (c + 1 < gridDim.x) {
+        if (seam_fits) {
+          const ulonglong2 fl = s_seam[(size_t)c * K + j];
+          fe = fl.x; le = fl.y; cnt = fl.y ? 1u : 0u;
+        } else {
+          const KmerXchg* x = run.xchg + (size_t)c * 32 + j;  // complete: the loop above saw both sequence numbers
+          fe = __ldcg(&x->first_end); le = __ldcg(&x->last_end); cnt = __ldcg(&x->count);
+        }
+      } else if (c + 1 == gridDim.x) {
+        cnt = s_count[j];
+        if (cnt) {
+          const uint32_t i0 = s_first[j], i1 = s_last[j] - 1;
+          fe = cta_base + s_raw[i0 >> 1] + (i0 & 1u);
+          le = cta_base + s_raw[i1 >> 1] + (i1 & 1u);
+        }
+      }
+      // last end among the CTAs before c (ends grow with c)
+      unsigned long long run_max = le;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(kFullMask, run_max, d);
+        if (lane >= d && o > run_max) run_max = o;
+      }
+      unsigned long long before = __shfl_up_sync(kFullMask, run_max, 1);
+      if (lane == 0) before = 0;
+      if (prev_last > before) before = prev_last;
+      if (cnt && before && fe - tb.match_len[j] < before) bad = 1;
+      const unsigned long long chunk_max = __shfl_sync(kFullMask, run_max, 31);
+      if (chunk_max > prev_last) prev_last = chunk_max;
+    }
+    bad = __any_sync(kFullMask, bad);
+    if (lane == 0) {
+      const unsigned long long total = (unsigned long long)s_base[j] + s_count[j];
+      unsigned int fl = s_total[1] | (bad ? kFinOverlap : 0u);
+      const unsigned long long le = prev_last;
+      volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.host_records + j);
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)total),
+                   "r"((unsigned int)(total >> 32)), "r"(fl), "r"(run.seq) : "memory");
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)le),
+                   "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"((unsigned int)le),
+                   "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
+    }
+  }
+  KmerTrace(run, 8);
+}
+
 // ---------------------------------------------------------------------------
 // K2 fallback: same automaton, 16-byte global loads, non-replicated table,
 // unordered append (dense matches / tables too large for k_dfa_tma).

@@ -437,6 +437,55 @@ bool BuildAutomaton(const LoweredRegexp& lr, CompiledAutomaton* out, std::string
   return true;
 }
 
+// See SetDfa::Kmer.  Replaces nothing in the reference: it is the set scan's
+// table for texts over a tiny alphabet (regex-dna, sample/regexdna.cc:52-62).
+static void BuildKmerIndex(SetDfa* out) {
+  SetDfa::Kmer& km = out->kmer;
+  km = SetDfa::Kmer();
+  if (out->max_len > 8) return;
+  const int C = out->n_classes;
+  // live bytes: some state moves somewhere else than where a byte no member knows leads
+  std::vector<int> live;
+  std::vector<char> class_live(C, 0);
+  for (int c = 0; c < C; ++c)
+    for (int s = 0; s < out->n_states && !class_live[c]; ++s)
+      if (out->next[static_cast<size_t>(s) * C + c] != 0) class_live[c] = 1;
+  int dead_byte = -1;
+  for (int b = 0; b < 256; ++b) {
+    if (class_live[out->byte_class[b]]) live.push_back(b); else if (dead_byte < 0) dead_byte = b;
+  }
+  if (live.empty() || live.size() > 4 || dead_byte < 0) return;
+  int shift = -1;
+  for (int s = 0; s <= 6 && shift < 0; ++s) {
+    uint32_t seen = 0;
+    bool distinct = true;
+    for (int b : live) { uint32_t c = (b >> s) & 3; if (seen >> c & 1) distinct = false; seen |= 1u << c; }
+    if (distinct) shift = s;
+  }
+  if (shift < 0) return;
+  km.shift = static_cast<uint32_t>(shift);
+  int canon[4] = {-1, -1, -1, -1};
+  for (int b : live) canon[(b >> shift) & 3] = b;
+  for (int c = 0; c < 4; ++c)
+    if (canon[c] >= 0) { km.canon |= static_cast<uint32_t>(canon[c]) << (8 * c); km.canon_ok |= 1u << c; }
+  for (int v = 0; v <= 8; ++v)
+    for (int j = 0; j < out->n_patterns; ++j) if (out->match_len[j] <= static_cast<uint32_t>(v)) km.len_le[v] |= 1u << j;
+  km.mask16.assign(65536, 0);
+  for (uint32_t x = 0; x < 65536; ++x) {
+    int st = 0;
+    for (int i = 0; i < 8; ++i) {
+      int code = (x >> (2 * i)) & 3;
+      int b = canon[code] >= 0 ? canon[code] : dead_byte;
+      st = out->next[static_cast<size_t>(st) * C + out->byte_class[b]];
+    }
+    km.mask16[x] = out->accept_mask[st];
+  }
+  km.bitmap.assign(8192, 0);
+  for (uint32_t x = 0; x < (1u << 18); ++x)
+    if (km.mask16[x & 0xFFFF] | km.mask16[x >> 2]) km.bitmap[x & 0x1FFF] |= 1u << (31 - (x >> 13));
+  km.ok = true;
+}
+
 bool BuildSetDfa(const std::vector<const CompiledAutomaton*>& members, SetDfa* out) {
   const int k = static_cast<int>(members.size());
   if (k < 2 || k > 32) return false;
@@ -571,6 +620,7 @@ bool BuildSetDfa(const std::vector<const CompiledAutomaton*>& members, SetDfa* o
       }
     }
   }
+  BuildKmerIndex(out);
   return true;
 }
 

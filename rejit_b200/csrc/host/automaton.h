@@ -109,6 +109,24 @@ struct SetDfa {
   std::vector<uint16_t> t1;              // [n_rows*C]   next state * C
   std::vector<uint32_t> t2;              // [n_rows][2^row_shift / 4]: (row after two bytes) << row_shift
   int row_shift = 0;                     // log2 of the padded row size in bytes
+  // k-mer index (k_set_kmer): when every member is at most 8 bytes long and the
+  // bytes any pattern position accepts ("live" bytes) are at most four values
+  // that (b >> shift) & 3 tells apart, "does a member end at e" depends only on
+  // the 2-bit codes of the eight bytes before e: no state, no dependent chain.
+  //   mask16[x]  x = eight codes, oldest in the low bits; bit j: member j accepts
+  //              the last match_len[j] letters of the (canonical) 8-mer
+  //   bitmap[w]  nine codes x18 (two consecutive ends at once): bit 31-(x18>>13) of
+  //              word x18 & 0x1FFF is set iff mask16[x18 & 0xFFFF] | mask16[x18 >> 2]
+  // A byte whose code aliases a live byte is weeded out by the exact check on a hit.
+  struct Kmer {
+    bool ok = false;
+    uint32_t shift = 0;
+    uint32_t canon = 0;                  // byte c: the live byte with code c
+    uint32_t canon_ok = 0;               // bit c: code c has a live byte
+    uint32_t len_le[9] = {0};            // bit j: match_len[j] <= v
+    std::vector<uint32_t> bitmap;        // [8192]
+    std::vector<uint32_t> mask16;        // [65536]
+  } kmer;
 };
 // Returns false when the set cannot be fused (a member is not a fixed-length
 // anchor-free DFA pattern, or the tables exceed the kernel's budget).

@@ -394,6 +394,19 @@ void rejit_b200_set_free(rejit_b200_set* set) {
 
 const char* rejit_b200_set_describe(const rejit_b200_set* set) { return set ? set->set->describe().c_str() : ""; }
 
+int rejit_b200_set_kmer_tables(const rejit_b200_set* set, uint32_t* info, uint32_t* bitmap, uint32_t* mask16) {
+  if (!set || !set->set->fused() || !set->set->dfa().kmer.ok) return 0;
+  const SetDfa::Kmer& km = set->set->dfa().kmer;
+  if (info) {
+    info[0] = km.shift; info[1] = km.canon; info[2] = km.canon_ok; info[3] = (uint32_t)set->set->dfa().n_patterns;
+    for (int v = 0; v <= 8; ++v) info[4 + v] = km.len_le[v];
+    info[13] = 0;
+  }
+  if (bitmap) memcpy(bitmap, km.bitmap.data(), km.bitmap.size() * 4);
+  if (mask16) memcpy(mask16, km.mask16.data(), km.mask16.size() * 4);
+  return 1;
+}
+
 int rejit_b200_match_all_set_device(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
                                     int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) {
   std::string error;

@@ -239,6 +239,39 @@ def test_fused_pattern_set(rj):
         got = rj.RegejSet(pats).match_all(t)
         for p, g in zip(pats, got):
             assert g == O.Oracle(p).match_all(t), (pats, p)
+    # five live bytes / a nine-byte member: no k-mer index, the union automaton scans (k_set_tma)
+    t = fuzzgen.rand_text(random.Random(5), "acgtn", 200000)
+    for pats in (["acgn", "ttgca", "a[ct]g"], ["acgtacgta", "ttg[ac]a"]):
+        rs2 = rj.RegejSet(pats)
+        assert rs2.describe().startswith("fused set") and "k-mer" not in rs2.describe(), rs2.describe()
+        for p, g in zip(pats, rs2.match_all(t)):
+            assert g == O.Oracle(p).match_all(t), (pats, p)
+    # k-mer index: aliases of live bytes (upper case, IUB codes), members cut by both text ends
+    rs = rj.RegejSet(W.DNA_PATTERNS)
+    assert "k-mer index" in rs.describe(), rs.describe()
+    for text in (b"ggtaaa" + data[:70000] + b"AGGGTAAA" + b"agggtaaB" + data[600000:700000] + b"agggtaaa" + b"tttaccc",
+                 b"agggtaaa", b"agggtaa", b"tttaccct" * 3000, data[590000:610000].upper() + b"cgggtaaa"):
+        for p, g in zip(W.DNA_PATTERNS, rs.match_all(text)):
+            assert g == O.Oracle(p).match_all(text), (p, len(text))
+    # the set call on slabs with carries
+    dt = rj.DeviceText(seq)
+    try:
+        exp = [len(O.Oracle(p).match_all(data)) for p in W.DNA_PATTERNS]
+        n = len(seq)
+        for k in (2, 5):
+            arr = rj.Carry * len(W.DNA_PATTERNS)
+            carry = arr(*[rj.Carry(0, 0xFFFFFFFFFFFFFFFF) for _ in W.DNA_PATTERNS])
+            total = [0] * len(W.DNA_PATTERNS)
+            for i in range(k):
+                lo = n * i // k
+                hi = n * (i + 1) // k if i + 1 < k else n + 1
+                nxt = arr()
+                cnts = rs.match_all_device(dt, own=(lo, hi), carry_in=carry, carry_out=nxt)
+                total = [a + b for a, b in zip(total, cnts)]
+                carry = nxt
+            assert total == exp, (k, total, exp)
+    finally:
+        dt.free()
 
 
 def test_fixed_length_finish_in_kernel_and_overlap_fallback(rj):

@@ -1,0 +1,129 @@
+"""The k-mer index of a fused pattern set (host/automaton.cc BuildKmerIndex) and
+the arithmetic k_set_kmer does with it, restated in numpy on the CPU: pack 16
+bytes into 2-bit codes with one AND + one multiply per word, look two
+consecutive ends up in the 18-bit bitmap, check a hit exactly against the
+bytes.  The candidate ends must equal every (overlapping) occurrence Python's
+`re` finds; the GPU tier (test_gpu_parity.py) checks the kernel itself against
+the oracle.  The patterns are the regex-dna variants of
+/root/reference/sample/regexdna.cc:52-62.
+"""
+import re
+
+import numpy as np
+import pytest
+
+import rejit_b200
+from rejit_b200 import workloads as W
+
+STREAM = 272          # kDfaStreamBytes
+GROUPS = 17
+
+
+def _pack(words, fm, mult):
+    """KmerPack: four little-endian words -> 16 codes (32 bits)."""
+    p = [((w & fm) * mult) & 0xFFFFFFFF for w in words]
+    return (p[0] >> 24) | ((p[1] >> 24) << 8) | ((p[2] >> 24) << 16) | ((p[3] >> 24) << 24)
+
+
+def emulate(kset, text: bytes, seed=0):
+    info, bitmap, mask16 = kset.kmer_tables()
+    shift, canon, canon_ok, K = int(info[0]), int(info[1]), int(info[2]), int(info[3])
+    len_le = [int(x) for x in info[4:13]]
+    lens = [len(re.sub(r"\[[^\]]*\]", "x", p.split("|")[0])) for p in kset.patterns]
+    fm = np.uint64((0x03030303 << shift) & 0xFFFFFFFF)
+    mult = np.uint64(0x01041040 >> shift)
+    n = len(text)
+    rng = np.random.RandomState(seed)
+    nstreams = (n + STREAM - 1) // STREAM
+    # what a lane sees: the 16 bytes before its sub-stream + the sub-stream; bytes
+    # outside the text are arbitrary (stale shared memory in the kernel)
+    buf = rng.randint(0, 256, size=16 + nstreams * STREAM + 16, dtype=np.uint8)
+    buf[16:16 + n] = np.frombuffer(text, dtype=np.uint8)
+    # adversarial garbage: bytes of the alphabet itself
+    alpha = np.frombuffer(b"acgtACGTBD", dtype=np.uint8)
+    buf[:16] = alpha[rng.randint(0, len(alpha), 16)]
+    buf[16 + n:] = alpha[rng.randint(0, len(alpha), len(buf) - 16 - n)]
+    idx = (np.arange(nstreams)[:, None] * STREAM + np.arange(16 + STREAM)[None, :])
+    lanes = buf[idx]                                            # [nstreams, 288]
+    words = lanes.reshape(nstreams, -1, 4).astype(np.uint64)
+    words = words[:, :, 0] | (words[:, :, 1] << np.uint64(8)) | (words[:, :, 2] << np.uint64(16)) | (words[:, :, 3] << np.uint64(24))
+    codes = [_pack([words[:, 4 * g + i] for i in range(4)], fm, mult) for g in range(GROUPS + 1)]
+    found = [[] for _ in range(K)]
+    a = np.arange(nstreams, dtype=np.int64) * STREAM
+    limit = np.minimum(a + STREAM, n)
+    for g in range(GROUPS):
+        P, Q = codes[g], codes[g + 1]
+        both = P | (Q << np.uint64(32))
+        for t in range(8):
+            w = (both >> np.uint64(16 + 4 * t)) & np.uint64(0xFFFFFFFF)
+            word = bitmap[((w & np.uint64(0x7FFC)) >> np.uint64(2)).astype(np.int64)].astype(np.uint64)
+            hit = ((word << ((w >> np.uint64(15)) & np.uint64(31))) >> np.uint64(31)) & np.uint64(1)
+            for s in np.nonzero(hit)[0]:
+                rel = 16 * g + 2 * t + 1
+                for r in (rel, rel + 1):
+                    e = int(a[s]) + r
+                    if e > limit[s]:
+                        continue
+                    x, v, run = 0, 0, True
+                    for i in range(8):
+                        byte = int(lanes[s, 16 + r - 1 - i])
+                        code = (byte >> shift) & 3
+                        ok = i < e and (canon_ok >> code) & 1 and ((canon >> (8 * code)) & 0xFF) == byte
+                        x |= code << (2 * (7 - i))
+                        run = run and bool(ok)
+                        v += run
+                    m = int(mask16[x]) & len_le[v]
+                    for j in range(K):
+                        if (m >> j) & 1:
+                            found[j].append((e - lens[j], e))
+    return [sorted(f) for f in found]
+
+
+def occurrences(pattern: str, text: bytes):
+    rx = re.compile(b"(?=(" + pattern.encode("latin-1") + b"))")
+    return [(m.start(1), m.end(1)) for m in rx.finditer(text)]
+
+
+class _Set(rejit_b200.RegejSet):
+    def __init__(self, patterns):
+        super().__init__(patterns)
+        self.patterns = list(patterns)
+
+
+def test_dna_set_has_a_kmer_index():
+    s = _Set(W.DNA_PATTERNS)
+    t = s.kmer_tables()
+    assert t is not None and "k-mer index" in s.describe()
+    info, bitmap, mask16 = t
+    assert int(info[0]) == 1                                  # (byte >> 1) & 3 separates a, c, g, t
+    assert bytes(int(info[1]).to_bytes(4, "little")) == b"actg"
+    # 2 + 8 * 6 distinct 8-mers are accepted by some member
+    assert int(np.count_nonzero(mask16)) == 50
+
+
+@pytest.mark.parametrize("n,seed", [(3000, 1), (20000, 2)])
+def test_kmer_arithmetic_finds_every_occurrence(n, seed):
+    s = _Set(W.DNA_PATTERNS)
+    text = W.fasta_sequence(n).tobytes()
+    # make the aliases bite: upper-case copies of real hits, hits cut by the text end and start
+    text = b"ggtaaa" + text[:5000] + b"AGGGTAAA" + b"agggtaaB" + text[5000:] + b"agggtaaa" + b"tttaccc"
+    got = emulate(s, text, seed)
+    for j, p in enumerate(W.DNA_PATTERNS):
+        assert got[j] == occurrences(p, text), p
+
+
+def test_short_members_and_few_live_bytes():
+    pats = ["ab", "b[ab]a", "abba|baab"]
+    s = _Set(pats)
+    assert s.kmer_tables() is not None
+    rng = np.random.RandomState(3)
+    text = bytes(rng.choice(np.frombuffer(b"abab ABc", dtype=np.uint8), 5000))
+    got = emulate(s, text, 4)
+    for j, p in enumerate(pats):
+        assert got[j] == occurrences(p, text), p
+
+
+def test_sets_without_a_kmer_index():
+    assert _Set(["abcde", "edcba"]).kmer_tables() is None          # five live bytes
+    assert _Set(["aaaaaaaaa", "ccccccccc"]).kmer_tables() is None  # nine bytes long
+    assert _Set(["a[bB]", "ba"]).kmer_tables() is None             # no two adjacent bits tell a, b, B apart
