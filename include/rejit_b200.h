@@ -182,8 +182,9 @@ const char* rejit_b200_set_describe(const rejit_b200_set* set);
 /* Inspection (tests): the k-mer index of a fused set whose members are at most 8
  * bytes long over at most four live byte values (the table k_set_kmer scans
  * with).  Returns 1 and fills info[0..13] = {shift, canon, canon_ok, n_members,
- * match_len-independent len_le[0..8], reserved}, bitmap[8192], mask16[65536]
- * (any of them may be NULL); 0 when the set has no such index.                   */
+ * len_le[0..8], R}, bitmap[2^(2 (7 + R) - 5)] (at most 32768 words), mask16[65536]
+ * (any of them may be NULL); 0 when the set has no such index.  R = ends answered
+ * by one bitmap lookup.                                                           */
 int rejit_b200_set_kmer_tables(const rejit_b200_set* set, uint32_t* info, uint32_t* bitmap, uint32_t* mask16);
 int rejit_b200_match_all_set_text(rejit_b200_set* set, const rejit_b200_text* text, int64_t* out_counts,
                                   uint64_t** out_pairs, rejit_b200_stats* stats, char* err, size_t err_length);

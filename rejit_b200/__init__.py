@@ -454,10 +454,12 @@ class RegejSet:
         (rejit_b200_set_kmer_tables; tests emulate the kernel's arithmetic with it)."""
         import numpy as np
         info = np.zeros(14, dtype=np.uint32)
-        bitmap = np.zeros(8192, dtype=np.uint32)
+        bitmap = np.zeros(32768, dtype=np.uint32)
         mask16 = np.zeros(65536, dtype=np.uint32)
         ok = lib().rejit_b200_set_kmer_tables(self._set, info.ctypes.data, bitmap.ctypes.data, mask16.ctypes.data)
-        return (info, bitmap, mask16) if ok else None
+        if not ok:
+            return None
+        return info, bitmap[:1 << (2 * (7 + int(info[13])) - 5)], mask16
 
     def __del__(self):
         try:

@@ -544,7 +544,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     RJ_TRY(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     RJ_TRY(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RJ_TRY(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-    RJ_TRY(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmerSmemBytes));
+    RJ_TRY(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     c->attr_done = true;
   }
   if (c->dense_cap == 0 && !c->ReserveDense(1u << 16, error)) return false;
@@ -1146,7 +1146,7 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           !Check(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error) ||
           !Check(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "attr", error) ||
           !Check(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error) ||
-          !Check(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKmerSmemBytes), "attr", error)) return -1;
+          !Check(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error)) return -1;
       c->attr_done = true;
     }
     // what a finished call hands back (statuses in c->h_set_status, pairs in c->set_out)
@@ -1192,9 +1192,10 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
       const uint64_t last_end = std::min<uint64_t>(n, own.own_end + 8);          // an owned match ends at most here
       const uint64_t row_hi = std::max<uint64_t>(std::min<uint64_t>((last_end + 511) >> 9, (n16 + 511) >> 9), row_lo + 1);
       const uint64_t rows = row_hi - row_lo;
-      const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 31) / 32, (uint64_t)c->sm_count));
+      const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 31) / 32, std::min<uint64_t>(c->sm_count, kKmerMaxGrid)));
+      const size_t kmer_smem = kKmerSmemFixed + (size_t)kKmerMaxGrid * K * 8;
       const uint64_t rows_per_cta = (rows + blocks - 1) / blocks;
-      if (rows_per_cta <= kKmerMaxRows) {
+      if (rows_per_cta <= kKmerMaxRows && kmer_smem <= c->smem_optin) {
         for (int attempt = 0; attempt < 8; ++attempt) {
           const uint64_t per_cap = ds->per_cap;
           if (!c->set_out.Reserve(K * per_cap * 16, error)) return -1;
@@ -1214,6 +1215,8 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           run.host_records = c->h_fin_dev;
           run.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
           static const bool want_trace = getenv("RJ_FIN_TRACE") != nullptr;
+          static const int debug_stop = getenv("RJ_KMER_STOP") ? atoi(getenv("RJ_KMER_STOP")) : 0;
+          run.debug_stop = debug_stop;
           if (want_trace) {
             if (!c->fin_trace.Reserve((size_t)blocks * 16 * 8 + 64, error)) return -1;
             cudaMemsetAsync(c->fin_trace.p, 0, (size_t)blocks * 16 * 8 + 64, s);
@@ -1224,9 +1227,15 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           uint64_t n_arg = n;
           if (stats) cudaEventRecord(c->ev[0], s);
           void* kargs[] = {(void*)&d_text, (void*)&n_arg, (void*)&ds->tb, (void*)&ds->km, (void*)&own, (void*)&run, (void*)&carries};
-          if (!Check(cudaLaunchCooperativeKernel((const void*)k_set_kmer, dim3(blocks), dim3(kKmerThreads), kargs, kKmerSmemBytes, s),
+          if (!Check(cudaLaunchCooperativeKernel((const void*)k_set_kmer, dim3(blocks), dim3(kKmerThreads), kargs, kmer_smem, s),
                      "cooperative launch", error)) return -1;
           if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
+          if (debug_stop) {                                    // timing only: nothing was reported
+            cudaStreamSynchronize(s);
+            if (stats) { cudaEventRecord(c->ev[2], s); cudaEventSynchronize(c->ev[2]); cudaEventElapsedTime(&stats->scan_ms, c->ev[0], c->ev[1]); stats->total_ms = stats->scan_ms; }
+            for (int j = 0; j < K; ++j) counts[j] = 0;
+            return 0;
+          }
           if (!Check(cudaGetLastError(), "launch", error) || !WaitFinRecords(c, K, run.seq, error)) return -1;
           bool redo = false, give_up = false, dense = false;
           uint64_t need = 0;
@@ -1242,19 +1251,27 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
             std::vector<unsigned long long> tr((size_t)blocks * 16);
             cudaStreamSynchronize(s);
             cudaMemcpy(tr.data(), run.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
-            static const char* names[9] = {"start", "tables", "scanned", "compacted", "checked", "counted", "exchanged", "written", "reported"};
+            static const char* names[9] = {"start", "tables", "scanned(warp 0)", "checked", "published", "exchanged", "written", "reported", ""};
             unsigned long long t0 = ~0ull;
             for (int b2 = 0; b2 < blocks; ++b2) t0 = std::min(t0, tr[(size_t)b2 * 16]);
             std::string line = "[kmer trace]";
-            for (int q = 0; q < 9; ++q) {
+            for (int q = 0; q < 8; ++q) {
               unsigned long long mn = ~0ull, mx = 0;
+              std::vector<std::pair<unsigned long long, int>> dur;      // time since the phase before, per CTA
               for (int b2 = 0; b2 < blocks; ++b2) {
                 const unsigned long long v = tr[(size_t)b2 * 16 + q];
                 if (!v) continue;
                 mx = std::max(mx, v - t0);
                 mn = std::min(mn, v - t0);
+                if (q > 0 && tr[(size_t)b2 * 16 + q - 1]) dur.push_back({v - tr[(size_t)b2 * 16 + q - 1], b2});
               }
-              if (mx) line += " " + std::string(names[q]) + " " + std::to_string(mn) + ".." + std::to_string(mx);
+              if (!mx) continue;
+              line += " | " + std::string(names[q]) + " " + std::to_string(mn) + ".." + std::to_string(mx);
+              if (!dur.empty()) {
+                std::sort(dur.begin(), dur.end());
+                line += " (+" + std::to_string(dur[dur.size() / 2].first) + " med, +" + std::to_string(dur.back().first) +
+                        " cta" + std::to_string(dur.back().second) + ")";
+              }
             }
             fprintf(stderr, "%s (ns)\n", line.c_str());
           }

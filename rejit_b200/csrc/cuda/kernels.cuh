@@ -1228,7 +1228,7 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
 // Algorithmic traffic: N bytes read (once for all members) + 16 bytes per match.
 // ===========================================================================
 struct KmerTables {
-  const uint32_t* bitmap;              // [8192]
+  const uint32_t* bitmap;              // [2^(kIdxBits - 5)]
   const uint32_t* mask16;              // [65536]
   uint32_t field_mask;                 // 0x03030303 << shift
   uint32_t mult;                       // 0x01041040 >> shift: packs four fields into the top byte
@@ -1253,15 +1253,25 @@ struct KmerRun {
   FinRecord* host_records;
   unsigned int seq;
   unsigned long long* trace;           // optional: 16 globaltimer stamps per CTA
+  int debug_stop;                      // tuning aid (RJ_KMER_STOP): leave after phase n (results are then invalid)
 };
 
-constexpr uint32_t kKmerBitmapBytes = 32768;
+// R consecutive ends per lookup: a window of 7 + R codes indexes the bitmap
+constexpr int kKmerEnds = kKmerR;                                   // host/automaton.h
+constexpr int kKmerTests = (16 + kKmerEnds - 1) / kKmerEnds;        // lookups per 16-byte group
+constexpr int kKmerIdxBits = 2 * (7 + kKmerEnds);
+constexpr int kKmerWordBits = kKmerIdxBits - 5;
+constexpr uint32_t kKmerBitmapBytes = 4u << kKmerWordBits;          // 32 KB (R = 2), 128 KB (R = 3)
 constexpr uint32_t kKmerThreads = 1024;
-constexpr uint32_t kKmerMaxRows = 2048;            // rows per CTA (1 MB of text): 64 hit bytes per thread
-constexpr uint32_t kKmerRawCap = 2048;             // hits per CTA
-constexpr uint32_t kKmerChunks = 2 * kKmerRawCap / 32;
-constexpr uint32_t kKmerSmemBytes = kKmerBitmapBytes + kKmerMaxRows * 32 + kKmerRawCap * 4 + 2 * kKmerRawCap * 4 +
-                                    kKmerChunks * 32 * 2 + 2048;
+constexpr uint32_t kKmerWarps = kKmerThreads / 32;
+constexpr uint32_t kKmerMaxRows = 1024;            // rows per CTA (512 KB of text: 16 KB per warp against kKmerWarpRaw)
+constexpr uint32_t kKmerWarpRaw = 64;              // hits per warp (its run of rows)
+constexpr uint32_t kKmerMaxGrid = 160;             // five CTAs per lane in the seam check
+// dynamic shared memory: fixed part + the last CTA's seam table (kKmerMaxGrid x K x 8 bytes)
+constexpr uint32_t kKmerSmemFixed = kKmerBitmapBytes + kKmerWarps * kKmerWarpRaw * 4 * (2 + kKmerEnds) +
+                                    4 * kKmerWarps * 32 * 4 + 512;
+// first letter (0..15) of the ends lookup t answers: x, x+1, .., x+R-1; the last lookup is pulled back into the group
+__host__ __device__ constexpr int KmerTestX(int t) { return t * kKmerEnds < 16 - kKmerEnds ? t * kKmerEnds : 16 - kKmerEnds; }
 
 __device__ __forceinline__ uint32_t KmerPack(const uint4& v, uint32_t fm, uint32_t mult) {
   const uint32_t p0 = (v.x & fm) * mult, p1 = (v.y & fm) * mult, p2 = (v.z & fm) * mult, p3 = (v.w & fm) * mult;
@@ -1276,255 +1286,247 @@ __device__ __forceinline__ void KmerTrace(const KmerRun& run, int slot) {
   }
 }
 
-// the members that end at text offset e (exact): codes of the eight bytes before e,
-// how many of them, counted back from e, are live bytes, and the mask table
-__device__ __forceinline__ uint32_t KmerVerify(const uint8_t* __restrict__ text, uint64_t e, const KmerTables& km) {
-  uint32_t w0 = 0, w1 = 0;             // bytes e-8..e-5, e-4..e-1 (0 where the text has not begun)
+// The members that end at text offset e (exact), given the codes x16 of the eight bytes before e: the mask table
+// entry, cut to the members no longer than the run of live bytes that ends at e.  The nine loads do not depend on
+// each other: one round trip to L2.
+__device__ __forceinline__ uint32_t KmerVerify(const uint8_t* __restrict__ text, uint64_t e, uint32_t x16,
+                                               const KmerTables& km) {
+  const uint32_t members = __ldg(km.mask16 + x16);
+  uint32_t byte[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t hi = (e >= (uint64_t)(4 - i)) ? __ldg(text + e - 4 + i) : 0u;
-    const uint32_t lo = (e >= (uint64_t)(8 - i)) ? __ldg(text + e - 8 + i) : 0u;
-    w1 |= hi << (8 * i);
-    w0 |= lo << (8 * i);
-  }
-  // rebuild the canonical bytes from the codes and compare
-  const uint32_t c0 = ((w0 & km.field_mask) * km.mult) >> 24, c1 = ((w1 & km.field_mask) * km.mult) >> 24;
+  for (int i = 0; i < 8; ++i) byte[i] = (e >= (uint64_t)(8 - i)) ? __ldg(text + e - 8 + i) : 0x100u;   // text[e-8+i]
   uint32_t bad = 0;                    // bit i: byte e-8+i is not the live byte its code stands for
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const uint32_t byte = ((i < 4 ? w0 : w1) >> (8 * (i & 3))) & 0xFFu;
-    const uint32_t code = ((i < 4 ? c0 : c1) >> (2 * (i & 3))) & 3u;
-    const bool before = e < (uint64_t)(8 - i);
-    if (before || ((km.canon >> (8 * code)) & 0xFFu) != byte) bad |= 1u << i;
+    const uint32_t code = (x16 >> (2 * i)) & 3u;
+    if (((km.canon >> (8 * code)) & 0xFFu) != byte[i]) bad |= 1u << i;
   }
-  const uint32_t v = bad ? (uint32_t)__clz(bad << 24) : 8u;          // valid bytes counted back from e
-  return __ldg(km.mask16 + (c0 | (c1 << 8))) & km.len_le[v];
+  const uint32_t v = bad ? (uint32_t)__clz(bad << 24) : 8u;          // live bytes counted back from e
+  return members & km.len_le[v];
 }
 
 __global__ void __launch_bounds__(kKmerThreads, 1)
 k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTables km, ScanRange range, KmerRun run,
            CarrySet carries) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int R = kKmerEnds;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int K = tb.n_patterns;
-  // layout: [bitmap][hit bytes][raw hits u32][candidate masks u32][chunk counts u16][misc]
+  // layout: [bitmap][per warp: hits u32 [64], their window codes u32 [64], candidate masks u32 [64 R]]
+  //         [per warp and member: count, offset, first end, last end u32 [warp][32]][misc][seam table (last CTA)]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(smem_raw);
-  uint8_t* s_hit = smem_raw + kKmerBitmapBytes;
-  uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_hit + kKmerMaxRows * 32);
-  uint32_t* s_mask = s_raw + kKmerRawCap;
-  uint16_t* s_chunk = reinterpret_cast<uint16_t*>(s_mask + 2 * kKmerRawCap);          // [chunk][32]
-  uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_chunk + kKmerChunks * 32);
+  uint32_t* s_raw = s_bitmap + kKmerBitmapBytes / 4;
+  uint32_t* s_idx = s_raw + kKmerWarps * kKmerWarpRaw;
+  uint32_t* s_mask = s_idx + kKmerWarps * kKmerWarpRaw;
+  uint32_t* s_wcnt = s_mask + kKmerWarps * kKmerWarpRaw * R;
+  uint32_t* s_woff = s_wcnt + kKmerWarps * 32;
+  uint32_t* s_wfirst = s_woff + kKmerWarps * 32;
+  uint32_t* s_wlast = s_wfirst + kKmerWarps * 32;
+  uint32_t* s_misc = s_wlast + kKmerWarps * 32;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc);                              // 8 bytes
-  uint32_t* s_warp = s_misc + 2;                                                      // [32] block scan
-  uint32_t* s_total = s_misc + 34;                                                    // [0] raw hits, [1] flags
-  uint32_t* s_first = s_misc + 36;                                                    // [32] first candidate per member
-  uint32_t* s_last = s_first + 32;                                                    // [32] last candidate + 1
-  uint32_t* s_base = s_last + 32;                                                     // [32] matches of the CTAs before me
+  uint32_t* s_flags = s_misc + 2;
+  uint32_t* s_base = s_misc + 4;                                                      // [32] matches of the CTAs before me
   uint32_t* s_count = s_base + 32;                                                    // [32] my matches per member
+  uint2* s_seam = reinterpret_cast<uint2*>(s_misc + 128);                             // [CTA][K] {first, last} end - seam_base
 
+  KmerTrace(run, 0);
   if (threadIdx.x == 0) {
     MbarInit(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     MbarExpectTx(s_bar, kKmerBitmapBytes);
     TmaLoad1D(s_bitmap, km.bitmap, kKmerBitmapBytes, s_bar);
+    *s_flags = 0;
   }
-  KmerTrace(run, 0);
-  if (threadIdx.x < 32) { s_first[threadIdx.x] = ~0u; s_last[threadIdx.x] = 0; s_base[threadIdx.x] = 0; s_count[threadIdx.x] = 0; }
-  if (threadIdx.x < 2) s_total[threadIdx.x] = 0;
+  if (threadIdx.x < 32) { s_base[threadIdx.x] = 0; s_count[threadIdx.x] = 0; }
 
   // ---- scan --------------------------------------------------------------------
+  const uint64_t seam_base = run.row_lo << 9;
   const uint64_t cta_row0 = run.row_lo + (uint64_t)blockIdx.x * run.rows_per_cta;
+  const uint64_t cta_base = cta_row0 << 9;
   const uint64_t n16 = (n + 15) & ~15ull;                   // device texts are padded: whole groups can be read
   const uint64_t total_rows = (n16 + 511) >> 9;
-  uint64_t cta_rows = 0;
-  if (cta_row0 < total_rows) cta_rows = total_rows - cta_row0 < run.rows_per_cta ? total_rows - cta_row0 : run.rows_per_cta;
+  uint32_t cta_rows = 0;
+  if (cta_row0 < total_rows)
+    cta_rows = total_rows - cta_row0 < run.rows_per_cta ? (uint32_t)(total_rows - cta_row0) : run.rows_per_cta;
   const uint32_t w_row0 = (uint32_t)warp * run.rows_per_warp;
-  const uint32_t w_row1 = w_row0 + run.rows_per_warp < cta_rows ? w_row0 + run.rows_per_warp : (uint32_t)cta_rows;
+  const uint32_t w_row1 = w_row0 + run.rows_per_warp < cta_rows ? w_row0 + run.rows_per_warp : cta_rows;
+  // rows [w_row0, w_load1) have my 16 bytes inside the text (only the text's last row can be cut)
+  uint32_t w_load1 = w_row1;
+  if (w_row1 > w_row0 && cta_base + ((uint64_t)(w_row1 - 1) << 9) + (uint64_t)lane * 16 >= n16) w_load1 = w_row1 - 1;
   const uint32_t fm = km.field_mask, mult = km.mult;
   const uint32_t bm_base = SmemAddr(s_bitmap);
-  auto load_row = [&](uint32_t r) -> uint4 {
-    const uint64_t at = ((cta_row0 + r) << 9) + (uint64_t)lane * 16;
-    if (r < w_row1 && at < n16) return __ldg(reinterpret_cast<const uint4*>(text + at));
-    return make_uint4(0, 0, 0, 0);
-  };
-  uint4 v0 = load_row(w_row0), v1 = load_row(w_row0 + 1), v2 = load_row(w_row0 + 2), v3 = load_row(w_row0 + 3);
-  uint32_t prev31 = 0;                                      // codes of the 16 bytes before my first row
+  const uint4* src = reinterpret_cast<const uint4*>(text + cta_base + ((uint64_t)w_row0 << 9)) + lane;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  uint4 v0 = w_row0 < w_load1 ? __ldg(src) : zero4;
+  uint4 v1 = w_row0 + 1 < w_load1 ? __ldg(src + 32) : zero4;
+  uint4 v2 = w_row0 + 2 < w_load1 ? __ldg(src + 64) : zero4;
+  uint4 v3 = w_row0 + 3 < w_load1 ? __ldg(src + 96) : zero4;
+  src += 128;
+  uint32_t prevQ = 0;                                       // lane 31: codes of the 16 bytes before the row
   if (w_row0 < w_row1 && cta_row0 + w_row0 > 0)
-    prev31 = KmerPack(__ldg(reinterpret_cast<const uint4*>(text + ((cta_row0 + w_row0) << 9) - 16)), fm, mult);
+    prevQ = KmerPack(__ldg(reinterpret_cast<const uint4*>(text + cta_base + ((uint64_t)w_row0 << 9) - 16)), fm, mult);
+  uint32_t* my_raw = s_raw + warp * kKmerWarpRaw;
+  uint32_t* my_idx = s_idx + warp * kKmerWarpRaw;
+  uint32_t n_raw = 0;                                       // hits of my warp so far (uniform)
+  const int from = (lane + 31) & 31;
   __syncthreads();                                          // the barrier is initialised
   MbarWait(s_bar, 0);
   KmerTrace(run, 1);
   for (uint32_t r = w_row0; r < w_row1; ++r) {
     const uint32_t Q = KmerPack(v0, fm, mult);
     v0 = v1; v1 = v2; v2 = v3;
-    v3 = load_row(r + 4);
-    uint32_t P = __shfl_up_sync(kFullMask, Q, 1);
-    if (lane == 0) P = prev31;
-    prev31 = __shfl_sync(kFullMask, Q, 31);
+    v3 = r + 4 < w_load1 ? __ldg(src) : zero4;
+    src += 32;
+    // the codes before mine: my left neighbour's; lane 0 gets lane 31's of the row before
+    const uint32_t P = __shfl_sync(kFullMask, lane == 31 ? prevQ : Q, from);
+    prevQ = Q;
     uint32_t acc = 0;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      // bits [16 + 4t, ...) of (Q:P): nine codes from bit 2 on = the ends after letters 2t and 2t+1
-      const uint32_t w = t < 4 ? __funnelshift_r(P, Q, 16 + 4 * t) : (Q >> (4 * t - 16));
-      const uint32_t word = Lds32(bm_base + (w & 0x7FFCu));
-      acc = __funnelshift_l(__funnelshift_l(0u, word, w >> 15), acc, 1);
+    for (int t = 0; t < kKmerTests; ++t) {
+      // bits [16 + 2x, ...) of (Q:P): 7 + R codes from bit 2 on = the ends after letters x .. x+R-1
+      const int s0 = 16 + 2 * KmerTestX(t);
+      const uint32_t w = s0 < 32 ? __funnelshift_r(P, Q, s0) : (Q >> (s0 - 32));
+      const uint32_t word = Lds32(bm_base + (w & ((4u << kKmerWordBits) - 4u)));
+      acc = __funnelshift_l(__funnelshift_l(0u, word, w >> (kKmerWordBits + 2)), acc, 1);   // bit kKmerTests-1-t: lookup t
     }
-    s_hit[r * 32 + lane] = (uint8_t)acc;                    // bit 7 - t: lookup t
+    if (__any_sync(kFullMask, acc != 0)) {
+      // rare (about one row in four on regex-dna): append the row's hits, in position order, to my warp's list
+      const uint32_t cnt = __popc(acc);
+      const uint32_t incl = WarpInclusiveScan(cnt);
+      uint32_t at = n_raw + incl - cnt;
+      uint32_t x = __brev(acc) >> (32 - kKmerTests);        // bit t: lookup t
+      const unsigned long long stream = ((unsigned long long)Q << 32) | P;
+      while (x) {
+        const int t = __ffs(x) - 1;
+        x &= x - 1;
+        const int xt = t * R < 16 - R ? t * R : 16 - R;
+        if (at < kKmerWarpRaw) {
+          // first of the R ends (relative to the CTA's first byte) | the first end that is this lookup's own << 30
+          my_raw[at] = (((r << 5) + lane) * 16u + xt + 1u) | ((uint32_t)(t * R - xt) << 30);
+          my_idx[at] = (uint32_t)(stream >> (18 + 2 * xt)) & ((1u << kKmerIdxBits) - 1u);
+        }
+        ++at;
+      }
+      n_raw += __shfl_sync(kFullMask, incl, 31);
+    }
   }
-  __syncthreads();
   KmerTrace(run, 2);
+  if (run.debug_stop == 1) return;
 
-  // ---- finish: hits in position order --------------------------------------------
-  // thread i owns hit bytes [64 i, 64 i + 64) = rows 2i, 2i+1
-  uint4 hb[4];
-  uint32_t mine = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    hb[q] = (2u * threadIdx.x + (q >> 1) < cta_rows) ? *reinterpret_cast<const uint4*>(s_hit + 64 * threadIdx.x + 16 * q)
-                                                     : make_uint4(0, 0, 0, 0);
-    mine += __popc(hb[q].x) + __popc(hb[q].y) + __popc(hb[q].z) + __popc(hb[q].w);
-  }
-  const uint32_t incl = WarpInclusiveScan(mine);
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    const uint32_t wi = WarpInclusiveScan(s_warp[lane]);
-    s_warp[lane] = wi;
-    if (lane == 31) s_total[0] = wi;
-  }
-  __syncthreads();
-  const uint32_t n_raw = s_total[0];
+  // ---- my warp's hits: exact check, per-member counts -------------------------------
+  // candidate R h + k = end k of hit h; lane j keeps member j's numbers
   unsigned int flags = 0;
-  if (n_raw > kKmerRawCap) flags |= kFinDense;
-  // my hits, by position: hit byte, then lookup (bit 7 first)
-  if (mine && n_raw <= kKmerRawCap) {
-    uint32_t at = incl - mine + (warp ? s_warp[warp - 1] : 0u);
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      const uint4 h = hb[q4];
-      if (h.x | h.y | h.z | h.w) {
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          // bit 8k + t = lookup t of hit byte k: ascending bits = ascending positions
-          uint32_t x = __byte_perm(__brev(k4 == 0 ? h.x : k4 == 1 ? h.y : k4 == 2 ? h.z : h.w), 0, 0x0123);
-          while (x) {
-            const uint32_t bit = __ffs(x) - 1;
-            x &= x - 1;
-            // first of the two ends, relative to the CTA's first byte
-            s_raw[at++] = (64u * threadIdx.x + 16u * q4 + 4u * k4 + (bit >> 3)) * 16u + 2u * (bit & 7u) + 1u;
+  if (n_raw > kKmerWarpRaw) { flags |= kFinDense; n_raw = 0; }
+  __syncwarp();
+  const uint32_t n_cand = R * n_raw;
+  uint32_t* my_mask = s_mask + warp * kKmerWarpRaw * R;
+  uint32_t cj = 0, firstj = 0, lastj = 0;                   // member `lane`: count, first end, last end (relative to the CTA)
+  for (uint32_t i0 = 0; i0 < n_cand; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    uint32_t m = 0, erel = 0;
+    if (i < n_cand) {
+      const uint32_t h = i / R, k = i - h * R;
+      const uint32_t raw = my_raw[h];
+      erel = (raw & 0x3FFFFFFFu) + k;
+      const uint64_t e = cta_base + erel;
+      if (k >= (raw >> 30) && e <= n && run.debug_stop != 6) {
+        const uint32_t mv = KmerVerify(text, e, (my_idx[h] >> (2 * k)) & 0xFFFFu, km);
+        for (uint32_t mm = mv; mm; mm &= mm - 1) {
+          const int j = __ffs(mm) - 1;
+          const uint64_t b = e - tb.match_len[j];
+          if (b >= range.own_begin && b < range.own_end) {
+            m |= 1u << j;
+            if (b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
           }
         }
       }
+      my_mask[i] = m;
     }
-  }
-  __syncthreads();
-  KmerTrace(run, 3);
-
-  // ---- exact check: candidate 2h, 2h+1 = the two ends of hit h ---------------------
-  const uint64_t cta_base = cta_row0 << 9;
-  const uint32_t n_cand = n_raw <= kKmerRawCap ? 2 * n_raw : 0;
-  for (uint32_t i = threadIdx.x; i < n_cand; i += kKmerThreads) {
-    const uint64_t e = cta_base + s_raw[i >> 1] + (i & 1u);
-    uint32_t m = 0;
-    if (e <= n) {
-      m = KmerVerify(text, e, km);
-      uint32_t keep = 0;
-      for (uint32_t mm = m; mm; mm &= mm - 1) {
-        const int j = __ffs(mm) - 1;
-        const uint64_t b = e - tb.match_len[j];
-        if (b >= range.own_begin && b < range.own_end) {
-          keep |= 1u << j;
-          if (b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
-        }
-      }
-      m = keep;
-    }
-    s_mask[i] = m;
-  }
-  __syncthreads();
-  KmerTrace(run, 4);
-  // per-member counts of every chunk of 32 candidates (lane j keeps member j's)
-  const uint32_t n_chunks = (n_cand + 31) / 32;
-  for (uint32_t ch = warp; ch < n_chunks; ch += kKmerThreads / 32) {
-    const uint32_t i = ch * 32 + lane;
-    const uint32_t m = i < n_cand ? s_mask[i] : 0u;
-    uint32_t cj = 0;
+    // a candidate overlaps an earlier one of the same member iff that one ends less than a match length before
+    // it: its predecessor in this pass, the last one of the pass before; other warps and CTAs: the seam checks
     for (int j = 0; j < K; ++j) {
       const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
-      if (lane == j && bal) {
-        cj = __popc(bal);
-        atomicMin(&s_first[j], ch * 32 + (uint32_t)__ffs(bal) - 1u);
-        atomicMax(&s_last[j], ch * 32 + 32u - (uint32_t)__clz(bal));
-      }
-    }
-    s_chunk[ch * 32 + lane] = (uint16_t)cj;
-    // a candidate overlaps an earlier one of the same member iff that one ends less than a match length before it
-    if (m) {
-      const uint64_t e = s_raw[i >> 1] + (i & 1u);
-      for (uint32_t d = 1; d <= 8 && d <= i; ++d) {
-        const uint32_t m2 = s_mask[i - d] & m;
-        if (!m2) continue;
-        const uint64_t e2 = s_raw[(i - d) >> 1] + ((i - d) & 1u);
-        for (uint32_t mm = m2; mm; mm &= mm - 1)
-          if (e2 + tb.match_len[__ffs(mm) - 1] > e) flags |= kFinOverlap;
+      if (!bal) continue;
+      const uint32_t L = tb.match_len[j];
+      const int lo = __ffs(bal) - 1, hi = 31 - __clz(bal);
+      const uint32_t e_lo = __shfl_sync(kFullMask, erel, lo), e_hi = __shfl_sync(kFullMask, erel, hi);
+      const uint32_t before = bal & ((1u << lane) - 1u);
+      const int pl = before ? 31 - __clz(before) : lane;
+      const uint32_t e_prev = __shfl_sync(kFullMask, erel, pl);
+      if (((m >> j) & 1u) && before && e_prev + L > erel) flags |= kFinOverlap;
+      if (lane == j) {
+        if (cj && lastj + L > e_lo) flags |= kFinOverlap;
+        if (!cj) firstj = e_lo;
+        lastj = e_hi;
+        cj += __popc(bal);
       }
     }
   }
+  s_wcnt[warp * 32 + lane] = cj;
+  s_wfirst[warp * 32 + lane] = firstj;
+  s_wlast[warp * 32 + lane] = lastj;
+  if (flags) atomicOr(s_flags, flags);
   __syncthreads();
-  // warp j: exclusive prefix of member j's chunk counts (in place), total -> s_count[j]
-  if (warp < K) {
-    uint32_t carry = 0;
-    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32) {
-      const uint32_t ch = c0 + lane;
-      const uint32_t c = ch < n_chunks ? s_chunk[ch * 32 + warp] : 0u;
-      const uint32_t inc = WarpInclusiveScan(c);
-      if (ch < n_chunks) s_chunk[ch * 32 + warp] = (uint16_t)(carry + inc - c);
-      carry += __shfl_sync(kFullMask, inc, 31);
-    }
-    if (lane == 0) s_count[warp] = carry;
-  }
-  if (flags) atomicOr(&s_total[1], flags);
-  __syncthreads();
-  KmerTrace(run, 5);
+  KmerTrace(run, 3);
+  if (run.debug_stop == 2) return;
 
-  // ---- exchange ------------------------------------------------------------------
-  if (threadIdx.x < K) {
-    const int j = threadIdx.x;
-    const unsigned int c = s_count[j];
-    unsigned long long fe = 0, le = 0;
-    if (c) {
-      const uint32_t i0 = s_first[j], i1 = s_last[j] - 1;
-      fe = cta_base + s_raw[i0 >> 1] + (i0 & 1u);
-      le = cta_base + s_raw[i1 >> 1] + (i1 & 1u);
-    }
-    volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.xchg + (size_t)blockIdx.x * 32 + j);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)fe),
-                 "r"((unsigned int)(fe >> 32)), "r"(c), "r"(run.seq) : "memory");
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)le),
-                 "r"((unsigned int)(le >> 32)), "r"(s_total[1]), "r"(run.seq) : "memory");
-  }
+  // ---- warp j: member j over the 32 warps (lane = warp): offsets, seams, my CTA's record --------
   const bool last_cta = blockIdx.x + 1 == gridDim.x;
-  // the CTAs before me: warp w reads CTA w, w + 32, ... (lane j = member j), five CTAs' records in flight
-  // at once.  The last CTA keeps what it reads (s_seam, in the hit-byte area) for the seam check below.
-  ulonglong2* s_seam = reinterpret_cast<ulonglong2*>(s_hit);            // [CTA][member] {first end, last end}
-  const bool seam_fits = (uint64_t)gridDim.x * K * sizeof(ulonglong2) <= (uint64_t)kKmerMaxRows * 32;
+  if (warp < K) {
+    const int j = warp;
+    const uint32_t L = tb.match_len[j];
+    const uint32_t c = s_wcnt[lane * 32 + j], fe = s_wfirst[lane * 32 + j], le = s_wlast[lane * 32 + j];
+    const uint32_t incl = WarpInclusiveScan(c);
+    s_woff[lane * 32 + j] = incl - c;
+    const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+    // last end among the warps before me (ends grow with the warp index)
+    uint32_t run_max = c ? le : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(kFullMask, run_max, d);
+      if (lane >= d && o > run_max) run_max = o;
+    }
+    uint32_t before = __shfl_up_sync(kFullMask, run_max, 1);
+    if (lane == 0) before = 0;
+    const bool bad = c && before && before + L > fe;
+    const unsigned has = __ballot_sync(kFullMask, c != 0);
+    const bool any_bad = __any_sync(kFullMask, bad);
+    const uint32_t cta_first = __shfl_sync(kFullMask, fe, has ? __ffs(has) - 1 : 0);
+    const uint32_t cta_last = __shfl_sync(kFullMask, run_max, 31);
+    if (lane == 0) {
+      s_count[j] = total;
+      const unsigned long long f64 = total ? cta_base + cta_first : 0ull, l64 = total ? cta_base + cta_last : 0ull;
+      const unsigned int fl = *s_flags | (any_bad ? kFinOverlap : 0u);
+      if (any_bad) atomicOr(s_flags, kFinOverlap);
+      volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.xchg + (size_t)blockIdx.x * 32 + j);
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)f64),
+                   "r"((unsigned int)(f64 >> 32)), "r"(total), "r"(run.seq) : "memory");
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)l64),
+                   "r"((unsigned int)(l64 >> 32)), "r"(fl), "r"(run.seq) : "memory");
+      if (last_cta) s_seam[(size_t)blockIdx.x * K + j] = make_uint2((uint32_t)(f64 ? f64 - seam_base : 0), (uint32_t)(l64 ? l64 - seam_base : 0));
+    }
+  }
+  KmerTrace(run, 4);
+  if (run.debug_stop == 3) return;
+  // ---- exchange: the CTAs before me.  Warp w reads CTA w, w + 32, ... (lane j = member j), five CTAs' records
+  // in flight at once.  The last CTA keeps what it reads for the seam check below.
   for (uint32_t c0 = warp; c0 < blockIdx.x; c0 += 160) {
     uint4 a[5], b[5];
     unsigned pending = 0;
     uint32_t sum = 0;
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
-      a[u] = b[u] = make_uint4(0, 0, 0, 0);
+      a[u] = b[u] = zero4;
       if (c0 + 32 * u < blockIdx.x && lane < K) pending |= 1u << u;
     }
     while (pending) {
 #pragma unroll
       for (int u = 0; u < 5; ++u)
         if ((pending >> u) & 1u) {
-          const volatile uint4* src = reinterpret_cast<const volatile uint4*>(run.xchg + (size_t)(c0 + 32 * u) * 32 + lane);
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w) : "l"(src) : "memory");
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b[u].x), "=r"(b[u].y), "=r"(b[u].z), "=r"(b[u].w) : "l"(src + 1) : "memory");
+          const volatile uint4* p = reinterpret_cast<const volatile uint4*>(run.xchg + (size_t)(c0 + 32 * u) * 32 + lane);
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w) : "l"(p) : "memory");
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b[u].x), "=r"(b[u].y), "=r"(b[u].z), "=r"(b[u].w) : "l"(p + 1) : "memory");
         }
 #pragma unroll
       for (int u = 0; u < 5; ++u)
@@ -1532,90 +1534,86 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
           pending &= ~(1u << u);
           sum += a[u].z;
           if (last_cta) {
-            if (b[u].z) atomicOr(&s_total[1], b[u].z);
-            if (seam_fits)
-              s_seam[(size_t)(c0 + 32 * u) * K + lane] =
-                  make_ulonglong2(a[u].z ? ((unsigned long long)a[u].y << 32 | a[u].x) : 0ull,
-                                  a[u].z ? ((unsigned long long)b[u].y << 32 | b[u].x) : 0ull);
+            if (b[u].z) atomicOr(s_flags, b[u].z);
+            const unsigned long long f64 = (unsigned long long)a[u].y << 32 | a[u].x, l64 = (unsigned long long)b[u].y << 32 | b[u].x;
+            s_seam[(size_t)(c0 + 32 * u) * K + lane] =
+                make_uint2(a[u].z ? (uint32_t)(f64 - seam_base) : 0u, a[u].z ? (uint32_t)(l64 - seam_base) : 0u);
           }
         }
     }
     if (sum) atomicAdd(&s_base[lane], sum);
   }
   __syncthreads();
-  KmerTrace(run, 6);
+  KmerTrace(run, 5);
+  if (run.debug_stop == 4) return;
 
-  // ---- my matches, at their final place ------------------------------------------
-  for (uint32_t ch = warp; ch < n_chunks; ch += kKmerThreads / 32) {
-    const uint32_t i = ch * 32 + lane;
-    const uint32_t m = i < n_cand ? s_mask[i] : 0u;
-    const uint64_t e = cta_base + (i < n_cand ? s_raw[i >> 1] + (i & 1u) : 0u);
-    for (int j = 0; j < K; ++j) {
-      const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
-      if ((m >> j) & 1u) {
-        const unsigned long long at = (unsigned long long)s_base[j] + s_chunk[ch * 32 + j] + __popc(bal & ((1u << lane) - 1u));
-        if (at < run.out_cap)
-          reinterpret_cast<ulonglong2*>(run.out_pairs + (uint64_t)j * 2 * run.out_stride)[at] =
-              make_ulonglong2(e - tb.match_len[j] + run.base_offset, e + run.base_offset);
+  // ---- my warp's matches, at their final place -----------------------------------
+  {
+    uint32_t done = 0;                                      // member `lane`: matches of my warp already written
+    for (uint32_t i0 = 0; i0 < n_cand; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      const uint32_t m = i < n_cand ? my_mask[i] : 0u;
+      if (!__any_sync(kFullMask, m != 0)) continue;
+      const uint32_t h = i / R;
+      const uint64_t e = cta_base + (i < n_cand ? (my_raw[h] & 0x3FFFFFFFu) + (i - h * R) : 0u);
+      for (uint32_t todo = __reduce_or_sync(kFullMask, m); todo; todo &= todo - 1) {
+        const int j = __ffs(todo) - 1;
+        const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
+        const uint32_t dj = __shfl_sync(kFullMask, done, j);
+        if ((m >> j) & 1u) {
+          const unsigned long long at = (unsigned long long)s_base[j] + s_woff[warp * 32 + j] + dj + __popc(bal & ((1u << lane) - 1u));
+          if (at < run.out_cap)
+            reinterpret_cast<ulonglong2*>(run.out_pairs + (uint64_t)j * 2 * run.out_stride)[at] =
+                make_ulonglong2(e - tb.match_len[j] + run.base_offset, e + run.base_offset);
+        }
+        if (lane == j) done += __popc(bal);
       }
     }
   }
-  KmerTrace(run, 7);
-  if (!last_cta) return;
-  // ---- the last CTA: seams between CTAs, totals, report ----------------------------
+  KmerTrace(run, 6);
+  if (!last_cta || run.debug_stop == 5) return;
+  // ---- the last CTA: seams between CTAs, totals, report.  Warp j = member j; lane l looks at CTAs 5 l .. 5 l + 4
   if (warp < K) {
     const int j = warp;
-    unsigned long long prev_last = 0;
-    unsigned int bad = 0;
-    for (uint32_t c0 = 0; c0 < gridDim.x; c0 += 32) {
-      const uint32_t c = c0 + lane;
-      unsigned long long fe = 0, le = 0;
-      unsigned int cnt = 0;
-      if (c + 1 < gridDim.x) {
-        if (seam_fits) {
-          const ulonglong2 fl = s_seam[(size_t)c * K + j];
-          fe = fl.x; le = fl.y; cnt = fl.y ? 1u : 0u;
-        } else {
-          const KmerXchg* x = run.xchg + (size_t)c * 32 + j;  // complete: the loop above saw both sequence numbers
-          fe = __ldcg(&x->first_end); le = __ldcg(&x->last_end); cnt = __ldcg(&x->count);
-        }
-      } else if (c + 1 == gridDim.x) {
-        cnt = s_count[j];
-        if (cnt) {
-          const uint32_t i0 = s_first[j], i1 = s_last[j] - 1;
-          fe = cta_base + s_raw[i0 >> 1] + (i0 & 1u);
-          le = cta_base + s_raw[i1 >> 1] + (i1 & 1u);
-        }
-      }
-      // last end among the CTAs before c (ends grow with c)
-      unsigned long long run_max = le;
+    const uint32_t L = tb.match_len[j];
+    uint2 fl[5];
+    uint32_t lm = 0;                                         // last end among my five
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long o = __shfl_up_sync(kFullMask, run_max, d);
-        if (lane >= d && o > run_max) run_max = o;
-      }
-      unsigned long long before = __shfl_up_sync(kFullMask, run_max, 1);
-      if (lane == 0) before = 0;
-      if (prev_last > before) before = prev_last;
-      if (cnt && before && fe - tb.match_len[j] < before) bad = 1;
-      const unsigned long long chunk_max = __shfl_sync(kFullMask, run_max, 31);
-      if (chunk_max > prev_last) prev_last = chunk_max;
+    for (int u = 0; u < 5; ++u) {
+      const uint32_t c = 5 * lane + u;
+      fl[u] = c < gridDim.x ? s_seam[(size_t)c * K + j] : make_uint2(0, 0);
+      lm = fl[u].y > lm ? fl[u].y : lm;
+    }
+    uint32_t run_max = lm;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(kFullMask, run_max, d);
+      if (lane >= d && o > run_max) run_max = o;
+    }
+    uint32_t before = __shfl_up_sync(kFullMask, run_max, 1);    // last end among the CTAs before my five
+    if (lane == 0) before = 0;
+    bool bad = false;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      if (fl[u].y && before && before + L > fl[u].x) bad = true;
+      before = fl[u].y > before ? fl[u].y : before;
     }
     bad = __any_sync(kFullMask, bad);
+    const uint32_t all_last = __shfl_sync(kFullMask, run_max, 31);
     if (lane == 0) {
       const unsigned long long total = (unsigned long long)s_base[j] + s_count[j];
-      unsigned int fl = s_total[1] | (bad ? kFinOverlap : 0u);
-      const unsigned long long le = prev_last;
+      const unsigned int flg = *s_flags | (bad ? kFinOverlap : 0u);
+      const unsigned long long le = all_last ? seam_base + all_last : 0ull;
       volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.host_records + j);
       asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)total),
-                   "r"((unsigned int)(total >> 32)), "r"(fl), "r"(run.seq) : "memory");
+                   "r"((unsigned int)(total >> 32)), "r"(flg), "r"(run.seq) : "memory");
       asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)le),
                    "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
       asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"((unsigned int)le),
                    "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
     }
   }
-  KmerTrace(run, 8);
+  KmerTrace(run, 7);
 }
 
 // ---------------------------------------------------------------------------

@@ -480,9 +480,13 @@ static void BuildKmerIndex(SetDfa* out) {
     }
     km.mask16[x] = out->accept_mask[st];
   }
-  km.bitmap.assign(8192, 0);
-  for (uint32_t x = 0; x < (1u << 18); ++x)
-    if (km.mask16[x & 0xFFFF] | km.mask16[x >> 2]) km.bitmap[x & 0x1FFF] |= 1u << (31 - (x >> 13));
+  const int idx_bits = 2 * (7 + kKmerR), word_bits = idx_bits - 5;
+  km.bitmap.assign(static_cast<size_t>(1) << word_bits, 0);
+  for (uint32_t x = 0; x < (1u << idx_bits); ++x) {
+    uint32_t any = 0;
+    for (int k = 0; k < kKmerR; ++k) any |= km.mask16[(x >> (2 * k)) & 0xFFFF];
+    if (any) km.bitmap[x & ((1u << word_bits) - 1)] |= 1u << (31 - (x >> word_bits));
+  }
   km.ok = true;
 }
 

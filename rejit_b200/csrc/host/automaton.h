@@ -92,6 +92,8 @@ bool BuildAutomaton(const LoweredRegexp& lr, CompiledAutomaton* out, std::string
 // the union of the patterns' position automata, so one pass over the text
 // advances all patterns at once; an accepting state carries the bitmask of the
 // patterns that end there.  ("fused multi-pattern".)
+constexpr int kKmerR = 3;               // ends answered by one bitmap lookup (2: 32 KB bitmap, 3: 128 KB)
+
 struct SetDfa {
   int n_patterns = 0;
   int n_states = 0, n_classes = 0, first_accept = 0;
@@ -115,8 +117,9 @@ struct SetDfa {
   // the 2-bit codes of the eight bytes before e: no state, no dependent chain.
   //   mask16[x]  x = eight codes, oldest in the low bits; bit j: member j accepts
   //              the last match_len[j] letters of the (canonical) 8-mer
-  //   bitmap[w]  nine codes x18 (two consecutive ends at once): bit 31-(x18>>13) of
-  //              word x18 & 0x1FFF is set iff mask16[x18 & 0xFFFF] | mask16[x18 >> 2]
+  //   bitmap[w]  7 + R codes x (R = kKmerR consecutive ends at once), B = 2 (7 + R) - 5:
+  //              bit 31 - (x >> B) of word x & (2^B - 1) is set iff one of the R
+  //              8-mers (x >> 2k) & 0xFFFF, k < R, is accepted by some member
   // A byte whose code aliases a live byte is weeded out by the exact check on a hit.
   struct Kmer {
     bool ok = false;
@@ -124,7 +127,7 @@ struct SetDfa {
     uint32_t canon = 0;                  // byte c: the live byte with code c
     uint32_t canon_ok = 0;               // bit c: code c has a live byte
     uint32_t len_le[9] = {0};            // bit j: match_len[j] <= v
-    std::vector<uint32_t> bitmap;        // [8192]
+    std::vector<uint32_t> bitmap;        // [2^(2 (7 + R) - 5)]
     std::vector<uint32_t> mask16;        // [65536]
   } kmer;
 };

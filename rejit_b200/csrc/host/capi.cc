@@ -400,7 +400,7 @@ int rejit_b200_set_kmer_tables(const rejit_b200_set* set, uint32_t* info, uint32
   if (info) {
     info[0] = km.shift; info[1] = km.canon; info[2] = km.canon_ok; info[3] = (uint32_t)set->set->dfa().n_patterns;
     for (int v = 0; v <= 8; ++v) info[4 + v] = km.len_le[v];
-    info[13] = 0;
+    info[13] = (uint32_t)kKmerR;
   }
   if (bitmap) memcpy(bitmap, km.bitmap.data(), km.bitmap.size() * 4);
   if (mask16) memcpy(mask16, km.mask16.data(), km.mask16.size() * 4);

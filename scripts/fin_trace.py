@@ -10,6 +10,7 @@ rs = rj.RegejSet(W.DNA_PATTERNS)
 dt = rj.DeviceText(seq)
 st = rj.Stats()
 for i in range(6):
-    rj.lib().rejit_b200_flush_l2(0)
+    if not os.environ.get("RJ_NOFLUSH"):
+        rj.lib().rejit_b200_flush_l2(0)
     rs.match_all_device(dt, stats=st)
     print("total_ms", round(st.total_ms, 4), "scan_ms", round(st.scan_ms, 4), file=sys.stderr)

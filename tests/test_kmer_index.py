@@ -1,8 +1,8 @@
 """The k-mer index of a fused pattern set (host/automaton.cc BuildKmerIndex) and
 the arithmetic k_set_kmer does with it, restated in numpy on the CPU: pack 16
-bytes into 2-bit codes with one AND + one multiply per word, look two
-consecutive ends up in the 18-bit bitmap, check a hit exactly against the
-bytes.  The candidate ends must equal every (overlapping) occurrence Python's
+bytes into 2-bit codes with one AND + one multiply per word, look R
+consecutive ends up in the bitmap indexed by 7 + R codes, check a hit exactly
+against the bytes.  The candidate ends must equal every (overlapping) occurrence Python's
 `re` finds; the GPU tier (test_gpu_parity.py) checks the kernel itself against
 the oracle.  The patterns are the regex-dna variants of
 /root/reference/sample/regexdna.cc:52-62.
@@ -49,30 +49,39 @@ def emulate(kset, text: bytes, seed=0):
     words = words[:, :, 0] | (words[:, :, 1] << np.uint64(8)) | (words[:, :, 2] << np.uint64(16)) | (words[:, :, 3] << np.uint64(24))
     codes = [_pack([words[:, 4 * g + i] for i in range(4)], fm, mult) for g in range(GROUPS + 1)]
     found = [[] for _ in range(K)]
+    R = int(info[13])
+    idx_bits = 2 * (7 + R)
+    word_bits = idx_bits - 5
+    assert len(bitmap) == 1 << word_bits
+    tests = (16 + R - 1) // R
     a = np.arange(nstreams, dtype=np.int64) * STREAM
     limit = np.minimum(a + STREAM, n)
     for g in range(GROUPS):
         P, Q = codes[g], codes[g + 1]
         both = P | (Q << np.uint64(32))
-        for t in range(8):
-            w = (both >> np.uint64(16 + 4 * t)) & np.uint64(0xFFFFFFFF)
-            word = bitmap[((w & np.uint64(0x7FFC)) >> np.uint64(2)).astype(np.int64)].astype(np.uint64)
-            hit = ((word << ((w >> np.uint64(15)) & np.uint64(31))) >> np.uint64(31)) & np.uint64(1)
+        for t in range(tests):
+            x = min(t * R, 16 - R)                     # KmerTestX: first letter of the R ends this lookup answers
+            w = (both >> np.uint64(16 + 2 * x)) & np.uint64(0xFFFFFFFF)
+            word = bitmap[((w & np.uint64((4 << word_bits) - 4)) >> np.uint64(2)).astype(np.int64)].astype(np.uint64)
+            hit = ((word << ((w >> np.uint64(word_bits + 2)) & np.uint64(31))) >> np.uint64(31)) & np.uint64(1)
             for s in np.nonzero(hit)[0]:
-                rel = 16 * g + 2 * t + 1
-                for r in (rel, rel + 1):
+                idx = (int(both[s]) >> (18 + 2 * x)) & ((1 << idx_bits) - 1)
+                for k in range(t * R - x, R):          # the last lookup overlaps the one before it
+                    r = 16 * g + x + 1 + k
                     e = int(a[s]) + r
                     if e > limit[s]:
                         continue
-                    x, v, run = 0, 0, True
-                    for i in range(8):
-                        byte = int(lanes[s, 16 + r - 1 - i])
-                        code = (byte >> shift) & 3
-                        ok = i < e and (canon_ok >> code) & 1 and ((canon >> (8 * code)) & 0xFF) == byte
-                        x |= code << (2 * (7 - i))
-                        run = run and bool(ok)
-                        v += run
-                    m = int(mask16[x]) & len_le[v]
+                    x16 = (idx >> (2 * k)) & 0xFFFF
+                    v, run = 0, True
+                    for i in range(8):                  # byte e-8+i against the byte its code stands for
+                        byte = int(lanes[s, 16 + r - 8 + i]) if e >= 8 - i else 0x100
+                        code = (x16 >> (2 * i)) & 3
+                        ok = ((canon >> (8 * code)) & 0xFF) == byte and (canon_ok >> code) & 1
+                        if not ok:
+                            v = 0
+                        else:
+                            v += 1
+                    m = int(mask16[x16]) & len_le[v]
                     for j in range(K):
                         if (m >> j) & 1:
                             found[j].append((e - lens[j], e))
