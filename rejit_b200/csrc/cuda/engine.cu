@@ -1093,7 +1093,22 @@ DeviceSet* SetProgram::OnDevice(int device, std::string* error) {
       d->km.canon = f.kmer.canon;
       for (uint32_t cd = 0; cd < 4; ++cd)
         if (!((f.kmer.canon_ok >> cd) & 1u)) d->km.canon |= ((((cd + 1) & 3u) << f.kmer.shift) & 0xFFu) << (8 * cd);
-      for (int v = 0; v <= 8; ++v) d->km.len_le[v] = f.kmer.len_le[v];
+      // the small tables as one array of words (kKmerTab*); few accepted 8-mers: every CTA builds the bitmap and
+      // the member-mask hash from the list
+      std::vector<uint32_t> tab(kKmerTabWords, 0);
+      for (int j = 0; j < f.n_patterns; ++j) tab[kKmerTabMatchLen + j] = f.match_len[j];
+      for (int v = 0; v <= 8; ++v) tab[kKmerTabLenLe + v] = f.kmer.len_le[v];
+      static const bool no_list = getenv("RJ_KMER_NO_LIST") != nullptr;
+      std::vector<uint32_t> accepted;
+      for (uint32_t x = 0; x < 65536 && accepted.size() <= kKmerListMax; ++x) if (f.kmer.mask16[x]) accepted.push_back(x);
+      if (!no_list && !accepted.empty() && accepted.size() <= kKmerListMax) {
+        d->km.n_list = (uint32_t)accepted.size();
+        for (size_t i = 0; i < accepted.size(); ++i) {
+          tab[kKmerTabListX + i] = accepted[i];
+          tab[kKmerTabListMask + i] = f.kmer.mask16[accepted[i]];
+        }
+      }
+      if (!d->Upload(tab.data(), tab.size(), &d->km.tab, error)) { delete d; return nullptr; }
       d->kmer = true;
     }
     per_device_[device] = d;
@@ -1226,7 +1241,10 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           for (int j = 0; j < 32; ++j) carries.c[j] = (carry_in && j < K) ? carry_in[j] : Carry();
           uint64_t n_arg = n;
           if (stats) cudaEventRecord(c->ev[0], s);
-          void* kargs[] = {(void*)&d_text, (void*)&n_arg, (void*)&ds->tb, (void*)&ds->km, (void*)&own, (void*)&run, (void*)&carries};
+          run.has_carry = 0;
+          for (int j = 0; j < K; ++j) if (carries.c[j].cur != 0) run.has_carry = 1;
+          int k_arg = K;
+          void* kargs[] = {(void*)&d_text, (void*)&n_arg, (void*)&k_arg, (void*)&ds->km, (void*)&own, (void*)&run, (void*)&carries};
           if (!Check(cudaLaunchCooperativeKernel((const void*)k_set_kmer, dim3(blocks), dim3(kKmerThreads), kargs, kmer_smem, s),
                      "cooperative launch", error)) return -1;
           if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
@@ -1251,11 +1269,12 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
             std::vector<unsigned long long> tr((size_t)blocks * 16);
             cudaStreamSynchronize(s);
             cudaMemcpy(tr.data(), run.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
-            static const char* names[9] = {"start", "tables", "scanned(warp 0)", "checked", "published", "exchanged", "written", "reported", ""};
+            static const char* names[9] = {"start", "tables", "scanned(warp 0)", "checked", "published", "exchanged", "written", "reported",
+                                           "verified(warp 0)"};
             unsigned long long t0 = ~0ull;
             for (int b2 = 0; b2 < blocks; ++b2) t0 = std::min(t0, tr[(size_t)b2 * 16]);
             std::string line = "[kmer trace]";
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 9; ++q) {
               unsigned long long mn = ~0ull, mx = 0;
               std::vector<std::pair<unsigned long long, int>> dur;      // time since the phase before, per CTA
               for (int b2 = 0; b2 < blocks; ++b2) {
@@ -1263,7 +1282,8 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
                 if (!v) continue;
                 mx = std::max(mx, v - t0);
                 mn = std::min(mn, v - t0);
-                if (q > 0 && tr[(size_t)b2 * 16 + q - 1]) dur.push_back({v - tr[(size_t)b2 * 16 + q - 1], b2});
+                const int qp = q == 8 ? 2 : q - 1;          // the stamp this one follows
+                if (q > 0 && tr[(size_t)b2 * 16 + qp]) dur.push_back({v - tr[(size_t)b2 * 16 + qp], b2});
               }
               if (!mx) continue;
               line += " | " + std::string(names[q]) + " " + std::to_string(mn) + ".." + std::to_string(mx);
@@ -1274,6 +1294,19 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
               }
             }
             fprintf(stderr, "%s (ns)\n", line.c_str());
+            if (const char* which = getenv("RJ_FIN_TRACE_CTA")) {       // raw stamps of some CTAs, e.g. "29,60"
+              for (const char* q = which; *q;) {
+                const int b2 = atoi(q);
+                if (b2 >= 0 && b2 < blocks) {
+                  std::string l2 = "[kmer cta " + std::to_string(b2) + "]";
+                  for (int k2 : {0, 1, 2, 8, 3, 4, 5, 6, 7})
+                    l2 += " " + std::string(names[k2]) + "=" + (tr[(size_t)b2 * 16 + k2] ? std::to_string(tr[(size_t)b2 * 16 + k2] - t0) : std::string("-"));
+                  fprintf(stderr, "%s\n", l2.c_str());
+                }
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+              }
+            }
           }
           if (!dense) ds->kmer_dense = 0;
           if (give_up) {                                         // overlapping or too dense: the general path decides

@@ -1227,14 +1227,28 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
 // the host repeats the call with k_set_tma + the general resolve.
 // Algorithmic traffic: N bytes read (once for all members) + 16 bytes per match.
 // ===========================================================================
+constexpr uint32_t kKmerListMax = 128;  // accepted 8-mers up to which every CTA builds its tables itself
+constexpr uint32_t kKmerHashSlots = 512;
+// the set's small tables, one global array of words that every CTA copies to shared memory first thing (ONE
+// coalesced load; kernel parameters are read through the constant cache, and a constant-cache miss issued
+// while the text streams was measured to wait for microseconds)
+constexpr uint32_t kKmerTabMatchLen = 0;      // [32]
+constexpr uint32_t kKmerTabLenLe = 32;        // [9]
+constexpr uint32_t kKmerTabListX = 48;        // [kKmerListMax] accepted 8-mers (codes, oldest in the low bits)
+constexpr uint32_t kKmerTabListMask = kKmerTabListX + kKmerListMax;   // [kKmerListMax] their member masks
+constexpr uint32_t kKmerTabWords = kKmerTabListMask + kKmerListMax;
+
 struct KmerTables {
-  const uint32_t* bitmap;              // [2^(kIdxBits - 5)]
-  const uint32_t* mask16;              // [65536]
+  const uint32_t* bitmap;              // [2^(kIdxBits - 5)]   (n_list == 0)
+  const uint32_t* mask16;              // [65536]              (n_list == 0)
+  const uint32_t* tab;                 // [kKmerTabWords]
   uint32_t field_mask;                 // 0x03030303 << shift
   uint32_t mult;                       // 0x01041040 >> shift: packs four fields into the top byte
   uint32_t shift;
   uint32_t canon;                      // byte c: the live byte with code c (or a byte with another code)
-  uint32_t len_le[9];
+  // a short list of accepted 8-mers (the nine regex-dna variants accept 50): every CTA builds the bitmap and a
+  // hash of the member masks in shared memory itself instead of fetching 128 KB + one L2 miss per hit
+  uint32_t n_list;                     // 0: use bitmap / mask16 from global memory
 };
 
 struct __align__(16) KmerXchg {        // one per (CTA, member); each half is one 16-byte store
@@ -1254,6 +1268,7 @@ struct KmerRun {
   unsigned int seq;
   unsigned long long* trace;           // optional: 16 globaltimer stamps per CTA
   int debug_stop;                      // tuning aid (RJ_KMER_STOP): leave after phase n (results are then invalid)
+  int has_carry;                       // some member's chain arrives from the left (CarrySet is read only then)
 };
 
 // R consecutive ends per lookup: a window of 7 + R codes indexes the bitmap
@@ -1269,7 +1284,7 @@ constexpr uint32_t kKmerWarpRaw = 64;              // hits per warp (its run of 
 constexpr uint32_t kKmerMaxGrid = 160;             // five CTAs per lane in the seam check
 // dynamic shared memory: fixed part + the last CTA's seam table (kKmerMaxGrid x K x 8 bytes)
 constexpr uint32_t kKmerSmemFixed = kKmerBitmapBytes + kKmerWarps * kKmerWarpRaw * 4 * (2 + kKmerEnds) +
-                                    4 * kKmerWarps * 32 * 4 + 512;
+                                    4 * kKmerWarps * 32 * 4 + kKmerHashSlots * 8 + kKmerTabWords * 4 + 512;
 // first letter (0..15) of the ends lookup t answers: x, x+1, .., x+R-1; the last lookup is pulled back into the group
 __host__ __device__ constexpr int KmerTestX(int t) { return t * kKmerEnds < 16 - kKmerEnds ? t * kKmerEnds : 16 - kKmerEnds; }
 
@@ -1286,44 +1301,77 @@ __device__ __forceinline__ void KmerTrace(const KmerRun& run, int slot) {
   }
 }
 
-// The members that end at text offset e (exact), given the codes x16 of the eight bytes before e: the mask table
-// entry, cut to the members no longer than the run of live bytes that ends at e.  The nine loads do not depend on
-// each other: one round trip to L2.
-__device__ __forceinline__ uint32_t KmerVerify(const uint8_t* __restrict__ text, uint64_t e, uint32_t x16,
-                                               const KmerTables& km) {
-  const uint32_t members = __ldg(km.mask16 + x16);
-  uint32_t byte[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) byte[i] = (e >= (uint64_t)(8 - i)) ? __ldg(text + e - 8 + i) : 0x100u;   // text[e-8+i]
-  uint32_t bad = 0;                    // bit i: byte e-8+i is not the live byte its code stands for
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t code = (x16 >> (2 * i)) & 3u;
-    if (((km.canon >> (8 * code)) & 0xFFu) != byte[i]) bad |= 1u << i;
+// The members that end at text offset e (exact): the eight bytes before e give the codes x16 (oldest in the low
+// bits) and the run of live bytes that ends at e; the member mask of x16 (hash in shared memory, or the global
+// 65536-entry table) is cut to the members no longer than that run.  The eight loads do not depend on each other:
+// one round trip to L2.
+__device__ __forceinline__ uint32_t KmerVerify(const uint8_t* __restrict__ text, uint64_t e, uint32_t fm, uint32_t mult,
+                                               uint32_t shift, uint32_t canon, bool from_list,
+                                               const uint32_t* __restrict__ mask16, const uint32_t* s_hkey,
+                                               const uint32_t* s_hval, const uint32_t* s_lenle) {
+  // w = text[e-8 .. e), byte 0 the oldest; `missing`: 0xFF in the bytes that lie before the text
+  unsigned long long w, missing = 0;
+  if (e >= 8) {
+    const uint8_t* p = text + e - 8;
+    const unsigned long long* a = reinterpret_cast<const unsigned long long*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    const unsigned long long w0 = __ldg(a), w1 = __ldg(a + 1);       // device texts are padded: a + 16 <= e + 8
+    const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(p) & 7u) * 8u;
+    w = sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
+  } else {
+    w = 0;
+    for (uint32_t i = 0; i < 8; ++i) {
+      if (e >= 8 - i) w |= (unsigned long long)__ldg(text + e - 8 + i) << (8 * i);
+      else missing |= 0xFFull << (8 * i);
+    }
   }
-  const uint32_t v = bad ? (uint32_t)__clz(bad << 24) : 8u;          // live bytes counted back from e
-  return members & km.len_le[v];
+  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+  const uint32_t x16 = (((lo & fm) * mult) >> 24) | ((((hi & fm) * mult) >> 24) << 8);   // codes, oldest in the low bits
+  // the byte each code stands for (PRMT with the codes as selector nibbles) against the byte itself
+  const uint32_t c0 = (lo >> shift) & 0x03030303u, c1 = (hi >> shift) & 0x03030303u;
+  const uint32_t sel0 = ((c0 | (c0 >> 4)) & 0xFFu) | (((c0 >> 8) | (c0 >> 12)) & 0xFF00u);
+  const uint32_t sel1 = ((c1 | (c1 >> 4)) & 0xFFu) | (((c1 >> 8) | (c1 >> 12)) & 0xFF00u);
+  const unsigned long long diff =
+      ((unsigned long long)(__byte_perm(canon, 0u, sel1) ^ hi) << 32 | (__byte_perm(canon, 0u, sel0) ^ lo)) | missing;
+  const uint32_t v = diff ? (uint32_t)__clzll((long long)diff) >> 3 : 8u;     // live bytes counted back from e
+  uint32_t members = 0;
+  if (from_list) {
+    const uint32_t key = x16 | 0x10000u;
+    uint32_t slot = ((x16 * 0x9E3Bu) >> 5) & (kKmerHashSlots - 1u);
+    for (uint32_t kk; (kk = s_hkey[slot]) != 0u; slot = (slot + 1u) & (kKmerHashSlots - 1u))
+      if (kk == key) { members = s_hval[slot]; break; }
+  } else {
+    members = __ldg(mask16 + x16);
+  }
+  return members & s_lenle[v];
 }
 
 __global__ void __launch_bounds__(kKmerThreads, 1)
-k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTables km, ScanRange range, KmerRun run,
+k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTables km, ScanRange range, KmerRun run,
            CarrySet carries) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int R = kKmerEnds;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int K = tb.n_patterns;
-  // layout: [bitmap][per warp: hits u32 [64], their window codes u32 [64], candidate masks u32 [64 R]]
-  //         [per warp and member: count, offset, first end, last end u32 [warp][32]][misc][seam table (last CTA)]
+  const int K = n_patterns;
+  // the set's small tables: requested before anything else, while the memory system is still idle
+  const uint32_t tab_word = threadIdx.x < kKmerTabWords ? __ldg(km.tab + threadIdx.x) : 0u;
+  // layout: [bitmap][per warp: hits u32 [64], groups with a hit u32 [64], candidate masks u32 [64 R]]
+  //         [per warp and member: count, offset, first end, last end u32 [warp][32]][hash keys, values]
+  //         [small tables][misc][seam table (last CTA)]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* s_raw = s_bitmap + kKmerBitmapBytes / 4;
-  uint32_t* s_idx = s_raw + kKmerWarps * kKmerWarpRaw;
-  uint32_t* s_mask = s_idx + kKmerWarps * kKmerWarpRaw;
+  uint32_t* s_ent = s_raw + kKmerWarps * kKmerWarpRaw;
+  uint32_t* s_mask = s_ent + kKmerWarps * kKmerWarpRaw;
   uint32_t* s_wcnt = s_mask + kKmerWarps * kKmerWarpRaw * R;
   uint32_t* s_woff = s_wcnt + kKmerWarps * 32;
   uint32_t* s_wfirst = s_woff + kKmerWarps * 32;
   uint32_t* s_wlast = s_wfirst + kKmerWarps * 32;
-  uint32_t* s_misc = s_wlast + kKmerWarps * 32;
+  uint32_t* s_hkey = s_wlast + kKmerWarps * 32;
+  uint32_t* s_hval = s_hkey + kKmerHashSlots;
+  uint32_t* s_tab = s_hval + kKmerHashSlots;
+  const uint32_t* s_mlen = s_tab + kKmerTabMatchLen;                                  // [32] match length per member
+  const uint32_t* s_lenle = s_tab + kKmerTabLenLe;                                    // [9] members no longer than v
+  uint32_t* s_misc = s_tab + kKmerTabWords;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc);                              // 8 bytes
   uint32_t* s_flags = s_misc + 2;
   uint32_t* s_base = s_misc + 4;                                                      // [32] matches of the CTAs before me
@@ -1331,12 +1379,15 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
   uint2* s_seam = reinterpret_cast<uint2*>(s_misc + 128);                             // [CTA][K] {first, last} end - seam_base
 
   KmerTrace(run, 0);
+  const bool from_list = km.n_list != 0;
   if (threadIdx.x == 0) {
-    MbarInit(s_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    MbarExpectTx(s_bar, kKmerBitmapBytes);
-    TmaLoad1D(s_bitmap, km.bitmap, kKmerBitmapBytes, s_bar);
     *s_flags = 0;
+    if (!from_list) {
+      MbarInit(s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      MbarExpectTx(s_bar, kKmerBitmapBytes);
+      TmaLoad1D(s_bitmap, km.bitmap, kKmerBitmapBytes, s_bar);
+    }
   }
   if (threadIdx.x < 32) { s_base[threadIdx.x] = 0; s_count[threadIdx.x] = 0; }
 
@@ -1358,26 +1409,60 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
   const uint32_t bm_base = SmemAddr(s_bitmap);
   const uint4* src = reinterpret_cast<const uint4*>(text + cta_base + ((uint64_t)w_row0 << 9)) + lane;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  // the 16 bytes before my warp's first row (lane 31's codes of "the row before"), then four rows in flight;
+  // issued before the tables are built so that they arrive meanwhile
+  const bool has_prev = w_row0 < w_row1 && cta_row0 + w_row0 > 0;
+  const uint4 prev16 = has_prev ? __ldg(reinterpret_cast<const uint4*>(text + cta_base + ((uint64_t)w_row0 << 9) - 16)) : zero4;
   uint4 v0 = w_row0 < w_load1 ? __ldg(src) : zero4;
   uint4 v1 = w_row0 + 1 < w_load1 ? __ldg(src + 32) : zero4;
   uint4 v2 = w_row0 + 2 < w_load1 ? __ldg(src + 64) : zero4;
   uint4 v3 = w_row0 + 3 < w_load1 ? __ldg(src + 96) : zero4;
-  src += 128;
-  uint32_t prevQ = 0;                                       // lane 31: codes of the 16 bytes before the row
-  if (w_row0 < w_row1 && cta_row0 + w_row0 > 0)
-    prevQ = KmerPack(__ldg(reinterpret_cast<const uint4*>(text + cta_base + ((uint64_t)w_row0 << 9) - 16)), fm, mult);
-  uint32_t* my_raw = s_raw + warp * kKmerWarpRaw;
-  uint32_t* my_idx = s_idx + warp * kKmerWarpRaw;
-  uint32_t n_raw = 0;                                       // hits of my warp so far (uniform)
-  const int from = (lane + 31) & 31;
-  __syncthreads();                                          // the barrier is initialised
-  MbarWait(s_bar, 0);
+  if (from_list) {
+    // the bitmap: index x = 7 + R codes; bit set iff one of its R 8-mers (x >> 2k) & 0xFFFF is on the list
+    uint4* b4 = reinterpret_cast<uint4*>(s_bitmap);
+#pragma unroll
+    for (uint32_t i = 0; i < kKmerBitmapBytes / 16 / kKmerThreads; ++i) b4[i * kKmerThreads + threadIdx.x] = zero4;
+    if (threadIdx.x < kKmerHashSlots) s_hkey[threadIdx.x] = 0;
+  }
+  if (threadIdx.x < kKmerTabWords) s_tab[threadIdx.x] = tab_word;
+  __syncthreads();                                          // tables copied, bitmap zeroed / the barrier is initialised
+  if (from_list) {
+    // 8-mer a at codes [k, k + 8) of x: the k codes below it (fl) pick the word together with a's low bits, the
+    // R-1-k codes above it (fh) only pick bits of that word: one atomic per (a, k, fl), 1 + 4 + .. + 4^(R-1) per a
+    constexpr uint32_t kPerA = ((1u << (2 * R)) - 1u) / 3u;
+    const uint32_t total = km.n_list * kPerA;
+    for (uint32_t i = threadIdx.x; i < total; i += kKmerThreads) {
+      const uint32_t a = s_tab[kKmerTabListX + i / kPerA];
+      uint32_t rem = i % kPerA, k = 0;
+      while (rem >= (1u << (2 * k))) { rem -= 1u << (2 * k); ++k; }
+      const uint32_t fl = rem;
+      const uint32_t xl = fl | (a << (2 * k));             // x without the codes above the 8-mer
+      const uint32_t sh = 16 + 2 * k - kKmerWordBits;      // where those codes sit in x >> kKmerWordBits
+      uint32_t bits = 0;
+      for (uint32_t fh = 0; fh < (1u << (2 * (R - 1 - k))); ++fh) bits |= 1u << (31 - ((xl >> kKmerWordBits) | (fh << sh)));
+      atomicOr(&s_bitmap[xl & ((1u << kKmerWordBits) - 1u)], bits);
+    }
+    if (threadIdx.x < km.n_list) {
+      const uint32_t a = s_tab[kKmerTabListX + threadIdx.x];
+      uint32_t slot = ((a * 0x9E3Bu) >> 5) & (kKmerHashSlots - 1u);
+      while (atomicCAS(&s_hkey[slot], 0u, a | 0x10000u) != 0u) slot = (slot + 1u) & (kKmerHashSlots - 1u);
+      s_hval[slot] = s_tab[kKmerTabListMask + threadIdx.x];
+    }
+    __syncthreads();
+  } else {
+    MbarWait(s_bar, 0);
+  }
+  uint32_t prevQ = has_prev ? KmerPack(prev16, fm, mult) : 0u;   // lane 31: codes of the 16 bytes before the row
   KmerTrace(run, 1);
-  for (uint32_t r = w_row0; r < w_row1; ++r) {
-    const uint32_t Q = KmerPack(v0, fm, mult);
-    v0 = v1; v1 = v2; v2 = v3;
-    v3 = r + 4 < w_load1 ? __ldg(src) : zero4;
-    src += 32;
+  uint32_t* my_raw = s_raw + warp * kKmerWarpRaw;
+  uint32_t* my_ent = s_ent + warp * kKmerWarpRaw;
+  uint32_t n_ent = 0;                                       // 16-byte groups of my warp with a hit so far (uniform)
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int from = (lane + 31) & 31;
+  // one row: pack my 16 bytes, refill the register they came from with the row four ahead, look the 16 ends up
+  auto row = [&](uint4& v, uint32_t r) {
+    const uint32_t Q = KmerPack(v, fm, mult);
+    v = r + 4 < w_load1 ? __ldg(src + (size_t)(r + 4 - w_row0) * 32) : zero4;
     // the codes before mine: my left neighbour's; lane 0 gets lane 31's of the row before
     const uint32_t P = __shfl_sync(kFullMask, lane == 31 ? prevQ : Q, from);
     prevQ = Q;
@@ -1390,26 +1475,20 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
       const uint32_t word = Lds32(bm_base + (w & ((4u << kKmerWordBits) - 4u)));
       acc = __funnelshift_l(__funnelshift_l(0u, word, w >> (kKmerWordBits + 2)), acc, 1);   // bit kKmerTests-1-t: lookup t
     }
-    if (__any_sync(kFullMask, acc != 0)) {
-      // rare (about one row in four on regex-dna): append the row's hits, in position order, to my warp's list
-      const uint32_t cnt = __popc(acc);
-      const uint32_t incl = WarpInclusiveScan(cnt);
-      uint32_t at = n_raw + incl - cnt;
-      uint32_t x = __brev(acc) >> (32 - kKmerTests);        // bit t: lookup t
-      const unsigned long long stream = ((unsigned long long)Q << 32) | P;
-      while (x) {
-        const int t = __ffs(x) - 1;
-        x &= x - 1;
-        const int xt = t * R < 16 - R ? t * R : 16 - R;
-        if (at < kKmerWarpRaw) {
-          // first of the R ends (relative to the CTA's first byte) | the first end that is this lookup's own << 30
-          my_raw[at] = (((r << 5) + lane) * 16u + xt + 1u) | ((uint32_t)(t * R - xt) << 30);
-          my_idx[at] = (uint32_t)(stream >> (18 + 2 * xt)) & ((1u << kKmerIdxBits) - 1u);
-        }
-        ++at;
-      }
-      n_raw += __shfl_sync(kFullMask, incl, 31);
+    // a row with hits (about one in four on regex-dna): one entry per lane with a hit, in lane = position order
+    const uint32_t bal = __ballot_sync(kFullMask, acc != 0);
+    if (bal) {
+      const uint32_t at = n_ent + __popc(bal & lt_mask);
+      if (acc && at < kKmerWarpRaw) my_ent[at] = (((r << 5) + lane) << 8) | acc;
+      n_ent += __popc(bal);
     }
+  };
+  {
+    uint32_t r = w_row0;
+    for (; r + 4 <= w_row1; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
+    if (r < w_row1) row(v0, r);
+    if (r + 1 < w_row1) row(v1, r + 1);
+    if (r + 2 < w_row1) row(v2, r + 2);
   }
   KmerTrace(run, 2);
   if (run.debug_stop == 1) return;
@@ -1417,6 +1496,27 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
   // ---- my warp's hits: exact check, per-member counts -------------------------------
   // candidate R h + k = end k of hit h; lane j keeps member j's numbers
   unsigned int flags = 0;
+  if (n_ent > kKmerWarpRaw) { flags |= kFinDense; n_ent = 0; }
+  __syncwarp();
+  // groups -> hits, in position order: one entry of my_raw per lookup that hit
+  uint32_t n_raw = 0;
+  for (uint32_t base = 0; base < n_ent; base += 32) {
+    const uint32_t ent = base + lane < n_ent ? my_ent[base + lane] : 0u;
+    const uint32_t acc = ent & 0xFFu, pos16 = (ent >> 8) * 16u;     // bit kKmerTests-1-t: lookup t hit
+    const uint32_t cnt = __popc(acc);
+    const uint32_t incl = WarpInclusiveScan(cnt);
+    uint32_t at = n_raw + incl - cnt;
+    uint32_t x = __brev(acc) >> (32 - kKmerTests);                  // bit t: lookup t
+    while (x) {
+      const int t = __ffs(x) - 1;
+      x &= x - 1;
+      const int xt = t * R < 16 - R ? t * R : 16 - R;
+      // first of the R ends (relative to the CTA's first byte) | the first end that is this lookup's own << 30
+      if (at < kKmerWarpRaw) my_raw[at] = (pos16 + xt + 1u) | ((uint32_t)(t * R - xt) << 30);
+      ++at;
+    }
+    n_raw += __shfl_sync(kFullMask, incl, 31);
+  }
   if (n_raw > kKmerWarpRaw) { flags |= kFinDense; n_raw = 0; }
   __syncwarp();
   const uint32_t n_cand = R * n_raw;
@@ -1431,13 +1531,13 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
       erel = (raw & 0x3FFFFFFFu) + k;
       const uint64_t e = cta_base + erel;
       if (k >= (raw >> 30) && e <= n && run.debug_stop != 6) {
-        const uint32_t mv = KmerVerify(text, e, (my_idx[h] >> (2 * k)) & 0xFFFFu, km);
+        const uint32_t mv = KmerVerify(text, e, fm, mult, km.shift, km.canon, from_list, km.mask16, s_hkey, s_hval, s_lenle);
         for (uint32_t mm = mv; mm; mm &= mm - 1) {
           const int j = __ffs(mm) - 1;
-          const uint64_t b = e - tb.match_len[j];
+          const uint64_t b = e - s_mlen[j];
           if (b >= range.own_begin && b < range.own_end) {
             m |= 1u << j;
-            if (b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
+            if (run.has_carry && b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
           }
         }
       }
@@ -1445,10 +1545,10 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
     }
     // a candidate overlaps an earlier one of the same member iff that one ends less than a match length before
     // it: its predecessor in this pass, the last one of the pass before; other warps and CTAs: the seam checks
-    for (int j = 0; j < K; ++j) {
+    for (uint32_t todo = __reduce_or_sync(kFullMask, m); todo; todo &= todo - 1) {
+      const int j = __ffs(todo) - 1;
       const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
-      if (!bal) continue;
-      const uint32_t L = tb.match_len[j];
+      const uint32_t L = s_mlen[j];
       const int lo = __ffs(bal) - 1, hi = 31 - __clz(bal);
       const uint32_t e_lo = __shfl_sync(kFullMask, erel, lo), e_hi = __shfl_sync(kFullMask, erel, hi);
       const uint32_t before = bal & ((1u << lane) - 1u);
@@ -1467,6 +1567,7 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
   s_wfirst[warp * 32 + lane] = firstj;
   s_wlast[warp * 32 + lane] = lastj;
   if (flags) atomicOr(s_flags, flags);
+  KmerTrace(run, 8);
   __syncthreads();
   KmerTrace(run, 3);
   if (run.debug_stop == 2) return;
@@ -1475,7 +1576,7 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
   const bool last_cta = blockIdx.x + 1 == gridDim.x;
   if (warp < K) {
     const int j = warp;
-    const uint32_t L = tb.match_len[j];
+    const uint32_t L = s_mlen[j];
     const uint32_t c = s_wcnt[lane * 32 + j], fe = s_wfirst[lane * 32 + j], le = s_wlast[lane * 32 + j];
     const uint32_t incl = WarpInclusiveScan(c);
     s_woff[lane * 32 + j] = incl - c;
@@ -1507,6 +1608,9 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
       if (last_cta) s_seam[(size_t)blockIdx.x * K + j] = make_uint2((uint32_t)(f64 ? f64 - seam_base : 0), (uint32_t)(l64 ? l64 - seam_base : 0));
     }
   }
+  // nobody polls before this CTA's own records are out: warps spinning on system-scope loads keep the
+  // load/store queue full and starved the publishing warps of their shared-memory and shuffle slots
+  __syncthreads();
   KmerTrace(run, 4);
   if (run.debug_stop == 3) return;
   // ---- exchange: the CTAs before me.  Warp w reads CTA w, w + 32, ... (lane j = member j), five CTAs' records
@@ -1564,7 +1668,7 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
           const unsigned long long at = (unsigned long long)s_base[j] + s_woff[warp * 32 + j] + dj + __popc(bal & ((1u << lane) - 1u));
           if (at < run.out_cap)
             reinterpret_cast<ulonglong2*>(run.out_pairs + (uint64_t)j * 2 * run.out_stride)[at] =
-                make_ulonglong2(e - tb.match_len[j] + run.base_offset, e + run.base_offset);
+                make_ulonglong2(e - s_mlen[j] + run.base_offset, e + run.base_offset);
         }
         if (lane == j) done += __popc(bal);
       }
@@ -1575,7 +1679,7 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, KmerTable
   // ---- the last CTA: seams between CTAs, totals, report.  Warp j = member j; lane l looks at CTAs 5 l .. 5 l + 4
   if (warp < K) {
     const int j = warp;
-    const uint32_t L = tb.match_len[j];
+    const uint32_t L = s_mlen[j];
     uint2 fl[5];
     uint32_t lm = 0;                                         // last end among my five
 #pragma unroll

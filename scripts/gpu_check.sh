@@ -23,8 +23,8 @@ if [ "${RJ_PROFILE:-1}" = "1" ]; then
 echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_bench.log 2>&1
 tail -3 gpurun_out/ncu_bench.log
-echo "== ncu full dfa"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_set_tma -s 3 -c 2 -o gpurun_out/prof_dfa -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full.log 2>&1
+echo "== ncu full set scan"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_set_ -s 3 -c 1 -o gpurun_out/prof_set -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 fi
 ls -la gpurun_out

@@ -136,3 +136,75 @@ def test_sets_without_a_kmer_index():
     assert _Set(["abcde", "edcba"]).kmer_tables() is None          # five live bytes
     assert _Set(["aaaaaaaaa", "ccccccccc"]).kmer_tables() is None  # nine bytes long
     assert _Set(["a[bB]", "ba"]).kmer_tables() is None             # no two adjacent bits tell a, b, B apart
+
+
+@pytest.mark.parametrize("pats", [W.DNA_PATTERNS, ["ab", "b[ab]a", "abba|baab"]])
+def test_bitmap_built_from_the_accepted_list(pats):
+    """k_set_kmer builds the bitmap (and a hash of the member masks) in shared memory from the list of
+    accepted 8-mers when that list is short: the same arithmetic on the CPU must give the host's bitmap."""
+    info, bitmap, mask16 = _Set(pats).kmer_tables()
+    R = int(info[13])
+    word_bits = 2 * (7 + R) - 5
+    built = np.zeros(1 << word_bits, dtype=np.uint32)
+    slots = 512
+    hkey = np.zeros(slots, dtype=np.uint32)
+    hval = np.zeros(slots, dtype=np.uint32)
+    accepted = [int(a) for a in np.nonzero(mask16)[0]]
+    for a in accepted:
+        # one atomicOr per (a, k, fl): the codes above the 8-mer (fh) only pick bits of the word
+        for k in range(R):
+            for fl in range(1 << (2 * k)):
+                xl = fl | (a << (2 * k))
+                sh = 16 + 2 * k - word_bits
+                bits = 0
+                for fh in range(1 << (2 * (R - 1 - k))):
+                    bits |= 1 << (31 - ((xl >> word_bits) | (fh << sh)))
+                built[xl & ((1 << word_bits) - 1)] |= np.uint32(bits)
+        if len(accepted) <= 128:
+            slot = ((a * 0x9E3B) >> 5) & (slots - 1)
+            while hkey[slot]:
+                slot = (slot + 1) & (slots - 1)
+            hkey[slot], hval[slot] = a | 0x10000, mask16[a]
+    assert np.array_equal(built, bitmap)
+    if len(accepted) <= 128:                                  # kKmerListMax: the hash must hold every entry
+        for a in accepted:
+            slot = ((a * 0x9E3B) >> 5) & (slots - 1)
+            while hkey[slot] != (a | 0x10000):
+                assert hkey[slot] != 0
+                slot = (slot + 1) & (slots - 1)
+            assert hval[slot] == mask16[a]
+
+
+def test_verify_swar_arithmetic():
+    """KmerVerify: the eight bytes before an end as one 64-bit word; codes packed with the AND + multiply of
+    KmerPack, the canonical byte of every code fetched with one byte-permute per four bytes."""
+    info, _, _ = _Set(W.DNA_PATTERNS).kmer_tables()
+    shift, canon, canon_ok = int(info[0]), int(info[1]), int(info[2])
+    for cd in range(4):                                       # engine.cu: a code without a live byte gets a byte of another code
+        if not (canon_ok >> cd) & 1:
+            canon |= ((((cd + 1) & 3) << shift) & 0xFF) << (8 * cd)
+    fm, mult = (0x03030303 << shift) & 0xFFFFFFFF, 0x01041040 >> shift
+    rng = np.random.RandomState(11)
+    alpha = np.frombuffer(b"acgtacgtacgtACGTBn\xff\x00", dtype=np.uint8)
+
+    def prmt(a, sel):
+        return sum(((a >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i) for i in range(4))
+
+    for _ in range(3000):
+        by = [int(b) for b in alpha[rng.randint(0, len(alpha), 8)]]
+        lo = by[0] | by[1] << 8 | by[2] << 16 | by[3] << 24
+        hi = by[4] | by[5] << 8 | by[6] << 16 | by[7] << 24
+        x16 = ((((lo & fm) * mult) & 0xFFFFFFFF) >> 24) | (((((hi & fm) * mult) & 0xFFFFFFFF) >> 24) << 8)
+        diff = 0
+        for half, word in ((0, lo), (1, hi)):
+            c = (word >> shift) & 0x03030303
+            sel = ((c | (c >> 4)) & 0xFF) | (((c >> 8) | (c >> 12)) & 0xFF00)
+            diff |= (prmt(canon, sel) ^ word) << (32 * half)
+        v = 8 if diff == 0 else (64 - diff.bit_length()) >> 3
+        # the definition, byte by byte
+        exp_x, run = 0, 0
+        for i, b in enumerate(by):
+            code = (b >> shift) & 3
+            exp_x |= code << (2 * i)
+            run = run + 1 if ((canon >> (8 * code)) & 0xFF) == b else 0
+        assert (x16, v) == (exp_x, run), by
