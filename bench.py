@@ -31,7 +31,12 @@ over the calls of a step:  value = 9 * N_bytes / step_time.
                   results on these patterns) on the host cores.
   N > 1 ......... weak scaling: every rank owns one 50 MB slab of an N*50 MB
                   text (plus a right halo), resolves it locally and the chain is
-                  stitched with one all-gather per pattern (rejit_b200/sharding.py).
+                  stitched with ONE all-gather of a small record per step
+                  (rejit_b200/sharding.py).  The records are host data and all
+                  ranks share a box, so the all-gather runs over a shared-memory
+                  mailbox (config.stitch = "shm", ~2 us); the same step with the
+                  records sent through an NCCL all-gather is reported next to it
+                  as `nccl_stitch` (RJ_STITCH=nccl makes it the headline).
 """
 import argparse
 import ctypes
@@ -294,9 +299,10 @@ def main():
     if world > 1:
         import torch
         import torch.distributed as dist
+        import datetime
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
         tdev = torch.device("cuda", local_rank)
+        dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=180), device_id=tdev)
     if rj.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (rejit_b200 has no CPU fallback)")
 
@@ -318,7 +324,42 @@ def main():
     rset = rj.RegejSet(regs)
     K = len(regs)
 
-    def run_set(stats):
+    # the stitch exchange at N>1: a shared-memory mailbox (the records are host data, all ranks are on one box);
+    # the same protocol over an NCCL all-gather is timed next to it (`nccl_stitch`)
+    exchanges = {}
+    if world > 1:
+        exchanges["nccl"] = sharding.NcclExchange(dist, world, tdev)
+        if os.environ.get("RJ_STITCH", "shm") == "shm":
+            try:
+                ex = sharding.ShmExchange(rank, world, 3 * 33, os.environ.get("MASTER_PORT", "0"))
+                dist.barrier()
+                ex.attach()
+                exchanges["shm"] = ex
+            except Exception as exc:                      # no /dev/shm: every rank falls back together below
+                print("bench.py: shared-memory stitch unavailable (%s)" % exc, file=sys.stderr)
+            ok = torch.tensor([1 if "shm" in exchanges else 0], dtype=torch.int64, device=tdev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                exchanges.pop("shm", None)
+    stitch = "shm" if "shm" in exchanges else "nccl"
+    config["stitch"] = stitch if world > 1 else "none (one slab)"
+
+    class Timed:
+        """Host time spent inside the exchange (it contains the wait for the slowest rank)."""
+        def __init__(self, inner):
+            self.inner, self.spent = inner, 0.0
+
+        def __call__(self, rec):
+            t0 = time.perf_counter()
+            rows = self.inner(rec)
+            self.spent += time.perf_counter() - t0
+            return rows
+    timed = {k: Timed(v) for k, v in exchanges.items()}
+    if world > 1:
+        config["timing"] = ("step = device pipeline time of the rank's own call (CUDA events, as at N=1) + host time inside the "
+                            "stitch exchange; the ranks are aligned with an untimed exchange after the L2 flush, max over ranks")
+
+    def run_set(stats, how=None):
         """The nine patterns in ONE fused pass over the resident slab (+ the stitch
         all-gather at N>1); returns (counts, pipeline_ms, collective_s)."""
         if world == 1:
@@ -336,15 +377,23 @@ def main():
             outs = [(cout[j].cur + slab_lo, cout[j].tail + slab_lo if cout[j].tail != sharding.NO_TAIL else sharding.NO_TAIL)
                     for j in range(K)]
             return cnts, outs
-        t0 = time.perf_counter()
-        cnts, _ = sharding.stitched_counts_set(dist, rank, world, slab_lo, K, run, device=tdev)
-        coll = time.perf_counter() - t0 - ms[0] / 1e3
-        return cnts, ms[0], max(coll, 0.0)
+        ex = timed[how or stitch]
+        ex.spent = 0.0
+        cnts, _ = sharding.stitched_counts_set(dist, rank, world, slab_lo, K, run, device=tdev, exchange=ex)
+        return cnts, ms[0], ex.spent
 
-    def one_step_fused():
+    def flush():
+        """L2 flush, outside every timed region: at N > 1 the step is timed by the host clock (it contains the
+        exchange), so the flush kernel must have finished before that clock starts."""
         rj.lib().rejit_b200_flush_l2(local_rank)
+        if world > 1:
+            torch.cuda.synchronize(local_rank)
+            exchanges[stitch]([0])                            # all ranks start the step together (untimed)
+
+    def one_step_fused(how=None):
+        flush()
         st = rj.Stats()
-        cnts, ms, cs = run_set(st)
+        cnts, ms, cs = run_set(st, how)
         return ms + cs * 1e3, st.scan_ms, st.launches, cnts
 
     def run_pattern(r, stats):
@@ -364,15 +413,15 @@ def main():
             ms[0] += stats.total_ms
             tail_g = cout.tail + slab_lo if cout.tail != sharding.NO_TAIL else sharding.NO_TAIL
             return c, cout.cur + slab_lo, tail_g
-        t0 = time.perf_counter()
-        cnt, _ = sharding.stitched_count(dist, rank, world, slab_lo, run, device=tdev)
-        coll = time.perf_counter() - t0 - ms[0] / 1e3
-        return cnt, ms[0], max(coll, 0.0)
+        ex = timed[stitch]
+        ex.spent = 0.0
+        cnt, _ = sharding.stitched_count(dist, rank, world, slab_lo, run, device=tdev, exchange=ex)
+        return cnt, ms[0], ex.spent
 
     def one_step():
         step_ms, scan_ms, launches, counts, coll_s = 0.0, 0.0, 0, [], 0.0
         for r in regs:
-            rj.lib().rejit_b200_flush_l2(local_rank)
+            flush()
             st = rj.Stats()
             cnt, ms, cs = run_pattern(r, st)
             step_ms += ms + cs * 1e3
@@ -403,6 +452,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         f_ms = float(t.item())
         dist.barrier()
+    # the same fused step with the stitch over NCCL (N > 1 only)
+    nccl_ms = None
+    if world > 1 and stitch != "nccl":
+        for _ in range(3):
+            one_step_fused("nccl")
+        nccl_ms = 0.0
+        for _ in range(args.steps):
+            nccl_ms += one_step_fused("nccl")[0]
+        t = torch.tensor([nccl_ms], dtype=torch.float64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nccl_ms = float(t.item()) / args.steps
+        dist.barrier()
     t_wall = time.perf_counter()
     tot_ms = tot_scan = 0.0
     launches = 0
@@ -422,9 +483,11 @@ def main():
     if sampler and wall < 0.5:
         # the timed region is only milliseconds long: keep the same load running
         # until nvidia-smi (100 ms period) has seen it a few times
+        # (rank 0 only, so nothing here may enter a collective: the local fused call, no stitch)
         t_end = time.perf_counter() + 0.6
+        st_keep = rj.Stats()
         while time.perf_counter() < t_end:
-            one_step()
+            rset.match_all_device(dtext, stats=st_keep)
     clocks = sampler.stop() if sampler else None
     ms_per_step = tot_ms / args.steps                       # nine separate MatchAll calls
     value_calls = len(patterns) * total_text / (ms_per_step / 1e3) / 1e9
@@ -504,6 +567,11 @@ def main():
     e2e_percall = time_e2e(False, 3)
     L.rejit_b200_pinned_free(pinned)
 
+    if dist is not None:
+        dist.barrier()
+    for ex in exchanges.values():
+        if hasattr(ex, "close"):
+            ex.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -543,6 +611,9 @@ def main():
             "e2e_per_pattern_calls": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": n_own},
             "e2e_per_call_upload": {"value": round(e2e_percall, 3), "unit": "GB/s",
                                     "h2d_bytes_per_step": len(patterns) * n_own},
+            "nccl_stitch": None if nccl_ms is None else
+            {"value": round(len(patterns) * total_text / (nccl_ms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(nccl_ms, 4),
+             "how": "the same fused step with the stitch records exchanged by an NCCL all-gather instead of the shared-memory mailbox"},
             "gpu_launches": f_launches,
             "roofline": {"bound": "hbm", "kernel": set_kernel, "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic_of(set_kernel),

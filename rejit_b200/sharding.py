@@ -7,7 +7,8 @@ from the left.  One all-gather of a 4-word record per rank — (carry.cur,
 carry.tail, match count, slab begin) — then tells every rank whether the chain
 arriving from its left neighbour differs from that assumption; only in that
 case (a match straddling or abutting the boundary) does the rank resolve again
-with the real carry, and only then is a further round needed.
+with the real carry, and only then is a further round needed.  There is no
+second collective: all ranks evaluate the same predicate on the same rows.
 """
 from __future__ import annotations
 
@@ -22,78 +23,151 @@ def slab_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, hi
 
 
+class NcclExchange:
+    """The all-gather as a torch.distributed collective (backend nccl: the record
+    goes host -> device -> NVLink -> device -> host; backend gloo in the CPU tests)."""
+    name = "nccl"
+
+    def __init__(self, dist, world: int, device=None):
+        self.dist, self.world, self.device = dist, world, device
+
+    def __call__(self, rec):
+        import torch
+        t = torch.tensor(rec, dtype=torch.int64, device=self.device)
+        if self.world == 1:
+            return [t.tolist()]
+        gathered = [torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(gathered, t)
+        return [g.tolist() for g in gathered]
+
+
+class ShmExchange:
+    """The same all-gather through a POSIX shared-memory mailbox, for ranks on ONE
+    box (the only layout this engine shards over, SURVEY.md \u00a78e).  The records are
+    produced in host memory (the engine reports through mapped pinned memory), so a
+    host-to-host exchange skips two PCIe copies, the collective's launch and a
+    stream synchronisation: ~2 us instead of ~100 us per round, which matters when
+    the whole step is 40 us.
+
+    Layout: [world][2][1 + words] int64; a rank writes its record into the buffer
+    (seq & 1), then the sequence number; readers spin until every rank shows the
+    current sequence number.  Two buffers suffice: nobody can finish exchange s+1
+    before everybody has written it, i.e. before everybody has read exchange s."""
+    name = "shm"
+
+    def __init__(self, rank: int, world: int, words: int, key: str, timeout_s: float = 60.0):
+        import time
+        import numpy as np
+        from multiprocessing import shared_memory
+        self.rank, self.world, self.words = rank, world, words
+        size = world * 2 * (1 + words) * 8
+        name = "rejit_b200_" + key
+        if rank == 0:
+            try:
+                stale = shared_memory.SharedMemory(name=name)
+                stale.close()
+                stale.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=size)
+            self.shm.buf[:size] = bytes(size)
+        else:
+            self.shm = None
+        self._name, self._size, self._timeout = name, size, timeout_s
+        self._np, self._time = np, time
+        self.a = None
+        self.seq = 0
+
+    def attach(self):
+        """Call after a barrier that follows rank 0's constructor."""
+        from multiprocessing import shared_memory
+        if self.shm is None:
+            self.shm = shared_memory.SharedMemory(name=self._name)
+        self.a = self._np.ndarray((self.world, 2, 1 + self.words), dtype=self._np.int64, buffer=self.shm.buf)
+
+    def __call__(self, rec):
+        flat = self._np.asarray(rec, dtype=self._np.int64).reshape(-1)
+        assert flat.size <= self.words
+        self.seq += 1
+        b = self.seq & 1
+        mine = self.a[self.rank, b]
+        mine[1:1 + flat.size] = flat
+        mine[0] = self.seq                                   # published (x86 keeps the store order)
+        deadline = self._time.perf_counter() + self._timeout
+        col = self.a[:, b, 0]
+        while not (col == self.seq).all():
+            if self._time.perf_counter() > deadline:
+                raise TimeoutError("ShmExchange: a rank did not arrive (seq %d, seen %s)" % (self.seq, col.tolist()))
+        shape = self._np.asarray(rec).shape
+        return [self.a[r, b, 1:1 + flat.size].reshape(shape).tolist() for r in range(self.world)]
+
+    def close(self):
+        try:
+            self.a = None
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
 def stitched_count(dist, rank: int, world: int, slab_lo: int,
-                   run: Callable[[int, int], Tuple[int, int, int]], device=None) -> Tuple[int, int]:
+                   run: Callable[[int, int], Tuple[int, int, int]], device=None, exchange=None) -> Tuple[int, int]:
     """run(carry_cur, carry_tail) -> (count, carry_out_cur, carry_out_tail), all
-    offsets global.  Returns (global match count, collective rounds used)."""
-    import torch
-    used = (slab_lo, NO_TAIL)
-    count, ccur, ctail = run(*used)
+    offsets global.  Returns (global match count, collective rounds used).
+
+    ONE collective per round: every rank sees every rank's record and therefore
+    knows, without asking, which ranks have to resolve again (the carry a rank
+    assumed is a function of the records of the round before)."""
+    exchange = exchange or NcclExchange(dist, world, device)
+    count, ccur, ctail = run(slab_lo, NO_TAIL)
+    used = None                       # the carry every rank resolved with; known after the first gather
     rounds = 0
     while True:
-        rec = torch.tensor([ccur, ctail if ctail != NO_TAIL else -1, count, slab_lo], dtype=torch.int64,
-                           device=device)
-        if world > 1:
-            gathered = [torch.zeros_like(rec) for _ in range(world)]
-            dist.all_gather(gathered, rec)
-            rows = [g.tolist() for g in gathered]
-        else:
-            rows = [rec.tolist()]
+        rows = exchange([ccur, ctail if ctail != NO_TAIL else -1, count, slab_lo])
         rounds += 1
-        # every rank evaluates the same predicate for every rank
-        redo = []
+        if used is None:
+            used = [(rows[r][3], NO_TAIL) for r in range(world)]
+        changed = False
         for r in range(1, world):
             left_cur, left_tail = rows[r - 1][0], rows[r - 1][1]
             lo_r = rows[r][3]
-            want = (max(left_cur, lo_r), left_tail if left_tail == lo_r else -1)
-            redo.append(want)
-        changed = False
-        if rank > 0:
-            want = redo[rank - 1]
-            want_carry = (want[0], want[1] if want[1] != -1 else NO_TAIL)
-            if want_carry != used:
-                used = want_carry
-                count, ccur, ctail = run(*used)
+            want = (max(left_cur, lo_r), left_tail if left_tail == lo_r else NO_TAIL)
+            if want != used[r]:
+                used[r] = want
                 changed = True
-        flag = torch.tensor([1 if changed else 0], dtype=torch.int64, device=device)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag.item()) == 0:
+                if r == rank:
+                    count, ccur, ctail = run(*want)
+        if not changed:
             return sum(int(r[2]) for r in rows), rounds
 
 
-def stitched_counts_set(dist, rank: int, world: int, slab_lo: int, k: int, run, device=None):
+def stitched_counts_set(dist, rank: int, world: int, slab_lo: int, k: int, run, device=None, exchange=None):
     """Set version: run(carries) -> (counts[k], carries_out[k]) with carries as
-    lists of (cur, tail) in global offsets.  One all-gather of a [k, 3] block per
-    rank; a rank resolves again only if some member's arriving chain differs.
-    Returns (global counts[k], collective rounds)."""
-    import torch
-    used = [(slab_lo, NO_TAIL)] * k
-    counts, couts = run(used)
+    lists of (cur, tail) in global offsets.  One all-gather of a [k + 1, 3] block
+    per rank and round; a rank resolves again only if some member's arriving
+    chain differs.  Returns (global counts[k], collective rounds)."""
+    exchange = exchange or NcclExchange(dist, world, device)
+    counts, couts = run([(slab_lo, NO_TAIL)] * k)
+    used = None
     rounds = 0
     while True:
-        rec = torch.tensor([[couts[j][0], couts[j][1] if couts[j][1] != NO_TAIL else -1, counts[j]] for j in range(k)] +
-                           [[slab_lo, 0, 0]], dtype=torch.int64, device=device)
-        if world > 1:
-            gathered = [torch.zeros_like(rec) for _ in range(world)]
-            dist.all_gather(gathered, rec)
-            rows = [g.tolist() for g in gathered]
-        else:
-            rows = [rec.tolist()]
+        rows = exchange([[couts[j][0], couts[j][1] if couts[j][1] != NO_TAIL else -1, counts[j]] for j in range(k)] +
+                        [[slab_lo, 0, 0]])
         rounds += 1
+        if used is None:
+            used = [[(rows[r][k][0], NO_TAIL)] * k for r in range(world)]
         changed = False
-        if rank > 0:
-            lo_r = rows[rank][k][0]
+        for r in range(1, world):
+            lo_r = rows[r][k][0]
             want = []
             for j in range(k):
-                left_cur, left_tail = rows[rank - 1][j][0], rows[rank - 1][j][1]
+                left_cur, left_tail = rows[r - 1][j][0], rows[r - 1][j][1]
                 want.append((max(left_cur, lo_r), left_tail if left_tail == lo_r else NO_TAIL))
-            if want != used:
-                used = want
-                counts, couts = run(used)
+            if want != used[r]:
+                used[r] = want
                 changed = True
-        flag = torch.tensor([1 if changed else 0], dtype=torch.int64, device=device)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag.item()) == 0:
+                if r == rank:
+                    counts, couts = run(want)
+        if not changed:
             return [sum(int(r[j][2]) for r in rows) for j in range(k)], rounds

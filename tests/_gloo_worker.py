@@ -27,6 +27,11 @@ def main():
                                    ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     cases = json.loads(sys.argv[1])
     out = []
+    exchange = None                      # default: the torch.distributed all-gather (gloo here, nccl under bench.py)
+    if os.environ.get("RJ_STITCH") == "shm":
+        exchange = sharding.ShmExchange(rank, world, 3 * 33, os.environ.get("MASTER_PORT", "0"))
+        dist.barrier()
+        exchange.attach()
     for pat, text_hex in cases:
         text = bytes.fromhex(text_hex)
         pb = pat.encode("latin-1")
@@ -37,10 +42,32 @@ def main():
             c = L.hostsim_slab_run(pb, len(pb), text, len(text), lo, hi, 1 if rank + 1 == world else 0,
                                    cur, tail, ctypes.byref(oc), ctypes.byref(ot))
             return int(c), int(oc.value), int(ot.value)
-        total, rounds = sharding.stitched_count(dist, rank, world, lo, run)
+        total, rounds = sharding.stitched_count(dist, rank, world, lo, run, exchange=exchange)
         out.append([total, rounds])
+    # pattern sets (bench.py's fused step): one all-gather carries every member's record
+    set_out = []
+    for pats, text_hex in (json.loads(sys.argv[2]) if len(sys.argv) > 2 else []):
+        text = bytes.fromhex(text_hex)
+        lo, hi = sharding.slab_bounds(len(text), world, rank)
+
+        def run_set(carries):
+            counts, couts = [], []
+            for pat, (cur, tail) in zip(pats, carries):
+                pb = pat.encode("latin-1")
+                oc, ot = ctypes.c_uint64(), ctypes.c_uint64()
+                c = L.hostsim_slab_run(pb, len(pb), text, len(text), lo, hi, 1 if rank + 1 == world else 0,
+                                       cur, tail, ctypes.byref(oc), ctypes.byref(ot))
+                counts.append(int(c))
+                couts.append((int(oc.value), int(ot.value)))
+            return counts, couts
+        totals, rounds = sharding.stitched_counts_set(dist, rank, world, lo, len(pats), run_set, exchange=exchange)
+        set_out.append([totals, rounds])
     if rank == 0:
         print("RESULT " + json.dumps(out), flush=True)
+        print("SETRESULT " + json.dumps(set_out), flush=True)
+    if exchange is not None:
+        dist.barrier()
+        exchange.close()
     dist.destroy_process_group()
 
 

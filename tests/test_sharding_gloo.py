@@ -14,14 +14,38 @@ import rejit_oracle as O
 from conftest import ROOT
 
 
-def _run(world, cases, port):
+def _run(world, cases, port, set_cases=None, stitch="nccl"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "_gloo_worker.py"), json.dumps(cases)]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if set_cases is not None:
+        cmd.append(json.dumps(set_cases))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RJ_STITCH=stitch))
     assert p.returncode == 0, p.stderr[-2000:]
-    line = [l for l in p.stdout.split("\n") if l.startswith("RESULT ")][-1]
-    return json.loads(line[len("RESULT "):])
+    tag = "SETRESULT " if set_cases is not None else "RESULT "
+    line = [l for l in p.stdout.split("\n") if l.startswith(tag)][-1]
+    return json.loads(line[len(tag):])
+
+
+@pytest.mark.parametrize("world,port,stitch", [(2, 29613, "nccl"), (3, 29614, "nccl"), (2, 29615, "shm"), (4, 29616, "shm")])
+def test_set_stitching_over_gloo(hostsim, world, port, stitch):
+    """The fused-set stitch of bench.py --gpus N: k members' records in one all-gather per round."""
+    from rejit_b200 import workloads as W
+    seq = W.fasta_sequence(300).tobytes()
+    third = len(seq) // world
+    # matches of several members straddling and abutting every cut
+    planted = bytearray(seq)
+    for cut in range(third, len(seq) - 8, third):
+        planted[cut - 3:cut + 5] = b"agggtaaa"
+        planted[cut + 5:cut + 13] = b"tttaccct"
+    set_cases = [[W.DNA_PATTERNS, bytes(planted).hex()],
+                 [["aa", "aba", "ab"], (b"ab" * 40 + b"a" * 41).hex()],
+                 [["abc", "bca", "cab"], (b"abc" * 50).hex()]]
+    expect = [[len(O.Oracle(p).match_all(bytes.fromhex(t))) for p in pats] for pats, t in set_cases]
+    fixed = [["aa", (b"a" * 101).hex()], ["x|$", (b"ax\n" * 40).hex()], ["abc", (b"abc" * 41).hex()]]
+    got = _run(world, fixed * 5, port, set_cases * 5, stitch)
+    assert [g[0] for g in got] == expect * 5
+    assert max(g[1] for g in got) <= world
 
 
 @pytest.mark.parametrize("world,port", [(2, 29611), (3, 29612)])
