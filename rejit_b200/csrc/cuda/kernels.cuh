@@ -258,12 +258,52 @@ __device__ __forceinline__ void TmaLoad1D(void* smem_dst, const void* gmem_src, 
 // Survivors (rare) compare the rest of the needle from global memory.
 // Algorithmic traffic: N bytes read + 16 bytes written per occurrence.
 // ===========================================================================
-// Rare path of k_lit_scan, kept out of line so that the hot loop stays small:
-// validates the survivors of one 16-byte lane group (bounds, ownership, the rest
-// of the needle) and appends them in offset order.  Called by the whole warp.
-__device__ __noinline__ void LitEmit(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restrict__ needle,
-                                     uint32_t m, uint32_t p4, uint32_t pmask, const ScanRange& range,
-                                     const SubStore& out, uint64_t sub, uint32_t& k, uint64_t my, uint4 v, uint32_t nx) {
+// Hits of k_lit_scan are recorded in the hot loop as one shared-memory word per 16-byte lane group with a
+// survivor ({group index in the sub-region, 16 alignment bits}: a ballot and a store, no call -- a call from inside
+// the loop waits for every prefetched piece to land, which made dense texts latency-bound) and validated here, once
+// per sub-region: bounds, ownership, the rest of the needle; then appended in offset order.  Called by the whole warp.
+constexpr uint32_t kLitEntCap = kLitSubBytes / 16;      // every group of the sub-region may hold a survivor
+
+__device__ __noinline__ uint32_t LitFlush(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restrict__ needle,
+                                          uint32_t m, const ScanRange& range, const SubStore& out, uint64_t sub,
+                                          uint64_t sub_lo, const uint32_t* my_ent, uint32_t n_ent, uint32_t k) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  for (uint32_t base = 0; base < n_ent; base += 32) {
+    const uint32_t ent = base + lane < n_ent ? my_ent[base + lane] : 0u;
+    uint32_t valid = ent & 0xFFFFu;
+    const uint64_t my = sub_lo + (uint64_t)(ent >> 16) * 16;
+    uint32_t hh = valid;
+    while (hh) {
+      int j = __ffs(hh) - 1;
+      hh &= hh - 1;
+      uint64_t pos = my + j;
+      bool ok = pos >= range.own_begin && pos < range.own_end && pos + m <= n;
+      for (uint32_t i = 4; i < m && ok; ++i) ok = (text[pos + i] == needle[i]);
+      if (!ok) valid &= ~(1u << j);
+    }
+    __syncwarp();
+    uint32_t c = __popc(valid);
+    uint32_t incl = WarpInclusiveScan(c);
+    uint32_t total = __shfl_sync(kFullMask, incl, 31);
+    uint32_t idx = k + incl - c;
+    while (valid) {
+      int j = __ffs(valid) - 1;
+      valid &= valid - 1;
+      if (idx < out.cap) {
+        out.begin[sub * out.cap + idx] = my + j;
+        out.end[sub * out.cap + idx] = my + j + m;
+      }
+      ++idx;
+    }
+    k += total;
+  }
+  __syncwarp();
+  return k;
+}
+
+// the 16 alignment bits of one lane group: bit j = the first min(m, 4) needle bytes match at byte j
+__device__ __forceinline__ uint32_t LitMask(const uint4& v, uint32_t nx, uint32_t p4, uint32_t pmask) {
   const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
   uint32_t valid = 0;
 #pragma unroll
@@ -271,31 +311,7 @@ __device__ __noinline__ void LitEmit(const uint8_t* __restrict__ text, uint64_t 
     uint32_t x = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3));
     if (((x ^ p4) & pmask) == 0) valid |= 1u << j;
   }
-  uint32_t hh = valid;
-  while (hh) {
-    int j = __ffs(hh) - 1;
-    hh &= hh - 1;
-    uint64_t pos = my + j;
-    bool ok = pos >= range.own_begin && pos < range.own_end && pos + m <= n;
-    for (uint32_t i = 4; i < m && ok; ++i) ok = (text[pos + i] == needle[i]);
-    if (!ok) valid &= ~(1u << j);
-  }
-  __syncwarp();
-  uint32_t c = __popc(valid);
-  uint32_t incl = WarpInclusiveScan(c);
-  uint32_t total = __shfl_sync(kFullMask, incl, 31);
-  uint32_t idx = k + incl - c;
-  while (valid) {
-    int j = __ffs(valid) - 1;
-    valid &= valid - 1;
-    if (idx < out.cap) {
-      out.begin[sub * out.cap + idx] = my + j;
-      out.end[sub * out.cap + idx] = my + j + m;
-    }
-    ++idx;
-  }
-  __syncwarp();
-  k += total;
+  return valid;
 }
 
 template <bool kFull4>
@@ -325,9 +341,12 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   constexpr uint32_t kPieces = kLitSubBytes / 512;
+  __shared__ uint32_t s_lit_ent[8 * kLitEntCap];           // per warp: the lane groups with a survivor, in offset order
+  uint32_t* my_ent = s_lit_ent + (threadIdx.x >> 5) * kLitEntCap;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   for (uint64_t sub = warp; sub < out.nsub; sub += nwarps) {
     const uint64_t sub_lo = sub * kLitSubBytes;
-    uint32_t k = 0;
+    uint32_t k = 0, n_ent = 0;
     const bool live = sub_lo < n && sub_lo + kLitSubBytes > range.own_begin && sub_lo < range.own_end;
     if (live && sub_lo + kLitSubBytes + 16 <= n) {
       // ---- interior sub-region: unguarded 16-byte loads, 4 pieces per step, the
@@ -354,10 +373,12 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
           uint32_t up = __shfl_down_sync(kFullMask, v[u].x, 1);
           uint32_t wrap = __shfl_sync(kFullMask, (u < 3) ? v[u + 1].x : nxt[0].x, 0);
           uint32_t nx = (lane == 31) ? wrap : up;
-          bool any = LitAny<kFull4>(v[u], nx, p4, pmask);
-          if (__any_sync(kFullMask, any))
-            LitEmit(text, n, needle, m, p4, pmask, range, out, sub, k,
-                    sub_lo + (uint64_t)(pc + u) * 512 + (uint64_t)lane * 16, v[u], nx);
+          const bool any = LitAny<kFull4>(v[u], nx, p4, pmask);
+          const uint32_t bal = __ballot_sync(kFullMask, any);
+          if (bal) {
+            if (any) my_ent[n_ent + __popc(bal & lt_mask)] = (((pc + u) * 32u + lane) << 16) | LitMask(v[u], nx, p4, pmask);
+            n_ent += __popc(bal);
+          }
         }
       }
     } else if (live) {
@@ -368,10 +389,15 @@ k_lit_scan(const uint8_t* __restrict__ text, uint64_t n, const uint8_t* __restri
         uint4 v = (my < n) ? LoadText16(text, n, my) : make_uint4(0, 0, 0, 0);
         uint32_t nx = __shfl_down_sync(kFullMask, v.x, 1);
         if (lane == 31) nx = (my + 16 < n) ? LoadText4(text, n, my + 16) : 0u;
-        bool any = LitAny<kFull4>(v, nx, p4, pmask);
-        if (__any_sync(kFullMask, any)) LitEmit(text, n, needle, m, p4, pmask, range, out, sub, k, my, v, nx);
+        const bool any = LitAny<kFull4>(v, nx, p4, pmask);
+        const uint32_t bal = __ballot_sync(kFullMask, any);
+        if (bal) {
+          if (any) my_ent[n_ent + __popc(bal & lt_mask)] = ((pc * 32u + lane) << 16) | LitMask(v, nx, p4, pmask);
+          n_ent += __popc(bal);
+        }
       }
     }
+    if (n_ent) k = LitFlush(text, n, needle, m, range, out, sub, sub_lo, my_ent, n_ent, k);
     if (lane == 0) {
       out.count[sub] = k;
       FinishNote(fin, 0, sub, k, false, out.cap);
@@ -1204,27 +1230,37 @@ k_set_tma(const uint8_t* __restrict__ text, uint64_t n, SetTables tb, ScanRange 
 // sample/regexdna.cc:52-62).  "Does a member end at e" is a function of the
 // eight 2-bit codes before e, so there is no automaton state and no dependent
 // chain.
+//   tables   every CTA copies the set's small tables (match lengths, the list of
+//            accepted 8-mers and their member masks) to shared memory with one
+//            coalesced load issued before anything else, and builds from the
+//            list the bitmap (index = 7 + R codes, R = 3 consecutive ends per
+//            lookup: 2^20 bits = 128 KB) and a 512-slot hash 8-mer -> member mask.
+//            Sets that accept more than kKmerListMax 8-mers fetch the bitmap with
+//            one TMA bulk copy and read the masks from a global 65536-entry table.
 //   scan     every CTA owns a contiguous segment of 512-byte rows, every warp a
 //            contiguous run of them.  A lane loads 16 bytes of a row (coalesced
-//            uint4, four rows in flight), packs them into 16 codes (one AND + one
-//            multiply per four bytes), takes the seven codes before them from its
-//            neighbour (shuffle) and looks the two ends after letters 2t, 2t+1 up
-//            in an 18-bit bitmap (32 KB of shared memory, staged by one TMA bulk
-//            copy): eight lookups, whose answers go, as one byte, into a byte
-//            array in shared memory that is indexed by position.  No branch, no
-//            atomic, nothing written to global memory.
-//   finish   (same CTA, no second kernel) the byte array is compacted in position
-//            order (block scan); every hit is checked exactly against the text (a
-//            byte whose code aliases a live byte is not that byte) and fanned out
-//            per member through a 65536-entry mask table (global, L2 resident);
-//            per-member indices by ballot + a prefix over the 32-candidate chunks.
+//            uint4, four rows in flight, the loop unrolled by four so that the
+//            pipeline registers are renamed, not moved), packs them into 16 codes
+//            (one AND + one multiply per four bytes), takes the seven codes before
+//            them from its neighbour (shuffle) and does 16 / R lookups.  A row with
+//            a hit (one in four on regex-dna) costs one ballot and one shared-memory
+//            store per lane with a hit: {group index, lookup bits}.  No branch on
+//            data, no atomic, no call (a __noinline__ slow path drained the
+//            prefetched rows on every call), nothing written to global memory.
+//   finish   (same CTA, no second kernel) the warp expands its groups into hits in
+//            position order (one warp scan), checks every hit exactly against the
+//            text (one 64-bit read; a byte whose code aliases a live byte is not
+//            that byte) and fans it out per member through the hash; per-member
+//            indices by ballot.
 //   exchange every CTA publishes, per member, {count, first end, last end} as two
-//            16-byte records carrying the call's sequence number and waits for the
-//            CTAs before it (cooperative launch: all resident): this is the only
-//            grid-wide step.  It then writes its matches at their final place;
-//            the last CTA also checks the seams and reports to the host.
+//            16-byte records carrying the call's sequence number and reads the
+//            records of the CTAs before it (cooperative launch: all resident): this
+//            is the only grid-wide step.  It then writes its matches at their final
+//            place; the last CTA also checks the seams and reports to the host.
 // Candidates that overlap (or a carry reaching into the slab) raise kFinOverlap and
 // the host repeats the call with k_set_tma + the general resolve.
+// Kernel parameters stay small on purpose (the arrays live in `tab`): parameters
+// are read through the constant cache and are best touched before the text streams.
 // Algorithmic traffic: N bytes read (once for all members) + 16 bytes per match.
 // ===========================================================================
 constexpr uint32_t kKmerListMax = 128;  // accepted 8-mers up to which every CTA builds its tables itself
