@@ -8,15 +8,21 @@
 // tables for hand-written sm_100a CUDA kernels instead of being JIT-compiled
 // to x64 (see include/rejit_b200.h for the C boundary and DESIGN.md).
 //
-// Additions: Regej::MatchAllParallel and the free MatchAllParallel helper.
+// Additions (a program can test for them with `#ifdef REJIT_B200`):
+// Regej::MatchAllParallel and the free MatchAllParallel helper, Regej::MatchAllSet,
+// and rejit::Text, a text that is copied to the device once and matched many times.
 //
 // Written from scratch for this project; only the declarations' shapes are
 // shared with the reference, because they ARE the compatibility contract.
 #ifndef REJIT_H_
 #define REJIT_H_
 
+#include <stddef.h>
+
 #include <string>
 #include <vector>
+
+#define REJIT_B200 1
 
 using namespace std;   // the reference header exports std:: names to its users
 
@@ -38,6 +44,26 @@ enum Status { RejitSuccess = 0, ParserError = -1 };
 extern char* const rejit_status_string;
 
 namespace internal { class RegexpInfo; }
+
+// A text resident in device memory (new in rejit_b200): the constructor copies
+// `size` bytes to the device once; every Regej::MatchAll(const Text&, ...) then
+// costs a scan and the copy of its match list, no upload.  Matches point into
+// the caller's host buffer, which must stay alive and unchanged.
+class Text {
+ public:
+  Text(const char* text, size_t size, int device = 0);
+  ~Text();
+  const char* data() const { return text_; }
+  size_t size() const { return size_; }
+
+ private:
+  friend class Regej;
+  Text(const Text&);
+  Text& operator=(const Text&);
+  const char* text_;
+  size_t size_;
+  void* handle_;
+};
 
 class Regej {
  public:
@@ -62,6 +88,8 @@ class Regej {
   size_t MatchAll(const char* text, size_t text_size, std::vector<struct Match>* matches);
   size_t MatchAllCount(const string& text);
   size_t MatchAllCount(const char* text, size_t text_size);
+  // MatchAll over a text that is already on the device (new in rejit_b200).
+  size_t MatchAll(const Text& text, std::vector<struct Match>* matches);
   // Same result as MatchAll, with the text sharded by contiguous slab over
   // n_gpus devices of this machine (new in rejit_b200).
   size_t MatchAllParallel(const char* text, size_t text_size, std::vector<struct Match>* matches,

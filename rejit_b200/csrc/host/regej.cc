@@ -126,6 +126,32 @@ size_t Regej::MatchAll(const char* text, size_t text_size, vector<Match>* matche
   return matches ? matches->size() : static_cast<size_t>(n);
 }
 
+Text::Text(const char* text, size_t size, int device) : text_(text), size_(size), handle_(nullptr) {
+  char err[256];
+  err[0] = 0;
+  handle_ = rejit_b200_text_upload(device, text, size, err, sizeof err);
+  if (!handle_) Fatal("Text", err);
+}
+
+Text::~Text() {
+  if (handle_) rejit_b200_text_free(static_cast<rejit_b200_text*>(handle_));
+}
+
+size_t Regej::MatchAll(const Text& text, vector<Match>* matches) {
+  if (!Compile(kMatchAll)) return 0;
+  char err[256];
+  uint64_t* pairs = nullptr;
+  int64_t n = rejit_b200_match_all_text(rinfo_->program, static_cast<const rejit_b200_text*>(text.handle_), &pairs, nullptr,
+                                        err, sizeof err);
+  if (n < 0) Fatal("MatchAll", err);
+  if (matches) {
+    matches->reserve(matches->size() + static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) matches->push_back(Match{text.text_ + pairs[2 * i], text.text_ + pairs[2 * i + 1]});
+  }
+  rejit_b200_free(pairs);
+  return matches ? matches->size() : static_cast<size_t>(n);
+}
+
 size_t Regej::MatchAllParallel(const char* text, size_t text_size, vector<Match>* matches, int n_gpus) {
   if (!Compile(kMatchAll)) return 0;
   char err[256];

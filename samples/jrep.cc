@@ -1,0 +1,440 @@
+// jrep — a grep-like front end on rejit, written for a
+// device-side matcher: files are staged into ONE host blob per batch (a per-file
+// offset table beside it) and every batch costs one upload and one pass for the
+// pattern plus one for the line index "^", instead of two MatchAll calls per
+// file.  Output, options and exit codes follow the reference's jrep
+// (/root/reference/sample/jrep.cc: options :84-126, per-file printing :261-405,
+// path handling :518-545), which this file restates and does not copy.
+//
+// Compiles against include/rejit.h of this repository (REJIT_B200 defined: pinned
+// staging, one rejit::Text upload per batch, --gpus) and, unchanged, against the
+// reference's header and library (host-pointer MatchAll calls); tests/test_jrep.py
+// uses the second build, and the reference's own jrep, as the checkers of the first.
+//
+// Exactness of batching.  Files are independent texts in the reference.  In the
+// blob they are separated by one '\n', which gives every file the same line
+// context at both ends as a text of its own ("^" holds after '\n' and at offset
+// 0, "$" before '\n' and at the end).  A match that swallows a separator would
+// not exist in the reference, and it may hide matches that do: every file such a
+// match touches is scanned again on its own bytes (rare: the pattern has to
+// match across "last bytes of a file, '\n', first bytes of the next").
+#include <errno.h>
+#include <fcntl.h>
+#include <ftw.h>
+#include <getopt.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "rejit.h"
+#ifdef REJIT_B200
+#include "rejit_b200.h"
+#endif
+
+namespace {
+
+struct Options {
+  const char* pattern = nullptr;
+  std::vector<const char*> paths;
+  bool with_filename = false;
+  bool line_number = false;
+  bool colour = false;
+  int recursive = 0;             // 0 no, 1 do not follow symlinks, 2 follow them
+  unsigned jobs = 0;             // accepted for compatibility; batching replaces the worker threads
+  unsigned nopenfd = 1024;
+  unsigned before = 0;
+  unsigned after = 0;
+  size_t batch_bytes = size_t(256) << 20;   // 0: one call per file (the reference's granularity)
+  int gpus = 1;
+};
+
+struct FileSpan {
+  std::string path;
+  size_t begin;   // offset of the first byte in the blob
+  size_t size;
+};
+
+// ---- staging ------------------------------------------------------------------
+// One grow-only host buffer; pinned when the library offers it, so that the
+// upload of a batch is one DMA transfer.
+class Blob {
+ public:
+  ~Blob() { Release(); }
+  char* data() { return data_; }
+  size_t used() const { return used_; }
+  void Clear() { used_ = 0; }
+  char* Extend(size_t bytes) {
+    if (used_ + bytes > capacity_) Grow(used_ + bytes);
+    char* at = data_ + used_;
+    used_ += bytes;
+    return at;
+  }
+  void Shrink(size_t bytes) { used_ -= bytes; }
+
+ private:
+  void Grow(size_t need) {
+    size_t cap = std::max(need, capacity_ + capacity_ / 2);
+    cap = std::max(cap, size_t(1) << 20);
+    char* fresh = Allocate(cap);
+    if (!fresh) {
+      fprintf(stderr, "jrep: cannot allocate %zu bytes\n", cap);
+      exit(ENOMEM);
+    }
+    if (used_) memcpy(fresh, data_, used_);
+    bool was_pinned = pinned_;
+    pinned_ = fresh_pinned_;
+    std::swap(fresh, data_);
+    Free(fresh, was_pinned);
+    capacity_ = cap;
+  }
+  char* Allocate(size_t bytes) {
+    fresh_pinned_ = false;
+#ifdef REJIT_B200
+    if (void* p = rejit_b200_pinned_alloc(bytes)) {
+      fresh_pinned_ = true;
+      return static_cast<char*>(p);
+    }
+#endif
+    return static_cast<char*>(malloc(bytes));
+  }
+  static void Free(char* p, bool pinned) {
+    if (!p) return;
+#ifdef REJIT_B200
+    if (pinned) {
+      rejit_b200_pinned_free(p);
+      return;
+    }
+#endif
+    (void)pinned;
+    free(p);
+  }
+  void Release() {
+    Free(data_, pinned_);
+    data_ = nullptr;
+  }
+  char* data_ = nullptr;
+  size_t capacity_ = 0, used_ = 0;
+  bool pinned_ = false, fresh_pinned_ = false;
+};
+
+// ---- printing (one file) ---------------------------------------------------------
+class Printer {
+ public:
+  explicit Printer(const Options& o) : o_(o) {}
+  ~Printer() { Flush(); }
+  void Flush() {
+    if (!out_.empty()) fwrite(out_.data(), 1, out_.size(), stdout);
+    fflush(stdout);
+    out_.clear();
+  }
+
+  // `lines` = the "^" matches of the file followed by one (end, end) sentinel;
+  // `found` = the pattern's matches, at least one.  The walk below reproduces the
+  // reference's output byte for byte, including what it prints for matches that
+  // span lines (a line may be printed twice) and for a match at the very end of a
+  // file (a head without a line).
+  void File(const std::string& name, const rejit::Match* found, size_t n_found,
+            const std::vector<rejit::Match>& lines) {
+    const size_t n_lines = lines.size();
+    const char* const file_end = lines.back().begin;
+    size_t il = 0, im = 0;
+    while (il < n_lines && im < n_found) {
+      while (il < n_lines && lines[il].begin <= found[im].begin) ++il;
+      --il;                                            // the line the match begins on
+
+      if (o_.before) {
+        out_ += "--\n";
+        for (size_t i = il > o_.before ? il - o_.before : 0; i < il; ++i) {
+          Head(name, i + 1, '-');
+          Bytes(lines[i].begin, lines[i + 1].begin);
+        }
+      }
+
+      Head(name, il + 1, ':');
+      const char* at = lines[il].begin;
+      if (at == file_end) {                            // nothing after the last line start
+        ++im;
+        continue;
+      }
+      while (im < n_found && found[im].begin < lines[il + 1].begin) {
+        Bytes(at, found[im].begin);
+        if (o_.colour) out_ += "\x1B[31m";
+        Bytes(found[im].begin, found[im].end);
+        if (o_.colour) out_ += "\x1B[0m";
+        at = found[im].end;
+        ++im;
+      }
+      size_t tail = il;                                // first line start at or after the last match's end
+      while (lines[tail].begin < found[im - 1].end) ++tail;
+      Bytes(found[im - 1].end, lines[tail].end);
+
+      if (o_.after) {
+        const size_t stop = std::min(tail + size_t(o_.after), n_lines - 1);
+        size_t i = tail;
+        for (; i < stop; ++i) {
+          Head(name, i + 1, '-');
+          Bytes(lines[i].begin, lines[i + 1].begin);
+        }
+        if (i == n_lines - 1) out_ += "\n";
+        out_ += "--\n";
+      }
+    }
+    if (out_.size() > (size_t(4) << 20)) Flush();
+  }
+
+ private:
+  void Head(const std::string& name, size_t line, char separator) {
+    if (o_.with_filename) {
+      out_ += name;
+      out_ += separator;
+    }
+    if (o_.line_number) {
+      char number[24];
+      int n = snprintf(number, sizeof number, "%d", static_cast<int>(line));
+      out_.append(number, n);
+      out_ += separator;
+    }
+  }
+  void Bytes(const char* from, const char* to) {
+    if (to > from) out_.append(from, static_cast<size_t>(to - from));
+  }
+  const Options& o_;
+  std::string out_;
+};
+
+// ---- one batch --------------------------------------------------------------------
+class Jrep {
+ public:
+  Jrep(const Options& o) : o_(o), re_(o.pattern), sol_("^"), printer_(o) {}
+
+  bool Ready() {
+    if (re_.status() != rejit::RejitSuccess) {
+      fprintf(stderr, "jrep: %s\n", rejit::rejit_status_string);
+      return false;
+    }
+    re_.Compile(rejit::kMatchAll);
+    sol_.Compile(rejit::kMatchAll);
+    return true;
+  }
+
+  // Stages one file.  Returns 0 or the errno of the failed open (the reference
+  // stops the whole run there: sample/jrep.cc:269-274, 540-541).
+  int Add(const char* path) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return errno;
+    struct stat st;
+    size_t size = fstat(fd, &st) == 0 ? static_cast<size_t>(st.st_size) : 0;
+    if (size == 0) {
+      close(fd);
+      return 0;
+    }
+    if (!files_.empty() && (o_.batch_bytes == 0 || blob_.used() + size + 1 > o_.batch_bytes)) Run();
+    if (!files_.empty()) *blob_.Extend(1) = '\n';      // the separator
+    const size_t begin = blob_.used();
+    char* at = blob_.Extend(size);
+    size_t got = 0;
+    while (got < size) {
+      ssize_t r = read(fd, at + got, size - got);
+      if (r < 0 && errno == EINTR) continue;
+      if (r <= 0) break;
+      got += static_cast<size_t>(r);
+    }
+    close(fd);
+    blob_.Shrink(size - got);                          // the file shrank while we read it
+    if (got == 0) {
+      if (!files_.empty()) blob_.Shrink(1);
+      return 0;
+    }
+    files_.push_back(FileSpan{path, begin, got});
+    return 0;
+  }
+
+  // Scans what is staged, prints, and empties the batch.
+  void Run() {
+    if (files_.empty()) return;
+    const char* text = blob_.data();
+    const size_t length = blob_.used();
+    std::vector<rejit::Match> found, lines;
+#ifdef REJIT_B200
+    rejit::Text resident(text, length);                // the only upload of the batch
+    if (o_.gpus > 1) re_.MatchAllParallel(text, length, &found, o_.gpus);
+    else re_.MatchAll(resident, &found);
+#else
+    re_.MatchAll(text, length, &found);
+#endif
+
+    // Which file does each match begin in (a file owns [begin, begin + size], its
+    // separator's position included), and which files does a match that swallows
+    // a separator touch.
+    std::vector<char> alone(files_.size(), 0);
+    std::vector<size_t> first(files_.size() + 1, 0);   // found[first[f] .. first[f+1]) begin in file f
+    size_t f = 0;
+    for (size_t i = 0; i < found.size(); ++i) {
+      const size_t b = static_cast<size_t>(found[i].begin - text), e = static_cast<size_t>(found[i].end - text);
+      while (b > files_[f].begin + files_[f].size) first[++f] = i;
+      if (e > files_[f].begin + files_[f].size)
+        for (size_t g = f; g < files_.size() && files_[g].begin < e; ++g) alone[g] = 1;
+    }
+    while (f < files_.size()) first[++f] = found.size();
+
+    // The line index: one pass over the resident batch when much of it has
+    // matches, else per matching file (the reference indexes only those).
+    size_t hit_files = 0, hit_bytes = 0;
+    for (f = 0; f < files_.size(); ++f)
+      if (!alone[f] && first[f] != first[f + 1]) ++hit_files, hit_bytes += files_[f].size;
+    const bool whole = hit_files > 64 || hit_bytes * 8 > length;
+    if (whole && hit_files) {
+#ifdef REJIT_B200
+      if (o_.gpus > 1) sol_.MatchAllParallel(text, length, &lines, o_.gpus);
+      else sol_.MatchAll(resident, &lines);
+#else
+      sol_.MatchAll(text, length, &lines);
+#endif
+    }
+
+    size_t line_at = 0;
+    std::vector<rejit::Match> file_lines, file_found;
+    for (f = 0; f < files_.size(); ++f) {
+      const char* begin = text + files_[f].begin;
+      const char* end = begin + files_[f].size;
+      const rejit::Match* mine = found.data() + first[f];
+      size_t n_mine = first[f + 1] - first[f];
+      file_lines.clear();
+      if (alone[f]) {                                  // as a text of its own
+        file_found.clear();
+        re_.MatchAll(begin, files_[f].size, &file_found);
+        mine = file_found.data();
+        n_mine = file_found.size();
+      }
+      if (n_mine == 0) continue;
+      if (alone[f] || !whole) {
+        sol_.MatchAll(begin, files_[f].size, &file_lines);
+      } else {
+        while (line_at < lines.size() && lines[line_at].begin < begin) ++line_at;
+        for (; line_at < lines.size() && lines[line_at].begin <= end; ++line_at) file_lines.push_back(lines[line_at]);
+      }
+      file_lines.push_back(rejit::Match{end, end});    // lets the last line be printed (sample/jrep.cc:294-296)
+      printer_.File(files_[f].path, mine, n_mine, file_lines);
+    }
+    printer_.Flush();
+    files_.clear();
+    blob_.Clear();
+  }
+
+ private:
+  const Options& o_;
+  rejit::Regej re_, sol_;
+  Printer printer_;
+  Blob blob_;
+  std::vector<FileSpan> files_;
+};
+
+Jrep* g_jrep = nullptr;   // nftw has no user pointer
+
+int Visit(const char* path, const struct stat*, int type, struct FTW*) {
+  return type == FTW_F ? g_jrep->Add(path) : 0;
+}
+
+void Usage(FILE* to, const char* self) {
+  fprintf(to,
+          "Usage: %s [OPTION...] regexp file...\n"
+          "grep-like search powered by rejit (Extended Regular Expression syntax;\n"
+          "patterns may span lines, e.g. \"a\\nb\").\n\n"
+          "  -H, --with-filename           print the file name with output lines\n"
+          "  -n, --line-number             print the line number with output lines\n"
+          "  -r, --recursive               search directories, do not follow symbolic links\n"
+          "  -R, --dereference-recursive   search directories, follow symbolic links\n"
+          "  -c, --color_output            highlight matches in red\n"
+          "  -A, --after-context[=N]       print N lines of context after every match\n"
+          "  -B, --before-context[=N]      print N lines of context before every match\n"
+          "  -C, --context[=N]             both\n"
+          "  -j, --jobs[=N]                accepted; files are batched instead of handed to threads\n"
+          "  -k, --nopenfd[=N]             directories nftw() may hold open (default 1024)\n"
+          "      --batch-bytes=N           bytes staged per matcher call (default 256 MiB; 0 = one call per file)\n"
+          "      --gpus=N                  shard every batch over N devices (this library only)\n",
+          self);
+}
+
+unsigned Number(const char* s) {
+  while (*s == ' ') ++s;
+  return static_cast<unsigned>(atoi(s));
+}
+
+bool ParseArguments(int argc, char** argv, Options* o) {
+  static const struct option kLong[] = {
+      {"with-filename", no_argument, nullptr, 'H'},       {"line-number", no_argument, nullptr, 'n'},
+      {"recursive", no_argument, nullptr, 'r'},           {"dereference-recursive", no_argument, nullptr, 'R'},
+      {"color_output", no_argument, nullptr, 'c'},        {"jobs", optional_argument, nullptr, 'j'},
+      {"nopenfd", optional_argument, nullptr, 'k'},       {"after-context", optional_argument, nullptr, 'A'},
+      {"before-context", optional_argument, nullptr, 'B'}, {"context", optional_argument, nullptr, 'C'},
+      {"batch-bytes", required_argument, nullptr, 1000},  {"gpus", required_argument, nullptr, 1001},
+      {"help", no_argument, nullptr, '?'},                {nullptr, 0, nullptr, 0}};
+  int c;
+  while ((c = getopt_long(argc, argv, "HnrRcj::k::A::B::C::", kLong, nullptr)) != -1) {
+    switch (c) {
+      case 'H': o->with_filename = true; break;
+      case 'n': o->line_number = true; break;
+      case 'r': o->recursive = 1; break;
+      case 'R': o->recursive = 2; break;
+      case 'c': o->colour = true; break;
+      case 'j': o->jobs = optarg ? Number(optarg) : 1; break;
+      case 'k': if (optarg) o->nopenfd = Number(optarg); break;
+      case 'A': if (optarg) o->after = Number(optarg); break;
+      case 'B': if (optarg) o->before = Number(optarg); break;
+      case 'C': if (optarg) o->before = o->after = Number(optarg); break;
+      case 1000: o->batch_bytes = static_cast<size_t>(strtoull(optarg, nullptr, 10)); break;
+      case 1001: o->gpus = std::max(1, atoi(optarg)); break;
+      default: return false;
+    }
+  }
+  if (argc - optind < 2) return false;
+  o->pattern = argv[optind];
+  for (int i = optind + 1; i < argc; ++i) o->paths.push_back(argv[i]);
+  return true;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Options options;
+  if (!ParseArguments(argc, argv, &options)) {
+    Usage(stderr, argv[0]);
+    return 64;
+  }
+  if (options.pattern[0] == 0) return 0;
+
+  Jrep jrep(options);
+  if (!jrep.Ready()) return 2;
+  g_jrep = &jrep;
+
+  int rc = 0;
+  for (const char* path : options.paths) {
+    struct stat st;
+    rc = stat(path, &st);
+    if (rc) {
+      fprintf(stderr, "jrep: %s: %s\n", path, strerror(errno));
+      continue;
+    }
+    if (S_ISDIR(st.st_mode)) {
+      if (!options.recursive) {
+        fprintf(stderr, "jrep: %s: Is a directory.\n", path);
+        continue;
+      }
+      rc = nftw(path, Visit, static_cast<int>(options.nopenfd), options.recursive == 2 ? 0 : FTW_PHYS);
+    } else if (S_ISREG(st.st_mode)) {
+      rc = jrep.Add(path);
+    } else {
+      rc = 0;
+    }
+    if (rc != 0) break;            // an unreadable file ends the run; what was staged before it is still printed
+  }
+  jrep.Run();
+  return rc;
+}

@@ -89,7 +89,6 @@ print([[out[2*i], out[2*i+1]] for i in range(n)])
 '''
 
 
-@pytest.mark.skipif(not os.path.exists(REF_SO), reason="compiled reference not present (GPU box)")
 def _has_reference_ub(pat: str) -> bool:
     """literal{m} / literal{m,m} with m >= 3 makes the reference read freed
     memory (heap-use-after-free in Parser::ParseCurlyBrackets, parser.cc:395-404,
@@ -104,6 +103,7 @@ def _has_reference_ub(pat: str) -> bool:
     return False
 
 
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="compiled reference not present (GPU box)")
 def test_differential_vs_compiled_reference():
     """Random patterns x random texts against the real reference (noff).
     Patterns that trigger the reference's use-after-free are skipped; any other

@@ -1,22 +1,29 @@
-"""The C++ sample written against include/rejit.h (source compatibility with the
-reference's public header): it must compile and link against
+"""The C++ samples written against include/rejit.h (source compatibility with the
+reference's public header): they must compile and link against
 librejit_b200.so, refuse to run without a GPU (no CPU fallback), and on a GPU
-print what the oracle says."""
+print what the oracle / the reference's own program says.
+
+samples/jrep.cc also compiles against the REFERENCE's
+header and library; that build is the CPU-tier checker of its front end (file
+batching, line index, context printing) against the reference's own jrep."""
+import json
 import os
 import subprocess
 
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_INCLUDE = "/root/reference/include"
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-def _build(tmp_path):
+def _build(tmp_path, name="regexdna"):
     import __graft_entry__ as entry
     entry.build()
-    exe = str(tmp_path / "regexdna")
+    exe = str(tmp_path / name)
     libdir = os.path.join(ROOT, "rejit_b200")
     subprocess.run(["g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "include"),
-                    os.path.join(ROOT, "samples", "regexdna.cc"), "-L" + libdir, "-lrejit_b200",
+                    os.path.join(ROOT, "samples", name + ".cc"), "-L" + libdir, "-lrejit_b200",
                     "-Wl,-rpath," + libdir, "-o", exe], check=True)
     return exe
 
@@ -52,3 +59,75 @@ def test_sample_regexdna_output(tmp_path):
         cur = replace(code, cur, alt.encode())
     expected = "\n".join(lines) + "\n\n%d\n%d\n%d\n" % (len(fa), len(seq), len(cur))
     assert r.stdout.decode() == expected
+
+
+# ---- jrep --------------------------------------------------------------------------
+def _jrep_cases():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "jrep_cases.json")))["cases"]
+
+
+def _check_jrep_against_golden(exe, root, paths):
+    import jrep_tree
+    for case in _jrep_cases():
+        expected = case["stdout"].encode("latin-1")
+        for batch in jrep_tree.BATCHES:
+            r = subprocess.run([exe] + case["options"] + ["--batch-bytes=" + batch, case["re"]] + paths, cwd=root,
+                               capture_output=True)
+            assert r.returncode == 0, (case["re"], case["options"], batch, r.stderr[-300:])
+            got = r.stdout
+            if "-c" in case["options"]:
+                assert got.count(b"\x1B[31m") == got.count(b"\x1B[0m") == case["matches"]
+                got = got.replace(b"\x1B[31m", b"").replace(b"\x1B[0m", b"")
+            assert got == expected, (case["re"], case["options"], batch, len(got), len(expected))
+
+
+def test_jrep_compiles_against_rejit_h_and_needs_a_gpu(tmp_path):
+    exe = _build(tmp_path, "jrep")
+    r = subprocess.run([exe], capture_output=True)
+    assert r.returncode == 64 and b"Usage" in r.stderr
+    import rejit_b200
+    if rejit_b200.device_count() > 0:
+        pytest.skip("a GPU is present: covered by the gpu tier")
+    (tmp_path / "a.c").write_bytes(b"int x;\n}\n")
+    r = subprocess.run([exe, "x", str(tmp_path / "a.c")], capture_output=True)
+    assert r.returncode != 0 and b"no CUDA device" in r.stderr and r.stdout == b""
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(REF_INCLUDE, "rejit.h")) and
+                         os.path.exists(os.path.join(REF_DIR, "jrep_ref"))),
+                    reason="needs the reference's header and oracle/_ref (build container only)")
+def test_jrep_front_end_on_the_reference_library(tmp_path):
+    """samples/jrep.cc built UNCHANGED against the reference's header and library: same bytes as the
+    committed golden output (= the reference's jrep on explicit file lists), in every batching mode,
+    and the same bytes and exit code as the reference's jrep run live on a recursive walk."""
+    import jrep_tree
+    exe = str(tmp_path / "jrep_on_ref")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I" + REF_INCLUDE, os.path.join(ROOT, "samples", "jrep.cc"),
+                    "-L" + REF_DIR, "-lrejit_ref", "-Wl,-rpath," + REF_DIR, "-o", exe], check=True)
+    root = str(tmp_path / "tree")
+    os.makedirs(root)
+    paths = jrep_tree.make_tree(root)
+    _check_jrep_against_golden(exe, root, paths)
+    ref = os.path.join(REF_DIR, "jrep_ref")
+    for pat in (";\n}", "x*", "\n", "a.*b", "(;|\n)+}", "$"):      # incl. empty matches, matches that swallow separators
+        for opts in (["-n"], ["-H", "-n", "-A2", "-B1"], ["-H", "-C1"]):
+            a = subprocess.run([ref] + opts + ["-r", pat, "."], cwd=root, capture_output=True)
+            for batch in jrep_tree.BATCHES:
+                b = subprocess.run([exe] + opts + ["-r", "--batch-bytes=" + batch, pat, "."], cwd=root, capture_output=True)
+                assert (a.returncode, a.stdout) == (b.returncode, b.stdout), (pat, opts, batch)
+    for args in (["x", "missing.c"], ["x", "."], ["x", "d0"]):       # stat failure (exit 255), directory without -r
+        a = subprocess.run([ref] + args, cwd=root, capture_output=True)
+        b = subprocess.run([exe] + args, cwd=root, capture_output=True)
+        assert (a.returncode, a.stdout, a.stderr) == (b.returncode, b.stdout, b.stderr), args
+
+
+@pytest.mark.gpu
+def test_sample_jrep_output(tmp_path):
+    """The same program on librejit_b200.so: one pinned blob and one upload per batch, matches that
+    swallow a separator re-run per file; byte-identical to what the reference's jrep printed."""
+    import jrep_tree
+    exe = _build(tmp_path, "jrep")
+    root = str(tmp_path / "tree")
+    os.makedirs(root)
+    paths = jrep_tree.make_tree(root)
+    _check_jrep_against_golden(exe, root, paths)
