@@ -131,3 +131,51 @@ def test_sample_jrep_output(tmp_path):
     os.makedirs(root)
     paths = jrep_tree.make_tree(root)
     _check_jrep_against_golden(exe, root, paths)
+
+
+# ---- bench_engine --------------------------------------------------------------------
+def _table(stdout: bytes):
+    """Parses an engine's table the way tools/benchmarks/run.py:192-211 does."""
+    lines = stdout.decode().split("\n")
+    labels = lines[0].split()
+    assert "text_size" in labels
+    rows = {}
+    for raw in lines[1:]:
+        cells = raw.split()
+        if cells:
+            rows[int(cells[0])] = {labels[i]: float(v) for i, v in enumerate(cells[1:], start=1)}
+    return labels, rows
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(REF_INCLUDE, "rejit.h")) and
+                         os.path.exists(os.path.join(REF_DIR, "bench_ref"))),
+                    reason="needs the reference's header and oracle/_ref (build container only)")
+def test_bench_engine_speaks_the_reference_harness_format(tmp_path):
+    """samples/bench_engine.cc on the reference library against the reference's own engine binary:
+    same labels line (byte for byte), same sizes, same column layout, for both table shapes."""
+    exe = str(tmp_path / "bench_on_ref")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I" + REF_INCLUDE, os.path.join(ROOT, "samples", "bench_engine.cc"),
+                    "-L" + REF_DIR, "-lrejit_ref", "-Wl,-rpath," + REF_DIR, "-o", exe], check=True)
+    ref = os.path.join(REF_DIR, "bench_ref")
+    for extra in ([], ["--run_worst_case=0"]):
+        args = ["regexp", "--iterations=3", "--low_char=0", "--high_char=z", "--size=8,4096,1048576"] + extra
+        a = subprocess.run([ref] + args, capture_output=True, check=True).stdout
+        b = subprocess.run([exe] + args, capture_output=True, check=True).stdout
+        assert a.split(b"\n")[0] == b.split(b"\n")[0]
+        (la, ra), (lb, rb) = _table(a), _table(b)
+        assert la == lb and sorted(ra) == sorted(rb) == [8, 4096, 1048576]
+        assert [len(x) for x in a.split(b"\n")] == [len(x) for x in b.split(b"\n")]
+        assert all(v > 0 for row in rb.values() for v in row.values())
+    r = subprocess.run([exe, ""], capture_output=True)
+    assert r.returncode == 1 and b"Cannot test an empty regular expression." in r.stdout
+
+
+@pytest.mark.gpu
+def test_sample_bench_engine_runs(tmp_path):
+    exe = _build(tmp_path, "bench_engine")
+    for extra in ([], ["--resident=1"]):
+        r = subprocess.run([exe, "regexp", "--iterations=5", "--low_char=0", "--high_char=z", "--size=4096,4194304"] + extra,
+                           capture_output=True, check=True)
+        labels, rows = _table(r.stdout)
+        assert labels == ["text_size", "worse", "amortised", "best"] and sorted(rows) == [4096, 4194304]
+        assert all(v > 0 for row in rows.values() for v in row.values())
