@@ -66,7 +66,19 @@ void Flatten(const LoweredRegexp& lr, IrHolder* h) {
   h->ir.payload_length = h->payload.size();
 }
 
+// The IR comes from a foreign binding: everything that is later used as an index is checked here.
+constexpr int32_t kMaxIrStates = 1 << 20;
+constexpr int32_t kMaxIrEdges = 1 << 22;
+
 bool Unflatten(const rejit_b200_ir* ir, LoweredRegexp* lr, std::string* error) {
+  if (!ir) { *error = "rejit_b200_compile: no IR"; return false; }
+  if (ir->n_states < 1 || ir->n_states > kMaxIrStates || ir->entry_state < 0 || ir->entry_state >= ir->n_states ||
+      ir->exit_state < 0 || ir->exit_state >= ir->n_states || ir->n_matching < 0 || ir->n_control < 0 ||
+      ir->n_matching > kMaxIrEdges || ir->n_control > kMaxIrEdges ||
+      (ir->n_matching + ir->n_control > 0 && !ir->edges) || (ir->payload_length > 0 && !ir->payload)) {
+    *error = "rejit_b200_compile: malformed IR";
+    return false;
+  }
   lr->n_states = ir->n_states;
   lr->entry_state = ir->entry_state;
   lr->exit_state = ir->exit_state;

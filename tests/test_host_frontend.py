@@ -7,6 +7,7 @@ import os
 import random
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -90,6 +91,16 @@ def test_parse_errors_and_status_string(lib):
     # layout of the reference's Parser::ParseError (src/parser.cc:652-665)
     assert r.status_string == "Error parsing at index 2\na\\q\n  ^ \nunexpected character q\n"
     assert lib.Regej("a{3,2}").status_string.endswith("Invalid repetition bounds: 3 > 2\n")
+
+
+def test_compile_survives_malformed_ir():
+    """The C ABI takes the lowered regexp from a foreign binding: out-of-range states, kinds,
+    payload ranges and header fields must come back as an error (entry_state = 255 of 5 states used to fault)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ir_mutation_fuzz.py"), "11", "1500"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr[-300:])
+    compiled, rejected = [int(x) for x in r.stdout.split()[1::2]]
+    assert compiled > 100 and rejected > 500
 
 
 def test_strategies_for_the_baseline_patterns(lib):
