@@ -24,7 +24,7 @@ def _build(tmp_path, name="regexdna"):
     libdir = os.path.join(ROOT, "rejit_b200")
     subprocess.run(["g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "samples", name + ".cc"), "-L" + libdir, "-lrejit_b200",
-                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+                    "-Wl,-rpath," + libdir, "-lpthread", "-o", exe], check=True)
     return exe
 
 
@@ -179,3 +179,13 @@ def test_sample_bench_engine_runs(tmp_path):
         labels, rows = _table(r.stdout)
         assert labels == ["text_size", "worse", "amortised", "best"] and sorted(rows) == [4096, 4194304]
         assert all(v > 0 for row in rows.values() for v in row.values())
+
+
+# ---- concurrent callers ----------------------------------------------------------------
+@pytest.mark.gpu
+def test_concurrent_match_all_on_shared_programs(tmp_path):
+    """Eight threads, six compiled patterns shared by all of them (the reference's jrep calls MatchAll that
+    way, sample/jrep.cc:461-493): every result equals the one computed by a single thread."""
+    exe = _build(tmp_path, "threads")
+    r = subprocess.run([exe, "8", "12"], capture_output=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith(b"ok "), (r.returncode, r.stdout[-300:], r.stderr[-300:])
