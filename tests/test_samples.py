@@ -189,3 +189,21 @@ def test_concurrent_match_all_on_shared_programs(tmp_path):
     exe = _build(tmp_path, "threads")
     r = subprocess.run([exe, "8", "12"], capture_output=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith(b"ok "), (r.returncode, r.stdout[-300:], r.stderr[-300:])
+
+
+def test_jrep_patterns_through_the_host_tables(hostsim, tmp_path):
+    """What the GPU tier's jrep test will ask of the engine, asked of the product's own tables on the CPU
+    (tests/hostsim.cc): every golden pattern and the line index over every file of the tree and over the
+    batch blob (files joined by the separator), against the oracle."""
+    import jrep_tree
+    import rejit_oracle as O
+    root = str(tmp_path / "tree")
+    os.makedirs(root)
+    paths = jrep_tree.make_tree(root)
+    bodies = [open(os.path.join(root, p), "rb").read() for p in paths]
+    blob = b"\n".join(b for b in bodies if b)
+    for pat in sorted({c["re"] for c in _jrep_cases()} | {"^"}):
+        o = O.Oracle(pat)
+        for text in [blob] + [b for b in bodies if b]:
+            got, desc = hostsim.match_all(pat, text)
+            assert got == o.match_all(text), (pat, desc, len(text))

@@ -27,7 +27,7 @@ def _run(world, cases, port, set_cases=None, stitch="nccl"):
     return json.loads(line[len(tag):])
 
 
-@pytest.mark.parametrize("world,port,stitch", [(2, 29613, "nccl"), (3, 29614, "nccl"), (2, 29615, "shm"), (4, 29616, "shm")])
+@pytest.mark.parametrize("world,port,stitch", [(2, 29613, "nccl"), (3, 29614, "nccl"), (2, 29615, "shm"), (4, 29616, "shm"), (8, 29617, "shm")])
 def test_set_stitching_over_gloo(hostsim, world, port, stitch):
     """The fused-set stitch of bench.py --gpus N: k members' records in one all-gather per round."""
     from rejit_b200 import workloads as W
