@@ -28,6 +28,8 @@
 
 enum { K_MC = 0, K_PERIOD, K_BRACKET, K_SOL, K_EOL, K_EPS };
 enum { MODE_ALL = 0, MODE_FIRST, MODE_FULL, MODE_ANYWHERE };
+/* OR-ed into `mode`: compare literals the way the reference's emitted code does, defect included (below). */
+#define MODE_LONG_LITERAL_DEFECT 0x100
 
 #define RING_TIMES 66 /* 1 + kMaxNodeLength (src/codegen.cc:617) + spare */
 
@@ -53,6 +55,31 @@ static void vec_push(matches_t *m, uint64_t b, uint64_t e) {
   m->vec[2 * m->count] = b;
   m->vec[2 * m->count + 1] = e;
   m->count++;
+}
+
+/* MultipleChar against the text window w (both `len` bytes).
+ *
+ * exact = 1: byte equality, what the node means.  This is what the parity
+ * oracle uses and what the product implements.
+ *
+ * exact = 0: what the code emitted by MatchMultipleChar
+ * (/root/reference/src/x64/codegen-x64.cc:757-837) accepts.  For len > 8 it
+ * pre-checks the first 8 bytes, then runs a repeated quadword compare over
+ * len / 8 quadwords and, without looking at its flags, a repeated byte
+ * compare over len % 8 bytes FROM WHERE THE QUADWORD COMPARE STOPPED; only
+ * the last compare's flags are tested (:823-833).  So for len > 16 with
+ * len % 8 != 0 a window that differs from the literal in quadword q >= 1 is
+ * accepted whenever the len % 8 bytes after that quadword are equal
+ * (defect B20; tests/test_oracle.py pins this model
+ * against the compiled reference).  Lengths <= 16 and multiples of 8 are
+ * compared correctly. */
+static int mc_equal(const unsigned char *w, const unsigned char *lit, int len, int exact) {
+  if (exact || len <= 16 || len % 8 == 0) return memcmp(w, lit, (size_t)len) == 0;
+  if (memcmp(w, lit, 8) != 0) return 0;
+  int at = 8 * (len / 8);
+  for (int q = 0; q < len / 8; q++)
+    if (memcmp(w + 8 * q, lit + 8 * q, 8) != 0) { at = 8 * (q + 1); break; }
+  return memcmp(w + at, lit + at, (size_t)(len % 8)) == 0;
 }
 
 /* MatchAllAppend(filter=true), src/codegen.cc:36-76 */
@@ -88,6 +115,8 @@ int64_t nfa_sim_run(int mode, int n_states, int entry_state, int exit_state,
   const edge_t *cedges = medges + n_match;
   const unsigned char *pl = (const unsigned char *)payload_c;
   const unsigned char *text = (const unsigned char *)text_c;
+  const int exact_literals = !(mode & MODE_LONG_LITERAL_DEFECT);
+  mode &= 0xFF;
 
   uint64_t *ring = (uint64_t *)calloc((size_t)RING_TIMES * n_states, sizeof(uint64_t));
   unsigned char summary[RING_TIMES]; /* time summary bits, codegen-x64.cc:210-245 */
@@ -176,7 +205,7 @@ int64_t nfa_sim_run(int mode, int n_states, int entry_state, int exit_state,
       if (!sv) continue;
       unsigned char ch = text[p];
       if (ed->kind == K_MC) {
-        if (p + (size_t)ed->len <= n && memcmp(text + p, pl + ed->off, ed->len) == 0)
+        if (p + (size_t)ed->len <= n && mc_equal(text + p, pl + ed->off, ed->len, exact_literals))
           SET_STATE(ed->len, ed->exit, sv);
       } else if (ed->kind == K_PERIOD) {
         if (ch != '\n' && ch != '\r') SET_STATE(1, ed->exit, sv);

@@ -606,19 +606,29 @@ def _pack(lr: LoweredRegexp):
 
 
 MODE_ALL, MODE_FIRST, MODE_FULL, MODE_ANYWHERE = 0, 1, 2, 3
+MODE_LONG_LITERAL_DEFECT = 0x100      # nfa_sim.c: literals compared the way the reference's emitted code does (B20)
 
 
 class Oracle:
     """Compiled-once handle, mirrors rejit::Regej (include/rejit.h:105-138)."""
 
-    def __init__(self, pattern, parser_opt: bool = True):
+    def __init__(self, pattern, parser_opt: bool = True, long_literal_defect: bool = False):
+        """long_literal_defect=True reproduces the reference's compare of literals longer than 16 bytes
+        (nfa_sim.c mc_equal; defect B20): used only to pin this oracle against the compiled reference on
+        such patterns.  The parity oracle (default) compares literals exactly."""
         self.lowered = lower(pattern, parser_opt)
         self._edges, self._payload = _pack(self.lowered)
+        self._mode_bits = MODE_LONG_LITERAL_DEFECT if long_literal_defect else 0
+
+    @property
+    def longest_literal(self) -> int:
+        """Bytes of the longest MultipleChar node (literals coalesce up to 64 bytes, src/regexp.h:107)."""
+        return max([len(e.node.chars) for e in self.lowered.matching if e.kind == K_MC] or [0])
 
     def _run(self, mode: int, text: bytes, cap: int):
         lr = self.lowered
         out = (ctypes.c_uint64 * (2 * max(1, cap)))()
-        r = _sim().nfa_sim_run(mode, lr.n_states, lr.entry_state, lr.exit_state,
+        r = _sim().nfa_sim_run(mode | self._mode_bits, lr.n_states, lr.entry_state, lr.exit_state,
                                self._edges, len(lr.matching), len(lr.control),
                                1 if lr.topo_sorted else 0, self._payload, text,
                                len(text), out, cap)

@@ -74,3 +74,34 @@ def rand_pattern(r: random.Random, alpha_name: str = None) -> tuple:
 
 def rand_text(r: random.Random, alpha: str, n: int) -> bytes:
     return "".join(r.choice(alpha) for _ in range(n)).encode("latin-1")
+
+
+def rand_long_literal_case(r: random.Random) -> tuple:
+    """(pattern, text) around literals longer than the reference's 8-byte quadword compare: pure
+    literals of 9..70 bytes (nodes coalesce up to 64), a literal inside a larger pattern, and a group
+    repetition that the parser expands into one long node (`(abcab){3,6}` = 15 bytes + a bounded
+    repetition).  The text holds exact copies and near misses (1-3 bytes changed), so that a compare
+    that skips bytes shows up as a false positive."""
+    alpha = "abcd"
+    n = r.randint(9, 70)
+    lit = "".join(r.choice(alpha) for _ in range(n))
+    form = r.randint(0, 3)
+    if form == 0:
+        pat = lit
+    elif form == 1:
+        pat = "[ab]" + lit
+    elif form == 2:
+        pat = lit + "(a|bd)"
+    else:
+        unit = "".join(r.choice(alpha) for _ in range(r.randint(4, 8)))
+        lo = r.randint(3, 6)
+        pat = ".(" + unit + "){%d,%d}" % (lo, lo + r.randint(0, 3))
+        lit = unit * lo
+    parts = []
+    for _ in range(r.randint(2, 7)):
+        parts.append("".join(r.choice(alpha) for _ in range(r.randint(0, 40))))
+        w = list(lit)
+        for _ in range(r.choice([0, 0, 1, 1, 2, 3])):
+            w[r.randrange(len(w))] = r.choice(alpha)
+        parts.append(r.choice(alpha) + "".join(w) + r.choice(["a", "bd", "cc"]))
+    return pat, "".join(parts).encode("latin-1")

@@ -415,3 +415,15 @@ def test_multi_gpu_equals_single(rj):
         a = rj.Regej(p).match_all_array(seq)
         b = rj.Regej(p).match_all_array(seq, n_gpus=2)
         assert a.shape == b.shape and (a == b).all(), p
+
+
+def test_long_literals(rj):
+    """Literal nodes of 9..70 bytes (and the long node a group repetition expands to), exact copies and
+    near misses, short texts and one of several sub-regions: every byte of the needle counts (the
+    reference's own compare skips bytes for such nodes: defect B20, tests/test_oracle.py)."""
+    r = random.Random(2022)
+    for i in range(120):
+        pat, t = fuzzgen.rand_long_literal_case(r)
+        if i % 10 == 0:                                   # the same near misses spread over a 100 kB text
+            t = b"".join(t + fuzzgen.rand_text(r, "abcd", r.randint(0, 3000)) for _ in range(40))
+        assert rj.Regej(pat).match_all(t) == O.Oracle(pat).match_all(t), (pat, len(t))

@@ -168,6 +168,23 @@ def test_hostsim_fuzz_vs_oracle(hostsim):
     assert checked > 1500
 
 
+def test_hostsim_long_literals(hostsim):
+    """Literal nodes longer than 16 bytes, exact copies and near misses: the product compares every byte
+    (the reference does not: defect B20, tests/test_oracle.py)."""
+    r = random.Random(2021)
+    kinds = set()
+    for _ in range(400):
+        pat, t = fuzzgen.rand_long_literal_case(r)
+        exp = O.Oracle(pat).match_all(t)
+        for strategy in (-1, 3):
+            got, desc = hostsim.match_all(pat, t, strategy)
+            assert got == exp, (pat, t, desc, strategy)
+        got, desc = hostsim.match_all(pat, t)
+        kinds.add(desc.split(",")[0].split(";")[0])
+        assert hostsim.match_all_slabs(pat, t, r.choice([2, 3, 5])) == exp, (pat, t)
+    assert any(k.startswith("literal scan") for k in kinds), kinds
+
+
 def test_hostsim_slab_stitching(hostsim):
     """The carry protocol of MatchAllHostMultiGpu on non-re-entrant patterns."""
     r = random.Random(5)

@@ -125,6 +125,7 @@ def test_differential_vs_compiled_reference():
             continue
         for _ in range(3):
             t = fuzzgen.rand_text(r, alpha, r.randint(0, 48))
+            assert o.longest_literal <= 16          # else the reference's compare differs (B20, next test)
             got = [list(m) for m in o.match_all(t)]
             exp = ref.match_all(pb, t)
             checked += 1
@@ -133,3 +134,37 @@ def test_differential_vs_compiled_reference():
                                        capture_output=True, text=True).stdout.strip()
                 assert str(got) == fresh, (pat, t, got, exp, fresh)
     assert checked > 1000
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="compiled reference not present (GPU box)")
+def test_reference_long_literal_defect_is_modelled():
+    """Defect B20: the code the reference emits for a literal node longer than 16 bytes
+    whose length is not a multiple of 8 tests only the flags of its LAST repeated compare
+    (src/x64/codegen-x64.cc:819-833), so windows that differ from the literal are accepted.  The oracle
+    restates that compare behind a switch (nfa_sim.c mc_equal); with the switch ON it must equal the
+    compiled reference (fast-forward off) on every case, which pins the rest of the oracle on these
+    patterns too; with the switch OFF (the parity oracle, exact compare) it must find exactly the true
+    occurrences of a pure literal, and the two must differ somewhere (else the switch tests nothing)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import Ref
+    ref = Ref()
+    ref.flags(2)
+    r = random.Random(2020)
+    checked = differ = 0
+    for _ in range(500):
+        pat, t = fuzzgen.rand_long_literal_case(r)
+        pb = pat.encode("latin-1")
+        if _has_reference_ub(pat):
+            continue
+        modelled = [list(m) for m in O.Oracle(pat, long_literal_defect=True).match_all(t)]
+        exact = O.Oracle(pat).match_all(t)
+        assert modelled == ref.match_all(pb, t), (pat, t)
+        differ += modelled != [list(m) for m in exact]
+        if not any(c in pat for c in "[(."):       # a pure literal: greedy non-overlapping occurrences
+            want, at = [], t.find(pb)
+            while at >= 0:
+                want.append((at, at + len(pb)))
+                at = t.find(pb, at + len(pb))
+            assert exact == want, (pat, t)
+        checked += 1
+    assert checked > 400 and differ > 20, (checked, differ)
