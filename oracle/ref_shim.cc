@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <omp.h>
 
+#include <stdlib.h>
+
 #include "rejit.h"
 #include "flags.h"
 
@@ -32,6 +34,12 @@ void ref_set_flagset(int flagset) {
 }
 
 void ref_set_parser_opt(int on) { FLAG_use_parser_opt = (on != 0); }
+
+// Programs that link this library through rejit.h only (samples/jrep.cc built on the reference, the
+// checker of its batching) choose the flag set with REJIT_REF_FLAGSET=0|1|2 in the environment.
+__attribute__((constructor)) static void ref_flagset_from_environment() {
+  if (const char* v = getenv("REJIT_REF_FLAGSET")) ref_set_flagset(atoi(v));
+}
 
 // Returns the parse status (0 ok, -1 ParserError); on error copies the
 // reference's status string into msg.

@@ -15,9 +15,10 @@
 // blob they are separated by one '\n', which gives every file the same line
 // context at both ends as a text of its own ("^" holds after '\n' and at offset
 // 0, "$" before '\n' and at the end).  A match that swallows a separator would
-// not exist in the reference, and it may hide matches that do: every file such a
-// match touches is scanned again on its own bytes (rare: the pattern has to
-// match across "last bytes of a file, '\n', first bytes of the next").
+// not exist in the reference, and it may hide matches that do (also the empty
+// match at the first byte of a file it merely ends at): every file such a match
+// touches or abuts is scanned again on its own bytes (rare: the pattern has to
+// match across "last bytes of a file, '\n'").
 #include <errno.h>
 #include <fcntl.h>
 #include <ftw.h>
@@ -279,8 +280,8 @@ class Jrep {
     for (size_t i = 0; i < found.size(); ++i) {
       const size_t b = static_cast<size_t>(found[i].begin - text), e = static_cast<size_t>(found[i].end - text);
       while (b > files_[f].begin + files_[f].size) first[++f] = i;
-      if (e > files_[f].begin + files_[f].size)
-        for (size_t g = f; g < files_.size() && files_[g].begin < e; ++g) alone[g] = 1;
+      if (e > files_[f].begin + files_[f].size)                         // a file the match only abuts counts too:
+        for (size_t g = f; g < files_.size() && files_[g].begin <= e; ++g) alone[g] = 1;   // its empty match there is lost
     }
     while (f < files_.size()) first[++f] = found.size();
 

@@ -33,7 +33,12 @@ def main():
     with tempfile.TemporaryDirectory() as root:
         paths = jrep_tree.make_tree(root)
         bodies = [open(os.path.join(root, p), "rb").read() for p in paths]
-        for pat, opts in jrep_tree.CASES:
+        all_paths, all_bodies = paths, bodies
+        for case in jrep_tree.CASES:
+            pat, opts = case[0], case[1]
+            only = case[2] if len(case) > 2 else ""
+            paths = [p for p in all_paths if p.startswith(only)]
+            bodies = [b for p, b in zip(all_paths, all_bodies) if p.startswith(only)]
             o = O.Oracle(pat)
             for p, body in zip(paths, bodies):
                 if body:
@@ -47,10 +52,10 @@ def main():
                 # strips "\x1B[31m" / "\x1B[0m" from the sample's output and counts them.
                 assert b"\x1b" not in expected
                 n_matches = sum(len(o.match_all(body)) for body in bodies if body)
-            out.append({"re": pat, "options": opts, "stdout": expected.decode("latin-1"), "bytes": len(expected),
+            out.append({"re": pat, "options": opts, "only": only, "stdout": expected.decode("latin-1"), "bytes": len(expected),
                         "matches": n_matches})
             print(repr(pat), opts, "->", "%d bytes" % len(expected))
-    json.dump({"tree": "tests/jrep_tree.py make_tree()", "files": len(paths), "cases": out},
+    json.dump({"tree": "tests/jrep_tree.py make_tree()", "files": len(all_paths), "cases": out},
               open(os.path.join(HERE, "jrep_cases.json"), "w"), indent=0)
 
 
