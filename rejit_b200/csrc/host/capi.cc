@@ -72,6 +72,10 @@ constexpr int32_t kMaxIrEdges = 1 << 22;
 
 bool Unflatten(const rejit_b200_ir* ir, LoweredRegexp* lr, std::string* error) {
   if (!ir) { *error = "rejit_b200_compile: no IR"; return false; }
+  if (ir->n_states > kMaxIrStates || ir->n_matching > kMaxIrEdges || ir->n_control > kMaxIrEdges) {
+    *error = "regular expression too large for the sm_100a engine (more than 2^20 states or 2^22 edges)";
+    return false;
+  }
   if (ir->n_states < 1 || ir->n_states > kMaxIrStates || ir->entry_state < 0 || ir->entry_state >= ir->n_states ||
       ir->exit_state < 0 || ir->exit_state >= ir->n_states || ir->n_matching < 0 || ir->n_control < 0 ||
       ir->n_matching > kMaxIrEdges || ir->n_control > kMaxIrEdges ||
