@@ -31,7 +31,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rejit.h"
@@ -48,7 +51,7 @@ struct Options {
   bool line_number = false;
   bool colour = false;
   int recursive = 0;             // 0 no, 1 do not follow symlinks, 2 follow them
-  unsigned jobs = 0;             // accepted for compatibility; batching replaces the worker threads
+  unsigned jobs = 0;             // threads that read a batch's files into the blob (0: the walking thread reads)
   unsigned nopenfd = 1024;
   unsigned before = 0;
   unsigned after = 0;
@@ -60,6 +63,7 @@ struct FileSpan {
   std::string path;
   size_t begin;   // offset of the first byte in the blob
   size_t size;
+  int error;      // errno of a failed open by a staging thread (-j)
 };
 
 // ---- staging ------------------------------------------------------------------
@@ -226,60 +230,82 @@ class Jrep {
   }
 
   // Stages one file.  Returns 0 or the errno of the failed open (the reference
-  // stops the whole run there: sample/jrep.cc:269-274, 540-541).
+  // stops the whole run there: sample/jrep.cc:269-274, 540-541).  With -j N only
+  // the place in the blob is reserved here; N threads fill the batch in Run().
   int Add(const char* path) {
-    int fd = open(path, O_RDONLY);
-    if (fd < 0) return errno;
+    if (pending_error_) return pending_error_;
+    int fd = -1;
     struct stat st;
-    size_t size = fstat(fd, &st) == 0 ? static_cast<size_t>(st.st_size) : 0;
-    if (size == 0) {
-      close(fd);
-      return 0;
+    size_t size;
+    if (o_.jobs > 0) {
+      if (stat(path, &st) != 0) return errno;
+      size = static_cast<size_t>(st.st_size);
+      if (size == 0) return access(path, R_OK) == 0 ? 0 : errno;
+    } else {
+      fd = open(path, O_RDONLY);
+      if (fd < 0) return errno;
+      size = fstat(fd, &st) == 0 ? static_cast<size_t>(st.st_size) : 0;
+      if (size == 0) {
+        close(fd);
+        return 0;
+      }
     }
-    if (!files_.empty() && (o_.batch_bytes == 0 || blob_.used() + size + 1 > o_.batch_bytes)) Run();
+    if (!files_.empty() && (o_.batch_bytes == 0 || blob_.used() + size + 1 > o_.batch_bytes)) {
+      Run();
+      if (pending_error_) {
+        if (fd >= 0) close(fd);
+        return pending_error_;
+      }
+    }
     if (!files_.empty()) *blob_.Extend(1) = '\n';      // the separator
     const size_t begin = blob_.used();
     char* at = blob_.Extend(size);
-    size_t got = 0;
-    while (got < size) {
-      ssize_t r = read(fd, at + got, size - got);
-      if (r < 0 && errno == EINTR) continue;
-      if (r <= 0) break;
-      got += static_cast<size_t>(r);
+    if (o_.jobs > 0) {
+      files_.push_back(FileSpan{path, begin, size, 0});
+      return 0;
     }
+    const size_t got = ReadFile(fd, at, size);
     close(fd);
     blob_.Shrink(size - got);                          // the file shrank while we read it
     if (got == 0) {
       if (!files_.empty()) blob_.Shrink(1);
       return 0;
     }
-    files_.push_back(FileSpan{path, begin, got});
+    files_.push_back(FileSpan{path, begin, got, 0});
     return 0;
   }
+
+  // The errno that ended the run, if a staging thread could not open a file.
+  int error() const { return pending_error_; }
 
   // Scans what is staged, prints, and empties the batch.
   void Run() {
     if (files_.empty()) return;
+    bool gaps = false;
+    if (o_.jobs > 0 && !Stage(&gaps)) return;
     const char* text = blob_.data();
     const size_t length = blob_.used();
     std::vector<rejit::Match> found, lines;
 #ifdef REJIT_B200
-    rejit::Text resident(text, length);                // the only upload of the batch
-    if (o_.gpus > 1) re_.MatchAllParallel(text, length, &found, o_.gpus);
-    else re_.MatchAll(resident, &found);
+    std::unique_ptr<rejit::Text> resident;             // the only upload of the batch
+    if (!gaps) {
+      resident.reset(new rejit::Text(text, length));
+      if (o_.gpus > 1) re_.MatchAllParallel(text, length, &found, o_.gpus);
+      else re_.MatchAll(*resident, &found);
+    }
 #else
-    re_.MatchAll(text, length, &found);
+    if (!gaps) re_.MatchAll(text, length, &found);
 #endif
 
     // Which file does each match begin in (a file owns [begin, begin + size], its
     // separator's position included), and which files does a match that swallows
     // a separator touch.
-    std::vector<char> alone(files_.size(), 0);
+    std::vector<char> alone(files_.size(), gaps ? 1 : 0);   // a batch with holes: every file on its own bytes
     std::vector<size_t> first(files_.size() + 1, 0);   // found[first[f] .. first[f+1]) begin in file f
     size_t f = 0;
     for (size_t i = 0; i < found.size(); ++i) {
       const size_t b = static_cast<size_t>(found[i].begin - text), e = static_cast<size_t>(found[i].end - text);
-      while (b > files_[f].begin + files_[f].size) first[++f] = i;
+      while (f + 1 < files_.size() && b > files_[f].begin + files_[f].size) first[++f] = i;
       if (e > files_[f].begin + files_[f].size)                         // a file the match only abuts counts too:
         for (size_t g = f; g < files_.size() && files_[g].begin <= e; ++g) alone[g] = 1;   // its empty match there is lost
     }
@@ -290,11 +316,11 @@ class Jrep {
     size_t hit_files = 0, hit_bytes = 0;
     for (f = 0; f < files_.size(); ++f)
       if (!alone[f] && first[f] != first[f + 1]) ++hit_files, hit_bytes += files_[f].size;
-    const bool whole = hit_files > 64 || hit_bytes * 8 > length;
+    const bool whole = !gaps && (hit_files > 64 || hit_bytes * 8 > length);
     if (whole && hit_files) {
 #ifdef REJIT_B200
       if (o_.gpus > 1) sol_.MatchAllParallel(text, length, &lines, o_.gpus);
-      else sol_.MatchAll(resident, &lines);
+      else sol_.MatchAll(*resident, &lines);
 #else
       sol_.MatchAll(text, length, &lines);
 #endif
@@ -330,6 +356,73 @@ class Jrep {
   }
 
  private:
+  static size_t ReadFile(int fd, char* at, size_t size) {
+    size_t got = 0;
+    while (got < size) {
+      ssize_t r = read(fd, at + got, size - got);
+      if (r < 0 && errno == EINTR) continue;
+      if (r <= 0) break;
+      got += static_cast<size_t>(r);
+    }
+    return got;
+  }
+
+  // -j N: N threads read the batch's files into their reserved places (the blob does not move while
+  // they run).  A file that cannot be opened ends the run there, as in Add(): the batch is cut before
+  // it.  A file that shrank since stat() leaves a hole, filled with separators.  False: nothing to scan.
+  bool Stage(bool* gaps) {
+    std::atomic<size_t> next(0);
+    char* const base = blob_.data();
+    auto work = [&]() {
+      for (size_t i; (i = next.fetch_add(1)) < files_.size();) {
+        FileSpan& f = files_[i];
+        int fd = open(f.path.c_str(), O_RDONLY);
+        if (fd < 0) {
+          f.error = errno ? errno : EIO;
+          continue;
+        }
+        const size_t got = ReadFile(fd, base + f.begin, f.size);
+        close(fd);
+        if (got < f.size) memset(base + f.begin + got, '\n', f.size - got);
+        f.size = got | (got < f.size ? kShort : 0);
+      }
+    };
+    std::vector<std::thread> pool;
+    const size_t n_threads = std::min<size_t>(o_.jobs, files_.size());
+    for (size_t t = 1; t < n_threads; ++t) pool.push_back(std::thread(work));
+    work();
+    for (std::thread& t : pool) t.join();
+    size_t keep = files_.size();
+    for (size_t i = 0; i < files_.size(); ++i) {
+      if (files_[i].error) {
+        pending_error_ = files_[i].error;
+        keep = i;
+        break;
+      }
+      if (files_[i].size & kShort) {
+        files_[i].size &= ~kShort;
+        *gaps = true;
+      }
+    }
+    if (keep < files_.size()) {
+      files_.resize(keep);
+      blob_.Clear();
+      if (keep) blob_.Extend(files_[keep - 1].begin + files_[keep - 1].size);
+    }
+    // files that turned out empty own nothing (the reference skips them, sample/jrep.cc:277-279)
+    size_t w = 0;
+    for (size_t i = 0; i < files_.size(); ++i)
+      if (files_[i].size) files_[w++] = files_[i]; else *gaps = true;
+    files_.resize(w);
+    if (files_.empty()) {
+      blob_.Clear();
+      return false;
+    }
+    return true;
+  }
+
+  static const size_t kShort = size_t(1) << (sizeof(size_t) * 8 - 1);
+  int pending_error_ = 0;
   const Options& o_;
   rejit::Regej re_, sol_;
   Printer printer_;
@@ -356,7 +449,7 @@ void Usage(FILE* to, const char* self) {
           "  -A, --after-context[=N]       print N lines of context after every match\n"
           "  -B, --before-context[=N]      print N lines of context before every match\n"
           "  -C, --context[=N]             both\n"
-          "  -j, --jobs[=N]                accepted; files are batched instead of handed to threads\n"
+          "  -j, --jobs[=N]                N threads stage (read) the files of a batch; matching is per batch\n"
           "  -k, --nopenfd[=N]             directories nftw() may hold open (default 1024)\n"
           "      --batch-bytes=N           bytes staged per matcher call (default 256 MiB; 0 = one call per file)\n"
           "      --gpus=N                  shard every batch over N devices (this library only)\n",
@@ -385,7 +478,7 @@ bool ParseArguments(int argc, char** argv, Options* o) {
       case 'r': o->recursive = 1; break;
       case 'R': o->recursive = 2; break;
       case 'c': o->colour = true; break;
-      case 'j': o->jobs = optarg ? Number(optarg) : 1; break;
+      case 'j': o->jobs = optarg ? Number(optarg) : std::max(1u, std::thread::hardware_concurrency() - 1u); break;
       case 'k': if (optarg) o->nopenfd = Number(optarg); break;
       case 'A': if (optarg) o->after = Number(optarg); break;
       case 'B': if (optarg) o->before = Number(optarg); break;
@@ -437,5 +530,5 @@ int main(int argc, char** argv) {
     if (rc != 0) break;            // an unreadable file ends the run; what was staged before it is still printed
   }
   jrep.Run();
-  return rc;
+  return rc ? rc : jrep.error();
 }

@@ -72,7 +72,8 @@ def _check_jrep_against_golden(exe, root, paths):
         expected = case["stdout"].encode("latin-1")
         files = [p for p in paths if p.startswith(case.get("only", ""))]
         for batch in jrep_tree.BATCHES:
-            r = subprocess.run([exe] + case["options"] + ["--batch-bytes=" + batch, case["re"]] + files, cwd=root,
+            jobs = ["-j3"] if batch == "30000" else []       # one mode with the batch staged by three threads
+            r = subprocess.run([exe] + case["options"] + jobs + ["--batch-bytes=" + batch, case["re"]] + files, cwd=root,
                                capture_output=True)
             assert r.returncode == 0, (case["re"], case["options"], batch, r.stderr[-300:])
             got = r.stdout
@@ -104,7 +105,7 @@ def test_jrep_front_end_on_the_reference_library(tmp_path):
     import jrep_tree
     exe = str(tmp_path / "jrep_on_ref")
     subprocess.run(["g++", "-std=c++11", "-O2", "-I" + REF_INCLUDE, os.path.join(ROOT, "samples", "jrep.cc"),
-                    "-L" + REF_DIR, "-lrejit_ref", "-Wl,-rpath," + REF_DIR, "-o", exe], check=True)
+                    "-L" + REF_DIR, "-lrejit_ref", "-Wl,-rpath," + REF_DIR, "-lpthread", "-o", exe], check=True)
     root = str(tmp_path / "tree")
     os.makedirs(root)
     paths = jrep_tree.make_tree(root)
@@ -132,6 +133,24 @@ def test_jrep_front_end_on_the_reference_library(tmp_path):
         for batch in jrep_tree.BATCHES:
             b = subprocess.run([exe, "-n", "--batch-bytes=" + batch, pat] + names, cwd=meet, capture_output=True, env=noff)
             assert a.returncode == 0 and (a.returncode, a.stdout) == (b.returncode, b.stdout), (pat, batch)
+    # -j N: N threads stage the batch; same bytes whatever N and the batch size
+    a = subprocess.run([ref, "-H", "-n", "-A1", "-r", ";\n}", "."], cwd=root, capture_output=True, env=noff)
+    for jobs in ("-j1", "-j4", "-j16"):
+        for batch in jrep_tree.BATCHES:
+            b = subprocess.run([exe, jobs, "-H", "-n", "-A1", "-r", "--batch-bytes=" + batch, ";\n}", "."], cwd=root,
+                               capture_output=True, env=noff)
+            assert a.stdout and (a.returncode, a.stdout) == (b.returncode, b.stdout), (jobs, batch)
+    # a file that cannot be opened ends the run with its errno; what came before it is printed, what follows is not
+    # (sample/jrep.cc:269-274, 540-541).  Root opens anything, except a write-only sysfs attribute.
+    locked = [os.path.join(d, f) for d, _, fs in os.walk("/sys/class") for f in fs
+              if (os.stat(os.path.join(d, f)).st_mode & 0o777) == 0o200][:1] if os.path.isdir("/sys/class") else []
+    if locked:
+        names3 = [names[0], locked[0], names[1]]
+        a = subprocess.run([ref, "-H", "a", *names3], cwd=meet, capture_output=True, env=noff)
+        assert a.returncode == 13 and a.stdout
+        for extra in ([], ["-j3"], ["-j3", "--batch-bytes=0"], ["--batch-bytes=0"]):
+            b = subprocess.run([exe, "-H", *extra, "a", *names3], cwd=meet, capture_output=True, env=noff)
+            assert (a.returncode, a.stdout) == (b.returncode, b.stdout), extra
     for args in (["x", "missing.c"], ["x", "."], ["x", "d0"]):       # stat failure (exit 255), directory without -r
         a = subprocess.run([ref] + args, cwd=root, capture_output=True)
         b = subprocess.run([exe] + args, cwd=root, capture_output=True)
