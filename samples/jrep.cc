@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -44,6 +45,24 @@
 
 namespace {
 
+// JREP_TRACE=1: seconds spent staging (reading files into the blob), matching and printing, on stderr at exit.
+struct Trace {
+  bool on = getenv("JREP_TRACE") != nullptr;
+  double stage = 0, match = 0, print = 0;
+  size_t bytes = 0, batches = 0, files = 0, reruns = 0;
+  static double Now() {
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return static_cast<double>(t.tv_sec) + 1e-9 * static_cast<double>(t.tv_nsec);
+  }
+  ~Trace() {
+    if (on)
+      fprintf(stderr, "[jrep] %zu files, %zu bytes, %zu batches, %zu files matched again alone; stage %.3f s, match %.3f s, "
+              "print %.3f s\n", files, bytes, batches, reruns, stage, match, print);
+  }
+};
+Trace g_trace;
+
 struct Options {
   const char* pattern = nullptr;
   std::vector<const char*> paths;
@@ -51,7 +70,18 @@ struct Options {
   bool line_number = false;
   bool colour = false;
   int recursive = 0;             // 0 no, 1 do not follow symlinks, 2 follow them
-  unsigned jobs = 0;             // threads that read a batch's files into the blob (0: the walking thread reads)
+  // threads that read a batch's files into the blob (0: the walking thread reads).  The reference's default is 0;
+  // with a device-side matcher staging IS the bottleneck (1.6 GB/s with one thread, 12 GB/s with eight, page
+  // cache hot), so this library's build stages in parallel unless told otherwise.
+#ifdef REJIT_B200
+  unsigned jobs = DefaultJobs();
+#else
+  unsigned jobs = 0;
+#endif
+  static unsigned DefaultJobs() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw > 1 ? std::min(16u, hw - 1u) : 1u;
+  }
   unsigned nopenfd = 1024;
   unsigned before = 0;
   unsigned after = 0;
@@ -264,8 +294,10 @@ class Jrep {
       files_.push_back(FileSpan{path, begin, size, 0});
       return 0;
     }
+    const double t0 = Trace::Now();
     const size_t got = ReadFile(fd, at, size);
     close(fd);
+    g_trace.stage += Trace::Now() - t0;
     blob_.Shrink(size - got);                          // the file shrank while we read it
     if (got == 0) {
       if (!files_.empty()) blob_.Shrink(1);
@@ -282,10 +314,16 @@ class Jrep {
   void Run() {
     if (files_.empty()) return;
     bool gaps = false;
+    double t0 = Trace::Now();
     if (o_.jobs > 0 && !Stage(&gaps)) return;
     const char* text = blob_.data();
     const size_t length = blob_.used();
     std::vector<rejit::Match> found, lines;
+    double t1 = Trace::Now();
+    g_trace.stage += t1 - t0;
+    g_trace.bytes += length;
+    g_trace.files += files_.size();
+    ++g_trace.batches;
 #ifdef REJIT_B200
     std::unique_ptr<rejit::Text> resident;             // the only upload of the batch
     if (!gaps) {
@@ -326,6 +364,9 @@ class Jrep {
 #endif
     }
 
+    t0 = Trace::Now();
+    g_trace.match += t0 - t1;
+    double again = 0;
     size_t line_at = 0;
     std::vector<rejit::Match> file_lines, file_found;
     for (f = 0; f < files_.size(); ++f) {
@@ -334,15 +375,21 @@ class Jrep {
       const rejit::Match* mine = found.data() + first[f];
       size_t n_mine = first[f + 1] - first[f];
       file_lines.clear();
+      const double m0 = Trace::Now();
       if (alone[f]) {                                  // as a text of its own
         file_found.clear();
         re_.MatchAll(begin, files_[f].size, &file_found);
         mine = file_found.data();
         n_mine = file_found.size();
+        ++g_trace.reruns;
       }
-      if (n_mine == 0) continue;
+      if (n_mine == 0) {
+        again += Trace::Now() - m0;
+        continue;
+      }
       if (alone[f] || !whole) {
         sol_.MatchAll(begin, files_[f].size, &file_lines);
+        again += Trace::Now() - m0;
       } else {
         while (line_at < lines.size() && lines[line_at].begin < begin) ++line_at;
         for (; line_at < lines.size() && lines[line_at].begin <= end; ++line_at) file_lines.push_back(lines[line_at]);
@@ -351,6 +398,8 @@ class Jrep {
       printer_.File(files_[f].path, mine, n_mine, file_lines);
     }
     printer_.Flush();
+    g_trace.match += again;
+    g_trace.print += Trace::Now() - t0 - again;
     files_.clear();
     blob_.Clear();
   }
@@ -449,7 +498,7 @@ void Usage(FILE* to, const char* self) {
           "  -A, --after-context[=N]       print N lines of context after every match\n"
           "  -B, --before-context[=N]      print N lines of context before every match\n"
           "  -C, --context[=N]             both\n"
-          "  -j, --jobs[=N]                N threads stage (read) the files of a batch; matching is per batch\n"
+          "  -j, --jobs[=N]                N threads stage (read) the files of a batch (0: none); matching is per batch\n"
           "  -k, --nopenfd[=N]             directories nftw() may hold open (default 1024)\n"
           "      --batch-bytes=N           bytes staged per matcher call (default 256 MiB; 0 = one call per file)\n"
           "      --gpus=N                  shard every batch over N devices (this library only)\n",
@@ -478,7 +527,7 @@ bool ParseArguments(int argc, char** argv, Options* o) {
       case 'r': o->recursive = 1; break;
       case 'R': o->recursive = 2; break;
       case 'c': o->colour = true; break;
-      case 'j': o->jobs = optarg ? Number(optarg) : std::max(1u, std::thread::hardware_concurrency() - 1u); break;
+      case 'j': o->jobs = optarg ? Number(optarg) : Options::DefaultJobs(); break;
       case 'k': if (optarg) o->nopenfd = Number(optarg); break;
       case 'A': if (optarg) o->after = Number(optarg); break;
       case 'B': if (optarg) o->before = Number(optarg); break;

@@ -72,7 +72,8 @@ def _check_jrep_against_golden(exe, root, paths):
         expected = case["stdout"].encode("latin-1")
         files = [p for p in paths if p.startswith(case.get("only", ""))]
         for batch in jrep_tree.BATCHES:
-            jobs = ["-j3"] if batch == "30000" else []       # one mode with the batch staged by three threads
+            # staging: the build's default (threads on librejit_b200, none on the reference), none, three threads
+            jobs = {"5000": ["-j0"], "30000": ["-j3"]}.get(batch, [])
             r = subprocess.run([exe] + case["options"] + jobs + ["--batch-bytes=" + batch, case["re"]] + files, cwd=root,
                                capture_output=True)
             assert r.returncode == 0, (case["re"], case["options"], batch, r.stderr[-300:])
