@@ -45,19 +45,30 @@ extern char* const rejit_status_string;
 
 namespace internal { class RegexpInfo; }
 
+class Regej;
+
 // A text resident in device memory (new in rejit_b200): the constructor copies
 // `size` bytes to the device once; every Regej::MatchAll(const Text&, ...) then
 // costs a scan and the copy of its match list, no upload.  Matches point into
 // the caller's host buffer, which must stay alive and unchanged.
+// ReplaceAll produces a NEW text on the device (the rebuild of Replace runs there
+// too), so substitutions chain without the text ever returning to the host
+// (regex-dna: strip, nine counts, eleven substitutions on one upload).  Such a
+// text has no host buffer: data() is NULL, use MatchAllCount / MatchAllCountSet
+// / ReplaceAll / Download on it.
 class Text {
  public:
   Text(const char* text, size_t size, int device = 0);
   ~Text();
   const char* data() const { return text_; }
   size_t size() const { return size_; }
+  // Every match of `re` replaced by `with`; the caller owns the result.
+  Text* ReplaceAll(Regej& re, const string& with, size_t* n_matches = NULL) const;
+  string Download() const;
 
  private:
   friend class Regej;
+  Text(void* handle, size_t size);
   Text(const Text&);
   Text& operator=(const Text&);
   const char* text_;
@@ -90,6 +101,10 @@ class Regej {
   size_t MatchAllCount(const char* text, size_t text_size);
   // MatchAll over a text that is already on the device (new in rejit_b200).
   size_t MatchAll(const Text& text, std::vector<struct Match>* matches);
+  size_t MatchAllCount(const Text& text);
+  // (*counts)[i] = patterns[i]->MatchAllCount(text); sets of fixed-length
+  // alternations are fused into one scan of the text.  Returns the total.
+  static size_t MatchAllCountSet(const std::vector<Regej*>& patterns, const Text& text, std::vector<size_t>* counts);
   // Same result as MatchAll, with the text sharded by contiguous slab over
   // n_gpus devices of this machine (new in rejit_b200).
   size_t MatchAllParallel(const char* text, size_t text_size, std::vector<struct Match>* matches,
@@ -109,6 +124,7 @@ class Regej {
   bool Compile(MatchType match_type);
 
  private:
+  friend class Text;
   char const* const regexp_;
   internal::RegexpInfo* rinfo_;
   Status status_;

@@ -133,6 +133,29 @@ Text::Text(const char* text, size_t size, int device) : text_(text), size_(size)
   if (!handle_) Fatal("Text", err);
 }
 
+Text::Text(void* handle, size_t size) : text_(nullptr), size_(size), handle_(handle) {}
+
+Text* Text::ReplaceAll(Regej& re, const string& with, size_t* n_matches) const {
+  if (!re.Compile(kMatchAll)) return nullptr;
+  char err[256];
+  err[0] = 0;
+  int64_t n = 0;
+  rejit_b200_text* out = rejit_b200_replace_all_text(re.rinfo_->program, static_cast<const rejit_b200_text*>(handle_),
+                                                     with.data(), with.size(), &n, nullptr, err, sizeof err);
+  if (!out) Fatal("Text::ReplaceAll", err);
+  if (n_matches) *n_matches = static_cast<size_t>(n);
+  return new Text(out, rejit_b200_text_length(out));
+}
+
+string Text::Download() const {
+  string out(size_, '\0');
+  char err[256];
+  err[0] = 0;
+  if (rejit_b200_text_download(static_cast<const rejit_b200_text*>(handle_), size_ ? &out[0] : nullptr, size_, err, sizeof err) != 0)
+    Fatal("Text::Download", err);
+  return out;
+}
+
 Text::~Text() {
   if (handle_) rejit_b200_text_free(static_cast<rejit_b200_text*>(handle_));
 }
@@ -150,6 +173,37 @@ size_t Regej::MatchAll(const Text& text, vector<Match>* matches) {
   }
   rejit_b200_free(pairs);
   return matches ? matches->size() : static_cast<size_t>(n);
+}
+
+size_t Regej::MatchAllCount(const Text& text) {
+  if (!Compile(kMatchAll)) return 0;
+  char err[256];
+  int64_t n = rejit_b200_match_all_text(rinfo_->program, static_cast<const rejit_b200_text*>(text.handle_), nullptr, nullptr,
+                                        err, sizeof err);
+  if (n < 0) Fatal("MatchAllCount", err);
+  return static_cast<size_t>(n);
+}
+
+size_t Regej::MatchAllCountSet(const std::vector<Regej*>& patterns, const Text& text, std::vector<size_t>* counts) {
+  std::vector<rejit_b200_program*> progs;
+  for (Regej* r : patterns) {
+    if (!r->Compile(kMatchAll)) return 0;
+    progs.push_back(r->rinfo_->program);
+  }
+  if (progs.empty()) return 0;
+  char err[256];
+  err[0] = 0;
+  rejit_b200_set* set = rejit_b200_set_create(progs.data(), static_cast<int>(progs.size()));
+  if (!set) Fatal("MatchAllCountSet", "cannot create the pattern set");
+  std::vector<int64_t> found(progs.size(), 0);
+  if (rejit_b200_match_all_set_text(set, static_cast<const rejit_b200_text*>(text.handle_), found.data(), nullptr, nullptr, err,
+                                    sizeof err) != 0)
+    Fatal("MatchAllCountSet", err);
+  rejit_b200_set_free(set);
+  size_t total = 0;
+  if (counts) counts->assign(found.begin(), found.end());
+  for (int64_t c : found) total += static_cast<size_t>(c);
+  return total;
 }
 
 size_t Regej::MatchAllParallel(const char* text, size_t text_size, vector<Match>* matches, int n_gpus) {

@@ -28,8 +28,9 @@ def _build(tmp_path, name="regexdna"):
     return exe
 
 
-def test_sample_compiles_against_rejit_h_and_needs_a_gpu(tmp_path):
-    exe = _build(tmp_path)
+@pytest.mark.parametrize("name", ["regexdna", "regexdna_device"])
+def test_sample_compiles_against_rejit_h_and_needs_a_gpu(tmp_path, name):
+    exe = _build(tmp_path, name)
     import rejit_b200
     if rejit_b200.device_count() > 0:
         pytest.skip("a GPU is present: covered by the gpu tier")
@@ -38,10 +39,13 @@ def test_sample_compiles_against_rejit_h_and_needs_a_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-def test_sample_regexdna_output(tmp_path):
+@pytest.mark.parametrize("name", ["regexdna", "regexdna_device"])
+def test_sample_regexdna_output(tmp_path, name):
+    """regexdna: written against the reference's surface only (twelve host round trips);
+    regexdna_device: one upload, rejit::Text chain + the fused set count.  Same output."""
     import rejit_oracle as O
     from rejit_b200 import workloads as W
-    exe = _build(tmp_path)
+    exe = _build(tmp_path, name)
     fa = W.fasta_file(20000)
     r = subprocess.run([exe], input=fa, capture_output=True, check=True)
 
