@@ -85,7 +85,10 @@ struct Options {
   unsigned nopenfd = 1024;
   unsigned before = 0;
   unsigned after = 0;
-  size_t batch_bytes = size_t(256) << 20;   // 0: one call per file (the reference's granularity)
+  // bytes staged per matcher call; 0: one call per file (the reference's granularity).  64 MiB: half of the
+  // B200's L2, so the line-index pass and the per-file re-runs find the batch in L2, and small enough that
+  // staging memory is touched once and reused (a 1 GiB batch spends more time in page faults than in reading).
+  size_t batch_bytes = size_t(64) << 20;
   int gpus = 1;
 };
 
@@ -115,7 +118,7 @@ class Blob {
 
  private:
   void Grow(size_t need) {
-    size_t cap = std::max(need, capacity_ + capacity_ / 2);
+    size_t cap = std::max(need, 2 * capacity_);
     cap = std::max(cap, size_t(1) << 20);
     char* fresh = Allocate(cap);
     if (!fresh) {
@@ -262,14 +265,13 @@ class Jrep {
   // Stages one file.  Returns 0 or the errno of the failed open (the reference
   // stops the whole run there: sample/jrep.cc:269-274, 540-541).  With -j N only
   // the place in the blob is reserved here; N threads fill the batch in Run().
-  int Add(const char* path) {
+  int Add(const char* path, const struct stat& known) {
     if (pending_error_) return pending_error_;
     int fd = -1;
     struct stat st;
     size_t size;
-    if (o_.jobs > 0) {
-      if (stat(path, &st) != 0) return errno;
-      size = static_cast<size_t>(st.st_size);
+    if (o_.jobs > 0) {                                 // the walk has the size already: no system call here
+      size = static_cast<size_t>(known.st_size);
       if (size == 0) return access(path, R_OK) == 0 ? 0 : errno;
     } else {
       fd = open(path, O_RDONLY);
@@ -280,20 +282,23 @@ class Jrep {
         return 0;
       }
     }
-    if (!files_.empty() && (o_.batch_bytes == 0 || blob_.used() + size + 1 > o_.batch_bytes)) {
+    const size_t staged = o_.jobs > 0 ? planned_ : blob_.used();
+    if (!files_.empty() && (o_.batch_bytes == 0 || staged + size + 1 > o_.batch_bytes)) {
       Run();
       if (pending_error_) {
         if (fd >= 0) close(fd);
         return pending_error_;
       }
     }
+    if (o_.jobs > 0) {                                 // only a place in the batch; Stage() allocates once and fills it
+      if (!files_.empty()) ++planned_;
+      files_.push_back(FileSpan{path, planned_, size, 0});
+      planned_ += size;
+      return 0;
+    }
     if (!files_.empty()) *blob_.Extend(1) = '\n';      // the separator
     const size_t begin = blob_.used();
     char* at = blob_.Extend(size);
-    if (o_.jobs > 0) {
-      files_.push_back(FileSpan{path, begin, size, 0});
-      return 0;
-    }
     const double t0 = Trace::Now();
     const size_t got = ReadFile(fd, at, size);
     close(fd);
@@ -420,8 +425,12 @@ class Jrep {
   // they run).  A file that cannot be opened ends the run there, as in Add(): the batch is cut before
   // it.  A file that shrank since stat() leaves a hole, filled with separators.  False: nothing to scan.
   bool Stage(bool* gaps) {
+    blob_.Clear();
+    blob_.Extend(planned_);
+    planned_ = 0;
     std::atomic<size_t> next(0);
     char* const base = blob_.data();
+    for (size_t i = 1; i < files_.size(); ++i) base[files_[i].begin - 1] = '\n';      // the separators
     auto work = [&]() {
       for (size_t i; (i = next.fetch_add(1)) < files_.size();) {
         FileSpan& f = files_[i];
@@ -472,6 +481,7 @@ class Jrep {
 
   static const size_t kShort = size_t(1) << (sizeof(size_t) * 8 - 1);
   int pending_error_ = 0;
+  size_t planned_ = 0;                                 // -j: bytes of the batch being planned (files + separators)
   const Options& o_;
   rejit::Regej re_, sol_;
   Printer printer_;
@@ -481,8 +491,8 @@ class Jrep {
 
 Jrep* g_jrep = nullptr;   // nftw has no user pointer
 
-int Visit(const char* path, const struct stat*, int type, struct FTW*) {
-  return type == FTW_F ? g_jrep->Add(path) : 0;
+int Visit(const char* path, const struct stat* st, int type, struct FTW*) {
+  return type == FTW_F ? g_jrep->Add(path, *st) : 0;
 }
 
 void Usage(FILE* to, const char* self) {
@@ -500,7 +510,7 @@ void Usage(FILE* to, const char* self) {
           "  -C, --context[=N]             both\n"
           "  -j, --jobs[=N]                N threads stage (read) the files of a batch (0: none); matching is per batch\n"
           "  -k, --nopenfd[=N]             directories nftw() may hold open (default 1024)\n"
-          "      --batch-bytes=N           bytes staged per matcher call (default 256 MiB; 0 = one call per file)\n"
+          "      --batch-bytes=N           bytes staged per matcher call (default 64 MiB; 0 = one call per file)\n"
           "      --gpus=N                  shard every batch over N devices (this library only)\n",
           self);
 }
@@ -572,7 +582,7 @@ int main(int argc, char** argv) {
       }
       rc = nftw(path, Visit, static_cast<int>(options.nopenfd), options.recursive == 2 ? 0 : FTW_PHYS);
     } else if (S_ISREG(st.st_mode)) {
-      rc = jrep.Add(path);
+      rc = jrep.Add(path, st);
     } else {
       rc = 0;
     }
