@@ -2,7 +2,9 @@
 // device-side matcher: files are staged into ONE host blob per batch (a per-file
 // offset table beside it) and every batch costs one upload and one pass for the
 // pattern plus one for the line index "^", instead of two MatchAll calls per
-// file.  Output, options and exit codes follow the reference's jrep
+// file.  The walk plans a batch from the sizes it already has, N threads fill it
+// (-j N), and a matcher thread uploads, scans and prints it while the next batch
+// is being planned and filled.  Output, options and exit codes follow the reference's jrep
 // (/root/reference/sample/jrep.cc: options :84-126, per-file printing :261-405,
 // path handling :518-545), which this file restates and does not copy.
 //
@@ -33,7 +35,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -247,10 +251,21 @@ class Printer {
   std::string out_;
 };
 
-// ---- one batch --------------------------------------------------------------------
+// ---- batches -------------------------------------------------------------------------
+// Two of them: while the matcher works on one (upload, scans, printing), the walk plans and the staging
+// threads fill the other.
+struct Batch {
+  Blob blob;
+  std::vector<FileSpan> files;
+  size_t planned = 0;            // -j: bytes of the batch being planned (files + separators)
+  bool gaps = false;             // a file shrank or vanished while it was staged: no batch-wide scan
+  bool staged = false;           // handed to the matcher, not yet processed
+};
+
 class Jrep {
  public:
-  Jrep(const Options& o) : o_(o), re_(o.pattern), sol_("^"), printer_(o) {}
+  Jrep(const Options& o) : o_(o), re_(o.pattern), sol_("^"), printer_(o), cur_(&batches_[0]) {}
+  ~Jrep() { Finish(); }
 
   bool Ready() {
     if (re_.status() != rejit::RejitSuccess) {
@@ -282,8 +297,8 @@ class Jrep {
         return 0;
       }
     }
-    const size_t staged = o_.jobs > 0 ? planned_ : blob_.used();
-    if (!files_.empty() && (o_.batch_bytes == 0 || staged + size + 1 > o_.batch_bytes)) {
+    const size_t staged = o_.jobs > 0 ? cur_->planned : cur_->blob.used();
+    if (!cur_->files.empty() && (o_.batch_bytes == 0 || staged + size + 1 > o_.batch_bytes)) {
       Run();
       if (pending_error_) {
         if (fd >= 0) close(fd);
@@ -291,43 +306,94 @@ class Jrep {
       }
     }
     if (o_.jobs > 0) {                                 // only a place in the batch; Stage() allocates once and fills it
-      if (!files_.empty()) ++planned_;
-      files_.push_back(FileSpan{path, planned_, size, 0});
-      planned_ += size;
+      if (!cur_->files.empty()) ++cur_->planned;
+      cur_->files.push_back(FileSpan{path, cur_->planned, size, 0});
+      cur_->planned += size;
       return 0;
     }
-    if (!files_.empty()) *blob_.Extend(1) = '\n';      // the separator
-    const size_t begin = blob_.used();
-    char* at = blob_.Extend(size);
+    if (!cur_->files.empty()) *cur_->blob.Extend(1) = '\n';      // the separator
+    const size_t begin = cur_->blob.used();
+    char* at = cur_->blob.Extend(size);
     const double t0 = Trace::Now();
     const size_t got = ReadFile(fd, at, size);
     close(fd);
     g_trace.stage += Trace::Now() - t0;
-    blob_.Shrink(size - got);                          // the file shrank while we read it
+    cur_->blob.Shrink(size - got);                          // the file shrank while we read it
     if (got == 0) {
-      if (!files_.empty()) blob_.Shrink(1);
+      if (!cur_->files.empty()) cur_->blob.Shrink(1);
       return 0;
     }
-    files_.push_back(FileSpan{path, begin, got, 0});
+    cur_->files.push_back(FileSpan{path, begin, got, 0});
     return 0;
   }
 
   // The errno that ended the run, if a staging thread could not open a file.
   int error() const { return pending_error_; }
 
-  // Scans what is staged, prints, and empties the batch.
+  // Stages the batch that was planned and hands it to the matcher: inline without -j, else to the matcher
+  // thread, so that uploading, scanning and printing batch k overlap planning and staging batch k + 1.
   void Run() {
-    if (files_.empty()) return;
-    bool gaps = false;
-    double t0 = Trace::Now();
-    if (o_.jobs > 0 && !Stage(&gaps)) return;
-    const char* text = blob_.data();
-    const size_t length = blob_.used();
+    Batch& b = *cur_;
+    if (b.files.empty()) return;
+    b.gaps = false;
+    const double t0 = Trace::Now();
+    if (o_.jobs > 0 && !Stage(&b.gaps)) return;
+    g_trace.stage += Trace::Now() - t0;
+    if (o_.jobs == 0) {
+      Process(b);
+      return;
+    }
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      if (!matcher_.joinable()) matcher_ = std::thread(&Jrep::MatcherLoop, this);
+      b.staged = true;
+    }
+    cv_.notify_all();
+    cur_ = cur_ == &batches_[0] ? &batches_[1] : &batches_[0];
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return !cur_->staged; });
+  }
+
+  // Flushes the last batch and waits for the matcher.
+  void Finish() {
+    Run();
+    if (!matcher_.joinable()) return;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      done_ = true;
+    }
+    cv_.notify_all();
+    matcher_.join();
+  }
+
+ private:
+  void MatcherLoop() {
+    for (size_t k = 0;; ++k) {
+      Batch& b = batches_[k & 1];
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return b.staged || done_; });
+        if (!b.staged) return;
+      }
+      Process(b);
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        b.staged = false;
+      }
+      cv_.notify_all();
+    }
+  }
+
+  // Scans one staged batch, prints, and empties it.
+  void Process(Batch& batch) {
+    std::vector<FileSpan>& files = batch.files;
+    const bool gaps = batch.gaps;
+    const char* text = batch.blob.data();
+    const size_t length = batch.blob.used();
     std::vector<rejit::Match> found, lines;
-    double t1 = Trace::Now();
-    g_trace.stage += t1 - t0;
+    double t1 = Trace::Now(), t0;
     g_trace.bytes += length;
-    g_trace.files += files_.size();
+    g_trace.files += files.size();
     ++g_trace.batches;
 #ifdef REJIT_B200
     std::unique_ptr<rejit::Text> resident;             // the only upload of the batch
@@ -343,22 +409,22 @@ class Jrep {
     // Which file does each match begin in (a file owns [begin, begin + size], its
     // separator's position included), and which files does a match that swallows
     // a separator touch.
-    std::vector<char> alone(files_.size(), gaps ? 1 : 0);   // a batch with holes: every file on its own bytes
-    std::vector<size_t> first(files_.size() + 1, 0);   // found[first[f] .. first[f+1]) begin in file f
+    std::vector<char> alone(files.size(), gaps ? 1 : 0);   // a batch with holes: every file on its own bytes
+    std::vector<size_t> first(files.size() + 1, 0);   // found[first[f] .. first[f+1]) begin in file f
     size_t f = 0;
     for (size_t i = 0; i < found.size(); ++i) {
       const size_t b = static_cast<size_t>(found[i].begin - text), e = static_cast<size_t>(found[i].end - text);
-      while (f + 1 < files_.size() && b > files_[f].begin + files_[f].size) first[++f] = i;
-      if (e > files_[f].begin + files_[f].size)                         // a file the match only abuts counts too:
-        for (size_t g = f; g < files_.size() && files_[g].begin <= e; ++g) alone[g] = 1;   // its empty match there is lost
+      while (f + 1 < files.size() && b > files[f].begin + files[f].size) first[++f] = i;
+      if (e > files[f].begin + files[f].size)                         // a file the match only abuts counts too:
+        for (size_t g = f; g < files.size() && files[g].begin <= e; ++g) alone[g] = 1;   // its empty match there is lost
     }
-    while (f < files_.size()) first[++f] = found.size();
+    while (f < files.size()) first[++f] = found.size();
 
     // The line index: one pass over the resident batch when much of it has
     // matches, else per matching file (the reference indexes only those).
     size_t hit_files = 0, hit_bytes = 0;
-    for (f = 0; f < files_.size(); ++f)
-      if (!alone[f] && first[f] != first[f + 1]) ++hit_files, hit_bytes += files_[f].size;
+    for (f = 0; f < files.size(); ++f)
+      if (!alone[f] && first[f] != first[f + 1]) ++hit_files, hit_bytes += files[f].size;
     const bool whole = !gaps && (hit_files > 64 || hit_bytes * 8 > length);
     if (whole && hit_files) {
 #ifdef REJIT_B200
@@ -374,16 +440,16 @@ class Jrep {
     double again = 0;
     size_t line_at = 0;
     std::vector<rejit::Match> file_lines, file_found;
-    for (f = 0; f < files_.size(); ++f) {
-      const char* begin = text + files_[f].begin;
-      const char* end = begin + files_[f].size;
+    for (f = 0; f < files.size(); ++f) {
+      const char* begin = text + files[f].begin;
+      const char* end = begin + files[f].size;
       const rejit::Match* mine = found.data() + first[f];
       size_t n_mine = first[f + 1] - first[f];
       file_lines.clear();
       const double m0 = Trace::Now();
       if (alone[f]) {                                  // as a text of its own
         file_found.clear();
-        re_.MatchAll(begin, files_[f].size, &file_found);
+        re_.MatchAll(begin, files[f].size, &file_found);
         mine = file_found.data();
         n_mine = file_found.size();
         ++g_trace.reruns;
@@ -393,23 +459,23 @@ class Jrep {
         continue;
       }
       if (alone[f] || !whole) {
-        sol_.MatchAll(begin, files_[f].size, &file_lines);
+        sol_.MatchAll(begin, files[f].size, &file_lines);
         again += Trace::Now() - m0;
       } else {
         while (line_at < lines.size() && lines[line_at].begin < begin) ++line_at;
         for (; line_at < lines.size() && lines[line_at].begin <= end; ++line_at) file_lines.push_back(lines[line_at]);
       }
       file_lines.push_back(rejit::Match{end, end});    // lets the last line be printed (sample/jrep.cc:294-296)
-      printer_.File(files_[f].path, mine, n_mine, file_lines);
+      printer_.File(files[f].path, mine, n_mine, file_lines);
     }
     printer_.Flush();
     g_trace.match += again;
     g_trace.print += Trace::Now() - t0 - again;
-    files_.clear();
-    blob_.Clear();
+    files.clear();
+    batch.blob.Clear();
+    batch.planned = 0;
   }
 
- private:
   static size_t ReadFile(int fd, char* at, size_t size) {
     size_t got = 0;
     while (got < size) {
@@ -425,15 +491,15 @@ class Jrep {
   // they run).  A file that cannot be opened ends the run there, as in Add(): the batch is cut before
   // it.  A file that shrank since stat() leaves a hole, filled with separators.  False: nothing to scan.
   bool Stage(bool* gaps) {
-    blob_.Clear();
-    blob_.Extend(planned_);
-    planned_ = 0;
+    cur_->blob.Clear();
+    cur_->blob.Extend(cur_->planned);
+    cur_->planned = 0;
     std::atomic<size_t> next(0);
-    char* const base = blob_.data();
-    for (size_t i = 1; i < files_.size(); ++i) base[files_[i].begin - 1] = '\n';      // the separators
+    char* const base = cur_->blob.data();
+    for (size_t i = 1; i < cur_->files.size(); ++i) base[cur_->files[i].begin - 1] = '\n';      // the separators
     auto work = [&]() {
-      for (size_t i; (i = next.fetch_add(1)) < files_.size();) {
-        FileSpan& f = files_[i];
+      for (size_t i; (i = next.fetch_add(1)) < cur_->files.size();) {
+        FileSpan& f = cur_->files[i];
         int fd = open(f.path.c_str(), O_RDONLY);
         if (fd < 0) {
           f.error = errno ? errno : EIO;
@@ -446,34 +512,34 @@ class Jrep {
       }
     };
     std::vector<std::thread> pool;
-    const size_t n_threads = std::min<size_t>(o_.jobs, files_.size());
+    const size_t n_threads = std::min<size_t>(o_.jobs, cur_->files.size());
     for (size_t t = 1; t < n_threads; ++t) pool.push_back(std::thread(work));
     work();
     for (std::thread& t : pool) t.join();
-    size_t keep = files_.size();
-    for (size_t i = 0; i < files_.size(); ++i) {
-      if (files_[i].error) {
-        pending_error_ = files_[i].error;
+    size_t keep = cur_->files.size();
+    for (size_t i = 0; i < cur_->files.size(); ++i) {
+      if (cur_->files[i].error) {
+        pending_error_ = cur_->files[i].error;
         keep = i;
         break;
       }
-      if (files_[i].size & kShort) {
-        files_[i].size &= ~kShort;
+      if (cur_->files[i].size & kShort) {
+        cur_->files[i].size &= ~kShort;
         *gaps = true;
       }
     }
-    if (keep < files_.size()) {
-      files_.resize(keep);
-      blob_.Clear();
-      if (keep) blob_.Extend(files_[keep - 1].begin + files_[keep - 1].size);
+    if (keep < cur_->files.size()) {
+      cur_->files.resize(keep);
+      cur_->blob.Clear();
+      if (keep) cur_->blob.Extend(cur_->files[keep - 1].begin + cur_->files[keep - 1].size);
     }
     // files that turned out empty own nothing (the reference skips them, sample/jrep.cc:277-279)
     size_t w = 0;
-    for (size_t i = 0; i < files_.size(); ++i)
-      if (files_[i].size) files_[w++] = files_[i]; else *gaps = true;
-    files_.resize(w);
-    if (files_.empty()) {
-      blob_.Clear();
+    for (size_t i = 0; i < cur_->files.size(); ++i)
+      if (cur_->files[i].size) cur_->files[w++] = cur_->files[i]; else *gaps = true;
+    cur_->files.resize(w);
+    if (cur_->files.empty()) {
+      cur_->blob.Clear();
       return false;
     }
     return true;
@@ -481,12 +547,15 @@ class Jrep {
 
   static const size_t kShort = size_t(1) << (sizeof(size_t) * 8 - 1);
   int pending_error_ = 0;
-  size_t planned_ = 0;                                 // -j: bytes of the batch being planned (files + separators)
   const Options& o_;
   rejit::Regej re_, sol_;
   Printer printer_;
-  Blob blob_;
-  std::vector<FileSpan> files_;
+  Batch batches_[2];
+  Batch* cur_;                                         // the batch being planned
+  std::thread matcher_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  bool done_ = false;
 };
 
 Jrep* g_jrep = nullptr;   // nftw has no user pointer
@@ -588,6 +657,6 @@ int main(int argc, char** argv) {
     }
     if (rc != 0) break;            // an unreadable file ends the run; what was staged before it is still printed
   }
-  jrep.Run();
+  jrep.Finish();
   return rc ? rc : jrep.error();
 }
