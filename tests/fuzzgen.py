@@ -105,3 +105,74 @@ def rand_long_literal_case(r: random.Random) -> tuple:
             w[r.randrange(len(w))] = r.choice(alpha)
         parts.append(r.choice(alpha) + "".join(w) + r.choice(["a", "bd", "cc"]))
     return pat, "".join(parts).encode("latin-1")
+
+
+# ---- the rest of the dialect -------------------------------------------------------------------
+# Bracket ranges (also negated, with a leading / trailing '-'), the escapes of src/parser.cc:53-117
+# (classes, escaped metacharacters, \\xHH with the reference's letter quirk), repetitions on all of
+# them, and texts with bytes >= 0x80 (ranges compare as signed char, x64/codegen-x64.cc:898-908).
+RICH_ESCAPES = ["\\d", "\\D", "\\s", "\\S", "\\t", "\\n", "\\(", "\\)", "\\[", "\\]", "\\{", "\\}", "\\|", "\\*",
+                "\\+", "\\^", "\\$", "\\\\", "\\x41", "\\x4A", "\\x7e", "\\x09", "\\xaB"]
+RICH_TEXT = "ab19AzJ@ \t\n(~Z5" + "\x80\xab\xff"
+
+
+def _rich_atom(r: random.Random, depth: int) -> str:
+    k = r.random()
+    if k < 0.30:
+        return "".join(r.choice("ab19Az") for _ in range(r.randint(1, 3)))
+    if k < 0.45:
+        return r.choice(RICH_ESCAPES)
+    if k < 0.50:
+        return "."
+    if k < 0.75:
+        items = []
+        for _ in range(r.randint(1, 3)):
+            if r.random() < 0.5:
+                lo, hi = sorted(r.sample("09azAZ15bJ", 2))
+                items.append(lo + "-" + hi)
+            else:
+                items.append(r.choice("ab19AZ@ -"))
+        body = "".join(items)
+        if r.random() < 0.15:
+            body = "-" + body
+        if r.random() < 0.15:
+            body = body + "-"
+        return "[" + ("^" if r.random() < 0.3 else "") + body + "]"
+    if k < 0.80:
+        return r.choice(["^", "$"])
+    if depth > 0:
+        return "(" + _rich_alt(r, depth - 1) + ")"
+    return r.choice("ab19")
+
+
+def _rich_piece(r: random.Random, depth: int) -> str:
+    a = _rich_atom(r, depth)
+    if a in ("^", "$"):
+        return a
+    k = r.random()
+    if k < 0.6:
+        return a
+    if k < 0.7:
+        return a + "*"
+    if k < 0.8:
+        return a + "+"
+    if k < 0.86:
+        return a + "?"
+    lo = r.randint(0, 2)
+    return a + r.choice(["{%d}" % max(lo, 1), "{%d,%d}" % (lo, lo + r.randint(0, 2)), "{%d,}" % lo, "{,%d}" % (lo + 1)])
+
+
+def _rich_concat(r: random.Random, depth: int) -> str:
+    return "".join(_rich_piece(r, depth) for _ in range(r.randint(1, 4)))
+
+
+def _rich_alt(r: random.Random, depth: int) -> str:
+    return "|".join(_rich_concat(r, depth) for _ in range(1 if r.random() < 0.6 else r.randint(2, 3)))
+
+
+def rand_rich_pattern(r: random.Random) -> str:
+    return _rich_alt(r, 2)
+
+
+def rand_rich_text(r: random.Random, n: int) -> bytes:
+    return "".join(r.choice(RICH_TEXT) for _ in range(n)).encode("latin-1")

@@ -427,3 +427,23 @@ def test_long_literals(rj):
         if i % 10 == 0:                                   # the same near misses spread over a 100 kB text
             t = b"".join(t + fuzzgen.rand_text(r, "abcd", r.randint(0, 3000)) for _ in range(40))
         assert rj.Regej(pat).match_all(t) == O.Oracle(pat).match_all(t), (pat, len(t))
+
+
+def test_rich_dialect(rj):
+    """Bracket ranges, escapes, \\xHH, repetitions on them, texts with bytes >= 0x80 (tests/fuzzgen.py)."""
+    r = random.Random(4712)
+    checked = 0
+    for _ in range(250):
+        pat = fuzzgen.rand_rich_pattern(r)
+        try:
+            o = O.Oracle(pat)
+        except O.ParserError:
+            assert rj.Regej(pat).status == -1, pat
+            continue
+        g = rj.Regej(pat)
+        assert g.status == 0, pat
+        for n in (r.randint(0, 40), r.randint(200, 3000)):
+            t = fuzzgen.rand_rich_text(r, n)
+            assert g.match_all(t) == o.match_all(t), (pat, t, g.describe())
+            checked += 1
+    assert checked > 300

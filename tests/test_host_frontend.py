@@ -168,6 +168,29 @@ def test_hostsim_fuzz_vs_oracle(hostsim):
     assert checked > 1500
 
 
+def test_hostsim_rich_dialect(hostsim):
+    """The rest of the dialect (ranges, escapes, \\xHH, high bytes; tests/fuzzgen.py): the product's parser accepts
+    exactly what the oracle's accepts, and its tables match like the oracle."""
+    r = random.Random(4711)
+    checked = 0
+    for _ in range(700):
+        pat = fuzzgen.rand_rich_pattern(r)
+        try:
+            o = O.Oracle(pat)
+        except O.ParserError:
+            got, _ = hostsim.match_all(pat, b"")
+            assert got == -1, pat
+            continue
+        for n in (r.randint(0, 40), r.randint(60, 300)):
+            t = fuzzgen.rand_rich_text(r, n)
+            exp = o.match_all(t)
+            for strategy in (-1, 3):
+                got, desc = hostsim.match_all(pat, t, strategy)
+                assert got == exp, (pat, t, desc, strategy)
+            checked += 1
+    assert checked > 1000
+
+
 def test_hostsim_long_literals(hostsim):
     """Literal nodes longer than 16 bytes, exact copies and near misses: the product compares every byte
     (the reference does not: defect B20, tests/test_oracle.py)."""

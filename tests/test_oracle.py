@@ -168,3 +168,36 @@ def test_reference_long_literal_defect_is_modelled():
             assert exact == want, (pat, t)
         checked += 1
     assert checked > 400 and differ > 20, (checked, differ)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="compiled reference not present (GPU box)")
+def test_differential_rich_dialect_vs_compiled_reference():
+    """Bracket ranges, negation, '-' at the edges, the escapes and \\xHH, repetitions on all of them, texts with
+    bytes >= 0x80: the oracle's parser must accept exactly what the reference accepts and match like it."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import Ref
+    ref = Ref()
+    ref.flags(2)
+    r = random.Random(31337)
+    checked = rejected = 0
+    for _ in range(900):
+        pat = fuzzgen.rand_rich_pattern(r)
+        pb = pat.encode("latin-1")
+        try:
+            o = O.Oracle(pat, long_literal_defect=True)
+        except O.ParserError:
+            assert not ref.parse_ok(pb), pat
+            rejected += 1
+            continue
+        assert ref.parse_ok(pb), pat
+        if _has_reference_ub(pat):
+            continue
+        for _ in range(3):
+            t = fuzzgen.rand_rich_text(r, r.choice([r.randint(0, 40), r.randint(60, 300)]))
+            got = [list(m) for m in o.match_all(t)]
+            if got != ref.match_all(pb, t):
+                fresh = subprocess.run([sys.executable, "-c", _FRESH, REF_SO, pb.hex(), t.hex()],
+                                       capture_output=True, text=True).stdout.strip()
+                assert str(got) == fresh, (pat, t)
+            checked += 1
+    assert checked > 1500, (checked, rejected)
