@@ -4,7 +4,9 @@ Tiers:
   * default (`-m "not gpu"`): runs anywhere — oracle vs golden vectors, the host
     front end and table builder vs the oracle (through tests/hostsim.cc, a CPU
     emulation of what the kernels do with the tables), C-ABI symbol checks,
-    world_size-2 gloo test of the slab-stitching protocol.
+    world_size-2 gloo test of the slab-stitching protocol, the samples end to end
+    (on the reference's library, and on tests/hostsim_rejit.cc = the product's own
+    front end behind the rejit.h surface with the kernels emulated).
   * `-m gpu`: the parity tests proper — every call goes through the C ABI of
     librejit_b200.so and runs the sm_100a kernels; results are compared with the
     oracle (oracle/) and the committed golden fixtures (tests/golden/).
@@ -106,6 +108,22 @@ def hostsim():
             return L.hostsim_match_full(pb, len(pb), text, len(text))
 
     return Sim()
+
+
+@pytest.fixture(scope="session")
+def rejit_double(hostsim):
+    """tests/hostsim_rejit.cc: the include/rejit.h surface on top of tests/hostsim.cc (the product's own front end
+    and tables, kernels emulated on the CPU), built as a shared library the samples can link instead of
+    librejit_b200.so.  Test infrastructure only.  Returns the directory that holds libhostsim_rejit.so."""
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    so = os.path.join(out_dir, "libhostsim_rejit.so")
+    srcs = [os.path.join(ROOT, "tests", f) for f in ("hostsim_rejit.cc", "hostsim.cc")] + [
+        os.path.join(ROOT, "rejit_b200", "csrc", "host", f) for f in ("parser.cc", "lower.cc", "automaton.cc")]
+    deps = srcs + [os.path.join(ROOT, "include", "rejit.h"), os.path.join(ROOT, "rejit_b200", "csrc", "cuda", "device_program.h"),
+                   os.path.join(ROOT, "rejit_b200", "csrc", "host", "automaton.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so] + srcs)
+    return out_dir
 
 
 def expand_table_row(row):

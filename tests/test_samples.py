@@ -248,3 +248,53 @@ def test_jrep_patterns_through_the_host_tables(hostsim, tmp_path):
         for text in [blob] + [b for b in bodies if b]:
             got, desc = hostsim.match_all(pat, text)
             assert got == o.match_all(text), (pat, desc, len(text))
+
+
+# ---- the samples end to end on the product's own front end, no GPU ---------------------------------
+def _build_on_double(tmp_path, libdir, name):
+    exe = str(tmp_path / (name + "_on_double"))
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "samples", name + ".cc"),
+                    "-L" + libdir, "-lhostsim_rejit", "-Wl,-rpath," + libdir, "-lpthread", "-o", exe], check=True)
+    return exe
+
+
+def test_samples_end_to_end_on_the_host_tables(rejit_double, tmp_path):
+    """The samples built as for librejit_b200.so (REJIT_B200 defined: pinned staging, rejit::Text, MatchAllParallel,
+    device-side chains) but linked against tests/hostsim_rejit.cc, which answers through the product's parser,
+    lowering and tables with the kernels emulated on the CPU: the library-specific branches of the samples and
+    the front end are exercised together where no GPU exists.  jrep: every golden case in every batching mode,
+    and sharded over "two devices"; regex-dna (both programs): the oracle's counts and lengths; threads."""
+    import jrep_tree
+    import rejit_oracle as O
+    from rejit_b200 import workloads as W
+    root = str(tmp_path / "tree")
+    os.makedirs(root)
+    paths = jrep_tree.make_tree(root)
+    jrep = _build_on_double(tmp_path, rejit_double, "jrep")
+    _check_jrep_against_golden(jrep, root, paths)
+    for case in _jrep_cases()[:3]:
+        files = [p for p in paths if p.startswith(case.get("only", ""))]
+        r = subprocess.run([jrep] + case["options"] + ["--gpus=2", case["re"]] + files, cwd=root, capture_output=True)
+        assert r.returncode == 0 and r.stdout == case["stdout"].encode("latin-1"), (case["re"], r.stderr[-200:])
+
+    fa = W.fasta_file(3000)
+
+    def replace(pat, text, w):
+        out, at = bytearray(), 0
+        for b, e in O.Oracle(pat).match_all(text):
+            out += text[at:b] + w
+            at = e
+        return bytes(out + text[at:])
+
+    seq = replace(W.STRIP_PATTERN, fa, b"")
+    cur = seq
+    for code, alt in W.IUB_SUBSTITUTIONS:
+        cur = replace(code, cur, alt.encode())
+    expected = "\n".join("%s %d" % (p, len(O.Oracle(p).match_all(seq))) for p in W.DNA_PATTERNS) + \
+        "\n\n%d\n%d\n%d\n" % (len(fa), len(seq), len(cur))
+    for name in ("regexdna", "regexdna_device"):
+        r = subprocess.run([_build_on_double(tmp_path, rejit_double, name)], input=fa, capture_output=True, check=True)
+        assert r.stdout.decode() == expected, name
+
+    r = subprocess.run([_build_on_double(tmp_path, rejit_double, "threads"), "4", "2"], capture_output=True)
+    assert r.returncode == 0 and r.stdout.startswith(b"ok "), r.stdout[-200:]
