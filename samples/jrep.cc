@@ -94,7 +94,8 @@ struct Options {
   // 0.14 s at 64 MiB and 0.22 s at 1 GiB for a 512 MB tree); a batch stays far below the B200's L2, so the
   // line-index pass and the per-file re-runs find it there; and 16 MiB still gives every SM ~100 KB to scan.
   size_t batch_bytes = size_t(16) << 20;
-  int gpus = 1;
+  int gpus = 1;                  // devices: batches go to them in rotation (independent files: replicas)
+  bool shard = false;            // instead: every batch is one text cut into slabs over the devices (MatchAllParallel)
 };
 
 struct FileSpan {
@@ -170,13 +171,7 @@ class Blob {
 // ---- printing (one file) ---------------------------------------------------------
 class Printer {
  public:
-  explicit Printer(const Options& o) : o_(o) {}
-  ~Printer() { Flush(); }
-  void Flush() {
-    if (!out_.empty()) fwrite(out_.data(), 1, out_.size(), stdout);
-    fflush(stdout);
-    out_.clear();
-  }
+  Printer(const Options& o, std::string* out) : o_(o), out_(*out) {}
 
   // `lines` = the "^" matches of the file followed by one (end, end) sentinel;
   // `found` = the pattern's matches, at least one.  The walk below reproduces the
@@ -229,7 +224,6 @@ class Printer {
         out_ += "--\n";
       }
     }
-    if (out_.size() > (size_t(4) << 20)) Flush();
   }
 
  private:
@@ -249,23 +243,28 @@ class Printer {
     if (to > from) out_.append(from, static_cast<size_t>(to - from));
   }
   const Options& o_;
-  std::string out_;
+  std::string& out_;
 };
 
 // ---- batches -------------------------------------------------------------------------
-// Two of them: while the matcher works on one (upload, scans, printing), the walk plans and the staging
-// threads fill the other.
+// One more than there are matchers: while each matcher (one per device) works on a batch (upload, scans,
+// formatting), the walk plans and the staging threads fill the next one.  Output is written in batch order.
 struct Batch {
   Blob blob;
   std::vector<FileSpan> files;
   size_t planned = 0;            // -j: bytes of the batch being planned (files + separators)
   bool gaps = false;             // a file shrank or vanished while it was staged: no batch-wide scan
-  bool staged = false;           // handed to the matcher, not yet processed
+  bool staged = false;           // handed to a matcher, not yet printed
+  size_t seq = 0;                // position in the run: batches are printed in this order
+  std::string output;
 };
 
 class Jrep {
  public:
-  Jrep(const Options& o) : o_(o), re_(o.pattern), sol_("^"), printer_(o), cur_(&batches_[0]) {}
+  Jrep(const Options& o) : o_(o), re_(o.pattern), sol_("^"), n_matchers_(o.shard ? 1 : std::max(1, o.gpus)) {
+    for (size_t i = 0; i < n_matchers_ + 1; ++i) batches_.emplace_back(new Batch);
+    cur_ = batches_[0].get();
+  }
   ~Jrep() { Finish(); }
 
   bool Ready() {
@@ -331,8 +330,9 @@ class Jrep {
   // The errno that ended the run, if a staging thread could not open a file.
   int error() const { return pending_error_; }
 
-  // Stages the batch that was planned and hands it to the matcher: inline without -j, else to the matcher
-  // thread, so that uploading, scanning and printing batch k overlap planning and staging batch k + 1.
+  // Stages the batch that was planned and hands it to a matcher: inline without -j, else to the matcher
+  // thread of its device, so that uploading, scanning and formatting batch k overlap planning and staging
+  // batch k + 1 (and, with several devices, the work on batches k - 1, k - 2, ...).
   void Run() {
     Batch& b = *cur_;
     if (b.files.empty()) return;
@@ -341,66 +341,86 @@ class Jrep {
     if (o_.jobs > 0 && !Stage(&b.gaps)) return;
     g_trace.stage += Trace::Now() - t0;
     if (o_.jobs == 0) {
-      Process(b);
+      Process(b, 0);
+      Write(&b);
       return;
     }
     {
       std::unique_lock<std::mutex> lk(mu_);
-      if (!matcher_.joinable()) matcher_ = std::thread(&Jrep::MatcherLoop, this);
+      if (matchers_.empty())
+        for (size_t d = 0; d < n_matchers_; ++d) matchers_.push_back(std::thread(&Jrep::MatcherLoop, this, d));
+      b.seq = submitted_++;
       b.staged = true;
+      cur_ = batches_[submitted_ % batches_.size()].get();
     }
     cv_.notify_all();
-    cur_ = cur_ == &batches_[0] ? &batches_[1] : &batches_[0];
     std::unique_lock<std::mutex> lk(mu_);
     cv_.wait(lk, [&] { return !cur_->staged; });
   }
 
-  // Flushes the last batch and waits for the matcher.
+  // Flushes the last batch and waits for the matchers.
   void Finish() {
     Run();
-    if (!matcher_.joinable()) return;
+    if (matchers_.empty()) return;
     {
       std::unique_lock<std::mutex> lk(mu_);
       done_ = true;
     }
     cv_.notify_all();
-    matcher_.join();
+    for (std::thread& t : matchers_) t.join();
+    matchers_.clear();
   }
 
  private:
-  void MatcherLoop() {
-    for (size_t k = 0;; ++k) {
-      Batch& b = batches_[k & 1];
+  // Matcher d takes batches d, d + n, d + 2n, ... (n matchers), each on device d, and writes a batch's
+  // output when all batches before it have been written.
+  void MatcherLoop(size_t d) {
+    for (size_t k = d;; k += n_matchers_) {
+      Batch& b = *batches_[k % batches_.size()];
       {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return b.staged || done_; });
-        if (!b.staged) return;
+        cv_.wait(lk, [&] { return (b.staged && b.seq == k) || (done_ && submitted_ <= k); });
+        if (!(b.staged && b.seq == k)) return;
       }
-      Process(b);
+      Process(b, static_cast<int>(d));
       {
         std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return printed_ == k; });
+      }
+      Write(&b);
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        ++printed_;
         b.staged = false;
       }
       cv_.notify_all();
     }
   }
 
-  // Scans one staged batch, prints, and empties it.
-  void Process(Batch& batch) {
+  static void Write(Batch* b) {                        // one writer at a time: inline, or the matcher whose turn it is
+    if (!b->output.empty()) fwrite(b->output.data(), 1, b->output.size(), stdout);
+    fflush(stdout);
+    b->output.clear();
+  }
+
+  // Scans one staged batch on `device`, formats its output, and empties it.
+  void Process(Batch& batch, int device) {
+    Printer printer(o_, &batch.output);
     std::vector<FileSpan>& files = batch.files;
     const bool gaps = batch.gaps;
     const char* text = batch.blob.data();
     const size_t length = batch.blob.used();
     std::vector<rejit::Match> found, lines;
     double t1 = Trace::Now(), t0;
-    g_trace.bytes += length;
-    g_trace.files += files.size();
-    ++g_trace.batches;
+    const size_t n_files = files.size();
+    size_t reruns = 0;
+    double match_s = 0;
+    (void)device;
 #ifdef REJIT_B200
     std::unique_ptr<rejit::Text> resident;             // the only upload of the batch
     if (!gaps) {
-      resident.reset(new rejit::Text(text, length));
-      if (o_.gpus > 1) re_.MatchAllParallel(text, length, &found, o_.gpus);
+      resident.reset(new rejit::Text(text, length, device));
+      if (o_.shard && o_.gpus > 1) re_.MatchAllParallel(text, length, &found, o_.gpus);
       else re_.MatchAll(*resident, &found);
     }
 #else
@@ -429,7 +449,7 @@ class Jrep {
     const bool whole = !gaps && (hit_files > 64 || hit_bytes * 8 > length);
     if (whole && hit_files) {
 #ifdef REJIT_B200
-      if (o_.gpus > 1) sol_.MatchAllParallel(text, length, &lines, o_.gpus);
+      if (o_.shard && o_.gpus > 1) sol_.MatchAllParallel(text, length, &lines, o_.gpus);
       else sol_.MatchAll(*resident, &lines);
 #else
       sol_.MatchAll(text, length, &lines);
@@ -437,7 +457,7 @@ class Jrep {
     }
 
     t0 = Trace::Now();
-    g_trace.match += t0 - t1;
+    match_s += t0 - t1;
     double again = 0;
     size_t line_at = 0;
     std::vector<rejit::Match> file_lines, file_found;
@@ -453,7 +473,7 @@ class Jrep {
         re_.MatchAll(begin, files[f].size, &file_found);
         mine = file_found.data();
         n_mine = file_found.size();
-        ++g_trace.reruns;
+        ++reruns;
       }
       if (n_mine == 0) {
         again += Trace::Now() - m0;
@@ -467,11 +487,17 @@ class Jrep {
         for (; line_at < lines.size() && lines[line_at].begin <= end; ++line_at) file_lines.push_back(lines[line_at]);
       }
       file_lines.push_back(rejit::Match{end, end});    // lets the last line be printed (sample/jrep.cc:294-296)
-      printer_.File(files[f].path, mine, n_mine, file_lines);
+      printer.File(files[f].path, mine, n_mine, file_lines);
     }
-    printer_.Flush();
-    g_trace.match += again;
-    g_trace.print += Trace::Now() - t0 - again;
+    {
+      std::unique_lock<std::mutex> lk(mu_);            // several matchers report here
+      g_trace.bytes += length;
+      g_trace.files += n_files;
+      ++g_trace.batches;
+      g_trace.reruns += reruns;
+      g_trace.match += match_s + again;
+      g_trace.print += Trace::Now() - t0 - again;
+    }
     files.clear();
     batch.blob.Clear();
     batch.planned = 0;
@@ -550,12 +576,13 @@ class Jrep {
   int pending_error_ = 0;
   const Options& o_;
   rejit::Regej re_, sol_;
-  Printer printer_;
-  Batch batches_[2];
+  const size_t n_matchers_;
+  std::vector<std::unique_ptr<Batch> > batches_;       // slot of batch seq: seq % (n_matchers_ + 1)
   Batch* cur_;                                         // the batch being planned
-  std::thread matcher_;
+  std::vector<std::thread> matchers_;
   std::mutex mu_;
   std::condition_variable cv_;
+  size_t submitted_ = 0, printed_ = 0;
   bool done_ = false;
 };
 
@@ -581,7 +608,8 @@ void Usage(FILE* to, const char* self) {
           "  -j, --jobs[=N]                N threads stage (read) the files of a batch (0: none); matching is per batch\n"
           "  -k, --nopenfd[=N]             directories nftw() may hold open (default 1024)\n"
           "      --batch-bytes=N           bytes staged per matcher call (default 16 MiB; 0 = one call per file)\n"
-          "      --gpus=N                  shard every batch over N devices (this library only)\n",
+          "      --gpus=N                  use N devices: batches go to them in rotation (this library only)\n"
+          "      --shard                   with --gpus: cut every batch into N slabs instead, one per device\n",
           self);
 }
 
@@ -598,6 +626,7 @@ bool ParseArguments(int argc, char** argv, Options* o) {
       {"nopenfd", optional_argument, nullptr, 'k'},       {"after-context", optional_argument, nullptr, 'A'},
       {"before-context", optional_argument, nullptr, 'B'}, {"context", optional_argument, nullptr, 'C'},
       {"batch-bytes", required_argument, nullptr, 1000},  {"gpus", required_argument, nullptr, 1001},
+      {"shard", no_argument, nullptr, 1002},
       {"help", no_argument, nullptr, '?'},                {nullptr, 0, nullptr, 0}};
   int c;
   while ((c = getopt_long(argc, argv, "HnrRcj::k::A::B::C::", kLong, nullptr)) != -1) {
@@ -614,6 +643,7 @@ bool ParseArguments(int argc, char** argv, Options* o) {
       case 'C': if (optarg) o->before = o->after = Number(optarg); break;
       case 1000: o->batch_bytes = static_cast<size_t>(strtoull(optarg, nullptr, 10)); break;
       case 1001: o->gpus = std::max(1, atoi(optarg)); break;
+      case 1002: o->shard = true; break;
       default: return false;
     }
   }
@@ -632,6 +662,10 @@ int main(int argc, char** argv) {
     return 64;
   }
   if (options.pattern[0] == 0) return 0;
+#ifdef REJIT_B200
+  const int devices = rejit_b200_device_count();
+  if (devices > 0 && options.gpus > devices) options.gpus = devices;
+#endif
 
   Jrep jrep(options);
   if (!jrep.Ready()) return 2;

@@ -138,6 +138,11 @@ def test_jrep_front_end_on_the_reference_library(tmp_path):
         for batch in jrep_tree.BATCHES:
             b = subprocess.run([exe, "-n", "--batch-bytes=" + batch, pat] + names, cwd=meet, capture_output=True, env=noff)
             assert a.returncode == 0 and (a.returncode, a.stdout) == (b.returncode, b.stdout), (pat, batch)
+    # --gpus N on this build = N matcher threads calling the shared compiled Regej (as the reference's jrep does)
+    for extra in (["--gpus=3", "--batch-bytes=7000", "-j2"], ["--gpus=2", "-j4", "--batch-bytes=0"]):
+        a = subprocess.run([ref, "-H", "-n", "-B1", "-r", "ab", "."], cwd=root, capture_output=True, env=noff)
+        b = subprocess.run([exe, "-H", "-n", "-B1", "-r", *extra, "ab", "."], cwd=root, capture_output=True, env=noff)
+        assert a.stdout and (a.returncode, a.stdout) == (b.returncode, b.stdout), extra
     # -j N: N threads stage the batch; same bytes whatever N and the batch size
     a = subprocess.run([ref, "-H", "-n", "-A1", "-r", ";\n}", "."], cwd=root, capture_output=True, env=noff)
     for jobs in ("-j1", "-j4", "-j16"):
@@ -272,10 +277,13 @@ def test_samples_end_to_end_on_the_host_tables(rejit_double, tmp_path):
     paths = jrep_tree.make_tree(root)
     jrep = _build_on_double(tmp_path, rejit_double, "jrep")
     _check_jrep_against_golden(jrep, root, paths)
-    for case in _jrep_cases()[:3]:
+    # several devices: batches in rotation (one matcher thread per device, output in batch order), or every
+    # batch cut into slabs (--shard)
+    for case in _jrep_cases()[:4]:
         files = [p for p in paths if p.startswith(case.get("only", ""))]
-        r = subprocess.run([jrep] + case["options"] + ["--gpus=2", case["re"]] + files, cwd=root, capture_output=True)
-        assert r.returncode == 0 and r.stdout == case["stdout"].encode("latin-1"), (case["re"], r.stderr[-200:])
+        for extra in (["--gpus=2"], ["--gpus=3", "--batch-bytes=7000"], ["--gpus=2", "--shard"], ["--gpus=4", "--batch-bytes=0"]):
+            r = subprocess.run([jrep] + case["options"] + extra + [case["re"]] + files, cwd=root, capture_output=True)
+            assert r.returncode == 0 and r.stdout == case["stdout"].encode("latin-1"), (case["re"], extra, r.stderr[-200:])
 
     fa = W.fasta_file(3000)
 
