@@ -24,6 +24,16 @@ on the committed MatchAll offset fixtures (tests/golden/matchall_offsets.json),
 on the lowered-IR dumps (tests/golden/ir_dumps.json) and — when _ref is
 present — on randomized differential runs.
 
+Where the reference itself is wrong in that configuration the oracle states what
+it does: B19 (a match lost after an abutting match of a re-entrant pattern) is
+reproduced, because it is a property of the matching semantics; B18 (use after
+free in the parser for literal{m}) and B20 (literal nodes longer than 16 bytes
+compared on the last repeated compare's flags only) are NOT: the oracle expands
+and compares literals exactly, and B20 is restated behind a switch
+(Oracle(long_literal_defect=True), nfa_sim.c mc_equal) only so that
+tests/test_oracle.py can show that this compare is the whole difference.
+DESIGN.md section 2 has the evidence.
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 `--impl reference` legs may import this module.
 """
