@@ -168,6 +168,33 @@ def test_hostsim_fuzz_vs_oracle(hostsim):
     assert checked > 1500
 
 
+def test_baseline_config_0_plumbing(hostsim):
+    """BASELINE.json configs[0]: literal 'regexp' MatchAll over 1 MiB of random ASCII in ['0','z') on the CPU
+    (SURVEY.md §8d C1), without hits and with the literal planted every ~5000 bytes: the reference in its default
+    AND its parity configuration (when oracle/_ref is here), the oracle and the product's host tables agree."""
+    from rejit_b200 import workloads as W
+    ref = None
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "librejit_ref.so")):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from make_golden import Ref
+        ref = Ref()
+    plain = W.random_ascii(1 << 20, seed=1)
+    for text in (plain.tobytes(), W.plant(plain, [b"regexp"], every=5000).tobytes()):
+        exp = O.Oracle(W.LITERAL_PATTERN).match_all(text)
+        want, at = [], text.find(b"regexp")
+        while at >= 0:
+            want.append((at, at + 6))
+            at = text.find(b"regexp", at + 6)
+        assert exp == want
+        got, desc = hostsim.match_all(W.LITERAL_PATTERN, text)
+        assert got == exp and desc.startswith("literal scan, 6 bytes"), desc
+        if ref is not None:
+            for flagset in (0, 2):
+                ref.flags(flagset)
+                assert ref.match_all(b"regexp", text) == [list(m) for m in exp], flagset
+    assert len(exp) > 150
+
+
 def test_hostsim_rich_dialect(hostsim):
     """The rest of the dialect (ranges, escapes, \\xHH, high bytes; tests/fuzzgen.py): the product's parser accepts
     exactly what the oracle's accepts, and its tables match like the oracle."""
