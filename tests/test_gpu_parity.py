@@ -447,3 +447,21 @@ def test_rich_dialect(rj):
             assert g.match_all(t) == o.match_all(t), (pat, t, g.describe())
             checked += 1
     assert checked > 300
+
+
+def test_full_size_config_3_slab(rj):
+    """BASELINE configs[3]: the jrep-style literal spanning a line break over ONE GPU's slab of the 5 GB source
+    blob (625 MB; a 62.5 MB blob tiled, the generator is a Python loop).  The literal cannot overlap itself, so
+    every occurrence is a match: offsets from three shifted byte compares."""
+    from rejit_b200 import workloads as W
+    text = np.tile(W.source_blob(62_500_000, seed=4), 10)
+    hit = (text[:-2] == ord(";")) & (text[1:-1] == 10) & (text[2:] == ord("}"))
+    begins = np.flatnonzero(hit).astype(np.uint64)
+    del hit
+    assert begins.shape[0] > 500_000
+    got = rj.Regej(W.JREP_PATTERN).match_all_array(text)
+    assert got.shape == (begins.shape[0], 2)
+    assert (got[:, 0] == begins).all() and (got[:, 1] == begins + 3).all()
+    if rj.device_count() > 1:
+        again = rj.Regej(W.JREP_PATTERN).match_all_array(text, n_gpus=rj.device_count())
+        assert again.shape == got.shape and (again == got).all()
