@@ -3,15 +3,19 @@
 // offset table beside it) and every batch costs one upload and one pass for the
 // pattern plus one for the line index "^", instead of two MatchAll calls per
 // file.  The walk plans a batch from the sizes it already has, N threads fill it
-// (-j N), and a matcher thread uploads, scans and prints it while the next batch
-// is being planned and filled.  Output, options and exit codes follow the reference's jrep
+// (-j N), and a matcher thread per device (--gpus) uploads, scans and formats it
+// while the next batches are being planned and filled; output is written in
+// batch order.  Output, options and exit codes follow the reference's jrep
 // (/root/reference/sample/jrep.cc: options :84-126, per-file printing :261-405,
 // path handling :518-545), which this file restates and does not copy.
 //
 // Compiles against include/rejit.h of this repository (REJIT_B200 defined: pinned
-// staging, one rejit::Text upload per batch, --gpus) and, unchanged, against the
-// reference's header and library (host-pointer MatchAll calls); tests/test_jrep.py
-// uses the second build, and the reference's own jrep, as the checkers of the first.
+// staging, one rejit::Text upload per batch, one device per matcher) and,
+// unchanged, against the reference's header and library (host-pointer MatchAll
+// calls).  tests/test_samples.py checks both builds: the second against the
+// reference's own jrep and golden output, the first against the same golden
+// output on a test double of the library (CPU tier) and on librejit_b200.so
+// (GPU tier).
 //
 // Exactness of batching.  Files are independent texts in the reference.  In the
 // blob they are separated by one '\n', which gives every file the same line
