@@ -15,6 +15,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_INCLUDE = "/root/reference/include"
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+RUN_TIMEOUT = 600          # seconds for one run of a sample: a hang must fail the test, not stall the tier
 
 
 def _build(tmp_path, name="regexdna"):
@@ -34,7 +35,7 @@ def test_sample_compiles_against_rejit_h_and_needs_a_gpu(tmp_path, name):
     import rejit_b200
     if rejit_b200.device_count() > 0:
         pytest.skip("a GPU is present: covered by the gpu tier")
-    r = subprocess.run([exe], input=b">ONE x\nacgt\n", capture_output=True)
+    r = subprocess.run([exe], input=b">ONE x\nacgt\n", capture_output=True, timeout=RUN_TIMEOUT)
     assert r.returncode != 0 and b"no CUDA device" in r.stderr        # loud, not a silent CPU path
 
 
@@ -47,7 +48,7 @@ def test_sample_regexdna_output(tmp_path, name):
     from rejit_b200 import workloads as W
     exe = _build(tmp_path, name)
     fa = W.fasta_file(20000)
-    r = subprocess.run([exe], input=fa, capture_output=True, check=True)
+    r = subprocess.run([exe], input=fa, capture_output=True, check=True, timeout=RUN_TIMEOUT)
 
     def replace(pat, text, w):
         out, at = bytearray(), 0
@@ -79,7 +80,7 @@ def _check_jrep_against_golden(exe, root, paths):
             # staging: the build's default (threads on librejit_b200, none on the reference), none, three threads
             jobs = {"5000": ["-j0"], "30000": ["-j3"]}.get(batch, [])
             r = subprocess.run([exe] + case["options"] + jobs + ["--batch-bytes=" + batch, case["re"]] + files, cwd=root,
-                               capture_output=True)
+                               capture_output=True, timeout=RUN_TIMEOUT)
             assert r.returncode == 0, (case["re"], case["options"], batch, r.stderr[-300:])
             got = r.stdout
             if "-c" in case["options"]:
@@ -90,13 +91,13 @@ def _check_jrep_against_golden(exe, root, paths):
 
 def test_jrep_compiles_against_rejit_h_and_needs_a_gpu(tmp_path):
     exe = _build(tmp_path, "jrep")
-    r = subprocess.run([exe], capture_output=True)
+    r = subprocess.run([exe], capture_output=True, timeout=RUN_TIMEOUT)
     assert r.returncode == 64 and b"Usage" in r.stderr
     import rejit_b200
     if rejit_b200.device_count() > 0:
         pytest.skip("a GPU is present: covered by the gpu tier")
     (tmp_path / "a.c").write_bytes(b"int x;\n}\n")
-    r = subprocess.run([exe, "x", str(tmp_path / "a.c")], capture_output=True)
+    r = subprocess.run([exe, "x", str(tmp_path / "a.c")], capture_output=True, timeout=RUN_TIMEOUT)
     assert r.returncode != 0 and b"no CUDA device" in r.stderr and r.stdout == b""
 
 
@@ -119,11 +120,11 @@ def test_jrep_front_end_on_the_reference_library(tmp_path):
     noff = dict(os.environ, REJIT_REF_FLAGSET="2")        # both programs in the parity configuration (oracle/ref_shim.cc)
     for pat in (";\n}", "x*", "\n", "a.*b", "(;|\n)+}", "$"):      # incl. empty matches, matches that swallow separators
         for opts in (["-n"], ["-H", "-n", "-A2", "-B1"], ["-H", "-C1"]):
-            a = subprocess.run([ref] + opts + ["-r", pat, "."], cwd=root, capture_output=True, env=noff)
+            a = subprocess.run([ref] + opts + ["-r", pat, "."], cwd=root, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
             assert a.returncode == 0 and a.stdout
             for batch in jrep_tree.BATCHES:
                 b = subprocess.run([exe] + opts + ["-r", "--batch-bytes=" + batch, pat, "."], cwd=root, capture_output=True,
-                                   env=noff)
+                                   env=noff, timeout=RUN_TIMEOUT)
                 assert (a.returncode, a.stdout) == (b.returncode, b.stdout), (pat, opts, batch)
     # found by fuzzing batch against per-file mode: "aa\\n" swallows the separator after 'bbaaa' and ends at the
     # first byte of the next file, whose empty match at that offset used to be lost
@@ -134,21 +135,21 @@ def test_jrep_front_end_on_the_reference_library(tmp_path):
             f.write(body)
     names = sorted(os.listdir(meet))
     for pat in ("aa\\n*", "(aa\n)*", "a*\n*"):
-        a = subprocess.run([ref, "-n", pat] + names, cwd=meet, capture_output=True, env=noff)
+        a = subprocess.run([ref, "-n", pat] + names, cwd=meet, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
         for batch in jrep_tree.BATCHES:
-            b = subprocess.run([exe, "-n", "--batch-bytes=" + batch, pat] + names, cwd=meet, capture_output=True, env=noff)
+            b = subprocess.run([exe, "-n", "--batch-bytes=" + batch, pat] + names, cwd=meet, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
             assert a.returncode == 0 and (a.returncode, a.stdout) == (b.returncode, b.stdout), (pat, batch)
     # --gpus N on this build = N matcher threads calling the shared compiled Regej (as the reference's jrep does)
     for extra in (["--gpus=3", "--batch-bytes=7000", "-j2"], ["--gpus=2", "-j4", "--batch-bytes=0"]):
-        a = subprocess.run([ref, "-H", "-n", "-B1", "-r", "ab", "."], cwd=root, capture_output=True, env=noff)
-        b = subprocess.run([exe, "-H", "-n", "-B1", "-r", *extra, "ab", "."], cwd=root, capture_output=True, env=noff)
+        a = subprocess.run([ref, "-H", "-n", "-B1", "-r", "ab", "."], cwd=root, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
+        b = subprocess.run([exe, "-H", "-n", "-B1", "-r", *extra, "ab", "."], cwd=root, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
         assert a.stdout and (a.returncode, a.stdout) == (b.returncode, b.stdout), extra
     # -j N: N threads stage the batch; same bytes whatever N and the batch size
-    a = subprocess.run([ref, "-H", "-n", "-A1", "-r", ";\n}", "."], cwd=root, capture_output=True, env=noff)
+    a = subprocess.run([ref, "-H", "-n", "-A1", "-r", ";\n}", "."], cwd=root, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
     for jobs in ("-j1", "-j4", "-j16"):
         for batch in jrep_tree.BATCHES:
             b = subprocess.run([exe, jobs, "-H", "-n", "-A1", "-r", "--batch-bytes=" + batch, ";\n}", "."], cwd=root,
-                               capture_output=True, env=noff)
+                               capture_output=True, env=noff, timeout=RUN_TIMEOUT)
             assert a.stdout and (a.returncode, a.stdout) == (b.returncode, b.stdout), (jobs, batch)
     # a file that cannot be opened ends the run with its errno; what came before it is printed, what follows is not
     # (sample/jrep.cc:269-274, 540-541).  Root opens anything, except a write-only sysfs attribute.
@@ -156,14 +157,14 @@ def test_jrep_front_end_on_the_reference_library(tmp_path):
               if (os.stat(os.path.join(d, f)).st_mode & 0o777) == 0o200][:1] if os.path.isdir("/sys/class") else []
     if locked:
         names3 = [names[0], locked[0], names[1]]
-        a = subprocess.run([ref, "-H", "a", *names3], cwd=meet, capture_output=True, env=noff)
+        a = subprocess.run([ref, "-H", "a", *names3], cwd=meet, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
         assert a.returncode == 13 and a.stdout
         for extra in ([], ["-j3"], ["-j3", "--batch-bytes=0"], ["--batch-bytes=0"]):
-            b = subprocess.run([exe, "-H", *extra, "a", *names3], cwd=meet, capture_output=True, env=noff)
+            b = subprocess.run([exe, "-H", *extra, "a", *names3], cwd=meet, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
             assert (a.returncode, a.stdout) == (b.returncode, b.stdout), extra
     for args in (["x", "missing.c"], ["x", "."], ["x", "d0"]):       # stat failure (exit 255), directory without -r
-        a = subprocess.run([ref] + args, cwd=root, capture_output=True)
-        b = subprocess.run([exe] + args, cwd=root, capture_output=True)
+        a = subprocess.run([ref] + args, cwd=root, capture_output=True, timeout=RUN_TIMEOUT)
+        b = subprocess.run([exe] + args, cwd=root, capture_output=True, timeout=RUN_TIMEOUT)
         assert (a.returncode, a.stdout, a.stderr) == (b.returncode, b.stdout, b.stderr), args
 
 
@@ -205,14 +206,14 @@ def test_bench_engine_speaks_the_reference_harness_format(tmp_path):
     ref = os.path.join(REF_DIR, "bench_ref")
     for extra in ([], ["--run_worst_case=0"]):
         args = ["regexp", "--iterations=3", "--low_char=0", "--high_char=z", "--size=8,4096,1048576"] + extra
-        a = subprocess.run([ref] + args, capture_output=True, check=True).stdout
-        b = subprocess.run([exe] + args, capture_output=True, check=True).stdout
+        a = subprocess.run([ref] + args, capture_output=True, check=True, timeout=RUN_TIMEOUT).stdout
+        b = subprocess.run([exe] + args, capture_output=True, check=True, timeout=RUN_TIMEOUT).stdout
         assert a.split(b"\n")[0] == b.split(b"\n")[0]
         (la, ra), (lb, rb) = _table(a), _table(b)
         assert la == lb and sorted(ra) == sorted(rb) == [8, 4096, 1048576]
         assert [len(x) for x in a.split(b"\n")] == [len(x) for x in b.split(b"\n")]
         assert all(v > 0 for row in rb.values() for v in row.values())
-    r = subprocess.run([exe, ""], capture_output=True)
+    r = subprocess.run([exe, ""], capture_output=True, timeout=RUN_TIMEOUT)
     assert r.returncode == 1 and b"Cannot test an empty regular expression." in r.stdout
 
 
@@ -221,7 +222,7 @@ def test_sample_bench_engine_runs(tmp_path):
     exe = _build(tmp_path, "bench_engine")
     for extra in ([], ["--resident=1"]):
         r = subprocess.run([exe, "regexp", "--iterations=5", "--low_char=0", "--high_char=z", "--size=4096,4194304"] + extra,
-                           capture_output=True, check=True)
+                           capture_output=True, check=True, timeout=RUN_TIMEOUT)
         labels, rows = _table(r.stdout)
         assert labels == ["text_size", "worse", "amortised", "best"] and sorted(rows) == [4096, 4194304]
         assert all(v > 0 for row in rows.values() for v in row.values())
@@ -282,7 +283,7 @@ def test_samples_end_to_end_on_the_host_tables(rejit_double, tmp_path):
     for case in _jrep_cases()[:4]:
         files = [p for p in paths if p.startswith(case.get("only", ""))]
         for extra in (["--gpus=2"], ["--gpus=3", "--batch-bytes=7000"], ["--gpus=2", "--shard"], ["--gpus=4", "--batch-bytes=0"]):
-            r = subprocess.run([jrep] + case["options"] + extra + [case["re"]] + files, cwd=root, capture_output=True)
+            r = subprocess.run([jrep] + case["options"] + extra + [case["re"]] + files, cwd=root, capture_output=True, timeout=RUN_TIMEOUT)
             assert r.returncode == 0 and r.stdout == case["stdout"].encode("latin-1"), (case["re"], extra, r.stderr[-200:])
 
     fa = W.fasta_file(3000)
@@ -301,8 +302,8 @@ def test_samples_end_to_end_on_the_host_tables(rejit_double, tmp_path):
     expected = "\n".join("%s %d" % (p, len(O.Oracle(p).match_all(seq))) for p in W.DNA_PATTERNS) + \
         "\n\n%d\n%d\n%d\n" % (len(fa), len(seq), len(cur))
     for name in ("regexdna", "regexdna_device"):
-        r = subprocess.run([_build_on_double(tmp_path, rejit_double, name)], input=fa, capture_output=True, check=True)
+        r = subprocess.run([_build_on_double(tmp_path, rejit_double, name)], input=fa, capture_output=True, check=True, timeout=RUN_TIMEOUT)
         assert r.stdout.decode() == expected, name
 
-    r = subprocess.run([_build_on_double(tmp_path, rejit_double, "threads"), "4", "2"], capture_output=True)
+    r = subprocess.run([_build_on_double(tmp_path, rejit_double, "threads"), "4", "2"], capture_output=True, timeout=RUN_TIMEOUT)
     assert r.returncode == 0 and r.stdout.startswith(b"ok "), r.stdout[-200:]
