@@ -13,7 +13,8 @@ import fuzzgen
 import rejit_oracle as O
 from conftest import expand_table_row
 
-pytestmark = pytest.mark.gpu
+# a hung kernel must end the run, not stall the box: pytest-timeout's thread method exits the process
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1200, method="thread")]
 
 
 @pytest.fixture(scope="module")
