@@ -153,8 +153,14 @@ def test_jrep_front_end_on_the_reference_library(tmp_path):
             assert a.stdout and (a.returncode, a.stdout) == (b.returncode, b.stdout), (jobs, batch)
     # a file that cannot be opened ends the run with its errno; what came before it is printed, what follows is not
     # (sample/jrep.cc:269-274, 540-541).  Root opens anything, except a write-only sysfs attribute.
-    locked = [os.path.join(d, f) for d, _, fs in os.walk("/sys/class") for f in fs
-              if (os.stat(os.path.join(d, f)).st_mode & 0o777) == 0o200][:1] if os.path.isdir("/sys/class") else []
+    locked = []
+    for d, _, fs in os.walk("/sys/class") if os.path.isdir("/sys/class") else []:
+        for f in fs:
+            try:
+                if not locked and (os.stat(os.path.join(d, f)).st_mode & 0o777) == 0o200:
+                    locked.append(os.path.join(d, f))
+            except OSError:
+                pass
     if locked:
         names3 = [names[0], locked[0], names[1]]
         a = subprocess.run([ref, "-H", "a", *names3], cwd=meet, capture_output=True, env=noff, timeout=RUN_TIMEOUT)
