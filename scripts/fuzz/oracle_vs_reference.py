@@ -1,0 +1,32 @@
+"""scripts/fuzz/oracle_vs_reference.py — long-running differential run (scratch tooling behind the totals in DESIGN.md section 2;
+the committed tests run seeded, bounded versions of the same comparisons).  Usage: python scripts/fuzz/oracle_vs_reference.py <seed> <seconds>.
+Needs the build container (/root/reference, oracle/_ref) where it talks to the compiled reference."""
+import os as _os
+ROOT = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+TMP = _os.environ.get("REJIT_FUZZ_TMP", "/tmp/rejit_fuzz")
+_os.makedirs(TMP, exist_ok=True)
+import sys, os, random, time, subprocess
+sys.path[:0] = [ROOT, ROOT + "/oracle", ROOT + "/tests", ROOT + "/tests/golden"]
+import fuzzgen, rejit_oracle as O
+from make_golden import Ref
+import test_oracle as T
+ref = Ref(); ref.flags(2)
+seed = int(sys.argv[1]); budget = float(sys.argv[2]); t0 = time.time(); checked = fails = 0
+while time.time() - t0 < budget:
+    r = random.Random(seed); seed += 1
+    for _ in range(100):
+        pat, alpha = fuzzgen.rand_pattern(r)
+        try: o = O.Oracle(pat)
+        except O.ParserError: continue
+        pb = pat.encode("latin-1")
+        if T._has_reference_ub(pat) or not ref.parse_ok(pb): continue
+        for _ in range(3):
+            t = fuzzgen.rand_text(r, alpha, r.choice([r.randint(0, 48), r.randint(100, 600)]))
+            got = [list(m) for m in o.match_all(t)]
+            exp = ref.match_all(pb, t)
+            checked += 1
+            if got != exp:
+                fresh = subprocess.run([sys.executable, "-c", T._FRESH, T.REF_SO, pb.hex(), t.hex()], capture_output=True, text=True).stdout.strip()
+                if str(got) != fresh:
+                    fails += 1; print("DIFF", repr(pat), repr(t[:120]), len(t), flush=True)
+print("checked", checked, "fails", fails, flush=True)
