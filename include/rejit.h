@@ -64,6 +64,10 @@ class Text {
   size_t size() const { return size_; }
   // Every match of `re` replaced by `with`; the caller owns the result.
   Text* ReplaceAll(Regej& re, const string& with, size_t* n_matches = NULL) const;
+  // ReplaceAll(*patterns[0], withs[0]), then ReplaceAll(*patterns[1], withs[1]), ... — the same text as chaining
+  // the calls; patterns that each match one byte (regex-dna's IUB codes) are applied in ONE pass over the text.
+  Text* ReplaceAllSet(const std::vector<Regej*>& patterns, const std::vector<string>& withs,
+                      std::vector<size_t>* n_matches = NULL) const;
   string Download() const;
 
  private:

@@ -100,6 +100,15 @@ rejit_b200_program* rejit_b200_compile(const rejit_b200_ir* ir, char* err, size_
 void rejit_b200_program_free(rejit_b200_program* program);
 /* One-line description of the chosen scan strategy.                            */
 const char* rejit_b200_program_describe(const rejit_b200_program* program);
+/* 1 when the pattern's text may be cut into slabs (the *_slab entry points, a
+ * non-trivial carry_in, MatchAllParallel on several devices), 0 when it is
+ * "re-entrant": a running thread can re-enter the pattern's start (e.g.
+ * `.{,4}t`), which makes the reference drop a match that begins where the
+ * previous one ended; reproducing that needs the thread labels of the whole
+ * run, which a (cur, tail) carry cannot resume.  The slab entry points return
+ * an error for such a pattern; rejit_b200_match_all_multi_gpu matches it on
+ * one device and sets stats->large_path |= 2 to say so.                        */
+int rejit_b200_program_is_shardable(const rejit_b200_program* program);
 
 /* ---- the compiled matchers: replace the four JIT'd functions -------------- */
 /* Host text in, results out.  MatchAll writes up to `capacity` (begin,end)
@@ -135,7 +144,13 @@ int rejit_b200_copy_from_device(int device, void* dst, const void* src, size_t b
 void rejit_b200_flush_l2(int device);
 /* d_text: device pointer (16-byte aligned) to text_length bytes; d_out_pairs:
  * device buffer for `capacity` pairs (may be NULL with capacity 0 to count).
- * carry_in / carry_out may be NULL (whole text in one call).                   */
+ * carry_in / carry_out may be NULL (whole text in one call).
+ * PADDING: the kernels read whole 16-byte groups, and the 16 bytes after the
+ * group that holds the last text byte: the allocation behind d_text must be
+ * readable up to ((text_length + 15) & ~15) + 16 bytes (their contents do not
+ * matter).  rejit_b200_device_alloc and rejit_b200_text_upload add 64 bytes of
+ * slack; a foreign pointer that ends at an allocation boundary must be padded
+ * by the caller.  This holds for every entry point that takes a device text.   */
 int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, const void* d_text,
                                     size_t text_length, uint64_t* d_out_pairs, size_t capacity,
                                     const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
@@ -165,6 +180,18 @@ int64_t rejit_b200_replace_all(rejit_b200_program* program, const char* text, si
 rejit_b200_text* rejit_b200_replace_all_text(rejit_b200_program* program, const rejit_b200_text* text,
                                              const char* with, size_t with_length, int64_t* n_matches,
                                              rejit_b200_stats* stats, char* err, size_t err_length);
+/* `count` ReplaceAll calls applied one after the other — programs[0] with
+ * withs[0] first — as the eleven IUB substitutions of regex-dna are
+ * (sample/regexdna.cc:69-85).  When every pattern matches exactly one byte and
+ * no replacement holds a byte that a LATER pattern matches, the calls collapse
+ * into one byte -> string table: one counting pass, one prefix sum, one writing
+ * pass over the text instead of `count` scan + rebuild passes; any other set is
+ * simply run call by call.  The result is identical either way.
+ * n_matches[i] (may be NULL) = matches replaced by programs[i].                 */
+rejit_b200_text* rejit_b200_replace_all_set_text(rejit_b200_program* const* programs, int count,
+                                                 const rejit_b200_text* text, const char* const* withs,
+                                                 const size_t* with_lengths, int64_t* n_matches,
+                                                 rejit_b200_stats* stats, char* err, size_t err_length);
 size_t rejit_b200_text_length(const rejit_b200_text* text);
 int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capacity, char* err, size_t err_length);
 

@@ -43,7 +43,7 @@ class Carry(ctypes.Structure):
 # every symbol include/rejit_b200.h declares
 EXPORTED = [
     "rejit_b200_parse", "rejit_b200_ir_free", "rejit_b200_ir_dump", "rejit_b200_compile",
-    "rejit_b200_program_free", "rejit_b200_program_describe", "rejit_b200_match_all",
+    "rejit_b200_program_free", "rejit_b200_program_describe", "rejit_b200_program_is_shardable", "rejit_b200_match_all",
     "rejit_b200_match_all_alloc", "rejit_b200_match_first", "rejit_b200_match_full",
     "rejit_b200_match_anywhere", "rejit_b200_match_all_multi_gpu", "rejit_b200_device_count",
     "rejit_b200_device_alloc", "rejit_b200_device_free", "rejit_b200_pinned_alloc",
@@ -52,7 +52,7 @@ EXPORTED = [
     "rejit_b200_text_upload", "rejit_b200_text_free", "rejit_b200_match_all_text",
     "rejit_b200_set_create", "rejit_b200_set_free", "rejit_b200_set_describe", "rejit_b200_set_kmer_tables",
     "rejit_b200_match_all_set_text", "rejit_b200_match_all_set_device", "rejit_b200_match_all_set_device_slab",
-    "rejit_b200_replace_all", "rejit_b200_replace_all_text", "rejit_b200_text_length", "rejit_b200_text_download",
+    "rejit_b200_replace_all", "rejit_b200_replace_all_text", "rejit_b200_replace_all_set_text", "rejit_b200_text_length", "rejit_b200_text_download",
 ]
 
 
@@ -77,6 +77,8 @@ def lib():
     L.rejit_b200_program_free.argtypes = [vp]
     L.rejit_b200_program_describe.argtypes = [vp]
     L.rejit_b200_program_describe.restype = cp
+    L.rejit_b200_program_is_shardable.argtypes = [vp]
+    L.rejit_b200_program_is_shardable.restype = ctypes.c_int
     L.rejit_b200_match_all.argtypes = [vp, cp, sz, u64p, sz, cp, sz]
     L.rejit_b200_match_all.restype = ctypes.c_int64
     L.rejit_b200_match_all_alloc.argtypes = [vp, vp, sz, ctypes.POINTER(u64p), ctypes.POINTER(Stats), cp, sz]
@@ -130,6 +132,9 @@ def lib():
     L.rejit_b200_replace_all_text.argtypes = [vp, vp, vp, sz, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(Stats),
                                               cp, sz]
     L.rejit_b200_replace_all_text.restype = vp
+    L.rejit_b200_replace_all_set_text.argtypes = [ctypes.POINTER(vp), ctypes.c_int, vp, ctypes.POINTER(cp), ctypes.POINTER(sz),
+                                                  ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(Stats), cp, sz]
+    L.rejit_b200_replace_all_set_text.restype = vp
     L.rejit_b200_text_length.argtypes = [vp]
     L.rejit_b200_text_length.restype = sz
     L.rejit_b200_text_download.argtypes = [vp, vp, sz, cp, sz]
@@ -260,6 +265,10 @@ class Regej:
     def describe(self) -> str:
         self.compile()
         return lib().rejit_b200_program_describe(self._prog).decode("latin-1")
+
+    def shardable(self) -> bool:
+        """False for re-entrant patterns: the slab entry points refuse them (rejit_b200_program_is_shardable)."""
+        return bool(self.compile() and lib().rejit_b200_program_is_shardable(self._prog))
 
     def ir_dump(self) -> str:
         n = lib().rejit_b200_ir_dump(self._ir, None, 0)
@@ -524,6 +533,27 @@ class RegejSet:
             return out
         finally:
             L.rejit_b200_text_free(h)
+
+
+def replace_all_set_text(patterns, text: "Text", withs, stats: Optional[Stats] = None):
+    """ReplaceAll(patterns[0], withs[0]), then patterns[1], ... on an uploaded Text, as ONE pass when every pattern
+    matches exactly one byte (rejit_b200_replace_all_set_text).  Returns (new Text, [matches per pattern])."""
+    regs = [p if isinstance(p, Regej) else Regej(p) for p in patterns]
+    for r in regs:
+        if not r.compile():
+            raise ParserError(r.status_string)
+    k = len(regs)
+    progs = (ctypes.c_void_p * k)(*[r._prog for r in regs])
+    ws = [_as_bytes(w) for w in withs]
+    warr = (ctypes.c_char_p * k)(*ws)
+    lens = (ctypes.c_size_t * k)(*[len(w) for w in ws])
+    counts = (ctypes.c_int64 * k)()
+    err = ctypes.create_string_buffer(512)
+    h = lib().rejit_b200_replace_all_set_text(progs, k, text._h, warr, lens, counts,
+                                              ctypes.byref(stats) if stats is not None else None, err, len(err))
+    if not h:
+        raise RejitError(err.value.decode("latin-1"))
+    return Text(_handle=h), list(counts)
 
 
 def match_all(pattern, text):

@@ -32,6 +32,8 @@
 
 #include "device_program.h"
 #include "kernels.cuh"
+#include "scan_emit.cuh"
+#include "replace.cuh"
 
 namespace rejit_b200 {
 
@@ -48,6 +50,12 @@ bool Check(cudaError_t e, const char* what, std::string* error) {
 #define RJ_TRY(call)                                 \
   do {                                               \
     if (!Check((call), #call, error)) return false;  \
+  } while (0)
+
+// the same for functions that return a count (-1 = failed): `false` would read as "0 matches, success"
+#define RJ_TRY_COUNT(call)                           \
+  do {                                               \
+    if (!Check((call), #call, error)) return -1;     \
   } while (0)
 
 struct Buffer {
@@ -85,7 +93,7 @@ class DeviceContext {
   // ordered stores (slot ranges per sub-region): candidates and needle hits
   Buffer sub_b, sub_e, sub_count, hsub_b, hsub_e, hsub_count;
   // dense (gathered, sorted) lists
-  Buffer dense_b, dense_e, hits_b, hits_e, out_pairs, fin_trace, with_buf;
+  Buffer dense_b, dense_e, hits_b, hits_e, out_pairs, with_buf;
   uint64_t dense_cap = 0, hits_cap = 0;
   // unordered fallback (k_dfa_scan)
   Buffer cand_b, cand_e;
@@ -97,10 +105,13 @@ class DeviceContext {
   Buffer fscratch;                    // label scratch for re-entrant patterns
   // fused pattern sets
   Buffer set_sub_b, set_sub_e, set_sub_count, set_dense_b, set_dense_e, set_reach, set_take, set_fin, set_slot,
-      set_out, set_status, set_counts, kmer_xchg;
+      set_out, set_status, set_counts, kmer_xchg, kmer_stage;
   PipelineStatus* h_set_status = nullptr;      // pinned + mapped, 32 entries
   PipelineStatus* h_set_status_dev = nullptr;
   Buffer flush;
+  Buffer trans_tab, trans_len, trans_off, trans_counts;   // byte -> string table of ReplaceAllSetDevice and its tile sums
+  Buffer em_records;                  // look-back records of the single-pass scans (scan_emit.cuh)
+  bool emit = true;                   // single-pass scan + emit available (RJ_NO_EMIT=1: the round-1 pipelines only)
   PipelineStatus* h_status = nullptr; // pinned + mapped: the resolve kernel writes it, the host spins on seq
   PipelineStatus* h_status_dev = nullptr;   // device view of h_status
   FinRecord* h_fin = nullptr;               // mapped: records of the in-kernel finish (one per pattern)
@@ -119,6 +130,7 @@ class DeviceContext {
     sm_count = prop.multiProcessorCount;
     smem_optin = prop.sharedMemPerBlockOptin;
     coop = prop.cooperativeLaunch != 0 && getenv("RJ_NO_FUSED_FINISH") == nullptr;
+    emit = getenv("RJ_NO_EMIT") == nullptr && getenv("RJ_NO_FUSED_FINISH") == nullptr;
     RJ_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) RJ_TRY(cudaEventCreate(&e));
     RJ_TRY(cudaHostAlloc(&h_status, sizeof(PipelineStatus), cudaHostAllocMapped));
@@ -176,6 +188,8 @@ class DeviceProgram {
   size_t dfa_smem = 0;
   // adaptive capacities (remembered across calls so that steady state never reruns)
   GenFilter gen_filter{};             // start filter of the generic scan
+  EmFilter em_filter{};               // the same for the single-pass scan (SWAR form when the start set is small)
+  bool emit_off = false;              // candidates too dense for the single-pass scan's lists: round-1 pipeline
   uint32_t cand_sub_cap = 16;         // slots per sub-region, candidate store
   uint32_t hit_sub_cap = 16;          // slots per sub-region, needle-hit store
   bool dense_mode = false;            // k_dfa_tma's lane lists overflowed once: use k_dfa_scan
@@ -213,6 +227,31 @@ class DeviceProgram {
         int ctx = ca.nfa.has_anchor ? (sol | (eol << 1)) : 0;
         if (ca.start_ok[ctx][b] || ca.nfa.accept_empty[ctx]) gen_filter.t[sol][b >> 5] |= 1u << (b & 31);
       }
+    {
+      // SWAR form of the start filter: S0 = start bytes that need no context, S1 = start bytes right after a
+      // line break.  Exact when S0 has at most four bytes and S1 adds at most four more, or every byte.
+      EmFilter& f = em_filter;
+      memcpy(f.t, gen_filter.t, sizeof f.t);
+      std::vector<int> s0, extra;
+      bool subset = true;
+      for (int b = 0; b < 256; ++b) {
+        const bool in0 = (f.t[0][b >> 5] >> (b & 31)) & 1u, in1 = (f.t[1][b >> 5] >> (b & 31)) & 1u;
+        if (in0) s0.push_back(b);
+        if (in0 && !in1) subset = false;
+        if (in1 && !in0) extra.push_back(b);
+      }
+      f.use_sol = extra.empty() ? 0u : 1u;
+      f.all1 = (s0.size() + extra.size() == 256) ? 1u : 0u;
+      if (subset && s0.size() <= 4 && (extra.size() <= 4 || f.all1)) {
+        f.swar = 1;
+        f.n0 = (uint32_t)s0.size();
+        for (size_t i = 0; i < s0.size(); ++i) f.b0 |= (uint32_t)s0[i] << (8 * i);
+        if (!f.all1) {
+          f.n1 = (uint32_t)extra.size();
+          for (size_t i = 0; i < extra.size(); ++i) f.b1 |= (uint32_t)extra[i] << (8 * i);
+        }
+      }
+    }
     if (ca.strategy == ScanStrategy::Literal || ca.strategy == ScanStrategy::LiteralWindow) {
       if (!Upload(ca.literal, &needle, error)) return false;
       needle_len = (uint32_t)ca.literal.size();
@@ -429,7 +468,7 @@ PipelineStatus StatusFromRecord(const FinRecord& r, const Carry& carry_in) {
   st.carry_cur = carry_in.cur;
   st.carry_tail = carry_in.tail;
   if (r.n_matches) {
-    const bool last_is_empty = r.last_nonempty != r.last_end;
+    const bool last_is_empty = (r.flags & kFinLastEmpty) != 0 || r.last_nonempty != r.last_end;
     st.carry_cur = last_is_empty ? r.last_end + 1 : r.last_end;
     if (r.last_nonempty) st.carry_tail = r.last_nonempty;
   }
@@ -438,6 +477,23 @@ PipelineStatus StatusFromRecord(const FinRecord& r, const Carry& carry_in) {
   st.need_large = (r.flags & kFinOverlap) ? 1u : 0u;
   st.dense = (r.flags & kFinDense) ? 1u : 0u;
   return st;
+}
+
+// Kernels that use more dynamic shared memory than the default limit (once per device context).
+bool EnsureKernelAttributes(DeviceContext* c, std::string* error) {
+  if (c->attr_done) return true;
+  RJ_TRY(cudaFuncSetAttribute(k_resolve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallResolveMax * 16));
+  RJ_TRY(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  RJ_TRY(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  RJ_TRY(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  RJ_TRY(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmWindow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmGeneric, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_translate_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTransStage + 32 + kTransMaxBytes)));
+  c->attr_done = true;
+  return true;
 }
 
 struct Slab {                 // how a launch maps local offsets to the whole text
@@ -539,14 +595,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     if (error) *error = "rejit_b200: device text must be 16-byte aligned";
     return false;
   }
-  if (!c->attr_done) {
-    RJ_TRY(cudaFuncSetAttribute(k_resolve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallResolveMax * 16));
-    RJ_TRY(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-    RJ_TRY(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    RJ_TRY(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-    RJ_TRY(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-    c->attr_done = true;
-  }
+  if (!EnsureKernelAttributes(c, error)) return false;
   if (c->dense_cap == 0 && !c->ReserveDense(1u << 16, error)) return false;
   const int tma_warps = (ca.strategy == ScanStrategy::DfaFixed) ? DfaTmaWarps(c, dp->dfa) : 0;
   const uint32_t wsize = ca.window_hi - ca.window_lo + 1;
@@ -618,6 +667,48 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       fin.seq = fused_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
       return fin;
     };
+    // ---- single-pass scan + emit (scan_emit.cuh): the text is read once, the matches are written once ----
+    const bool window_fits = ca.strategy != ScanStrategy::LiteralWindow || (uint64_t)ca.window_hi + 64 <= kEmBias;
+    const bool use_emit = c->emit && try_fuse && !dp->emit_off && window_fits &&
+                          (ca.strategy == ScanStrategy::Literal || ca.strategy == ScanStrategy::LiteralWindow ||
+                           ca.strategy == ScanStrategy::Generic);
+    if (use_emit) {
+      EmitArgs em{};
+      const uint64_t first_start = std::min<uint64_t>(slab.own.own_begin, n);
+      uint64_t last_pos = slab.own.own_end ? slab.own.own_end - 1 : 0;            // last owned start
+      if (ca.strategy == ScanStrategy::LiteralWindow) last_pos += (uint64_t)ca.window_hi + 1;   // ... or needle hit
+      last_pos = std::min<uint64_t>(last_pos, n);
+      em.tile0 = first_start / kEmTileBytes;
+      em.ntiles = std::max<uint64_t>(last_pos / kEmTileBytes, em.tile0) - em.tile0 + 1;
+      if (!c->em_records.Reserve(em.ntiles * 32 + 64, error)) return false;
+      uint8_t* base = static_cast<uint8_t*>(c->status.p);
+      em.records = c->em_records.as<uint4>();
+      em.sync = reinterpret_cast<unsigned int*>(base + kFinSyncOffset);
+      em.final_state = reinterpret_cast<unsigned long long*>(base + kFinLastOffset);
+      em.out_pairs = outp;
+      em.out_cap = ocap;
+      em.base_offset = slab.base_offset;
+      em.host_records = c->h_fin_dev;
+      em.seq = fused_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+      em.carry_in = carry_in;
+      EmLit lit{};
+      lit.needle = dp->needle;
+      lit.m = dp->needle_len; lit.p4 = dp->p4; lit.pmask = dp->pmask;
+      lit.win_lo = ca.window_lo; lit.win_hi = ca.window_hi;
+      const int blocks = (int)std::min<uint64_t>(em.ntiles, (uint64_t)c->sm_count * 4);
+      if (ca.strategy == ScanStrategy::Literal) {
+        if (dp->needle_len >= 4)
+          k_scan_emit<kEmLiteral, true><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+        else
+          k_scan_emit<kEmLiteral, false><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+      } else if (ca.strategy == ScanStrategy::LiteralWindow) {
+        k_scan_emit<kEmWindow, true><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+      } else {
+        k_scan_emit<kEmGeneric, true><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+      }
+      fused = true;
+      if (stats) stats->launches += 1;
+    } else
     switch (ca.strategy) {
       case ScanStrategy::Literal: {
         cand.nsub = (n + kLitSubBytes - 1) / kLitSubBytes;
@@ -756,7 +847,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         break;
       }
     }
-    if (stats && ca.strategy != ScanStrategy::LiteralWindow) cudaEventRecord(c->ev[1], s);
+    if (stats && (use_emit || ca.strategy != ScanStrategy::LiteralWindow)) cudaEventRecord(c->ev[1], s);
     PipelineStatus st;
     // spin on the mapped status block; fall back to the stream state if the
     // kernel cannot have run (launch failure, sticky error)
@@ -786,7 +877,13 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       RJ_TRY(cudaGetLastError());
       if (!WaitFinRecords(c, 1, fused_seq, error)) return false;
       st = StatusFromRecord(c->h_fin[0], carry_in);
-      if (ca.strategy == ScanStrategy::LiteralWindow) {
+      if (use_emit) {
+        // the single-pass scan reports through the same record; when a chain crossed a tile edge (need_large) or a
+        // tile was too dense for its lists, the round-1 pipeline runs instead (next attempt)
+        if (st.dense) { dp->emit_off = true; if (stats) stats->reruns += 1; continue; }
+        if (st.need_large) { dp->fuse_misses++; dp->fuse_skips = 0; if (stats) stats->reruns += 1; continue; }
+        dp->fuse_misses = 0;
+      } else if (ca.strategy == ScanStrategy::LiteralWindow) {
         // outcome of the hit stage (k_gather_hits), published the same way in slot 31
         volatile FinRecord* hr = c->h_fin + 31;
         uint64_t spins = 0;
@@ -796,10 +893,10 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         st.n_hits = hr->n_matches;
         if (hr->flags & kFinOverflow) { st.overflow = 1; st.need_cap = std::max(st.need_cap, (unsigned int)hr->need_cap); }
       }
-      if (!st.overflow && !st.dense) {
+      if (!use_emit && !st.overflow && !st.dense) {
         if (st.need_large) { dp->fuse_misses++; dp->fuse_skips = 0; } else { dp->fuse_misses = 0; }
       }
-      if (st.need_large && !st.overflow && !st.dense) {
+      if (!use_emit && st.need_large && !st.overflow && !st.dense) {
         // neighbouring candidates overlap: the general resolve decides
         RJ_TRY(cudaMemsetAsync(d_status, 0, sizeof(PipelineStatus), s));
         if (!resolve_ordered()) return false;
@@ -1033,6 +1130,7 @@ class DeviceSet {
   std::vector<void*> allocs;
   size_t fixed_smem = 0;
   uint32_t sub_cap = 16;
+  uint32_t stage_cap = 64;            // k_set_kmer: staged matches per warp beyond its shared list
   uint64_t per_cap = 1u << 14;        // dense / output capacity per pattern
   bool dense_mode = false;
   ~DeviceSet() { for (void* p : allocs) cudaFree(p); }
@@ -1156,14 +1254,7 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
     if (!Check(cudaSetDevice(c->device), "cudaSetDevice", error)) return -1;
     if ((reinterpret_cast<uintptr_t>(d_text) & 15) != 0) { if (error) *error = "rejit_b200: device text must be 16-byte aligned"; return -1; }
     cudaStream_t s = c->stream;
-    if (!c->attr_done) {
-      if (!Check(cudaFuncSetAttribute(k_resolve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallResolveMax * 16), "attr", error) ||
-          !Check(cudaFuncSetAttribute(k_dfa_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error) ||
-          !Check(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "attr", error) ||
-          !Check(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error) ||
-          !Check(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin), "attr", error)) return -1;
-      c->attr_done = true;
-    }
+    if (!EnsureKernelAttributes(c, error)) return -1;
     // what a finished call hands back (statuses in c->h_set_status, pairs in c->set_out)
     auto deliver = [&](uint64_t per_cap, int strategy) -> int {
       uint64_t total_m = 0, total_c = 0;
@@ -1207,36 +1298,39 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
       const uint64_t last_end = std::min<uint64_t>(n, own.own_end + 8);          // an owned match ends at most here
       const uint64_t row_hi = std::max<uint64_t>(std::min<uint64_t>((last_end + 511) >> 9, (n16 + 511) >> 9), row_lo + 1);
       const uint64_t rows = row_hi - row_lo;
-      const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 31) / 32, std::min<uint64_t>(c->sm_count, kKmerMaxGrid)));
-      const size_t kmer_smem = kKmerSmemFixed + (size_t)kKmerMaxGrid * K * 8;
-      const uint64_t rows_per_cta = (rows + blocks - 1) / blocks;
-      if (rows_per_cta <= kKmerMaxRows && kmer_smem <= c->smem_optin) {
+      // one CTA per SM (cooperative: every CTA waits for the records of the CTAs before it); a warp owns a
+      // contiguous run of rows of any length
+      const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 31) / 32, (uint64_t)c->sm_count));
+      const size_t kmer_smem = kKmerSmemFixed;
+      const uint64_t rows_per_warp = (rows + (uint64_t)blocks * kKmerWarps - 1) / ((uint64_t)blocks * kKmerWarps);
+      const uint64_t rows_per_cta = rows_per_warp * kKmerWarps;
+      if (rows_per_cta < kKmerMaxRowsPerCta && kmer_smem <= c->smem_optin) {
         for (int attempt = 0; attempt < 8; ++attempt) {
           const uint64_t per_cap = ds->per_cap;
           if (!c->set_out.Reserve(K * per_cap * 16, error)) return -1;
           if (!c->kmer_xchg.p) {
-            if (!c->kmer_xchg.Reserve((size_t)c->sm_count * 32 * sizeof(KmerXchg), error) ||
-                !Check(cudaMemsetAsync(c->kmer_xchg.p, 0, (size_t)c->sm_count * 32 * sizeof(KmerXchg), s), "memset", error)) return -1;
+            // exchange records, then the two sync words and the per-member totals (all zero between calls)
+            const size_t bytes = (size_t)c->sm_count * 32 * sizeof(KmerXchg) + 1024;
+            if (!c->kmer_xchg.Reserve(bytes, error) || !Check(cudaMemsetAsync(c->kmer_xchg.p, 0, bytes, s), "memset", error)) return -1;
           }
+          // staging area of the warps whose shared lists overflow: sized for the text's density (grows on demand)
+          if (!c->kmer_stage.Reserve((size_t)blocks * kKmerWarps * ds->stage_cap * sizeof(uint2), error)) return -1;
           KmerRun run{};
           run.row_lo = row_lo;
           run.rows_per_cta = (uint32_t)rows_per_cta;
-          run.rows_per_warp = (uint32_t)((rows_per_cta + 31) / 32);
+          run.rows_per_warp = (uint32_t)rows_per_warp;
           run.xchg = c->kmer_xchg.as<KmerXchg>();
+          uint8_t* tail = c->kmer_xchg.as<uint8_t>() + (size_t)c->sm_count * 32 * sizeof(KmerXchg);
+          run.gsync = reinterpret_cast<unsigned int*>(tail);
+          run.gfinal = reinterpret_cast<unsigned long long*>(tail + 64);
+          run.stage = c->kmer_stage.as<uint2>();
+          run.stage_cap = ds->stage_cap;
           run.out_pairs = c->set_out.as<uint64_t>();
           run.out_stride = per_cap;
           run.out_cap = per_cap;
           run.base_offset = base_offset;
           run.host_records = c->h_fin_dev;
           run.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
-          static const bool want_trace = getenv("RJ_FIN_TRACE") != nullptr;
-          static const int debug_stop = getenv("RJ_KMER_STOP") ? atoi(getenv("RJ_KMER_STOP")) : 0;
-          run.debug_stop = debug_stop;
-          if (want_trace) {
-            if (!c->fin_trace.Reserve((size_t)blocks * 16 * 8 + 64, error)) return -1;
-            cudaMemsetAsync(c->fin_trace.p, 0, (size_t)blocks * 16 * 8 + 64, s);
-            run.trace = c->fin_trace.as<unsigned long long>();
-          }
           CarrySet carries;
           for (int j = 0; j < 32; ++j) carries.c[j] = (carry_in && j < K) ? carry_in[j] : Carry();
           uint64_t n_arg = n;
@@ -1248,72 +1342,25 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           if (!Check(cudaLaunchCooperativeKernel((const void*)k_set_kmer, dim3(blocks), dim3(kKmerThreads), kargs, kmer_smem, s),
                      "cooperative launch", error)) return -1;
           if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
-          if (debug_stop) {                                    // timing only: nothing was reported
-            cudaStreamSynchronize(s);
-            if (stats) { cudaEventRecord(c->ev[2], s); cudaEventSynchronize(c->ev[2]); cudaEventElapsedTime(&stats->scan_ms, c->ev[0], c->ev[1]); stats->total_ms = stats->scan_ms; }
-            for (int j = 0; j < K; ++j) counts[j] = 0;
-            return 0;
-          }
           if (!Check(cudaGetLastError(), "launch", error) || !WaitFinRecords(c, K, run.seq, error)) return -1;
-          bool redo = false, give_up = false, dense = false;
+          bool redo = false, give_up = false, dense = false, grow_stage = false;
           uint64_t need = 0;
           for (int j = 0; j < K; ++j) {
             c->h_set_status[j] = StatusFromRecord(c->h_fin[j], carries.c[j]);
             const PipelineStatus& h = c->h_set_status[j];
-            if (h.overflow || h.dense || h.need_large) give_up = true;
+            if (h.dense || h.need_large) give_up = true;
             if (h.dense) dense = true;
+            if (h.overflow) grow_stage = true;
             if (h.n_matches > per_cap) { need = std::max<uint64_t>(need, h.n_matches); redo = true; }
-          }
-          if (run.trace) {
-            // debugging aid: phase times (ns, relative to the earliest CTA start): min..max over the CTAs
-            std::vector<unsigned long long> tr((size_t)blocks * 16);
-            cudaStreamSynchronize(s);
-            cudaMemcpy(tr.data(), run.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
-            static const char* names[9] = {"start", "tables", "scanned(warp 0)", "checked", "published", "exchanged", "written", "reported",
-                                           "verified(warp 0)"};
-            unsigned long long t0 = ~0ull;
-            for (int b2 = 0; b2 < blocks; ++b2) t0 = std::min(t0, tr[(size_t)b2 * 16]);
-            std::string line = "[kmer trace]";
-            for (int q = 0; q < 9; ++q) {
-              unsigned long long mn = ~0ull, mx = 0;
-              std::vector<std::pair<unsigned long long, int>> dur;      // time since the phase before, per CTA
-              for (int b2 = 0; b2 < blocks; ++b2) {
-                const unsigned long long v = tr[(size_t)b2 * 16 + q];
-                if (!v) continue;
-                mx = std::max(mx, v - t0);
-                mn = std::min(mn, v - t0);
-                const int qp = q == 8 ? 2 : q - 1;          // the stamp this one follows
-                if (q > 0 && tr[(size_t)b2 * 16 + qp]) dur.push_back({v - tr[(size_t)b2 * 16 + qp], b2});
-              }
-              if (!mx) continue;
-              line += " | " + std::string(names[q]) + " " + std::to_string(mn) + ".." + std::to_string(mx);
-              if (!dur.empty()) {
-                std::sort(dur.begin(), dur.end());
-                line += " (+" + std::to_string(dur[dur.size() / 2].first) + " med, +" + std::to_string(dur.back().first) +
-                        " cta" + std::to_string(dur.back().second) + ")";
-              }
-            }
-            fprintf(stderr, "%s (ns)\n", line.c_str());
-            if (const char* which = getenv("RJ_FIN_TRACE_CTA")) {       // raw stamps of some CTAs, e.g. "29,60"
-              for (const char* q = which; *q;) {
-                const int b2 = atoi(q);
-                if (b2 >= 0 && b2 < blocks) {
-                  std::string l2 = "[kmer cta " + std::to_string(b2) + "]";
-                  for (int k2 : {0, 1, 2, 8, 3, 4, 5, 6, 7})
-                    l2 += " " + std::string(names[k2]) + "=" + (tr[(size_t)b2 * 16 + k2] ? std::to_string(tr[(size_t)b2 * 16 + k2] - t0) : std::string("-"));
-                  fprintf(stderr, "%s\n", l2.c_str());
-                }
-                while (*q && *q != ',') ++q;
-                if (*q == ',') ++q;
-              }
-            }
           }
           if (!dense) ds->kmer_dense = 0;
           if (give_up) {                                         // overlapping or too dense: the general path decides
             if (dense && ++ds->kmer_dense >= 2) ds->kmer_off = true;
             break;
           }
-          if (redo) { ds->per_cap = need + need / 4 + 1024; if (stats) stats->reruns += 1; continue; }
+          if (grow_stage) { ds->stage_cap *= 4; redo = true; }
+          if (need) ds->per_cap = need + need / 4 + 1024;
+          if (redo) { if (stats) stats->reruns += 1; continue; }
           return deliver(per_cap, 4);
         }
       }
@@ -1404,12 +1451,6 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         fin.host_records = c->h_fin_dev;
         fin.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
         dense_flag = fin.sync + 4;
-        static const bool want_trace = getenv("RJ_FIN_TRACE") != nullptr;
-        if (want_trace) {
-          if (!c->fin_trace.Reserve((size_t)blocks * 8 * 8 + 8 * 8, error)) return -1;
-          cudaMemsetAsync(c->fin_trace.p, 0, (size_t)blocks * 8 * 8 + 64, s);
-          fin.trace = c->fin_trace.as<unsigned long long>();
-        }
         uint64_t n_arg = n, nsub_arg = nsub;
         void* args[] = {(void*)&d_text, (void*)&n_arg, (void*)&ds->tb, (void*)&own, (void*)&st, (void*)&nsub_arg,
                         (void*)&dense_flag, (void*)&work, (void*)&fin, (void*)&carries};
@@ -1418,45 +1459,6 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
         if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
         if (!Check(cudaGetLastError(), "launch", error) || !WaitFinRecords(c, K, fin.seq, error)) return -1;
         for (int j = 0; j < K; ++j) c->h_set_status[j] = StatusFromRecord(c->h_fin[j], carries.c[j]);
-        if (fin.trace) {
-          // debugging aid: phase times of the in-kernel finish (ns, relative to the earliest scan end)
-          std::vector<unsigned long long> tr((size_t)blocks * 8);
-          cudaStreamSynchronize(s);
-          cudaMemcpy(tr.data(), fin.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
-          unsigned long long t0 = ~0ull, mx[5] = {0, 0, 0, 0, 0}, mn[5] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull};
-          for (int b2 = 0; b2 < blocks; ++b2) t0 = std::min(t0, tr[(size_t)b2 * 8]);
-          for (int b2 = 0; b2 < blocks; ++b2)
-            for (int q = 0; q < 5; ++q) {
-              unsigned long long v = tr[(size_t)b2 * 8 + q];
-              if (!v) continue;
-              mx[q] = std::max(mx[q], v - t0);
-              mn[q] = std::min(mn[q], v - t0);
-            }
-          fprintf(stderr, "[fin trace] scan_end %llu..%llu  barrier_out %llu..%llu  copied %llu..%llu  last_in %llu  published %llu (ns)\n",
-                  mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mx[3], mx[4]);
-          // the slowest copies
-          std::vector<std::pair<unsigned long long, int>> slow;
-          for (int b2 = 0; b2 < blocks; ++b2) slow.push_back({tr[(size_t)b2 * 8 + 2] - tr[(size_t)b2 * 8 + 1], b2});
-          std::sort(slow.begin(), slow.end());
-          fprintf(stderr, "[fin trace] copy time ns: median %llu; slowest:", slow[slow.size() / 2].first);
-          for (size_t q = 0; q < 6 && q < slow.size(); ++q)
-            fprintf(stderr, " cta%d=%llu", slow[slow.size() - 1 - q].second, slow[slow.size() - 1 - q].first);
-          fprintf(stderr, "\n");
-          {
-            // medians of the three passes
-            std::vector<unsigned long long> p1, p2, p3;
-            for (int b2 = 0; b2 < blocks; ++b2) {
-              const unsigned long long* r = &tr[(size_t)b2 * 8];
-              if (!r[5] || !r[6]) continue;
-              p1.push_back(r[5] - r[1]); p2.push_back(r[6] - r[5]); p3.push_back(r[7] - r[6]);
-            }
-            if (!p1.empty()) {
-              std::sort(p1.begin(), p1.end()); std::sort(p2.begin(), p2.end()); std::sort(p3.begin(), p3.end());
-              fprintf(stderr, "[fin trace] pass medians ns: %llu %llu %llu  (max %llu %llu %llu)\n", p1[p1.size() / 2],
-                      p2[p2.size() / 2], p3[p3.size() / 2], p1.back(), p2.back(), p3.back());
-            }
-          }
-        }
         bool overlap = false, clean = true;
         for (int j = 0; j < K; ++j) {
           const PipelineStatus& h = c->h_set_status[j];
@@ -1503,8 +1505,9 @@ int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int
   if (!CudaOk(error)) return -1;
   int g = std::max(1, std::min(n_gpus, DeviceCount()));
   if (n < (uint64_t)g * 4096) g = 1;
-  // the label replay of re-entrant patterns cannot be cut at a slab edge
-  if (prog->automaton().reentrant) g = 1;
+  // the label replay of re-entrant patterns cannot be cut at a slab edge: one device, and the caller is told
+  // (stats->large_path bit 1; rejit_b200_program_is_shardable answers the same question beforehand)
+  if (prog->automaton().reentrant && g > 1) { g = 1; if (stats) stats->large_path |= 2; }
   std::vector<std::vector<uint64_t>> part(g);
   std::vector<Carry> carry_out(g);
   std::vector<std::string> errs(g);
@@ -1567,6 +1570,8 @@ int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int
 int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_t n, const uint8_t* with,
                          uint64_t with_len, void** d_out, uint64_t* out_len, uint64_t* out_capacity,
                          RunStats* stats, std::string* error) {
+  if (d_out) *d_out = nullptr;
+  if (out_len) *out_len = 0;
   DeviceContext* c = ContextFor(device, error);
   if (!c) return -1;
   DeviceProgram* dp = prog->OnDevice(device, error);
@@ -1589,11 +1594,11 @@ int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint6
     if (!c->cub_tmp.Reserve(tmp, error)) return -1;
     int blocks = (int)std::min<uint64_t>((m + 255) / 256, (uint64_t)c->sm_count * 8);
     k_match_lengths<<<blocks, 256, 0, s>>>(pairs, m, c->wide.as<uint64_t>());
-    RJ_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->wide.as<uint64_t>(), c->slot.as<uint64_t>(), (int64_t)m, s));
+    RJ_TRY_COUNT(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->wide.as<uint64_t>(), c->slot.as<uint64_t>(), (int64_t)m, s));
     uint64_t tail[2] = {0, 0};
-    RJ_TRY(cudaMemcpyAsync(&tail[0], c->slot.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, s));
-    RJ_TRY(cudaMemcpyAsync(&tail[1], c->wide.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, s));
-    RJ_TRY(cudaStreamSynchronize(s));
+    RJ_TRY_COUNT(cudaMemcpyAsync(&tail[0], c->slot.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, s));
+    RJ_TRY_COUNT(cudaMemcpyAsync(&tail[1], c->wide.as<uint64_t>() + (m - 1), 8, cudaMemcpyDeviceToHost, s));
+    RJ_TRY_COUNT(cudaStreamSynchronize(s));
     total_removed = tail[0] + tail[1];
     if (stats) stats->launches += 3;
   }
@@ -1610,9 +1615,9 @@ int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint6
     if (ok) {
       const uint64_t n_tiles = n / kReplaceTile + 1;
       int blocks = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 8);
-      k_replace_tiles<<<blocks, 256, 0, s>>>(d_text, n, pairs, c->slot.as<uint64_t>(), m, c->with_buf.as<uint8_t>(),
+      k_replace_stage<<<blocks, 256, 0, s>>>(d_text, n, pairs, c->slot.as<uint64_t>(), m, c->with_buf.as<uint8_t>(),
                                              (uint32_t)with_len, static_cast<uint8_t*>(out), n_tiles);
-      ok = Check(cudaGetLastError(), "k_replace_tiles", error);
+      ok = Check(cudaGetLastError(), "k_replace_stage", error);
       if (stats) stats->launches += 1;
     }
   }
@@ -1630,6 +1635,115 @@ int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint6
   *out_len = len;
   if (out_capacity) *out_capacity = cap;
   return (int64_t)m;
+}
+
+// ---------------------------------------------------------------------------
+// A set of one-byte patterns as one byte -> string table (replace.cuh k_translate_*).
+// ---------------------------------------------------------------------------
+bool ReplaceSetFusable(const std::vector<Program*>& progs, const std::vector<std::string>& withs) {
+  if (progs.empty() || progs.size() > 32 || progs.size() != withs.size()) return false;
+  size_t bytes = 0;
+  for (size_t i = 0; i < progs.size(); ++i) {
+    const PositionNfa& a = progs[i]->automaton().nfa;
+    if (a.n_pos != 1 || a.has_anchor || a.min_len != 1 || a.max_len != 1 || a.accept_empty[0]) return false;
+    if (withs[i].size() > 0xFFF0) return false;
+    bytes += withs[i].size();
+  }
+  if (bytes > kTransMaxBytes) return false;
+  // the calls run one after the other in the reference: a replacement must not hold a byte a LATER pattern matches
+  for (size_t i = 0; i < progs.size(); ++i)
+    for (size_t j = i + 1; j < progs.size(); ++j) {
+      const std::array<uint32_t, 8>& cls = progs[j]->automaton().nfa.cls[0];
+      for (unsigned char ch : withs[i]) if ((cls[ch >> 5] >> (ch & 31)) & 1u) return false;
+    }
+  return true;
+}
+
+int64_t ReplaceAllSetDevice(int device, const std::vector<Program*>& progs, const uint8_t* d_text, uint64_t n,
+                            const std::vector<std::string>& withs, void** d_out, uint64_t* out_len, uint64_t* out_capacity,
+                            int64_t* counts, RunStats* stats, std::string* error) {
+  if (d_out) *d_out = nullptr;
+  if (out_len) *out_len = 0;
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return -1;
+  if (!ReplaceSetFusable(progs, withs)) { if (error) *error = "rejit_b200: this set is not a byte -> string table"; return -1; }
+  const int K = (int)progs.size();
+  TranslateTable tab;
+  memset(&tab, 0, sizeof tab);
+  uint32_t at = 0;
+  std::vector<uint32_t> off(K);
+  for (int i = 0; i < K; ++i) {
+    off[i] = at;
+    memcpy(tab.bytes + at, withs[i].data(), withs[i].size());
+    at += (uint32_t)withs[i].size();
+  }
+  for (int b = 0; b < 256; ++b) {
+    tab.len[b] = 1; tab.off[b] = 0xFFFF; tab.pat[b] = kTransNone;
+    for (int i = 0; i < K; ++i) {
+      const std::array<uint32_t, 8>& cls = progs[i]->automaton().nfa.cls[0];
+      if ((cls[b >> 5] >> (b & 31)) & 1u) {                 // the first pattern that matches the byte replaces it
+        tab.len[b] = (uint16_t)withs[i].size(); tab.off[b] = (uint16_t)off[i]; tab.pat[b] = (uint8_t)i;
+        break;
+      }
+    }
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  RJ_TRY_COUNT(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const uint64_t n_tiles = (n + kTransTile - 1) / kTransTile;
+  if (!c->trans_tab.Reserve(sizeof tab, error) || !c->trans_len.Reserve((n_tiles + 1) * 8, error) ||
+      !c->trans_off.Reserve((n_tiles + 1) * 8, error) || !c->trans_counts.Reserve(32 * 8, error)) return -1;
+  if (stats) cudaEventRecord(c->ev[0], s);
+  RJ_TRY_COUNT(cudaMemcpyAsync(c->trans_tab.p, &tab, sizeof tab, cudaMemcpyHostToDevice, s));
+  RJ_TRY_COUNT(cudaMemsetAsync(c->trans_counts.p, 0, 32 * 8, s));
+  unsigned long long h_counts[32] = {0};
+  uint64_t total = 0;
+  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 8));
+  if (n_tiles) {
+    k_translate_count<<<blocks, 256, 0, s>>>(d_text, n, c->trans_tab.as<TranslateTable>(), c->trans_len.as<uint64_t>(),
+                                             c->trans_counts.as<unsigned long long>(), n_tiles);
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->trans_len.as<uint64_t>(), c->trans_off.as<uint64_t>(), (int64_t)n_tiles, s);
+    if (!c->cub_tmp.Reserve(tmp, error)) return -1;
+    RJ_TRY_COUNT(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->trans_len.as<uint64_t>(), c->trans_off.as<uint64_t>(), (int64_t)n_tiles, s));
+    uint64_t tail[2] = {0, 0};
+    RJ_TRY_COUNT(cudaMemcpyAsync(&tail[0], c->trans_off.as<uint64_t>() + (n_tiles - 1), 8, cudaMemcpyDeviceToHost, s));
+    RJ_TRY_COUNT(cudaMemcpyAsync(&tail[1], c->trans_len.as<uint64_t>() + (n_tiles - 1), 8, cudaMemcpyDeviceToHost, s));
+    RJ_TRY_COUNT(cudaMemcpyAsync(h_counts, c->trans_counts.p, 32 * 8, cudaMemcpyDeviceToHost, s));
+    RJ_TRY_COUNT(cudaStreamSynchronize(s));
+    total = tail[0] + tail[1];
+  }
+  const uint64_t cap = total + 64;
+  void* out = DeviceAlloc(device, cap, error);
+  if (!out) return -1;
+  bool ok = true;
+  if (n_tiles) {
+    const size_t smem = kTransStage + 32 + kTransMaxBytes;
+    ok = EnsureKernelAttributes(c, error);
+    if (ok) {
+      k_translate_write<<<blocks, 256, smem, s>>>(d_text, n, c->trans_tab.as<TranslateTable>(), c->trans_off.as<uint64_t>(),
+                                                  static_cast<uint8_t*>(out), n_tiles);
+      ok = Check(cudaGetLastError(), "k_translate_write", error);
+    }
+  }
+  if (ok && stats) {
+    cudaEventRecord(c->ev[1], s);
+    ok = Check(cudaEventSynchronize(c->ev[1]), "sync", error);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    stats->total_ms += ms;
+    stats->scan_ms += ms;
+    stats->launches += n_tiles ? 5 : 0;
+  } else if (ok) {
+    ok = Check(cudaStreamSynchronize(s), "sync", error);
+  }
+  if (!ok) { DeviceFree(device, out); return -1; }
+  int64_t all = 0;
+  for (int i = 0; i < K; ++i) { if (counts) counts[i] = (int64_t)h_counts[i]; all += (int64_t)h_counts[i]; }
+  *d_out = out;
+  *out_len = total;
+  if (out_capacity) *out_capacity = cap;
+  return all;
 }
 
 int64_t ReplaceAllHost(int device, Program* prog, const uint8_t* text, uint64_t n, const uint8_t* with,

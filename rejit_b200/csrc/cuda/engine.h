@@ -125,6 +125,15 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
 int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_t n, const uint8_t* with,
                          uint64_t with_len, void** d_out, uint64_t* out_len, uint64_t* out_capacity,
                          RunStats* stats, std::string* error);
+// A SET of patterns that each match exactly one byte, applied "one after the other" (regex-dna's eleven IUB
+// substitutions, /root/reference/sample/regexdna.cc:69-85) as ONE byte -> string table: a counting pass, a prefix
+// sum and a writing pass instead of one scan + rebuild per pattern.  ReplaceSetFusable says whether the table gives
+// exactly what the sequential calls give (one-byte patterns, no replacement holds a byte that a later pattern
+// matches); counts[i] = matches of pattern i.  Returns the total number of matches, or -1.
+bool ReplaceSetFusable(const std::vector<Program*>& progs, const std::vector<std::string>& withs);
+int64_t ReplaceAllSetDevice(int device, const std::vector<Program*>& progs, const uint8_t* d_text, uint64_t n,
+                            const std::vector<std::string>& withs, void** d_out, uint64_t* out_len, uint64_t* out_capacity,
+                            int64_t* counts, RunStats* stats, std::string* error);
 // Host-pointer convenience: uploads, replaces, downloads (*out is malloc'ed).
 int64_t ReplaceAllHost(int device, Program* prog, const uint8_t* text, uint64_t n, const uint8_t* with,
                        uint64_t with_len, uint8_t** out, uint64_t* out_len, RunStats* stats, std::string* error);

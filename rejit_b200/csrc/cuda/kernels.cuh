@@ -115,7 +115,6 @@ struct FinishArgs {
   uint64_t base_offset;
   FinRecord* host_records;             // [K] mapped host memory (see FinRecord)
   unsigned int seq;
-  unsigned long long* trace;           // optional (RJ_FIN_TRACE): 5 globaltimer stamps per CTA
 };
 constexpr unsigned int kFinOverlap = 1u, kFinDense = 2u, kFinOverflow = 4u;
 constexpr uint32_t kFinScratchWords = 4096;   // dynamic shared memory of the non-TMA scans (16 KB)
@@ -459,14 +458,6 @@ __device__ __forceinline__ void GridBarrier(unsigned int* ctr, unsigned int expe
   __syncthreads();
 }
 
-__device__ __forceinline__ void FinTrace(const FinishArgs& fin, int slot) {
-  if (fin.trace && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    fin.trace[(size_t)blockIdx.x * 8 + slot] = t;
-  }
-}
-
 // the scan's bookkeeping for one (pattern, sub-region) count
 __device__ __forceinline__ void FinishNote(const FinishArgs& fin, int j, uint64_t sub, uint32_t total, bool over,
                                            uint32_t cap) {
@@ -532,9 +523,7 @@ __device__ __forceinline__ bool FinTaken(uint64_t b, uint64_t e, uint64_t P, con
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_pat, int K, const FinishArgs& fin,
                                               const Carry* carries, uint32_t* scratch, uint32_t scratch_words) {
-  FinTrace(fin, 0);
   GridBarrier(&fin.sync[0], gridDim.x);
-  FinTrace(fin, 1);
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
@@ -594,7 +583,6 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
       }
     }
     __syncthreads();
-    FinTrace(fin, 5);
     // ---- pass 2: where every sub-region's candidates go, and who precedes them ---
     for (uint32_t it = warp_in_cta, k = 0; it < items; it += nwarps, ++k) {
       const uint32_t j = it / nch, ci = it - j * nch;
@@ -662,7 +650,6 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
         for (uint32_t c2 = 0; c2 < nch; ++c2) { const uint64_t q = s_last[j * nch + c2]; m2 = q > m2 ? q : m2; }
         if (m2) atomicMax(&fin.last_end[j], (unsigned long long)(m2 - 1));
       }
-    FinTrace(fin, 6);
     // ---- pass 3: the copy.  Cells with at most 4 candidates: one LANE per cell (all
     // loads of 32 cells in flight at once); larger cells: the whole warp per cell,
     // 128 candidates in flight.
@@ -739,7 +726,6 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
       }
       if (__any_sync(kFullMask, bad) && lane == 0) atomicOr(&fin.sync[2], kFinOverlap);
     }
-    FinTrace(fin, 7);
     __syncthreads();
     if (usable)
       for (int j = threadIdx.x; j < K; j += blockDim.x)
@@ -748,7 +734,6 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
   }
   // the last WARP of the grid to get here publishes the records (every warp
   // counts once; its atomics above are ordered before the count by the fence)
-  FinTrace(fin, 2);
   __syncwarp();
   int is_last = 0;
   if (lane == 0) {
@@ -757,11 +742,6 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
   }
   if (!__shfl_sync(kFullMask, is_last, 0)) return;
   __threadfence();
-  if (fin.trace && lane == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    fin.trace[(size_t)blockIdx.x * 8 + 3] = t;
-  }
   const unsigned int flags = __ldcg(&fin.sync[2]);
   const unsigned int need_cap = __ldcg(&fin.sync[3]);
   for (int j = lane; j < K; j += 32) {
@@ -775,11 +755,6 @@ __device__ __forceinline__ void FinishOrdered(const SubStore& st, uint64_t nsub_
                  "r"((unsigned int)(le >> 32)), "r"(need_cap), "r"(fin.seq) : "memory");
     asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"((unsigned int)ln),
                  "r"((unsigned int)(ln >> 32)), "r"(0u), "r"(fin.seq) : "memory");
-  }
-  if (fin.trace && lane == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    fin.trace[(size_t)blockIdx.x * 8 + 4] = t;
   }
 }
 
@@ -1298,12 +1273,14 @@ struct KmerRun {
   uint64_t row_lo;                     // first 512-byte row that can hold an owned end
   uint32_t rows_per_cta, rows_per_warp;
   KmerXchg* xchg;                      // [gridDim.x][32]
+  uint2* stage;                        // [gridDim.x * 32][stage_cap]: matches of a warp that no longer fit its shared list
+  uint32_t stage_cap;
+  unsigned int* gsync;                 // [0] flags, [1] CTAs done; zero between calls (the reporting CTA clears them)
+  unsigned long long* gfinal;          // [32][2]: per member {matches, last end}, written by the CTA with the highest index
   uint64_t* out_pairs;                 // member j's pairs start at out_pairs + j * 2 * out_stride
   uint64_t out_stride, out_cap, base_offset;
   FinRecord* host_records;
   unsigned int seq;
-  unsigned long long* trace;           // optional: 16 globaltimer stamps per CTA
-  int debug_stop;                      // tuning aid (RJ_KMER_STOP): leave after phase n (results are then invalid)
   int has_carry;                       // some member's chain arrives from the left (CarrySet is read only then)
 };
 
@@ -1315,26 +1292,18 @@ constexpr int kKmerWordBits = kKmerIdxBits - 5;
 constexpr uint32_t kKmerBitmapBytes = 4u << kKmerWordBits;          // 32 KB (R = 2), 128 KB (R = 3)
 constexpr uint32_t kKmerThreads = 1024;
 constexpr uint32_t kKmerWarps = kKmerThreads / 32;
-constexpr uint32_t kKmerMaxRows = 1024;            // rows per CTA (512 KB of text: 16 KB per warp against kKmerWarpRaw)
-constexpr uint32_t kKmerWarpRaw = 64;              // hits per warp (its run of rows)
-constexpr uint32_t kKmerMaxGrid = 160;             // five CTAs per lane in the seam check
-// dynamic shared memory: fixed part + the last CTA's seam table (kKmerMaxGrid x K x 8 bytes)
-constexpr uint32_t kKmerSmemFixed = kKmerBitmapBytes + kKmerWarps * kKmerWarpRaw * 4 * (2 + kKmerEnds) +
-                                    4 * kKmerWarps * 32 * 4 + kKmerHashSlots * 8 + kKmerTabWords * 4 + 512;
+constexpr uint32_t kKmerMaxRowsPerCta = 1u << 19;  // offsets inside a CTA's rows fit 28 bits (256 MB of text per CTA)
+constexpr uint32_t kKmerWarpRaw = 64;              // 16-byte groups with a hit / hits a warp collects before it checks them
+constexpr uint32_t kKmerFlushAt = 32;              // ... it stops streaming and checks them at this many groups
+constexpr uint32_t kKmerStageSm = 64;              // checked matches a warp keeps in shared memory
+constexpr uint32_t kKmerSmemFixed = kKmerBitmapBytes + kKmerWarps * (kKmerWarpRaw * 8 + kKmerStageSm * 8) +
+                                    4 * kKmerWarps * 32 * 4 + kKmerHashSlots * 8 + kKmerTabWords * 4 + 2048;
 // first letter (0..15) of the ends lookup t answers: x, x+1, .., x+R-1; the last lookup is pulled back into the group
 __host__ __device__ constexpr int KmerTestX(int t) { return t * kKmerEnds < 16 - kKmerEnds ? t * kKmerEnds : 16 - kKmerEnds; }
 
 __device__ __forceinline__ uint32_t KmerPack(const uint4& v, uint32_t fm, uint32_t mult) {
   const uint32_t p0 = (v.x & fm) * mult, p1 = (v.y & fm) * mult, p2 = (v.z & fm) * mult, p3 = (v.w & fm) * mult;
   return __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);
-}
-
-__device__ __forceinline__ void KmerTrace(const KmerRun& run, int slot) {
-  if (run.trace && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    run.trace[(size_t)blockIdx.x * 16 + slot] = t;
-  }
 }
 
 // The members that end at text offset e (exact): the eight bytes before e give the codes x16 (oldest in the low
@@ -1381,6 +1350,11 @@ __device__ __forceinline__ uint32_t KmerVerify(const uint8_t* __restrict__ text,
   return members & s_lenle[v];
 }
 
+// Round 2: a warp owns a contiguous run of rows of ANY length.  It streams them until its list of groups with a
+// hit is half full, leaves the streaming loop, checks those hits (exact check, per-member counts, overlap test) and
+// keeps the checked matches {end, members} — in shared memory while they fit, else in a per-warp staging area in
+// global memory — and goes on streaming.  Nothing but the final exchange is grid-wide, so the fixed costs (tables,
+// exchange, report) are paid once per call whatever the text size.
 __global__ void __launch_bounds__(kKmerThreads, 1)
 k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTables km, ScanRange range, KmerRun run,
            CarrySet carries) {
@@ -1391,14 +1365,14 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
   const int K = n_patterns;
   // the set's small tables: requested before anything else, while the memory system is still idle
   const uint32_t tab_word = threadIdx.x < kKmerTabWords ? __ldg(km.tab + threadIdx.x) : 0u;
-  // layout: [bitmap][per warp: hits u32 [64], groups with a hit u32 [64], candidate masks u32 [64 R]]
+  // layout: [bitmap][per warp: hits u32 [64], groups with a hit u32 [64], checked matches uint2 [64]]
   //         [per warp and member: count, offset, first end, last end u32 [warp][32]][hash keys, values]
-  //         [small tables][misc][seam table (last CTA)]
+  //         [small tables][misc]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* s_raw = s_bitmap + kKmerBitmapBytes / 4;
   uint32_t* s_ent = s_raw + kKmerWarps * kKmerWarpRaw;
-  uint32_t* s_mask = s_ent + kKmerWarps * kKmerWarpRaw;
-  uint32_t* s_wcnt = s_mask + kKmerWarps * kKmerWarpRaw * R;
+  uint2* s_stage = reinterpret_cast<uint2*>(s_ent + kKmerWarps * kKmerWarpRaw);
+  uint32_t* s_wcnt = reinterpret_cast<uint32_t*>(s_stage + kKmerWarps * kKmerStageSm);
   uint32_t* s_woff = s_wcnt + kKmerWarps * 32;
   uint32_t* s_wfirst = s_woff + kKmerWarps * 32;
   uint32_t* s_wlast = s_wfirst + kKmerWarps * 32;
@@ -1412,9 +1386,10 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
   uint32_t* s_flags = s_misc + 2;
   uint32_t* s_base = s_misc + 4;                                                      // [32] matches of the CTAs before me
   uint32_t* s_count = s_base + 32;                                                    // [32] my matches per member
-  uint2* s_seam = reinterpret_cast<uint2*>(s_misc + 128);                             // [CTA][K] {first, last} end - seam_base
+  unsigned long long* s_prevlast = reinterpret_cast<unsigned long long*>(s_count + 32);   // [32] last end before my CTA
+  unsigned long long* s_cfirst = s_prevlast + 32;                                     // [32] my first / last end
+  unsigned long long* s_clast = s_cfirst + 32;
 
-  KmerTrace(run, 0);
   const bool from_list = km.n_list != 0;
   if (threadIdx.x == 0) {
     *s_flags = 0;
@@ -1425,10 +1400,9 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
       TmaLoad1D(s_bitmap, km.bitmap, kKmerBitmapBytes, s_bar);
     }
   }
-  if (threadIdx.x < 32) { s_base[threadIdx.x] = 0; s_count[threadIdx.x] = 0; }
+  if (threadIdx.x < 32) { s_base[threadIdx.x] = 0; s_count[threadIdx.x] = 0; s_prevlast[threadIdx.x] = 0; }
 
-  // ---- scan --------------------------------------------------------------------
-  const uint64_t seam_base = run.row_lo << 9;
+  // ---- my warp's rows -------------------------------------------------------------
   const uint64_t cta_row0 = run.row_lo + (uint64_t)blockIdx.x * run.rows_per_cta;
   const uint64_t cta_base = cta_row0 << 9;
   const uint64_t n16 = (n + 15) & ~15ull;                   // device texts are padded: whole groups can be read
@@ -1489,12 +1463,16 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
     MbarWait(s_bar, 0);
   }
   uint32_t prevQ = has_prev ? KmerPack(prev16, fm, mult) : 0u;   // lane 31: codes of the 16 bytes before the row
-  KmerTrace(run, 1);
   uint32_t* my_raw = s_raw + warp * kKmerWarpRaw;
   uint32_t* my_ent = s_ent + warp * kKmerWarpRaw;
+  uint2* my_stage = s_stage + warp * kKmerStageSm;
+  uint2* my_gstage = run.stage + ((size_t)blockIdx.x * kKmerWarps + warp) * run.stage_cap;
   uint32_t n_ent = 0;                                       // 16-byte groups of my warp with a hit so far (uniform)
+  uint32_t n_sm = 0, n_gl = 0;                              // checked matches in my shared list / in the staging area
   const uint32_t lt_mask = (1u << lane) - 1u;
   const int from = (lane + 31) & 31;
+  unsigned int flags = 0;
+  uint32_t cj = 0, firstj = 0, lastj = 0;                   // member `lane`: count, first end, last end (relative to the CTA)
   // one row: pack my 16 bytes, refill the register they came from with the row four ahead, look the 16 ends up
   auto row = [&](uint4& v, uint32_t r) {
     const uint32_t Q = KmerPack(v, fm, mult);
@@ -1519,97 +1497,115 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
       n_ent += __popc(bal);
     }
   };
-  {
-    uint32_t r = w_row0;
-    for (; r + 4 <= w_row1; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
-    if (r < w_row1) row(v0, r);
-    if (r + 1 < w_row1) row(v1, r + 1);
-    if (r + 2 < w_row1) row(v2, r + 2);
-  }
-  KmerTrace(run, 2);
-  if (run.debug_stop == 1) return;
-
-  // ---- my warp's hits: exact check, per-member counts -------------------------------
-  // candidate R h + k = end k of hit h; lane j keeps member j's numbers
-  unsigned int flags = 0;
-  if (n_ent > kKmerWarpRaw) { flags |= kFinDense; n_ent = 0; }
-  __syncwarp();
-  // groups -> hits, in position order: one entry of my_raw per lookup that hit
-  uint32_t n_raw = 0;
-  for (uint32_t base = 0; base < n_ent; base += 32) {
-    const uint32_t ent = base + lane < n_ent ? my_ent[base + lane] : 0u;
-    const uint32_t acc = ent & 0xFFu, pos16 = (ent >> 8) * 16u;     // bit kKmerTests-1-t: lookup t hit
-    const uint32_t cnt = __popc(acc);
-    const uint32_t incl = WarpInclusiveScan(cnt);
-    uint32_t at = n_raw + incl - cnt;
-    uint32_t x = __brev(acc) >> (32 - kKmerTests);                  // bit t: lookup t
-    while (x) {
-      const int t = __ffs(x) - 1;
-      x &= x - 1;
-      const int xt = t * R < 16 - R ? t * R : 16 - R;
-      // first of the R ends (relative to the CTA's first byte) | the first end that is this lookup's own << 30
-      if (at < kKmerWarpRaw) my_raw[at] = (pos16 + xt + 1u) | ((uint32_t)(t * R - xt) << 30);
-      ++at;
+  uint32_t r = w_row0;
+  bool reload = false;
+#pragma unroll 1
+  for (;;) {
+    if (reload) {
+      // back from checking hits: the rows in flight were dropped, fetch them again (they are in L2)
+      v0 = r < w_load1 ? __ldg(src + (size_t)(r - w_row0) * 32) : zero4;
+      v1 = r + 1 < w_load1 ? __ldg(src + (size_t)(r + 1 - w_row0) * 32) : zero4;
+      v2 = r + 2 < w_load1 ? __ldg(src + (size_t)(r + 2 - w_row0) * 32) : zero4;
+      v3 = r + 3 < w_load1 ? __ldg(src + (size_t)(r + 3 - w_row0) * 32) : zero4;
     }
-    n_raw += __shfl_sync(kFullMask, incl, 31);
-  }
-  if (n_raw > kKmerWarpRaw) { flags |= kFinDense; n_raw = 0; }
-  __syncwarp();
-  const uint32_t n_cand = R * n_raw;
-  uint32_t* my_mask = s_mask + warp * kKmerWarpRaw * R;
-  uint32_t cj = 0, firstj = 0, lastj = 0;                   // member `lane`: count, first end, last end (relative to the CTA)
-  for (uint32_t i0 = 0; i0 < n_cand; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    uint32_t m = 0, erel = 0;
-    if (i < n_cand) {
-      const uint32_t h = i / R, k = i - h * R;
-      const uint32_t raw = my_raw[h];
-      erel = (raw & 0x3FFFFFFFu) + k;
-      const uint64_t e = cta_base + erel;
-      if (k >= (raw >> 30) && e <= n && run.debug_stop != 6) {
-        const uint32_t mv = KmerVerify(text, e, fm, mult, km.shift, km.canon, from_list, km.mask16, s_hkey, s_hval, s_lenle);
-        for (uint32_t mm = mv; mm; mm &= mm - 1) {
-          const int j = __ffs(mm) - 1;
-          const uint64_t b = e - s_mlen[j];
-          if (b >= range.own_begin && b < range.own_end) {
-            m |= 1u << j;
-            if (run.has_carry && b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
+    reload = true;
+    // ---- stream until the list of groups with a hit is half full ------------------------------------
+#pragma unroll 1
+    for (; r + 4 <= w_row1 && n_ent < kKmerFlushAt; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
+    if (r + 4 > w_row1) {
+      if (r < w_row1) row(v0, r);
+      if (r + 1 < w_row1) row(v1, r + 1);
+      if (r + 2 < w_row1) row(v2, r + 2);
+      r = w_row1;
+    }
+    // ---- my hits so far: exact check, per-member counts ---------------------------------------------
+    if (n_ent > kKmerWarpRaw) { flags |= kFinDense; n_ent = 0; }
+    __syncwarp();
+    // groups -> hits, in position order: one entry of my_raw per lookup that hit
+    uint32_t n_raw = 0;
+    for (uint32_t base = 0; base < n_ent; base += 32) {
+      const uint32_t ent = base + lane < n_ent ? my_ent[base + lane] : 0u;
+      const uint32_t acc = ent & 0xFFu, pos16 = (ent >> 8) * 16u;     // bit kKmerTests-1-t: lookup t hit
+      const uint32_t cnt = __popc(acc);
+      const uint32_t incl = WarpInclusiveScan(cnt);
+      uint32_t at = n_raw + incl - cnt;
+      uint32_t x = __brev(acc) >> (32 - kKmerTests);                  // bit t: lookup t
+      while (x) {
+        const int t = __ffs(x) - 1;
+        x &= x - 1;
+        const int xt = t * R < 16 - R ? t * R : 16 - R;
+        // first of the R ends (relative to the CTA's first byte) | the first end that is this lookup's own << 30
+        if (at < kKmerWarpRaw) my_raw[at] = (pos16 + xt + 1u) | ((uint32_t)(t * R - xt) << 30);
+        ++at;
+      }
+      n_raw += __shfl_sync(kFullMask, incl, 31);
+    }
+    if (n_raw > kKmerWarpRaw) { flags |= kFinDense; n_raw = 0; }
+    n_ent = 0;
+    __syncwarp();
+    const uint32_t n_cand = R * n_raw;
+    for (uint32_t i0 = 0; i0 < n_cand; i0 += 32) {
+      // room for 32 more checked matches in my shared list, else it moves to the staging area
+      if (n_sm + 32 > kKmerStageSm) {
+        for (uint32_t q = lane; q < n_sm; q += 32)
+          if (n_gl + q < run.stage_cap) my_gstage[n_gl + q] = my_stage[q];
+        n_gl += n_sm;
+        n_sm = 0;
+        __syncwarp();
+      }
+      const uint32_t i = i0 + lane;
+      uint32_t m = 0, erel = 0;
+      if (i < n_cand) {
+        const uint32_t h = i / R, k = i - h * R;
+        const uint32_t raw = my_raw[h];
+        erel = (raw & 0x3FFFFFFFu) + k;
+        const uint64_t e = cta_base + erel;
+        if (k >= (raw >> 30) && e <= n) {
+          const uint32_t mv = KmerVerify(text, e, fm, mult, km.shift, km.canon, from_list, km.mask16, s_hkey, s_hval, s_lenle);
+          for (uint32_t mm = mv; mm; mm &= mm - 1) {
+            const int j = __ffs(mm) - 1;
+            const uint64_t b = e - s_mlen[j];
+            if (b >= range.own_begin && b < range.own_end) {
+              m |= 1u << j;
+              if (run.has_carry && b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
+            }
           }
         }
       }
-      my_mask[i] = m;
-    }
-    // a candidate overlaps an earlier one of the same member iff that one ends less than a match length before
-    // it: its predecessor in this pass, the last one of the pass before; other warps and CTAs: the seam checks
-    for (uint32_t todo = __reduce_or_sync(kFullMask, m); todo; todo &= todo - 1) {
-      const int j = __ffs(todo) - 1;
-      const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
-      const uint32_t L = s_mlen[j];
-      const int lo = __ffs(bal) - 1, hi = 31 - __clz(bal);
-      const uint32_t e_lo = __shfl_sync(kFullMask, erel, lo), e_hi = __shfl_sync(kFullMask, erel, hi);
-      const uint32_t before = bal & ((1u << lane) - 1u);
-      const int pl = before ? 31 - __clz(before) : lane;
-      const uint32_t e_prev = __shfl_sync(kFullMask, erel, pl);
-      if (((m >> j) & 1u) && before && e_prev + L > erel) flags |= kFinOverlap;
-      if (lane == j) {
-        if (cj && lastj + L > e_lo) flags |= kFinOverlap;
-        if (!cj) firstj = e_lo;
-        lastj = e_hi;
-        cj += __popc(bal);
+      // a candidate overlaps an earlier one of the same member iff that one ends less than a match length before
+      // it: its predecessor in this pass, the last one of the passes before; other warps and CTAs: the seam checks
+      for (uint32_t todo = __reduce_or_sync(kFullMask, m); todo; todo &= todo - 1) {
+        const int j = __ffs(todo) - 1;
+        const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
+        const uint32_t L = s_mlen[j];
+        const int lo = __ffs(bal) - 1, hi = 31 - __clz(bal);
+        const uint32_t e_lo = __shfl_sync(kFullMask, erel, lo), e_hi = __shfl_sync(kFullMask, erel, hi);
+        const uint32_t before = bal & ((1u << lane) - 1u);
+        const int pl = before ? 31 - __clz(before) : lane;
+        const uint32_t e_prev = __shfl_sync(kFullMask, erel, pl);
+        if (((m >> j) & 1u) && before && e_prev + L > erel) flags |= kFinOverlap;
+        if (lane == j) {
+          if (cj && lastj + L > e_lo) flags |= kFinOverlap;
+          if (!cj) firstj = e_lo;
+          lastj = e_hi;
+          cj += __popc(bal);
+        }
       }
+      const uint32_t balm = __ballot_sync(kFullMask, m != 0);
+      if (m) my_stage[n_sm + __popc(balm & lt_mask)] = make_uint2(erel, m);
+      n_sm += __popc(balm);
+      __syncwarp();
     }
+    if (r >= w_row1) break;
   }
+  if (n_gl > run.stage_cap) flags |= kFinOverflow;
   s_wcnt[warp * 32 + lane] = cj;
   s_wfirst[warp * 32 + lane] = firstj;
   s_wlast[warp * 32 + lane] = lastj;
   if (flags) atomicOr(s_flags, flags);
-  KmerTrace(run, 8);
   __syncthreads();
-  KmerTrace(run, 3);
-  if (run.debug_stop == 2) return;
 
   // ---- warp j: member j over the 32 warps (lane = warp): offsets, seams, my CTA's record --------
-  const bool last_cta = blockIdx.x + 1 == gridDim.x;
   if (warp < K) {
     const int j = warp;
     const uint32_t L = s_mlen[j];
@@ -1634,27 +1630,26 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
     if (lane == 0) {
       s_count[j] = total;
       const unsigned long long f64 = total ? cta_base + cta_first : 0ull, l64 = total ? cta_base + cta_last : 0ull;
-      const unsigned int fl = *s_flags | (any_bad ? kFinOverlap : 0u);
+      s_cfirst[j] = f64;
+      s_clast[j] = l64;
       if (any_bad) atomicOr(s_flags, kFinOverlap);
       volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.xchg + (size_t)blockIdx.x * 32 + j);
       asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)f64),
                    "r"((unsigned int)(f64 >> 32)), "r"(total), "r"(run.seq) : "memory");
       asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)l64),
-                   "r"((unsigned int)(l64 >> 32)), "r"(fl), "r"(run.seq) : "memory");
-      if (last_cta) s_seam[(size_t)blockIdx.x * K + j] = make_uint2((uint32_t)(f64 ? f64 - seam_base : 0), (uint32_t)(l64 ? l64 - seam_base : 0));
+                   "r"((unsigned int)(l64 >> 32)), "r"(0u), "r"(run.seq) : "memory");
     }
   }
   // nobody polls before this CTA's own records are out: warps spinning on system-scope loads keep the
   // load/store queue full and starved the publishing warps of their shared-memory and shuffle slots
   __syncthreads();
-  KmerTrace(run, 4);
-  if (run.debug_stop == 3) return;
   // ---- exchange: the CTAs before me.  Warp w reads CTA w, w + 32, ... (lane j = member j), five CTAs' records
-  // in flight at once.  The last CTA keeps what it reads for the seam check below.
+  // in flight at once: matches before me, and the last end before me (for the seam between CTAs).
   for (uint32_t c0 = warp; c0 < blockIdx.x; c0 += 160) {
     uint4 a[5], b[5];
     unsigned pending = 0;
     uint32_t sum = 0;
+    unsigned long long prev_last = 0;
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
       a[u] = b[u] = zero4;
@@ -1673,29 +1668,32 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
         if (((pending >> u) & 1u) && a[u].w == run.seq && b[u].w == run.seq) {
           pending &= ~(1u << u);
           sum += a[u].z;
-          if (last_cta) {
-            if (b[u].z) atomicOr(s_flags, b[u].z);
-            const unsigned long long f64 = (unsigned long long)a[u].y << 32 | a[u].x, l64 = (unsigned long long)b[u].y << 32 | b[u].x;
-            s_seam[(size_t)(c0 + 32 * u) * K + lane] =
-                make_uint2(a[u].z ? (uint32_t)(f64 - seam_base) : 0u, a[u].z ? (uint32_t)(l64 - seam_base) : 0u);
-          }
+          const unsigned long long l64 = (unsigned long long)b[u].y << 32 | b[u].x;
+          if (a[u].z && l64 > prev_last) prev_last = l64;
         }
     }
     if (sum) atomicAdd(&s_base[lane], sum);
+    if (prev_last) atomicMax(&s_prevlast[lane], prev_last);
   }
   __syncthreads();
-  KmerTrace(run, 5);
-  if (run.debug_stop == 4) return;
+  // the seam between my CTA and the ones before it
+  if (threadIdx.x < K) {
+    const int j = threadIdx.x;
+    if (s_count[j] && s_prevlast[j] && s_prevlast[j] + s_mlen[j] > s_cfirst[j]) atomicOr(s_flags, kFinOverlap);
+  }
 
-  // ---- my warp's matches, at their final place -----------------------------------
+  // ---- my warp's matches, at their final place: first the ones that moved to the staging area, then my shared list
   {
     uint32_t done = 0;                                      // member `lane`: matches of my warp already written
-    for (uint32_t i0 = 0; i0 < n_cand; i0 += 32) {
+    const uint32_t n_gl_ok = n_gl < run.stage_cap ? n_gl : run.stage_cap;
+    const uint32_t n_all = n_gl_ok + n_sm;
+    for (uint32_t i0 = 0; i0 < n_all; i0 += 32) {
       const uint32_t i = i0 + lane;
-      const uint32_t m = i < n_cand ? my_mask[i] : 0u;
-      if (!__any_sync(kFullMask, m != 0)) continue;
-      const uint32_t h = i / R;
-      const uint64_t e = cta_base + (i < n_cand ? (my_raw[h] & 0x3FFFFFFFu) + (i - h * R) : 0u);
+      uint2 ent = make_uint2(0, 0);
+      if (i < n_gl_ok) ent = __ldcg(my_gstage + i);
+      else if (i < n_all) ent = my_stage[i - n_gl_ok];
+      const uint32_t m = ent.y;
+      const uint64_t e = cta_base + ent.x;
       for (uint32_t todo = __reduce_or_sync(kFullMask, m); todo; todo &= todo - 1) {
         const int j = __ffs(todo) - 1;
         const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
@@ -1710,50 +1708,42 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
       }
     }
   }
-  KmerTrace(run, 6);
-  if (!last_cta || run.debug_stop == 5) return;
-  // ---- the last CTA: seams between CTAs, totals, report.  Warp j = member j; lane l looks at CTAs 5 l .. 5 l + 4
-  if (warp < K) {
-    const int j = warp;
-    const uint32_t L = s_mlen[j];
-    uint2 fl[5];
-    uint32_t lm = 0;                                         // last end among my five
-#pragma unroll
-    for (int u = 0; u < 5; ++u) {
-      const uint32_t c = 5 * lane + u;
-      fl[u] = c < gridDim.x ? s_seam[(size_t)c * K + j] : make_uint2(0, 0);
-      lm = fl[u].y > lm ? fl[u].y : lm;
+  __syncthreads();
+  // ---- the CTA that finishes last reports (and leaves the two sync words zero for the next call) ----------
+  if (warp == 0) {
+    const bool top = blockIdx.x + 1 == gridDim.x;
+    if (top && lane < K) {
+      // totals and last ends are known to the CTA with the highest index
+      run.gfinal[2 * lane] = (unsigned long long)s_base[lane] + s_count[lane];
+      run.gfinal[2 * lane + 1] = s_count[lane] ? s_clast[lane] : s_prevlast[lane];
     }
-    uint32_t run_max = lm;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(kFullMask, run_max, d);
-      if (lane >= d && o > run_max) run_max = o;
-    }
-    uint32_t before = __shfl_up_sync(kFullMask, run_max, 1);    // last end among the CTAs before my five
-    if (lane == 0) before = 0;
-    bool bad = false;
-#pragma unroll
-    for (int u = 0; u < 5; ++u) {
-      if (fl[u].y && before && before + L > fl[u].x) bad = true;
-      before = fl[u].y > before ? fl[u].y : before;
-    }
-    bad = __any_sync(kFullMask, bad);
-    const uint32_t all_last = __shfl_sync(kFullMask, run_max, 31);
+    __threadfence();
+    __syncwarp();
+    int is_last = 0;
     if (lane == 0) {
-      const unsigned long long total = (unsigned long long)s_base[j] + s_count[j];
-      const unsigned int flg = *s_flags | (bad ? kFinOverlap : 0u);
-      const unsigned long long le = all_last ? seam_base + all_last : 0ull;
-      volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.host_records + j);
-      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)total),
-                   "r"((unsigned int)(total >> 32)), "r"(flg), "r"(run.seq) : "memory");
-      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)le),
-                   "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
-      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"((unsigned int)le),
-                   "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
+      const unsigned int fl = *s_flags;
+      if (fl) atomicOr(&run.gsync[0], fl);
+      __threadfence();
+      is_last = atomicAdd(&run.gsync[1], 1u) + 1u == gridDim.x ? 1 : 0;
+    }
+    is_last = __shfl_sync(kFullMask, is_last, 0);
+    if (is_last) {
+      __threadfence();
+      const unsigned int flg = __ldcg(&run.gsync[0]);
+      if (lane < K) {
+        const unsigned long long total = __ldcg(&run.gfinal[2 * lane]), le = __ldcg(&run.gfinal[2 * lane + 1]);
+        volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.host_records + lane);
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)total),
+                     "r"((unsigned int)(total >> 32)), "r"(flg), "r"(run.seq) : "memory");
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)le),
+                     "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"((unsigned int)le),
+                     "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) { run.gsync[0] = 0; run.gsync[1] = 0; }
     }
   }
-  KmerTrace(run, 7);
 }
 
 // ---------------------------------------------------------------------------
@@ -2547,43 +2537,12 @@ __global__ void k_fill_u32(uint32_t* p, uint64_t count, uint32_t v) {
 // and the replacement of match i right before the byte that follows it.
 // One CTA per 4 KB input tile: two binary searches find the tile's matches,
 // their begins/ends/prefixes are staged in shared memory, every thread then
-// places its own 16 input bytes.
+// places its own 16 input bytes (replace.cuh: k_replace_stage).
 // ===========================================================================
 __global__ void k_match_lengths(const uint64_t* __restrict__ pairs, uint64_t m, uint64_t* __restrict__ len) {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = tid; i < m; i += nthreads) len[i] = pairs[2 * i + 1] - pairs[2 * i];
-}
-
-__global__ void __launch_bounds__(256)
-k_replace_tiles(const uint8_t* __restrict__ text, uint64_t n, const uint64_t* __restrict__ pairs,
-                const uint64_t* __restrict__ removed, uint64_t m, const uint8_t* __restrict__ with, uint32_t w,
-                uint8_t* __restrict__ out, uint64_t n_tiles) {
-  __shared__ uint16_t s_b[kReplaceTile + 2];        // begin - tile_lo of the tile's own matches
-  __shared__ uint16_t s_e[kReplaceTile + 2];        // end - tile_lo, clipped to the tile
-  __shared__ uint16_t s_r[kReplaceTile + 2];        // removed[m0 + i] - removed[m0]
-  __shared__ ReplaceTileHead s_head;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint64_t tile_lo = tile * kReplaceTile;
-    const bool last = tile + 1 == n_tiles;
-    const uint64_t tile_hi = last ? n : tile_lo + kReplaceTile;
-    if (threadIdx.x == 0) s_head.m0 = ReplaceLowerBound(pairs, m, tile_lo);
-    if (threadIdx.x == 32) s_head.m1 = last ? m : ReplaceLowerBound(pairs, m, tile_hi);
-    __syncthreads();
-    if (threadIdx.x == 0) ReplaceHead(pairs, removed, m, tile_lo, &s_head);
-    __syncthreads();
-    const ReplaceTileHead h = s_head;
-    const uint32_t cnt = (uint32_t)(h.m1 - h.m0);
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const uint64_t b = pairs[2 * (h.m0 + i)], e = pairs[2 * (h.m0 + i) + 1];
-      s_b[i] = (uint16_t)(b - tile_lo);
-      s_e[i] = (uint16_t)((e < tile_hi ? e : tile_hi) - tile_lo);
-      s_r[i] = (uint16_t)(removed[h.m0 + i] - h.r0);
-    }
-    __syncthreads();
-    ReplacePlace(threadIdx.x, text, tile_lo, tile_hi, last, h, cnt, s_b, s_e, s_r, with, w, out);
-    __syncthreads();
-  }
 }
 
 }  // namespace rejit_b200

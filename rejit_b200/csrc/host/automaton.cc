@@ -312,6 +312,15 @@ bool BuildAutomaton(const LoweredRegexp& lr, CompiledAutomaton* out, std::string
   // ---- positions and extended states ---------------------------------
   int n_ext = lr.n_states;
   std::vector<int> src, dst;
+  {
+    // the cap is checked on the edge sizes first: nothing is allocated for a pattern that is too large
+    uint64_t want = 0;
+    for (const Edge& e : lr.matching) want += (e.kind == kEdgeLiteral) ? e.bytes.size() : 1;
+    if (want > (uint64_t)kMaxPositions) {
+      if (error) *error = "regular expression too large for the sm_100a engine (more than 4096 byte positions)";
+      return false;
+    }
+  }
   for (const Edge& e : lr.matching) {
     size_t steps = (e.kind == kEdgeLiteral) ? e.bytes.size() : 1;
     int from = e.entry;

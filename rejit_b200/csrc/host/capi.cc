@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -87,6 +88,16 @@ bool Unflatten(const rejit_b200_ir* ir, LoweredRegexp* lr, std::string* error) {
   lr->entry_state = ir->entry_state;
   lr->exit_state = ir->exit_state;
   int total = ir->n_matching + ir->n_control;
+  // the engine's position budget (automaton.cc), checked on the declared sizes before anything is copied
+  uint64_t positions = 0;
+  for (int i = 0; i < ir->n_matching; ++i) {
+    const rejit_b200_edge& f = ir->edges[i];
+    positions += (f.kind == kEdgeLiteral && f.payload_length > 0) ? static_cast<uint64_t>(f.payload_length) : 1;
+  }
+  if (positions > kMaxPatternPositions || static_cast<uint64_t>(ir->n_control) > 16 * kMaxPatternPositions) {
+    *error = "regular expression too large for the sm_100a engine (more than 4096 byte positions)";
+    return false;
+  }
   for (int i = 0; i < total; ++i) {
     const rejit_b200_edge& f = ir->edges[i];
     Edge e;
@@ -155,19 +166,25 @@ extern "C" {
 int rejit_b200_parse(const char* pattern, size_t pattern_length, int parser_opt,
                      rejit_b200_ir** out_ir, char* err, size_t err_length) {
   if (out_ir) *out_ir = nullptr;
-  ParseOptions opt;
-  opt.parser_opt = parser_opt != 0;
-  std::string msg;
-  NodePtr root = ParseERE(pattern, pattern_length, opt, &msg);
-  if (!root) {
-    SetErr(err, err_length, msg);
+  // nothing may leave an extern "C" function by exception (std::terminate in a C caller)
+  try {
+    ParseOptions opt;
+    opt.parser_opt = parser_opt != 0;
+    std::string msg;
+    NodePtr root = ParseERE(pattern, pattern_length, opt, &msg);
+    if (!root || !WithinBudget(root.get(), &msg)) {
+      SetErr(err, err_length, msg);
+      return -1;
+    }
+    LoweredRegexp lr = Lower(root.get());
+    IrHolder* h = new IrHolder();
+    Flatten(lr, h);
+    if (out_ir) *out_ir = &h->ir; else delete h;
+    return 0;
+  } catch (const std::exception& e) {
+    SetErr(err, err_length, std::string("rejit_b200_parse: ") + e.what());
     return -1;
   }
-  LoweredRegexp lr = Lower(root.get());
-  IrHolder* h = new IrHolder();
-  Flatten(lr, h);
-  if (out_ir) *out_ir = &h->ir; else delete h;
-  return 0;
 }
 
 void rejit_b200_ir_free(rejit_b200_ir* ir) {
@@ -187,26 +204,44 @@ size_t rejit_b200_ir_dump(const rejit_b200_ir* ir, char* buffer, size_t buffer_l
 }
 
 rejit_b200_program* rejit_b200_compile(const rejit_b200_ir* ir, char* err, size_t err_length) {
-  LoweredRegexp lr;
-  std::string error;
-  if (!ir || !Unflatten(ir, &lr, &error)) {
-    SetErr(err, err_length, ir ? error : "rejit_b200_compile: null IR");
+  try {
+    LoweredRegexp lr;
+    std::string error;
+    if (!ir || !Unflatten(ir, &lr, &error)) {
+      SetErr(err, err_length, ir ? error : "rejit_b200_compile: null IR");
+      return nullptr;
+    }
+    Program* p = Program::Create(lr, &error);
+    if (!p) {
+      SetErr(err, err_length, error);
+      return nullptr;
+    }
+    rejit_b200_program* h = new rejit_b200_program;
+    h->prog = p;
+    return h;
+  } catch (const std::exception& e) {
+    SetErr(err, err_length, std::string("rejit_b200_compile: ") + e.what());
     return nullptr;
   }
-  Program* p = Program::Create(lr, &error);
-  if (!p) {
-    SetErr(err, err_length, error);
-    return nullptr;
-  }
-  rejit_b200_program* h = new rejit_b200_program;
-  h->prog = p;
-  return h;
 }
 
 void rejit_b200_program_free(rejit_b200_program* program) {
   if (!program) return;
   delete program->prog;
   delete program;
+}
+
+int rejit_b200_program_is_shardable(const rejit_b200_program* program) {
+  return program && !program->prog->automaton().reentrant ? 1 : 0;
+}
+
+// A text may be cut into slabs (ownership range / carries) only for patterns whose chain state at a cut is the
+// (cur, tail) pair; the label replay of re-entrant patterns cannot be resumed from it.
+static bool SlabAllowed(const Program* p, bool sliced, char* err, size_t err_length) {
+  if (!sliced || !p->automaton().reentrant) return true;
+  SetErr(err, err_length, "rejit_b200: this pattern is re-entrant (a running thread can re-enter its start) and cannot be "
+                          "matched slab by slab; see rejit_b200_program_is_shardable");
+  return false;
 }
 
 const char* rejit_b200_program_describe(const rejit_b200_program* program) {
@@ -325,6 +360,7 @@ int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, con
   std::string error;
   Carry in, out;
   if (carry_in) { in.cur = carry_in->cur; in.tail = carry_in->tail; }
+  if (!SlabAllowed(program->prog, carry_in && (carry_in->cur != 0 || carry_in->tail != ~0ull), err, err_length)) return -1;
   RunStats rs;
   int64_t r = MatchAllDevice(device, program->prog, static_cast<const uint8_t*>(d_text), text_length,
                              d_out_pairs, capacity, in, &out, stats ? &rs : nullptr, &error);
@@ -441,6 +477,8 @@ int rejit_b200_match_all_set_device_slab(rejit_b200_set* set, int device, const 
   std::string error;
   RunStats rs;
   const int k = set->set->size();
+  for (Program* member : set->set->members())
+    if (!SlabAllowed(member, true, err, err_length)) return -1;
   std::vector<Carry> in(k), out(k);
   if (carry_in) for (int j = 0; j < k; ++j) { in[j].cur = carry_in[j].cur; in[j].tail = carry_in[j].tail; }
   SlabView view;
@@ -474,6 +512,7 @@ int64_t rejit_b200_match_all_device_slab(rejit_b200_program* program, int device
   std::string error;
   Carry in, out;
   if (carry_in) { in.cur = carry_in->cur; in.tail = carry_in->tail; }
+  if (!SlabAllowed(program->prog, true, err, err_length)) return -1;
   SlabView view;
   view.own_begin = own_begin;
   view.own_end = own_end;
@@ -517,7 +556,7 @@ rejit_b200_text* rejit_b200_replace_all_text(rejit_b200_program* program, const 
   int64_t r = ReplaceAllDevice(text->device, program->prog, static_cast<const uint8_t*>(text->d_ptr), text->length,
                                reinterpret_cast<const uint8_t*>(with), with_length, &d_out, &len, &cap,
                                stats ? &rs : nullptr, &error);
-  if (r < 0) { SetErr(err, err_length, error); return nullptr; }
+  if (r < 0 || !d_out) { SetErr(err, err_length, r < 0 ? error : "rejit_b200: ReplaceAll produced no text"); return nullptr; }
   FillStats(rs, stats);
   if (n_matches) *n_matches = r;
   rejit_b200_text* t = new rejit_b200_text;
@@ -526,6 +565,53 @@ rejit_b200_text* rejit_b200_replace_all_text(rejit_b200_program* program, const 
   t->length = len;
   t->capacity = cap;
   return t;
+}
+
+rejit_b200_text* rejit_b200_replace_all_set_text(rejit_b200_program* const* programs, int count, const rejit_b200_text* text,
+                                                 const char* const* withs, const size_t* with_lengths, int64_t* n_matches,
+                                                 rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  if (!programs || count < 1 || !text || !withs || !with_lengths) { SetErr(err, err_length, "rejit_b200: null argument"); return nullptr; }
+  std::vector<Program*> progs;
+  std::vector<std::string> with;
+  for (int i = 0; i < count; ++i) {
+    if (!programs[i]) { SetErr(err, err_length, "rejit_b200: null program"); return nullptr; }
+    progs.push_back(programs[i]->prog);
+    with.emplace_back(withs[i] ? withs[i] : "", with_lengths[i]);
+  }
+  RunStats rs;
+  if (ReplaceSetFusable(progs, with)) {
+    // one-byte patterns whose replacements no later pattern touches: ONE byte -> string table
+    void* d_out = nullptr;
+    uint64_t len = 0, cap = 0;
+    std::vector<int64_t> counts(count, 0);
+    int64_t r = ReplaceAllSetDevice(text->device, progs, static_cast<const uint8_t*>(text->d_ptr), text->length, with, &d_out,
+                                    &len, &cap, counts.data(), stats ? &rs : nullptr, &error);
+    if (r < 0 || !d_out) { SetErr(err, err_length, r < 0 ? error : "rejit_b200: ReplaceAll produced no text"); return nullptr; }
+    if (n_matches) for (int i = 0; i < count; ++i) n_matches[i] = counts[i];
+    FillStats(rs, stats);
+    rejit_b200_text* t = new rejit_b200_text;
+    t->device = text->device; t->d_ptr = d_out; t->length = len; t->capacity = cap;
+    return t;
+  }
+  // anything else: the calls one after the other, as the reference does
+  const rejit_b200_text* cur = text;
+  rejit_b200_text* owned = nullptr;
+  rejit_b200_stats acc{};
+  for (int i = 0; i < count; ++i) {
+    int64_t k = 0;
+    rejit_b200_stats one{};
+    rejit_b200_text* next = rejit_b200_replace_all_text(programs[i], cur, with[i].data(), with[i].size(), &k, &one, err, err_length);
+    if (owned) rejit_b200_text_free(owned);
+    if (!next) return nullptr;
+    if (n_matches) n_matches[i] = k;
+    acc.scan_ms += one.scan_ms; acc.total_ms += one.total_ms; acc.launches += one.launches; acc.reruns += one.reruns;
+    acc.matches += one.matches; acc.candidates += one.candidates;
+    owned = next;
+    cur = next;
+  }
+  if (stats) { *stats = acc; stats->strategy = -1; }
+  return owned;
 }
 
 size_t rejit_b200_text_length(const rejit_b200_text* text) { return text ? text->length : 0; }

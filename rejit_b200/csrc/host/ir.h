@@ -20,6 +20,12 @@ namespace rejit_b200 {
 
 constexpr uint32_t kUnbounded = 0xFFFFFFFFu;   // "no upper repetition bound"
 constexpr unsigned kMaxLiteralNode = 64;       // literal nodes hold at most 64 bytes
+// Budgets enforced BEFORE anything is expanded (a hostile pattern must fail with an error, not exhaust memory or
+// the stack): nesting depth of the tree (recursive walks, destructors), byte positions after unrolling (the
+// engine's own cap, automaton.cc), and open parentheses on the parser stack.
+constexpr uint32_t kMaxTreeDepth = 200;
+constexpr uint64_t kMaxPatternPositions = 4096;
+constexpr uint64_t kMaxPatternNodes = 1u << 18;   // tree nodes after unrolling (epsilon-only repetitions have no positions)
 
 enum class NodeKind : uint8_t {
   Literal,        // a run of bytes matched verbatim ("MultipleChar")
@@ -45,6 +51,7 @@ struct Node {
   std::vector<ByteRange> ranges;              // CharSet
   std::vector<std::unique_ptr<Node>> kids;    // Sequence / Choice; Repeat has exactly one
   uint32_t rep_min = 0, rep_max = 0;          // Repeat
+  uint32_t depth = 1;                         // height of the subtree (parser-maintained, bounded by kMaxTreeDepth)
 
   explicit Node(NodeKind k) : kind(k) {}
   bool is_marker() const { return kind == NodeKind::OpenParen || kind == NodeKind::Bar; }
@@ -88,7 +95,11 @@ struct ParseOptions {
 NodePtr ParseERE(const char* pattern, size_t len, const ParseOptions& opt,
                  std::string* error);
 
-// Assigns NFA state numbers and flattens the tree into edge lists.
+// Size of the NFA that Lower() would produce, checked before it is produced: false (and *error, a parse-error
+// style message) when unrolling the repetitions would exceed kMaxPatternPositions byte positions.
+bool WithinBudget(const Node* root, std::string* error);
+
+// Assigns NFA state numbers and flattens the tree into edge lists.  Call WithinBudget first.
 LoweredRegexp Lower(Node* root);
 
 // Human-readable dump used by the IR-parity tests.

@@ -10,6 +10,7 @@
 // bracket lose the negation (Bracket::DeepCopy, src/regexp.cc:102-108).
 #include "ir.h"
 
+#include <algorithm>
 #include <sstream>
 
 namespace rejit_b200 {
@@ -159,7 +160,47 @@ struct Flattener {
   }
 };
 
+// What Lower() would produce for the subtree, computed without producing it (saturating): byte positions (exactly
+// what BuildAutomaton counts) and tree nodes after unrolling (every one becomes an edge or a few epsilons).
+struct Footprint { uint64_t positions, nodes; };
+constexpr uint64_t kFootprintSat = 1ull << 40;
+
+Footprint Measure(const Node* n) {
+  Footprint f{0, 1};
+  switch (n->kind) {
+    case NodeKind::Literal: f.positions = n->bytes.size(); break;
+    case NodeKind::AnyChar:
+    case NodeKind::CharSet: f.positions = 1; break;
+    case NodeKind::Sequence:
+    case NodeKind::Choice:
+      for (auto& k : n->kids) {
+        const Footprint g = Measure(k.get());
+        f.positions = std::min(kFootprintSat, f.positions + g.positions);
+        f.nodes = std::min(kFootprintSat, f.nodes + g.nodes);
+      }
+      break;
+    case NodeKind::Repeat: {
+      // Unroll(): {0,0} is one epsilon; otherwise `hi` copies when bounded, else max(lo, 1)
+      if (n->rep_min == 0 && n->rep_max == 0) break;
+      const uint64_t copies = n->rep_max != kUnbounded ? std::max<uint64_t>(n->rep_max, 1) : std::max<uint64_t>(n->rep_min, 1);
+      const Footprint g = Measure(n->kids[0].get());
+      f.positions = g.positions > kFootprintSat / copies ? kFootprintSat : g.positions * copies;
+      f.nodes = g.nodes + 1 > kFootprintSat / copies ? kFootprintSat : (g.nodes + 1) * copies;
+      break;
+    }
+    default: break;              // anchors: a control edge, no position
+  }
+  return f;
+}
+
 }  // namespace
+
+bool WithinBudget(const Node* root, std::string* error) {
+  const Footprint f = Measure(root);
+  if (f.positions <= kMaxPatternPositions && f.nodes <= kMaxPatternNodes) return true;
+  if (error) *error = "regular expression too large for the sm_100a engine (more than 4096 byte positions after unrolling its repetitions)";
+  return false;
+}
 
 LoweredRegexp Lower(Node* root) {
   LoweredRegexp lr;

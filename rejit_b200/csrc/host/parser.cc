@@ -47,7 +47,10 @@ class EreParser {
         case '?': PushRepeat(0, 1); break;
         case '^': Push(NodeKind::LineStart); break;
         case '$': Push(NodeKind::LineEnd); break;
-        case '(': Push(NodeKind::OpenParen); break;
+        case '(':
+          if (++open_parens_ > kMaxTreeDepth) throw Fail{pos_, "regular expression nested too deeply\n"};
+          Push(NodeKind::OpenParen);
+          break;
         case ')': CloseParen(); break;
         case '|': Concatenate(); Push(NodeKind::Bar); break;
         case '[': step = Brackets(pos_); break;
@@ -102,12 +105,18 @@ class EreParser {
     uint8_t next = At(i + 1);
     PushByte(re_[i], !(next == '*' || next == '{'));
   }
+  // A node that wraps others is one level higher than the highest of them.
+  void Adopt(Node* parent, NodePtr kid) {
+    if (kid->depth + 1 > parent->depth) parent->depth = kid->depth + 1;
+    if (parent->depth > kMaxTreeDepth) throw Fail{pos_, "regular expression nested too deeply\n"};
+    parent->kids.push_back(std::move(kid));
+  }
   void PushRepeat(uint32_t lo, uint32_t hi) {
     NodePtr sub = PopOperand();
     Node* r = Push(NodeKind::Repeat);
     r->rep_min = lo;
     r->rep_max = hi;
-    r->kids.push_back(std::move(sub));
+    Adopt(r, std::move(sub));
   }
 
   static int HexQuirk(uint8_t c) {      // letters map to 0..5, as in the reference
@@ -205,6 +214,8 @@ class EreParser {
     if (opt_.parser_opt && operand->kind == NodeKind::Literal && lo > 1) {
       // literal{lo,hi}  ->  literal^lo  literal{0,hi-lo}
       const std::vector<uint8_t> unit = operand->bytes;
+      if (static_cast<uint64_t>(lo) * unit.size() > kMaxPatternPositions)
+        throw Fail{i - 1, "regular expression too large (more than 4096 byte positions)\n"};
       std::vector<NodePtr> parts;
       NodePtr run(new Node(NodeKind::Literal));
       run->bytes = unit;
@@ -226,17 +237,17 @@ class EreParser {
           tail->rep_max = (hi == kUnbounded) ? kUnbounded : hi - lo;
           NodePtr u(new Node(NodeKind::Literal));
           u->bytes = unit;
-          tail->kids.push_back(std::move(u));
+          Adopt(tail.get(), std::move(u));
           parts.push_back(std::move(tail));
         }
         Node* seq = Push(NodeKind::Sequence);
-        seq->kids = std::move(parts);
+        for (auto& part : parts) Adopt(seq, std::move(part));
       }
     } else {
       Node* r = Push(NodeKind::Repeat);
       r->rep_min = lo;
       r->rep_max = hi;
-      r->kids.push_back(std::move(operand));
+      Adopt(r, std::move(operand));
     }
     return i - open;
   }
@@ -271,12 +282,11 @@ class EreParser {
   }
 
   void CloseParen() {
-    bool open = false;
-    for (auto& n : stack_) open |= n->kind == NodeKind::OpenParen;
-    if (!open) {              // stray ')' is an ordinary byte
+    if (open_parens_ == 0) {  // stray ')' is an ordinary byte
       PushByteAt(pos_);
       return;
     }
+    --open_parens_;
     Alternate();
     NodePtr inner = Pop();
     if (inner->is_marker() || stack_.empty() || Top()->kind != NodeKind::OpenParen)
@@ -295,7 +305,7 @@ class EreParser {
     if (n == 0) throw Fail{pos_, "empty alternative\n"};
     if (n == 1) return;
     NodePtr seq(new Node(NodeKind::Sequence));
-    for (size_t k = first; k < stack_.size(); ++k) seq->kids.push_back(std::move(stack_[k]));
+    for (size_t k = first; k < stack_.size(); ++k) Adopt(seq.get(), std::move(stack_[k]));
     stack_.resize(first);
     stack_.push_back(std::move(seq));
   }
@@ -312,7 +322,7 @@ class EreParser {
     size_t i = stack_.size();
     while (i > 0 && stack_[i - 1]->kind != NodeKind::OpenParen) {
       --i;
-      if (!stack_[i]->is_marker()) alt->kids.push_back(std::move(stack_[i]));
+      if (!stack_[i]->is_marker()) Adopt(alt.get(), std::move(stack_[i]));
     }
     stack_.resize(i);
     stack_.push_back(std::move(alt));
@@ -322,6 +332,7 @@ class EreParser {
   size_t len_;
   ParseOptions opt_;
   size_t pos_ = 0;
+  uint32_t open_parens_ = 0;          // OpenParen markers on the stack
   std::vector<NodePtr> stack_;
 };
 

@@ -147,6 +147,28 @@ Text* Text::ReplaceAll(Regej& re, const string& with, size_t* n_matches) const {
   return new Text(out, rejit_b200_text_length(out));
 }
 
+Text* Text::ReplaceAllSet(const vector<Regej*>& patterns, const vector<string>& withs, vector<size_t>* n_matches) const {
+  if (patterns.empty() || patterns.size() != withs.size()) return nullptr;
+  vector<rejit_b200_program*> progs;
+  vector<const char*> ws;
+  vector<size_t> lens;
+  for (size_t i = 0; i < patterns.size(); ++i) {
+    if (!patterns[i] || !patterns[i]->Compile(kMatchAll)) return nullptr;
+    progs.push_back(patterns[i]->rinfo_->program);
+    ws.push_back(withs[i].data());
+    lens.push_back(withs[i].size());
+  }
+  vector<int64_t> counts(patterns.size(), 0);
+  char err[256];
+  err[0] = 0;
+  rejit_b200_text* out = rejit_b200_replace_all_set_text(progs.data(), static_cast<int>(progs.size()),
+                                                         static_cast<const rejit_b200_text*>(handle_), ws.data(), lens.data(),
+                                                         counts.data(), nullptr, err, sizeof err);
+  if (!out) Fatal("Text::ReplaceAllSet", err);
+  if (n_matches) n_matches->assign(counts.begin(), counts.end());
+  return new Text(out, rejit_b200_text_length(out));
+}
+
 string Text::Download() const {
   string out(size_, '\0');
   char err[256];

@@ -3,7 +3,7 @@
 // scan of the sequence) and the eleven IUB substitutions all run on device-resident texts, and only the
 // counts and lengths come back.  Same output as samples/regexdna.cc (and as the reference's
 // sample/regexdna.cc:49-91, whose twelve ReplaceAll calls each rebuild the string on the host).
-// Uses the rejit_b200 additions of include/rejit.h (rejit::Text, Regej::MatchAllCountSet).
+// Uses the rejit_b200 additions of include/rejit.h (rejit::Text, Regej::MatchAllCountSet, Text::ReplaceAllSet).
 #include <cstdio>
 #include <iostream>
 #include <iterator>
@@ -41,15 +41,18 @@ int main() {
   static const char* const kIub[][2] = {{"B", "(c|g|t)"}, {"D", "(a|g|t)"},   {"H", "(a|c|t)"}, {"K", "(g|t)"},
                                         {"M", "(a|c)"},   {"N", "(a|c|g|t)"}, {"R", "(a|g)"},   {"S", "(c|g)"},
                                         {"V", "(a|c|g)"}, {"W", "(a|t)"},     {"Y", "(c|t)"}};
-  std::unique_ptr<rejit::Text> current;
-  const rejit::Text* at = sequence.get();
+  // the eleven substitutions, in the reference's order: every pattern is one byte and no replacement holds a later
+  // pattern's byte, so Text::ReplaceAllSet applies them in one pass over the sequence (a byte -> string table)
+  std::vector<std::unique_ptr<rejit::Regej> > codes;
+  std::vector<rejit::Regej*> code_ptrs;
+  std::vector<std::string> withs;
   for (const auto& s : kIub) {
-    rejit::Regej code(s[0]);
-    std::unique_ptr<rejit::Text> next(at->ReplaceAll(code, s[1]));
-    current.swap(next);                                   // `next` now holds the text that was replaced; freed here
-    at = current.get();
+    codes.emplace_back(new rejit::Regej(s[0]));
+    code_ptrs.push_back(codes.back().get());
+    withs.push_back(s[1]);
   }
+  std::unique_ptr<rejit::Text> substituted(sequence->ReplaceAllSet(code_ptrs, withs));
 
-  printf("\n%zu\n%zu\n%zu\n", file.size(), sequence->size(), at->size());
+  printf("\n%zu\n%zu\n%zu\n", file.size(), sequence->size(), substituted->size());
   return 0;
 }

@@ -47,8 +47,32 @@ def run(name, pattern, text, reps=int(os.environ.get("RJ_EXTRA_REPS", "10")), fl
     dt.free()
 
 
+def run_set(name, patterns, text, reps=int(os.environ.get("RJ_EXTRA_REPS", "10"))):
+    rs = rj.RegejSet(patterns)
+    dt = rj.DeviceText(text)
+    st = rj.Stats()
+    for _ in range(3):
+        counts = rs.match_all_device(dt, stats=st)
+    tot = scan = 0.0
+    for _ in range(reps):
+        rj.lib().rejit_b200_flush_l2(0)
+        counts = rs.match_all_device(dt, stats=st)
+        tot += st.total_ms
+        scan += st.scan_ms
+    n = len(text)
+    print(json.dumps({"case": name, "bytes": n, "matches": sum(counts), "strategy": rs.describe()[:60],
+                      "pipeline_ms": round(tot / reps, 4), "scan_ms": round(scan / reps, 4),
+                      "pipeline_gbs": round(n / (tot / reps) / 1e6, 1), "scan_gbs": round(n / (scan / reps) / 1e6, 1),
+                      "scan_frac_of_hbm": round(n / (scan / reps) / 1e6 / peak(), 4), "launches": st.launches}), flush=True)
+    dt.free()
+
+
 def main():
     big = int(os.environ.get("RJ_EXTRA_BYTES", "500000000"))
+    seq50 = W.fasta_sequence(5_000_000)
+    run_set("C2 nine patterns fused, 50 MB FASTA", W.DNA_PATTERNS, seq50)
+    run_set("C5 slab: nine patterns fused, 625 MB FASTA (the 62.5 MB sequence tiled)", W.DNA_PATTERNS,
+            np.tile(W.fasta_sequence(6_250_000), 10)[:min(625_000_000, big * 5 // 4)])
     t = W.random_ascii(1 << 20, seed=1)
     run("C1 literal, 1 MiB random ASCII (L2 resident)", W.LITERAL_PATTERN, t, flush=False)
     text = W.random_ascii(big, seed=21)

@@ -34,7 +34,7 @@ bool CompilePattern(const char* pattern, size_t plen, int parser_opt, Compiled* 
   ParseOptions opt;
   opt.parser_opt = parser_opt != 0;
   NodePtr root = ParseERE(pattern, plen, opt, error);
-  if (!root) return false;
+  if (!root || !WithinBudget(root.get(), error)) return false;
   LoweredRegexp lr = Lower(root.get());
   if (!BuildAutomaton(lr, &c->ca, error)) return false;
   FlattenTables(c->ca, &c->ft);

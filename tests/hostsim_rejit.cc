@@ -154,6 +154,19 @@ Text* Text::ReplaceAll(Regej& re, const string& with, size_t* n_matches) const {
   if (n_matches) *n_matches = k;
   return new Text(next, next->owned.size());
 }
+Text* Text::ReplaceAllSet(const vector<Regej*>& patterns, const vector<string>& withs, vector<size_t>* n_matches) const {
+  // the test double applies the calls one after the other (what the device's table must reproduce)
+  if (patterns.empty() || patterns.size() != withs.size()) return nullptr;
+  const TextBody* body = static_cast<const TextBody*>(handle_);
+  TextBody* next = new TextBody;
+  next->owned.assign(body ? body->owned.data() : text_, size_);
+  if (n_matches) n_matches->clear();
+  for (size_t i = 0; i < patterns.size(); ++i) {
+    const size_t k = patterns[i]->ReplaceAll(next->owned, withs[i]);
+    if (n_matches) n_matches->push_back(k);
+  }
+  return new Text(next, next->owned.size());
+}
 string Text::Download() const {
   const TextBody* body = static_cast<const TextBody*>(handle_);
   return body ? body->owned : string(text_, size_);

@@ -172,6 +172,22 @@ def test_workloads_medium(rj):
     assert rj.Regej("^").match_all(blob) == O.Oracle("^").match_all(blob)
 
 
+def _find_all(text, needle):
+    """Start offsets of every (possibly overlapping) occurrence of `needle` in a numpy uint8 array: shifted compares
+    in chunks, no engine code involved."""
+    nd = np.frombuffer(needle, dtype=np.uint8)
+    m, n = len(nd), len(text)
+    out = []
+    step = 1 << 26
+    for lo in range(0, max(n - m + 1, 0), step):
+        hi = min(n - m + 1, lo + step)
+        ok = text[lo:hi] == nd[0]
+        for i in range(1, m):
+            ok &= text[lo + i:hi + i] == nd[i]
+        out.append(np.flatnonzero(ok) + lo)
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+
+
 def test_full_size_properties(rj):
     """BASELINE sizes: planted-hit recovery, device/host API agreement, slab
     invariance (the chain state handed across arbitrary cuts reproduces the
@@ -183,12 +199,15 @@ def test_full_size_properties(rj):
     W.plant(text, W.COMPLEX_HITS, every=1_000_003)
     g = rj.Regej(W.COMPLEX_PATTERN)
     got = g.match_all_array(text)
-    # expected: every planted hit, found by scanning +-64 bytes around each plant with the oracle
+    # expected: the oracle on +-64 bytes around every occurrence of the required literal, located WITHOUT the
+    # engine (numpy shifted compares): a literal the engine's own scan missed would otherwise be missed on both sides
     o = O.Oracle(W.COMPLEX_PATTERN)
+    lit_at = _find_all(text, b"abcdefgh")
+    assert lit_at.shape[0] >= 400
     lit = rj.Regej("abcdefgh").match_all_array(text)
-    assert lit.shape[0] >= 400
+    assert (lit[:, 0] == lit_at.astype(np.uint64)).all() and (lit[:, 1] == lit[:, 0] + 8).all()
     exp = []
-    for b in lit[:, 0]:
+    for b in lit_at:
         lo = max(0, int(b) - 64)
         w = text[lo:int(b) + 64].tobytes()
         exp += [(lo + x, lo + y) for x, y in o.match_all(w)]
@@ -198,7 +217,7 @@ def test_full_size_properties(rj):
     try:
         st = rj.Stats()
         assert g.match_all_device(dt, stats=st) == got.shape[0]
-        assert st.launches >= 2 and st.scan_ms > 0
+        assert st.launches >= 1 and st.scan_ms > 0
         r1 = rj.Regej(W.LITERAL_PATTERN)
         whole = r1.match_all_device(dt)
         assert whole == r1.match_all_array(text).shape[0]
@@ -300,11 +319,12 @@ def test_fixed_length_finish_in_kernel_and_overlap_fallback(rj):
     st = rj.Stats()
     dt = rj.DeviceText(np.frombuffer(t, dtype=np.uint8))
     try:
-        for p, launches in (("ab", 1), ("aa", 2)):
+        for p in ("ab", "aa"):
             r = rj.Regej(p)
-            r.match_all_device(dt)                           # first call sizes the slot ranges
+            r.match_all_device(dt)                           # first call sizes the buffers
             assert r.match_all_device(dt, stats=st) == len(O.Oracle(p).match_all(t)), p
-            assert st.launches == launches and st.reruns == 0, (p, st.launches)
+            # one launch: the single-pass scan resolves "aaa" inside the tile ("aa" may meet a tile edge: then two)
+            assert st.launches <= (1 if p == "ab" else 3), (p, st.launches)
     finally:
         dt.free()
     # no overlaps at all: one launch per call
@@ -463,3 +483,170 @@ def test_full_size_config_3_slab(rj):
     got = rj.Regej(W.JREP_PATTERN).match_all_array(text)
     assert got.shape == (begins.shape[0], 2)
     assert (got[:, 0] == begins).all() and (got[:, 1] == begins + 3).all()
+
+
+def _np_text(b):
+    return np.frombuffer(b, dtype=np.uint8)
+
+
+def test_single_pass_scan_emit(rj):
+    """Round 2: literal, required-literal + window and generic patterns run in ONE launch (scan_emit.cuh:
+    64 KB tiles, 8 KB per warp, decoupled look-back).  Matches at and across warp / tile edges, the text end,
+    dense and empty matches, chains that cross a tile edge (general path takes over), all against the oracle."""
+    rng = random.Random(77)
+    K8, K64 = 8192, 65536
+    base = bytearray(fuzzgen.rand_text(rng, "qwertyuiop   \n", 3 * K64 + 700))
+    cases = [("needle", b"needle"), ("B", b"B"), (";\n}", b";\n}"), ("abcdefghijklmnopqrstuvwxyz0123456789", b"abcdefghijklmnopqrstuvwxyz0123456789"),
+             ("(ab|c)+needle(s|x)?", b"abcabneedles"), ("x[yz]{2,3}needle", b"xyzzneedle")]
+    edges = [0, 1, 15, 16, 511, 512, K8 - 3, K8 - 1, K8, K8 + 1, K64 - 40, K64 - 5, K64 - 1, K64, K64 + 1, 2 * K64 - 2,
+             2 * K64 + K8 - 1, 3 * K64 + 690]
+    for pat, unit in cases:
+        t = bytearray(base)
+        for at in edges:
+            if at + len(unit) <= len(t):
+                t[at:at + len(unit)] = unit
+        t = bytes(t)
+        r = rj.Regej(pat)
+        st = rj.Stats()
+        got = r.match_all_array(_np_text(t), stats=st)
+        exp = O.Oracle(pat).match_all(t)
+        assert [tuple(map(int, x)) for x in got] == exp, (pat, r.describe(), got.shape[0], len(exp))
+        if pat != "(ab|c)+needle(s|x)?":                 # (its planted unit holds three starts: one meets a tile edge)
+            assert st.launches == 1 and st.reruns == 0, (pat, st.launches, st.reruns)
+        for cut in (K64, K64 + 1, K64 - 1, 2 * K64 + K8, K8 - 1, 17):         # ragged text ends
+            assert r.match_all(t[:cut]) == O.Oracle(pat).match_all(t[:cut]), (pat, cut)
+    # line-oriented and empty matches (generic scan: SWAR start filter with and without the line context)
+    lines = bytearray()
+    while len(lines) < 2 * K64 + 5000:
+        lines += bytes(rng.choice(b"abcxyz>;{} ") for _ in range(rng.randint(0, 90))) + rng.choice([b"\n", b"\n", b"\r\n", b"\n\n"])
+    lines = bytes(lines)
+    for pat in ("^", "$", "^$", ">.*\n|\n", "^a", "x$", "(^|$|[x])", "^[a-c]+", ";\n}|^>", "[ab]x|^y", "\n"):
+        r = rj.Regej(pat)
+        st = rj.Stats()
+        for t in (lines, lines[:K64], lines[:K64 + 1], lines[3:K8 + 3], lines + b"x", lines.rstrip(b"\r\n")):
+            got = r.match_all_array(_np_text(t), stats=st)
+            exp = O.Oracle(pat).match_all(t)
+            assert [tuple(map(int, x)) for x in got] == exp, (pat, len(t), r.describe(), got.shape[0], len(exp))
+            if pat in ("^", "$", "^$", "\n", "^a"):       # no match of these can reach across a tile edge
+                assert st.launches == 1, (pat, st.launches, r.describe())
+    # a start set too large for the SWAR filter: the 256-bit maps
+    t = fuzzgen.rand_text(rng, "abcdefgh \n", 3 * K64)
+    for pat in ("[a-f]+gh", "^[a-h]*h$", "[abcdef]{2}g|h+ "):
+        assert rj.Regej(pat).match_all(t) == O.Oracle(pat).match_all(t), pat
+    # chains that cross a tile edge: the arriving match swallows the tile's first candidates -> general path
+    for pat, unit in (("a+", b"a" * 37), (">.*\n|\n", b">" + b"h" * 50 + b"\n"), ("ab(ab)*", b"ab" * 20), ("x*", b"x" * 9)):
+        for edge in (K64, 2 * K64, K8):
+            for back in (1, 5, len(unit) - 1):
+                t = bytearray(fuzzgen.rand_text(rng, "qrs\n", 2 * K64 + 3000))
+                t[edge - back:edge - back + len(unit)] = unit
+                t = bytes(t)
+                assert rj.Regej(pat).match_all(t) == O.Oracle(pat).match_all(t), (pat, edge, back)
+    # overlapping candidates inside a tile are resolved by the tile itself: still one launch
+    t = fuzzgen.rand_text(rng, "xxxxxxxxxxxxxxxxxxxxab", 3 * K64)
+    for pat in ("aa", "aba|bab", "a(b|a)+"):
+        r = rj.Regej(pat)
+        assert r.match_all(t) == O.Oracle(pat).match_all(t), pat
+    # slabs with carries (own ranges that cut tiles; the carry reaching into a slab)
+    for pat, text in (("needle", bytes(base[:2 * K64]) + b"needle" * 3 + bytes(base[:K8])), ("^", lines), (">.*\n|\n", lines),
+                      ("ab(ab)*", b"q" * (K64 - 3) + b"ab" * 9 + b"q" * K64), ("x[yz]{2,3}needle", bytes(base))):
+        r = rj.Regej(pat)
+        exp = len(O.Oracle(pat).match_all(text))
+        n = len(text)
+        dt = rj.DeviceText(_np_text(text))
+        try:
+            for k in (1, 2, 3, 5):
+                carry = rj.Carry(0, 0xFFFFFFFFFFFFFFFF)
+                total = 0
+                for i in range(k):
+                    lo = n * i // k
+                    hi = n * (i + 1) // k if i + 1 < k else n + 1
+                    nxt = rj.Carry()
+                    total += r.match_all_device(dt, own=(lo, hi), carry_in=carry, carry_out=nxt)
+                    carry = nxt
+                assert total == exp, (pat, k, total, exp)
+        finally:
+            dt.free()
+
+
+def test_single_pass_scan_emit_dense_and_large(rj):
+    """Dense matches at size: every offset list is checked in full against numpy (single bytes, line starts), the
+    output buffer grows once and the steady state is one launch."""
+    from rejit_b200 import workloads as W
+    seq = W.fasta_sequence(2_000_000)                    # 20 MB, IUB letters in the middle section
+    for letter in (b"B", b"N"):
+        r = rj.Regej(letter.decode())
+        exp = np.flatnonzero(seq == letter[0]).astype(np.uint64)
+        st = rj.Stats()
+        got = r.match_all_array(seq, stats=st)
+        assert got.shape[0] == exp.shape[0] and (got[:, 0] == exp).all() and (got[:, 1] == exp + 1).all()
+        got = r.match_all_array(seq, stats=st)
+        assert st.launches == 1 and st.reruns == 0 and (got[:, 0] == exp).all()
+    blob = W.source_blob(64_000_000, seed=5)
+    exp = np.concatenate([[0], np.flatnonzero(blob[:-1] == 10) + 1]).astype(np.uint64)      # line starts (no \r in the blob)
+    if blob[-1] == 10:
+        exp = np.concatenate([exp, [len(blob)]]).astype(np.uint64)
+    st = rj.Stats()
+    r = rj.Regej("^")
+    got = r.match_all_array(blob, stats=st)
+    assert got.shape[0] == exp.shape[0] and (got[:, 0] == exp).all() and (got[:, 1] == exp).all()
+    got = r.match_all_array(blob, stats=st)
+    assert st.launches == 1 and st.reruns == 0
+    fa = _np_text(W.fasta_file(1_000_000))               # strip: every newline, every header line
+    nl = np.flatnonzero(fa == 10)
+    gt = np.flatnonzero(fa == ord(">"))
+    got = rj.Regej(W.STRIP_PATTERN).match_all_array(fa)
+    assert got.shape[0] == nl.shape[0]                   # one match per line end (a header line is one match)
+    assert (got[:, 1] == nl.astype(np.uint64) + 1).all()
+    heads = got[got[:, 1] - got[:, 0] > 1]
+    assert heads.shape[0] == gt.shape[0] and (heads[:, 0] == gt.astype(np.uint64)).all()
+
+
+def test_kmer_set_long_runs(rj):
+    """Round 2: k_set_kmer is size-independent — a warp owns a run of rows of any length, checks its hits in
+    batches and moves them to a staging area when its shared list is full.  400 MB with a member occurrence every
+    200 bytes (every warp flushes and spills many times; the staging area grows once), checked offset by offset."""
+    from rejit_b200 import workloads as W
+    rng = np.random.RandomState(5)
+    unit = np.frombuffer(b"agggtaaa", dtype=np.uint8)
+    # filler over {a, c}: every alternative of every member needs a 't', so only the planted 8-mers match
+    block = rng.choice(np.frombuffer(b"ac", dtype=np.uint8), size=200 * 5000).astype(np.uint8)
+    for k in range(0, len(block), 200):
+        block[k + 100:k + 108] = unit
+    text = np.tile(block, 400)                           # 400 MB
+    n_occ = len(text) // 200
+    rs = rj.RegejSet(W.DNA_PATTERNS)
+    assert "k-mer index" in rs.describe()
+    exp_small = [O.Oracle(p).match_all(block[:400000].tobytes()) for p in W.DNA_PATTERNS]
+    got_small = rs.match_all(block[:400000])
+    assert got_small == exp_small
+    which = [len(e) > 0 for e in exp_small]              # the members the planted 8-mer matches: the first only
+    assert which == [True] + [False] * 8
+    dt = rj.DeviceText(text)
+    try:
+        st = rj.Stats()
+        counts = rs.match_all_device(dt, stats=st)
+        assert st.strategy == 4, st.strategy
+        counts = rs.match_all_device(dt, stats=st)       # steady state: one launch, no rerun
+        assert st.launches == 1 and st.reruns == 0 and st.strategy == 4
+        for j, w in enumerate(which):
+            assert counts[j] == (n_occ if w else 0), (j, counts[j])
+    finally:
+        dt.free()
+    # full offset lists through the text API
+    lists = rs.match_all(text[:100_000_000])
+    begins = np.arange(100, 100_000_000, 200, dtype=np.uint64)
+    for j, w in enumerate(which):
+        got = np.array(lists[j], dtype=np.uint64).reshape(-1, 2)
+        if w:
+            assert got.shape[0] == begins.shape[0] and (got[:, 0] == begins).all() and (got[:, 1] == begins + 8).all(), j
+        else:
+            assert got.shape[0] == 0
+    # against the nine single-pattern scans (k_dfa_tma, an independent kernel) on 300 MB of FASTA
+    seq = np.tile(W.fasta_sequence(3_000_000), 10)
+    dt = rj.DeviceText(seq)
+    try:
+        counts = rs.match_all_device(dt)
+        single = [rj.Regej(p).match_all_device(dt) for p in W.DNA_PATTERNS]
+        assert counts == single, (counts, single)
+    finally:
+        dt.free()

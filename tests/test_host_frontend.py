@@ -93,6 +93,46 @@ def test_parse_errors_and_status_string(lib):
     assert lib.Regej("a{3,2}").status_string.endswith("Invalid repetition bounds: 3 > 2\n")
 
 
+def test_hostile_patterns_fail_before_expanding(lib):
+    """Patterns whose unrolled form would be huge, or whose tree is absurdly deep, come back as
+    a parse error in milliseconds: no allocation storm, no recursion crash, no exception
+    crossing the C boundary (`.{50000000}`, `a{3000000000}`, `a????...`)."""
+    import time
+    hostile = [b".{50000000}", b"a{3000000000}", b"a" + b"?" * 100000, b"(" * 50000 + b"a" + b")" * 50000,
+               b"(a*){999999}", b"((a{64}){64}){2}", b"(x{0,0}){4000000000}", b"a{,4097}", b"(abc){1,1400}"]
+    t0 = time.perf_counter()
+    for pat in hostile:
+        r = lib.Regej(pat)
+        assert r.status == -1, pat[:20]
+        assert "too large" in r.status_string or "too deeply" in r.status_string or r.status_string.startswith("Error parsing"), pat[:20]
+    assert time.perf_counter() - t0 < 5.0
+    # what fits the engine's 4096 byte positions still parses and compiles
+    for pat in (b"(abc){1000}", b"a{,4096}", b"x" * 4096, b"(" * 150 + b"a" + b")" * 150, b"a" + b"?" * 150):
+        r = lib.Regej(pat)
+        assert r.status == 0 and r.compile(), pat[:20]
+    over = lib.Regej(b"x" * 4097)                      # one position more than the engine's cap
+    assert over.status == -1 and "too large" in over.status_string
+
+
+def test_slab_entry_points_refuse_reentrant_patterns(lib):
+    """`.{,4}t` can re-enter its own start (defect B19): its chain cannot be resumed from a
+    (cur, tail) carry, so the slab / carry entry points return an error instead of wrong
+    matches.  The check runs before any device work: no GPU needed."""
+    bad, good = lib.Regej(".{,4}t"), lib.Regej("abc|abd")
+    assert not bad.shardable() and good.shardable()
+    L = lib.lib()
+    err = ctypes.create_string_buffer(512)
+    r = L.rejit_b200_match_all_device_slab(bad._prog, 0, None, 0, 0, 1, 0, None, 0, None, None, None, err, len(err))
+    assert r == -1 and b"re-entrant" in err.value
+    cin = lib.Carry(5, 5)
+    r = L.rejit_b200_match_all_device(bad._prog, 0, None, 0, None, 0, ctypes.byref(cin), None, None, err, len(err))
+    assert r == -1 and b"re-entrant" in err.value
+    rs = lib.RegejSet([bad, good])
+    counts = (ctypes.c_int64 * 2)()
+    r = L.rejit_b200_match_all_set_device_slab(rs._set, 0, None, 0, 0, 1, 0, None, None, counts, None, err, len(err))
+    assert r == -1 and b"re-entrant" in err.value
+
+
 def test_compile_survives_malformed_ir():
     """The C ABI takes the lowered regexp from a foreign binding: out-of-range states, kinds,
     payload ranges and header fields must come back as an error (entry_state = 255 of 5 states used to fault)."""
