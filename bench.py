@@ -1,42 +1,45 @@
 #!/usr/bin/env python3
 """bench.py — GB/s of text scanned by MatchAll (BASELINE.json's metric).
 
-Workload (config.workload): BASELINE.json configs[1] — the regex-dna alternation
-set (the reference sample has NINE variants, sample/regexdna.cc:52-62) counted
-over a 50 MB synthetic FASTA sequence, one `MatchAll` call per pattern exactly
-as the reference sample does.  A "step" = those nine calls over the text.
-"GB/s text scanned" follows the reference's definition of speed, text_size /
-time per MatchAll call (tools/benchmarks/engines/bench_engine.cc:244-249), summed
-over the calls of a step:  value = 9 * N_bytes / step_time.
-
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-  value ......... text resident in HBM; step time = sum of the nine calls' device
-                  pipeline times (CUDA events on the engine's stream, from the
-                  first kernel launch to the match count being back on the
-                  host); L2 is flushed before every call (50 MB < 126 MB L2),
-                  outside the timed events.
-  e2e ........... the text starts in pinned host memory; per step it is uploaded
-                  once (H2D inside the timed region), the nine patterns are matched
-                  against the resident copy through the C ABI and the match lists
-                  are copied back (D2H); host wall clock.  e2e_per_call_upload:
-                  every call uploads the text again (the unmodified MatchAll
-                  signature).
-  roofline ...... the dominant kernel (k_dfa_tma): algorithmic bytes
-                  (N + 16*M per launch) / its CUDA-event time, against the
-                  measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline .. the reference's own JIT (oracle/_ref, built from
-                  /root/reference; flag set "noreduce" = fast-forward on,
-                  ff_reduce off — its fastest configuration that returns correct
-                  results on these patterns) on the host cores.
-  N > 1 ......... weak scaling: every rank owns one 50 MB slab of an N*50 MB
-                  text (plus a right halo), resolves it locally and the chain is
-                  stitched with ONE all-gather of a small record per step
-                  (rejit_b200/sharding.py).  The records are host data and all
-                  ranks share a box, so the all-gather runs over a shared-memory
-                  mailbox (config.stitch = "shm", ~2 us); the same step with the
-                  records sent through an NCCL all-gather is reported next to it
-                  as `nccl_stitch` (RJ_STITCH=nccl makes it the headline).
+Headline workload (config.workload): BASELINE.json configs[1] — the regex-dna
+alternation set (the reference sample has NINE variants, sample/regexdna.cc:52-62)
+counted over a 50 MB synthetic FASTA sequence.  A "step" = the nine patterns over
+the text once.
+
+  value ......... PHYSICAL rate: text bytes / step time (round 2; round 1 counted
+                  the text once per pattern, k*N/time — kept as `value_per_pattern`).
+                  Text resident in HBM, ONE fused set call per step (k_set_kmer);
+                  step time = the call's device pipeline time (CUDA events on the
+                  engine's stream, first launch to the counts being on the host);
+                  L2 flushed before every call (50 MB < 126 MB L2), outside the events.
+  e2e ........... the text starts in pinned host memory: uploaded once per step
+                  (H2D inside the timed region), one fused set call through the C ABI,
+                  every match list copied back (D2H inside); host wall clock.
+  e2e_dropin .... a C++ program (samples/e2e_dropin.cc) that calls the UNMODIFIED
+                  signature Regej::MatchAll(const char*, size_t, ...) nine times on a
+                  std::string (pageable memory), timed inside the program.
+  roofline ...... the dominant kernel (k_set_kmer): algorithmic bytes (N + 16*M per
+                  launch) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline .. the reference's own JIT (oracle/_ref, flag set "noreduce": its
+                  fastest configuration that is correct on these patterns), 1 core.
+  configs ....... one row per BASELINE.json configuration at its stated size:
+                  C1 literal over 1 MiB (reference JIT on the CPU, and the engine),
+                  C3 complex regex over 500 MB random text (without / with hits),
+                  C4 jrep literal over a 5 GB source text (one text; 16 MiB batches),
+                  C5 regex-dna chain (strip, nine counts, eleven substitutions) over a
+                  5 GB FASTA file — each with GB/s (physical), the scan kernel's
+                  roofline fraction, launches and an independent count check.
+                  At N > 1 the 5 GB texts are strong-scaled: rank r owns slab r.
+                  RJ_BENCH_CONFIGS=0 skips the rows (the headline only).
+  N > 1 ......... weak scaling of the headline: every rank owns one 50 MB slab (plus a
+                  right halo) of an N*50 MB text.  The chain is stitched on the
+                  DEVICES: after its scan a rank sends the chain state leaving its slab
+                  into the right neighbour's HBM with a peer store over NVLink and
+                  checks the one arriving from the left (k_stitch; config.stitch =
+                  "nvlink").  The same step with the records exchanged by an NCCL
+                  all-gather (torch.distributed) is reported as `nccl_stitch`.
 """
 import argparse
 import ctypes
@@ -230,6 +233,313 @@ def traffic_of(kernel):
         return None
 
 
+# ---------------------------------------------------------------------------
+# rows for the other BASELINE.json configurations
+# ---------------------------------------------------------------------------
+def _timed_calls(rj, regej, dt, reps, device, flush=True, **kw):
+    """Device-resident MatchAll `reps` times (L2 flushed before each); returns (count, pipeline_ms, scan_ms, launches)."""
+    st = rj.Stats()
+    cnt = 0
+    for _ in range(2):
+        cnt = regej.match_all_device(dt, stats=st, **kw)
+    tot = scan = 0.0
+    for _ in range(reps):
+        if flush:
+            rj.lib().rejit_b200_flush_l2(device)
+        cnt = regej.match_all_device(dt, stats=st, **kw)
+        tot += st.total_ms
+        scan += st.scan_ms
+    return cnt, tot / reps, scan / reps, st.launches
+
+
+def _row(name, n_bytes, matches, pipeline_ms, scan_ms, launches, peak, kernel, **extra):
+    alg = n_bytes + 16.0 * matches
+    row = {"config": name, "bytes": int(n_bytes), "matches": int(matches), "gbs": round(n_bytes / pipeline_ms / 1e6, 1),
+           "pipeline_ms": round(pipeline_ms, 4), "launches": int(launches),
+           "roofline": {"kernel": kernel, "bound": "hbm", "achieved": round(alg / scan_ms / 1e6, 1), "peak": peak,
+                        "unit": "GB/s", "frac": round(alg / scan_ms / 1e6 / peak, 4), "avg_launch_ms": round(scan_ms, 4)}}
+    row.update(extra)
+    return row
+
+
+def _device_text(rj, tensor, n, device):
+    """A torch uint8 tensor (n bytes + 64 bytes of padding) as a device text the engine borrows."""
+    return rj.DeviceText(nbytes=n, device=device, borrowed_ptr=tensor.data_ptr())
+
+
+def _count_literal(torch, t, n, needle):
+    """Occurrences of `needle` in t[:n] by shifted compares in torch (no engine code): (count, positions or None)."""
+    total = 0
+    step = 1 << 28
+    m = len(needle)
+    for lo in range(0, max(n - m + 1, 0), step):
+        hi = min(n - m + 1, lo + step)
+        ok = t[lo:hi] == needle[0]
+        for i in range(1, m):
+            ok &= t[lo + i:hi + i] == needle[i]
+        total += int(ok.sum().item())
+    return total
+
+
+def config_rows(rj, W, torch, peak, device, rank, world, dist, tdev, reps):
+    """One row per BASELINE.json configuration (see the module docstring).  Every row is independent: a failure
+    becomes {"config": ..., "error": ...} instead of taking the bench line down."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    rows = []
+    cuda = torch.device("cuda", device)
+
+    def guarded(name, fn):
+        try:
+            out = fn()
+            if out is not None:
+                rows.extend(out if isinstance(out, list) else [out])
+        except Exception as exc:                        # noqa: BLE001 — a row must not take the line down
+            rows.append({"config": name, "error": "%s: %s" % (type(exc).__name__, str(exc)[:200])})
+        torch.cuda.empty_cache()
+
+    # ---- C1: literal over 1 MiB random ASCII — the reference JIT on the CPU (plumbing) and the engine --------
+    def c1():
+        if rank != 0:
+            return None
+        text = W.random_ascii(1 << 20, seed=1)
+        L = ref_lib()
+        ref = None
+        if L is not None:
+            L.ref_set_flagset(0)
+            h = L.ref_compile(W.LITERAL_PATTERN.encode())
+            best = None
+            for _ in range(20):
+                t0 = time.perf_counter()
+                cnt_ref = int(L.ref_run_match_all(h, ctypes.c_void_p(text.ctypes.data), len(text)))
+                dt_ = time.perf_counter() - t0
+                best = dt_ if best is None else min(best, dt_)
+            L.ref_free(h)
+            ref = {"gbs": round(len(text) / best / 1e9, 3), "matches": cnt_ref, "cores": 1, "flags": "default"}
+        r = rj.Regej(W.LITERAL_PATTERN)
+        dt = rj.DeviceText(text, device=device)
+        cnt, pms, sms, la = _timed_calls(rj, r, dt, reps, device, flush=False)
+        dt.free()
+        return _row("C1 literal 'regexp', 1 MiB random ASCII (L2 resident; the reference runs it on the CPU)", len(text), cnt,
+                    pms, sms, la, peak, "k_scan_emit<literal>", reference_cpu=ref,
+                    oracle_counts_equal=(ref is None or ref["matches"] == cnt))
+    guarded("C1", c1)
+
+    # ---- C3: complex regex over 500 MB random text, without and with hits ---------------------------------------
+    def c3():
+        n = 500_000_000
+        if world > 1 and rank != 0:
+            return None                                 # a single-GPU configuration
+        import rejit_oracle
+        t = torch.empty(n + 64, dtype=torch.uint8, device=cuda)
+        t[:n] = W.random_ascii_range(0, n, device=cuda, seed=21)
+        t[n:] = 0
+        r = rj.Regej(W.COMPLEX_PATTERN)
+        dt = _device_text(rj, t, n, device)
+        out = []
+        lit = torch.tensor(list(b"abcdefgh"), dtype=torch.uint8, device=cuda)
+        natural = _count_literal(torch, t, n, lit)
+        cnt, pms, sms, la = _timed_calls(rj, r, dt, reps, device)
+        out.append(_row("C3 complex regex, 500 MB random text, no hits", n, cnt, pms, sms, la, peak, "k_scan_emit<window>",
+                        oracle_counts_equal=(natural == 0 and cnt == 0), oracle="torch: the required literal does not occur"))
+        # hits every ~10 kB: the three needles in turn
+        pos = torch.arange(5003, n - 64, 10007, dtype=torch.int64, device=cuda)
+        for j, nd in enumerate(W.COMPLEX_HITS):
+            pj = pos[j::len(W.COMPLEX_HITS)]
+            for k2, byte in enumerate(nd):
+                t[pj + k2] = byte
+        torch.cuda.synchronize(device)
+        cnt, pms, sms, la = _timed_calls(rj, r, dt, reps, device)
+        # the oracle on +-64 bytes around every planted needle (bounded: the first 3000 plants), and the plant count
+        o = rejit_oracle.Oracle(W.COMPLEX_PATTERN)
+        sample = pos[:3000].cpu().numpy()
+        exp = 0
+        for pp in sample:
+            w = bytes(t[int(pp) - 64:int(pp) + 64].cpu().numpy())
+            exp += len(o.match_all(w))
+        hi_off = int(sample[-1]) + 64
+        got_sample = r.match_all_device(_device_text(rj, t, hi_off, device))
+        out.append(_row("C3 complex regex, 500 MB random text, a hit every ~10 kB", n, cnt, pms, sms, la, peak, "k_scan_emit<window>",
+                        oracle_counts_equal=(exp == got_sample and cnt == int(pos.numel())),
+                        oracle="oracle windows around the first 3000 plants (%d matches) + one match per plant (%d)" % (exp, int(pos.numel()))))
+        del t
+        return out
+    guarded("C3", c3)
+
+    # ---- C4: jrep literal over a 5 GB source text, sharded by slab ---------------------------------------------------
+    def c4():
+        total = 5_000_000_000
+        slab = total // world
+        lo, hi = rank * slab, (total if rank + 1 == world else (rank + 1) * slab)
+        halo = 16 if rank + 1 < world else 0
+        n = hi - lo + halo
+        t = torch.empty(n + 64, dtype=torch.uint8, device=cuda)
+        t[:n] = W.source_text_range(lo, lo + n, device=cuda)
+        t[n:] = 0
+        torch.cuda.synchronize(device)
+        r = rj.Regej(W.JREP_PATTERN)
+        dt = _device_text(rj, t, n, device)
+        own = (0, (hi - lo) if rank + 1 < world else (1 << 62))
+        if dist is not None:
+            dist.barrier()
+        cnt, pms, sms, la = _timed_calls(rj, r, dt, max(2, reps // 2), device, own=own, base_offset=lo)
+        needle = torch.tensor(list(W.JREP_PATTERN.encode()), dtype=torch.uint8, device=cuda)
+        exp = _count_literal(torch, t, (hi - lo) + (2 if rank + 1 < world else 0), needle)
+        vals = torch.tensor([float(pms), float(cnt), float(exp), float(sms)], dtype=torch.float64, device=cuda)
+        if dist is not None:
+            allv = [torch.zeros_like(vals) for _ in range(world)]
+            dist.all_gather(allv, vals)
+            pms_max = max(float(v[0]) for v in allv)
+            sms_max = max(float(v[3]) for v in allv)
+            cnt_all, exp_all = int(sum(float(v[1]) for v in allv)), int(sum(float(v[2]) for v in allv))
+        else:
+            pms_max, sms_max, cnt_all, exp_all = pms, sms, cnt, exp
+        out = []
+        if rank == 0:
+            out.append(_row("C4 jrep literal ';\\n}' over a 5 GB source text, one text, %d slab(s) of %d MB" % (world, slab // 1_000_000),
+                            total, cnt_all, pms_max, sms_max, la, peak, "k_scan_emit<literal>", n_gpus=world,
+                            oracle_counts_equal=(cnt_all == exp_all), oracle="torch shifted compares on every slab",
+                            stitch="none needed: the literal cannot overlap itself, a match belongs to the slab it begins in"))
+        # the same bytes as independent 16 MiB batches (jrep matches file by file: nothing spans two batches)
+        if world == 1:
+            piece = 16 << 20
+            st = rj.Stats()
+            tot_ms, got, exp_b = 0.0, 0, 0
+            pieces = list(range(0, n, piece))
+            for p0 in pieces[:64]:                      # bounded: 64 batches = 1 GiB
+                ln = min(piece, n - p0)
+                v = rj.DeviceText(nbytes=ln, device=device, borrowed_ptr=t.data_ptr() + p0)
+                r.match_all_device(v, stats=st)
+                got += r.match_all_device(v, stats=st)
+                tot_ms += st.total_ms
+                exp_b += _count_literal(torch, t[p0:p0 + ln], ln, needle)
+            nb = min(len(pieces), 64)
+            out.append({"config": "C4 per-file flavour: the first %d batches of 16 MiB, one MatchAll each" % nb, "bytes": nb * piece,
+                        "matches": got, "gbs": round(nb * piece / tot_ms / 1e6, 1), "pipeline_ms": round(tot_ms, 3),
+                        "launches": nb, "oracle_counts_equal": got == exp_b})
+        del t
+        return out
+    guarded("C4", c4)
+
+    # ---- C5: the regex-dna chain over a 5 GB FASTA file, sharded by slab ----------------------------------------------
+    class _Cai:                                         # a device pointer as a torch tensor (zero copy)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def c5():
+        n_lines = 500_000_000                           # fasta_file(500 M): 5.08 GB, 5.0 G letters
+        size = W.fasta_file_size(n_lines)
+        per = -(-size // world)
+        lo, hi = rank * per, min(size, (rank + 1) * per)
+        margin = 128
+
+        def first_line_start(at):                       # smallest p >= at where a line begins
+            if at == 0:
+                return 0
+            if at >= size:
+                return size
+            w = W.fasta_file_range(n_lines, at - 1, min(size, at - 1 + margin), device=cuda)
+            return at + int((w == 10).nonzero()[0].item())
+        begin, end = first_line_start(lo), first_line_start(hi)        # this rank owns the lines that begin in [lo, hi)
+        n = end - begin
+        t = torch.empty(n + 64, dtype=torch.uint8, device=cuda)
+        t[:n] = W.fasta_file_range(n_lines, begin, end, device=cuda)
+        t[n:] = 0
+        torch.cuda.synchronize(device)
+        raw = rj.Text(device=device, device_ptr=t.data_ptr(), nbytes=n)
+        del t
+        torch.cuda.empty_cache()
+        strip = rj.Regej(W.STRIP_PATTERN)
+        rs = rj.RegejSet(W.DNA_PATTERNS)
+        pats = [c for c, _ in W.IUB_SUBSTITUTIONS]
+        withs = [a.encode() for _, a in W.IUB_SUBSTITUTIONS]
+        regs5 = [rj.Regej(c) for c in pats]
+        best, letters = None, None
+        for rep in range(2):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            st = rj.Stats()
+            seq5, n_strip = strip.replace_all_text(raw, b"", stats=st)
+            strip_ms = st.total_ms
+            t1 = time.perf_counter()
+            n_seq = len(seq5)
+            if world > 1:
+                # the "tiny all-gather": every rank's first 16 letters, so that a variant spanning a cut of the
+                # sequence is counted by the rank it begins in (halo written into the text's padding)
+                view = torch.as_tensor(_Cai(seq5.device_ptr(), n_seq + 16), device=cuda)
+                head = view[:16].clone() if n_seq >= 16 else torch.zeros(16, dtype=torch.uint8, device=cuda)
+                heads = [torch.zeros_like(head) for _ in range(world)]
+                dist.all_gather(heads, head)
+                torch.cuda.synchronize(device)
+                if rank + 1 < world:
+                    view[n_seq:n_seq + 16] = heads[rank + 1]
+                    torch.cuda.synchronize(device)
+                dt5 = rj.DeviceText(nbytes=n_seq + (16 if rank + 1 < world else 0), device=device, borrowed_ptr=seq5.device_ptr())
+                counts = rs.match_all_device(dt5, stats=st, own=(0, n_seq if rank + 1 < world else (1 << 62)))
+            else:
+                counts = rs.match_all_text(seq5, stats=st)
+            count_ms = st.total_ms
+            t2 = time.perf_counter()
+            outp, ks = rj.replace_all_set_text(regs5, seq5, withs, stats=st)
+            iub_ms = st.total_ms
+            t3 = time.perf_counter()
+            res = {"wall_ms": (t3 - t0) * 1e3, "strip_ms": (t1 - t0) * 1e3, "count9_ms": (t2 - t1) * 1e3, "iub11_ms": (t3 - t2) * 1e3,
+                   "device_ms": strip_ms + count_ms + iub_ms, "stripped": n_seq, "final": len(outp), "counts": counts, "iub": ks}
+            if rep == 1:
+                # independent of the engine: letter counts of the stripped text by torch
+                view = torch.as_tensor(_Cai(seq5.device_ptr(), n_seq + (16 if rank + 1 < world else 0)), device=cuda)
+                letters = torch.zeros(256, dtype=torch.int64, device=cuda)
+                for c0 in range(0, n_seq, 1 << 28):
+                    letters += torch.bincount(view[c0:min(n_seq, c0 + (1 << 28))].to(torch.int64), minlength=256)
+                lit_a = _count_literal(torch, view, n_seq + (7 if rank + 1 < world else 0), torch.tensor(list(b"agggtaaa"), dtype=torch.uint8, device=cuda))
+                lit_b = _count_literal(torch, view, n_seq + (7 if rank + 1 < world else 0), torch.tensor(list(b"tttaccct"), dtype=torch.uint8, device=cuda))
+                res["torch_first_variant"] = lit_a + lit_b
+                res["torch_letters"] = sum(int(letters[c]) for c in range(256))
+                res["torch_final"] = n_seq + sum(int(letters[ord(c)]) * (len(w) - 1) for c, w in zip(pats, withs))
+                res["torch_iub"] = [int(letters[ord(c)]) for c in pats]
+            seq5.free()
+            outp.free()
+            if best is None or res["wall_ms"] < best["wall_ms"]:
+                keep = {k: res[k] for k in res if k.startswith("torch_")} if rep == 1 else {}
+                best = dict(res, **keep)
+            if rep == 1:
+                for k in ("torch_first_variant", "torch_final", "torch_iub", "torch_letters"):
+                    best[k] = res[k]
+        raw.free()
+        ok_local = (best["final"] == best["torch_final"] and best["iub"] == best["torch_iub"] and
+                    best["counts"][0] == best["torch_first_variant"])
+        vals = torch.tensor([best["wall_ms"], best["device_ms"], float(n), float(best["stripped"]), float(best["final"]),
+                             1.0 if ok_local else 0.0] + [float(c) for c in best["counts"]], dtype=torch.float64, device=cuda)
+        if dist is not None:
+            allv = [torch.zeros_like(vals) for _ in range(world)]
+            dist.all_gather(allv, vals)
+        else:
+            allv = [vals]
+        if rank != 0:
+            return None
+        wall = max(float(v[0]) for v in allv)
+        dev_ms = max(float(v[1]) for v in allv)
+        tot_in = int(sum(float(v[2]) for v in allv))
+        stripped = int(sum(float(v[3]) for v in allv))
+        final = int(sum(float(v[4]) for v in allv))
+        counts_all = [int(sum(float(v[6 + j]) for v in allv)) for j in range(len(W.DNA_PATTERNS))]
+        return {"config": "C5 regex-dna chain (strip, nine counts, eleven IUB substitutions) over a 5.08 GB FASTA file, %d slab(s)" % world,
+                "bytes": size, "n_gpus": world, "gbs": round(size / wall / 1e6, 2), "wall_ms": round(wall, 3),
+                "device_ms": round(dev_ms, 3), "gbs_device": round(size / dev_ms / 1e6, 2),
+                "phases_ms_rank0": {k: round(best[k], 3) for k in ("strip_ms", "count9_ms", "iub11_ms")},
+                "stripped": stripped, "final": final, "counts": counts_all,
+                "oracle_counts_equal": (tot_in == size and stripped == 10 * n_lines and all(float(v[5]) == 1.0 for v in allv)),
+                "oracle": "file arithmetic (every letter kept, every header / newline removed); torch on the stripped text: letter "
+                          "histogram -> substitution counts and final length, shifted compares -> the first variant's count",
+                "stitch": "slabs are cut at line ends; the nine counts use a 16-byte halo exchanged by ONE NCCL all-gather per step"
+                          if world > 1 else "one slab",
+                "launches": "strip 1 scan + 3 rebuild, counts 1, substitutions 5"}
+    guarded("C5", c5)
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -242,11 +552,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from rejit_b200 import workloads as W
     patterns = W.DNA_PATTERNS
+    K = len(patterns)
     config = {"workload": "regex-dna alternation set (9 patterns, sample/regexdna.cc:52-62; BASELINE says 8) "
-                          "over 50 MB synthetic FASTA sequence per GPU, one MatchAll per pattern",
-              "text_bytes_per_gpu": FASTA_N * 10, "patterns": len(patterns),
-              "l2": "flushed before every MatchAll call (256 MB write), outside the timed events",
-              "parallelism": "slab%d" % args.gpus}
+                          "over 50 MB synthetic FASTA sequence per GPU (BASELINE.json configs[1])",
+              "text_bytes_per_gpu": FASTA_N * 10, "patterns": K,
+              "l2": "flushed before every call (256 MB write), outside the timed events",
+              "parallelism": "slab%d" % args.gpus,
+              "value_definition": "physical: text bytes / step time (the nine patterns share ONE pass); value_per_pattern = 9x"}
 
     # ---------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -255,10 +567,6 @@ def main():
         seq = W.fasta_sequence(FASTA_N)
         ncpu = os.cpu_count() or 1
         sample = 50_000_000
-        # "all the host threads it can use": the compiled matcher is single-threaded
-        # per call, so the text is cut into slabs; both ways of running slabs
-        # concurrently (threads of one process / worker processes) are tried at a few
-        # widths and the fastest is reported (all tried configurations are listed).
         t0 = time.perf_counter()
         tried = []
         best = None
@@ -270,20 +578,21 @@ def main():
                 except Exception as exc:          # a configuration that cannot run is skipped, not fatal
                     tried.append({"mode": mode, "width": w, "error": str(exc)[:80]})
                     continue
-                tried.append({"mode": mode, "width": w, "gbs": round(r[0], 3)})
+                tried.append({"mode": mode, "width": w, "gbs_per_pattern": round(r[0], 3)})
                 if best is None or r[0] > best[0]:
                     best = r
         single = cpu_reference_run(seq, patterns, 1, 1, sample)
-        tried.append({"mode": "single", "width": 1, "gbs": round(single[0], 3)})
+        tried.append({"mode": "single", "width": 1, "gbs_per_pattern": round(single[0], 3)})
         if best is None or single[0] > best[0]:
             best = single
-        gbs, kind, cores, counts, what = best
+        gbs_k, kind, cores, counts, what = best
+        gbs = gbs_k / K                              # physical: the reference reads the text once per pattern
         wall = time.perf_counter() - t0
         line = {"impl": "reference", "metric": "GB/s text scanned (MatchAll)", "value": round(gbs, 4), "unit": "GB/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": round(len(patterns) * min(len(seq), sample) / gbs / 1e6, 3),
+                "ms_per_step": round(min(len(seq), sample) / gbs / 1e6, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": config, "gpu_launches": 0,
+                "data": "synthetic", "config": config, "gpu_launches": 0, "value_per_pattern": round(gbs_k, 4),
                 "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": kind, "sample": what},
                 "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "match_counts": counts, "wall_s": round(wall, 2), "configurations_tried": tried}
@@ -292,26 +601,26 @@ def main():
 
     # ---------------------------------------------------------------- our arm
     import numpy as np
+    import torch
     import rejit_b200 as rj
     from rejit_b200 import sharding
     dist = None
     tdev = None
+    torch.cuda.set_device(local_rank)
     if world > 1:
-        import torch
         import torch.distributed as dist
         import datetime
-        torch.cuda.set_device(local_rank)
         tdev = torch.device("cuda", local_rank)
-        dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=180), device_id=tdev)
+        dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=240), device_id=tdev)
     if rj.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (rejit_b200 has no CPU fallback)")
+    peak, peak_src = load_peaks()
 
     # every rank generates its own slab (+ the first bytes of its right neighbour as halo)
     seq = W.fasta_sequence(FASTA_N, seed=42 + rank)
     n_own = len(seq)
     if world > 1 and rank + 1 < world:
         nxt = W.fasta_sequence(HALO // 10 + 10, seed=42 + rank + 1)[:HALO]
-        # the neighbour's slab begins with its ALU section
         buf = np.concatenate([seq, nxt])
     else:
         buf = seq
@@ -322,122 +631,101 @@ def main():
     dtext = rj.DeviceText(buf, device=local_rank)
     total_text = n_own * world
     rset = rj.RegejSet(regs)
-    K = len(regs)
 
-    # the stitch exchange at N>1: a shared-memory mailbox (the records are host data, all ranks are on one box);
-    # the same protocol over an NCCL all-gather is timed next to it (`nccl_stitch`)
-    exchanges = {}
+    # ---- the stitch at N > 1: device-side neighbour exchange over NVLink; the NCCL all-gather is timed next to it
+    stitch = None
+    nccl_ex = None
     if world > 1:
-        exchanges["nccl"] = sharding.NcclExchange(dist, world, tdev)
-        if os.environ.get("RJ_STITCH", "shm") == "shm":
+        nccl_ex = sharding.NcclExchange(dist, world, tdev)
+        if os.environ.get("RJ_STITCH", "nvlink") == "nvlink":
             try:
-                ex = sharding.ShmExchange(rank, world, 3 * 33, os.environ.get("MASTER_PORT", "0"))
-                dist.barrier()
-                ex.attach()
-                exchanges["shm"] = ex
-            except Exception as exc:                      # no /dev/shm: every rank falls back together below
-                print("bench.py: shared-memory stitch unavailable (%s)" % exc, file=sys.stderr)
-            ok = torch.tensor([1 if "shm" in exchanges else 0], dtype=torch.int64, device=tdev)
+                stitch = sharding.DeviceStitch(dist, rank, world, local_rank, tdev)
+            except Exception as exc:
+                print("bench.py: device-side stitch unavailable (%s)" % exc, file=sys.stderr)
+                stitch = None
+            ok = torch.tensor([1 if stitch is not None else 0], dtype=torch.int64, device=tdev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
-                exchanges.pop("shm", None)
-    stitch = "shm" if "shm" in exchanges else "nccl"
-    config["stitch"] = stitch if world > 1 else "none (one slab)"
-
-    class Timed:
-        """Host time spent inside the exchange (it contains the wait for the slowest rank)."""
-        def __init__(self, inner):
-            self.inner, self.spent = inner, 0.0
-
-        def __call__(self, rec):
-            t0 = time.perf_counter()
-            rows = self.inner(rec)
-            self.spent += time.perf_counter() - t0
-            return rows
-    timed = {k: Timed(v) for k, v in exchanges.items()}
+                stitch = None
+    config["stitch"] = ("nvlink" if stitch is not None else "nccl") if world > 1 else "none (one slab)"
     if world > 1:
         config["timing"] = ("step = device pipeline time of the rank's own call (CUDA events, as at N=1) + host time inside the "
-                            "stitch exchange; the ranks are aligned with an untimed exchange after the L2 flush, max over ranks")
+                            "stitch (k_stitch: launch, peer store, wait for the left neighbour); ranks aligned by an untimed "
+                            "barrier after the L2 flush; max over ranks")
 
-    def run_set(stats, how=None):
-        """The nine patterns in ONE fused pass over the resident slab (+ the stitch
-        all-gather at N>1); returns (counts, pipeline_ms, collective_s)."""
-        if world == 1:
-            cnts = rset.match_all_device(dtext, stats=stats)
-            return cnts, stats.total_ms, 0.0
-        ms = [0.0]
-
+    def slab_run(stats, acc):
         def run(carries):
             cin = (rj.Carry * K)(*[rj.Carry(max(c - slab_lo, 0), t - slab_lo if t != sharding.NO_TAIL and t >= slab_lo else sharding.NO_TAIL)
                                    for c, t in carries])
             cout = (rj.Carry * K)()
             own_end = n_own if rank + 1 < world else (1 << 62)
             cnts = rset.match_all_device(dtext, stats=stats, own=(0, own_end), base_offset=slab_lo, carry_in=cin, carry_out=cout)
-            ms[0] += stats.total_ms
+            acc[0] += stats.total_ms
+            acc[1] += stats.scan_ms
+            acc[2] += stats.launches
             outs = [(cout[j].cur + slab_lo, cout[j].tail + slab_lo if cout[j].tail != sharding.NO_TAIL else sharding.NO_TAIL)
                     for j in range(K)]
             return cnts, outs
-        ex = timed[how or stitch]
-        ex.spent = 0.0
-        cnts, _ = sharding.stitched_counts_set(dist, rank, world, slab_lo, K, run, device=tdev, exchange=ex)
-        return cnts, ms[0], ex.spent
+        return run
 
-    def flush():
-        """L2 flush, outside every timed region: at N > 1 the step is timed by the host clock (it contains the
-        exchange), so the flush kernel must have finished before that clock starts."""
-        rj.lib().rejit_b200_flush_l2(local_rank)
-        if world > 1:
-            torch.cuda.synchronize(local_rank)
-            exchanges[stitch]([0])                            # all ranks start the step together (untimed)
+    cascades = [0]
 
     def one_step_fused(how=None):
-        flush()
+        """One step: (step ms, scan ms, launches, this rank's counts)."""
+        rj.lib().rejit_b200_flush_l2(local_rank)
         st = rj.Stats()
-        cnts, ms, cs = run_set(st, how)
-        return ms + cs * 1e3, st.scan_ms, st.launches, cnts
-
-    def run_pattern(r, stats):
-        """One MatchAll over the resident slab; returns (count, pipeline_ms, collective_s)."""
         if world == 1:
-            cnt = r.match_all_device(dtext, stats=stats)
-            return cnt, stats.total_ms, 0.0
-        ms = [0.0]
+            cnts = rset.match_all_device(dtext, stats=st)
+            return st.total_ms, st.scan_ms, st.launches, cnts
+        torch.cuda.synchronize(local_rank)
+        dist.barrier()                                       # all ranks start the step together (untimed)
+        acc = [0.0, 0.0, 0]
+        run = slab_run(st, acc)
+        t0 = time.perf_counter()
+        if how == "nccl" or stitch is None:
+            t_run = [0.0]
 
-        def run(cur, tail):
-            cin = rj.Carry(max(cur - slab_lo, 0), tail - slab_lo if tail != sharding.NO_TAIL and tail >= slab_lo else sharding.NO_TAIL)
-            cout = rj.Carry()
-            # owned starts: [0, n_own) — the last rank also owns the offset n
-            own_end = n_own if rank + 1 < world else (1 << 62)
-            c = r.match_all_device(dtext, length=len(buf), stats=stats, carry_in=cin, carry_out=cout,
-                                   own=(0, own_end), base_offset=slab_lo)
-            ms[0] += stats.total_ms
-            tail_g = cout.tail + slab_lo if cout.tail != sharding.NO_TAIL else sharding.NO_TAIL
-            return c, cout.cur + slab_lo, tail_g
-        ex = timed[stitch]
-        ex.spent = 0.0
-        cnt, _ = sharding.stitched_count(dist, rank, world, slab_lo, run, device=tdev, exchange=ex)
-        return cnt, ms[0], ex.spent
+            def timed_run(c):
+                a = time.perf_counter()
+                out = run(c)
+                t_run[0] += time.perf_counter() - a
+                return out
+            totals, _ = sharding.stitched_counts_set(dist, rank, world, slab_lo, K, timed_run, device=tdev, exchange=nccl_ex)
+            ex_s = (time.perf_counter() - t0) - t_run[0]
+            return acc[0] + ex_s * 1e3, acc[1], acc[2], totals
+        cnts, couts = run([(slab_lo, sharding.NO_TAIL)] * K)
+        a = time.perf_counter()
+        arrived, redo = stitch.exchange(couts, slab_lo)
+        ex_s = time.perf_counter() - a
+        if redo:
+            want = [(max(arrived[j][0], slab_lo), arrived[j][1] if arrived[j][1] == slab_lo else sharding.NO_TAIL)
+                    if (redo >> j) & 1 else (slab_lo, sharding.NO_TAIL) for j in range(K)]
+            cnts, couts2 = run(want)
+            if couts2 != couts:
+                cascades[0] += 1
+        return acc[0] + ex_s * 1e3, acc[1], acc[2], cnts
 
-    def one_step():
-        step_ms, scan_ms, launches, counts, coll_s = 0.0, 0.0, 0, [], 0.0
+    def one_step_calls():
+        """The same workload as nine separate MatchAll calls (N = 1 only)."""
+        step_ms = scan_ms = 0.0
+        launches, counts = 0, []
         for r in regs:
-            flush()
+            rj.lib().rejit_b200_flush_l2(local_rank)
             st = rj.Stats()
-            cnt, ms, cs = run_pattern(r, st)
-            step_ms += ms + cs * 1e3
+            counts.append(r.match_all_device(dtext, stats=st))
+            step_ms += st.total_ms
             scan_ms += st.scan_ms
             launches += st.launches
-            counts.append(cnt)
-            coll_s += cs
-        return step_ms, scan_ms, launches, counts, coll_s
+        return step_ms, scan_ms, launches, counts
 
     sampler = ClockSampler(local_rank) if rank == 0 else None     # covers warm-up + timed region
-    for _ in range(max(3, args.warmup)):
-        one_step()
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         one_step_fused()
     if dist is not None:
         dist.barrier()
     # ---- headline: the fused set path ----------------------------------------------
+    t_wall = time.perf_counter()
     f_ms = f_scan = 0.0
     f_launches = 0
     f_counts = []
@@ -447,69 +735,71 @@ def main():
         f_scan += sc
         f_launches += la
     if dist is not None:
-        import torch
         t = torch.tensor([f_ms], dtype=torch.float64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         f_ms = float(t.item())
+        # the per-rank counts of the last step -> totals; did any stitch cascade
+        t = torch.tensor(list(f_counts) + [cascades[0]], dtype=torch.int64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if stitch is not None:
+            f_counts = [int(x) for x in t[:K].tolist()]
+        n_cascades = int(t[K].item())
         dist.barrier()
-    # the same fused step with the stitch over NCCL (N > 1 only)
+    else:
+        n_cascades = 0
+    # the same fused step with the stitch records through an NCCL all-gather (N > 1 only)
     nccl_ms = None
-    if world > 1 and stitch != "nccl":
+    nccl_counts = None
+    if world > 1 and stitch is not None:
         for _ in range(3):
             one_step_fused("nccl")
         nccl_ms = 0.0
         for _ in range(args.steps):
-            nccl_ms += one_step_fused("nccl")[0]
+            ms, _, _, nccl_counts = one_step_fused("nccl")
+            nccl_ms += ms
         t = torch.tensor([nccl_ms], dtype=torch.float64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         nccl_ms = float(t.item()) / args.steps
         dist.barrier()
-    t_wall = time.perf_counter()
-    tot_ms = tot_scan = 0.0
-    launches = 0
-    counts = []
-    for _ in range(args.steps):
-        ms, sc, la, counts, _cs = one_step()
-        tot_ms += ms
-        tot_scan += sc
-        launches += la
-    if dist is not None:
-        import torch
-        t = torch.tensor([tot_ms], dtype=torch.float64, device=tdev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot_ms = float(t.item())
-        dist.barrier()
     wall = time.perf_counter() - t_wall
+    # ---- nine separate calls (N = 1) ---------------------------------------------------
+    calls = None
+    if world == 1:
+        for _ in range(2):
+            one_step_calls()
+        c_ms = c_scan = 0.0
+        c_launches = 0
+        for _ in range(args.steps):
+            ms, sc, la, c_counts = one_step_calls()
+            c_ms += ms
+            c_scan += sc
+            c_launches += la
+        ms_calls = c_ms / args.steps
+        alg_call = len(buf) + 16.0 * sum(c_counts) / K
+        scan_call = c_scan / (args.steps * K)
+        calls = {"value": round(total_text / ms_calls / 1e6, 3), "unit": "GB/s (physical: the text is read nine times per step)",
+                 "ms_per_step": round(ms_calls, 4), "gpu_launches": c_launches, "counts_equal_fused": c_counts == f_counts,
+                 "roofline": {"kernel": "k_dfa_tma", "achieved": round(alg_call / scan_call / 1e6, 2),
+                              "frac": round(alg_call / scan_call / 1e6 / peak, 4), "avg_launch_ms": round(scan_call, 5)}}
     if sampler and wall < 0.5:
-        # the timed region is only milliseconds long: keep the same load running
-        # until nvidia-smi (100 ms period) has seen it a few times
-        # (rank 0 only, so nothing here may enter a collective: the local fused call, no stitch)
+        # the timed region is only milliseconds long: keep the same load running until nvidia-smi (100 ms period) has
+        # seen it a few times (rank 0 only, nothing here enters a collective: the local fused call, no stitch)
         t_end = time.perf_counter() + 0.6
         st_keep = rj.Stats()
         while time.perf_counter() < t_end:
             rset.match_all_device(dtext, stats=st_keep)
     clocks = sampler.stop() if sampler else None
-    ms_per_step = tot_ms / args.steps                       # nine separate MatchAll calls
-    value_calls = len(patterns) * total_text / (ms_per_step / 1e3) / 1e9
-    f_ms_per_step = f_ms / args.steps                        # one fused pass
-    value_fused = len(patterns) * total_text / (f_ms_per_step / 1e3) / 1e9
+    f_ms_per_step = f_ms / args.steps
+    value = total_text / (f_ms_per_step / 1e3) / 1e9
 
     # ---- e2e: host buffers in, match lists out -------------------------------------
-    # The step a regex-dna user runs: the sequence sits in (pinned) host memory;
-    # it is uploaded ONCE (rejit_b200_text_upload: H2D inside the timed region),
-    # the nine patterns are matched against the resident copy and every match
-    # list is copied back (D2H inside the timed region).  The per-call variant
-    # (every MatchAll call uploads the text again, what the unmodified
-    # Regej::MatchAll(const char*, size_t, ...) signature implies) is reported
-    # next to it as e2e_per_call_upload.
     L = rj.lib()
     pinned = L.rejit_b200_pinned_alloc(n_own)
     ctypes.memmove(pinned, seq.ctypes.data, n_own)
-    e2e_matches = 0
     err = ctypes.create_string_buffer(256)
+    e2e_d2h = [0]
 
     def e2e_step_fused():
-        nonlocal e2e_matches
         handle = L.rejit_b200_text_upload(local_rank, pinned, n_own, err, 256)
         if not handle:
             raise SystemExit(err.value.decode())
@@ -517,103 +807,139 @@ def main():
         prs = (ctypes.POINTER(ctypes.c_uint64) * K)()
         if L.rejit_b200_match_all_set_text(rset._set, handle, cnts, prs, None, err, 256) != 0:
             raise SystemExit(err.value.decode())
-        e2e_matches = sum(cnts)
+        e2e_d2h[0] = 16 * sum(cnts) + 64 * K
         for j in range(K):
             L.rejit_b200_free(prs[j])
         L.rejit_b200_text_free(handle)
 
-    def e2e_step(upload_once):
-        nonlocal e2e_matches
-        if upload_once == "fused":
-            return e2e_step_fused()
-        e2e_matches = 0
-        handle = None
-        if upload_once:
-            handle = L.rejit_b200_text_upload(local_rank, pinned, n_own, err, 256)
-            if not handle:
-                raise SystemExit(err.value.decode())
+    def e2e_step_percall():
         for r in regs:
             pairs = ctypes.POINTER(ctypes.c_uint64)()
-            if upload_once:
-                k = L.rejit_b200_match_all_text(r._prog, handle, ctypes.byref(pairs), None, err, 256)
-            else:
-                k = L.rejit_b200_match_all_alloc(r._prog, pinned, n_own, ctypes.byref(pairs), None, err, 256)
+            k = L.rejit_b200_match_all_alloc(r._prog, pinned, n_own, ctypes.byref(pairs), None, err, 256)
             if k < 0:
                 raise SystemExit(err.value.decode())
-            e2e_matches += k
             L.rejit_b200_free(pairs)
-        if handle:
-            L.rejit_b200_text_free(handle)
 
-    def time_e2e(upload_once, reps):
+    def time_e2e(fn, reps):
         for _ in range(2):
-            e2e_step(upload_once)
+            fn()
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(reps):
-            e2e_step(upload_once)
-        dt = (time.perf_counter() - t0) / reps
+            fn()
+        dt_ = (time.perf_counter() - t0) / reps
         if dist is not None:
-            import torch
-            t = torch.tensor([dt], dtype=torch.float64, device=tdev)
+            t = torch.tensor([dt_], dtype=torch.float64, device=tdev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return len(patterns) * total_text / dt / 1e9
+            dt_ = float(t.item())
+        return total_text / dt_ / 1e9
 
     e2e_reps = max(3, min(args.steps, 10))
-    e2e_fused = time_e2e("fused", e2e_reps)
-    e2e_value = time_e2e(True, e2e_reps)
-    e2e_percall = time_e2e(False, 3)
+    e2e_fused = time_e2e(e2e_step_fused, e2e_reps)
+    e2e_percall = time_e2e(e2e_step_percall, 3) if world == 1 else None
     L.rejit_b200_pinned_free(pinned)
 
-    if dist is not None:
+    # ---- e2e through the unmodified C++ signature, pageable memory (N = 1) -------------------------------
+    dropin = None
+    if world == 1:
+        try:
+            exe = os.path.join(ROOT, "samples", "_build", "e2e_dropin")
+            src = os.path.join(ROOT, "samples", "e2e_dropin.cc")
+            if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+                os.makedirs(os.path.dirname(exe), exist_ok=True)
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                                       "-L", os.path.join(ROOT, "rejit_b200"), "-lrejit_b200",
+                                       "-Wl,-rpath," + os.path.join(ROOT, "rejit_b200")])
+            fa_path = os.path.join(ROOT, "samples", "_build", "seq50.bin")
+            seq.tofile(fa_path)
+            outp = subprocess.run([exe, fa_path, str(e2e_reps)], capture_output=True, text=True, timeout=300)
+            os.remove(fa_path)
+            dropin = json.loads(outp.stdout.strip().split("\n")[-1])
+        except Exception as exc:                                   # noqa: BLE001
+            dropin = {"error": str(exc)[:200]}
+
+    # ---- the other configurations ----------------------------------------------------------------------
+    rows = None
+    if os.environ.get("RJ_BENCH_CONFIGS", "1") != "0":
+        rows = config_rows(rj, W, torch, peak, local_rank, rank, world, dist, tdev, max(3, min(args.steps, 5)))
+
+    # ---- MatchAllParallel on rank 0 over all N devices, against the compiled reference (N > 1) -----------
+    parallel = None
+    if world > 1:
         dist.barrier()
-    for ex in exchanges.values():
-        if hasattr(ex, "close"):
-            ex.close()
+        if rank == 0:
+            try:
+                whole = np.concatenate([W.fasta_sequence(FASTA_N, seed=42 + r2) for r2 in range(world)])
+                Lr = ref_lib()
+                parallel = {"n_gpus": world, "patterns": []}
+                for p in (patterns[0], patterns[4]):
+                    t0 = time.perf_counter()
+                    got = rj.Regej(p).match_all_array(whole, n_gpus=world)
+                    dt_ = time.perf_counter() - t0
+                    exp = None
+                    if Lr is not None:
+                        Lr.ref_set_flagset(1)
+                        h = Lr.ref_compile(p.encode())
+                        exp = int(Lr.ref_run_match_all_mt(h, ctypes.c_void_p(whole.ctypes.data), len(whole), min(16, os.cpu_count() or 1), 7))
+                        Lr.ref_free(h)
+                    parallel["patterns"].append({"pattern": p, "matches": int(got.shape[0]), "reference_matches": exp,
+                                                 "equal": exp is None or exp == int(got.shape[0]), "wall_ms": round(dt_ * 1e3, 2)})
+                parallel["fused_totals_equal_reference"] = None
+                if Lr is not None:
+                    Lr.ref_set_flagset(1)
+                    tot = []
+                    for p in patterns:
+                        h = Lr.ref_compile(p.encode())
+                        tot.append(int(Lr.ref_run_match_all_mt(h, ctypes.c_void_p(whole.ctypes.data), len(whole), min(16, os.cpu_count() or 1), 7)))
+                        Lr.ref_free(h)
+                    parallel["fused_totals_equal_reference"] = (tot == f_counts)
+                    parallel["reference_totals"] = tot
+            except Exception as exc:                               # noqa: BLE001
+                parallel = {"error": str(exc)[:200]}
+        dist.barrier()
+
+    if stitch is not None:
+        stitch.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    peak, peak_src = load_peaks()
-    m_total = sum(f_counts)
-    alg_bytes = len(buf) + 16.0 * m_total                     # text once + every match of the nine patterns
-    f_scan_avg = f_scan / args.steps
+    m_total = sum(f_counts) if world == 1 else None
+    # roofline of the set kernel on THIS rank's launches
+    own_counts = f_counts if world == 1 else None
+    f_scan_avg = f_scan / max(1, f_launches) if world > 1 else f_scan / args.steps
+    m_rank = sum(f_counts) / world if world > 1 else sum(f_counts)
+    alg_bytes = len(buf) + 16.0 * m_rank
     achieved = alg_bytes / (f_scan_avg / 1e3) / 1e9
-    n_launch_scan = args.steps * len(patterns)
-    alg_call = len(buf) + 16.0 * sum(counts) / len(patterns)
-    scan_call_avg = tot_scan / n_launch_scan
     cpu = None
     if world == 1:
         gbs, kind, cores, ccounts, what = cpu_reference_run(seq, patterns, 1, 2, 50_000_000)
-        cpu = {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": kind, "sample": what,
-               "match_counts_equal": ccounts == f_counts}
+        cpu = {"value": round(gbs / K, 4), "unit": "GB/s", "cores": cores, "kind": kind, "sample": what,
+               "value_per_pattern": round(gbs, 4), "match_counts_equal": ccounts == f_counts}
     set_kernel = "k_set_kmer" if "k-mer index" in rset.describe() and not os.environ.get("RJ_NO_KMER") else "k_set_tma"
-    config["how"] = ("the nine patterns are fused into one automaton (rejit_b200_match_all_set_device) and the text is "
-                     "scanned ONCE per step; GB/s counts the text once per pattern (k*N/time), as the nine separate "
-                     "MatchAll calls of the reference sample do; `per_pattern_calls` gives the same workload run as nine "
-                     "separate MatchAll calls")
-    line = {"metric": "GB/s text scanned (MatchAll)", "value": round(value_fused, 3), "unit": "GB/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+    config["how"] = ("the nine patterns are fused into one scan (rejit_b200_match_all_set_device): the text is read ONCE per step")
+    line = {"metric": "GB/s text scanned (MatchAll)", "value": round(value, 3), "unit": "GB/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
             "ms_per_step": round(f_ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-            "value_text_bytes_once": round(total_text / (f_ms_per_step / 1e3) / 1e9, 3),
-            "per_pattern_calls": {"value": round(value_calls, 3), "unit": "GB/s", "ms_per_step": round(ms_per_step, 4),
-                                  "gpu_launches": launches,
-                                  "roofline": {"kernel": "k_dfa_tma", "achieved": round(alg_call / (scan_call_avg / 1e3) / 1e9, 2),
-                                               "frac": round(alg_call / (scan_call_avg / 1e3) / 1e9 / peak, 4),
-                                               "avg_launch_ms": round(scan_call_avg, 5)}},
+            "value_per_pattern": round(K * value, 3),
+            "per_pattern_calls": calls,
             "e2e": {"value": round(e2e_fused, 3), "unit": "GB/s", "h2d_bytes_per_step": n_own,
-                    "d2h_bytes_per_step": int(16 * sum(f_counts) + 64 * len(patterns)),
+                    "d2h_bytes_per_step": int(e2e_d2h[0]), "api": "rejit_b200_text_upload + rejit_b200_match_all_set_text (C ABI)",
                     "how": "text uploaded once per step from pinned host memory (H2D inside the timed region), one fused "
                            "set call, every match list copied back (D2H inside)"},
-            "e2e_per_pattern_calls": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": n_own},
-            "e2e_per_call_upload": {"value": round(e2e_percall, 3), "unit": "GB/s",
-                                    "h2d_bytes_per_step": len(patterns) * n_own},
+            "e2e_per_call_upload": None if e2e_percall is None else
+            {"value": round(e2e_percall, 3), "unit": "GB/s", "h2d_bytes_per_step": K * n_own,
+             "api": "rejit_b200_match_all_alloc x 9 (pinned source)"},
+            "e2e_dropin": dropin,
             "nccl_stitch": None if nccl_ms is None else
-            {"value": round(len(patterns) * total_text / (nccl_ms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(nccl_ms, 4),
-             "how": "the same fused step with the stitch records exchanged by an NCCL all-gather instead of the shared-memory mailbox"},
+            {"value": round(total_text / (nccl_ms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(nccl_ms, 4),
+             "counts_equal": nccl_counts == f_counts,
+             "how": "the same fused step with the stitch records exchanged by an NCCL all-gather (torch.distributed) instead "
+                    "of the device-side neighbour exchange"},
+            "stitch_cascades": n_cascades,
+            "parallel_parity": parallel,
             "gpu_launches": f_launches,
             "roofline": {"bound": "hbm", "kernel": set_kernel, "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic_of(set_kernel),
@@ -621,13 +947,12 @@ def main():
                                            "ncu --set full capture of this workload)",
                          "note": "one launch = the scan of the text for all nine patterns plus the in-kernel finish "
                                  "(exact check of the hits, grid-wide exchange of the counts, matches written at their "
-                                 "final place, report to the host); a 50 MB text is 7.7 us of HBM time, the rest is the "
-                                 "integer pipe (the scan issues ~70 instructions per 512 bytes), start-up and the "
-                                 "finish: see DESIGN.md \u00a74",
+                                 "final place, report to the host); a 50 MB text is 7.7 us of HBM time: the fixed costs "
+                                 "(first byte after ~5 us, ordered finish ~10 us) dominate at this size, see the 625 MB row "
+                                 "of `configs` and DESIGN.md",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "avg_launch_ms": round(f_scan_avg, 5)},
-            "cpu_baseline": cpu, "clocks": clocks, "match_counts": f_counts,
-            "match_counts_equal_per_pattern_path": f_counts == counts, "wall_s": round(wall, 2)}
+            "cpu_baseline": cpu, "clocks": clocks, "match_counts": f_counts, "configs": rows, "wall_s": round(wall, 2)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

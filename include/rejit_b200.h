@@ -162,6 +162,11 @@ int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, con
 typedef struct rejit_b200_text rejit_b200_text;
 rejit_b200_text* rejit_b200_text_upload(int device, const char* text, size_t text_length,
                                         char* err, size_t err_length);
+/* The same from bytes that are already in device memory (a device-to-device copy
+ * into a padded buffer the text owns): a pipeline that produces its input on the
+ * device chains into ReplaceAll / set calls without a host round trip.            */
+rejit_b200_text* rejit_b200_text_from_device(int device, const void* d_text, size_t text_length,
+                                             char* err, size_t err_length);
 void rejit_b200_text_free(rejit_b200_text* text);
 int64_t rejit_b200_match_all_text(rejit_b200_program* program, const rejit_b200_text* text,
                                   uint64_t** out_pairs, rejit_b200_stats* stats,
@@ -193,6 +198,8 @@ rejit_b200_text* rejit_b200_replace_all_set_text(rejit_b200_program* const* prog
                                                  const size_t* with_lengths, int64_t* n_matches,
                                                  rejit_b200_stats* stats, char* err, size_t err_length);
 size_t rejit_b200_text_length(const rejit_b200_text* text);
+/* Where the text lives on its device (readable for 64 bytes past its length); valid until the text is freed. */
+const void* rejit_b200_text_device_ptr(const rejit_b200_text* text);
 int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capacity, char* err, size_t err_length);
 
 /* Pattern sets: several compiled patterns matched
@@ -236,6 +243,26 @@ int64_t rejit_b200_match_all_device_slab(rejit_b200_program* program, int device
                                          uint64_t base_offset, uint64_t* d_out_pairs, size_t capacity,
                                          const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
                                          rejit_b200_stats* stats, char* err, size_t err_length);
+
+/* ---- device-side stitch (one process per GPU) ----------------
+ * The "tiny allgather to stitch boundary matches" as peer-to-peer stores over
+ * NVLink: every rank owns an inbox in device memory; its CUDA IPC handle (64
+ * bytes) goes to the neighbouring ranks by whatever channel the job has (an
+ * all-gather of the handles at start-up), and rejit_b200_stitch_connect maps
+ * the neighbours' inboxes (NULL at the ends of the chain).  After a slab call
+ * rejit_b200_stitch_exchange sends the chain states that leave the slab
+ * (`leaving[j]`, the slab call's carry_out in GLOBAL offsets) into the right
+ * neighbour's device memory, waits for the states arriving from the left
+ * (`arrived[j]`) and sets bit j of *redo_mask when pattern j's arriving chain
+ * reaches into this slab (first owned start = slab_begin, global): only then
+ * must the slab call be repeated with carry_in = arrived.  One warp on the
+ * engine's stream; no host-to-host hop, no collective.  Every rank must call it
+ * the same number of times.  Returns 0, or -1 (a neighbour did not answer).     */
+int rejit_b200_stitch_open(int device, int rank, int world, void* handle_out /* 64 bytes */, char* err, size_t err_length);
+int rejit_b200_stitch_connect(int device, const void* left_handle, const void* right_handle, char* err, size_t err_length);
+void rejit_b200_stitch_close(int device);
+int rejit_b200_stitch_exchange(int device, int count, const rejit_b200_carry* leaving, uint64_t slab_begin,
+                               rejit_b200_carry* arrived, uint32_t* redo_mask, char* err, size_t err_length);
 
 void rejit_b200_free(void* ptr);
 

@@ -49,10 +49,11 @@ EXPORTED = [
     "rejit_b200_device_alloc", "rejit_b200_device_free", "rejit_b200_pinned_alloc",
     "rejit_b200_pinned_free", "rejit_b200_copy_to_device", "rejit_b200_copy_from_device",
     "rejit_b200_flush_l2", "rejit_b200_match_all_device", "rejit_b200_match_all_device_slab", "rejit_b200_free",
-    "rejit_b200_text_upload", "rejit_b200_text_free", "rejit_b200_match_all_text",
+    "rejit_b200_text_upload", "rejit_b200_text_from_device", "rejit_b200_text_free", "rejit_b200_match_all_text",
     "rejit_b200_set_create", "rejit_b200_set_free", "rejit_b200_set_describe", "rejit_b200_set_kmer_tables",
     "rejit_b200_match_all_set_text", "rejit_b200_match_all_set_device", "rejit_b200_match_all_set_device_slab",
-    "rejit_b200_replace_all", "rejit_b200_replace_all_text", "rejit_b200_replace_all_set_text", "rejit_b200_text_length", "rejit_b200_text_download",
+    "rejit_b200_replace_all", "rejit_b200_replace_all_text", "rejit_b200_replace_all_set_text",
+    "rejit_b200_stitch_open", "rejit_b200_stitch_connect", "rejit_b200_stitch_close", "rejit_b200_stitch_exchange", "rejit_b200_text_length", "rejit_b200_text_device_ptr", "rejit_b200_text_download",
 ]
 
 
@@ -109,6 +110,8 @@ def lib():
     L.rejit_b200_free.argtypes = [vp]
     L.rejit_b200_text_upload.argtypes = [ctypes.c_int, vp, sz, cp, sz]
     L.rejit_b200_text_upload.restype = vp
+    L.rejit_b200_text_from_device.argtypes = [ctypes.c_int, vp, sz, cp, sz]
+    L.rejit_b200_text_from_device.restype = vp
     L.rejit_b200_text_free.argtypes = [vp]
     L.rejit_b200_match_all_text.argtypes = [vp, vp, ctypes.POINTER(u64p), ctypes.POINTER(Stats), cp, sz]
     L.rejit_b200_match_all_text.restype = ctypes.c_int64
@@ -135,8 +138,15 @@ def lib():
     L.rejit_b200_replace_all_set_text.argtypes = [ctypes.POINTER(vp), ctypes.c_int, vp, ctypes.POINTER(cp), ctypes.POINTER(sz),
                                                   ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(Stats), cp, sz]
     L.rejit_b200_replace_all_set_text.restype = vp
+    L.rejit_b200_stitch_open.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, cp, sz]
+    L.rejit_b200_stitch_connect.argtypes = [ctypes.c_int, vp, vp, cp, sz]
+    L.rejit_b200_stitch_close.argtypes = [ctypes.c_int]
+    L.rejit_b200_stitch_exchange.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Carry), ctypes.c_uint64,
+                                             ctypes.POINTER(Carry), ctypes.POINTER(ctypes.c_uint32), cp, sz]
     L.rejit_b200_text_length.argtypes = [vp]
     L.rejit_b200_text_length.restype = sz
+    L.rejit_b200_text_device_ptr.argtypes = [vp]
+    L.rejit_b200_text_device_ptr.restype = vp
     L.rejit_b200_text_download.argtypes = [vp, vp, sz, cp, sz]
     _lib = L
     return L
@@ -153,9 +163,14 @@ def _as_bytes(x) -> bytes:
 class DeviceText:
     """Text resident in HBM (16-byte aligned, padded allocation)."""
 
-    def __init__(self, data=None, device: int = 0, nbytes: Optional[int] = None):
+    def __init__(self, data=None, device: int = 0, nbytes: Optional[int] = None, borrowed_ptr: Optional[int] = None):
         L = lib()
         self.device = device
+        if borrowed_ptr is not None:
+            # a device buffer owned by the caller (16-byte aligned, readable 32 bytes past nbytes: rejit_b200.h)
+            self.nbytes, self.ptr, self._borrowed = int(nbytes), ctypes.c_void_p(borrowed_ptr), True
+            return
+        self._borrowed = False
         self.nbytes = len(data) if data is not None else int(nbytes)
         self.ptr = L.rejit_b200_device_alloc(device, max(self.nbytes, 1))
         if not self.ptr:
@@ -179,7 +194,8 @@ class DeviceText:
 
     def free(self):
         if self.ptr:
-            lib().rejit_b200_device_free(self.device, self.ptr)
+            if not getattr(self, "_borrowed", False):
+                lib().rejit_b200_device_free(self.device, self.ptr)
             self.ptr = None
 
     def __del__(self):
@@ -193,10 +209,17 @@ class Text:
     """An uploaded text (rejit_b200_text): searched and rewritten on the device;
     `replace_all` returns a new Text, so substitutions chain without host copies."""
 
-    def __init__(self, data=None, device: int = 0, _handle=None):
+    def __init__(self, data=None, device: int = 0, _handle=None, device_ptr=None, nbytes: int = 0):
         L = lib()
         if _handle is not None:
             self._h = ctypes.c_void_p(_handle)
+            return
+        if device_ptr is not None:                 # bytes already on the device: copied into a text of its own
+            err = ctypes.create_string_buffer(512)
+            h = L.rejit_b200_text_from_device(device, ctypes.c_void_p(device_ptr), nbytes, err, len(err))
+            if not h:
+                raise RejitError(err.value.decode("latin-1"))
+            self._h = ctypes.c_void_p(h)
             return
         if hasattr(data, "ctypes"):
             import numpy as np
@@ -213,6 +236,9 @@ class Text:
 
     def __len__(self) -> int:
         return int(lib().rejit_b200_text_length(self._h))
+
+    def device_ptr(self) -> int:
+        return int(lib().rejit_b200_text_device_ptr(self._h) or 0)
 
     def download(self) -> bytes:
         n = len(self)

@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    extra = os.environ.get("RJ_NVCC_EXTRA", "").split()       # tuning builds only (e.g. -DRJ_KMER_PROBE)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
           [os.path.join(CSRC, s) for s in HOST_SOURCES + CUDA_SOURCES]
     print("[rejit_b200.build]", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)

@@ -23,6 +23,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -76,6 +78,77 @@ struct Buffer {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// A small pool of persistent worker threads: parallel-for over task indices.  Used to stage pageable host text
+// into pinned chunks (several memcpy streams keep PCIe busy) and to drive one slab per device in MatchAllParallel
+// (round 1 spawned threads per call).
+// ---------------------------------------------------------------------------
+class WorkerPool {
+ public:
+  static WorkerPool& Staging() { static WorkerPool* pool = new WorkerPool(12); return *pool; }   // memcpy streams
+  static WorkerPool& Devices() { static WorkerPool* pool = new WorkerPool(15); return *pool; }   // one task per GPU
+  int size() const { return (int)threads_.size(); }
+  // fn(i) for i in [0, n), on up to `width` threads (the caller works too); returns when all are done
+  void Run(int n, int width, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    if (n == 1 || width <= 1 || threads_.empty()) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::unique_lock<std::mutex> gate(run_mu_);              // one parallel-for at a time
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn; next_ = 0; total_ = n; done_ = 0;
+      helpers_ = std::min<int>(width - 1, (int)threads_.size());
+      ++epoch_;
+    }
+    cv_.notify_all();
+    Work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return done_ == total_ && active_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  explicit WorkerPool(unsigned cap) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = (int)std::max(1u, std::min(cap, hw > 2 ? hw / 2 : 1u));
+    for (int i = 0; i < n; ++i) threads_.emplace_back([this, i] { Loop(i); });
+    for (auto& t : threads_) t.detach();
+  }
+  void Work() {
+    for (;;) {
+      int i;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (next_ >= total_) return;
+        i = next_++;
+      }
+      (*fn_)(i);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (++done_ == total_) done_cv_.notify_all();
+    }
+  }
+  void Loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (id >= helpers_ || !fn_) continue;
+        ++active_;
+      }
+      Work();
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--active_ == 0) done_cv_.notify_all();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, total_ = 0, done_ = 0, helpers_ = 0, active_ = 0;
+  uint64_t epoch_ = 0;
+};
+
 // finish area inside DeviceContext::status
 constexpr size_t kFinMaxSegments = 1024;
 constexpr size_t kFinSyncOffset = 128, kFinLastOffset = 160, kFinTotalOffset = 168, kFinLastNeOffset = 176,
@@ -105,11 +178,24 @@ class DeviceContext {
   Buffer fscratch;                    // label scratch for re-entrant patterns
   // fused pattern sets
   Buffer set_sub_b, set_sub_e, set_sub_count, set_dense_b, set_dense_e, set_reach, set_take, set_fin, set_slot,
-      set_out, set_status, set_counts, kmer_xchg, kmer_stage;
+      set_out, set_status, set_counts, kmer_xchg, kmer_stage, kmer_probe;
   PipelineStatus* h_set_status = nullptr;      // pinned + mapped, 32 entries
   PipelineStatus* h_set_status_dev = nullptr;
   Buffer flush;
+  // pinned staging ring for pageable host texts (UploadHostText)
+  static constexpr int kStageBufs = 12;
+  static constexpr size_t kStageBytes = 2u << 20;
+  uint8_t* stage_buf[kStageBufs] = {nullptr};
+  cudaEvent_t stage_ev[kStageBufs] = {nullptr};
   Buffer trans_tab, trans_len, trans_off, trans_counts;   // byte -> string table of ReplaceAllSetDevice and its tile sums
+  // device-side stitch (one process per GPU): my inbox, the neighbours' inboxes mapped through CUDA IPC
+  void* stitch_inbox = nullptr;
+  void* stitch_right = nullptr;
+  void* stitch_left = nullptr;
+  int stitch_rank = 0, stitch_world = 1;
+  unsigned int stitch_step = 0;
+  StitchReport* h_stitch = nullptr;
+  StitchReport* h_stitch_dev = nullptr;
   Buffer em_records;                  // look-back records of the single-pass scans (scan_emit.cuh)
   bool emit = true;                   // single-pass scan + emit available (RJ_NO_EMIT=1: the round-1 pipelines only)
   PipelineStatus* h_status = nullptr; // pinned + mapped: the resolve kernel writes it, the host spins on seq
@@ -395,6 +481,11 @@ bool CopyToDevice(int device, void* dst, const void* src, size_t bytes, std::str
   RJ_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
   return true;
 }
+bool CopyOnDevice(int device, void* dst, const void* src, size_t bytes, std::string* error) {
+  RJ_TRY(cudaSetDevice(device));
+  RJ_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+  return true;
+}
 bool CopyFromDevice(int device, void* dst, const void* src, size_t bytes, std::string* error) {
   RJ_TRY(cudaSetDevice(device));
   RJ_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
@@ -677,6 +768,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       const uint64_t first_start = std::min<uint64_t>(slab.own.own_begin, n);
       uint64_t last_pos = slab.own.own_end ? slab.own.own_end - 1 : 0;            // last owned start
       if (ca.strategy == ScanStrategy::LiteralWindow) last_pos += (uint64_t)ca.window_hi + 1;   // ... or needle hit
+      if (ca.strategy != ScanStrategy::Generic) last_pos += 3;      // a literal is tested by the lane that holds its fourth byte
       last_pos = std::min<uint64_t>(last_pos, n);
       em.tile0 = first_start / kEmTileBytes;
       em.ntiles = std::max<uint64_t>(last_pos / kEmTileBytes, em.tile0) - em.tile0 + 1;
@@ -695,7 +787,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       lit.needle = dp->needle;
       lit.m = dp->needle_len; lit.p4 = dp->p4; lit.pmask = dp->pmask;
       lit.win_lo = ca.window_lo; lit.win_hi = ca.window_hi;
-      const int blocks = (int)std::min<uint64_t>(em.ntiles, (uint64_t)c->sm_count * 4);
+      const int blocks = (int)std::min<uint64_t>((em.ntiles + kEmWarps - 1) / kEmWarps, (uint64_t)c->sm_count * 4);
       if (ca.strategy == ScanStrategy::Literal) {
         if (dp->needle_len >= 4)
           k_scan_emit<kEmLiteral, true><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
@@ -1003,6 +1095,46 @@ int64_t MatchAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_
 }
 
 namespace {
+// Host text -> device, on the context's stream.  Pinned (or registered) memory goes in one asynchronous copy.
+// Pageable memory — what a caller of Regej::MatchAll(const char*, size_t, ...) hands over — is staged by several
+// threads through a ring of pinned 2 MB chunks, so that the page-locked copies keep PCIe busy instead of the
+// driver's single staging stream: a std::string uploads at close to the pinned rate.
+bool UploadHostText(DeviceContext* c, void* d_dst, const uint8_t* src, size_t len, std::string* error) {
+  if (!len) return true;
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (pinned || len < (4u << 20)) {
+    RJ_TRY(cudaMemcpyAsync(d_dst, src, len, cudaMemcpyHostToDevice, c->stream));
+    return true;
+  }
+  if (!c->stage_buf[0]) {
+    for (int i = 0; i < DeviceContext::kStageBufs; ++i) {
+      RJ_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->stage_buf[i]), DeviceContext::kStageBytes, cudaHostAllocDefault));
+      RJ_TRY(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t chunk = DeviceContext::kStageBytes;
+  const int n_chunks = (int)((len + chunk - 1) / chunk);
+  std::atomic<int> failed{0};
+  std::mutex ring_mu[DeviceContext::kStageBufs];
+  const int device = c->device;
+  // chunk i goes through ring buffer i % kStageBufs; a buffer is reused once its previous copy has left it
+  WorkerPool::Staging().Run(n_chunks, 8, [&](int i) {
+    if (failed.load()) return;
+    cudaSetDevice(device);
+    const int b = i % DeviceContext::kStageBufs;
+    const size_t off = (size_t)i * chunk, n = std::min(chunk, len - off);
+    std::lock_guard<std::mutex> lk(ring_mu[b]);
+    if (cudaEventSynchronize(c->stage_ev[b]) != cudaSuccess) { failed = 1; return; }
+    memcpy(c->stage_buf[b], src + off, n);
+    if (cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, c->stage_buf[b], n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaEventRecord(c->stage_ev[b], c->stream) != cudaSuccess) failed = 1;
+  });
+  if (failed.load()) { Check(cudaGetLastError(), "staged upload", error); if (error && error->empty()) *error = "rejit_b200: staged upload failed"; return false; }
+  return true;
+}
+
 // Device work for one slab of a host text: copy [lo, hi) of the text in, scan
 // the owned starts, copy the matches out.
 bool MatchSlabFromHost(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8_t* text, uint64_t n,
@@ -1020,7 +1152,7 @@ bool MatchSlabFromHost(DeviceContext* c, Program* prog, DeviceProgram* dp, const
   if (!last && ca.nfa.max_len != kInfLen) hi = std::min<uint64_t>(n, own_hi + ca.nfa.max_len + 2);
   uint64_t len = hi - lo;
   if (!c->text.Reserve(len + 64, error)) return false;
-  if (len) RJ_TRY(cudaMemcpyAsync(c->text.p, text + lo, len, cudaMemcpyHostToDevice, c->stream));
+  if (!UploadHostText(c, c->text.p, text + lo, len, error)) return false;
   Slab slab;
   slab.own.own_begin = own_lo - lo;
   slab.own.own_end = (last ? n + 1 : own_hi) - lo;
@@ -1331,6 +1463,11 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           run.base_offset = base_offset;
           run.host_records = c->h_fin_dev;
           run.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+#ifdef RJ_KMER_PROBE
+          if (!c->kmer_probe.Reserve((size_t)blocks * 65 * 8, error)) return -1;
+          cudaMemsetAsync(c->kmer_probe.p, 0, (size_t)blocks * 65 * 8, s);
+          run.probe = c->kmer_probe.as<unsigned long long>();
+#endif
           CarrySet carries;
           for (int j = 0; j < 32; ++j) carries.c[j] = (carry_in && j < K) ? carry_in[j] : Carry();
           uint64_t n_arg = n;
@@ -1343,6 +1480,36 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
                      "cooperative launch", error)) return -1;
           if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }
           if (!Check(cudaGetLastError(), "launch", error) || !WaitFinRecords(c, K, run.seq, error)) return -1;
+#ifdef RJ_KMER_PROBE
+          {
+            // tuning builds only: when did the warps start / stop streaming, when did the CTAs leave (ns after the first start)
+            std::vector<unsigned long long> pr((size_t)blocks * 65);
+            cudaStreamSynchronize(s);
+            cudaMemcpy(pr.data(), run.probe, pr.size() * 8, cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull;
+            for (int b2 = 0; b2 < blocks * 32; ++b2) if (pr[(size_t)b2 * 2]) t0 = std::min(t0, pr[(size_t)b2 * 2]);
+            std::vector<unsigned long long> ends, cta_scan, cta_exit, starts;
+            std::vector<std::vector<unsigned long long>> by_wid(32);
+            for (int b2 = 0; b2 < blocks; ++b2) {
+              unsigned long long mx = 0;
+              for (int w = 0; w < 32; ++w) {
+                const unsigned long long a = pr[((size_t)b2 * 32 + w) * 2], e = pr[((size_t)b2 * 32 + w) * 2 + 1];
+                if (!a || !e) continue;
+                starts.push_back(a - t0); ends.push_back(e - t0); by_wid[w].push_back(e - t0);
+                mx = std::max(mx, e - t0);
+              }
+              cta_scan.push_back(mx);
+              cta_exit.push_back(pr[(size_t)blocks * 64 + b2] - t0);
+            }
+            auto q = [](std::vector<unsigned long long> v, double f) { if (v.empty()) return 0ull; std::sort(v.begin(), v.end()); return v[(size_t)(f * (v.size() - 1))]; };
+            fprintf(stderr, "[kmer probe] n=%llu rows/warp=%llu | warp scan start med %llu | warp scan end min %llu med %llu p90 %llu max %llu | CTA scan end (slowest warp) min %llu med %llu max %llu | CTA exit med %llu max %llu (ns)\n",
+                    (unsigned long long)n, (unsigned long long)rows_per_warp, q(starts, 0.5), q(ends, 0.0), q(ends, 0.5), q(ends, 0.9), q(ends, 1.0),
+                    q(cta_scan, 0.0), q(cta_scan, 0.5), q(cta_scan, 1.0), q(cta_exit, 0.5), q(cta_exit, 1.0));
+            std::string line = "[kmer probe] median scan end by warp id:";
+            for (int w = 0; w < 32; ++w) line += " " + std::to_string(q(by_wid[w], 0.5));
+            fprintf(stderr, "%s\n", line.c_str());
+          }
+#endif
           bool redo = false, give_up = false, dense = false, grow_stage = false;
           uint64_t need = 0;
           for (int j = 0; j < K; ++j) {
@@ -1515,19 +1682,14 @@ int64_t MatchAllHostMultiGpu(Program* prog, const uint8_t* text, uint64_t n, int
   std::vector<RunStats> st(g);
   auto bounds = [&](int i) { return (n / g) * (uint64_t)i; };
   // round 1: every slab resolved as if no match from the left neighbour reached into it
-  {
-    std::vector<std::thread> pool;
-    for (int i = 0; i < g; ++i)
-      pool.emplace_back([&, i]() {
-        DeviceContext* c = ContextFor(i, &errs[i]);
-        DeviceProgram* dp = c ? prog->OnDevice(i, &errs[i]) : nullptr;
-        if (!c || !dp) { ok[i] = 0; return; }
-        uint64_t lo = bounds(i), hi = (i + 1 == g) ? n : bounds(i + 1);
-        Carry in{lo, kNoMatch};
-        ok[i] = MatchSlabFromHost(c, prog, dp, text, n, lo, hi, i + 1 == g, in, &carry_out[i], &part[i], &st[i], &errs[i]);
-      });
-    for (auto& t : pool) t.join();
-  }
+  WorkerPool::Devices().Run(g, g, [&](int i) {               // persistent threads, one slab per device
+    DeviceContext* c = ContextFor(i, &errs[i]);
+    DeviceProgram* dp = c ? prog->OnDevice(i, &errs[i]) : nullptr;
+    if (!c || !dp) { ok[i] = 0; return; }
+    uint64_t lo = bounds(i), hi = (i + 1 == g) ? n : bounds(i + 1);
+    Carry in{lo, kNoMatch};
+    ok[i] = MatchSlabFromHost(c, prog, dp, text, n, lo, hi, i + 1 == g, in, &carry_out[i], &part[i], &st[i], &errs[i]);
+  });
   for (int i = 0; i < g; ++i) if (!ok[i]) { if (error) *error = errs[i]; return -1; }
   // stitch: slab i must be redone when the chain arriving from the left differs
   // from the assumption (cur == slab start, no abutting non-empty match)
@@ -1763,6 +1925,104 @@ int64_t ReplaceAllHost(int device, Program* prog, const uint8_t* text, uint64_t 
   if (!ok) { free(*out); *out = nullptr; if (error && error->empty()) *error = "rejit_b200: out of memory"; return -1; }
   *out_len = len;
   return m;
+}
+
+// ===========================================================================
+// device-side stitch (scan_emit.cuh: k_stitch)
+// ===========================================================================
+bool StitchOpen(int device, int rank, int world, void* handle64, std::string* error) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return false;
+  std::lock_guard<std::mutex> lk(c->mu);
+  RJ_TRY(cudaSetDevice(c->device));
+  if (!c->stitch_inbox) {
+    RJ_TRY(cudaMalloc(&c->stitch_inbox, kStitchInboxBytes));
+    RJ_TRY(cudaHostAlloc(&c->h_stitch, sizeof(StitchReport), cudaHostAllocMapped));
+    RJ_TRY(cudaHostGetDevicePointer(&c->h_stitch_dev, c->h_stitch, 0));
+  }
+  RJ_TRY(cudaMemset(c->stitch_inbox, 0, kStitchInboxBytes));
+  memset(c->h_stitch, 0, sizeof(StitchReport));
+  c->stitch_rank = rank;
+  c->stitch_world = world;
+  c->stitch_step = 0;
+  cudaIpcMemHandle_t h;
+  RJ_TRY(cudaIpcGetMemHandle(&h, c->stitch_inbox));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return true;
+}
+
+bool StitchConnect(int device, const void* left_handle64, const void* right_handle64, std::string* error) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return false;
+  std::lock_guard<std::mutex> lk(c->mu);
+  RJ_TRY(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  if (left_handle64 && !c->stitch_left) {
+    memcpy(&h, left_handle64, 64);
+    RJ_TRY(cudaIpcOpenMemHandle(&c->stitch_left, h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  if (right_handle64 && !c->stitch_right) {
+    memcpy(&h, right_handle64, 64);
+    RJ_TRY(cudaIpcOpenMemHandle(&c->stitch_right, h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  return true;
+}
+
+void StitchClose(int device) {
+  std::string err;
+  DeviceContext* c = ContextFor(device, &err);
+  if (!c) return;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->stitch_left) cudaIpcCloseMemHandle(c->stitch_left);
+  if (c->stitch_right) cudaIpcCloseMemHandle(c->stitch_right);
+  c->stitch_left = c->stitch_right = nullptr;
+}
+
+bool StitchExchange(int device, int K, const Carry* leaving, uint64_t slab_begin, Carry* arrived, uint32_t* redo_mask,
+                    std::string* error) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return false;
+  if (!c->stitch_inbox || K < 1 || K > 32) { if (error) *error = "rejit_b200: stitch not opened (or more than 32 patterns)"; return false; }
+  std::lock_guard<std::mutex> lk(c->mu);
+  RJ_TRY(cudaSetDevice(c->device));
+  StitchArgs a{};
+  a.K = K;
+  a.rank = c->stitch_rank;
+  for (int j = 0; j < K; ++j) {
+    // a chain that has not moved past the slab's first byte cannot reach the neighbour: nothing to say
+    const bool has = leaving[j].cur > slab_begin || (leaving[j].tail != kNoMatch);
+    a.sent_cur[j] = has ? leaving[j].cur : 0;
+    if (has) a.sent_has |= 1u << j;
+    if (has && leaving[j].tail == leaving[j].cur) a.sent_ne |= 1u << j;
+  }
+  a.slab_begin = slab_begin;
+  a.inbox = static_cast<uint4*>(c->stitch_inbox);
+  a.right_inbox = static_cast<uint4*>(c->stitch_right);
+  a.left_ack = c->stitch_left ? reinterpret_cast<unsigned int*>(c->stitch_left) + kStitchAckWord : nullptr;
+  a.step = ++c->stitch_step ? c->stitch_step : ++c->stitch_step;
+  a.report = c->h_stitch_dev;
+  k_stitch<<<1, 32, 0, c->stream>>>(a);
+  RJ_TRY(cudaGetLastError());
+  volatile StitchReport* r = c->h_stitch;
+  uint64_t spins = 0;
+  while (r->step != a.step) {
+    if ((++spins & 0x3FFF) == 0) {
+      cudaError_t q = cudaStreamQuery(c->stream);
+      if (q == cudaSuccess) { if (r->step == a.step) break; if (error) *error = "rejit_b200: the stitch kernel did not report"; return false; }
+      if (q != cudaErrorNotReady) { Check(q, "cudaStreamQuery", error); return false; }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (r->status & 2u) { if (error) *error = "rejit_b200: a neighbouring rank did not answer the stitch"; return false; }
+  for (int j = 0; j < K; ++j) {
+    arrived[j].cur = r->arrived_cur[j];
+    arrived[j].tail = ((r->arrived_ne >> j) & 1u) ? r->arrived_cur[j] : kNoMatch;
+  }
+  *redo_mask = r->redo;
+  return true;
 }
 
 int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error) {

@@ -54,6 +54,7 @@ void* PinnedAlloc(size_t bytes);
 void PinnedFree(void* p);
 bool CopyToDevice(int device, void* dst, const void* src, size_t bytes, std::string* error);
 bool CopyFromDevice(int device, void* dst, const void* src, size_t bytes, std::string* error);
+bool CopyOnDevice(int device, void* dst, const void* src, size_t bytes, std::string* error);
 void FlushL2(int device);                              // writes a buffer larger than L2
 
 // ---- the hot path -----------------------------------------------------------
@@ -140,6 +141,17 @@ int64_t ReplaceAllHost(int device, Program* prog, const uint8_t* text, uint64_t 
 
 // MatchFirst (pair != nullptr) / MatchAnywhere with early exit: 1 / 0, or -1 on error.
 int MatchFirstHost(int device, Program* prog, const uint8_t* text, uint64_t n, uint64_t pair[2], std::string* error);
+
+// Device-side stitch for one-process-per-GPU sharding: StitchOpen creates this rank's inbox in
+// device memory and returns its CUDA IPC handle (64 bytes) for the neighbours; StitchConnect maps the neighbours'
+// inboxes (either may be null at the ends of the chain); StitchExchange sends the chain states that leave this
+// rank's slab (global offsets) into the right neighbour's device memory over NVLink, waits for the states arriving
+// from the left and says for which patterns (bit mask) the arriving chain reaches into the slab.
+bool StitchOpen(int device, int rank, int world, void* handle64, std::string* error);
+bool StitchConnect(int device, const void* left_handle64, const void* right_handle64, std::string* error);
+void StitchClose(int device);
+bool StitchExchange(int device, int K, const Carry* leaving, uint64_t slab_begin, Carry* arrived, uint32_t* redo_mask,
+                    std::string* error);
 
 // MatchFull: 1 / 0, or -1 on error.
 int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error);

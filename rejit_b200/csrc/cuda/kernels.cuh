@@ -1276,13 +1276,30 @@ struct KmerRun {
   uint2* stage;                        // [gridDim.x * 32][stage_cap]: matches of a warp that no longer fit its shared list
   uint32_t stage_cap;
   unsigned int* gsync;                 // [0] flags, [1] CTAs done; zero between calls (the reporting CTA clears them)
-  unsigned long long* gfinal;          // [32][2]: per member {matches, last end}, written by the CTA with the highest index
+  unsigned long long* gfinal;          // [32][2]: per member {matches, last end}, written by the CTA with the highest index;
+                                       // [64]: the call's flags (for the stitch kernel that may follow, scan_emit.cuh)
   uint64_t* out_pairs;                 // member j's pairs start at out_pairs + j * 2 * out_stride
   uint64_t out_stride, out_cap, base_offset;
   FinRecord* host_records;
   unsigned int seq;
   int has_carry;                       // some member's chain arrives from the left (CarrySet is read only then)
+#ifdef RJ_KMER_PROBE
+  unsigned long long* probe;           // tuning builds only: [grid][32][2] globaltimer at scan start / end, then [grid] at exit
+#endif
 };
+
+#ifdef RJ_KMER_PROBE
+#define RJ_KMER_STAMP(slot)                                                                          \
+  do {                                                                                               \
+    if (run.probe && lane == 0) {                                                                    \
+      unsigned long long t_;                                                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                         \
+      run.probe[((size_t)blockIdx.x * 32 + warp) * 2 + (slot)] = t_;                                 \
+    }                                                                                                \
+  } while (0)
+#else
+#define RJ_KMER_STAMP(slot) do {} while (0)
+#endif
 
 // R consecutive ends per lookup: a window of 7 + R codes indexes the bitmap
 constexpr int kKmerEnds = kKmerR;                                   // host/automaton.h
@@ -1293,9 +1310,9 @@ constexpr uint32_t kKmerBitmapBytes = 4u << kKmerWordBits;          // 32 KB (R 
 constexpr uint32_t kKmerThreads = 1024;
 constexpr uint32_t kKmerWarps = kKmerThreads / 32;
 constexpr uint32_t kKmerMaxRowsPerCta = 1u << 19;  // offsets inside a CTA's rows fit 28 bits (256 MB of text per CTA)
-constexpr uint32_t kKmerWarpRaw = 64;              // 16-byte groups with a hit / hits a warp collects before it checks them
-constexpr uint32_t kKmerFlushAt = 32;              // ... it stops streaming and checks them at this many groups
-constexpr uint32_t kKmerStageSm = 64;              // checked matches a warp keeps in shared memory
+constexpr uint32_t kKmerWarpRaw = 128;             // 16-byte groups with a hit / hits a warp collects before it checks them
+constexpr uint32_t kKmerFlushAt = 96;              // ... it stops streaming and checks them at this many groups
+constexpr uint32_t kKmerStageSm = 128;             // checked matches a warp keeps in shared memory
 constexpr uint32_t kKmerSmemFixed = kKmerBitmapBytes + kKmerWarps * (kKmerWarpRaw * 8 + kKmerStageSm * 8) +
                                     4 * kKmerWarps * 32 * 4 + kKmerHashSlots * 8 + kKmerTabWords * 4 + 2048;
 // first letter (0..15) of the ends lookup t answers: x, x+1, .., x+R-1; the last lookup is pulled back into the group
@@ -1498,17 +1515,9 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
     }
   };
   uint32_t r = w_row0;
-  bool reload = false;
+  RJ_KMER_STAMP(0);
 #pragma unroll 1
   for (;;) {
-    if (reload) {
-      // back from checking hits: the rows in flight were dropped, fetch them again (they are in L2)
-      v0 = r < w_load1 ? __ldg(src + (size_t)(r - w_row0) * 32) : zero4;
-      v1 = r + 1 < w_load1 ? __ldg(src + (size_t)(r + 1 - w_row0) * 32) : zero4;
-      v2 = r + 2 < w_load1 ? __ldg(src + (size_t)(r + 2 - w_row0) * 32) : zero4;
-      v3 = r + 3 < w_load1 ? __ldg(src + (size_t)(r + 3 - w_row0) * 32) : zero4;
-    }
-    reload = true;
     // ---- stream until the list of groups with a hit is half full ------------------------------------
 #pragma unroll 1
     for (; r + 4 <= w_row1 && n_ent < kKmerFlushAt; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
@@ -1518,6 +1527,8 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
       if (r + 2 < w_row1) row(v2, r + 2);
       r = w_row1;
     }
+    // (v0 .. v3 already hold the four rows that follow — every row() refilled its register — and stay in flight
+    // while the hits are checked)
     // ---- my hits so far: exact check, per-member counts ---------------------------------------------
     if (n_ent > kKmerWarpRaw) { flags |= kFinDense; n_ent = 0; }
     __syncwarp();
@@ -1544,60 +1555,70 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
     n_ent = 0;
     __syncwarp();
     const uint32_t n_cand = R * n_raw;
-    for (uint32_t i0 = 0; i0 < n_cand; i0 += 32) {
-      // room for 32 more checked matches in my shared list, else it moves to the staging area
-      if (n_sm + 32 > kKmerStageSm) {
+    // candidate R h + k = end k of hit h.  Two batches of 32 are checked at a time (their text reads are in flight
+    // together), then accounted for one after the other, in position order.
+    for (uint32_t i0 = 0; i0 < n_cand; i0 += 64) {
+      // room for 64 more checked matches in my shared list, else it moves to the staging area
+      if (n_sm + 64 > kKmerStageSm) {
         for (uint32_t q = lane; q < n_sm; q += 32)
           if (n_gl + q < run.stage_cap) my_gstage[n_gl + q] = my_stage[q];
         n_gl += n_sm;
         n_sm = 0;
         __syncwarp();
       }
-      const uint32_t i = i0 + lane;
-      uint32_t m = 0, erel = 0;
-      if (i < n_cand) {
-        const uint32_t h = i / R, k = i - h * R;
-        const uint32_t raw = my_raw[h];
-        erel = (raw & 0x3FFFFFFFu) + k;
-        const uint64_t e = cta_base + erel;
-        if (k >= (raw >> 30) && e <= n) {
-          const uint32_t mv = KmerVerify(text, e, fm, mult, km.shift, km.canon, from_list, km.mask16, s_hkey, s_hval, s_lenle);
-          for (uint32_t mm = mv; mm; mm &= mm - 1) {
-            const int j = __ffs(mm) - 1;
-            const uint64_t b = e - s_mlen[j];
-            if (b >= range.own_begin && b < range.own_end) {
-              m |= 1u << j;
-              if (run.has_carry && b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
-            }
+      uint32_t mm2[2] = {0, 0}, er2[2] = {0, 0};
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t i = i0 + 32 * half + lane;
+        if (i < n_cand) {
+          const uint32_t h = i / R, k = i - h * R;
+          const uint32_t raw = my_raw[h];
+          er2[half] = (raw & 0x3FFFFFFFu) + k;
+          const uint64_t e = cta_base + er2[half];
+          if (k >= (raw >> 30) && e <= n)
+            mm2[half] = KmerVerify(text, e, fm, mult, km.shift, km.canon, from_list, km.mask16, s_hkey, s_hval, s_lenle);
+        }
+      }
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t erel = half ? er2[1] : er2[0];
+        uint32_t m = 0;
+        for (uint32_t mm = half ? mm2[1] : mm2[0]; mm; mm &= mm - 1) {
+          const int j = __ffs(mm) - 1;
+          const uint64_t b = cta_base + erel - s_mlen[j];
+          if (b >= range.own_begin && b < range.own_end) {
+            m |= 1u << j;
+            if (run.has_carry && b < carries.c[j].cur) flags |= kFinOverlap;    // the chain arriving from the left reaches past it
           }
         }
-      }
-      // a candidate overlaps an earlier one of the same member iff that one ends less than a match length before
-      // it: its predecessor in this pass, the last one of the passes before; other warps and CTAs: the seam checks
-      for (uint32_t todo = __reduce_or_sync(kFullMask, m); todo; todo &= todo - 1) {
-        const int j = __ffs(todo) - 1;
-        const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
-        const uint32_t L = s_mlen[j];
-        const int lo = __ffs(bal) - 1, hi = 31 - __clz(bal);
-        const uint32_t e_lo = __shfl_sync(kFullMask, erel, lo), e_hi = __shfl_sync(kFullMask, erel, hi);
-        const uint32_t before = bal & ((1u << lane) - 1u);
-        const int pl = before ? 31 - __clz(before) : lane;
-        const uint32_t e_prev = __shfl_sync(kFullMask, erel, pl);
-        if (((m >> j) & 1u) && before && e_prev + L > erel) flags |= kFinOverlap;
-        if (lane == j) {
-          if (cj && lastj + L > e_lo) flags |= kFinOverlap;
-          if (!cj) firstj = e_lo;
-          lastj = e_hi;
-          cj += __popc(bal);
+        // a candidate overlaps an earlier one of the same member iff that one ends less than a match length before
+        // it: its predecessor in this pass, the last one of the passes before; other warps and CTAs: the seam checks
+        for (uint32_t todo = __reduce_or_sync(kFullMask, m); todo; todo &= todo - 1) {
+          const int j = __ffs(todo) - 1;
+          const uint32_t bal = __ballot_sync(kFullMask, (m >> j) & 1u);
+          const uint32_t L = s_mlen[j];
+          const int lo = __ffs(bal) - 1, hi = 31 - __clz(bal);
+          const uint32_t e_lo = __shfl_sync(kFullMask, erel, lo), e_hi = __shfl_sync(kFullMask, erel, hi);
+          const uint32_t before = bal & ((1u << lane) - 1u);
+          const int pl = before ? 31 - __clz(before) : lane;
+          const uint32_t e_prev = __shfl_sync(kFullMask, erel, pl);
+          if (((m >> j) & 1u) && before && e_prev + L > erel) flags |= kFinOverlap;
+          if (lane == j) {
+            if (cj && lastj + L > e_lo) flags |= kFinOverlap;
+            if (!cj) firstj = e_lo;
+            lastj = e_hi;
+            cj += __popc(bal);
+          }
         }
+        const uint32_t balm = __ballot_sync(kFullMask, m != 0);
+        if (m) my_stage[n_sm + __popc(balm & lt_mask)] = make_uint2(erel, m);
+        n_sm += __popc(balm);
+        __syncwarp();
       }
-      const uint32_t balm = __ballot_sync(kFullMask, m != 0);
-      if (m) my_stage[n_sm + __popc(balm & lt_mask)] = make_uint2(erel, m);
-      n_sm += __popc(balm);
-      __syncwarp();
     }
     if (r >= w_row1) break;
   }
+  RJ_KMER_STAMP(1);
   if (n_gl > run.stage_cap) flags |= kFinOverflow;
   s_wcnt[warp * 32 + lane] = cj;
   s_wfirst[warp * 32 + lane] = firstj;
@@ -1741,9 +1762,16 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
                      "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
       }
       __syncwarp();
-      if (lane == 0) { run.gsync[0] = 0; run.gsync[1] = 0; }
+      if (lane == 0) { run.gfinal[64] = flg; run.gsync[0] = 0; run.gsync[1] = 0; }
     }
   }
+#ifdef RJ_KMER_PROBE
+  if (run.probe && threadIdx.x == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    run.probe[(size_t)gridDim.x * 64 + blockIdx.x] = t_;
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------

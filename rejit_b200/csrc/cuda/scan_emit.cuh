@@ -3,37 +3,40 @@
 // One kernel reads the text ONCE and writes the matches ONCE, at their final
 // place, in text order — no slot ranges, no grid barrier, no second kernel:
 //
-//   tiles     the text is cut into tiles of 64 KB; a CTA (8 warps) takes tiles in
-//             order from a ticket counter; warp w owns bytes [8 KB w, 8 KB (w+1))
-//             of the tile and streams them as 16 rows of 512 bytes (a lane holds 16
-//             bytes of a row: one coalesced 16-byte load, four rows in flight).
-//   filter    literal: the first <= 4 needle bytes at the lane's 16 alignments
-//             (funnel shifts, the straddling word from the next lane);
+//   tiles     the text is cut into tiles of 32 KB; a WARP takes tiles in order from
+//             a ticket counter and works on its own: no block-wide barrier anywhere.
+//             It streams the tile as 64 rows of 512 bytes (a lane holds 16 bytes of
+//             a row: one coalesced 16-byte load, four rows in flight).
+//   filter    literal: the first <= 4 needle bytes at 16 alignments (funnel shifts;
+//             the window that begins in the three bytes before the lane's 16 comes
+//             from the left neighbour, so nothing waits for a row still in flight);
 //             generic: "can a match begin at this byte" as SWAR byte compares
 //             (<= 4 start bytes and "right after a line break") or a 256-bit map.
 //             Lanes with a survivor leave one word in shared memory (a ballot and
 //             a store; nothing else happens inside the streaming loop).
-//   evaluate  after its rows the warp turns survivors into candidates
-//             (begin, E(begin)): the rest of the needle / one NFA run per start
-//             (device_program.h NfaRun) / for "required literal + window" patterns
-//             one NFA run per start in front of every needle hit.  One lane per
-//             candidate, results compacted in order.
-//   select    candidates of one warp are sorted by construction.  When every
-//             candidate begins after its predecessor ended (the rule of ChainTake)
-//             the candidates ARE the matches; otherwise one thread walks the tile's
-//             lists with ChainTake (leftmost-longest, /root/reference/src/
-//             x64/codegen-x64.cc:401-522, src/codegen.cc:36-86).
-//   place     the CTA publishes {count, chain state} of its tile and looks back
+//   evaluate  when its list of survivors fills up, and after the last row, the warp
+//             turns survivors into candidates (begin, E(begin)): the rest of the
+//             needle / one NFA run per start (device_program.h NfaRun) / for
+//             "required literal + window" patterns one NFA run per start in front
+//             of every needle hit.  One lane per candidate, results compacted in
+//             order.  The rows in flight stay in flight meanwhile.
+//   select    candidates of a tile are sorted by construction.  When every candidate
+//             begins after its predecessor ended (the rule of ChainTake) the
+//             candidates ARE the matches; otherwise one lane walks the list with
+//             ChainTake (leftmost-longest, /root/reference/src/x64/codegen-x64.cc:
+//             401-522, src/codegen.cc:36-86).
+//   place     the warp publishes {count, chain state} of its tile and looks back
 //             over the tiles before it (decoupled look-back: records tagged with
 //             the call's sequence number, 32 predecessors per step) for the number
 //             of matches before it and the chain state arriving from the left; a
 //             state that reaches into the tile (a match straddling the tile edge)
 //             cannot be repaired locally — counts are already published — so it
 //             raises kFinOverlap and the host runs the general path instead.
-//   report    the CTA that finishes last writes the FinRecord to mapped host memory.
+//   report    the warp that finishes the last tile writes the FinRecord to mapped
+//             host memory.
 //
 // Algorithmic traffic: N bytes read + 16 bytes written per match; the look-back
-// records (32 bytes per 64 KB tile) stay in L2.
+// records (32 bytes per 32 KB tile) stay in L2.
 #ifndef REJIT_B200_CUDA_SCAN_EMIT_CUH_
 #define REJIT_B200_CUDA_SCAN_EMIT_CUH_
 
@@ -43,18 +46,23 @@ namespace rejit_b200 {
 
 constexpr uint32_t kEmWarps = 8;
 constexpr uint32_t kEmThreads = kEmWarps * 32;
-constexpr uint32_t kEmRows = 16;                              // rows of 512 bytes per warp and tile
-constexpr uint32_t kEmWarpBytes = kEmRows * 512;              // 8 KB
-constexpr uint32_t kEmTileBytes = kEmWarps * kEmWarpBytes;    // 64 KB
-constexpr uint32_t kEmEntCap = kEmWarpBytes / 16;             // every 16-byte group may hold a survivor
-constexpr uint32_t kEmCandCap = 512;                          // candidates per warp and tile
-constexpr uint32_t kEmWinCandCap = 256;                       // ... in window mode (the other half holds the needle hits)
-constexpr uint32_t kEmBias = 8192;                            // offsets in a tile are relative to tile_lo - kEmBias
-constexpr uint32_t kEmDropped = 0xFFFFFFFFu;                  // length of a candidate the chain did not take
-constexpr uint32_t kEmPending = 0xFFFFFFFEu;                  // length of a start that has not been evaluated yet
+constexpr uint32_t kEmRows = 64;                              // rows of 512 bytes per tile
+constexpr uint32_t kEmTileBytes = kEmRows * 512;              // 32 KB, one warp
+constexpr uint32_t kEmEntCap = 512;                           // survivors (16-byte groups) a warp collects before it evaluates them
+constexpr uint32_t kEmEntFlush = kEmEntCap - 128;             // ... checked every four rows (at most 128 more)
+constexpr uint32_t kEmCandCap = 1024;                         // candidates per tile
+constexpr uint32_t kEmWinCandCap = 512;                       // ... in window mode (the other half holds the needle hits)
+constexpr uint32_t kEmBias = 8192;                            // offsets in a tile are relative to tile_lo - kEmBias (16 bits)
+constexpr uint32_t kEmDropped = 0xFFFFu;                      // length field of a candidate the chain did not take
+constexpr uint32_t kEmPending = 0xFFFEu;                      // length field of a start that has not been evaluated yet
 constexpr unsigned int kFinLastEmpty = 8u;                    // FinRecord.flags: the last match is empty
 constexpr unsigned int kFinStuck = 16u;                       // a look-back gave up waiting (never expected)
-constexpr size_t kEmSmemBytes = kEmWarps * (kEmEntCap * 4 + kEmCandCap * 8);
+constexpr size_t kEmSmemBytes = kEmWarps * (kEmEntCap * 4 + kEmCandCap * 4);
+
+// a candidate in shared memory: begin - tile_base in the low half, length in the high half
+__device__ __forceinline__ uint32_t EmCand(uint32_t rel, uint32_t len) { return rel | (len << 16); }
+__device__ __forceinline__ uint32_t EmRel(uint32_t c) { return c & 0xFFFFu; }
+__device__ __forceinline__ uint32_t EmLen(uint32_t c) { return c >> 16; }
 
 enum : int { kEmLiteral = 0, kEmWindow = 1, kEmGeneric = 2 };
 
@@ -133,57 +141,42 @@ __device__ __forceinline__ uint4 EmLoadRow(const uint8_t* __restrict__ text, uin
 }
 
 // ===========================================================================
-// filters: the warp's 16 rows -> entries {group << 16 | 16 flag bits} in position order
+// filters: one row (the lane's 16 bytes) -> 16 flag bits
 // ===========================================================================
-// literal: flag bits in natural order (bit j = the first min(m, 4) needle bytes match at byte j)
+// literal: bit j = the first min(m, 4) needle bytes match at the window that BEGINS three bytes before the lane's
+// 16 plus j, i.e. at offset (lane's offset) - 3 + j.  `pw` = the four bytes before the lane's 16.
 template <bool kFull4>
-__device__ __forceinline__ uint32_t EmScanLiteral(const uint8_t* __restrict__ text, uint64_t n, uint64_t n16, uint64_t warp_lo,
-                                                   uint32_t p4, uint32_t pmask, uint32_t* my_ent) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint64_t mine = warp_lo + (uint64_t)lane * 16;
-  uint32_t n_ent = 0;
-  uint4 nxt[4];
+__device__ __forceinline__ uint32_t EmLitFlags(const uint4& v, uint32_t pw, uint32_t p4, uint32_t pmask) {
+  const uint32_t w[5] = {pw, v.x, v.y, v.z, v.w};
+  uint32_t flags = 0;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) nxt[u] = EmLoadRow(text, n16, mine + (uint64_t)u * 512);
-#pragma unroll 1
-  for (uint32_t r0 = 0; r0 < kEmRows; r0 += 4) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = nxt[u];
-    if (r0 + 4 < kEmRows) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) nxt[u] = EmLoadRow(text, n16, mine + (uint64_t)(r0 + 4 + u) * 512);
-    } else {
-      // the word that follows the warp's bytes
-      const uint64_t after = warp_lo + kEmWarpBytes;
-      nxt[0].x = (lane == 0 && after < n16) ? __ldg(reinterpret_cast<const uint32_t*>(text + after)) : 0u;
-    }
-    if (warp_lo + (uint64_t)r0 * 512 >= n) continue;          // rows beyond the text (uniform)
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t up = __shfl_down_sync(kFullMask, v[u].x, 1);
-      const uint32_t wrap = __shfl_sync(kFullMask, (u < 3) ? v[u + 1].x : nxt[0].x, 0);
-      const uint32_t nx = (lane == 31) ? wrap : up;
-      const bool any = LitAny<kFull4>(v[u], nx, p4, pmask);
-      const uint32_t bal = __ballot_sync(kFullMask, any);
-      if (bal) {
-        if (any) my_ent[n_ent + __popc(bal & lt_mask)] = (((r0 + u) * 32u + lane) << 16) | LitMask(v[u], nx, p4, pmask);
-        n_ent += __popc(bal);
-      }
-    }
+  for (int j = 0; j < 16; ++j) {
+    const int o = j + 1;                                      // byte offset in the 20-byte buffer
+    const uint32_t x = (o & 3) ? __funnelshift_r(w[o >> 2], w[(o >> 2) + 1], 8 * (o & 3)) : w[o >> 2];
+    if (kFull4 ? (x == p4) : (((x ^ p4) & pmask) == 0)) flags |= 1u << j;
   }
-  return n_ent;
+  return flags;
+}
+template <bool kFull4>
+__device__ __forceinline__ bool EmLitAny(const uint4& v, uint32_t pw, uint32_t p4, uint32_t pmask) {
+  const uint32_t w[5] = {pw, v.x, v.y, v.z, v.w};
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int o = j + 1;
+    const uint32_t x = (o & 3) ? __funnelshift_r(w[o >> 2], w[(o >> 2) + 1], 8 * (o & 3)) : w[o >> 2];
+    any |= kFull4 ? (x == p4) : (((x ^ p4) & pmask) == 0);
+  }
+  return any;
 }
 
-// generic: flag bits transposed (EmEqT)
-__device__ __forceinline__ uint32_t EmFilterGroup(const uint4& v, uint32_t prev_is_break, const EmFilter& f, uint32_t* brk_out) {
+// generic: flag bits transposed (EmEqT), 28 bits
+__device__ __forceinline__ uint32_t EmFilterGroup(const uint4& v, uint32_t prev_is_break, const EmFilter& f) {
   if (f.swar) {
     uint32_t m0 = 0;
     for (uint32_t i = 0; i < f.n0; ++i) m0 |= EmEqT(v, (f.b0 >> (8 * i)) & 0xFFu);
-    if (!f.use_sol) { *brk_out = 0; return m0; }
+    if (!f.use_sol) return m0;
     const uint32_t brk = EmEqT(v, 0x0Au) | EmEqT(v, 0x0Du);
-    *brk_out = brk;
     uint32_t m1 = 0x0F0F0F0Fu;
     if (!f.all1) {
       m1 = 0;
@@ -192,7 +185,7 @@ __device__ __forceinline__ uint32_t EmFilterGroup(const uint4& v, uint32_t prev_
     return m0 | (EmShiftT(brk, prev_is_break) & m1);
   }
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t cand = 0, brk = 0;
+  uint32_t cand = 0;
   uint32_t sol = prev_is_break;
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
@@ -200,83 +193,30 @@ __device__ __forceinline__ uint32_t EmFilterGroup(const uint4& v, uint32_t prev_
     const uint32_t bit = (f.t[sol][c >> 5] >> (c & 31)) & 1u;
     cand |= bit << (((p & 3) << 3) | (p >> 2));
     sol = (c == 0x0Au || c == 0x0Du) ? 1u : 0u;
-    brk |= sol << (((p & 3) << 3) | (p >> 2));
   }
-  *brk_out = brk;
   return cand;
 }
 
-__device__ __forceinline__ uint32_t EmScanGeneric(const uint8_t* __restrict__ text, uint64_t n, uint64_t n16, uint64_t warp_lo,
-                                                   const EmFilter& f, uint32_t* my_ent) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint64_t mine = warp_lo + (uint64_t)lane * 16;
-  uint32_t n_ent = 0;
-  // is the byte before the warp's first byte a line break (offset 0: the text start counts as one)
-  uint32_t carry = 1u;
-  if (warp_lo > 0) { const uint8_t pb = (warp_lo - 1 < n) ? __ldg(text + warp_lo - 1) : 0; carry = (pb == 0x0Au || pb == 0x0Du) ? 1u : 0u; }
-  uint4 nxt[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) nxt[u] = EmLoadRow(text, n16, mine + (uint64_t)u * 512);
-#pragma unroll 1
-  for (uint32_t r0 = 0; r0 < kEmRows; r0 += 4) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = nxt[u];
-    if (r0 + 4 < kEmRows) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) nxt[u] = EmLoadRow(text, n16, mine + (uint64_t)(r0 + 4 + u) * 512);
-    }
-    if (warp_lo + (uint64_t)r0 * 512 >= n) continue;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint64_t at = mine + (uint64_t)(r0 + u) * 512;
-      // the line-break flag of the byte before my 16: my left neighbour's last byte (lane 0: the row before)
-      uint32_t brk = 0, cand;
-      if (f.use_sol || !f.swar) {
-        const uint32_t w3 = v[u].w >> 24;
-        const uint32_t my_last = (w3 == 0x0Au || w3 == 0x0Du) ? 1u : 0u;
-        uint32_t prev = __shfl_up_sync(kFullMask, my_last, 1);
-        if (lane == 0) prev = carry;
-        carry = __shfl_sync(kFullMask, my_last, 31);
-        cand = EmFilterGroup(v[u], prev, f, &brk);
-      } else {
-        cand = EmFilterGroup(v[u], 0u, f, &brk);
-      }
-      if (at + 16 > n) cand = at < n ? EmKeepBelowT(cand, (uint32_t)(n - at)) : 0u;      // bytes beyond the text
-      const uint32_t bal = __ballot_sync(kFullMask, cand != 0);
-      if (bal) {
-        // 28-bit transposed flags (bit 8 k + j) -> 16 bits (bit 4 k + j)
-        if (cand) my_ent[n_ent + __popc(bal & lt_mask)] = (((r0 + u) * 32u + lane) << 16) | __byte_perm(cand | (cand >> 4), 0u, 0x4420);
-        n_ent += __popc(bal);
-      }
-    }
-  }
-  return n_ent;
-}
-
-
 // ===========================================================================
-// evaluation: entries -> candidates {begin - tile_base, length}, in position order.
-// Every function is called by the whole warp and returns the number of candidates
-// (a value above `cap` means the list overflowed: the tile is too dense).
+// evaluation: survivors -> candidates (begin - tile_base | length << 16), appended to the tile's list in position
+// order.  Called by the whole warp; return the new number of candidates (above `cap`: the list overflowed).
 // ===========================================================================
-// literal occurrences (natural flag order): bounds, ownership, the rest of the needle.  kHits: the results are
-// needle hits (u32 offsets) for the window stage instead of candidates.
+// literal occurrences (flag j of a group = the window that begins at group offset - 3 + j): bounds, ownership, the
+// rest of the needle.  kHits: the results are needle hits (u32 offsets) for the window stage instead of candidates.
 template <bool kHits>
 __device__ __forceinline__ uint32_t EmEvalLiteral(const uint8_t* __restrict__ text, uint64_t n, const EmLit& lit,
-                                                   uint64_t own_lo, uint64_t own_hi, uint64_t tile_base, uint64_t warp_lo,
-                                                   const uint32_t* my_ent, uint32_t n_ent, void* out, uint32_t cap) {
+                                                   uint64_t own_lo, uint64_t own_hi, uint64_t tile_base, uint64_t tile_lo,
+                                                   const uint32_t* my_ent, uint32_t n_ent, uint32_t* out, uint32_t k,
+                                                   uint32_t cap) {
   const int lane = threadIdx.x & 31;
-  uint32_t k = 0;
   for (uint32_t base = 0; base < n_ent; base += 32) {
     const uint32_t ent = base + lane < n_ent ? my_ent[base + lane] : 0u;
     uint32_t valid = ent & 0xFFFFu;
-    const uint64_t my = warp_lo + (uint64_t)(ent >> 16) * 16;
+    const uint64_t my = tile_lo + (uint64_t)(ent >> 16) * 16;          // the group's offset; flag j: my - 3 + j
     for (uint32_t hh = valid; hh; hh &= hh - 1) {
       const int j = __ffs(hh) - 1;
-      const uint64_t pos = my + j;
-      bool ok = pos >= own_lo && pos < own_hi && pos + lit.m <= n;
+      const uint64_t pos = my + j - 3;                                 // (wraps below zero for the text's first bytes)
+      bool ok = my + j >= 3 && pos >= own_lo && pos < own_hi && pos + lit.m <= n;
       for (uint32_t i = 4; i < lit.m && ok; ++i) ok = (__ldg(text + pos + i) == __ldg(lit.needle + i));
       if (!ok) valid &= ~(1u << j);
     }
@@ -284,11 +224,8 @@ __device__ __forceinline__ uint32_t EmEvalLiteral(const uint8_t* __restrict__ te
     const uint32_t incl = WarpInclusiveScan(c);
     uint32_t idx = k + incl - c;
     for (; valid; valid &= valid - 1) {
-      const uint32_t rel = (uint32_t)(my + (__ffs(valid) - 1) - tile_base);
-      if (idx < cap) {
-        if (kHits) static_cast<uint32_t*>(out)[idx] = rel;
-        else static_cast<uint2*>(out)[idx] = make_uint2(rel, lit.m);
-      }
+      const uint32_t rel = (uint32_t)(my + (__ffs(valid) - 1) - 3 - tile_base);
+      if (idx < cap) out[idx] = kHits ? rel : EmCand(rel, lit.m);
       ++idx;
     }
     k += __shfl_sync(kFullMask, incl, 31);
@@ -297,23 +234,21 @@ __device__ __forceinline__ uint32_t EmEvalLiteral(const uint8_t* __restrict__ te
   return k;
 }
 
-// one NFA run per start in front of every needle hit (the windows of neighbouring hits of this warp are clipped
+// one NFA run per start in front of every needle hit (the windows of neighbouring hits of this tile are clipped
 // against each other so that every start is tried once, in order)
 __device__ __forceinline__ uint32_t EmEvalWindow(const uint8_t* __restrict__ text, uint64_t n, const NfaTables& nfa,
                                                   const EmLit& lit, const ScanRange& range, uint64_t tile_base,
-                                                  const uint32_t* my_hits, uint32_t n_hits, uint2* my_cand, uint32_t cap,
-                                                  unsigned int* flags) {
+                                                  const uint32_t* my_hits, uint32_t n_hits, uint64_t* prev_hit,
+                                                  uint32_t* my_cand, uint32_t k, uint32_t cap, unsigned int* flags) {
   const int lane = threadIdx.x & 31;
-  uint32_t k = 0;
   for (uint32_t q = 0; q < n_hits; ++q) {
     const uint64_t h = tile_base + my_hits[q];
+    const uint64_t prev = *prev_hit;                           // the hit before it in this tile (kNoMatch: none)
+    *prev_hit = h;
     if (h < lit.win_lo) continue;
     const uint64_t s_max = h - lit.win_lo;                     // inclusive
     uint64_t s_min = h >= lit.win_hi ? h - lit.win_hi : 0;
-    if (q > 0) {
-      const uint64_t prev = tile_base + my_hits[q - 1];
-      if (prev >= lit.win_lo && prev - lit.win_lo + 1 > s_min) s_min = prev - lit.win_lo + 1;
-    }
+    if (prev != kNoMatch && prev >= lit.win_lo && prev - lit.win_lo + 1 > s_min) s_min = prev - lit.win_lo + 1;
     for (uint64_t base = s_min; base <= s_max; base += 32) {
       const uint64_t s = base + lane;
       uint64_t e = kNoMatch;
@@ -327,7 +262,7 @@ __device__ __forceinline__ uint32_t EmEvalWindow(const uint8_t* __restrict__ tex
       const uint32_t bal = __ballot_sync(kFullMask, has);
       if (bal) {
         const uint32_t idx = k + __popc(bal & ((1u << lane) - 1u));
-        if (has && idx < cap) my_cand[idx] = make_uint2((uint32_t)(s - tile_base), (uint32_t)(e - s));
+        if (has && idx < cap) my_cand[idx] = EmCand((uint32_t)(s - tile_base), (uint32_t)(e - s));
         k += __popc(bal);
       }
     }
@@ -336,44 +271,44 @@ __device__ __forceinline__ uint32_t EmEvalWindow(const uint8_t* __restrict__ tex
   return k;
 }
 
-// generic: entries (transposed flags) -> starts, in place in the candidate list, then one NFA run per start
+// generic: survivors (transposed flags, flag of position p of a group = a start at group offset + p) -> starts,
+// appended to the candidate list as pending entries, then one NFA run per start, compacted in place
 __device__ __forceinline__ uint32_t EmEvalGeneric(const uint8_t* __restrict__ text, uint64_t n, const NfaTables& nfa,
-                                                   const ScanRange& range, uint64_t tile_base, uint64_t warp_lo,
-                                                   const uint32_t* my_ent, uint32_t n_ent, uint2* my_cand, uint32_t cap,
-                                                   unsigned int* flags) {
+                                                   const ScanRange& range, uint64_t tile_base, uint64_t tile_lo,
+                                                   const uint32_t* my_ent, uint32_t n_ent, bool add_end, uint32_t* my_cand,
+                                                   uint32_t k, uint32_t cap, unsigned int* flags) {
   const int lane = threadIdx.x & 31;
-  uint32_t n_start = 0;
+  uint32_t n_start = k;
   for (uint32_t base = 0; base < n_ent; base += 32) {
     const uint32_t ent = base + lane < n_ent ? my_ent[base + lane] : 0u;
     const uint32_t f16 = ent & 0xFFFFu;
-    const uint64_t my = warp_lo + (uint64_t)(ent >> 16) * 16;
+    const uint64_t my = tile_lo + (uint64_t)(ent >> 16) * 16;
     const uint32_t c = __popc(f16);
     const uint32_t incl = WarpInclusiveScan(c);
     uint32_t idx = n_start + incl - c;
     if (f16) {
 #pragma unroll 1
       for (uint32_t p = 0; p < 16; ++p) {
-        if (!((f16 >> (((p & 3u) << 2) | (p >> 2))) & 1u)) continue;
-        if (idx < cap) my_cand[idx] = make_uint2((uint32_t)(my + p - tile_base), kEmPending);
+        if (!((f16 >> EmPosOfT16((int)p)) & 1u)) continue;          // (the 4 x 4 transpose is its own inverse)
+        if (idx < cap) my_cand[idx] = EmCand((uint32_t)(my + p - tile_base), kEmPending);
         ++idx;
       }
     }
     n_start += __shfl_sync(kFullMask, incl, 31);
   }
   // the offset n itself: only the empty match can begin there (the run decides)
-  if (n >= warp_lo && n < warp_lo + kEmWarpBytes) {
-    if (lane == 0 && n_start < cap) my_cand[n_start] = make_uint2((uint32_t)(n - tile_base), kEmPending);
+  if (add_end) {
+    if (lane == 0 && n_start < cap) my_cand[n_start] = EmCand((uint32_t)(n - tile_base), kEmPending);
     ++n_start;
   }
   __syncwarp();
   if (n_start > cap) return n_start;
-  uint32_t k = 0;
-  for (uint32_t base = 0; base < n_start; base += 32) {
+  for (uint32_t base = k; base < n_start; base += 32) {
     const uint32_t i = base + lane;
     uint32_t rel = 0;
     uint64_t s = 0, e = kNoMatch;
     if (i < n_start) {
-      rel = my_cand[i].x;
+      rel = EmRel(my_cand[i]);
       s = tile_base + rel;
       if (s >= range.own_begin && s < range.own_end && s <= n) e = NfaRunAny(nfa, text, n, s);
     }
@@ -381,7 +316,7 @@ __device__ __forceinline__ uint32_t EmEvalGeneric(const uint8_t* __restrict__ te
     const bool has = e != kNoMatch;
     if (has && e - s >= kEmPending) { *flags |= kFinDense; e = s; }
     const uint32_t bal = __ballot_sync(kFullMask, has);
-    if (has) my_cand[k + __popc(bal & ((1u << lane) - 1u))] = make_uint2(rel, (uint32_t)(e - s));
+    if (has) my_cand[k + __popc(bal & ((1u << lane) - 1u))] = EmCand(rel, (uint32_t)(e - s));
     k += __popc(bal);
     __syncwarp();
   }
@@ -406,8 +341,8 @@ __device__ __forceinline__ void EmPublish(uint4* rec, uint32_t tag, uint64_t cou
   EmStore16(rec + 1, (uint32_t)st.cur, (uint32_t)(st.cur >> 32) | (st.ne << 31) | (has ? 1u << 30 : 0u), tag, 0u);
 }
 
-// Called by warp 0.  Returns (in every lane) the number of matches in the tiles before `t` and the chain state
-// that arrives at the tile (the state after the last match before it, or the call's carry).
+// Called by a whole warp.  Returns (in every lane) the number of matches in the tiles before `t` and the chain
+// state that arrives at the tile (the state after the last match before it, or the call's carry).
 __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint64_t* before, EmState* arriving) {
   const int lane = threadIdx.x & 31;
   uint64_t excl = 0;
@@ -467,182 +402,185 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint6
 }
 
 // ===========================================================================
-// the kernel
+// the kernel: every warp is on its own
 // ===========================================================================
-constexpr uint32_t kEmSeqMax = 4096;        // candidates of a tile up to which one thread resolves an overlap
-
 template <int kMode, bool kFull4>
 __global__ void __launch_bounds__(kEmThreads, 4)
 k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables nfa, EmFilter flt, ScanRange range,
             EmitArgs em) {
   extern __shared__ __align__(16) uint8_t em_smem[];
-  __shared__ unsigned long long s_ticket, s_before;
-  __shared__ uint32_t s_cnt[kEmWarps], s_off[kEmWarps], s_ok[kEmWarps];
-  __shared__ uint2 s_first[kEmWarps], s_last[kEmWarps];
-  __shared__ unsigned int s_flags, s_mode;         // s_mode: 0 write, 1 resolve + compact first, 2 nothing to write
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   uint32_t* my_ent = reinterpret_cast<uint32_t*>(em_smem) + warp * kEmEntCap;
-  uint2* cand_all = reinterpret_cast<uint2*>(em_smem + kEmWarps * kEmEntCap * 4);
-  uint2* my_cand = cand_all + warp * kEmCandCap;
+  uint32_t* my_cand = reinterpret_cast<uint32_t*>(em_smem + kEmWarps * kEmEntCap * 4) + warp * kEmCandCap;
+  uint32_t* my_hits = my_cand + kEmWinCandCap;                                          // window mode: the upper half
   const uint64_t n16 = (n + 15) & ~15ull;
   const uint32_t cap = kMode == kEmWindow ? kEmWinCandCap : kEmCandCap;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   // needle hits may sit up to win_hi bytes after an owned start
   const uint64_t hit_hi = kMode == kEmWindow ? range.own_end + lit.win_hi + 1 : range.own_end;
+  // a literal window begins up to three bytes before a lane's 16: rows are scanned up to the one that holds n + 2
+  const uint64_t scan_end = kMode == kEmGeneric ? n : n + 3;
 
+  unsigned long long next_ticket = 0;
+  if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
   for (;;) {
-    if (threadIdx.x == 0) { s_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull); s_flags = 0; }
-    __syncthreads();
-    const uint64_t t = s_ticket;
+    const uint64_t t = __shfl_sync(kFullMask, next_ticket, 0);
     if (t >= em.ntiles) break;
     const uint64_t tile_lo = (em.tile0 + t) * kEmTileBytes;
     const uint64_t tile_base = tile_lo >= kEmBias ? tile_lo - kEmBias : 0;
-    const uint64_t warp_lo = tile_lo + (uint64_t)warp * kEmWarpBytes;
+    const uint64_t mine = tile_lo + (uint64_t)lane * 16;
     unsigned int flags = 0;
-    uint32_t cnt = 0;
-    // ---- filter + evaluate: my 8 KB -----------------------------------------------------------
-    if (warp_lo <= n && warp_lo < hit_hi + 16 && warp_lo + kEmWarpBytes + 16 > range.own_begin) {
-      uint32_t n_ent;
-      if (kMode == kEmGeneric) n_ent = EmScanGeneric(text, n, n16, warp_lo, flt, my_ent);
-      else n_ent = EmScanLiteral<kFull4>(text, n, n16, warp_lo, lit.p4, lit.pmask, my_ent);
-      __syncwarp();
-      if (kMode == kEmLiteral) {
-        cnt = n_ent ? EmEvalLiteral<false>(text, n, lit, range.own_begin, range.own_end, tile_base, warp_lo, my_ent, n_ent, my_cand, cap) : 0u;
-      } else if (kMode == kEmWindow) {
-        uint32_t* my_hits = reinterpret_cast<uint32_t*>(my_cand + kEmWinCandCap);       // the upper half of my list
-        const uint32_t n_hits = n_ent ? EmEvalLiteral<true>(text, n, lit, range.own_begin, hit_hi, tile_base, warp_lo, my_ent, n_ent, my_hits, 2 * kEmWinCandCap) : 0u;
-        if (n_hits > 2 * kEmWinCandCap) { flags |= kFinDense; }
-        else if (n_hits) cnt = EmEvalWindow(text, n, nfa, lit, range, tile_base, my_hits, n_hits, my_cand, cap, &flags);
-      } else {
-        cnt = EmEvalGeneric(text, n, nfa, range, tile_base, warp_lo, my_ent, n_ent, my_cand, cap, &flags);
+    uint32_t cnt = 0;                                       // candidates of the tile so far
+    uint64_t prev_hit = kNoMatch;
+    const bool live = tile_lo <= n && tile_lo < hit_hi + 16 && tile_lo + kEmTileBytes + 16 > range.own_begin;
+    if (live) {
+      // ---- stream the rows; evaluate the survivors whenever their list fills up, and at the end --------------
+      uint32_t n_ent = 0;
+      uint4 v0 = EmLoadRow(text, n16, mine), v1 = EmLoadRow(text, n16, mine + 512), v2 = EmLoadRow(text, n16, mine + 1024),
+            v3 = EmLoadRow(text, n16, mine + 1536);
+      // what precedes the tile: its last word (literal windows) / whether its last byte is a line break
+      uint32_t tail = 0;
+      if (kMode == kEmGeneric) {
+        tail = 1u;                                          // the text start counts as "after a line break"
+        if (tile_lo > 0) { const uint8_t pb = __ldg(text + tile_lo - 1); tail = (pb == 0x0Au || pb == 0x0Du) ? 1u : 0u; }
+      } else if (tile_lo >= 4) {
+        tail = __ldg(reinterpret_cast<const uint32_t*>(text + tile_lo - 4));
       }
-      if (cnt > cap) { flags |= kFinDense; cnt = 0; }
+      // rows that hold text (or, for literals, the three bytes after it)
+      uint32_t rows = kEmRows;
+      if (tile_lo + kEmTileBytes > scan_end) rows = scan_end > tile_lo ? (uint32_t)((scan_end - tile_lo + 511) >> 9) : 0u;
+      auto row = [&](uint4& v, uint32_t r) {
+        const uint4 cur = v;
+        v = r + 4 < rows ? EmLoadRow(text, n16, mine + (uint64_t)(r + 4) * 512) : make_uint4(0, 0, 0, 0);
+        uint32_t f16 = 0;
+        if (kMode == kEmGeneric) {
+          uint32_t prev = 0;
+          if (flt.use_sol || !flt.swar) {
+            const uint32_t w3 = cur.w >> 24;
+            const uint32_t my_last = (w3 == 0x0Au || w3 == 0x0Du) ? 1u : 0u;
+            prev = __shfl_up_sync(kFullMask, my_last, 1);
+            if (lane == 0) prev = tail;
+            tail = __shfl_sync(kFullMask, my_last, 31);
+          }
+          uint32_t cand = EmFilterGroup(cur, prev, flt);
+          const uint64_t at = mine + (uint64_t)r * 512;
+          if (at + 16 > n) cand = at < n ? EmKeepBelowT(cand, (uint32_t)(n - at)) : 0u;      // bytes beyond the text
+          f16 = __byte_perm(cand | (cand >> 4), 0u, 0x4420);                               // bit 8 k + j -> bit 4 k + j
+        } else {
+          uint32_t pw = __shfl_up_sync(kFullMask, cur.w, 1);
+          if (lane == 0) pw = tail;
+          tail = __shfl_sync(kFullMask, cur.w, 31);
+          if (EmLitAny<kFull4>(cur, pw, lit.p4, lit.pmask)) f16 = EmLitFlags<kFull4>(cur, pw, lit.p4, lit.pmask);
+        }
+        const uint32_t bal = __ballot_sync(kFullMask, f16 != 0);
+        if (bal) {
+          if (f16) my_ent[n_ent + __popc(bal & lt_mask)] = ((r * 32u + lane) << 16) | f16;
+          n_ent += __popc(bal);
+        }
+      };
+      uint32_t r = 0;
+#pragma unroll 1
+      for (;;) {
+#pragma unroll 1
+        for (; r + 4 <= rows && n_ent <= kEmEntFlush; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
+        if (r + 4 > rows) {
+          if (r < rows) row(v0, r);
+          if (r + 1 < rows) row(v1, r + 1);
+          if (r + 2 < rows) row(v2, r + 2);
+          r = rows;
+        }
+        __syncwarp();
+        if (kMode == kEmLiteral) {
+          if (n_ent) cnt = EmEvalLiteral<false>(text, n, lit, range.own_begin, range.own_end, tile_base, tile_lo, my_ent, n_ent, my_cand, cnt, cap);
+        } else if (kMode == kEmWindow) {
+          const uint32_t n_hits = n_ent ? EmEvalLiteral<true>(text, n, lit, range.own_begin, hit_hi, tile_base, tile_lo, my_ent, n_ent, my_hits, 0u, kEmWinCandCap) : 0u;
+          if (n_hits > kEmWinCandCap) flags |= kFinDense;
+          else if (n_hits) cnt = EmEvalWindow(text, n, nfa, lit, range, tile_base, my_hits, n_hits, &prev_hit, my_cand, cnt, cap, &flags);
+        } else {
+          const bool add_end = r >= rows && n >= tile_lo && n < tile_lo + kEmTileBytes;
+          cnt = EmEvalGeneric(text, n, nfa, range, tile_base, tile_lo, my_ent, n_ent, add_end, my_cand, cnt, cap, &flags);
+        }
+        n_ent = 0;
+        if (cnt > cap) { flags |= kFinDense; cnt = 0; }
+        if (r >= rows) break;
+      }
     }
-    // ---- does every candidate of my list begin after its predecessor ended? ----------------------
+    // The next tile is taken now, not earlier: a tile that has an owner but has not been started holds up the
+    // look-back of every tile after it, so a ticket is held only while this tile is being finished.
+    if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
+    flags = __reduce_or_sync(kFullMask, flags);
+    if (flags) cnt = 0;
+    // ---- does every candidate begin after its predecessor ended?  Else one lane walks the chain ----------------
     bool ok = true;
     for (uint32_t base = 0; base < cnt; base += 32) {
       const uint32_t i = base + lane;
       if (i > 0 && i < cnt) {
-        const uint2 p = my_cand[i - 1], c = my_cand[i];
-        ok &= EmTakes(EmAfter(p.x, p.y), c.x, c.y);
+        const uint32_t p = my_cand[i - 1], c = my_cand[i];
+        ok &= EmTakes(EmAfter(EmRel(p), EmLen(p)), EmRel(c), EmLen(c));
+        if (EmRel(c) <= EmRel(p)) flags |= kFinOverlap;        // not even sorted (windows of two tiles interleave)
       }
     }
     ok = __all_sync(kFullMask, ok);
     flags = __reduce_or_sync(kFullMask, flags);
-    if (lane == 0) {
-      s_cnt[warp] = cnt;
-      s_ok[warp] = ok ? 1u : 0u;
-      if (cnt) { s_first[warp] = my_cand[0]; s_last[warp] = my_cand[cnt - 1]; }
-      if (flags) atomicOr(&s_flags, flags);
-    }
-    __syncthreads();
-    // ---- the tile: list boundaries, one-thread resolve when candidates overlap -----------------------
-    if (threadIdx.x == 0) {
-      bool all_ok = true, ordered = true;
-      uint32_t total = 0;
-      bool seen = false;
-      uint2 last = make_uint2(0, 0);
-      for (uint32_t w = 0; w < kEmWarps; ++w) {
-        if (!s_cnt[w]) continue;
-        all_ok &= s_ok[w] != 0;
-        if (seen) {
-          all_ok &= EmTakes(EmAfter(last.x, last.y), s_first[w].x, s_first[w].y);
-          ordered &= s_first[w].x > last.x;
-        }
-        seen = true;
-        last = s_last[w];
-        total += s_cnt[w];
-      }
-      unsigned int mode = 0;
-      if (s_flags) mode = 2;
-      else if (!all_ok) {
-        if (!ordered || total > kEmSeqMax) { s_flags = kFinOverlap; mode = 2; }
-        else {
-          // leftmost-longest over the tile's candidates, as if nothing reached in from the left
-          ChainState cs;
-          cs.cur = 0; cs.tail = kNoMatch;
-          for (uint32_t w = 0; w < kEmWarps; ++w) {
-            uint2* list = cand_all + w * kEmCandCap;
-            for (uint32_t i = 0; i < s_cnt[w]; ++i)
-              if (!ChainTake(&cs, list[i].x, (uint64_t)list[i].x + list[i].y)) list[i].y = kEmDropped;
-          }
-          mode = 1;
+    if (flags) cnt = 0;
+    if (!ok && cnt) {
+      // leftmost-longest over the tile's candidates, as if nothing reached in from the left
+      __syncwarp();
+      if (lane == 0) {
+        ChainState cs;
+        cs.cur = 0; cs.tail = kNoMatch;
+        for (uint32_t i = 0; i < cnt; ++i) {
+          const uint32_t c = my_cand[i];
+          if (!ChainTake(&cs, EmRel(c), (uint64_t)EmRel(c) + EmLen(c))) my_cand[i] = EmCand(EmRel(c), kEmDropped);
         }
       }
-      s_mode = mode;
-    }
-    __syncthreads();
-    if (s_mode == 1) {
-      // my list without the candidates the chain dropped
+      __syncwarp();
       uint32_t k = 0;
       for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t i = base + lane;
-        const uint2 c = i < cnt ? my_cand[i] : make_uint2(0, kEmDropped);
+        const uint32_t c = i < cnt ? my_cand[i] : EmCand(0, kEmDropped);
         __syncwarp();
-        const bool keep = c.y != kEmDropped;
+        const bool keep = EmLen(c) != kEmDropped;
         const uint32_t bal = __ballot_sync(kFullMask, keep);
-        if (keep) my_cand[k + __popc(bal & ((1u << lane) - 1u))] = c;
+        if (keep) my_cand[k + __popc(bal & lt_mask)] = c;
         k += __popc(bal);
         __syncwarp();
       }
       cnt = k;
-      if (lane == 0) {
-        s_cnt[warp] = cnt;
-        if (cnt) { s_first[warp] = my_cand[0]; s_last[warp] = my_cand[cnt - 1]; }
-      }
-      __syncthreads();
-    } else if (s_mode == 2) {
-      cnt = 0;
     }
-    // ---- publish, look back, check the seam (warp 0) ---------------------------------------------------
-    if (warp == 0) {
-      uint32_t total = 0;
-      bool seen = false;
-      uint2 first = make_uint2(0, 0), last = make_uint2(0, 0);
-      if (s_mode != 2)
-        for (uint32_t w = 0; w < kEmWarps; ++w) {
-          if (!s_cnt[w]) continue;
-          if (!seen) first = s_first[w];
-          seen = true;
-          last = s_last[w];
-          if (lane == 0) s_off[w] = total;
-          total += s_cnt[w];
-        }
-      EmState mine = EmAfter(tile_base + last.x, last.y);
-      uint4* rec = em.records + 2 * t;
-      const uint32_t tag = (em.seq & 0x3FFFFFFFu) << 2;
-      if (lane == 0) EmPublish(rec, tag | 1u, total, seen, mine);
-      uint64_t before;
-      EmState arriving;
-      EmLookBack(em, t, &before, &arriving);
-      if (lane == 0) {
-        unsigned int fl = s_flags;
-        if (seen && !EmTakes(arriving, tile_base + first.x, first.y)) fl |= kFinOverlap;   // the chain from the left reaches in
-        EmPublish(rec, tag | 2u, before + total, true, seen ? mine : arriving);
-        if (fl) atomicOr(&em.sync[2], fl);
-        s_before = before;
-        if (t + 1 == em.ntiles) {
-          const EmState fin = seen ? mine : arriving;
-          em.final_state[0] = before + total;
-          em.final_state[1] = fin.cur;
-          em.final_state[2] = fin.ne;
-        }
+    // ---- publish, look back, check the seam ---------------------------------------------------------------------
+    const uint32_t first = cnt ? my_cand[0] : 0u, last = cnt ? my_cand[cnt - 1] : 0u;
+    const EmState mine_out = EmAfter(tile_base + EmRel(last), EmLen(last));
+    uint4* rec = em.records + 2 * t;
+    const uint32_t tag = (em.seq & 0x3FFFFFFFu) << 2;
+    if (lane == 0) EmPublish(rec, tag | 1u, cnt, cnt != 0, mine_out);
+    uint64_t before;
+    EmState arriving;
+    EmLookBack(em, t, &before, &arriving);
+    if (cnt && !EmTakes(arriving, tile_base + EmRel(first), EmLen(first))) flags |= kFinOverlap;   // the chain from the left reaches in
+    if (lane == 0) {
+      EmPublish(rec, tag | 2u, before + cnt, true, cnt ? mine_out : arriving);
+      if (flags) atomicOr(&em.sync[2], flags);
+      if (t + 1 == em.ntiles) {
+        const EmState fin = cnt ? mine_out : arriving;
+        em.final_state[0] = before + cnt;
+        em.final_state[1] = fin.cur;
+        em.final_state[2] = fin.ne;
       }
     }
-    __syncthreads();
-    // ---- my matches, at their final place --------------------------------------------------------------
-    if (cnt) {
-      const uint64_t at0 = s_before + s_off[warp];
+    // ---- my matches, at their final place ------------------------------------------------------------------------
+    {
       ulonglong2* outp = reinterpret_cast<ulonglong2*>(em.out_pairs);
       for (uint32_t i = lane; i < cnt; i += 32) {
-        const uint2 c = my_cand[i];
-        const uint64_t b = tile_base + c.x + em.base_offset;
-        if (at0 + i < em.out_cap) outp[at0 + i] = make_ulonglong2(b, b + c.y);
+        const uint32_t c = my_cand[i];
+        const uint64_t b = tile_base + EmRel(c) + em.base_offset;
+        if (before + i < em.out_cap) outp[before + i] = make_ulonglong2(b, b + EmLen(c));
       }
     }
-    __syncthreads();
-    // ---- the CTA that finishes the last tile reports ------------------------------------------------------
-    if (threadIdx.x == 0) {
+    __syncwarp();
+    // ---- the warp that finishes the last tile reports --------------------------------------------------------------
+    if (lane == 0) {
       __threadfence();
       const unsigned int done = atomicAdd(&em.sync[3], 1u);
       if ((uint64_t)done + 1 == em.ntiles) {
@@ -662,6 +600,91 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
                      "r"((unsigned int)(last_ne >> 32)), "r"(0u), "r"(em.seq) : "memory");
       }
     }
+  }
+}
+
+// ===========================================================================
+// Device-side stitch of slab-sharded texts (one process per GPU): every rank sends the chain state
+// that leaves its slab — per pattern: where the next match may begin — straight into the right neighbour's device
+// memory (a peer store over NVLink; the inbox is mapped through CUDA IPC) and checks the state that arrives from
+// the left: only when that chain reaches into the slab does the host repeat the slab call with the real carry.
+// One warp on the engine's stream; no host-to-host hop, no collective.
+//   inbox slot (step & 63): [32] uint4 {cur lo, cur hi | ne << 31 | has << 30, step, 0}
+//   flow control: a rank is at most 32 steps ahead of its right neighbour (ack word written back by the receiver)
+// ===========================================================================
+constexpr uint32_t kStitchSlots = 64;
+constexpr uint32_t kStitchAckWord = kStitchSlots * 32 * 4;               // index (in words) of the ack word
+constexpr uint32_t kStitchInboxBytes = kStitchSlots * 32 * 16 + 64;
+
+struct StitchReport {                   // mapped host memory, one per device context
+  unsigned long long arrived_cur[32];   // global offset where the chain arriving from the left lets a match begin (0: none)
+  unsigned int arrived_ne;              // bit j: that chain's last match was non-empty
+  unsigned int redo;                    // bit j: the arriving chain of pattern j reaches into the slab
+  unsigned int status;                  // 2: a neighbour did not answer
+  unsigned int step;                    // written last
+};
+
+struct StitchArgs {
+  int K, rank;
+  unsigned long long sent_cur[32];      // what leaves my slab, global offsets
+  unsigned int sent_ne, sent_has;
+  uint64_t slab_begin;                  // first owned start, global
+  uint4* inbox;                         // mine
+  uint4* right_inbox;                   // the right neighbour's (NULL on the last rank)
+  unsigned int* left_ack;               // the ack word in the left neighbour's inbox (NULL on rank 0)
+  unsigned int step;
+  StitchReport* report;
+};
+
+__global__ void __launch_bounds__(32, 1) k_stitch(StitchArgs a) {
+  const int lane = threadIdx.x;
+  uint32_t status = 0;
+  const uint32_t slot = (a.step & (kStitchSlots - 1)) * 32;
+  // ---- send to the right (not more than 32 steps ahead of what the neighbour has consumed) ------------
+  if (a.right_inbox) {
+    const volatile unsigned int* ack = reinterpret_cast<const volatile unsigned int*>(a.inbox) + kStitchAckWord;
+    for (uint32_t polls = 0; (int)(a.step - *ack) > 32; ++polls)
+      if (polls > (1u << 22)) { status |= 2u; break; }
+    if (lane < a.K) {
+      const unsigned long long cur = a.sent_cur[lane];
+      EmStore16(a.right_inbox + slot + lane, (uint32_t)cur,
+                (uint32_t)(cur >> 32) | (((a.sent_ne >> lane) & 1u) << 31) | (((a.sent_has >> lane) & 1u) << 30), a.step, 0u);
+    }
+    __threadfence_system();
+  }
+  // ---- what arrives from the left ---------------------------------------------------------------------
+  unsigned long long arr = 0;
+  uint32_t arr_ne = 0, arr_has = 0;
+  if (a.rank > 0) {
+    if (lane < a.K) {
+      for (uint32_t polls = 0;; ++polls) {
+        const uint4 v = EmLoad16(a.inbox + slot + lane);
+        if (v.z == a.step) {
+          arr = (unsigned long long)(v.y & 0x3FFFFFFFu) << 32 | v.x;
+          arr_ne = v.y >> 31;
+          arr_has = (v.y >> 30) & 1u;
+          break;
+        }
+        if (polls > (1u << 22)) { status |= 2u; break; }
+        const long long t0 = clock64();
+        while (clock64() - t0 < 128) {}
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && a.left_ack) *reinterpret_cast<volatile unsigned int*>(a.left_ack) = a.step;
+  }
+  const bool redo = arr_has && (arr > a.slab_begin || (arr_ne && arr == a.slab_begin));
+  const uint32_t redo_mask = __ballot_sync(kFullMask, redo), arr_ne_mask = __ballot_sync(kFullMask, arr_ne != 0);
+  status = __reduce_or_sync(kFullMask, status);
+  volatile StitchReport* r = a.report;
+  r->arrived_cur[lane] = arr_has ? arr : 0ull;
+  __syncwarp();
+  if (lane == 0) {
+    r->arrived_ne = arr_ne_mask;
+    r->redo = redo_mask;
+    r->status = status;
+    __threadfence_system();
+    r->step = a.step;
   }
 }
 

@@ -403,6 +403,24 @@ rejit_b200_text* rejit_b200_text_upload(int device, const char* text, size_t tex
   return t;
 }
 
+rejit_b200_text* rejit_b200_text_from_device(int device, const void* d_text, size_t text_length, char* err,
+                                             size_t err_length) {
+  std::string error;
+  void* d = DeviceAlloc(device, text_length ? text_length : 1, &error);
+  if (!d) { SetErr(err, err_length, error); return nullptr; }
+  if (text_length && !CopyOnDevice(device, d, d_text, text_length, &error)) {
+    DeviceFree(device, d);
+    SetErr(err, err_length, error);
+    return nullptr;
+  }
+  rejit_b200_text* t = new rejit_b200_text;
+  t->device = device;
+  t->d_ptr = d;
+  t->length = text_length;
+  t->capacity = text_length ? text_length : 1;
+  return t;
+}
+
 void rejit_b200_text_free(rejit_b200_text* text) {
   if (!text) return;
   {
@@ -615,6 +633,7 @@ rejit_b200_text* rejit_b200_replace_all_set_text(rejit_b200_program* const* prog
 }
 
 size_t rejit_b200_text_length(const rejit_b200_text* text) { return text ? text->length : 0; }
+const void* rejit_b200_text_device_ptr(const rejit_b200_text* text) { return text ? text->d_ptr : nullptr; }
 
 int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capacity, char* err, size_t err_length) {
   std::string error;
@@ -624,6 +643,32 @@ int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capa
     SetErr(err, err_length, error);
     return -1;
   }
+  return 0;
+}
+
+int rejit_b200_stitch_open(int device, int rank, int world, void* handle_out, char* err, size_t err_length) {
+  std::string error;
+  if (!handle_out) { SetErr(err, err_length, "rejit_b200: null argument"); return -1; }
+  if (!StitchOpen(device, rank, world, handle_out, &error)) { SetErr(err, err_length, error); return -1; }
+  return 0;
+}
+
+int rejit_b200_stitch_connect(int device, const void* left_handle, const void* right_handle, char* err, size_t err_length) {
+  std::string error;
+  if (!StitchConnect(device, left_handle, right_handle, &error)) { SetErr(err, err_length, error); return -1; }
+  return 0;
+}
+
+void rejit_b200_stitch_close(int device) { StitchClose(device); }
+
+int rejit_b200_stitch_exchange(int device, int count, const rejit_b200_carry* leaving, uint64_t slab_begin,
+                               rejit_b200_carry* arrived, uint32_t* redo_mask, char* err, size_t err_length) {
+  std::string error;
+  if (count < 1 || count > 32 || !leaving || !arrived || !redo_mask) { SetErr(err, err_length, "rejit_b200: bad argument"); return -1; }
+  Carry out[32], in[32];
+  for (int j = 0; j < count; ++j) { out[j].cur = leaving[j].cur; out[j].tail = leaving[j].tail; }
+  if (!StitchExchange(device, count, out, slab_begin, in, redo_mask, &error)) { SetErr(err, err_length, error); return -1; }
+  for (int j = 0; j < count; ++j) { arrived[j].cur = in[j].cur; arrived[j].tail = in[j].tail; }
   return 0;
 }
 

@@ -171,3 +171,107 @@ def stitched_counts_set(dist, rank: int, world: int, slab_lo: int, k: int, run, 
                     counts, couts = run(want)
         if not changed:
             return [sum(int(r[j][2]) for r in rows) for j in range(k)], rounds
+
+
+# ---------------------------------------------------------------------------
+# Neighbour stitch (round 2): the chain state only ever matters to the RIGHT neighbour, so the all-gather above is
+# replaced by one send to the right / one receive from the left.  On GPUs the send is a peer-to-peer store over
+# NVLink into the neighbour's device memory, issued by a one-warp kernel on the engine's stream
+# (rejit_b200_stitch_exchange; the inboxes are mapped once through CUDA IPC); the CPU tests run the same protocol
+# over gloo point-to-point messages.
+# ---------------------------------------------------------------------------
+def _reaches(arrived, slab_lo):
+    """The predicate of k_stitch: does the chain that arrives from the left reach into a slab that begins at slab_lo."""
+    cur, tail = arrived
+    return cur > slab_lo or (tail != NO_TAIL and tail == cur and cur == slab_lo)
+
+
+class GlooNeighbourStitch:
+    """exchange(leaving, slab_lo) -> (arrived[k], redo_mask) over torch.distributed point-to-point messages."""
+    name = "p2p"
+
+    def __init__(self, dist, rank: int, world: int):
+        self.dist, self.rank, self.world = dist, rank, world
+
+    def exchange(self, leaving, slab_lo):
+        import torch
+        k = len(leaving)
+        out = torch.tensor([[c if (c > slab_lo or t != NO_TAIL) else 0, -1 if t == NO_TAIL else t] for c, t in leaving], dtype=torch.int64)
+        req = self.dist.isend(out, self.rank + 1) if self.rank + 1 < self.world else None
+        arrived = [(0, NO_TAIL)] * k
+        if self.rank > 0:
+            got = torch.zeros((k, 2), dtype=torch.int64)
+            self.dist.recv(got, self.rank - 1)
+            arrived = [(int(c), NO_TAIL if int(t) < 0 else int(t)) for c, t in got.tolist()]
+        if req is not None:
+            req.wait()
+        redo = 0
+        for j, a in enumerate(arrived):
+            if a[0] and _reaches(a, slab_lo):
+                redo |= 1 << j
+        return arrived, redo
+
+    def close(self):
+        pass
+
+
+class DeviceStitch:
+    """The same over NVLink peer stores (include/rejit_b200.h: rejit_b200_stitch_*).  `dist` is only used once, to
+    hand the 64-byte CUDA IPC handles of the inboxes to the neighbours."""
+    name = "nvlink"
+
+    def __init__(self, dist, rank: int, world: int, device: int, tdev=None):
+        import ctypes
+        import torch
+        import rejit_b200 as rj
+        self.rj, self.device, self.rank, self.world = rj, device, rank, world
+        L = rj.lib()
+        handle = (ctypes.c_ubyte * 64)()
+        err = ctypes.create_string_buffer(256)
+        if L.rejit_b200_stitch_open(device, rank, world, handle, err, len(err)) != 0:
+            raise rj.RejitError(err.value.decode("latin-1"))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=tdev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        hs = [bytes(t.cpu().tolist()) for t in every]
+        left = (ctypes.c_ubyte * 64)(*hs[rank - 1]) if rank > 0 else None
+        right = (ctypes.c_ubyte * 64)(*hs[rank + 1]) if rank + 1 < world else None
+        if L.rejit_b200_stitch_connect(device, left, right, err, len(err)) != 0:
+            raise rj.RejitError(err.value.decode("latin-1"))
+        dist.barrier()
+
+    def exchange(self, leaving, slab_lo):
+        import ctypes
+        rj = self.rj
+        k = len(leaving)
+        out = (rj.Carry * k)(*[rj.Carry(c, t) for c, t in leaving])
+        arr = (rj.Carry * k)()
+        redo = ctypes.c_uint32()
+        err = ctypes.create_string_buffer(256)
+        if rj.lib().rejit_b200_stitch_exchange(self.device, k, out, slab_lo, arr, ctypes.byref(redo), err, len(err)) != 0:
+            raise rj.RejitError(err.value.decode("latin-1"))
+        return [(int(a.cur), int(a.tail)) for a in arr], int(redo.value)
+
+    def close(self):
+        self.rj.lib().rejit_b200_stitch_close(self.device)
+
+
+def stitched_set_neighbour(stitch, slab_lo: int, k: int, run):
+    """One step of the neighbour protocol.  run(carries) -> (counts[k], carries_out[k]) (global offsets, as for
+    stitched_counts_set).  Returns (this rank's counts[k], cascaded): `cascaded` says that resolving again with the
+    arriving chain changed the state this rank had already sent to its right neighbour (a slab without a
+    re-synchronisation point: the caller then repeats the step with stitched_counts_set, which iterates)."""
+    counts, couts = run([(slab_lo, NO_TAIL)] * k)
+    arrived, redo = stitch.exchange(couts, slab_lo)
+    cascaded = False
+    if redo:
+        want = []
+        for j in range(k):
+            if (redo >> j) & 1:
+                cur, tail = arrived[j]
+                want.append((max(cur, slab_lo), tail if tail == slab_lo else NO_TAIL))
+            else:
+                want.append((slab_lo, NO_TAIL))
+        counts, couts2 = run(want)
+        cascaded = couts2 != couts
+    return counts, cascaded

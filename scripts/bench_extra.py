@@ -111,11 +111,9 @@ def regexdna_chain(n_lines=2_000_000):
         t2 = time.perf_counter()
         counts = rs.match_all_text(cur)
         t3 = time.perf_counter()
-        iub_dev = 0.0
-        for r, a in iub:
-            nxt, _ = r.replace_all_text(cur, a, stats=st)
-            iub_dev += st.total_ms
-            cur.free(); cur = nxt
+        nxt, _ = rj.replace_all_set_text([r for r, _ in iub], cur, [a for _, a in iub], stats=st)
+        iub_dev = st.total_ms
+        cur.free(); cur = nxt
         final = len(cur)
         t4 = time.perf_counter()
         cur.free()
@@ -132,3 +130,4 @@ def regexdna_chain(n_lines=2_000_000):
 if __name__ == "__main__":
     main()
     regexdna_chain()
+    regexdna_chain(int(os.environ.get("RJ_EXTRA_CHAIN_LINES", "50000000")))

@@ -60,7 +60,22 @@ def main():
                 counts.append(int(c))
                 couts.append((int(oc.value), int(ot.value)))
             return counts, couts
-        totals, rounds = sharding.stitched_counts_set(dist, rank, world, lo, len(pats), run_set, exchange=exchange)
+        if os.environ.get("RJ_STITCH") == "p2p":
+            # the neighbour protocol of the device-side stitch (one send right, one receive left), then ONE gather of
+            # the per-rank counts and "did my answer change what I had sent"; a cascade repeats the step the old way
+            import torch
+            stitch = sharding.GlooNeighbourStitch(dist, rank, world)
+            counts, cascaded = sharding.stitched_set_neighbour(stitch, lo, len(pats), run_set)
+            mine = torch.tensor(counts + [1 if cascaded else 0], dtype=torch.int64)
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            if any(int(e[-1]) for e in every):
+                totals, rounds = sharding.stitched_counts_set(dist, rank, world, lo, len(pats), run_set)
+                rounds += 1
+            else:
+                totals, rounds = [sum(int(e[j]) for e in every) for j in range(len(pats))], 1
+        else:
+            totals, rounds = sharding.stitched_counts_set(dist, rank, world, lo, len(pats), run_set, exchange=exchange)
         set_out.append([totals, rounds])
     if rank == 0:
         print("RESULT " + json.dumps(out), flush=True)

@@ -517,9 +517,15 @@ def test_single_pass_scan_emit(rj):
             assert r.match_all(t[:cut]) == O.Oracle(pat).match_all(t[:cut]), (pat, cut)
     # line-oriented and empty matches (generic scan: SWAR start filter with and without the line context)
     lines = bytearray()
-    while len(lines) < 2 * K64 + 5000:
-        lines += bytes(rng.choice(b"abcxyz>;{} ") for _ in range(rng.randint(0, 90))) + rng.choice([b"\n", b"\n", b"\r\n", b"\n\n"])
+    while len(lines) < 2 * K64 + 5000:                   # lines long enough for the tile's candidate list (1 per 32 bytes)
+        lines += bytes(rng.choice(b"abcxyz>;{} ") for _ in range(rng.randint(30, 150))) + rng.choice([b"\n", b"\n", b"\r\n", b"\n\n"])
     lines = bytes(lines)
+    short = bytearray()                                  # ... and lines too short for it: the round-1 pipeline takes over
+    while len(short) < K64 + 3000:
+        short += bytes(rng.choice(b"abx>") for _ in range(rng.randint(0, 12))) + b"\n"
+    short = bytes(short)
+    for pat in ("^", "$", ">.*\n|\n", "(^|$|[x])"):
+        assert rj.Regej(pat).match_all(short) == O.Oracle(pat).match_all(short), pat
     for pat in ("^", "$", "^$", ">.*\n|\n", "^a", "x$", "(^|$|[x])", "^[a-c]+", ";\n}|^>", "[ab]x|^y", "\n"):
         r = rj.Regej(pat)
         st = rj.Stats()
@@ -650,3 +656,104 @@ def test_kmer_set_long_runs(rj):
         assert counts == single, (counts, single)
     finally:
         dt.free()
+
+
+def test_replace_all_set_one_pass(rj):
+    """Round 2: ReplaceAll calls applied one after the other collapse into ONE byte -> string table when every
+    pattern matches one byte and no replacement holds a later pattern's byte (regex-dna's eleven IUB codes,
+    /root/reference/sample/regexdna.cc:69-85); any other set is run call by call.  Either way the text and the
+    per-pattern counts are those of the sequential calls (oracle matches + the reference's Replace)."""
+    from rejit_b200 import workloads as W
+    seq = W.fasta_sequence(60000).tobytes()              # 600 KB, IUB codes in the middle third
+    pats = [c for c, _ in W.IUB_SUBSTITUTIONS]
+    withs = [a.encode() for _, a in W.IUB_SUBSTITUTIONS]
+
+    def sequential(text, pats, withs):
+        counts = []
+        for p, w in zip(pats, withs):
+            text, k = _replace_expected(p, text, w)
+            counts.append(k)
+        return text, counts
+
+    for text in (seq, seq[:4096], seq[:4097], seq[170000:170017], b"", b"B", b"acgt" * 3000, b"BDHKMNRSVWY" * 5000):
+        exp, exp_counts = sequential(text, pats, withs)
+        src = rj.Text(text)
+        try:
+            st = rj.Stats()
+            out, counts = rj.replace_all_set_text(pats, src, withs, stats=st)
+            assert counts == exp_counts and len(out) == len(exp) and out.download() == exp, len(text)
+            assert st.strategy != -1                       # the table, not call by call
+            out.free()
+        finally:
+            src.free()
+    # classes, deletions, long replacements, overlapping classes (the FIRST pattern that matches a byte wins)
+    t = fuzzgen.rand_text(random.Random(6), "abcdefgh\n", 70000)
+    for ps, ws in ((["[abc]", "d", "[a-e]"], [b"<1>", b"", b"Z"]), (["\n"], [b""]), (["a"], [b"x" * 40]),
+                   (["a", "b"], [b"yy", b"zz"]), (["h"], [b"h"])):
+        exp, exp_counts = sequential(t, ps, ws)
+        src = rj.Text(t)
+        out, counts = rj.replace_all_set_text(ps, src, ws)
+        assert counts == exp_counts and out.download() == exp, ps
+        out.free()
+        src.free()
+    # not a table: a replacement feeds a later pattern / a two-byte pattern -> call by call, same answer
+    for ps, ws in ((["a", "b"], [b"b", b"c"]), (["ab", "c"], [b"X", b"Y"]), (["a*", "b"], [b"-", b"+"])):
+        exp, exp_counts = sequential(t[:20000], ps, ws)
+        src = rj.Text(t[:20000])
+        st = rj.Stats()
+        out, counts = rj.replace_all_set_text(ps, src, ws, stats=st)
+        assert st.strategy == -1 and counts == exp_counts and out.download() == exp, ps
+        out.free()
+        src.free()
+
+
+def test_regexdna_chain_at_size(rj):
+    """BASELINE configs[4] on one GPU's share: strip, nine counts, eleven substitutions over a 510 MB FASTA file on
+    device-resident texts.  Size-independent checks: the stripped text IS the sequence the file was made from, the
+    nine counts equal ten times the counts of the 50 MB sequence it tiles plus the seams (counted by the oracle on
+    the seam windows), the final length is the stripped length plus (len(alt) - 1) per IUB letter."""
+    from rejit_b200 import workloads as W
+    seq = W.fasta_sequence(5_000_000)                    # 50 MB
+    tiled = np.tile(seq, 10)                             # 500 MB
+    # a FASTA file of it: one header, 60-column lines
+    n = len(tiled)
+    body = np.full(n + (n + 59) // 60, 10, dtype=np.uint8)
+    idx = np.arange(n, dtype=np.int64)
+    body[idx + idx // 60] = tiled
+    del idx
+    fa = np.concatenate([_np_text(b">ONE Homo sapiens alu\n"), body])
+    del body
+    raw = rj.Text(fa)
+    strip = rj.Regej(W.STRIP_PATTERN)
+    st = rj.Stats()
+    cur, n_strip = strip.replace_all_text(raw, b"", stats=st)
+    raw.free()
+    assert n_strip == 1 + (n + 59) // 60 and len(cur) == n
+    # the stripped text, byte for byte (sampled windows + a device-side count of every letter below)
+    got = _np_text(cur.download())
+    assert (got == tiled).all()
+    del got
+    rs = rj.RegejSet(W.DNA_PATTERNS)
+    counts = rs.match_all_text(cur)
+    base = rj.RegejSet(W.DNA_PATTERNS).match_all(seq)    # lists on the 50 MB sequence (checked against the oracle elsewhere)
+    seam = np.concatenate([seq[-16:], seq[:16]]).tobytes()
+    for j, p in enumerate(W.DNA_PATTERNS):
+        across = sum(1 for b, e in O.Oracle(p).match_all(seam) if b < 16 < e)
+        assert counts[j] == 10 * len(base[j]) + 9 * across, (p, counts[j], len(base[j]), across)
+    pats = [c for c, _ in W.IUB_SUBSTITUTIONS]
+    withs = [a.encode() for _, a in W.IUB_SUBSTITUTIONS]
+    out, k = rj.replace_all_set_text(pats, cur, withs, stats=st)
+    letters = np.bincount(tiled, minlength=256)
+    assert k == [int(letters[ord(c)]) for c in pats]
+    assert len(out) == n + sum(int(letters[ord(c)]) * (len(w) - 1) for c, w in zip(pats, withs))
+    # section ONE (10 MB, the ALU repeat) holds no IUB code: the result is unchanged up to there; the MB that
+    # follows (section TWO) against the sequential reference semantics
+    res = out.download()
+    assert res[:10_000_000] == seq[:10_000_000].tobytes()
+    exp = seq[10_000_000:11_000_000].tobytes()
+    for c, w in zip(pats, withs):
+        exp = exp.replace(c.encode(), w)
+    assert res[10_000_000:10_000_000 + len(exp)] == exp
+    del res
+    out.free()
+    cur.free()
