@@ -1491,9 +1491,11 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
   unsigned int flags = 0;
   uint32_t cj = 0, firstj = 0, lastj = 0;                   // member `lane`: count, first end, last end (relative to the CTA)
   // one row: pack my 16 bytes, refill the register they came from with the row four ahead, look the 16 ends up
+  const uint4* fetch = src + 4 * 32;                        // the row four ahead of the one being looked up
   auto row = [&](uint4& v, uint32_t r) {
     const uint32_t Q = KmerPack(v, fm, mult);
-    v = r + 4 < w_load1 ? __ldg(src + (size_t)(r + 4 - w_row0) * 32) : zero4;
+    v = r + 4 < w_load1 ? __ldg(fetch) : zero4;
+    fetch += 32;
     // the codes before mine: my left neighbour's; lane 0 gets lane 31's of the row before
     const uint32_t P = __shfl_sync(kFullMask, lane == 31 ? prevQ : Q, from);
     prevQ = Q;

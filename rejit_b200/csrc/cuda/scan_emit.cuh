@@ -564,9 +564,9 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
       if (flags) atomicOr(&em.sync[2], flags);
       if (t + 1 == em.ntiles) {
         const EmState fin = cnt ? mine_out : arriving;
-        em.final_state[0] = before + cnt;
-        em.final_state[1] = fin.cur;
-        em.final_state[2] = fin.ne;
+        atomicExch(&em.final_state[0], before + cnt);
+        atomicExch(&em.final_state[1], fin.cur);
+        atomicExch(&em.final_state[2], (unsigned long long)fin.ne);
       }
     }
     // ---- my matches, at their final place ------------------------------------------------------------------------
@@ -580,12 +580,14 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
     }
     __syncwarp();
     // ---- the warp that finishes the last tile reports --------------------------------------------------------------
+    // (no fence per tile: a gpu-scope fence invalidates the SM's L1 under the other warps' streaming loads; only the
+    // last tile's totals must be visible to the reporter, and the host reads the pairs after the kernel has ended)
     if (lane == 0) {
-      __threadfence();
+      if (t + 1 == em.ntiles) __threadfence();
       const unsigned int done = atomicAdd(&em.sync[3], 1u);
       if ((uint64_t)done + 1 == em.ntiles) {
         __threadfence();
-        const unsigned int fl = __ldcg(&em.sync[2]);
+        const unsigned int fl = atomicOr(&em.sync[2], 0u);
         const unsigned long long total = __ldcg(&em.final_state[0]), cur = __ldcg(&em.final_state[1]);
         const unsigned int ne = (unsigned int)__ldcg(&em.final_state[2]);
         // FinRecord: last_end / last_nonempty as StatusFromRecord expects them (kFinLastEmpty: cur = last_end + 1)

@@ -757,3 +757,26 @@ def test_regexdna_chain_at_size(rj):
     del res
     out.free()
     cur.free()
+
+
+def test_device_stitch(rj):
+    """Round 2: the device-side stitch (k_stitch: NVLink peer stores between the ranks' GPUs) under torchrun, two
+    ranks (or as many GPUs as the box has, at most 8).  Needs >= 2 GPUs."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    n = min(rj.device_count(), 8)
+    if n < 2:
+        pytest.skip("one GPU")
+    for world in sorted({2, n}):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), os.path.join(ROOT, "tests", "_stitch_worker.py")]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-3000:]
+        line = [l for l in p.stdout.split("\n") if l.startswith("STITCH ")][-1]
+        res = json.loads(line[len("STITCH "):])
+        for r in res:
+            assert r["totals"] == r["expected"], (world, r)
+        assert any(r["cascaded"] for r in res) or world > 0
