@@ -264,6 +264,18 @@ void rejit_b200_stitch_close(int device);
 int rejit_b200_stitch_exchange(int device, int count, const rejit_b200_carry* leaving, uint64_t slab_begin,
                                rejit_b200_carry* arrived, uint32_t* redo_mask, char* err, size_t err_length);
 
+/* The slab call of a pattern set and the exchange in ONE step: as
+ * rejit_b200_match_all_set_device_slab with "nothing arrives from the left",
+ * followed by rejit_b200_stitch_exchange — but when the fused k-mer scan runs, the
+ * CTA that reports the result sends and receives the chain states itself, inside
+ * the scan kernel (no second launch, no host hop in between; the step's device time
+ * includes the neighbour's answer).  carry_out: buffer coordinates, as for the slab
+ * call; arrived / redo_mask: as for rejit_b200_stitch_exchange.                       */
+int rejit_b200_match_all_set_device_stitched(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
+                                             uint64_t own_begin, uint64_t own_end, uint64_t base_offset,
+                                             rejit_b200_carry* carry_out, rejit_b200_carry* arrived, uint32_t* redo_mask,
+                                             int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length);
+
 void rejit_b200_free(void* ptr);
 
 #ifdef __cplusplus

@@ -53,7 +53,8 @@ EXPORTED = [
     "rejit_b200_set_create", "rejit_b200_set_free", "rejit_b200_set_describe", "rejit_b200_set_kmer_tables",
     "rejit_b200_match_all_set_text", "rejit_b200_match_all_set_device", "rejit_b200_match_all_set_device_slab",
     "rejit_b200_replace_all", "rejit_b200_replace_all_text", "rejit_b200_replace_all_set_text",
-    "rejit_b200_stitch_open", "rejit_b200_stitch_connect", "rejit_b200_stitch_close", "rejit_b200_stitch_exchange", "rejit_b200_text_length", "rejit_b200_text_device_ptr", "rejit_b200_text_download",
+    "rejit_b200_stitch_open", "rejit_b200_stitch_connect", "rejit_b200_stitch_close", "rejit_b200_stitch_exchange",
+    "rejit_b200_match_all_set_device_stitched", "rejit_b200_text_length", "rejit_b200_text_device_ptr", "rejit_b200_text_download",
 ]
 
 
@@ -143,6 +144,9 @@ def lib():
     L.rejit_b200_stitch_close.argtypes = [ctypes.c_int]
     L.rejit_b200_stitch_exchange.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Carry), ctypes.c_uint64,
                                              ctypes.POINTER(Carry), ctypes.POINTER(ctypes.c_uint32), cp, sz]
+    L.rejit_b200_match_all_set_device_stitched.argtypes = [vp, ctypes.c_int, vp, sz, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                                           ctypes.POINTER(Carry), ctypes.POINTER(Carry), ctypes.POINTER(ctypes.c_uint32),
+                                                           ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(Stats), cp, sz]
     L.rejit_b200_text_length.argtypes = [vp]
     L.rejit_b200_text_length.restype = sz
     L.rejit_b200_text_device_ptr.argtypes = [vp]
@@ -519,6 +523,21 @@ class RegejSet:
         if r < 0:
             raise RejitError(err.value.decode("latin-1"))
         return list(counts)
+
+    def match_all_device_stitched(self, dtext: "DeviceText", own, base_offset: int, stats: Optional[Stats] = None):
+        """Slab call + device-side stitch in one step (rejit_b200_match_all_set_device_stitched).
+        Returns (counts, carries_out [(cur, tail)] in buffer coordinates, arrived [(cur, tail)] global, redo mask)."""
+        k = len(self.members)
+        counts = (ctypes.c_int64 * k)()
+        cout, arr = (Carry * k)(), (Carry * k)()
+        redo = ctypes.c_uint32()
+        err = ctypes.create_string_buffer(512)
+        r = lib().rejit_b200_match_all_set_device_stitched(self._set, dtext.device, dtext.ptr, dtext.nbytes, own[0], own[1], base_offset,
+                                                           cout, arr, ctypes.byref(redo), counts,
+                                                           ctypes.byref(stats) if stats is not None else None, err, len(err))
+        if r < 0:
+            raise RejitError(err.value.decode("latin-1"))
+        return list(counts), [(int(c.cur), int(c.tail)) for c in cout], [(int(a.cur), int(a.tail)) for a in arr], int(redo.value)
 
     def match_all_text(self, text: "Text", stats: Optional[Stats] = None) -> List[int]:
         """Counts per member over an uploaded Text (no match lists copied back)."""

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "librejit_b200.so")
 
 HOST_SOURCES = ["host/parser.cc", "host/lower.cc", "host/automaton.cc", "host/capi.cc", "host/regej.cc"]
 CUDA_SOURCES = ["cuda/engine.cu"]
-HEADERS = ["host/ir.h", "host/automaton.h", "cuda/engine.h", "cuda/device_program.h", "cuda/kernels.cuh",
+HEADERS = ["host/ir.h", "host/automaton.h", "cuda/engine.h", "cuda/device_program.h", "cuda/kernels.cuh", "cuda/scan_emit.cuh", "cuda/replace.cuh", "cuda/stitch.cuh",
            "../../include/rejit.h", "../../include/rejit_b200.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

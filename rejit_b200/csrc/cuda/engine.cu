@@ -85,7 +85,7 @@ struct Buffer {
 // ---------------------------------------------------------------------------
 class WorkerPool {
  public:
-  static WorkerPool& Staging() { static WorkerPool* pool = new WorkerPool(12); return *pool; }   // memcpy streams
+  static WorkerPool& Staging() { static WorkerPool* pool = new WorkerPool(31); return *pool; }   // memcpy streams
   static WorkerPool& Devices() { static WorkerPool* pool = new WorkerPool(15); return *pool; }   // one task per GPU
   int size() const { return (int)threads_.size(); }
   // fn(i) for i in [0, n), on up to `width` threads (the caller works too); returns when all are done
@@ -109,7 +109,7 @@ class WorkerPool {
  private:
   explicit WorkerPool(unsigned cap) {
     unsigned hw = std::thread::hardware_concurrency();
-    int n = (int)std::max(1u, std::min(cap, hw > 2 ? hw / 2 : 1u));
+    int n = (int)std::max(1u, std::min(cap, hw > 3 ? hw - 2 : 1u));
     for (int i = 0; i < n; ++i) threads_.emplace_back([this, i] { Loop(i); });
     for (auto& t : threads_) t.detach();
   }
@@ -183,8 +183,8 @@ class DeviceContext {
   PipelineStatus* h_set_status_dev = nullptr;
   Buffer flush;
   // pinned staging ring for pageable host texts (UploadHostText)
-  static constexpr int kStageBufs = 12;
-  static constexpr size_t kStageBytes = 2u << 20;
+  static constexpr int kStageBufs = 24;
+  static constexpr size_t kStageBytes = 1u << 20;
   uint8_t* stage_buf[kStageBufs] = {nullptr};
   cudaEvent_t stage_ev[kStageBufs] = {nullptr};
   Buffer trans_tab, trans_len, trans_off, trans_counts;   // byte -> string table of ReplaceAllSetDevice and its tile sums
@@ -1120,7 +1120,8 @@ bool UploadHostText(DeviceContext* c, void* d_dst, const uint8_t* src, size_t le
   std::mutex ring_mu[DeviceContext::kStageBufs];
   const int device = c->device;
   // chunk i goes through ring buffer i % kStageBufs; a buffer is reused once its previous copy has left it
-  WorkerPool::Staging().Run(n_chunks, 8, [&](int i) {
+  static const int width = getenv("RJ_STAGE_WIDTH") ? std::max(1, atoi(getenv("RJ_STAGE_WIDTH"))) : 12;
+  WorkerPool::Staging().Run(n_chunks, width, [&](int i) {
     if (failed.load()) return;
     cudaSetDevice(device);
     const int b = i % DeviceContext::kStageBufs;
@@ -1348,7 +1349,7 @@ DeviceSet* SetProgram::OnDevice(int device, std::string* error) {
 
 int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint64_t n, int64_t* counts,
                         uint64_t** pairs, RunStats* stats, std::string* error, const SlabView* own_view,
-                        const Carry* carry_in, Carry* carry_out) {
+                        const Carry* carry_in, Carry* carry_out, StitchCall* stitch) {
   DeviceContext* c = ContextFor(device, error);
   if (!c) return -1;
   const int K = set->size();
@@ -1463,6 +1464,16 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           run.base_offset = base_offset;
           run.host_records = c->h_fin_dev;
           run.seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
+          if (stitch && c->stitch_inbox) {
+            run.stitch.enabled = 1;
+            run.stitch.rank = c->stitch_rank;
+            run.stitch.slab_begin = stitch->slab_begin;
+            run.stitch.inbox = static_cast<uint4*>(c->stitch_inbox);
+            run.stitch.right_inbox = static_cast<uint4*>(c->stitch_right);
+            run.stitch.left_ack = c->stitch_left ? reinterpret_cast<unsigned int*>(c->stitch_left) + kStitchAckWord : nullptr;
+            run.stitch.step = stitch->step;
+            run.stitch.report = c->h_stitch_dev;
+          }
 #ifdef RJ_KMER_PROBE
           if (!c->kmer_probe.Reserve((size_t)blocks * 65 * 8, error)) return -1;
           cudaMemsetAsync(c->kmer_probe.p, 0, (size_t)blocks * 65 * 8, s);
@@ -1528,6 +1539,7 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           if (grow_stage) { ds->stage_cap *= 4; redo = true; }
           if (need) ds->per_cap = need + need / 4 + 1024;
           if (redo) { if (stats) stats->reruns += 1; continue; }
+          if (run.stitch.enabled) stitch->sent = true;          // the kernel has sent this step's states (valid)
           return deliver(per_cap, 4);
         }
       }
@@ -1981,37 +1993,14 @@ void StitchClose(int device) {
   c->stitch_left = c->stitch_right = nullptr;
 }
 
-bool StitchExchange(int device, int K, const Carry* leaving, uint64_t slab_begin, Carry* arrived, uint32_t* redo_mask,
-                    std::string* error) {
-  DeviceContext* c = ContextFor(device, error);
-  if (!c) return false;
-  if (!c->stitch_inbox || K < 1 || K > 32) { if (error) *error = "rejit_b200: stitch not opened (or more than 32 patterns)"; return false; }
-  std::lock_guard<std::mutex> lk(c->mu);
-  RJ_TRY(cudaSetDevice(c->device));
-  StitchArgs a{};
-  a.K = K;
-  a.rank = c->stitch_rank;
-  for (int j = 0; j < K; ++j) {
-    // a chain that has not moved past the slab's first byte cannot reach the neighbour: nothing to say
-    const bool has = leaving[j].cur > slab_begin || (leaving[j].tail != kNoMatch);
-    a.sent_cur[j] = has ? leaving[j].cur : 0;
-    if (has) a.sent_has |= 1u << j;
-    if (has && leaving[j].tail == leaving[j].cur) a.sent_ne |= 1u << j;
-  }
-  a.slab_begin = slab_begin;
-  a.inbox = static_cast<uint4*>(c->stitch_inbox);
-  a.right_inbox = static_cast<uint4*>(c->stitch_right);
-  a.left_ack = c->stitch_left ? reinterpret_cast<unsigned int*>(c->stitch_left) + kStitchAckWord : nullptr;
-  a.step = ++c->stitch_step ? c->stitch_step : ++c->stitch_step;
-  a.report = c->h_stitch_dev;
-  k_stitch<<<1, 32, 0, c->stream>>>(a);
-  RJ_TRY(cudaGetLastError());
+namespace {
+bool WaitStitchReport(DeviceContext* c, unsigned int step, int K, Carry* arrived, uint32_t* redo_mask, std::string* error) {
   volatile StitchReport* r = c->h_stitch;
   uint64_t spins = 0;
-  while (r->step != a.step) {
+  while (r->step != step) {
     if ((++spins & 0x3FFF) == 0) {
       cudaError_t q = cudaStreamQuery(c->stream);
-      if (q == cudaSuccess) { if (r->step == a.step) break; if (error) *error = "rejit_b200: the stitch kernel did not report"; return false; }
+      if (q == cudaSuccess) { if (r->step == step) break; if (error) *error = "rejit_b200: the stitch did not report"; return false; }
       if (q != cudaErrorNotReady) { Check(q, "cudaStreamQuery", error); return false; }
     }
   }
@@ -2023,6 +2012,54 @@ bool StitchExchange(int device, int K, const Carry* leaving, uint64_t slab_begin
   }
   *redo_mask = r->redo;
   return true;
+}
+}  // namespace
+
+unsigned int StitchNextStep(int device) {
+  std::string err;
+  DeviceContext* c = ContextFor(device, &err);
+  if (!c || !c->stitch_inbox) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  return ++c->stitch_step ? c->stitch_step : ++c->stitch_step;
+}
+
+bool StitchCollect(int device, unsigned int step, int K, Carry* arrived, uint32_t* redo_mask, std::string* error) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return false;
+  std::lock_guard<std::mutex> lk(c->mu);
+  return WaitStitchReport(c, step, K, arrived, redo_mask, error);
+}
+
+bool StitchExchange(int device, int K, const Carry* leaving, uint64_t slab_begin, Carry* arrived, uint32_t* redo_mask,
+                    std::string* error, unsigned int step) {
+  DeviceContext* c = ContextFor(device, error);
+  if (!c) return false;
+  if (!c->stitch_inbox || K < 1 || K > 32) { if (error) *error = "rejit_b200: stitch not opened (or more than 32 patterns)"; return false; }
+  std::lock_guard<std::mutex> lk(c->mu);
+  RJ_TRY(cudaSetDevice(c->device));
+  StitchArgs a{};
+  a.K = K;
+  for (int j = 0; j < K; ++j) {
+    // a chain that has not moved past the slab's first byte cannot reach the neighbour: nothing to say
+    const bool has = leaving[j].cur > slab_begin || (leaving[j].tail != kNoMatch);
+    a.sent_cur[j] = has ? leaving[j].cur : 0;
+    if (has) a.sent_has |= 1u << j;
+    if (has && leaving[j].tail == leaving[j].cur) a.sent_ne |= 1u << j;
+  }
+  a.link.enabled = 1;
+  a.link.rank = c->stitch_rank;
+  a.link.slab_begin = slab_begin;
+  a.link.inbox = static_cast<uint4*>(c->stitch_inbox);
+  a.link.right_inbox = static_cast<uint4*>(c->stitch_right);
+  a.link.left_ack = c->stitch_left ? reinterpret_cast<unsigned int*>(c->stitch_left) + kStitchAckWord : nullptr;
+  if (!step) step = ++c->stitch_step ? c->stitch_step : ++c->stitch_step;
+  a.link.step = step;
+  a.link.report = c->h_stitch_dev;
+  c->h_stitch->step = 0;                                     // (a fused attempt of the same step may have reported already)
+  std::atomic_thread_fence(std::memory_order_release);
+  k_stitch<<<1, 32, 0, c->stream>>>(a);
+  RJ_TRY(cudaGetLastError());
+  return WaitStitchReport(c, step, K, arrived, redo_mask, error);
 }
 
 int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error) {

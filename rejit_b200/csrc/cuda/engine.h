@@ -115,9 +115,17 @@ class SetProgram {
 // matches of member j; if pairs != nullptr, pairs[j] receives a malloc'ed array
 // of counts[j] (begin,end) pairs.  Returns 0, or -1 with *error set.
 // `own`, `carry_in` (one per member) and `carry_out` are optional: slab sharding.
+// `stitch` (optional, one process per GPU): the call is step `step` of the device-side stitch; when the k-mer scan
+// ran, its reporting CTA has exchanged the chain states with the neighbouring GPUs itself (sent = true) and the
+// answer waits in the context's report (StitchCollect); otherwise the caller sends with StitchExchange(step).
+struct StitchCall {
+  unsigned int step = 0;
+  uint64_t slab_begin = 0;             // first owned start, global
+  bool sent = false;
+};
 int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint64_t n, int64_t* counts,
                         uint64_t** pairs, RunStats* stats, std::string* error, const SlabView* own = nullptr,
-                        const Carry* carry_in = nullptr, Carry* carry_out = nullptr);
+                        const Carry* carry_in = nullptr, Carry* carry_out = nullptr, StitchCall* stitch = nullptr);
 
 // Regej::ReplaceAll on the device (reference
 // src/rejit.cc:221-226, 97-112): every match in d_text[0..n) is replaced by
@@ -151,7 +159,9 @@ bool StitchOpen(int device, int rank, int world, void* handle64, std::string* er
 bool StitchConnect(int device, const void* left_handle64, const void* right_handle64, std::string* error);
 void StitchClose(int device);
 bool StitchExchange(int device, int K, const Carry* leaving, uint64_t slab_begin, Carry* arrived, uint32_t* redo_mask,
-                    std::string* error);
+                    std::string* error, unsigned int step = 0);
+unsigned int StitchNextStep(int device);                 // the step number of the next exchange (0: stitch not opened)
+bool StitchCollect(int device, unsigned int step, int K, Carry* arrived, uint32_t* redo_mask, std::string* error);
 
 // MatchFull: 1 / 0, or -1 on error.
 int MatchFullHost(int device, Program* prog, const uint8_t* text, uint64_t n, std::string* error);

@@ -29,6 +29,7 @@
 
 #include "device_program.h"
 #include "engine.h"
+#include "stitch.cuh"
 
 namespace rejit_b200 {
 
@@ -1283,6 +1284,8 @@ struct KmerRun {
   FinRecord* host_records;
   unsigned int seq;
   int has_carry;                       // some member's chain arrives from the left (CarrySet is read only then)
+  StitchLink stitch;                   // one process per GPU: the reporting CTA exchanges the chain states with the
+                                       // neighbouring ranks' GPUs before it reports (stitch.cuh); enabled = 0 otherwise
 #ifdef RJ_KMER_PROBE
   unsigned long long* probe;           // tuning builds only: [grid][32][2] globaltimer at scan start / end, then [grid] at exit
 #endif
@@ -1753,6 +1756,19 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
     if (is_last) {
       __threadfence();
       const unsigned int flg = __ldcg(&run.gsync[0]);
+      if (run.stitch.enabled) {
+        // scan + stitch in one kernel: the chain states leave for the right neighbour's HBM now; a call that the
+        // host will repeat (flags, output too small) is sent as invalid and sent again by the repeat
+        unsigned long long cur = 0;
+        uint32_t has = 0, invalid = flg ? 1u : 0u;
+        if (lane < K) {
+          const unsigned long long total = __ldcg(&run.gfinal[2 * lane]), le = __ldcg(&run.gfinal[2 * lane + 1]);
+          if (total > run.out_cap) invalid = 1;
+          if (total) { cur = le + run.base_offset; has = 1; }
+        }
+        invalid = __any_sync(kFullMask, invalid != 0) ? 1u : 0u;
+        StitchExchangeWarp(run.stitch, K, cur, has, has, invalid);
+      }
       if (lane < K) {
         const unsigned long long total = __ldcg(&run.gfinal[2 * lane]), le = __ldcg(&run.gfinal[2 * lane + 1]);
         volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.host_records + lane);

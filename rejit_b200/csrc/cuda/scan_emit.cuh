@@ -57,7 +57,8 @@ constexpr uint32_t kEmDropped = 0xFFFFu;                      // length field of
 constexpr uint32_t kEmPending = 0xFFFEu;                      // length field of a start that has not been evaluated yet
 constexpr unsigned int kFinLastEmpty = 8u;                    // FinRecord.flags: the last match is empty
 constexpr unsigned int kFinStuck = 16u;                       // a look-back gave up waiting (never expected)
-constexpr size_t kEmSmemBytes = kEmWarps * (kEmEntCap * 4 + kEmCandCap * 4);
+constexpr uint32_t kEmTableBytes = 6144;                      // the pattern's NFA tables, when they fit (else they stay in global memory)
+constexpr size_t kEmSmemBytes = kEmWarps * (kEmEntCap * 4 + kEmCandCap * 4) + kEmTableBytes;
 
 // a candidate in shared memory: begin - tile_base in the low half, length in the high half
 __device__ __forceinline__ uint32_t EmCand(uint32_t rel, uint32_t len) { return rel | (len << 16); }
@@ -411,6 +412,28 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
   extern __shared__ __align__(16) uint8_t em_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  if (kMode != kEmLiteral) {
+    // The NFA tables go to shared memory when they fit (one- and two-word patterns do): with 200 KB of shared
+    // memory per SM in use the L1 is 30 KB under 32 streaming warps, and every table lookup of an NFA run was an
+    // L2 round trip.  The pointers in `nfa` are generic, so the runs do not care where the tables live.
+    const uint32_t W = (uint32_t)nfa.words, P = (uint32_t)(nfa.n_pos > 0 ? nfa.n_pos : 1);
+    const uint32_t words = 256 * W + 4 * W + 4 * P * W + 4 * W + W;             // byte_mask, first, follow, accept, chain
+    const uint32_t bytes = words * 4 + (kMode == kEmWindow ? 1024u : 0u);       // + start_ok
+    if (bytes <= kEmTableBytes) {
+      uint32_t* tab = reinterpret_cast<uint32_t*>(em_smem + kEmWarps * (kEmEntCap * 4 + kEmCandCap * 4));
+      uint32_t* s_bm = tab, *s_first = s_bm + 256 * W, *s_follow = s_first + 4 * W, *s_accept = s_follow + 4 * P * W,
+                *s_chain = s_accept + 4 * W;
+      uint8_t* s_ok = reinterpret_cast<uint8_t*>(s_chain + W);
+      for (uint32_t i = threadIdx.x; i < 256 * W; i += kEmThreads) s_bm[i] = nfa.byte_mask[i];
+      for (uint32_t i = threadIdx.x; i < 4 * W; i += kEmThreads) { s_first[i] = nfa.first[i]; s_accept[i] = nfa.accept[i]; }
+      for (uint32_t i = threadIdx.x; i < 4 * P * W; i += kEmThreads) s_follow[i] = nfa.follow[i];
+      for (uint32_t i = threadIdx.x; i < W; i += kEmThreads) s_chain[i] = nfa.chain[i];
+      if (kMode == kEmWindow) for (uint32_t i = threadIdx.x; i < 1024; i += kEmThreads) s_ok[i] = nfa.start_ok[i];
+      __syncthreads();
+      nfa.byte_mask = s_bm; nfa.first = s_first; nfa.follow = s_follow; nfa.accept = s_accept; nfa.chain = s_chain;
+      if (kMode == kEmWindow) nfa.start_ok = s_ok;
+    }
+  }
   uint32_t* my_ent = reinterpret_cast<uint32_t*>(em_smem) + warp * kEmEntCap;
   uint32_t* my_cand = reinterpret_cast<uint32_t*>(em_smem + kEmWarps * kEmEntCap * 4) + warp * kEmCandCap;
   uint32_t* my_hits = my_cand + kEmWinCandCap;                                          // window mode: the upper half
@@ -602,91 +625,6 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
                      "r"((unsigned int)(last_ne >> 32)), "r"(0u), "r"(em.seq) : "memory");
       }
     }
-  }
-}
-
-// ===========================================================================
-// Device-side stitch of slab-sharded texts (one process per GPU): every rank sends the chain state
-// that leaves its slab — per pattern: where the next match may begin — straight into the right neighbour's device
-// memory (a peer store over NVLink; the inbox is mapped through CUDA IPC) and checks the state that arrives from
-// the left: only when that chain reaches into the slab does the host repeat the slab call with the real carry.
-// One warp on the engine's stream; no host-to-host hop, no collective.
-//   inbox slot (step & 63): [32] uint4 {cur lo, cur hi | ne << 31 | has << 30, step, 0}
-//   flow control: a rank is at most 32 steps ahead of its right neighbour (ack word written back by the receiver)
-// ===========================================================================
-constexpr uint32_t kStitchSlots = 64;
-constexpr uint32_t kStitchAckWord = kStitchSlots * 32 * 4;               // index (in words) of the ack word
-constexpr uint32_t kStitchInboxBytes = kStitchSlots * 32 * 16 + 64;
-
-struct StitchReport {                   // mapped host memory, one per device context
-  unsigned long long arrived_cur[32];   // global offset where the chain arriving from the left lets a match begin (0: none)
-  unsigned int arrived_ne;              // bit j: that chain's last match was non-empty
-  unsigned int redo;                    // bit j: the arriving chain of pattern j reaches into the slab
-  unsigned int status;                  // 2: a neighbour did not answer
-  unsigned int step;                    // written last
-};
-
-struct StitchArgs {
-  int K, rank;
-  unsigned long long sent_cur[32];      // what leaves my slab, global offsets
-  unsigned int sent_ne, sent_has;
-  uint64_t slab_begin;                  // first owned start, global
-  uint4* inbox;                         // mine
-  uint4* right_inbox;                   // the right neighbour's (NULL on the last rank)
-  unsigned int* left_ack;               // the ack word in the left neighbour's inbox (NULL on rank 0)
-  unsigned int step;
-  StitchReport* report;
-};
-
-__global__ void __launch_bounds__(32, 1) k_stitch(StitchArgs a) {
-  const int lane = threadIdx.x;
-  uint32_t status = 0;
-  const uint32_t slot = (a.step & (kStitchSlots - 1)) * 32;
-  // ---- send to the right (not more than 32 steps ahead of what the neighbour has consumed) ------------
-  if (a.right_inbox) {
-    const volatile unsigned int* ack = reinterpret_cast<const volatile unsigned int*>(a.inbox) + kStitchAckWord;
-    for (uint32_t polls = 0; (int)(a.step - *ack) > 32; ++polls)
-      if (polls > (1u << 22)) { status |= 2u; break; }
-    if (lane < a.K) {
-      const unsigned long long cur = a.sent_cur[lane];
-      EmStore16(a.right_inbox + slot + lane, (uint32_t)cur,
-                (uint32_t)(cur >> 32) | (((a.sent_ne >> lane) & 1u) << 31) | (((a.sent_has >> lane) & 1u) << 30), a.step, 0u);
-    }
-    __threadfence_system();
-  }
-  // ---- what arrives from the left ---------------------------------------------------------------------
-  unsigned long long arr = 0;
-  uint32_t arr_ne = 0, arr_has = 0;
-  if (a.rank > 0) {
-    if (lane < a.K) {
-      for (uint32_t polls = 0;; ++polls) {
-        const uint4 v = EmLoad16(a.inbox + slot + lane);
-        if (v.z == a.step) {
-          arr = (unsigned long long)(v.y & 0x3FFFFFFFu) << 32 | v.x;
-          arr_ne = v.y >> 31;
-          arr_has = (v.y >> 30) & 1u;
-          break;
-        }
-        if (polls > (1u << 22)) { status |= 2u; break; }
-        const long long t0 = clock64();
-        while (clock64() - t0 < 128) {}
-      }
-    }
-    __syncwarp();
-    if (lane == 0 && a.left_ack) *reinterpret_cast<volatile unsigned int*>(a.left_ack) = a.step;
-  }
-  const bool redo = arr_has && (arr > a.slab_begin || (arr_ne && arr == a.slab_begin));
-  const uint32_t redo_mask = __ballot_sync(kFullMask, redo), arr_ne_mask = __ballot_sync(kFullMask, arr_ne != 0);
-  status = __reduce_or_sync(kFullMask, status);
-  volatile StitchReport* r = a.report;
-  r->arrived_cur[lane] = arr_has ? arr : 0ull;
-  __syncwarp();
-  if (lane == 0) {
-    r->arrived_ne = arr_ne_mask;
-    r->redo = redo_mask;
-    r->status = status;
-    __threadfence_system();
-    r->step = a.step;
   }
 }
 

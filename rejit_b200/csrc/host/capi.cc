@@ -672,6 +672,51 @@ int rejit_b200_stitch_exchange(int device, int count, const rejit_b200_carry* le
   return 0;
 }
 
+int rejit_b200_match_all_set_device_stitched(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
+                                             uint64_t own_begin, uint64_t own_end, uint64_t base_offset,
+                                             rejit_b200_carry* carry_out, rejit_b200_carry* arrived, uint32_t* redo_mask,
+                                             int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) {
+  std::string error;
+  RunStats rs;
+  const int k = set->set->size();
+  if (k > 32 || !arrived || !redo_mask) { SetErr(err, err_length, "rejit_b200: bad argument"); return -1; }
+  for (Program* member : set->set->members())
+    if (!SlabAllowed(member, true, err, err_length)) return -1;
+  StitchCall sc;
+  sc.step = StitchNextStep(device);
+  if (!sc.step) { SetErr(err, err_length, "rejit_b200: stitch not opened"); return -1; }
+  sc.slab_begin = base_offset + own_begin;
+  std::vector<Carry> in(k), out(k);
+  for (int j = 0; j < k; ++j) { in[j].cur = own_begin; in[j].tail = ~0ull; }      // nothing arrives (to be checked by the stitch)
+  SlabView view;
+  view.own_begin = own_begin;
+  view.own_end = own_end;
+  view.base_offset = base_offset;
+  int r = MatchAllSetResident(device, set->set, static_cast<const uint8_t*>(d_text), text_length, out_counts, nullptr,
+                              stats ? &rs : nullptr, &error, &view, in.data(), out.data(), &sc);
+  Carry got[32];
+  bool ok = r >= 0;
+  if (ok && sc.sent) {
+    ok = StitchCollect(device, sc.step, k, got, redo_mask, &error);
+  } else {
+    // another scan path ran (or the call failed: the neighbours must still get this step's record)
+    Carry leaving[32];
+    for (int j = 0; j < k; ++j) {
+      leaving[j].cur = (ok ? out[j].cur : own_begin) + base_offset;
+      leaving[j].tail = (ok && out[j].tail != ~0ull) ? out[j].tail + base_offset : ~0ull;
+    }
+    const bool sent = StitchExchange(device, k, leaving, sc.slab_begin, got, redo_mask, ok ? &error : nullptr, sc.step);
+    ok = ok && sent;
+  }
+  if (!ok) { SetErr(err, err_length, error); return -1; }
+  for (int j = 0; j < k; ++j) {
+    arrived[j].cur = got[j].cur; arrived[j].tail = got[j].tail;
+    if (carry_out) { carry_out[j].cur = out[j].cur; carry_out[j].tail = out[j].tail; }
+  }
+  FillStats(rs, stats);
+  return 0;
+}
+
 void rejit_b200_free(void* ptr) { free(ptr); }
 
 }  // extern "C"
