@@ -55,6 +55,7 @@ sys.path.insert(0, ROOT)
 
 FASTA_N = 5_000_000            # -> 50,000,000 bytes per slab
 HALO = 64
+ROTATE = 6                     # device copies of the slab the timed steps rotate over (300 MB > L2)
 
 
 def load_peaks():
@@ -556,7 +557,8 @@ def main():
     config = {"workload": "regex-dna alternation set (9 patterns, sample/regexdna.cc:52-62; BASELINE says 8) "
                           "over 50 MB synthetic FASTA sequence per GPU (BASELINE.json configs[1])",
               "text_bytes_per_gpu": FASTA_N * 10, "patterns": K,
-              "l2": "flushed before every call (256 MB write), outside the timed events",
+              "l2": "the timed steps rotate over %d device copies of the slab (%d MB > the 126 MB L2): every step reads "
+                    "HBM-cold text, no flush kernel between steps (ms_per_step_l2_flushed: the round-1 protocol)" % (ROTATE, ROTATE * 50),
               "parallelism": "slab%d" % args.gpus,
               "value_definition": "physical: text bytes / step time (the nine patterns share ONE pass); value_per_pattern = 9x"}
 
@@ -629,6 +631,10 @@ def main():
     for r in regs:
         r.compile()
     dtext = rj.DeviceText(buf, device=local_rank)
+    # the timed steps rotate over ROTATE device copies of the text (ROTATE * 50 MB > the 126 MB L2): every step reads
+    # HBM-cold bytes without a flush kernel (and, at N > 1, without a barrier) between the steps
+    rotation = [dtext] + [rj.DeviceText(buf, device=local_rank) for _ in range(ROTATE - 1)]
+    step_no = [0]
     total_text = n_own * world
     rset = rj.RegejSet(regs)
 
@@ -649,11 +655,12 @@ def main():
                 stitch = None
     config["stitch"] = ("nvlink" if stitch is not None else "nccl") if world > 1 else "none (one slab)"
     if world > 1:
-        config["timing"] = ("step = device pipeline time of the rank's own call (CUDA events, as at N=1) + host time inside the "
-                            "stitch (k_stitch: launch, peer store, wait for the left neighbour); ranks aligned by an untimed "
-                            "barrier after the L2 flush; max over ranks")
+        config["timing"] = ("step = device pipeline time of the rank's own call (CUDA events on the engine's stream, as at N=1); "
+                            "the scan kernel's reporting CTA sends the chain states to the right neighbour and waits for the "
+                            "left neighbour's INSIDE the kernel, so the events include the exchange and any rank skew; K steps "
+                            "back to back between barrier + synchronize brackets, no barrier inside; max over ranks")
 
-    def slab_run(stats, acc):
+    def slab_run(stats, acc, dtext=dtext):
         def run(carries):
             cin = (rj.Carry * K)(*[rj.Carry(max(c - slab_lo, 0), t - slab_lo if t != sharding.NO_TAIL and t >= slab_lo else sharding.NO_TAIL)
                                    for c, t in carries])
@@ -669,20 +676,45 @@ def main():
         return run
 
     cascades = [0]
+    fused_stitch = [os.environ.get("RJ_STITCH_FUSED", "1") != "0"]
+
+    own_end = n_own if rank + 1 < world else (1 << 62)
 
     def one_step_fused(how=None):
         """One step: (step ms, scan ms, launches, this rank's counts)."""
-        rj.lib().rejit_b200_flush_l2(local_rank)
         st = rj.Stats()
-        if world == 1:
+        if how == "flush":                                   # the round-1 protocol: one buffer, L2 flushed before the call
+            rj.lib().rejit_b200_flush_l2(local_rank)
             cnts = rset.match_all_device(dtext, stats=st)
             return st.total_ms, st.scan_ms, st.launches, cnts
-        torch.cuda.synchronize(local_rank)
-        dist.barrier()                                       # all ranks start the step together (untimed)
+        dt_now = rotation[step_no[0] % ROTATE]
+        step_no[0] += 1
+        if world == 1:
+            cnts = rset.match_all_device(dt_now, stats=st)
+            return st.total_ms, st.scan_ms, st.launches, cnts
         acc = [0.0, 0.0, 0]
-        run = slab_run(st, acc)
+        run = slab_run(st, acc, dt_now)
+        if how is None and stitch is not None and fused_stitch[0]:
+            # scan + stitch in ONE kernel: the reporting CTA of k_set_kmer sends the chain states to the right
+            # neighbour's HBM and waits for the left neighbour's; the device time of the call includes that wait
+            cnts, couts, arrived, redo = rset.match_all_device_stitched(dt_now, (0, own_end), slab_lo, stats=st)
+            acc = [st.total_ms, st.scan_ms, st.launches]
+            if redo:
+                want = [(max(arrived[j][0], slab_lo), arrived[j][1] if arrived[j][1] == slab_lo else sharding.NO_TAIL)
+                        if (redo >> j) & 1 else (slab_lo, sharding.NO_TAIL) for j in range(K)]
+                cnts, couts2 = run(want)
+                acc[0] += st.total_ms
+                acc[1] += st.scan_ms
+                acc[2] += st.launches
+                couts_g = [(c + slab_lo, t + slab_lo if t != sharding.NO_TAIL else sharding.NO_TAIL) for c, t in couts]
+                if couts2 != couts_g:
+                    cascades[0] += 1
+            return acc[0], acc[1], acc[2], cnts
         t0 = time.perf_counter()
         if how == "nccl" or stitch is None:
+            torch.cuda.synchronize(local_rank)
+            dist.barrier()                                   # all ranks start the step together (untimed)
+            t0 = time.perf_counter()
             t_run = [0.0]
 
             def timed_run(c):
@@ -722,9 +754,10 @@ def main():
     warm = max(3, args.warmup)
     for _ in range(warm):
         one_step_fused()
+    torch.cuda.synchronize(local_rank)
     if dist is not None:
         dist.barrier()
-    # ---- headline: the fused set path ----------------------------------------------
+    # ---- headline: the fused set path: EXACTLY K steps between barrier + synchronize brackets -------------
     t_wall = time.perf_counter()
     f_ms = f_scan = 0.0
     f_launches = 0
@@ -734,6 +767,8 @@ def main():
         f_ms += ms
         f_scan += sc
         f_launches += la
+    torch.cuda.synchronize(local_rank)
+    host_ms_per_step = (time.perf_counter() - t_wall) * 1e3 / args.steps      # host clock incl. the Python call overhead
     if dist is not None:
         t = torch.tensor([f_ms], dtype=torch.float64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -747,6 +782,27 @@ def main():
         dist.barrier()
     else:
         n_cascades = 0
+    # the same step with the stitch as a second launch (k_stitch) after the scan (N > 1 only)
+    sep_ms = None
+    if world > 1 and stitch is not None and fused_stitch[0]:
+        fused_stitch[0] = False
+        for _ in range(3):
+            one_step_fused()
+        sep_ms = 0.0
+        for _ in range(args.steps):
+            ms, _, _, _ = one_step_fused()
+            sep_ms += ms
+        fused_stitch[0] = True
+        t = torch.tensor([sep_ms], dtype=torch.float64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sep_ms = float(t.item()) / args.steps
+        dist.barrier()
+    # the round-1 protocol at N = 1: one buffer, the L2 flushed before every call (cross-check of the rotation)
+    flush_ms = None
+    if world == 1:
+        for _ in range(2):
+            one_step_fused("flush")
+        flush_ms = sum(one_step_fused("flush")[0] for _ in range(args.steps)) / args.steps
     # the same fused step with the stitch records through an NCCL all-gather (N > 1 only)
     nccl_ms = None
     nccl_counts = None
@@ -938,6 +994,11 @@ def main():
              "counts_equal": nccl_counts == f_counts,
              "how": "the same fused step with the stitch records exchanged by an NCCL all-gather (torch.distributed) instead "
                     "of the device-side neighbour exchange"},
+            "stitch_separate_launch": None if sep_ms is None else
+            {"value": round(total_text / (sep_ms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(sep_ms, 4),
+             "how": "scan kernel, then k_stitch as a second launch (host time inside the exchange added to the device time)"},
+            "ms_per_step_l2_flushed": None if flush_ms is None else round(flush_ms, 4),
+            "ms_per_step_host_clock": round(host_ms_per_step, 4),
             "stitch_cascades": n_cascades,
             "parallel_parity": parallel,
             "gpu_launches": f_launches,

@@ -16,7 +16,7 @@ import os
 from typing import List, Optional, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librejit_b200.so")
+LIB_PATH = os.environ.get("RJ_LIB") or os.path.join(_HERE, "librejit_b200.so")     # RJ_LIB: tuning builds (scripts/ab_build.sh)
 
 _lib = None
 

@@ -582,7 +582,6 @@ bool EnsureKernelAttributes(DeviceContext* c, std::string* error) {
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmWindow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmGeneric, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
-  RJ_TRY(cudaFuncSetAttribute(k_translate_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTransStage + 32 + kTransMaxBytes)));
   c->attr_done = true;
   return true;
 }
@@ -1820,7 +1819,7 @@ bool ReplaceSetFusable(const std::vector<Program*>& progs, const std::vector<std
   for (size_t i = 0; i < progs.size(); ++i) {
     const PositionNfa& a = progs[i]->automaton().nfa;
     if (a.n_pos != 1 || a.has_anchor || a.min_len != 1 || a.max_len != 1 || a.accept_empty[0]) return false;
-    if (withs[i].size() > 0xFFF0) return false;
+    if (withs[i].size() > kTr2MaxLen) return false;
     bytes += withs[i].size();
   }
   if (bytes > kTransMaxBytes) return false;
@@ -1864,7 +1863,7 @@ int64_t ReplaceAllSetDevice(int device, const std::vector<Program*>& progs, cons
   std::lock_guard<std::mutex> lk(c->mu);
   RJ_TRY_COUNT(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
-  const uint64_t n_tiles = (n + kTransTile - 1) / kTransTile;
+  const uint64_t n_tiles = (n + kTr2Tile - 1) / kTr2Tile;
   if (!c->trans_tab.Reserve(sizeof tab, error) || !c->trans_len.Reserve((n_tiles + 1) * 8, error) ||
       !c->trans_off.Reserve((n_tiles + 1) * 8, error) || !c->trans_counts.Reserve(32 * 8, error)) return -1;
   if (stats) cudaEventRecord(c->ev[0], s);
@@ -1872,10 +1871,14 @@ int64_t ReplaceAllSetDevice(int device, const std::vector<Program*>& progs, cons
   RJ_TRY_COUNT(cudaMemsetAsync(c->trans_counts.p, 0, 32 * 8, s));
   unsigned long long h_counts[32] = {0};
   uint64_t total = 0;
-  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 8));
+  // one warp per 16 KB tile, eight warps per CTA, at most four CTAs per SM (32 warps x four rows in flight)
+  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + kTr2Warps - 1) / kTr2Warps, (uint64_t)c->sm_count * 4));
   if (n_tiles) {
-    k_translate_count<<<blocks, 256, 0, s>>>(d_text, n, c->trans_tab.as<TranslateTable>(), c->trans_len.as<uint64_t>(),
-                                             c->trans_counts.as<unsigned long long>(), n_tiles);
+    const size_t count_smem = ((sizeof(Tr2Tables) + 15) & ~(size_t)15) + (size_t)kTr2Warps * K * 32 * 4;
+    k_translate_count2<<<blocks, kTr2Warps * 32, count_smem, s>>>(d_text, n, c->trans_tab.as<TranslateTable>(), K,
+                                                                  c->trans_len.as<uint64_t>(),
+                                                                  c->trans_counts.as<unsigned long long>(), n_tiles);
+    RJ_TRY_COUNT(cudaGetLastError());
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->trans_len.as<uint64_t>(), c->trans_off.as<uint64_t>(), (int64_t)n_tiles, s);
     if (!c->cub_tmp.Reserve(tmp, error)) return -1;
@@ -1892,13 +1895,9 @@ int64_t ReplaceAllSetDevice(int device, const std::vector<Program*>& progs, cons
   if (!out) return -1;
   bool ok = true;
   if (n_tiles) {
-    const size_t smem = kTransStage + 32 + kTransMaxBytes;
-    ok = EnsureKernelAttributes(c, error);
-    if (ok) {
-      k_translate_write<<<blocks, 256, smem, s>>>(d_text, n, c->trans_tab.as<TranslateTable>(), c->trans_off.as<uint64_t>(),
-                                                  static_cast<uint8_t*>(out), n_tiles);
-      ok = Check(cudaGetLastError(), "k_translate_write", error);
-    }
+    k_translate_write2<<<blocks, kTr2Warps * 32, 0, s>>>(d_text, n, c->trans_tab.as<TranslateTable>(), c->trans_off.as<uint64_t>(),
+                                                         static_cast<uint8_t*>(out), n_tiles);
+    ok = Check(cudaGetLastError(), "k_translate_write2", error);
   }
   if (ok && stats) {
     cudaEventRecord(c->ev[1], s);

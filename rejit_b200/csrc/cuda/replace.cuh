@@ -6,7 +6,7 @@
 //                     memory: the tile is fetched with coalesced 16-byte loads, its output is assembled in
 //                     shared memory and leaves with coalesced 16-byte stores.  Round 1 read and wrote single
 //                     bytes from global memory: 0.2 TB/s.
-//   k_translate_*     a SET of patterns that each match exactly one byte (regex-dna's eleven IUB codes,
+//   k_translate_*2    a SET of patterns that each match exactly one byte (regex-dna's eleven IUB codes,
 //                     /root/reference/sample/regexdna.cc:69-85) is one byte -> string table: one counting pass,
 //                     one prefix sum over the tiles, one writing pass — instead of eleven scan + rebuild passes.
 //                     Sequential ReplaceAll calls and the table give the same text iff no replacement holds a
@@ -124,8 +124,6 @@ k_replace_stage(const uint8_t* __restrict__ text, uint64_t n, const uint64_t* __
 // ===========================================================================
 // byte -> string table (a set of one-byte patterns)
 // ===========================================================================
-constexpr uint32_t kTransTile = 4096;
-constexpr uint32_t kTransStage = 4096 * 8;          // a tile whose output is longer goes straight to global memory
 constexpr uint32_t kTransMaxBytes = 4096;           // all replacement strings together
 constexpr uint8_t kTransNone = 0xFF;
 
@@ -136,92 +134,233 @@ struct TranslateTable {                 // device memory
   uint8_t bytes[kTransMaxBytes];
 };
 
-// pass 1: per tile the number of output bytes, per pattern the number of matches
-__global__ void __launch_bounds__(256)
-k_translate_count(const uint8_t* __restrict__ text, uint64_t n, const TranslateTable* __restrict__ tab,
-                  uint64_t* __restrict__ tile_len, unsigned long long* __restrict__ counts, uint64_t n_tiles) {
-  __shared__ uint16_t s_len[256];
-  __shared__ uint8_t s_pat[256];
-  __shared__ uint32_t s_hist[8][32];
-  __shared__ uint32_t s_sum[8];
-  s_len[threadIdx.x] = tab->len[threadIdx.x];
-  s_pat[threadIdx.x] = tab->pat[threadIdx.x];
-  s_hist[threadIdx.x >> 5][threadIdx.x & 31] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t n16 = (n + 15) & ~15ull;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint64_t at = tile * kTransTile + (uint64_t)threadIdx.x * 16;
-    const uint4 v = at < n16 ? __ldg(reinterpret_cast<const uint4*>(text + at)) : make_uint4(0, 0, 0, 0);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t mine = 0;
-#pragma unroll
-    for (int p = 0; p < 16; ++p) {
-      if (at + p >= n) break;
-      const uint32_t b = (w[p >> 2] >> (8 * (p & 3))) & 0xFFu;
-      mine += s_len[b];
-      const uint32_t j = s_pat[b];
-      if (j != kTransNone) atomicAdd(&s_hist[warp][j & 31], 1u);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(kFullMask, mine, d);
-    if (lane == 0) s_sum[warp] = mine;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint64_t t = 0;
-      for (int q = 0; q < 8; ++q) t += s_sum[q];
-      tile_len[tile] = t;
-    }
-    __syncthreads();
+// ===========================================================================
+// byte -> string table, round 2b: warp-autonomous streaming passes.
+//   The first version worked a 4 KB tile per CTA iteration with one load per thread in flight, two block barriers
+//   per tile, shared-memory atomics per replaced byte and byte-wide stores with four-way bank conflicts for EVERY
+//   byte: 0.5 TB/s of traffic.  Here a WARP owns a 16 KB tile (32 rows of 512 bytes, four rows in flight, no block
+//   barrier after the tables are loaded):
+//   count   one class lookup per byte (0: copied, j + 1: replaced by pattern j); only lanes that hold a replaced
+//           byte look again (lane-private histogram bins in shared memory: no atomics, bank = lane).
+//   write   a row without replaced bytes (the common case) is COPIED: the output offset is not 16-byte aligned in
+//           general, so every lane builds the aligned 16-byte chunk that covers its place from its left
+//           neighbour's bytes and its own (shuffle + byte permute) and the warp stores 512 aligned bytes; the
+//           chunk cut by the row's end waits for the next row.  A row with replaced bytes is assembled in the
+//           warp's staging area and leaves with aligned 16-byte stores.
+// Algorithmic traffic: 2 N read, N' written.
+// ===========================================================================
+constexpr uint32_t kTr2Rows = 32;                                   // rows of 512 bytes per tile
+constexpr uint32_t kTr2Tile = kTr2Rows * 512;                       // 16 KB, one warp
+constexpr uint32_t kTr2Warps = 8;
+constexpr uint32_t kTr2Stage = 2048;                                // output of one row that is assembled in shared memory
+constexpr uint32_t kTr2MaxLen = 4095;                               // longest replacement (16 of them fit 16 bits)
+
+struct Tr2Tables {                      // shared memory, loaded once per CTA
+  uint8_t cls[256];                     // 0: the byte is copied; j + 1: pattern j replaces it
+  uint16_t len[34];                     // [cls]: output bytes (len[0] = 1)
+  uint16_t off[34];                     // [cls]: the replacement starts at bytes[off]
+};
+
+__device__ __forceinline__ void Tr2LoadTables(const TranslateTable* __restrict__ tab, Tr2Tables* t) {
+  for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {
+    const uint8_t pj = tab->pat[b];
+    t->cls[b] = pj == kTransNone ? 0 : (uint8_t)(pj + 1);
+    if (pj != kTransNone) { t->len[pj + 1] = tab->len[b]; t->off[pj + 1] = tab->off[b]; }     // (same value from every byte of the pattern)
   }
-  if (threadIdx.x < 32) {
-    unsigned long long t = 0;
-    for (int q = 0; q < 8; ++q) t += s_hist[q][threadIdx.x];
-    if (t) atomicAdd(&counts[threadIdx.x], t);
+  if (threadIdx.x == 0) { t->len[0] = 1; t->off[0] = 0; }
+}
+
+// class ids of my 16 bytes OR-ed together (0: nothing to replace)
+__device__ __forceinline__ uint32_t Tr2AnySpecial(const uint4& v, const uint8_t* cls) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t any = 0;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) any |= cls[__byte_perm(w[p >> 2], 0u, 0x4440 | (p & 3))];
+  return any;
+}
+
+__global__ void __launch_bounds__(kTr2Warps * 32)
+k_translate_count2(const uint8_t* __restrict__ text, uint64_t n, const TranslateTable* __restrict__ tab, int K,
+                   uint64_t* __restrict__ tile_len, unsigned long long* __restrict__ counts, uint64_t n_tiles) {
+  extern __shared__ __align__(16) uint8_t tr_smem[];
+  Tr2Tables* t = reinterpret_cast<Tr2Tables*>(tr_smem);
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(tr_smem + ((sizeof(Tr2Tables) + 15) & ~15u));      // [warp][K][32 lanes]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Tr2LoadTables(tab, t);
+  for (uint32_t i = threadIdx.x; i < kTr2Warps * (uint32_t)K * 32; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  uint32_t* my_hist = s_hist + (uint32_t)warp * K * 32 + lane;
+  const uint64_t n16 = (n + 15) & ~15ull;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const uint64_t n_warps = (uint64_t)gridDim.x * kTr2Warps;
+  for (uint64_t tile = (uint64_t)blockIdx.x * kTr2Warps + warp; tile < n_tiles; tile += n_warps) {
+    const uint64_t tile_lo = tile * kTr2Tile;
+    const uint64_t mine = tile_lo + (uint64_t)lane * 16;
+    const uint32_t rows = n - tile_lo >= kTr2Tile ? kTr2Rows : (uint32_t)((n - tile_lo + 511) >> 9);
+    const uint32_t rows_ld = mine < n16 ? (uint32_t)(((n16 - mine + 511) >> 9) < kTr2Rows ? ((n16 - mine + 511) >> 9) : kTr2Rows) : 0u;
+    const uint4* src = reinterpret_cast<const uint4*>(text + mine);
+    uint4 v0 = 0 < rows_ld ? __ldg(src) : zero4, v1 = 1 < rows_ld ? __ldg(src + 32) : zero4,
+          v2 = 2 < rows_ld ? __ldg(src + 64) : zero4, v3 = 3 < rows_ld ? __ldg(src + 96) : zero4;
+    uint32_t extra = 0;                                     // output bytes beyond one per input byte (may be "negative")
+    auto row = [&](uint4& v, uint32_t r) {
+      const uint4 cur = v;
+      v = r + 4 < rows_ld ? __ldg(src + (r + 4) * 32) : zero4;
+      if (Tr2AnySpecial(cur, t->cls)) {
+        const uint64_t at = mine + (uint64_t)r * 512;
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const uint32_t c = t->cls[__byte_perm(w[p >> 2], 0u, 0x4440 | (p & 3))];
+          if (c && at + p < n) { extra += (uint32_t)t->len[c] - 1u; my_hist[(c - 1) * 32] += 1; }
+        }
+      }
+    };
+    uint32_t r = 0;
+#pragma unroll 1
+    for (; r + 4 <= rows; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
+    if (r < rows) row(v0, r);
+    if (r + 1 < rows) row(v1, r + 1);
+    if (r + 2 < rows) row(v2, r + 2);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) extra += __shfl_xor_sync(kFullMask, extra, d);
+    if (lane == 0) {
+      const uint64_t in_bytes = n - tile_lo < kTr2Tile ? n - tile_lo : kTr2Tile;
+      tile_len[tile] = in_bytes + (uint64_t)(int64_t)(int32_t)extra;
+    }
+  }
+  __syncwarp();
+  for (int j = 0; j < K; ++j) {
+    uint32_t c = my_hist[j * 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFullMask, c, d);
+    if (lane == 0 && c) atomicAdd(&counts[j], (unsigned long long)c);
   }
 }
 
-// pass 2: tile_off = exclusive prefix sum of tile_len; the tile's output is assembled in shared memory
-__global__ void __launch_bounds__(256)
-k_translate_write(const uint8_t* __restrict__ text, uint64_t n, const TranslateTable* __restrict__ tab,
-                  const uint64_t* __restrict__ tile_off, uint8_t* __restrict__ out, uint64_t n_tiles) {
-  extern __shared__ __align__(16) uint8_t s_dyn[];              // [kTransStage + 32] output, then the table's strings
-  __shared__ uint16_t s_len[256], s_off[256];
-  __shared__ uint32_t s_warp[33];
-  uint8_t* s_out = s_dyn;
-  uint8_t* s_bytes = s_dyn + kTransStage + 32;
-  s_len[threadIdx.x] = tab->len[threadIdx.x];
-  s_off[threadIdx.x] = tab->off[threadIdx.x];
+// the aligned 16-byte chunk that begins `o` bytes (1..15) into the 32-byte window p:v
+__device__ __forceinline__ uint4 Tr2Window(const uint4& p, const uint4& v, uint32_t o) {
+  const uint32_t w[8] = {p.x, p.y, p.z, p.w, v.x, v.y, v.z, v.w};
+  const bool s2 = (o & 8u) != 0, s1 = (o & 4u) != 0;
+  uint32_t a[6], b[5];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) a[i] = s2 ? w[i + 2] : w[i];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) b[i] = s1 ? a[i + 1] : a[i];
+  const uint32_t sel = 0x3210u + 0x1111u * (o & 3u);
+  return make_uint4(__byte_perm(b[0], b[1], sel), __byte_perm(b[1], b[2], sel), __byte_perm(b[2], b[3], sel),
+                    __byte_perm(b[3], b[4], sel));
+}
+
+__global__ void __launch_bounds__(kTr2Warps * 32)
+k_translate_write2(const uint8_t* __restrict__ text, uint64_t n, const TranslateTable* __restrict__ tab,
+                   const uint64_t* __restrict__ tile_off, uint8_t* __restrict__ out, uint64_t n_tiles) {
+  __shared__ Tr2Tables s_t;
+  __shared__ __align__(16) uint8_t s_bytes[kTransMaxBytes];
+  __shared__ __align__(16) uint8_t s_stage_all[kTr2Warps][kTr2Stage + 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Tr2LoadTables(tab, &s_t);
   for (uint32_t i = threadIdx.x; i < kTransMaxBytes; i += blockDim.x) s_bytes[i] = tab->bytes[i];
   __syncthreads();
+  const Tr2Tables* t = &s_t;
+  uint8_t* stage = s_stage_all[warp];
   const uint64_t n16 = (n + 15) & ~15ull;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint64_t at = tile * kTransTile + (uint64_t)threadIdx.x * 16;
-    const uint4 v = at < n16 ? __ldg(reinterpret_cast<const uint4*>(text + at)) : make_uint4(0, 0, 0, 0);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t mine = 0;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const uint64_t n_warps = (uint64_t)gridDim.x * kTr2Warps;
+  for (uint64_t tile = (uint64_t)blockIdx.x * kTr2Warps + warp; tile < n_tiles; tile += n_warps) {
+    const uint64_t tile_lo = tile * kTr2Tile;
+    const uint64_t mine = tile_lo + (uint64_t)lane * 16;
+    const uint32_t rows = n - tile_lo >= kTr2Tile ? kTr2Rows : (uint32_t)((n - tile_lo + 511) >> 9);
+    const uint32_t rows_ld = mine < n16 ? (uint32_t)(((n16 - mine + 511) >> 9) < kTr2Rows ? ((n16 - mine + 511) >> 9) : kTr2Rows) : 0u;
+    const uint4* src = reinterpret_cast<const uint4*>(text + mine);
+    uint4 v0 = 0 < rows_ld ? __ldg(src) : zero4, v1 = 1 < rows_ld ? __ldg(src + 32) : zero4,
+          v2 = 2 < rows_ld ? __ldg(src + 64) : zero4, v3 = 3 < rows_ld ? __ldg(src + 96) : zero4;
+    uint64_t pos = tile_off[tile];                          // where the next row's output begins (uniform)
+    bool pend = false;                                      // the last sh bytes of the row before wait in `last` (lane 31)
+    uint4 last = zero4;
+    auto flush = [&]() {
+      if (pend) {
+        const uint32_t sh = (uint32_t)pos & 15u;            // (pos moved by whole rows since the run began)
+        if (lane == 31) {
+          const uint32_t w[4] = {last.x, last.y, last.z, last.w};
+          for (uint32_t k = 16 - sh; k < 16; ++k) out[pos - 16 + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+        }
+        pend = false;
+      }
+    };
+    auto row = [&](uint4& v, uint32_t r) {
+      const uint4 cur = v;
+      v = r + 4 < rows_ld ? __ldg(src + (r + 4) * 32) : zero4;
+      const uint64_t at = mine + (uint64_t)r * 512;
+      const bool whole = tile_lo + (uint64_t)(r + 1) * 512 <= n;                           // every byte of the row is text
+      const uint32_t any = Tr2AnySpecial(cur, t->cls);
+      if (whole && !__any_sync(kFullMask, any != 0)) {
+        // ---- copy -----------------------------------------------------------------------------------
+        const uint32_t sh = (uint32_t)pos & 15u;
+        if (sh == 0) {
+          *reinterpret_cast<uint4*>(out + pos + (uint64_t)lane * 16) = cur;
+        } else {
+          uint4 give = lane == 31 ? last : cur, p;
+          const int from = (lane + 31) & 31;
+          p.x = __shfl_sync(kFullMask, give.x, from); p.y = __shfl_sync(kFullMask, give.y, from);
+          p.z = __shfl_sync(kFullMask, give.z, from); p.w = __shfl_sync(kFullMask, give.w, from);
+          if (lane > 0 || pend) {
+            *reinterpret_cast<uint4*>(out + (pos - sh) + (uint64_t)lane * 16) = Tr2Window(p, cur, 16 - sh);
+          } else {
+            const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+            for (uint32_t k = 0; k < 16 - sh; ++k) out[pos + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+          }
+          pend = true;
+          last = cur;
+        }
+        pos += 512;
+        return;
+      }
+      // ---- a row with replaced bytes (or the text's last row): assembled in shared memory ----------------
+      flush();
+      const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+      uint32_t mylen = 0;
 #pragma unroll
-    for (int p = 0; p < 16; ++p)
-      if (at + p < n) mine += s_len[(w[p >> 2] >> (8 * (p & 3))) & 0xFFu];
-    uint32_t total;
-    const uint32_t before = BlockExclusiveSum(mine, &total, s_warp);
-    const uint64_t out_base = tile_off[tile];
-    const bool staged = total <= kTransStage;
-    const uint32_t align = (uint32_t)(reinterpret_cast<uintptr_t>(out + out_base) & 15u);
-    uint8_t* dst = staged ? s_out + align + before : out + out_base + before;
+      for (int p = 0; p < 16; ++p)
+        if (at + p < n) mylen += t->len[t->cls[__byte_perm(w[p >> 2], 0u, 0x4440 | (p & 3))]];
+      const uint32_t incl = WarpInclusiveScan(mylen);
+      const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+      const uint32_t a = (uint32_t)pos & 15u;
+      const bool staged = total <= kTr2Stage;
+      uint8_t* dst = staged ? stage + a + (incl - mylen) : out + pos + (incl - mylen);
 #pragma unroll 1
-    for (int p = 0; p < 16; ++p) {
-      if (at + p >= n) break;
-      const uint32_t b = (w[p >> 2] >> (8 * (p & 3))) & 0xFFu;
-      const uint32_t l = s_len[b];
-      if (l == 1 && s_off[b] == 0xFFFFu) { *dst++ = (uint8_t)b; continue; }
-      const uint8_t* src = s_bytes + s_off[b];
-      for (uint32_t k = 0; k < l; ++k) dst[k] = src[k];
-      dst += l;
-    }
-    __syncthreads();
-    if (staged) StageCopyOut(out + out_base, s_out, total);
-    __syncthreads();
+      for (int p = 0; p < 16; ++p) {
+        if (at + p >= n) break;
+        const uint32_t b = (w[p >> 2] >> (8 * (p & 3))) & 0xFFu;
+        const uint32_t c = t->cls[b];
+        if (!c) { *dst++ = (uint8_t)b; continue; }
+        const uint32_t l = t->len[c];
+        const uint8_t* from = s_bytes + t->off[c];
+        for (uint32_t k = 0; k < l; ++k) dst[k] = from[k];
+        dst += l;
+      }
+      __syncwarp();
+      if (staged) {
+        uint8_t* o = out + pos;
+        uint32_t head = (16u - a) & 15u;
+        if (head > total) head = total;
+        if ((uint32_t)lane < head) o[lane] = stage[a + lane];
+        const uint32_t body = (total - head) >> 4;
+        const uint4* sv = reinterpret_cast<const uint4*>(stage + a + head);
+        uint4* dv = reinterpret_cast<uint4*>(o + head);
+        for (uint32_t i = lane; i < body; i += 32) dv[i] = sv[i];
+        const uint32_t done = head + (body << 4);
+        if ((uint32_t)lane < total - done) o[done + lane] = stage[a + done + lane];
+        __syncwarp();
+      }
+      pos += total;
+    };
+    uint32_t r = 0;
+#pragma unroll 1
+    for (; r + 4 <= rows; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
+    if (r < rows) row(v0, r);
+    if (r + 1 < rows) row(v1, r + 1);
+    if (r + 2 < rows) row(v2, r + 2);
+    flush();
   }
 }
 

@@ -46,7 +46,13 @@ namespace rejit_b200 {
 
 constexpr uint32_t kEmWarps = 8;
 constexpr uint32_t kEmThreads = kEmWarps * 32;
-constexpr uint32_t kEmRows = 64;                              // rows of 512 bytes per tile
+#ifndef RJ_EM_ROWS
+#define RJ_EM_ROWS 64
+#endif
+#ifndef RJ_EM_SLEEP
+#define RJ_EM_SLEEP 64
+#endif
+constexpr uint32_t kEmRows = RJ_EM_ROWS;                      // rows of 512 bytes per tile
 constexpr uint32_t kEmTileBytes = kEmRows * 512;              // 32 KB, one warp
 constexpr uint32_t kEmEntCap = 512;                           // survivors (16-byte groups) a warp collects before it evaluates them
 constexpr uint32_t kEmEntFlush = kEmEntCap - 128;             // ... checked every four rows (at most 128 more)
@@ -161,14 +167,15 @@ __device__ __forceinline__ uint32_t EmLitFlags(const uint4& v, uint32_t pw, uint
 template <bool kFull4>
 __device__ __forceinline__ bool EmLitAny(const uint4& v, uint32_t pw, uint32_t p4, uint32_t pmask) {
   const uint32_t w[5] = {pw, v.x, v.y, v.z, v.w};
-  bool any = false;
+  // four independent chains of compares (one chain of sixteen dependent predicate updates stalled every row)
+  bool any[4] = {false, false, false, false};
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int o = j + 1;
     const uint32_t x = (o & 3) ? __funnelshift_r(w[o >> 2], w[(o >> 2) + 1], 8 * (o & 3)) : w[o >> 2];
-    any |= kFull4 ? (x == p4) : (((x ^ p4) & pmask) == 0);
+    any[j & 3] |= kFull4 ? (x == p4) : (((x ^ p4) & pmask) == 0);
   }
-  return any;
+  return (any[0] | any[1]) | (any[2] | any[3]);
 }
 
 // generic: flag bits transposed (EmEqT), 28 bits
@@ -371,8 +378,12 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint6
           has = (b.y >> 30) & 1u;
           break;
         }
+#ifdef RJ_EM_SPIN
         const long long t0 = clock64();
         while (clock64() - t0 < 64) {}
+#else
+        __nanosleep(RJ_EM_SLEEP);                  // (a clock-counting spin took issue slots from the streaming warps)
+#endif
       }
     } else if (idx == -1) {                        // before the first tile: nothing counted, the call's carry
       state = 2;
@@ -419,7 +430,11 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
     const uint32_t W = (uint32_t)nfa.words, P = (uint32_t)(nfa.n_pos > 0 ? nfa.n_pos : 1);
     const uint32_t words = 256 * W + 4 * W + 4 * P * W + 4 * W + W;             // byte_mask, first, follow, accept, chain
     const uint32_t bytes = words * 4 + (kMode == kEmWindow ? 1024u : 0u);       // + start_ok
+#ifdef RJ_EM_NO_SMEM_TABLES
+    if (false) {
+#else
     if (bytes <= kEmTableBytes) {
+#endif
       uint32_t* tab = reinterpret_cast<uint32_t*>(em_smem + kEmWarps * (kEmEntCap * 4 + kEmCandCap * 4));
       uint32_t* s_bm = tab, *s_first = s_bm + 256 * W, *s_follow = s_first + 4 * W, *s_accept = s_follow + 4 * P * W,
                 *s_chain = s_accept + 4 * W;
@@ -460,8 +475,12 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
     if (live) {
       // ---- stream the rows; evaluate the survivors whenever their list fills up, and at the end --------------
       uint32_t n_ent = 0;
-      uint4 v0 = EmLoadRow(text, n16, mine), v1 = EmLoadRow(text, n16, mine + 512), v2 = EmLoadRow(text, n16, mine + 1024),
-            v3 = EmLoadRow(text, n16, mine + 1536);
+      // rows [0, rows_ld) have my 16 bytes inside the (padded) text: one compare per load instead of a 64-bit bound
+      const uint32_t rows_ld = mine < n16 ? (uint32_t)(((n16 - mine + 511) >> 9) < kEmRows ? ((n16 - mine + 511) >> 9) : kEmRows) : 0u;
+      const uint4* src = reinterpret_cast<const uint4*>(text + mine);
+      const uint4 zero4 = make_uint4(0, 0, 0, 0);
+      uint4 v0 = 0 < rows_ld ? __ldg(src) : zero4, v1 = 1 < rows_ld ? __ldg(src + 32) : zero4,
+            v2 = 2 < rows_ld ? __ldg(src + 64) : zero4, v3 = 3 < rows_ld ? __ldg(src + 96) : zero4;
       // what precedes the tile: its last word (literal windows) / whether its last byte is a line break
       uint32_t tail = 0;
       if (kMode == kEmGeneric) {
@@ -475,7 +494,7 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
       if (tile_lo + kEmTileBytes > scan_end) rows = scan_end > tile_lo ? (uint32_t)((scan_end - tile_lo + 511) >> 9) : 0u;
       auto row = [&](uint4& v, uint32_t r) {
         const uint4 cur = v;
-        v = r + 4 < rows ? EmLoadRow(text, n16, mine + (uint64_t)(r + 4) * 512) : make_uint4(0, 0, 0, 0);
+        v = r + 4 < rows_ld ? __ldg(src + (r + 4) * 32) : zero4;
         uint32_t f16 = 0;
         if (kMode == kEmGeneric) {
           uint32_t prev = 0;
@@ -578,12 +597,20 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
     uint4* rec = em.records + 2 * t;
     const uint32_t tag = (em.seq & 0x3FFFFFFFu) << 2;
     if (lane == 0) EmPublish(rec, tag | 1u, cnt, cnt != 0, mine_out);
-    uint64_t before;
+    // A tile without matches needs nothing from its predecessors — no place for matches, no seam — and its own record
+    // already says all there is to say about it: it does not look back at all.  Every 32nd tile does, so that a
+    // tile with matches finds an inclusive record within a step or two (a look-back blocks the warp with no loads in
+    // flight: on a text without hits it was a quarter of the kernel's time).
+    uint64_t before = 0;
     EmState arriving;
-    EmLookBack(em, t, &before, &arriving);
-    if (cnt && !EmTakes(arriving, tile_base + EmRel(first), EmLen(first))) flags |= kFinOverlap;   // the chain from the left reaches in
+    arriving.cur = 0; arriving.ne = 0;
+    const bool look = cnt != 0 || (t & 31u) == 31u || t + 1 == em.ntiles;
+    if (look) {
+      EmLookBack(em, t, &before, &arriving);
+      if (cnt && !EmTakes(arriving, tile_base + EmRel(first), EmLen(first))) flags |= kFinOverlap;   // the chain from the left reaches in
+    }
     if (lane == 0) {
-      EmPublish(rec, tag | 2u, before + cnt, true, cnt ? mine_out : arriving);
+      if (look) EmPublish(rec, tag | 2u, before + cnt, true, cnt ? mine_out : arriving);
       if (flags) atomicOr(&em.sync[2], flags);
       if (t + 1 == em.ntiles) {
         const EmState fin = cnt ? mine_out : arriving;
