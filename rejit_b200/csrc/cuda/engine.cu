@@ -1432,7 +1432,7 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
       const uint64_t rows = row_hi - row_lo;
       // one CTA per SM (cooperative: every CTA waits for the records of the CTAs before it); a warp owns a
       // contiguous run of rows of any length
-      const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 31) / 32, (uint64_t)c->sm_count));
+      const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 31) / 32, std::min<uint64_t>((uint64_t)c->sm_count, 160)));
       const size_t kmer_smem = kKmerSmemFixed;
       const uint64_t rows_per_warp = (rows + (uint64_t)blocks * kKmerWarps - 1) / ((uint64_t)blocks * kKmerWarps);
       const uint64_t rows_per_cta = rows_per_warp * kKmerWarps;

@@ -1436,7 +1436,6 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
   uint32_t w_load1 = w_row1;
   if (w_row1 > w_row0 && cta_base + ((uint64_t)(w_row1 - 1) << 9) + (uint64_t)lane * 16 >= n16) w_load1 = w_row1 - 1;
   const uint32_t fm = km.field_mask, mult = km.mult;
-  const uint32_t bm_base = SmemAddr(s_bitmap);
   const uint4* src = reinterpret_cast<const uint4*>(text + cta_base + ((uint64_t)w_row0 << 9)) + lane;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   // the 16 bytes before my warp's first row (lane 31's codes of "the row before"), then four rows in flight;
@@ -1508,7 +1507,7 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
       // bits [16 + 2x, ...) of (Q:P): 7 + R codes from bit 2 on = the ends after letters x .. x+R-1
       const int s0 = 16 + 2 * KmerTestX(t);
       const uint32_t w = s0 < 32 ? __funnelshift_r(P, Q, s0) : (Q >> (s0 - 32));
-      const uint32_t word = Lds32(bm_base + (w & ((4u << kKmerWordBits) - 4u)));
+      const uint32_t word = *reinterpret_cast<const uint32_t*>(smem_raw + (w & ((4u << kKmerWordBits) - 4u)));   // (the bitmap is first)
       acc = __funnelshift_l(__funnelshift_l(0u, word, w >> (kKmerWordBits + 2)), acc, 1);   // bit kKmerTests-1-t: lookup t
     }
     // a row with hits (about one in four on regex-dna): one entry per lane with a hit, in lane = position order
@@ -1658,56 +1657,105 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
       const unsigned long long f64 = total ? cta_base + cta_first : 0ull, l64 = total ? cta_base + cta_last : 0ull;
       s_cfirst[j] = f64;
       s_clast[j] = l64;
+      // every flag this CTA can raise is known now (the seams BETWEEN CTAs are checked by the top CTA, which reads
+      // every record anyway): it travels in the record, nothing is left to say after the exchange
+      const unsigned int fl = *s_flags | (any_bad ? kFinOverlap : 0u);
       if (any_bad) atomicOr(s_flags, kFinOverlap);
       volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.xchg + (size_t)blockIdx.x * 32 + j);
       asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)f64),
                    "r"((unsigned int)(f64 >> 32)), "r"(total), "r"(run.seq) : "memory");
       asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 1), "r"((unsigned int)l64),
-                   "r"((unsigned int)(l64 >> 32)), "r"(0u), "r"(run.seq) : "memory");
+                   "r"((unsigned int)(l64 >> 32)), "r"(fl), "r"(run.seq) : "memory");
     }
   }
   // nobody polls before this CTA's own records are out: warps spinning on system-scope loads keep the
   // load/store queue full and starved the publishing warps of their shared-memory and shuffle slots
   __syncthreads();
   // ---- exchange: the CTAs before me.  Warp w reads CTA w, w + 32, ... (lane j = member j), five CTAs' records
-  // in flight at once: matches before me, and the last end before me (for the seam between CTAs).
-  for (uint32_t c0 = warp; c0 < blockIdx.x; c0 += 160) {
-    uint4 a[5], b[5];
-    unsigned pending = 0;
-    uint32_t sum = 0;
-    unsigned long long prev_last = 0;
+  // in flight at once: the number of matches before me.  The CTA with the highest index (the "top" CTA) also keeps
+  // every record in shared memory — the bitmap's space is free now — for the seams and the report.
+  static_assert(kKmerBitmapBytes >= 96 * 1024 + 160 * 32 * 4 && 160 * 32 * 16 <= 96 * 1024, "the top CTA's record copy lives in the bitmap's space");
+  const bool top = blockIdx.x + 1 == gridDim.x;              // (the host launches at most 160 CTAs)
+  uint4* s_rec = reinterpret_cast<uint4*>(smem_raw);                 // [CTA][32]: {first end lo, hi, last end lo, hi}, top CTA only
+  uint32_t* s_rcnt = reinterpret_cast<uint32_t*>(smem_raw + 96 * 1024);   // [CTA][32]: matches
+  {
+    unsigned int seen_flags = 0;
+    for (uint32_t c0 = warp; c0 < blockIdx.x; c0 += 160) {
+      uint4 a[5], b[5];
+      unsigned pending = 0;
+      uint32_t sum = 0;
 #pragma unroll
-    for (int u = 0; u < 5; ++u) {
-      a[u] = b[u] = zero4;
-      if (c0 + 32 * u < blockIdx.x && lane < K) pending |= 1u << u;
+      for (int u = 0; u < 5; ++u) {
+        a[u] = b[u] = zero4;
+        if (c0 + 32 * u < blockIdx.x && lane < K) pending |= 1u << u;
+      }
+      while (pending) {
+#pragma unroll
+        for (int u = 0; u < 5; ++u)
+          if ((pending >> u) & 1u) {
+            const volatile uint4* p = reinterpret_cast<const volatile uint4*>(run.xchg + (size_t)(c0 + 32 * u) * 32 + lane);
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w) : "l"(p) : "memory");
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b[u].x), "=r"(b[u].y), "=r"(b[u].z), "=r"(b[u].w) : "l"(p + 1) : "memory");
+          }
+#pragma unroll
+        for (int u = 0; u < 5; ++u)
+          if (((pending >> u) & 1u) && a[u].w == run.seq && b[u].w == run.seq) {
+            pending &= ~(1u << u);
+            sum += a[u].z;
+            seen_flags |= b[u].z;
+            if (top) {
+              s_rec[(c0 + 32 * u) * 32 + lane] = make_uint4(a[u].x, a[u].y, b[u].x, b[u].y);
+              s_rcnt[(c0 + 32 * u) * 32 + lane] = a[u].z;
+            }
+          }
+      }
+      if (sum) atomicAdd(&s_base[lane], sum);
     }
-    while (pending) {
-#pragma unroll
-      for (int u = 0; u < 5; ++u)
-        if ((pending >> u) & 1u) {
-          const volatile uint4* p = reinterpret_cast<const volatile uint4*>(run.xchg + (size_t)(c0 + 32 * u) * 32 + lane);
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w) : "l"(p) : "memory");
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b[u].x), "=r"(b[u].y), "=r"(b[u].z), "=r"(b[u].w) : "l"(p + 1) : "memory");
-        }
-#pragma unroll
-      for (int u = 0; u < 5; ++u)
-        if (((pending >> u) & 1u) && a[u].w == run.seq && b[u].w == run.seq) {
-          pending &= ~(1u << u);
-          sum += a[u].z;
-          const unsigned long long l64 = (unsigned long long)b[u].y << 32 | b[u].x;
-          if (a[u].z && l64 > prev_last) prev_last = l64;
-        }
+    if (top) {
+      seen_flags = __reduce_or_sync(kFullMask, seen_flags);
+      if (seen_flags && lane == 0) atomicOr(s_flags, seen_flags);
     }
-    if (sum) atomicAdd(&s_base[lane], sum);
-    if (prev_last) atomicMax(&s_prevlast[lane], prev_last);
   }
   __syncthreads();
-  // the seam between my CTA and the ones before it
-  if (threadIdx.x < K) {
-    const int j = threadIdx.x;
-    if (s_count[j] && s_prevlast[j] && s_prevlast[j] + s_mlen[j] > s_cfirst[j]) atomicOr(s_flags, kFinOverlap);
+  // ---- the top CTA: the seams between the CTAs (warp j = member j, 32 CTAs per step, in order), then the report ----
+  if (top) {
+    if (warp < K) {
+      const int j = warp;
+      const unsigned long long L = s_mlen[j];
+      unsigned long long carry = 0;                         // last end of member j so far (0: none)
+      bool bad = false;
+      for (uint32_t cb = 0; cb < gridDim.x; cb += 32) {
+        const uint32_t cc = cb + lane;
+        unsigned long long fe = 0, le = 0;
+        uint32_t cnt = 0;
+        if (cc < blockIdx.x) {
+          const uint4 r = s_rec[cc * 32 + j];
+          cnt = s_rcnt[cc * 32 + j];
+          fe = (unsigned long long)r.y << 32 | r.x;
+          le = (unsigned long long)r.w << 32 | r.z;
+        } else if (cc == blockIdx.x) {
+          cnt = s_count[j]; fe = s_cfirst[j]; le = s_clast[j];
+        }
+        unsigned long long run_max = cnt ? le : 0ull;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned long long o = __shfl_up_sync(kFullMask, run_max, d);
+          if (lane >= d && o > run_max) run_max = o;
+        }
+        unsigned long long before = __shfl_up_sync(kFullMask, run_max, 1);
+        if (lane == 0 || before < carry) before = carry;
+        if (cnt && before && before + L > fe) bad = true;
+        const unsigned long long last = __shfl_sync(kFullMask, run_max, 31);
+        if (last > carry) carry = last;
+      }
+      bad = __any_sync(kFullMask, bad);
+      if (lane == 0) {
+        s_prevlast[j] = carry;                              // (here: the last end of member j in the whole call)
+        if (bad) atomicOr(s_flags, kFinOverlap);
+      }
+    }
+    // (a named barrier for the K + 1 warps involved would do; the other warps only have their matches left to write)
   }
-
   // ---- my warp's matches, at their final place: first the ones that moved to the staging area, then my shared list
   {
     uint32_t done = 0;                                      // member `lane`: matches of my warp already written
@@ -1734,35 +1782,26 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
       }
     }
   }
-  __syncthreads();
-  // ---- the CTA that finishes last reports (and leaves the two sync words zero for the next call) ----------
-  if (warp == 0) {
-    const bool top = blockIdx.x + 1 == gridDim.x;
-    if (top && lane < K) {
-      // totals and last ends are known to the CTA with the highest index
-      run.gfinal[2 * lane] = (unsigned long long)s_base[lane] + s_count[lane];
-      run.gfinal[2 * lane + 1] = s_count[lane] ? s_clast[lane] : s_prevlast[lane];
-    }
-    __threadfence();
-    __syncwarp();
-    int is_last = 0;
-    if (lane == 0) {
-      const unsigned int fl = *s_flags;
-      if (fl) atomicOr(&run.gsync[0], fl);
-      __threadfence();
-      is_last = atomicAdd(&run.gsync[1], 1u) + 1u == gridDim.x ? 1 : 0;
-    }
-    is_last = __shfl_sync(kFullMask, is_last, 0);
-    if (is_last) {
-      __threadfence();
-      const unsigned int flg = __ldcg(&run.gsync[0]);
+  // ---- the top CTA reports: totals, last ends and flags are all known to it (its matches are on their way; the
+  // host reads the pairs after the kernel has ended) ------------------------------------------------------------
+  if (top) {
+    __syncthreads();                                        // the seams above
+    if (warp == 0) {
+      const unsigned int flg = *s_flags;
+      unsigned long long total = 0, le = 0;
+      if (lane < K) {
+        total = (unsigned long long)s_base[lane] + s_count[lane];
+        le = s_prevlast[lane];
+        run.gfinal[2 * lane] = total;
+        run.gfinal[2 * lane + 1] = le;
+      }
+      if (lane == 0) run.gfinal[64] = flg;
       if (run.stitch.enabled) {
         // scan + stitch in one kernel: the chain states leave for the right neighbour's HBM now; a call that the
         // host will repeat (flags, output too small) is sent as invalid and sent again by the repeat
         unsigned long long cur = 0;
         uint32_t has = 0, invalid = flg ? 1u : 0u;
         if (lane < K) {
-          const unsigned long long total = __ldcg(&run.gfinal[2 * lane]), le = __ldcg(&run.gfinal[2 * lane + 1]);
           if (total > run.out_cap) invalid = 1;
           if (total) { cur = le + run.base_offset; has = 1; }
         }
@@ -1770,7 +1809,6 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
         StitchExchangeWarp(run.stitch, K, cur, has, has, invalid);
       }
       if (lane < K) {
-        const unsigned long long total = __ldcg(&run.gfinal[2 * lane]), le = __ldcg(&run.gfinal[2 * lane + 1]);
         volatile uint4* dst = reinterpret_cast<volatile uint4*>(run.host_records + lane);
         asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((unsigned int)total),
                      "r"((unsigned int)(total >> 32)), "r"(flg), "r"(run.seq) : "memory");
@@ -1779,8 +1817,6 @@ k_set_kmer(const uint8_t* __restrict__ text, uint64_t n, int n_patterns, KmerTab
         asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"((unsigned int)le),
                      "r"((unsigned int)(le >> 32)), "r"(0u), "r"(run.seq) : "memory");
       }
-      __syncwarp();
-      if (lane == 0) { run.gfinal[64] = flg; run.gsync[0] = 0; run.gsync[1] = 0; }
     }
   }
 #ifdef RJ_KMER_PROBE

@@ -49,9 +49,6 @@ constexpr uint32_t kEmThreads = kEmWarps * 32;
 #ifndef RJ_EM_ROWS
 #define RJ_EM_ROWS 64
 #endif
-#ifndef RJ_EM_SLEEP
-#define RJ_EM_SLEEP 64
-#endif
 constexpr uint32_t kEmRows = RJ_EM_ROWS;                      // rows of 512 bytes per tile
 constexpr uint32_t kEmTileBytes = kEmRows * 512;              // 32 KB, one warp
 constexpr uint32_t kEmEntCap = 512;                           // survivors (16-byte groups) a warp collects before it evaluates them
@@ -63,8 +60,9 @@ constexpr uint32_t kEmDropped = 0xFFFFu;                      // length field of
 constexpr uint32_t kEmPending = 0xFFFEu;                      // length field of a start that has not been evaluated yet
 constexpr unsigned int kFinLastEmpty = 8u;                    // FinRecord.flags: the last match is empty
 constexpr unsigned int kFinStuck = 16u;                       // a look-back gave up waiting (never expected)
-constexpr uint32_t kEmTableBytes = 6144;                      // the pattern's NFA tables, when they fit (else they stay in global memory)
-constexpr size_t kEmSmemBytes = kEmWarps * (kEmEntCap * 4 + kEmCandCap * 4) + kEmTableBytes;
+// (the pattern's NFA tables stay in global memory: a copy in shared memory made the window / generic kernels slower,
+// with and without hits — the rewritten table pointers cost registers in the streaming loop; A/B in profiles/r2j_*)
+constexpr size_t kEmSmemBytes = kEmWarps * (kEmEntCap * 4 + kEmCandCap * 4);
 
 // a candidate in shared memory: begin - tile_base in the low half, length in the high half
 __device__ __forceinline__ uint32_t EmCand(uint32_t rel, uint32_t len) { return rel | (len << 16); }
@@ -143,6 +141,24 @@ __device__ __forceinline__ uint32_t EmKeepBelowT(uint32_t t, uint32_t limit) {
   return t & keep;
 }
 
+// the streaming load of a row: read once, must not push the pattern's tables (and the bytes the NFA runs re-read) out of L1
+__device__ __forceinline__ uint4 EmLoadStream(const uint4* p) {
+#if defined(RJ_EM_LDG)
+  return __ldg(p);
+#else
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#endif
+}
+// a hint: bring [p, p + bytes) into L2 (one bulk prefetch, no destination, no barrier) so that the loads that follow a few
+// rows later wait for an L2 hit instead of an HBM access; `bytes` a multiple of 16
+__device__ __forceinline__ void EmPrefetchL2(const uint8_t* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+#ifndef RJ_EM_PF_ROWS
+#define RJ_EM_PF_ROWS 0            // rows the L2 prefetch runs ahead of the row being looked at (0: off)
+#endif
 __device__ __forceinline__ uint4 EmLoadRow(const uint8_t* __restrict__ text, uint64_t n16, uint64_t at) {
   return at < n16 ? __ldg(reinterpret_cast<const uint4*>(text + at)) : make_uint4(0, 0, 0, 0);
 }
@@ -378,12 +394,10 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint6
           has = (b.y >> 30) & 1u;
           break;
         }
-#ifdef RJ_EM_SPIN
+        // (a short clock-counting spin: __nanosleep(64) here made the chain of look-backs 20-60 % slower on texts
+        // with matches, measured — the wake-up granularity is far above the L2 round trip the poll waits for)
         const long long t0 = clock64();
         while (clock64() - t0 < 64) {}
-#else
-        __nanosleep(RJ_EM_SLEEP);                  // (a clock-counting spin took issue slots from the streaming warps)
-#endif
       }
     } else if (idx == -1) {                        // before the first tile: nothing counted, the call's carry
       state = 2;
@@ -423,32 +437,6 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
   extern __shared__ __align__(16) uint8_t em_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  if (kMode != kEmLiteral) {
-    // The NFA tables go to shared memory when they fit (one- and two-word patterns do): with 200 KB of shared
-    // memory per SM in use the L1 is 30 KB under 32 streaming warps, and every table lookup of an NFA run was an
-    // L2 round trip.  The pointers in `nfa` are generic, so the runs do not care where the tables live.
-    const uint32_t W = (uint32_t)nfa.words, P = (uint32_t)(nfa.n_pos > 0 ? nfa.n_pos : 1);
-    const uint32_t words = 256 * W + 4 * W + 4 * P * W + 4 * W + W;             // byte_mask, first, follow, accept, chain
-    const uint32_t bytes = words * 4 + (kMode == kEmWindow ? 1024u : 0u);       // + start_ok
-#ifdef RJ_EM_NO_SMEM_TABLES
-    if (false) {
-#else
-    if (bytes <= kEmTableBytes) {
-#endif
-      uint32_t* tab = reinterpret_cast<uint32_t*>(em_smem + kEmWarps * (kEmEntCap * 4 + kEmCandCap * 4));
-      uint32_t* s_bm = tab, *s_first = s_bm + 256 * W, *s_follow = s_first + 4 * W, *s_accept = s_follow + 4 * P * W,
-                *s_chain = s_accept + 4 * W;
-      uint8_t* s_ok = reinterpret_cast<uint8_t*>(s_chain + W);
-      for (uint32_t i = threadIdx.x; i < 256 * W; i += kEmThreads) s_bm[i] = nfa.byte_mask[i];
-      for (uint32_t i = threadIdx.x; i < 4 * W; i += kEmThreads) { s_first[i] = nfa.first[i]; s_accept[i] = nfa.accept[i]; }
-      for (uint32_t i = threadIdx.x; i < 4 * P * W; i += kEmThreads) s_follow[i] = nfa.follow[i];
-      for (uint32_t i = threadIdx.x; i < W; i += kEmThreads) s_chain[i] = nfa.chain[i];
-      if (kMode == kEmWindow) for (uint32_t i = threadIdx.x; i < 1024; i += kEmThreads) s_ok[i] = nfa.start_ok[i];
-      __syncthreads();
-      nfa.byte_mask = s_bm; nfa.first = s_first; nfa.follow = s_follow; nfa.accept = s_accept; nfa.chain = s_chain;
-      if (kMode == kEmWindow) nfa.start_ok = s_ok;
-    }
-  }
   uint32_t* my_ent = reinterpret_cast<uint32_t*>(em_smem) + warp * kEmEntCap;
   uint32_t* my_cand = reinterpret_cast<uint32_t*>(em_smem + kEmWarps * kEmEntCap * 4) + warp * kEmCandCap;
   uint32_t* my_hits = my_cand + kEmWinCandCap;                                          // window mode: the upper half
@@ -479,8 +467,8 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
       const uint32_t rows_ld = mine < n16 ? (uint32_t)(((n16 - mine + 511) >> 9) < kEmRows ? ((n16 - mine + 511) >> 9) : kEmRows) : 0u;
       const uint4* src = reinterpret_cast<const uint4*>(text + mine);
       const uint4 zero4 = make_uint4(0, 0, 0, 0);
-      uint4 v0 = 0 < rows_ld ? __ldg(src) : zero4, v1 = 1 < rows_ld ? __ldg(src + 32) : zero4,
-            v2 = 2 < rows_ld ? __ldg(src + 64) : zero4, v3 = 3 < rows_ld ? __ldg(src + 96) : zero4;
+      uint4 v0 = 0 < rows_ld ? EmLoadStream(src) : zero4, v1 = 1 < rows_ld ? EmLoadStream(src + 32) : zero4,
+            v2 = 2 < rows_ld ? EmLoadStream(src + 64) : zero4, v3 = 3 < rows_ld ? EmLoadStream(src + 96) : zero4;
       // what precedes the tile: its last word (literal windows) / whether its last byte is a line break
       uint32_t tail = 0;
       if (kMode == kEmGeneric) {
@@ -494,7 +482,7 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
       if (tile_lo + kEmTileBytes > scan_end) rows = scan_end > tile_lo ? (uint32_t)((scan_end - tile_lo + 511) >> 9) : 0u;
       auto row = [&](uint4& v, uint32_t r) {
         const uint4 cur = v;
-        v = r + 4 < rows_ld ? __ldg(src + (r + 4) * 32) : zero4;
+        v = r + 4 < rows_ld ? EmLoadStream(src + (r + 4) * 32) : zero4;
         uint32_t f16 = 0;
         if (kMode == kEmGeneric) {
           uint32_t prev = 0;
@@ -522,10 +510,25 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
         }
       };
       uint32_t r = 0;
+#if RJ_EM_PF_ROWS > 0
+      // rows 4 .. PF + 3 now (rows 0 .. 3 are being loaded), then four rows every four rows
+      if (lane == 0) {
+        const uint64_t lo = tile_lo + 2048, hi = tile_lo + (uint64_t)(RJ_EM_PF_ROWS + 4) * 512 < n16 ? tile_lo + (uint64_t)(RJ_EM_PF_ROWS + 4) * 512 : n16;
+        if (hi > lo) EmPrefetchL2(text + lo, (uint32_t)(hi - lo));
+      }
+#endif
 #pragma unroll 1
       for (;;) {
 #pragma unroll 1
-        for (; r + 4 <= rows && n_ent <= kEmEntFlush; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
+        for (; r + 4 <= rows && n_ent <= kEmEntFlush; r += 4) {
+#if RJ_EM_PF_ROWS > 0
+          if (lane == 0 && r + RJ_EM_PF_ROWS + 4 < kEmRows) {
+            const uint64_t lo = tile_lo + (uint64_t)(r + RJ_EM_PF_ROWS + 4) * 512;
+            if (lo + 2048 <= n16) EmPrefetchL2(text + lo, 2048u);
+          }
+#endif
+          row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3);
+        }
         if (r + 4 > rows) {
           if (r < rows) row(v0, r);
           if (r + 1 < rows) row(v1, r + 1);
