@@ -12,8 +12,12 @@ the text once.
                   the text once per pattern, k*N/time — kept as `value_per_pattern`).
                   Text resident in HBM, ONE fused set call per step (k_set_kmer);
                   step time = the call's device pipeline time (CUDA events on the
-                  engine's stream, first launch to the counts being on the host);
-                  L2 flushed before every call (50 MB < 126 MB L2), outside the events.
+                  engine's stream, first launch to the counts being on the host).
+                  The K timed steps run back to back between barrier + synchronize
+                  brackets and rotate over six device copies of the text (300 MB > the
+                  126 MB L2), so every step reads HBM-cold bytes without a flush kernel
+                  in between; `ms_per_step_l2_flushed` is the round-1 protocol (one
+                  buffer, L2 flushed before every call) measured in the same run.
   e2e ........... the text starts in pinned host memory: uploaded once per step
                   (H2D inside the timed region), one fused set call through the C ABI,
                   every match list copied back (D2H inside); host wall clock.
@@ -35,11 +39,14 @@ the text once.
                   RJ_BENCH_CONFIGS=0 skips the rows (the headline only).
   N > 1 ......... weak scaling of the headline: every rank owns one 50 MB slab (plus a
                   right halo) of an N*50 MB text.  The chain is stitched on the
-                  DEVICES: after its scan a rank sends the chain state leaving its slab
-                  into the right neighbour's HBM with a peer store over NVLink and
-                  checks the one arriving from the left (k_stitch; config.stitch =
-                  "nvlink").  The same step with the records exchanged by an NCCL
-                  all-gather (torch.distributed) is reported as `nccl_stitch`.
+                  DEVICES, inside the scan kernel: the CTA of k_set_kmer that reports the
+                  result sends the chain state leaving its slab into the right
+                  neighbour's HBM with a peer store over NVLink (inbox mapped through
+                  CUDA IPC) and waits for the one arriving from the left
+                  (config.stitch = "nvlink"; rejit_b200_match_all_set_device_stitched).
+                  Reported next to it: the same exchange as a second launch (k_stitch,
+                  `stitch_separate_launch`) and through an NCCL all-gather
+                  (torch.distributed, `nccl_stitch`).
 """
 import argparse
 import ctypes

@@ -183,10 +183,10 @@ class DeviceContext {
   PipelineStatus* h_set_status_dev = nullptr;
   Buffer flush;
   // pinned staging ring for pageable host texts (UploadHostText)
-  static constexpr int kStageBufs = 24;
-  static constexpr size_t kStageBytes = 1u << 20;
-  uint8_t* stage_buf[kStageBufs] = {nullptr};
-  cudaEvent_t stage_ev[kStageBufs] = {nullptr};
+  uint8_t* arena = nullptr;            // pinned, grows to the longest pageable text seen (<= 256 MB)
+  size_t arena_bytes = 0;
+  bool arena_used = false;
+  cudaEvent_t arena_ev = nullptr;      // recorded after the last copy out of the arena
   Buffer trans_tab, trans_len, trans_off, trans_counts;   // byte -> string table of ReplaceAllSetDevice and its tile sums
   // device-side stitch (one process per GPU): my inbox, the neighbours' inboxes mapped through CUDA IPC
   void* stitch_inbox = nullptr;
@@ -769,8 +769,14 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       if (ca.strategy == ScanStrategy::LiteralWindow) last_pos += (uint64_t)ca.window_hi + 1;   // ... or needle hit
       if (ca.strategy != ScanStrategy::Generic) last_pos += 3;      // a literal is tested by the lane that holds its fourth byte
       last_pos = std::min<uint64_t>(last_pos, n);
-      em.tile0 = first_start / kEmTileBytes;
-      em.ntiles = std::max<uint64_t>(last_pos / kEmTileBytes, em.tile0) - em.tile0 + 1;
+      // tile size: 32 KB for sparse matches; patterns whose every start is a candidate (generic scans, one-byte
+      // literals) fill the per-tile candidate lists: 24 / 16 KB tiles measured 15-25 % faster there and 4-15 % slower on
+      // sparse literals (gpurun_out/r2o_ab_rows*.txt)
+      em.rows = ca.strategy == ScanStrategy::Generic ? 48u : (ca.strategy == ScanStrategy::Literal && dp->needle_len == 1 ? 32u : kEmRows);
+      if (const char* env = getenv("RJ_EM_TILE_ROWS")) em.rows = (uint32_t)std::max(4, std::min<int>(atoi(env), (int)kEmRows));
+      const uint64_t tile_bytes = (uint64_t)em.rows * 512;
+      em.tile0 = first_start / tile_bytes;
+      em.ntiles = std::max<uint64_t>(last_pos / tile_bytes, em.tile0) - em.tile0 + 1;
       if (!c->em_records.Reserve(em.ntiles * 32 + 64, error)) return false;
       uint8_t* base = static_cast<uint8_t*>(c->status.p);
       em.records = c->em_records.as<uint4>();
@@ -1095,9 +1101,11 @@ int64_t MatchAllDevice(int device, Program* prog, const uint8_t* d_text, uint64_
 
 namespace {
 // Host text -> device, on the context's stream.  Pinned (or registered) memory goes in one asynchronous copy.
-// Pageable memory — what a caller of Regej::MatchAll(const char*, size_t, ...) hands over — is staged by several
-// threads through a ring of pinned 2 MB chunks, so that the page-locked copies keep PCIe busy instead of the
-// driver's single staging stream: a std::string uploads at close to the pinned rate.
+// Pageable memory — what a caller of Regej::MatchAll(const char*, size_t, ...) hands over — is staged through a
+// pinned arena: worker threads only memcpy (1 MB chunks, claimed in order), and whichever worker finishes the next
+// chunk in line issues the DMA for every consecutive chunk that is ready — one thread in the driver at a time, copies
+// in order, merged when several chunks are ready.  (Round 2a let every worker wait on an event, memcpy and enqueue
+// its own copy: past four threads they queued on the driver's lock and the upload got slower.)
 bool UploadHostText(DeviceContext* c, void* d_dst, const uint8_t* src, size_t len, std::string* error) {
   if (!len) return true;
   cudaPointerAttributes attr{};
@@ -1107,31 +1115,60 @@ bool UploadHostText(DeviceContext* c, void* d_dst, const uint8_t* src, size_t le
     RJ_TRY(cudaMemcpyAsync(d_dst, src, len, cudaMemcpyHostToDevice, c->stream));
     return true;
   }
-  if (!c->stage_buf[0]) {
-    for (int i = 0; i < DeviceContext::kStageBufs; ++i) {
-      RJ_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->stage_buf[i]), DeviceContext::kStageBytes, cudaHostAllocDefault));
-      RJ_TRY(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+  constexpr size_t kChunk = 1u << 20;
+  constexpr size_t kArenaMax = 256u << 20;                  // longer texts go through the arena in rounds
+  const size_t want = std::min(kArenaMax, (len + kChunk - 1) / kChunk * kChunk);
+  if (c->arena_bytes < want) {
+    if (c->arena) { RJ_TRY(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->arena); c->arena = nullptr; c->arena_bytes = 0; }
+    RJ_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->arena), want, cudaHostAllocDefault));
+    c->arena_bytes = want;
+    if (!c->arena_ev) RJ_TRY(cudaEventCreateWithFlags(&c->arena_ev, cudaEventDisableTiming));
+  }
+  static const int width = getenv("RJ_STAGE_WIDTH") ? std::max(1, atoi(getenv("RJ_STAGE_WIDTH"))) : 4;     // (measured: 2: 21, 4: 30, 6: 25, 8: 21, 14: 17 GB/s on a 16-core host)
+  const int device = c->device;
+  for (size_t round_lo = 0; round_lo < len; round_lo += c->arena_bytes) {
+    const size_t round_len = std::min(c->arena_bytes, len - round_lo);
+    // the arena's previous contents have left for the device
+    if (c->arena_used) RJ_TRY(cudaEventSynchronize(c->arena_ev));
+    const int n_chunks = (int)((round_len + kChunk - 1) / kChunk);
+    std::unique_ptr<std::atomic<uint8_t>[]> ready(new std::atomic<uint8_t>[n_chunks]);
+    for (int i = 0; i < n_chunks; ++i) ready[i].store(0, std::memory_order_relaxed);
+    std::mutex issue_mu;
+    int cursor = 0;                                         // next chunk to hand to the DMA engine (under issue_mu)
+    std::atomic<int> failed{0};
+    auto issue = [&]() {                                    // (issue_mu held)
+      while (cursor < n_chunks && ready[cursor].load(std::memory_order_acquire)) {
+        int j = cursor + 1;
+        while (j < n_chunks && j - cursor < 8 && ready[j].load(std::memory_order_acquire)) ++j;
+        const size_t off = (size_t)cursor * kChunk, n = std::min((size_t)j * kChunk, round_len) - off;
+        if (cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + round_lo + off, c->arena + off, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+          failed = 1;
+        cursor = j;
+      }
+    };
+    WorkerPool::Staging().Run(n_chunks, width, [&](int i) {
+      const size_t off = (size_t)i * kChunk, n = std::min(kChunk, round_len - off);
+      memcpy(c->arena + off, src + round_lo + off, n);
+      ready[i].store(1, std::memory_order_release);
+      // hand over what is ready, unless another thread is doing just that (it will see this chunk too: it re-checks
+      // `ready` under the lock, and the last chunk is always followed by the drain below)
+      if (issue_mu.try_lock()) {
+        cudaSetDevice(device);
+        issue();
+        issue_mu.unlock();
+      }
+    });
+    {
+      std::lock_guard<std::mutex> lk(issue_mu);
+      issue();
+    }
+    c->arena_used = true;
+    if (failed.load() || cursor != n_chunks || cudaEventRecord(c->arena_ev, c->stream) != cudaSuccess) {
+      Check(cudaGetLastError(), "staged upload", error);
+      if (error && error->empty()) *error = "rejit_b200: staged upload failed";
+      return false;
     }
   }
-  const size_t chunk = DeviceContext::kStageBytes;
-  const int n_chunks = (int)((len + chunk - 1) / chunk);
-  std::atomic<int> failed{0};
-  std::mutex ring_mu[DeviceContext::kStageBufs];
-  const int device = c->device;
-  // chunk i goes through ring buffer i % kStageBufs; a buffer is reused once its previous copy has left it
-  static const int width = getenv("RJ_STAGE_WIDTH") ? std::max(1, atoi(getenv("RJ_STAGE_WIDTH"))) : 12;
-  WorkerPool::Staging().Run(n_chunks, width, [&](int i) {
-    if (failed.load()) return;
-    cudaSetDevice(device);
-    const int b = i % DeviceContext::kStageBufs;
-    const size_t off = (size_t)i * chunk, n = std::min(chunk, len - off);
-    std::lock_guard<std::mutex> lk(ring_mu[b]);
-    if (cudaEventSynchronize(c->stage_ev[b]) != cudaSuccess) { failed = 1; return; }
-    memcpy(c->stage_buf[b], src + off, n);
-    if (cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, c->stage_buf[b], n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
-        cudaEventRecord(c->stage_ev[b], c->stream) != cudaSuccess) failed = 1;
-  });
-  if (failed.load()) { Check(cudaGetLastError(), "staged upload", error); if (error && error->empty()) *error = "rejit_b200: staged upload failed"; return false; }
   return true;
 }
 
@@ -1787,11 +1824,15 @@ int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint6
     if (ok && with_len) ok = Check(cudaMemcpyAsync(c->with_buf.p, with, with_len, cudaMemcpyHostToDevice, s), "H2D", error);
     if (ok) {
       const uint64_t n_tiles = n / kReplaceTile + 1;
-      int blocks = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 8);
-      k_replace_stage<<<blocks, 256, 0, s>>>(d_text, n, pairs, c->slot.as<uint64_t>(), m, c->with_buf.as<uint8_t>(),
-                                             (uint32_t)with_len, static_cast<uint8_t*>(out), n_tiles);
-      ok = Check(cudaGetLastError(), "k_replace_stage", error);
-      if (stats) stats->launches += 1;
+      ok = c->trans_off.Reserve((n_tiles + 1) * 8, error);      // (the translate path's tile array: free here)
+      if (ok) {
+        k_replace_index<<<(unsigned)((n_tiles + 256) / 256), 256, 0, s>>>(pairs, m, n_tiles, c->trans_off.as<uint64_t>());
+        int blocks = (int)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 8);
+        k_replace_stage<<<blocks, 256, 0, s>>>(d_text, n, pairs, c->slot.as<uint64_t>(), m, c->with_buf.as<uint8_t>(),
+                                               (uint32_t)with_len, static_cast<uint8_t*>(out), n_tiles, c->trans_off.as<uint64_t>());
+        ok = Check(cudaGetLastError(), "k_replace_stage", error);
+        if (stats) stats->launches += 2;
+      }
     }
   }
   if (ok && stats) {
@@ -1859,6 +1900,13 @@ int64_t ReplaceAllSetDevice(int device, const std::vector<Program*>& progs, cons
         break;
       }
     }
+  }
+  {
+    // the bits all replaced bytes have in common (the kernels' SWAR pre-filter)
+    uint32_t ones = 0xFF, zeros = 0xFF;
+    for (int b = 0; b < 256; ++b) if (tab.pat[b] != kTransNone) { ones &= (uint32_t)b; zeros &= ~(uint32_t)b & 0xFFu; }
+    tab.pre_mask = (ones | zeros) * 0x01010101u;
+    tab.pre_value = ones * 0x01010101u;
   }
   std::lock_guard<std::mutex> lk(c->mu);
   RJ_TRY_COUNT(cudaSetDevice(c->device));

@@ -67,10 +67,21 @@ __device__ __forceinline__ void ReplacePlaceStaged(uint32_t thread, const uint8_
   }
 }
 
+// first[t] = index of the first match that begins at or after tile t's first byte (first[n_tiles] = m): one thread
+// per tile, so that the ~log2(m) dependent loads of a million searches overlap.  (k_replace_stage used to search
+// twice per tile on one thread of the CTA: with 80 M matches that was 25 us of latency per 4 KB tile, 3/4 of the
+// rebuild of a 5 GB FASTA file.)
+__global__ void __launch_bounds__(256)
+k_replace_index(const uint64_t* __restrict__ pairs, uint64_t m, uint64_t n_tiles, uint64_t* __restrict__ first) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  first[t] = t == n_tiles ? m : ReplaceLowerBound(pairs, m, t * kReplaceTile);
+}
+
 __global__ void __launch_bounds__(256)
 k_replace_stage(const uint8_t* __restrict__ text, uint64_t n, const uint64_t* __restrict__ pairs,
                 const uint64_t* __restrict__ removed, uint64_t m, const uint8_t* __restrict__ with, uint32_t w,
-                uint8_t* __restrict__ out, uint64_t n_tiles) {
+                uint8_t* __restrict__ out, uint64_t n_tiles, const uint64_t* __restrict__ first) {
   __shared__ uint16_t s_b[kReplaceTile + 2];        // begin - tile_lo of the tile's own matches
   __shared__ uint16_t s_e[kReplaceTile + 2];        // end - tile_lo, clipped to the tile
   __shared__ uint16_t s_r[kReplaceTile + 2];        // removed[m0 + i] - removed[m0]
@@ -88,8 +99,8 @@ k_replace_stage(const uint8_t* __restrict__ text, uint64_t n, const uint64_t* __
       const uint4 v = at < n16 ? __ldg(reinterpret_cast<const uint4*>(text + at)) : make_uint4(0, 0, 0, 0);
       reinterpret_cast<uint4*>(s_in)[threadIdx.x] = v;
     }
-    if (threadIdx.x == 0) s_head.m0 = ReplaceLowerBound(pairs, m, tile_lo);
-    if (threadIdx.x == 32) s_next.m0 = last ? m : ReplaceLowerBound(pairs, m, tile_hi);
+    if (threadIdx.x == 0) s_head.m0 = first[tile];
+    if (threadIdx.x == 32) s_next.m0 = first[tile + 1];
     __syncthreads();
     if (threadIdx.x == 0) { s_head.m1 = s_next.m0; ReplaceHead(pairs, removed, m, tile_lo, &s_head); }
     if (threadIdx.x == 32) ReplaceHead(pairs, removed, m, tile_hi, &s_next);
@@ -128,6 +139,7 @@ constexpr uint32_t kTransMaxBytes = 4096;           // all replacement strings t
 constexpr uint8_t kTransNone = 0xFF;
 
 struct TranslateTable {                 // device memory
+  uint32_t pre_mask, pre_value;         // every replaced byte b has (b & pre_mask) == pre_value (both x 0x01010101)
   uint16_t len[256];                    // output bytes of input byte b (1 = copied)
   uint16_t off[256];                    // its replacement starts at bytes[off[b]]
   uint8_t pat[256];                     // the pattern that matches it, kTransNone = none
@@ -170,12 +182,20 @@ __device__ __forceinline__ void Tr2LoadTables(const TranslateTable* __restrict__
   if (threadIdx.x == 0) { t->len[0] = 1; t->off[0] = 0; }
 }
 
-// class ids of my 16 bytes OR-ed together (0: nothing to replace)
-__device__ __forceinline__ uint32_t Tr2AnySpecial(const uint4& v, const uint8_t* cls) {
+// class ids of my 16 bytes OR-ed together (0: nothing to replace).  First a SWAR test on the bits that all replaced
+// bytes have in common (a word without a candidate byte costs 4 instructions instead of 16): "some byte of x is zero"
+// may also fire on the byte above a zero byte, which only sends the word to the exact test.
+__device__ __forceinline__ uint32_t Tr2AnySpecial(const uint4& v, const uint8_t* cls, uint32_t pm, uint32_t pv) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
   uint32_t any = 0;
 #pragma unroll
-  for (int p = 0; p < 16; ++p) any |= cls[__byte_perm(w[p >> 2], 0u, 0x4440 | (p & 3))];
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t x = (w[j] & pm) ^ pv;
+    if ((x - 0x01010101u) & ~x & 0x80808080u) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) any |= cls[__byte_perm(w[j], 0u, 0x4440 | k)];
+    }
+  }
   return any;
 }
 
@@ -190,6 +210,7 @@ k_translate_count2(const uint8_t* __restrict__ text, uint64_t n, const Translate
   for (uint32_t i = threadIdx.x; i < kTr2Warps * (uint32_t)K * 32; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   uint32_t* my_hist = s_hist + (uint32_t)warp * K * 32 + lane;
+  const uint32_t pm = tab->pre_mask, pv = tab->pre_value;
   const uint64_t n16 = (n + 15) & ~15ull;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   const uint64_t n_warps = (uint64_t)gridDim.x * kTr2Warps;
@@ -205,7 +226,7 @@ k_translate_count2(const uint8_t* __restrict__ text, uint64_t n, const Translate
     auto row = [&](uint4& v, uint32_t r) {
       const uint4 cur = v;
       v = r + 4 < rows_ld ? __ldg(src + (r + 4) * 32) : zero4;
-      if (Tr2AnySpecial(cur, t->cls)) {
+      if (Tr2AnySpecial(cur, t->cls, pm, pv)) {
         const uint64_t at = mine + (uint64_t)r * 512;
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
@@ -263,6 +284,7 @@ k_translate_write2(const uint8_t* __restrict__ text, uint64_t n, const Translate
   for (uint32_t i = threadIdx.x; i < kTransMaxBytes; i += blockDim.x) s_bytes[i] = tab->bytes[i];
   __syncthreads();
   const Tr2Tables* t = &s_t;
+  const uint32_t pm = tab->pre_mask, pv = tab->pre_value;
   uint8_t* stage = s_stage_all[warp];
   uint32_t* list = s_list_all[warp];
   const uint64_t n16 = (n + 15) & ~15ull;
@@ -294,7 +316,7 @@ k_translate_write2(const uint8_t* __restrict__ text, uint64_t n, const Translate
       v = r + 4 < rows_ld ? __ldg(src + (r + 4) * 32) : zero4;
       const uint64_t at = mine + (uint64_t)r * 512;
       const bool whole = tile_lo + (uint64_t)(r + 1) * 512 <= n;                           // every byte of the row is text
-      const uint32_t any = Tr2AnySpecial(cur, t->cls);
+      const uint32_t any = Tr2AnySpecial(cur, t->cls, pm, pv);
       if (whole && !__any_sync(kFullMask, any != 0)) {
         // ---- copy -----------------------------------------------------------------------------------
         const uint32_t sh = (uint32_t)pos & 15u;
@@ -325,9 +347,10 @@ k_translate_write2(const uint8_t* __restrict__ text, uint64_t n, const Translate
       flush();
       const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
       uint32_t packed = 0;                                  // output bytes | replaced bytes << 22
+      const uint32_t nb = whole ? 16u : (at < n ? (n - at < 16 ? (uint32_t)(n - at) : 16u) : 0u);      // my bytes that are text
 #pragma unroll
       for (int p = 0; p < 16; ++p)
-        if (at + p < n) {
+        if ((uint32_t)p < nb) {
           const uint32_t c = t->cls[__byte_perm(w[p >> 2], 0u, 0x4440 | (p & 3))];
           packed += (uint32_t)t->len[c] + (c ? 1u << 22 : 0u);
         }
@@ -341,7 +364,7 @@ k_translate_write2(const uint8_t* __restrict__ text, uint64_t n, const Translate
         uint32_t q = a + (excl & 0x3FFFFFu), li = excl >> 22;
 #pragma unroll
         for (int p = 0; p < 16; ++p)
-          if (at + p < n) {
+          if ((uint32_t)p < nb) {
             const uint32_t b = __byte_perm(w[p >> 2], 0u, 0x4440 | (p & 3));
             const uint32_t c = t->cls[b];
             if (!c) { stage[q++] = (uint8_t)b; }

@@ -94,6 +94,7 @@ struct EmitArgs {
   unsigned int* sync;               // [0..1] ticket (64 bit), [2] flags, [3] tiles done; zeroed by the host before the launch
   unsigned long long* final_state;  // [3]: total matches, chain state (cur, non-empty); written by the last tile
   uint64_t tile0, ntiles;           // tiles [tile0, tile0 + ntiles) hold every owned start (and needle hit)
+  uint32_t rows;                    // rows of 512 bytes per tile (<= kEmRows; the host picks: dense candidates want smaller tiles)
   uint64_t* out_pairs;
   uint64_t out_cap, base_offset;
   FinRecord* host_records;
@@ -151,14 +152,6 @@ __device__ __forceinline__ uint4 EmLoadStream(const uint4* p) {
   return v;
 #endif
 }
-// a hint: bring [p, p + bytes) into L2 (one bulk prefetch, no destination, no barrier) so that the loads that follow a few
-// rows later wait for an L2 hit instead of an HBM access; `bytes` a multiple of 16
-__device__ __forceinline__ void EmPrefetchL2(const uint8_t* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-}
-#ifndef RJ_EM_PF_ROWS
-#define RJ_EM_PF_ROWS 0            // rows the L2 prefetch runs ahead of the row being looked at (0: off)
-#endif
 __device__ __forceinline__ uint4 EmLoadRow(const uint8_t* __restrict__ text, uint64_t n16, uint64_t at) {
   return at < n16 ? __ldg(reinterpret_cast<const uint4*>(text + at)) : make_uint4(0, 0, 0, 0);
 }
@@ -448,23 +441,28 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
   // a literal window begins up to three bytes before a lane's 16: rows are scanned up to the one that holds n + 2
   const uint64_t scan_end = kMode == kEmGeneric ? n : n + 3;
 
+  const uint32_t tile_rows = em.rows, tile_bytes = em.rows * 512u;
   unsigned long long next_ticket = 0;
   if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
   for (;;) {
     const uint64_t t = __shfl_sync(kFullMask, next_ticket, 0);
     if (t >= em.ntiles) break;
-    const uint64_t tile_lo = (em.tile0 + t) * kEmTileBytes;
+    const uint64_t tile_lo = (em.tile0 + t) * tile_bytes;
     const uint64_t tile_base = tile_lo >= kEmBias ? tile_lo - kEmBias : 0;
     const uint64_t mine = tile_lo + (uint64_t)lane * 16;
     unsigned int flags = 0;
     uint32_t cnt = 0;                                       // candidates of the tile so far
     uint64_t prev_hit = kNoMatch;
-    const bool live = tile_lo <= n && tile_lo < hit_hi + 16 && tile_lo + kEmTileBytes + 16 > range.own_begin;
+    // The next ticket is asked for a few rows before this tile's last row, so that its round trip hides behind them (a
+    // tile that has an owner but has not been started holds up the look-back of every tile after it: not earlier).
+    // (An L2 bulk prefetch a few rows ahead of the loads was tried too: 8 / 16 / 32 rows ahead all cost 10-20 %.)
+    bool asked = false;
+    const bool live = tile_lo <= n && tile_lo < hit_hi + 16 && tile_lo + tile_bytes + 16 > range.own_begin;
     if (live) {
       // ---- stream the rows; evaluate the survivors whenever their list fills up, and at the end --------------
       uint32_t n_ent = 0;
       // rows [0, rows_ld) have my 16 bytes inside the (padded) text: one compare per load instead of a 64-bit bound
-      const uint32_t rows_ld = mine < n16 ? (uint32_t)(((n16 - mine + 511) >> 9) < kEmRows ? ((n16 - mine + 511) >> 9) : kEmRows) : 0u;
+      const uint32_t rows_ld = mine < n16 ? (uint32_t)(((n16 - mine + 511) >> 9) < tile_rows ? ((n16 - mine + 511) >> 9) : tile_rows) : 0u;
       const uint4* src = reinterpret_cast<const uint4*>(text + mine);
       const uint4 zero4 = make_uint4(0, 0, 0, 0);
       uint4 v0 = 0 < rows_ld ? EmLoadStream(src) : zero4, v1 = 1 < rows_ld ? EmLoadStream(src + 32) : zero4,
@@ -478,8 +476,8 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
         tail = __ldg(reinterpret_cast<const uint32_t*>(text + tile_lo - 4));
       }
       // rows that hold text (or, for literals, the three bytes after it)
-      uint32_t rows = kEmRows;
-      if (tile_lo + kEmTileBytes > scan_end) rows = scan_end > tile_lo ? (uint32_t)((scan_end - tile_lo + 511) >> 9) : 0u;
+      uint32_t rows = tile_rows;
+      if (tile_lo + tile_bytes > scan_end) rows = scan_end > tile_lo ? (uint32_t)((scan_end - tile_lo + 511) >> 9) : 0u;
       auto row = [&](uint4& v, uint32_t r) {
         const uint4 cur = v;
         v = r + 4 < rows_ld ? EmLoadStream(src + (r + 4) * 32) : zero4;
@@ -501,7 +499,11 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
           uint32_t pw = __shfl_up_sync(kFullMask, cur.w, 1);
           if (lane == 0) pw = tail;
           tail = __shfl_sync(kFullMask, cur.w, 31);
+#ifdef RJ_EM_READONLY      // tuning builds: the memory side of this tiling alone (the filter replaced by four XORs)
+          if ((cur.x ^ cur.y ^ cur.z ^ cur.w ^ pw) == 0x12345679u) f16 = 1;
+#else
           if (EmLitAny<kFull4>(cur, pw, lit.p4, lit.pmask)) f16 = EmLitFlags<kFull4>(cur, pw, lit.p4, lit.pmask);
+#endif
         }
         const uint32_t bal = __ballot_sync(kFullMask, f16 != 0);
         if (bal) {
@@ -510,23 +512,14 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
         }
       };
       uint32_t r = 0;
-#if RJ_EM_PF_ROWS > 0
-      // rows 4 .. PF + 3 now (rows 0 .. 3 are being loaded), then four rows every four rows
-      if (lane == 0) {
-        const uint64_t lo = tile_lo + 2048, hi = tile_lo + (uint64_t)(RJ_EM_PF_ROWS + 4) * 512 < n16 ? tile_lo + (uint64_t)(RJ_EM_PF_ROWS + 4) * 512 : n16;
-        if (hi > lo) EmPrefetchL2(text + lo, (uint32_t)(hi - lo));
-      }
-#endif
 #pragma unroll 1
       for (;;) {
 #pragma unroll 1
         for (; r + 4 <= rows && n_ent <= kEmEntFlush; r += 4) {
-#if RJ_EM_PF_ROWS > 0
-          if (lane == 0 && r + RJ_EM_PF_ROWS + 4 < kEmRows) {
-            const uint64_t lo = tile_lo + (uint64_t)(r + RJ_EM_PF_ROWS + 4) * 512;
-            if (lo + 2048 <= n16) EmPrefetchL2(text + lo, 2048u);
+          if (!asked && r + 12 >= rows) {
+            asked = true;
+            if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
           }
-#endif
           row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3);
         }
         if (r + 4 > rows) {
@@ -543,7 +536,7 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
           if (n_hits > kEmWinCandCap) flags |= kFinDense;
           else if (n_hits) cnt = EmEvalWindow(text, n, nfa, lit, range, tile_base, my_hits, n_hits, &prev_hit, my_cand, cnt, cap, &flags);
         } else {
-          const bool add_end = r >= rows && n >= tile_lo && n < tile_lo + kEmTileBytes;
+          const bool add_end = r >= rows && n >= tile_lo && n < tile_lo + tile_bytes;
           cnt = EmEvalGeneric(text, n, nfa, range, tile_base, tile_lo, my_ent, n_ent, add_end, my_cand, cnt, cap, &flags);
         }
         n_ent = 0;
@@ -551,9 +544,7 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
         if (r >= rows) break;
       }
     }
-    // The next tile is taken now, not earlier: a tile that has an owner but has not been started holds up the
-    // look-back of every tile after it, so a ticket is held only while this tile is being finished.
-    if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
+    if (!asked && lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
     flags = __reduce_or_sync(kFullMask, flags);
     if (flags) cnt = 0;
     // ---- does every candidate begin after its predecessor ended?  Else one lane walks the chain ----------------
@@ -635,10 +626,19 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
     // ---- the warp that finishes the last tile reports --------------------------------------------------------------
     // (no fence per tile: a gpu-scope fence invalidates the SM's L1 under the other warps' streaming loads; only the
     // last tile's totals must be visible to the reporter, and the host reads the pairs after the kernel has ended)
+    // Every tile counts itself done with a reduction nobody waits for; the warp of the LAST tile waits until all
+    // have (it is the last to start, so not for long) and reports.  A tile that raised a flag makes it visible first.
     if (lane == 0) {
-      if (t + 1 == em.ntiles) __threadfence();
-      const unsigned int done = atomicAdd(&em.sync[3], 1u);
-      if ((uint64_t)done + 1 == em.ntiles) {
+      if (flags) __threadfence();
+      if (t + 1 != em.ntiles) {
+        atomicAdd(&em.sync[3], 1u);
+      } else {
+        __threadfence();
+        const volatile unsigned int* done = em.sync + 3;
+        for (uint32_t polls = 0; (uint64_t)*done + 1 < em.ntiles; ++polls) {
+          if (polls > (1u << 24)) { atomicOr(&em.sync[2], kFinOverlap | kFinStuck); break; }
+          __nanosleep(100);
+        }
         __threadfence();
         const unsigned int fl = atomicOr(&em.sync[2], 0u);
         const unsigned long long total = __ldcg(&em.final_state[0]), cur = __ldcg(&em.final_state[1]);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Tuning aid: a few device-resident cases, one short line each (select the library with RJ_LIB=...).
-   usage: ab_run.py [case ...]   cases: lit c3 c3hits c4 b hat strip kmer50 kmer625 iub"""
+   usage: ab_run.py [case ...]   cases: lit c3 c3hits c4 b hat strip kmer50 kmer625 iub striprep"""
 import os
 import sys
 
@@ -76,6 +76,22 @@ for c in cases:
         for i in range(REPS + 2):
             st = rj.Stats()
             res, _counts = rj.replace_all_set_text(regs, tx, withs, stats=st)
+            out = len(res)
+            res.free()
+            if i >= 2:
+                tot += st.total_ms
+                best = min(best, st.total_ms)
+        avg, la = tot / REPS, st.launches
+        dt = tx
+    elif c == "striprep":
+        text = np.frombuffer(W.fasta_file(50_000_000), dtype=np.uint8)
+        n = len(text)
+        tx = rj.Text(text)
+        r = rj.Regej(W.STRIP_PATTERN)
+        best, tot = 1e9, 0.0
+        for i in range(REPS + 2):
+            st = rj.Stats()
+            res, _m = r.replace_all_text(tx, b"", stats=st)
             out = len(res)
             res.free()
             if i >= 2:

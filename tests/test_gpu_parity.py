@@ -696,6 +696,21 @@ def test_replace_all_set_one_pass(rj):
         assert counts == exp_counts and out.download() == exp, ps
         out.free()
         src.free()
+    # rows that are copied (no replaced byte in 512 bytes) between rows that are not: every output alignment, texts that
+    # end inside a row / a tile, one replacement longer than the staging area of a row
+    rng = random.Random(11)
+    for n, every in ((16384 * 3 + 5, 700), (16384, 2000), (100001, 97), (513, 1000), (511, 3), (40000, 10 ** 9)):
+        body = bytearray(rng.choice(b"acgt") for _ in range(n))
+        for at in range(every // 2, n, every):
+            body[at] = rng.choice(b"XYZ")
+        body = bytes(body)
+        for ps, ws in ((["X", "Y", "Z"], [b"(x|y)", b"", b"0123456789abcdefg"]), (["[XY]"], [b"q" * 3000])):
+            exp, exp_counts = sequential(body, ps, ws)
+            src = rj.Text(body)
+            out, counts = rj.replace_all_set_text(ps, src, ws)
+            assert counts == exp_counts and out.download() == exp, (n, every, ps)
+            out.free()
+            src.free()
     # not a table: a replacement feeds a later pattern / a two-byte pattern -> call by call, same answer
     for ps, ws in ((["a", "b"], [b"b", b"c"]), (["ab", "c"], [b"X", b"Y"]), (["a*", "b"], [b"-", b"+"])):
         exp, exp_counts = sequential(t[:20000], ps, ws)
