@@ -578,10 +578,12 @@ bool EnsureKernelAttributes(DeviceContext* c, std::string* error) {
   RJ_TRY(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   RJ_TRY(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   RJ_TRY(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
-  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
-  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmWindow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
-  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmGeneric, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmWindow, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmGeneric, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   c->attr_done = true;
   return true;
 }
@@ -792,16 +794,22 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       lit.needle = dp->needle;
       lit.m = dp->needle_len; lit.p4 = dp->p4; lit.pmask = dp->pmask;
       lit.win_lo = ca.window_lo; lit.win_hi = ca.window_hi;
-      const int blocks = (int)std::min<uint64_t>((em.ntiles + kEmWarps - 1) / kEmWarps, (uint64_t)c->sm_count * 4);
+      static const bool no_deep = getenv("RJ_EM_DEPTH4") != nullptr;          // (tuning: the four-row literal kernels)
+      const bool deep = ca.strategy == ScanStrategy::Literal && !no_deep;      // eight rows in flight, three CTAs per SM
+      const int blocks = (int)std::min<uint64_t>((em.ntiles + kEmWarps - 1) / kEmWarps, (uint64_t)c->sm_count * (deep ? 3 : 4));
       if (ca.strategy == ScanStrategy::Literal) {
-        if (dp->needle_len >= 4)
-          k_scan_emit<kEmLiteral, true><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+        if (dp->needle_len >= 4 && deep)
+          k_scan_emit<kEmLiteral, true, 8><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+        else if (deep)
+          k_scan_emit<kEmLiteral, false, 8><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+        else if (dp->needle_len >= 4)
+          k_scan_emit<kEmLiteral, true, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
         else
-          k_scan_emit<kEmLiteral, false><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+          k_scan_emit<kEmLiteral, false, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
       } else if (ca.strategy == ScanStrategy::LiteralWindow) {
-        k_scan_emit<kEmWindow, true><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+        k_scan_emit<kEmWindow, true, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
       } else {
-        k_scan_emit<kEmGeneric, true><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+        k_scan_emit<kEmGeneric, true, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
       }
       fused = true;
       if (stats) stats->launches += 1;

@@ -166,6 +166,12 @@ constexpr uint32_t kTr2Tile = kTr2Rows * 512;                       // 16 KB, on
 constexpr uint32_t kTr2Warps = 8;
 constexpr uint32_t kTr2Stage = 2048;                                // output of one row that is assembled in shared memory
 constexpr uint32_t kTr2MaxLen = 4095;                               // longest replacement (16 of them fit 16 bits)
+constexpr int kTr2Depth = 8;                                        // rows in flight per warp, counting pass
+__device__ __forceinline__ uint4 Tr2Load(const uint4* p) {          // read once: no L1 allocation
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 
 struct Tr2Tables {                      // shared memory, loaded once per CTA
   uint8_t cls[256];                     // 0: the byte is copied; j + 1: pattern j replaces it
@@ -220,12 +226,13 @@ k_translate_count2(const uint8_t* __restrict__ text, uint64_t n, const Translate
     const uint32_t rows = n - tile_lo >= kTr2Tile ? kTr2Rows : (uint32_t)((n - tile_lo + 511) >> 9);
     const uint32_t rows_ld = mine < n16 ? (uint32_t)(((n16 - mine + 511) >> 9) < kTr2Rows ? ((n16 - mine + 511) >> 9) : kTr2Rows) : 0u;
     const uint4* src = reinterpret_cast<const uint4*>(text + mine);
-    uint4 v0 = 0 < rows_ld ? __ldg(src) : zero4, v1 = 1 < rows_ld ? __ldg(src + 32) : zero4,
-          v2 = 2 < rows_ld ? __ldg(src + 64) : zero4, v3 = 3 < rows_ld ? __ldg(src + 96) : zero4;
+    uint4 v[kTr2Depth];                                     // rows in flight (see k_scan_emit: four were latency-bound)
+#pragma unroll
+    for (int u = 0; u < kTr2Depth; ++u) v[u] = (uint32_t)u < rows_ld ? Tr2Load(src + u * 32) : zero4;
     uint32_t extra = 0;                                     // output bytes beyond one per input byte (may be "negative")
     auto row = [&](uint4& v, uint32_t r) {
       const uint4 cur = v;
-      v = r + 4 < rows_ld ? __ldg(src + (r + 4) * 32) : zero4;
+      v = r + kTr2Depth < rows_ld ? Tr2Load(src + (r + kTr2Depth) * 32) : zero4;
       if (Tr2AnySpecial(cur, t->cls, pm, pv)) {
         const uint64_t at = mine + (uint64_t)r * 512;
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
@@ -238,10 +245,13 @@ k_translate_count2(const uint8_t* __restrict__ text, uint64_t n, const Translate
     };
     uint32_t r = 0;
 #pragma unroll 1
-    for (; r + 4 <= rows; r += 4) { row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3); }
-    if (r < rows) row(v0, r);
-    if (r + 1 < rows) row(v1, r + 1);
-    if (r + 2 < rows) row(v2, r + 2);
+    for (; r + kTr2Depth <= rows; r += kTr2Depth) {
+#pragma unroll
+      for (int u = 0; u < kTr2Depth; ++u) row(v[u], r + u);
+    }
+#pragma unroll
+    for (int u = 0; u < kTr2Depth - 1; ++u)
+      if (r + u < rows) row(v[u], r + u);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) extra += __shfl_xor_sync(kFullMask, extra, d);
     if (lane == 0) {

@@ -252,12 +252,47 @@ __device__ __forceinline__ uint32_t EmEvalLiteral(const uint8_t* __restrict__ te
 }
 
 // one NFA run per start in front of every needle hit (the windows of neighbouring hits of this tile are clipped
-// against each other so that every start is tried once, in order)
-__device__ __forceinline__ uint32_t EmEvalWindow(const uint8_t* __restrict__ text, uint64_t n, const NfaTables& nfa,
+// against each other so that every start is tried once, in order).  Two phases: the starts of ALL the tile's hits
+// are first put to the one-byte test "can a match begin with this byte here" (nine in ten fail it on the complex
+// benchmark pattern) and the survivors collected, in order, in `my_list`; then the NFA runs, 32 survivors at a time.
+// (Running the windows hit by hit — two batches of mostly idle lanes per hit, each a chain of dependent table
+// lookups — was 60 % of the kernel on a text with a hit every 10 KB.)
+// the NFA runs for the starts my_list[0 .. n_list) (offsets from tile_base, ascending), 32 at a time; candidates appended in order
+__device__ __forceinline__ uint32_t EmRunList(const uint8_t* __restrict__ text, uint64_t n, const NfaTables& nfa, uint64_t tile_base,
+                                               const uint32_t* my_list, uint32_t n_list, uint32_t* my_cand, uint32_t k, uint32_t cap,
+                                               unsigned int* flags) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t base = 0; base < n_list; base += 32) {
+    const uint32_t i = base + lane;
+    uint64_t s = 0, e = kNoMatch;
+    if (i < n_list) {
+      s = tile_base + my_list[i];
+      e = NfaRunAny(nfa, text, n, s);
+    }
+    __syncwarp();
+    const bool has = e != kNoMatch;
+    if (has && e - s >= kEmPending) { *flags |= kFinDense; e = s; }      // length does not fit: the general path
+    const uint32_t bal = __ballot_sync(kFullMask, has);
+    if (bal) {
+      const uint32_t idx = k + __popc(bal & ((1u << lane) - 1u));
+      if (has && idx < cap) my_cand[idx] = EmCand((uint32_t)(s - tile_base), (uint32_t)(e - s));
+      k += __popc(bal);
+    }
+  }
+  __syncwarp();
+  return k;
+}
+
+// (not inlined: its NFA runs would share the streaming loop's 64 registers and push the rows in flight into local memory;
+// at the end of a tile, where it is called, no row is in flight and the call saves nothing)
+__device__ __noinline__ uint32_t EmEvalWindow(const uint8_t* __restrict__ text, uint64_t n, const NfaTables& nfa,
                                                   const EmLit& lit, const ScanRange& range, uint64_t tile_base,
                                                   const uint32_t* my_hits, uint32_t n_hits, uint64_t* prev_hit,
-                                                  uint32_t* my_cand, uint32_t k, uint32_t cap, unsigned int* flags) {
+                                                  uint32_t* my_cand, uint32_t k, uint32_t cap, unsigned int* flags,
+                                                  uint32_t* my_list, uint32_t list_cap) {
   const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t n_list = 0;
   for (uint32_t q = 0; q < n_hits; ++q) {
     const uint64_t h = tile_base + my_hits[q];
     const uint64_t prev = *prev_hit;                           // the hit before it in this tile (kNoMatch: none)
@@ -268,22 +303,21 @@ __device__ __forceinline__ uint32_t EmEvalWindow(const uint8_t* __restrict__ tex
     if (prev != kNoMatch && prev >= lit.win_lo && prev - lit.win_lo + 1 > s_min) s_min = prev - lit.win_lo + 1;
     for (uint64_t base = s_min; base <= s_max; base += 32) {
       const uint64_t s = base + lane;
-      uint64_t e = kNoMatch;
+      bool ok = false;
       if (s <= s_max && s >= range.own_begin && s < range.own_end && s < n) {
         const int ctx = nfa.has_anchor ? ContextAt(text, n, s) : 0;
-        if (nfa.start_ok[ctx * 256 + text[s]]) e = NfaRunAny(nfa, text, n, s);
+        ok = nfa.start_ok[ctx * 256 + text[s]] != 0;
       }
-      __syncwarp();
-      const bool has = e != kNoMatch;
-      if (has && e - s >= kEmPending) { *flags |= kFinDense; e = s; }      // length does not fit: the general path
-      const uint32_t bal = __ballot_sync(kFullMask, has);
+      const uint32_t bal = __ballot_sync(kFullMask, ok);
       if (bal) {
-        const uint32_t idx = k + __popc(bal & ((1u << lane) - 1u));
-        if (has && idx < cap) my_cand[idx] = EmCand((uint32_t)(s - tile_base), (uint32_t)(e - s));
-        k += __popc(bal);
+        if (ok) my_list[n_list + __popc(bal & lt_mask)] = (uint32_t)(s - tile_base);
+        n_list += __popc(bal);
+        __syncwarp();
+        if (n_list + 32 > list_cap) { k = EmRunList(text, n, nfa, tile_base, my_list, n_list, my_cand, k, cap, flags); n_list = 0; }
       }
     }
   }
+  if (n_list) k = EmRunList(text, n, nfa, tile_base, my_list, n_list, my_cand, k, cap, flags);
   __syncwarp();
   return k;
 }
@@ -423,8 +457,12 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint6
 // ===========================================================================
 // the kernel: every warp is on its own
 // ===========================================================================
-template <int kMode, bool kFull4>
-__global__ void __launch_bounds__(kEmThreads, 4)
+// kDepth rows in flight per warp.  A warp asks for a new row only when it has looked at one, so its time per row is
+// the memory latency / kDepth PLUS its own instructions: with four rows the literal kernels ran at 4.0 TB/s where the
+// same tiling with an empty loop body reads 6.9 TB/s (scripts/probe/read_bw.cu); eight rows cost sixteen registers
+// (three CTAs per SM instead of four).  The window / generic kernels are at their register limit with four.
+template <int kMode, bool kFull4, int kDepth>
+__global__ void __launch_bounds__(kEmThreads, kDepth > 4 ? 3 : 4)
 k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables nfa, EmFilter flt, ScanRange range,
             EmitArgs em) {
   extern __shared__ __align__(16) uint8_t em_smem[];
@@ -465,8 +503,9 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
       const uint32_t rows_ld = mine < n16 ? (uint32_t)(((n16 - mine + 511) >> 9) < tile_rows ? ((n16 - mine + 511) >> 9) : tile_rows) : 0u;
       const uint4* src = reinterpret_cast<const uint4*>(text + mine);
       const uint4 zero4 = make_uint4(0, 0, 0, 0);
-      uint4 v0 = 0 < rows_ld ? EmLoadStream(src) : zero4, v1 = 1 < rows_ld ? EmLoadStream(src + 32) : zero4,
-            v2 = 2 < rows_ld ? EmLoadStream(src + 64) : zero4, v3 = 3 < rows_ld ? EmLoadStream(src + 96) : zero4;
+      uint4 v[kDepth];
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) v[u] = (uint32_t)u < rows_ld ? EmLoadStream(src + u * 32) : zero4;
       // what precedes the tile: its last word (literal windows) / whether its last byte is a line break
       uint32_t tail = 0;
       if (kMode == kEmGeneric) {
@@ -480,7 +519,7 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
       if (tile_lo + tile_bytes > scan_end) rows = scan_end > tile_lo ? (uint32_t)((scan_end - tile_lo + 511) >> 9) : 0u;
       auto row = [&](uint4& v, uint32_t r) {
         const uint4 cur = v;
-        v = r + 4 < rows_ld ? EmLoadStream(src + (r + 4) * 32) : zero4;
+        v = r + kDepth < rows_ld ? EmLoadStream(src + (r + kDepth) * 32) : zero4;
         uint32_t f16 = 0;
         if (kMode == kEmGeneric) {
           uint32_t prev = 0;
@@ -515,17 +554,25 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
 #pragma unroll 1
       for (;;) {
 #pragma unroll 1
-        for (; r + 4 <= rows && n_ent <= kEmEntFlush; r += 4) {
-          if (!asked && r + 12 >= rows) {
+        for (; r + kDepth <= rows && n_ent + 32 * kDepth <= kEmEntCap; r += kDepth) {
+          if (!asked && r + kDepth + 8 >= rows) {
             asked = true;
             if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
           }
-          row(v0, r); row(v1, r + 1); row(v2, r + 2); row(v3, r + 3);
+#pragma unroll
+          for (int u = 0; u < kDepth; ++u) row(v[u], r + u);
         }
-        if (r + 4 > rows) {
-          if (r < rows) row(v0, r);
-          if (r + 1 < rows) row(v1, r + 1);
-          if (r + 2 < rows) row(v2, r + 2);
+        if (r + kDepth > rows) {
+#pragma unroll
+          for (int u = 0; u < kDepth - 1; ++u)
+            if (r + u < rows) row(v[u], r + u);
+          r = rows;
+        } else if (kMode == kEmWindow) {
+          // more needle hits in one tile than the list holds (one per 64 bytes): the general path.  The windows are
+          // evaluated once, after the tile's last row — a call in the middle of the tile, with rows in flight, kept
+          // those rows in local memory for the whole streaming loop.
+          flags |= kFinDense;
+          n_ent = 0;
           r = rows;
         }
         __syncwarp();
@@ -534,7 +581,8 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
         } else if (kMode == kEmWindow) {
           const uint32_t n_hits = n_ent ? EmEvalLiteral<true>(text, n, lit, range.own_begin, hit_hi, tile_base, tile_lo, my_ent, n_ent, my_hits, 0u, kEmWinCandCap) : 0u;
           if (n_hits > kEmWinCandCap) flags |= kFinDense;
-          else if (n_hits) cnt = EmEvalWindow(text, n, nfa, lit, range, tile_base, my_hits, n_hits, &prev_hit, my_cand, cnt, cap, &flags);
+          else if (n_hits) cnt = EmEvalWindow(text, n, nfa, lit, range, tile_base, my_hits, n_hits, &prev_hit, my_cand, cnt, cap, &flags,
+                                              my_ent, kEmEntCap);             // (the survivors' list is free: they have become hits)
         } else {
           const bool add_end = r >= rows && n >= tile_lo && n < tile_lo + tile_bytes;
           cnt = EmEvalGeneric(text, n, nfa, range, tile_base, tile_lo, my_ent, n_ent, add_end, my_cand, cnt, cap, &flags);
