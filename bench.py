@@ -36,6 +36,9 @@ the text once.
                   5 GB FASTA file — each with GB/s (physical), the scan kernel's
                   roofline fraction, launches and an independent count check.
                   At N > 1 the 5 GB texts are strong-scaled: rank r owns slab r.
+                  Last row (N = 1): samples/jrep.cc over a 1 GiB source tree of 2048
+                  files next to the reference's own jrep (oracle/_ref/jrep_ref, all host
+                  cores), outputs compared (scripts/jrep_bench.py; RJ_BENCH_JREP=0 skips).
                   RJ_BENCH_CONFIGS=0 skips the rows (the headline only).
   N > 1 ......... weak scaling of the headline: every rank owns one 50 MB slab (plus a
                   right halo) of an N*50 MB text.  The chain is stitched on the
@@ -926,6 +929,16 @@ def main():
     rows = None
     if os.environ.get("RJ_BENCH_CONFIGS", "1") != "0":
         rows = config_rows(rj, W, torch, peak, local_rank, rank, world, dist, tdev, max(3, min(args.steps, 5)))
+
+    # ---- jrep on the GPU next to the reference's jrep on the host cores (N = 1) ---------
+    if rows is not None and world == 1 and os.environ.get("RJ_BENCH_JREP", "1") != "0":
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "jrep_bench.py"),
+                                  "--bytes", os.environ.get("RJ_BENCH_JREP_BYTES", str(1 << 30)), "--files", "2048"],
+                                 capture_output=True, text=True, timeout=600)
+            rows.append(json.loads(out.stdout.strip().split("\n")[-1]))
+        except Exception as exc:                                   # noqa: BLE001
+            rows.append({"config": "jrep", "error": str(exc)[:200]})
 
     # ---- MatchAllParallel on rank 0 over all N devices, against the compiled reference (N > 1) -----------
     parallel = None

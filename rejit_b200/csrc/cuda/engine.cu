@@ -578,8 +578,6 @@ bool EnsureKernelAttributes(DeviceContext* c, std::string* error) {
   RJ_TRY(cudaFuncSetAttribute(k_dfa_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   RJ_TRY(cudaFuncSetAttribute(k_set_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
   RJ_TRY(cudaFuncSetAttribute(k_set_kmer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
-  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmWindow, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
@@ -775,7 +773,8 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       // literals) fill the per-tile candidate lists: 24 / 16 KB tiles measured 15-25 % faster there and 4-15 % slower on
       // sparse literals (gpurun_out/r2o_ab_rows*.txt)
       em.rows = ca.strategy == ScanStrategy::Generic ? 48u : (ca.strategy == ScanStrategy::Literal && dp->needle_len == 1 ? 32u : kEmRows);
-      if (const char* env = getenv("RJ_EM_TILE_ROWS")) em.rows = (uint32_t)std::max(4, std::min<int>(atoi(env), (int)kEmRows));
+      // (Tiles up to a quarter smaller so that the last round of tiles is full — 500 MB in 32 KB tiles is 3.22 rounds —
+      // measured no better on the literal scans and 12 % worse on the generic ones: r2v against r2p.)
       const uint64_t tile_bytes = (uint64_t)em.rows * 512;
       em.tile0 = first_start / tile_bytes;
       em.ntiles = std::max<uint64_t>(last_pos / tile_bytes, em.tile0) - em.tile0 + 1;
@@ -794,15 +793,11 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       lit.needle = dp->needle;
       lit.m = dp->needle_len; lit.p4 = dp->p4; lit.pmask = dp->pmask;
       lit.win_lo = ca.window_lo; lit.win_hi = ca.window_hi;
-      static const bool no_deep = getenv("RJ_EM_DEPTH4") != nullptr;          // (tuning: the four-row literal kernels)
-      const bool deep = ca.strategy == ScanStrategy::Literal && !no_deep;      // eight rows in flight, three CTAs per SM
-      const int blocks = (int)std::min<uint64_t>((em.ntiles + kEmWarps - 1) / kEmWarps, (uint64_t)c->sm_count * (deep ? 3 : 4));
+      // (eight rows in flight — 80 registers, three CTAs per SM — measured 4.1 TB/s against 4.5 TB/s for four rows and four
+      // CTAs on a 2 GB text: the literal filter is bound by the integer pipe, not by the loads in flight)
+      const int blocks = (int)std::min<uint64_t>((em.ntiles + kEmWarps - 1) / kEmWarps, (uint64_t)c->sm_count * 4);
       if (ca.strategy == ScanStrategy::Literal) {
-        if (dp->needle_len >= 4 && deep)
-          k_scan_emit<kEmLiteral, true, 8><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
-        else if (deep)
-          k_scan_emit<kEmLiteral, false, 8><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
-        else if (dp->needle_len >= 4)
+        if (dp->needle_len >= 4)
           k_scan_emit<kEmLiteral, true, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
         else
           k_scan_emit<kEmLiteral, false, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);

@@ -110,6 +110,18 @@ int main() {
     snprintf(name, sizeof name, "warp tiles of %u rows, 8 in flight, 4 CTAs/SM", rows);
     time(name, [&] { k_tiles<<<sms * 4, 256>>>(a, n16, rows, ticket, sink, 8); }, bytes);
   }
+  // the same tiling with dynamic shared memory allocated (not used): does the L1 that is left bound the loads in flight?
+  for (int kb : {0, 16, 32, 48, 55}) {
+    char name[96];
+    snprintf(name, sizeof name, "warp tiles of 64 rows, 4 in flight, %d KB smem/CTA", kb);
+    cudaFuncSetAttribute(k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+    time(name, [&] { k_tiles<<<sms * 4, 256, kb * 1024>>>(a, n16, 64, ticket, sink, 4); }, bytes);
+  }
+  for (int kb : {48}) {
+    char name[96];
+    snprintf(name, sizeof name, "warp tiles of 64 rows, 8 in flight, %d KB smem/CTA, 3 CTAs/SM", kb);
+    time(name, [&] { k_tiles<<<sms * 3, 256, kb * 1024>>>(a, n16, 64, ticket, sink, 8); }, bytes);
+  }
   // the same at 500 MB (the C3 text): three tiles of 64 rows per warp
   const size_t small16 = 500000000ull / 16;
   time("500 MB: linear read, 4 loads in flight", [&] { k_linear<4><<<sms * 8, 256>>>(a, small16, sink); }, 5e8);
