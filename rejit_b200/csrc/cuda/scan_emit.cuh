@@ -394,89 +394,56 @@ __device__ __forceinline__ void EmPublish(uint4* rec, uint32_t tag, uint64_t cou
 
 // Called by a whole warp.  Returns (in every lane) the number of matches in the tiles before `t` and the chain
 // state that arrives at the tile (the state after the last match before it, or the call's carry).
-// A step looks at the 32 x kEmLookK records before the tile, kEmLookK per lane, all loads in flight together.  The
-// inclusive records advance along the text by one step's worth of tiles per L2 round trip at best, whatever the
-// number of warps: with 32 records per step and 32 KB tiles that was ~1.5 TB/s, and the bound of every text whose
-// tiles all hold matches (C4 over 5 GB: 1.3 TB/s against 2.0 TB/s for its first 500 MB).
-constexpr int kEmLookK = 4;
+// (A step that looks at 128 records, four per lane with their loads in flight together, was tried against the idea
+// that the inclusive records advance by one step's worth of tiles per L2 round trip: it halved the throughput of
+// every text with matches in all tiles — four times the polling reads on the lines the publishers are writing.)
 __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint64_t* before, EmState* arriving) {
   const int lane = threadIdx.x & 31;
-  const uint32_t want = em.seq & 0x3FFFFFFFu;
   uint64_t excl = 0;
   EmState st;
   st.cur = 0; st.ne = 0;
   bool have = false;
-  for (int64_t base = (int64_t)t;; base -= 32 * kEmLookK) {
-    // my records, nearest first: base - 1 - (lane * kEmLookK + k)
-    const int64_t idx0 = base - 1 - (int64_t)lane * kEmLookK;
-    uint4 ra[kEmLookK], rb[kEmLookK];
-    unsigned pending = 0;
-#pragma unroll
-    for (int k = 0; k < kEmLookK; ++k) {
-      ra[k] = rb[k] = make_uint4(0, 0, 0, 0);
-      if (idx0 - k >= 0) pending |= 1u << k;
-    }
-    for (uint32_t polls = 0; pending; ++polls) {
-      if (polls == (1u << 20)) {                   // a predecessor that never reports would hang the device: give up,
-        atomicOr(&em.sync[2], kFinOverlap | kFinStuck);        // the host runs the general path and says so
-#pragma unroll
-        for (int k = 0; k < kEmLookK; ++k)
-          if ((pending >> k) & 1u) { ra[k] = make_uint4(0, 0, (want << 2) | 2u, 0); rb[k] = ra[k]; }
-        break;
-      }
-#pragma unroll
-      for (int k = 0; k < kEmLookK; ++k)
-        if ((pending >> k) & 1u) {
-          const uint4* rec = em.records + 2 * (uint64_t)(idx0 - k);
-          ra[k] = EmLoad16(rec);
-          rb[k] = EmLoad16(rec + 1);
+  for (int64_t base = (int64_t)t;; base -= 32) {
+    const int64_t idx = base - 1 - lane;
+    uint64_t cnt = 0, cur = 0;
+    uint32_t state = 0, ne = 0, has = 0;
+    if (idx >= 0) {
+      const uint4* rec = em.records + 2 * (uint64_t)idx;
+      for (uint32_t polls = 0;; ++polls) {
+        if (polls == (1u << 20)) {                 // a predecessor that never reports would hang the device: give up,
+          atomicOr(&em.sync[2], kFinOverlap | kFinStuck);      // the host runs the general path and says so
+          state = 2;
+          break;
         }
-#pragma unroll
-      for (int k = 0; k < kEmLookK; ++k)
-        if (((pending >> k) & 1u) && ra[k].z == rb[k].z && (ra[k].z >> 2) == want && (ra[k].z & 3u) != 0) pending &= ~(1u << k);
-      if (pending) {
+        const uint4 a = EmLoad16(rec), b = EmLoad16(rec + 1);
+        if (a.z == b.z && (a.z >> 2) == (em.seq & 0x3FFFFFFFu) && (a.z & 3u) != 0) {
+          state = a.z & 3u;
+          cnt = (uint64_t)a.y << 32 | a.x;
+          cur = (uint64_t)(b.y & 0x3FFFFFFFu) << 32 | b.x;
+          ne = b.y >> 31;
+          has = (b.y >> 30) & 1u;
+          break;
+        }
         // (a short clock-counting spin: __nanosleep(64) here made the chain of look-backs 20-60 % slower on texts
         // with matches, measured — the wake-up granularity is far above the L2 round trip the poll waits for)
         const long long t0 = clock64();
         while (clock64() - t0 < 64) {}
       }
+    } else if (idx == -1) {                        // before the first tile: nothing counted, the call's carry
+      state = 2;
+      cur = em.carry_in.cur;
+      ne = (em.carry_in.tail == em.carry_in.cur) ? 1u : 0u;
+      has = 1;
+    } else {
+      state = 2;                                   // further back: nothing
     }
-    // my records up to and including the first inclusive one
-    uint64_t sum = 0, cur = 0;
-    uint32_t ne = 0, has = 0;
-    bool stopped = false;
-#pragma unroll
-    for (int k = 0; k < kEmLookK; ++k) {
-      const int64_t idx = idx0 - k;
-      uint64_t cnt_k = 0, cur_k = 0;
-      uint32_t state_k, ne_k = 0, has_k = 0;
-      if (idx >= 0) {
-        state_k = ra[k].z & 3u;
-        cnt_k = (uint64_t)ra[k].y << 32 | ra[k].x;
-        cur_k = (uint64_t)(rb[k].y & 0x3FFFFFFFu) << 32 | rb[k].x;
-        ne_k = rb[k].y >> 31;
-        has_k = (rb[k].y >> 30) & 1u;
-      } else if (idx == -1) {                      // before the first tile: nothing counted, the call's carry
-        state_k = 2;
-        cur_k = em.carry_in.cur;
-        ne_k = (em.carry_in.tail == em.carry_in.cur) ? 1u : 0u;
-        has_k = 1;
-      } else {
-        state_k = 2;                               // further back: nothing
-      }
-      if (!stopped) {
-        sum += cnt_k;
-        if (!has && has_k) { has = 1; cur = cur_k; ne = ne_k; }
-        if (state_k == 2) stopped = true;
-      }
-    }
-    const uint32_t incl_mask = __ballot_sync(kFullMask, stopped);
+    const uint32_t incl_mask = __ballot_sync(kFullMask, state == 2);
     const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;
     const bool use = lane <= stop;
-    uint64_t part = use ? sum : 0;
+    uint64_t sum = use ? cnt : 0;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(kFullMask, part, d);
-    excl += part;
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
+    excl += sum;
     const uint32_t st_mask = __ballot_sync(kFullMask, use && has);
     if (!have && st_mask) {
       const int src = __ffs(st_mask) - 1;
@@ -493,9 +460,10 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint6
 // ===========================================================================
 // the kernel: every warp is on its own
 // ===========================================================================
-// kDepth rows in flight per warp (four everywhere: the same tiling with an empty loop body reads 6.9 TB/s,
-// scripts/probe/read_bw.cu, so the loads in flight are not the bound; eight rows — sixteen more registers, three CTAs
-// per SM — were slower on every text size, gpurun_out/r2u_size_sweep*.txt).
+// kDepth rows in flight per warp.  A warp asks for a new row only when it has looked at one, so its time per row is
+// the memory latency / kDepth PLUS its own instructions: with four rows the literal kernels ran at 4.0 TB/s where the
+// same tiling with an empty loop body reads 6.9 TB/s (scripts/probe/read_bw.cu); eight rows cost sixteen registers
+// (three CTAs per SM instead of four).  The window / generic kernels are at their register limit with four.
 template <int kMode, bool kFull4, int kDepth>
 __global__ void __launch_bounds__(kEmThreads, kDepth > 4 ? 3 : 4)
 k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables nfa, EmFilter flt, ScanRange range,

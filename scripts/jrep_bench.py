@@ -85,7 +85,8 @@ def main():
         os.makedirs(tree)
         total = make_tree(tree, args.bytes, args.files)
         pattern = ";\n}"
-        ours_cmd = [exe, "-H", "-n", "-r", pattern, tree] + (["--gpus=%d" % args.gpus] if args.gpus > 1 else [])
+        stagers = max(1, min(16, (os.cpu_count() or 2) - 2))                # threads that read files into the pinned blob
+        ours_cmd = [exe, "-H", "-n", "-r", "-j%d" % stagers, pattern, tree] + (["--gpus=%d" % args.gpus] if args.gpus > 1 else [])
         env = dict(os.environ, JREP_TRACE="1")
         run(ours_cmd, os.path.join(base, "warm.out"), env=env, reps=1)                   # context, kernels, page cache
         t_ours, trace = run(ours_cmd, os.path.join(base, "ours.out"), env=env)
