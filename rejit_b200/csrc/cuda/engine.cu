@@ -2046,21 +2046,29 @@ void StitchClose(int device) {
 namespace {
 bool WaitStitchReport(DeviceContext* c, unsigned int step, int K, Carry* arrived, uint32_t* redo_mask, std::string* error) {
   volatile StitchReport* r = c->h_stitch;
+  // every record carries the step: the head and the K records are complete once each shows it (one 16-byte store each)
+  auto complete = [&]() {
+    if (r->head.w != step) return false;
+    for (int j = 0; j < K; ++j) if (r->rec[j].z != step) return false;
+    return true;
+  };
   uint64_t spins = 0;
-  while (r->step != step) {
+  while (!complete()) {
     if ((++spins & 0x3FFF) == 0) {
       cudaError_t q = cudaStreamQuery(c->stream);
-      if (q == cudaSuccess) { if (r->step == step) break; if (error) *error = "rejit_b200: the stitch did not report"; return false; }
+      if (q == cudaSuccess) { if (complete()) break; if (error) *error = "rejit_b200: the stitch did not report"; return false; }
       if (q != cudaErrorNotReady) { Check(q, "cudaStreamQuery", error); return false; }
     }
   }
   std::atomic_thread_fence(std::memory_order_acquire);
-  if (r->status & 2u) { if (error) *error = "rejit_b200: a neighbouring rank did not answer the stitch"; return false; }
+  const unsigned int redo = r->head.x, status = r->head.y, ne = r->head.z;
+  if (status & 2u) { if (error) *error = "rejit_b200: a neighbouring rank did not answer the stitch"; return false; }
   for (int j = 0; j < K; ++j) {
-    arrived[j].cur = r->arrived_cur[j];
-    arrived[j].tail = ((r->arrived_ne >> j) & 1u) ? r->arrived_cur[j] : kNoMatch;
+    const uint64_t cur = (uint64_t)r->rec[j].y << 32 | r->rec[j].x;
+    arrived[j].cur = cur;
+    arrived[j].tail = ((ne >> j) & 1u) ? cur : kNoMatch;
   }
-  *redo_mask = r->redo;
+  *redo_mask = redo;
   return true;
 }
 }  // namespace
@@ -2105,7 +2113,8 @@ bool StitchExchange(int device, int K, const Carry* leaving, uint64_t slab_begin
   if (!step) step = ++c->stitch_step ? c->stitch_step : ++c->stitch_step;
   a.link.step = step;
   a.link.report = c->h_stitch_dev;
-  c->h_stitch->step = 0;                                     // (a fused attempt of the same step may have reported already)
+  c->h_stitch->head.w = 0;                                   // (a fused attempt of the same step may have reported already)
+  for (int j = 0; j < 32; ++j) c->h_stitch->rec[j].z = 0;
   std::atomic_thread_fence(std::memory_order_release);
   k_stitch<<<1, 32, 0, c->stream>>>(a);
   RJ_TRY(cudaGetLastError());

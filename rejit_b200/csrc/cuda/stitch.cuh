@@ -22,12 +22,15 @@ constexpr uint32_t kStitchSlots = 64;
 constexpr uint32_t kStitchAckWord = kStitchSlots * 32 * 4;               // index (in words) of the ack word
 constexpr uint32_t kStitchInboxBytes = kStitchSlots * 32 * 16 + 64;
 
-struct StitchReport {                   // mapped host memory, one per device context
-  unsigned long long arrived_cur[32];   // global offset where the chain arriving from the left lets a match begin (0: none)
-  unsigned int arrived_ne;              // bit j: that chain's last match was non-empty
-  unsigned int redo;                    // bit j: the arriving chain of pattern j reaches into the slab
-  unsigned int status;                  // 1: sent as invalid (send again), 2: a neighbour did not answer
-  unsigned int step;                    // written last
+// Mapped host memory, one per device context.  Every 16-byte record carries the step it belongs to and is written with
+// ONE store, so the host needs no ordering between them and the kernel no system-scope fence (two of those — one after
+// the peer store, one before the report — were 3-4 us of every step).
+struct StitchReport {
+  uint4 rec[32];                        // [j] = {cur lo, cur hi, step, 0}: global offset where the chain arriving from the
+                                        // left lets a match of pattern j begin (0: none)
+  uint4 head;                           // {redo, status, arrived_ne, step}: bit j of redo: that chain reaches into the slab;
+                                        // status 1: sent as invalid (send again), 2: a neighbour did not answer;
+                                        // bit j of arrived_ne: that chain's last match was non-empty
 };
 
 struct StitchLink {                     // where to send, where to listen (kernel parameter)
@@ -62,7 +65,7 @@ __device__ __forceinline__ void StitchExchangeWarp(const StitchLink& a, int K, u
       if (polls > (1u << 22)) { status |= 2u; break; }
     if (lane < K)
       StitchStore16(a.right_inbox + slot + lane, (uint32_t)cur, (uint32_t)(cur >> 32) | (ne << 31) | (has << 30), a.step, invalid);
-    __threadfence_system();
+    // (no fence: a record is one 16-byte store that carries its own step number)
   }
   // ---- what arrives from the left (an `invalid` record is followed by a valid one for the same step) ------
   unsigned long long arr = 0;
@@ -88,16 +91,9 @@ __device__ __forceinline__ void StitchExchangeWarp(const StitchLink& a, int K, u
   const bool redo = arr_has && (arr > a.slab_begin || (arr_ne && arr == a.slab_begin));
   const uint32_t redo_mask = __ballot_sync(0xFFFFFFFFu, redo), arr_ne_mask = __ballot_sync(0xFFFFFFFFu, arr_ne != 0);
   status = __reduce_or_sync(0xFFFFFFFFu, status);
-  volatile StitchReport* r = a.report;
-  r->arrived_cur[lane] = arr_has ? arr : 0ull;
-  __syncwarp();
-  if (lane == 0) {
-    r->arrived_ne = arr_ne_mask;
-    r->redo = redo_mask;
-    r->status = status;
-    __threadfence_system();
-    r->step = a.step;
-  }
+  const unsigned long long rep = arr_has ? arr : 0ull;
+  StitchStore16(a.report->rec + lane, (uint32_t)rep, (uint32_t)(rep >> 32), a.step, 0u);
+  if (lane == 0) StitchStore16(&a.report->head, redo_mask, status, arr_ne_mask, a.step);
 }
 
 struct StitchArgs {                     // k_stitch: the host hands over the leaving states
