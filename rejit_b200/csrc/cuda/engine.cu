@@ -778,9 +778,11 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       const uint64_t tile_bytes = (uint64_t)em.rows * 512;
       em.tile0 = first_start / tile_bytes;
       em.ntiles = std::max<uint64_t>(last_pos / tile_bytes, em.tile0) - em.tile0 + 1;
-      if (!c->em_records.Reserve(em.ntiles * 32 + 64, error)) return false;
+      const uint64_t n_groups = (em.ntiles + 31) / 32;
+      if (!c->em_records.Reserve((em.ntiles + n_groups) * 32 + 64, error)) return false;
       uint8_t* base = static_cast<uint8_t*>(c->status.p);
       em.records = c->em_records.as<uint4>();
+      em.group_records = em.records + 2 * em.ntiles;
       em.sync = reinterpret_cast<unsigned int*>(base + kFinSyncOffset);
       em.final_state = reinterpret_cast<unsigned long long*>(base + kFinLastOffset);
       em.out_pairs = outp;

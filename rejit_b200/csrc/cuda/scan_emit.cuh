@@ -90,7 +90,8 @@ struct EmFilter {
 };
 
 struct EmitArgs {
-  uint4* records;                   // [ntiles][2]: look-back records
+  uint4* records;                   // [ntiles][2]: what every tile found
+  uint4* group_records;             // [ceil(ntiles / 32)][2]: groups of 32 tiles (own numbers, then inclusive)
   unsigned int* sync;               // [0..1] ticket (64 bit), [2] flags, [3] tiles done; zeroed by the host before the launch
   unsigned long long* final_state;  // [3]: total matches, chain state (cur, non-empty); written by the last tile
   uint64_t tile0, ntiles;           // tiles [tile0, tile0 + ntiles) hold every owned start (and needle hit)
@@ -397,7 +398,15 @@ __device__ __forceinline__ void EmPublish(uint4* rec, uint32_t tag, uint64_t cou
 // (A step that looks at 128 records, four per lane with their loads in flight together, was tried against the idea
 // that the inclusive records advance by one step's worth of tiles per L2 round trip: it halved the throughput of
 // every text with matches in all tiles — four times the polling reads on the lines the publishers are writing.)
-__device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint64_t* before, EmState* arriving) {
+//
+// Two levels (round 2c).  With one level, the inclusive records advance along the text by at most 32 tiles per L2
+// round trip whatever the number of warps: ~1.5-2 TB/s with 32 KB tiles, and the bound of every long text whose
+// tiles all hold matches (C4: 2.0 TB/s over 500 MB, 1.3 TB/s over 5 GB).  Now a tile record only ever says what the
+// tile itself found; the LAST tile of every group of 32 adds its group's records up and publishes a GROUP record
+// (own numbers first, then — after a look-back over the group records before it, 32 groups = 1024 tiles per step —
+// everything up to and including the group).  A tile's prefix = the tiles before it in its group + the groups before.
+__device__ __forceinline__ void EmLookBack(const EmitArgs& em, const uint4* records, uint64_t t, uint64_t* before, EmState* arriving,
+                                           bool* found) {
   const int lane = threadIdx.x & 31;
   uint64_t excl = 0;
   EmState st;
@@ -408,7 +417,7 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint6
     uint64_t cnt = 0, cur = 0;
     uint32_t state = 0, ne = 0, has = 0;
     if (idx >= 0) {
-      const uint4* rec = em.records + 2 * (uint64_t)idx;
+      const uint4* rec = records + 2 * (uint64_t)idx;
       for (uint32_t polls = 0;; ++polls) {
         if (polls == (1u << 20)) {                 // a predecessor that never reports would hang the device: give up,
           atomicOr(&em.sync[2], kFinOverlap | kFinStuck);      // the host runs the general path and says so
@@ -455,6 +464,38 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, uint64_t t, uint6
   }
   *before = excl;
   *arriving = st;
+  *found = have;
+}
+
+// The tiles of tile t's group that come before it (t & 31 of them, one per lane): their matches, and the chain state
+// after the last match among them (*found: there is one).
+__device__ __forceinline__ void EmGroupBefore(const EmitArgs& em, uint64_t t, uint32_t* before, EmState* after, bool* found) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t j = (uint32_t)t & 31u;
+  uint32_t cnt = 0, ne = 0, has = 0;
+  uint64_t cur = 0;
+  if ((uint32_t)lane < j) {
+    const uint4* rec = em.records + 2 * (t - j + lane);
+    for (uint32_t polls = 0;; ++polls) {
+      if (polls == (1u << 20)) { atomicOr(&em.sync[2], kFinOverlap | kFinStuck); break; }
+      const uint4 a = EmLoad16(rec), b = EmLoad16(rec + 1);
+      if (a.z == b.z && (a.z >> 2) == (em.seq & 0x3FFFFFFFu) && (a.z & 3u) != 0) {
+        cnt = a.x;                                 // (a tile holds at most kEmCandCap matches)
+        cur = (uint64_t)(b.y & 0x3FFFFFFFu) << 32 | b.x;
+        ne = b.y >> 31;
+        has = (b.y >> 30) & 1u;
+        break;
+      }
+      const long long t0 = clock64();
+      while (clock64() - t0 < 64) {}
+    }
+  }
+  *before = __reduce_add_sync(kFullMask, cnt);
+  const uint32_t st_mask = __ballot_sync(kFullMask, has != 0);
+  const int src = st_mask ? 31 - __clz(st_mask) : 0;        // the nearest tile before me with a match
+  after->cur = __shfl_sync(kFullMask, cur, src);
+  after->ne = __shfl_sync(kFullMask, ne, src);
+  *found = st_mask != 0;
 }
 
 // ===========================================================================
@@ -482,6 +523,13 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
   // a literal window begins up to three bytes before a lane's 16: rows are scanned up to the one that holds n + 2
   const uint64_t scan_end = kMode == kEmGeneric ? n : n + 3;
 
+  // the survivors are evaluated when their list reaches this length (and after the tile's last row).  Generic scans
+  // re-read the text around every start (line context, NFA run): evaluated early, those bytes are still in L2 — at the
+  // end of a 24 KB tile, with 4736 tiles in flight, half of them had been evicted (DRAM traffic 1.8 x the text).
+#ifndef RJ_EM_GEN_STOP
+#define RJ_EM_GEN_STOP kEmEntCap
+#endif
+  constexpr uint32_t kEntStop = kMode == kEmGeneric ? (uint32_t)(RJ_EM_GEN_STOP) : kEmEntCap;
   const uint32_t tile_rows = em.rows, tile_bytes = em.rows * 512u;
   unsigned long long next_ticket = 0;
   if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
@@ -557,7 +605,7 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
 #pragma unroll 1
       for (;;) {
 #pragma unroll 1
-        for (; r + kDepth <= rows && n_ent + 32 * kDepth <= kEmEntCap; r += kDepth) {
+        for (; r + kDepth <= rows && n_ent + 32 * kDepth <= kEntStop; r += kDepth) {
           if (!asked && r + kDepth + 8 >= rows) {
             asked = true;
             if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
@@ -643,19 +691,31 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
     const uint32_t tag = (em.seq & 0x3FFFFFFFu) << 2;
     if (lane == 0) EmPublish(rec, tag | 1u, cnt, cnt != 0, mine_out);
     // A tile without matches needs nothing from its predecessors — no place for matches, no seam — and its own record
-    // already says all there is to say about it: it does not look back at all.  Every 32nd tile does, so that a
-    // tile with matches finds an inclusive record within a step or two (a look-back blocks the warp with no loads in
-    // flight: on a text without hits it was a quarter of the kernel's time).
+    // already says all there is to say about it: it does not look back at all, unless it closes its group (a look-back
+    // blocks the warp with no loads in flight: on a text without hits it was a quarter of the kernel's time).
     uint64_t before = 0;
     EmState arriving;
     arriving.cur = 0; arriving.ne = 0;
-    const bool look = cnt != 0 || (t & 31u) == 31u || t + 1 == em.ntiles;
+    const bool closes_group = (t & 31u) == 31u || t + 1 == em.ntiles;        // the last tile of its group
+    const bool look = cnt != 0 || closes_group;
     if (look) {
-      EmLookBack(em, t, &before, &arriving);
+      uint32_t in_group;
+      EmState st_group, st_before;
+      bool have_group, have_before;
+      uint64_t groups_before;
+      EmGroupBefore(em, t, &in_group, &st_group, &have_group);
+      uint4* grec = em.group_records + 2 * (t >> 5);
+      const uint64_t group_count = (uint64_t)in_group + cnt;
+      const bool group_has = cnt != 0 || have_group;
+      const EmState group_out = cnt ? mine_out : st_group;
+      if (closes_group && lane == 0) EmPublish(grec, tag | 1u, group_count, group_has, group_out);
+      EmLookBack(em, em.group_records, t >> 5, &groups_before, &st_before, &have_before);
+      before = groups_before + in_group;
+      arriving = have_group ? st_group : st_before;
+      if (closes_group && lane == 0) EmPublish(grec, tag | 2u, groups_before + group_count, true, group_has ? group_out : st_before);
       if (cnt && !EmTakes(arriving, tile_base + EmRel(first), EmLen(first))) flags |= kFinOverlap;   // the chain from the left reaches in
     }
     if (lane == 0) {
-      if (look) EmPublish(rec, tag | 2u, before + cnt, true, cnt ? mine_out : arriving);
       if (flags) atomicOr(&em.sync[2], flags);
       if (t + 1 == em.ntiles) {
         const EmState fin = cnt ? mine_out : arriving;

@@ -83,6 +83,13 @@ for c in cases:
                 best = min(best, st.total_ms)
         avg, la = tot / REPS, st.launches
         dt = tx
+    elif c in ("c4big", "litbig"):
+        import torch
+        n = 5_000_000_000
+        t = (W.source_text_range(0, n + 64, device="cuda") if c == "c4big" else W.random_ascii_range(0, n + 64, device="cuda"))
+        r = rj.Regej(W.JREP_PATTERN if c == "c4big" else W.LITERAL_PATTERN)
+        dt = rj.DeviceText(nbytes=n, device=0, borrowed_ptr=t.data_ptr())
+        out, avg, best, la = timed(lambda d, s: r.match_all_device(d, stats=s), dt)
     elif c == "striprep":
         text = np.frombuffer(W.fasta_file(50_000_000), dtype=np.uint8)
         n = len(text)
