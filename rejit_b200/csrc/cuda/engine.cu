@@ -197,6 +197,7 @@ class DeviceContext {
   StitchReport* h_stitch = nullptr;
   StitchReport* h_stitch_dev = nullptr;
   Buffer em_records;                  // look-back records of the single-pass scans (scan_emit.cuh)
+  int em_blocks_per_sm = 0;           // resident CTAs of k_scan_emit per SM (asked once)
   bool emit = true;                   // single-pass scan + emit available (RJ_NO_EMIT=1: the round-1 pipelines only)
   PipelineStatus* h_status = nullptr; // pinned + mapped: the resolve kernel writes it, the host spins on seq
   PipelineStatus* h_status_dev = nullptr;   // device view of h_status
@@ -797,17 +798,33 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       lit.win_lo = ca.window_lo; lit.win_hi = ca.window_hi;
       // (eight rows in flight — 80 registers, three CTAs per SM — measured 4.1 TB/s against 4.5 TB/s for four rows and four
       // CTAs on a 2 GB text: the literal filter is bound by the integer pipe, not by the loads in flight)
-      const int blocks = (int)std::min<uint64_t>((em.ntiles + kEmWarps - 1) / kEmWarps, (uint64_t)c->sm_count * 4);
-      if (ca.strategy == ScanStrategy::Literal) {
-        if (dp->needle_len >= 4)
-          k_scan_emit<kEmLiteral, true, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
-        else
-          k_scan_emit<kEmLiteral, false, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
-      } else if (ca.strategy == ScanStrategy::LiteralWindow) {
-        k_scan_emit<kEmWindow, true, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
-      } else {
-        k_scan_emit<kEmGeneric, true, 4><<<blocks, kEmThreads, kEmSmemBytes, s>>>(d_text, n, lit, dp->nfa, dp->em_filter, slab.own, em);
+      const void* fn = ca.strategy == ScanStrategy::Literal
+                           ? (dp->needle_len >= 4 ? (const void*)k_scan_emit<kEmLiteral, true, 4> : (const void*)k_scan_emit<kEmLiteral, false, 4>)
+                           : ca.strategy == ScanStrategy::LiteralWindow ? (const void*)k_scan_emit<kEmWindow, true, 4>
+                                                                        : (const void*)k_scan_emit<kEmGeneric, true, 4>;
+      // CTAs that are resident together (the round-robin deal needs all of them; four per SM by construction, asked once)
+      if (c->em_blocks_per_sm == 0) {
+        int nb = 4;
+        const void* all[4] = {(const void*)k_scan_emit<kEmLiteral, true, 4>, (const void*)k_scan_emit<kEmLiteral, false, 4>,
+                              (const void*)k_scan_emit<kEmWindow, true, 4>, (const void*)k_scan_emit<kEmGeneric, true, 4>};
+        for (const void* f : all) {
+          int k = 0;
+          RJ_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, f, (int)kEmThreads, kEmSmemBytes));
+          nb = std::min(nb, k);
+        }
+        c->em_blocks_per_sm = std::max(1, nb);
       }
+      const int blocks = (int)std::min<uint64_t>((em.ntiles + kEmWarps - 1) / kEmWarps, (uint64_t)c->sm_count * c->em_blocks_per_sm);
+      // Round robin needs every CTA of the grid resident at once: the grid is never larger than what the occupancy
+      // calculator says fits.  A plain launch, not a cooperative one: cudaLaunchCooperativeKernel costs this kernel
+      // 20 us (0.130 vs 0.110 ms for 500 MB), and a look-back that waits in vain (another client of the GPU holding SMs
+      // for good) times out, raises kFinStuck and sends the call to the general path.  RJ_EM_TICKETS=1: the ticket counter.
+      static const bool tickets = getenv("RJ_EM_TICKETS") != nullptr;
+      em.static_stride = tickets ? 0u : (uint32_t)blocks * kEmWarps;
+      uint64_t n_arg = n;
+      ScanRange own_arg = slab.own;
+      void* kargs[] = {(void*)&d_text, (void*)&n_arg, (void*)&lit, (void*)&dp->nfa, (void*)&dp->em_filter, (void*)&own_arg, (void*)&em};
+      RJ_TRY(cudaLaunchKernel(fn, dim3(blocks), dim3(kEmThreads), kargs, kEmSmemBytes, s));
       fused = true;
       if (stats) stats->launches += 1;
     } else
@@ -1528,6 +1545,7 @@ int MatchAllSetResident(int device, SetProgram* set, const uint8_t* d_text, uint
           for (int j = 0; j < K; ++j) if (carries.c[j].cur != 0) run.has_carry = 1;
           int k_arg = K;
           void* kargs[] = {(void*)&d_text, (void*)&n_arg, (void*)&k_arg, (void*)&ds->km, (void*)&own, (void*)&run, (void*)&carries};
+          // (a plain launch was measured too: no difference for this kernel, unlike k_scan_emit)
           if (!Check(cudaLaunchCooperativeKernel((const void*)k_set_kmer, dim3(blocks), dim3(kKmerThreads), kargs, kmer_smem, s),
                      "cooperative launch", error)) return -1;
           if (stats) { cudaEventRecord(c->ev[1], s); stats->launches += 1; }

@@ -95,6 +95,7 @@ struct EmitArgs {
   unsigned int* sync;               // [0..1] ticket (64 bit), [2] flags, [3] tiles done; zeroed by the host before the launch
   unsigned long long* final_state;  // [3]: total matches, chain state (cur, non-empty); written by the last tile
   uint64_t tile0, ntiles;           // tiles [tile0, tile0 + ntiles) hold every owned start (and needle hit)
+  uint32_t static_stride;           // warps of the grid when the tiles are dealt round robin, 0: ticket counter
   uint32_t rows;                    // rows of 512 bytes per tile (<= kEmRows; the host picks: dense candidates want smaller tiles)
   uint64_t* out_pairs;
   uint64_t out_cap, base_offset;
@@ -531,8 +532,14 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
 #endif
   constexpr uint32_t kEntStop = kMode == kEmGeneric ? (uint32_t)(RJ_EM_GEN_STOP) : kEmEntCap;
   const uint32_t tile_rows = em.rows, tile_bytes = em.rows * 512u;
+  // Tiles are dealt round robin (em.static_stride = warps of the grid; the host launches no more CTAs than are resident
+  // together, so the warp that owns a tile someone looks back at is running) or, with static_stride == 0, taken from a
+  // ticket counter.  One counter for 4736 warps was the largest single cost of the no-hit scan: 3.9 -> 4.6 TB/s at
+  // 500 MB, 4.4 -> 5.1 TB/s at 5 GB, C4 over 5 GB 1.4 -> 2.0 TB/s (profiles/r2_ab_scan_emit.txt).
+  const unsigned long long stride = em.static_stride;
   unsigned long long next_ticket = 0;
-  if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
+  if (stride) next_ticket = (unsigned long long)blockIdx.x * kEmWarps + warp;
+  else if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
   for (;;) {
     const uint64_t t = __shfl_sync(kFullMask, next_ticket, 0);
     if (t >= em.ntiles) break;
@@ -608,7 +615,7 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
         for (; r + kDepth <= rows && n_ent + 32 * kDepth <= kEntStop; r += kDepth) {
           if (!asked && r + kDepth + 8 >= rows) {
             asked = true;
-            if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
+            if (!stride && lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
           }
 #pragma unroll
           for (int u = 0; u < kDepth; ++u) row(v[u], r + u);
@@ -643,7 +650,8 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
         if (r >= rows) break;
       }
     }
-    if (!asked && lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
+    if (stride) next_ticket = t + stride;
+    else if (!asked && lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
     flags = __reduce_or_sync(kFullMask, flags);
     if (flags) cnt = 0;
     // ---- does every candidate begin after its predecessor ended?  Else one lane walks the chain ----------------

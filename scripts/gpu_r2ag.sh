@@ -1,0 +1,9 @@
+#!/bin/bash
+# Round 2, call AG: tiles dealt round robin under a cooperative launch.
+set -u
+mkdir -p gpurun_out
+python __graft_entry__.py > gpurun_out/build.log 2>&1
+echo "== tests"
+timeout 1500 python -m pytest tests -x -q -m gpu --timeout 1000 2>&1 | tail -8 | tee gpurun_out/r2ag_pytest.log
+echo "== ab_run"
+timeout 900 python scripts/ab_run.py lit c3 c3hits c4 b hat strip striprep c4big litbig 2>&1 | tail -11 | tee gpurun_out/r2ag_ab.txt
