@@ -537,12 +537,16 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
   // ticket counter.  One counter for 4736 warps was the largest single cost of the no-hit scan: 3.9 -> 4.6 TB/s at
   // 500 MB, 4.4 -> 5.1 TB/s at 5 GB, C4 over 5 GB 1.4 -> 2.0 TB/s (profiles/r2_ab_scan_emit.txt).
   const unsigned long long stride = em.static_stride;
+  unsigned int done_mine = 0;                               // (lane 0) tiles this warp has finished and not yet reported
   unsigned long long next_ticket = 0;
   if (stride) next_ticket = (unsigned long long)blockIdx.x * kEmWarps + warp;
   else if (lane == 0) next_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(em.sync), 1ull);
   for (;;) {
     const uint64_t t = __shfl_sync(kFullMask, next_ticket, 0);
-    if (t >= em.ntiles) break;
+    if (t >= em.ntiles) {
+      if (lane == 0 && done_mine) atomicAdd(&em.sync[3], done_mine);
+      break;
+    }
     const uint64_t tile_lo = (em.tile0 + t) * tile_bytes;
     const uint64_t tile_base = tile_lo >= kEmBias ? tile_lo - kEmBias : 0;
     const uint64_t mine = tile_lo + (uint64_t)lane * 16;
@@ -747,11 +751,15 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
     // last tile's totals must be visible to the reporter, and the host reads the pairs after the kernel has ended)
     // Every tile counts itself done with a reduction nobody waits for; the warp of the LAST tile waits until all
     // have (it is the last to start, so not for long) and reports.  A tile that raised a flag makes it visible first.
+    // (a warp adds up its finished tiles and tells the counter once, when it leaves or when it holds the last tile:
+    // one reduction per tile on one address was 150 k of them for a 5 GB text)
     if (lane == 0) {
       if (flags) __threadfence();
       if (t + 1 != em.ntiles) {
-        atomicAdd(&em.sync[3], 1u);
+        ++done_mine;
       } else {
+        if (done_mine) atomicAdd(&em.sync[3], done_mine);
+        done_mine = 0;
         __threadfence();
         const volatile unsigned int* done = em.sync + 3;
         for (uint32_t polls = 0; (uint64_t)*done + 1 < em.ntiles; ++polls) {
