@@ -56,9 +56,15 @@ class ShmExchange:
     name = "shm"
 
     def __init__(self, rank: int, world: int, words: int, key: str, timeout_s: float = 60.0):
+        import platform
         import time
         import numpy as np
         from multiprocessing import shared_memory
+        # record, then sequence number, with plain numpy stores: that order is only kept by x86 (total store order);
+        # on a weakly ordered host (Grace) a reader could see the new number with a stale record
+        if platform.machine().lower() not in ("x86_64", "amd64", "i686", "i386"):
+            raise RuntimeError("ShmExchange relies on x86 store ordering: use the device-side stitch or NcclExchange on %s"
+                               % platform.machine())
         self.rank, self.world, self.words = rank, world, words
         size = world * 2 * (1 + words) * 8
         name = "rejit_b200_" + key
