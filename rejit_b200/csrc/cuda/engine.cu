@@ -583,6 +583,7 @@ bool EnsureKernelAttributes(DeviceContext* c, std::string* error) {
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmLiteral, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmWindow, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmGeneric, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
+  RJ_TRY(cudaFuncSetAttribute(k_scan_emit<kEmGeneric, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmSmemBytes));
   c->attr_done = true;
   return true;
 }
@@ -676,9 +677,19 @@ int DfaTmaWarps(const DeviceContext* c, const DfaTables& dfa) {
 
 // Runs scan (+verify) + resolve for one slab whose text is at d_text[0..n).
 // Matches are written to d_out (or the context's out_pairs) as global offsets.
+// `rebuild` (optional, ReplaceAll): the single-pass generic scan writes the rebuilt text itself (scan_emit.cuh,
+// EmitArgs::rep_out); done = it did (else the matches are in out_pairs as usual and the caller rebuilds).
+struct FusedRebuild {
+  uint8_t* d_out = nullptr;            // >= n + 64 bytes
+  const uint8_t* d_with = nullptr;     // the replacement, device memory
+  uint32_t with_len = 0;
+  bool done = false;
+  uint64_t removed = 0;                // bytes inside the matches
+};
+
 bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8_t* d_text, uint64_t n,
                  const Slab& slab, const Carry& carry_in, uint64_t* d_out, uint64_t out_cap,
-                 PipelineStatus* result, RunStats* stats, std::string* error) {
+                 PipelineStatus* result, RunStats* stats, std::string* error, FusedRebuild* rebuild = nullptr) {
   const CompiledAutomaton& ca = prog->automaton();
   cudaStream_t s = c->stream;
   RJ_TRY(cudaSetDevice(c->device));
@@ -724,6 +735,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     const bool try_fuse = c->coop && !fa.enabled && (dp->fuse_misses == 0 || (dp->fuse_skips & 31) == 31);
     if (c->coop && !fa.enabled && !try_fuse) dp->fuse_skips++;
     bool fused = false;                 // the scan kernel also produced the matches and the status
+    bool rebuild_launched = false;      // ... and (ReplaceAll) the rebuilt text instead of the match list
     unsigned int fused_seq = 0, hits_seq = 0;
     // largest co-resident grid of a 256-thread kernel with the finish scratch (cached occupancy query)
     auto coop_blocks = [&](const void* fn, int* cache) -> int {
@@ -792,6 +804,9 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       em.host_records = c->h_fin_dev;
       em.seq = fused_seq = ++c->call_seq ? c->call_seq : ++c->call_seq;
       em.carry_in = carry_in;
+      const bool fuse_rebuild = rebuild && rebuild->d_out && ca.strategy == ScanStrategy::Generic;
+      if (fuse_rebuild) { em.rep_out = rebuild->d_out; em.rep_with = rebuild->d_with; em.rep_w = rebuild->with_len; }
+      rebuild_launched = fuse_rebuild;
       EmLit lit{};
       lit.needle = dp->needle;
       lit.m = dp->needle_len; lit.p4 = dp->p4; lit.pmask = dp->pmask;
@@ -801,12 +816,14 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
       const void* fn = ca.strategy == ScanStrategy::Literal
                            ? (dp->needle_len >= 4 ? (const void*)k_scan_emit<kEmLiteral, true, 4> : (const void*)k_scan_emit<kEmLiteral, false, 4>)
                            : ca.strategy == ScanStrategy::LiteralWindow ? (const void*)k_scan_emit<kEmWindow, true, 4>
-                                                                        : (const void*)k_scan_emit<kEmGeneric, true, 4>;
+                           : fuse_rebuild ? (const void*)k_scan_emit<kEmGeneric, true, 4, true>
+                                          : (const void*)k_scan_emit<kEmGeneric, true, 4>;
       // CTAs that are resident together (the round-robin deal needs all of them; four per SM by construction, asked once)
       if (c->em_blocks_per_sm == 0) {
         int nb = 4;
-        const void* all[4] = {(const void*)k_scan_emit<kEmLiteral, true, 4>, (const void*)k_scan_emit<kEmLiteral, false, 4>,
-                              (const void*)k_scan_emit<kEmWindow, true, 4>, (const void*)k_scan_emit<kEmGeneric, true, 4>};
+        const void* all[5] = {(const void*)k_scan_emit<kEmLiteral, true, 4>, (const void*)k_scan_emit<kEmLiteral, false, 4>,
+                              (const void*)k_scan_emit<kEmWindow, true, 4>, (const void*)k_scan_emit<kEmGeneric, true, 4>,
+                              (const void*)k_scan_emit<kEmGeneric, true, 4, true>};
         for (const void* f : all) {
           int k = 0;
           RJ_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, f, (int)kEmThreads, kEmSmemBytes));
@@ -994,7 +1011,7 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
     };
     if (ordered && fused) {
       RJ_TRY(cudaGetLastError());
-      if (!WaitFinRecords(c, 1, fused_seq, error)) return false;
+      if (!WaitFinRecords(c, rebuild_launched ? 2 : 1, fused_seq, error)) return false;
       st = StatusFromRecord(c->h_fin[0], carry_in);
       if (use_emit) {
         // the single-pass scan reports through the same record; when a chain crossed a tile edge (need_large) or a
@@ -1002,6 +1019,24 @@ bool RunPipeline(DeviceContext* c, Program* prog, DeviceProgram* dp, const uint8
         if (st.dense) { dp->emit_off = true; if (stats) stats->reruns += 1; continue; }
         if (st.need_large) { dp->fuse_misses++; dp->fuse_skips = 0; if (stats) stats->reruns += 1; continue; }
         dp->fuse_misses = 0;
+        if (rebuild_launched && !st.overflow) {
+          // the rebuilt text is in place: no match list to make room for, nothing more to run
+          rebuild->done = true;
+          rebuild->removed = c->h_fin[1].n_matches;
+          if (stats) {
+            cudaEventRecord(c->ev[2], s);
+            cudaEventSynchronize(c->ev[2]);
+            cudaEventElapsedTime(&stats->scan_ms, c->ev[0], c->ev[1]);
+            cudaEventElapsedTime(&stats->total_ms, c->ev[0], c->ev[2]);
+            stats->candidates = st.n_candidates;
+            stats->matches = st.n_matches;
+            stats->strategy = (int)ca.strategy;
+          } else {
+            RJ_TRY(cudaStreamSynchronize(s));           // (the report leaves a few microseconds before the last warps do)
+          }
+          *result = st;
+          return true;
+        }
       } else if (ca.strategy == ScanStrategy::LiteralWindow) {
         // outcome of the hit stage (k_gather_hits), published the same way in slot 31
         volatile FinRecord* hr = c->h_fin + 31;
@@ -1814,8 +1849,41 @@ int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint6
   Slab slab{{0, n + 1}, 0};
   PipelineStatus st;
   Carry in;
-  if (!RunPipeline(c, prog, dp, d_text, n, slab, in, nullptr, 0, &st, stats, error)) return -1;
   cudaStream_t s = c->stream;
+  // Generic scans whose every match is at least as long as the replacement (the strip of a FASTA file: `>.*\n|\n` -> "")
+  // write the rebuilt text from the scan kernel itself: one launch, no match list, no lengths / prefix sum / index /
+  // staging passes.  The output is never longer than the text, so it can be allocated before the matches are known.
+  // A call the single-pass scan cannot finish (chains across tile edges, tiles too dense for their lists) comes back
+  // with the matches as usual and is rebuilt below.  RJ_NO_FUSED_REBUILD=1: always the separate passes.
+  static const bool no_fused_rebuild = getenv("RJ_NO_FUSED_REBUILD") != nullptr;
+  const CompiledAutomaton& ca = prog->automaton();
+  if (!no_fused_rebuild && c->emit && !dp->emit_off && !ca.reentrant && ca.strategy == ScanStrategy::Generic &&
+      with_len <= ca.nfa.min_len && n > 0) {
+    FusedRebuild fr;
+    if (!c->with_buf.Reserve(with_len + 16, error)) return -1;
+    RJ_TRY_COUNT(cudaSetDevice(c->device));
+    if (with_len) RJ_TRY_COUNT(cudaMemcpyAsync(c->with_buf.p, with, with_len, cudaMemcpyHostToDevice, s));
+    void* out = DeviceAlloc(device, n + 64, error);
+    if (!out) return -1;
+    fr.d_out = static_cast<uint8_t*>(out);
+    fr.d_with = c->with_buf.as<uint8_t>();
+    fr.with_len = (uint32_t)with_len;
+    if (!RunPipeline(c, prog, dp, d_text, n, slab, in, nullptr, 0, &st, stats, error, &fr)) { DeviceFree(device, out); return -1; }
+    if (fr.done) {
+      if (fr.removed > n + st.n_matches * with_len) {
+        DeviceFree(device, out);
+        if (error) *error = "rejit_b200: the fused rebuild reported an impossible length";
+        return -1;
+      }
+      *d_out = out;
+      *out_len = n - fr.removed + st.n_matches * with_len;
+      if (out_capacity) *out_capacity = n + 64;
+      return (int64_t)st.n_matches;
+    }
+    DeviceFree(device, out);          // (back to the pool; the separate rebuild below asks for the exact size)
+  } else if (!RunPipeline(c, prog, dp, d_text, n, slab, in, nullptr, 0, &st, stats, error)) {
+    return -1;
+  }
   const uint64_t m = st.n_matches;
   const uint64_t* pairs = c->out_pairs.as<uint64_t>();
   if (stats) cudaEventRecord(c->ev[0], s);

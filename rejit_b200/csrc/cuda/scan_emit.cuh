@@ -95,6 +95,13 @@ struct EmitArgs {
   unsigned int* sync;               // [0..1] ticket (64 bit), [2] flags, [3] tiles done; zeroed by the host before the launch
   unsigned long long* final_state;  // [3]: total matches, chain state (cur, non-empty); written by the last tile
   uint64_t tile0, ntiles;           // tiles [tile0, tile0 + ntiles) hold every owned start (and needle hit)
+  // ReplaceAll fused into the scan (generic scans, replacement not longer than the shortest match: the output is never
+  // longer than the text): instead of the match pairs the kernel writes the rebuilt text — every tile copies the bytes
+  // between its matches and the replacement strings to their final place (the look-back also carries the bytes removed
+  // so far) — and the lengths pass, the prefix sum, the index and the staged rebuild of the separate path are not run.
+  uint8_t* rep_out;                 // the rebuilt text (NULL: the usual MatchAll)
+  const uint8_t* rep_with;          // the replacement string, device memory
+  uint32_t rep_w;                   // its length
   uint32_t static_stride;           // warps of the grid when the tiles are dealt round robin, 0: ticket counter
   uint32_t rows;                    // rows of 512 bytes per tile (<= kEmRows; the host picks: dense candidates want smaller tiles)
   uint64_t* out_pairs;
@@ -389,9 +396,10 @@ __device__ __forceinline__ uint4 EmLoad16(const uint4* p) {
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void EmPublish(uint4* rec, uint32_t tag, uint64_t count, bool has, const EmState& st) {
-  EmStore16(rec, (uint32_t)count, (uint32_t)(count >> 32), tag, 0u);
-  EmStore16(rec + 1, (uint32_t)st.cur, (uint32_t)(st.cur >> 32) | (st.ne << 31) | (has ? 1u << 30 : 0u), tag, 0u);
+// (`removed`: bytes inside the counted matches — only the fused ReplaceAll uses it; low word in half 0, high word in half 1)
+__device__ __forceinline__ void EmPublish(uint4* rec, uint32_t tag, uint64_t count, bool has, const EmState& st, uint64_t removed = 0) {
+  EmStore16(rec, (uint32_t)count, (uint32_t)(count >> 32), tag, (uint32_t)removed);
+  EmStore16(rec + 1, (uint32_t)st.cur, (uint32_t)(st.cur >> 32) | (st.ne << 31) | (has ? 1u << 30 : 0u), tag, (uint32_t)(removed >> 32));
 }
 
 // Called by a whole warp.  Returns (in every lane) the number of matches in the tiles before `t` and the chain
@@ -406,16 +414,17 @@ __device__ __forceinline__ void EmPublish(uint4* rec, uint32_t tag, uint64_t cou
 // tile itself found; the LAST tile of every group of 32 adds its group's records up and publishes a GROUP record
 // (own numbers first, then — after a look-back over the group records before it, 32 groups = 1024 tiles per step —
 // everything up to and including the group).  A tile's prefix = the tiles before it in its group + the groups before.
+template <bool kRebuild>
 __device__ __forceinline__ void EmLookBack(const EmitArgs& em, const uint4* records, uint64_t t, uint64_t* before, EmState* arriving,
-                                           bool* found) {
+                                           bool* found, uint64_t* removed_before) {
   const int lane = threadIdx.x & 31;
-  uint64_t excl = 0;
+  uint64_t excl = 0, excl_rem = 0;
   EmState st;
   st.cur = 0; st.ne = 0;
   bool have = false;
   for (int64_t base = (int64_t)t;; base -= 32) {
     const int64_t idx = base - 1 - lane;
-    uint64_t cnt = 0, cur = 0;
+    uint64_t cnt = 0, cur = 0, rem = 0;
     uint32_t state = 0, ne = 0, has = 0;
     if (idx >= 0) {
       const uint4* rec = records + 2 * (uint64_t)idx;
@@ -432,6 +441,7 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, const uint4* reco
           cur = (uint64_t)(b.y & 0x3FFFFFFFu) << 32 | b.x;
           ne = b.y >> 31;
           has = (b.y >> 30) & 1u;
+          if (kRebuild) rem = (uint64_t)b.w << 32 | a.w;
           break;
         }
         // (a short clock-counting spin: __nanosleep(64) here made the chain of look-backs 20-60 % slower on texts
@@ -454,6 +464,12 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, const uint4* reco
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
     excl += sum;
+    if (kRebuild) {
+      uint64_t sr = use ? rem : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) sr += __shfl_xor_sync(kFullMask, sr, d);
+      excl_rem += sr;
+    }
     const uint32_t st_mask = __ballot_sync(kFullMask, use && has);
     if (!have && st_mask) {
       const int src = __ffs(st_mask) - 1;
@@ -466,15 +482,18 @@ __device__ __forceinline__ void EmLookBack(const EmitArgs& em, const uint4* reco
   *before = excl;
   *arriving = st;
   *found = have;
+  *removed_before = excl_rem;
 }
 
 // The tiles of tile t's group that come before it (t & 31 of them, one per lane): their matches, and the chain state
 // after the last match among them (*found: there is one).
-__device__ __forceinline__ void EmGroupBefore(const EmitArgs& em, uint64_t t, uint32_t* before, EmState* after, bool* found) {
+template <bool kRebuild>
+__device__ __forceinline__ void EmGroupBefore(const EmitArgs& em, uint64_t t, uint32_t* before, EmState* after, bool* found,
+                                              uint64_t* removed) {
   const int lane = threadIdx.x & 31;
   const uint32_t j = (uint32_t)t & 31u;
   uint32_t cnt = 0, ne = 0, has = 0;
-  uint64_t cur = 0;
+  uint64_t cur = 0, rem = 0;
   if ((uint32_t)lane < j) {
     const uint4* rec = em.records + 2 * (t - j + lane);
     for (uint32_t polls = 0;; ++polls) {
@@ -485,6 +504,7 @@ __device__ __forceinline__ void EmGroupBefore(const EmitArgs& em, uint64_t t, ui
         cur = (uint64_t)(b.y & 0x3FFFFFFFu) << 32 | b.x;
         ne = b.y >> 31;
         has = (b.y >> 30) & 1u;
+        if (kRebuild) rem = (uint64_t)b.w << 32 | a.w;
         break;
       }
       const long long t0 = clock64();
@@ -492,6 +512,12 @@ __device__ __forceinline__ void EmGroupBefore(const EmitArgs& em, uint64_t t, ui
     }
   }
   *before = __reduce_add_sync(kFullMask, cnt);
+  *removed = 0;
+  if (kRebuild) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) rem += __shfl_xor_sync(kFullMask, rem, d);
+    *removed = rem;
+  }
   const uint32_t st_mask = __ballot_sync(kFullMask, has != 0);
   const int src = st_mask ? 31 - __clz(st_mask) : 0;        // the nearest tile before me with a match
   after->cur = __shfl_sync(kFullMask, cur, src);
@@ -506,7 +532,7 @@ __device__ __forceinline__ void EmGroupBefore(const EmitArgs& em, uint64_t t, ui
 // the memory latency / kDepth PLUS its own instructions: with four rows the literal kernels ran at 4.0 TB/s where the
 // same tiling with an empty loop body reads 6.9 TB/s (scripts/probe/read_bw.cu); eight rows cost sixteen registers
 // (three CTAs per SM instead of four).  The window / generic kernels are at their register limit with four.
-template <int kMode, bool kFull4, int kDepth>
+template <int kMode, bool kFull4, int kDepth, bool kRebuild = false>
 __global__ void __launch_bounds__(kEmThreads, kDepth > 4 ? 3 : 4)
 k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables nfa, EmFilter flt, ScanRange range,
             EmitArgs em) {
@@ -701,31 +727,54 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
     const EmState mine_out = EmAfter(tile_base + EmRel(last), EmLen(last));
     uint4* rec = em.records + 2 * t;
     const uint32_t tag = (em.seq & 0x3FFFFFFFu) << 2;
-    if (lane == 0) EmPublish(rec, tag | 1u, cnt, cnt != 0, mine_out);
+    // (fused ReplaceAll: the bytes inside this tile's matches)
+    uint64_t tile_removed = 0;
+    if (kRebuild) {
+      uint32_t part = 0;
+      for (uint32_t i = lane; i < cnt; i += 32) part += EmLen(my_cand[i]);
+      tile_removed = __reduce_add_sync(kFullMask, part);
+    }
+    if (lane == 0) EmPublish(rec, tag | 1u, cnt, cnt != 0, mine_out, tile_removed);
     // A tile without matches needs nothing from its predecessors — no place for matches, no seam — and its own record
     // already says all there is to say about it: it does not look back at all, unless it closes its group (a look-back
     // blocks the warp with no loads in flight: on a text without hits it was a quarter of the kernel's time).
-    uint64_t before = 0;
+    uint64_t before = 0, removed_before = 0;
     EmState arriving;
     arriving.cur = 0; arriving.ne = 0;
     const bool closes_group = (t & 31u) == 31u || t + 1 == em.ntiles;        // the last tile of its group
-    const bool look = cnt != 0 || closes_group;
+    const bool look = cnt != 0 || closes_group || kRebuild;     // (every tile of a rebuild has bytes to place)
     if (look) {
       uint32_t in_group;
       EmState st_group, st_before;
       bool have_group, have_before;
-      uint64_t groups_before;
-      EmGroupBefore(em, t, &in_group, &st_group, &have_group);
+      uint64_t groups_before, rem_group, rem_groups_before;
+      EmGroupBefore<kRebuild>(em, t, &in_group, &st_group, &have_group, &rem_group);
       uint4* grec = em.group_records + 2 * (t >> 5);
       const uint64_t group_count = (uint64_t)in_group + cnt;
       const bool group_has = cnt != 0 || have_group;
       const EmState group_out = cnt ? mine_out : st_group;
-      if (closes_group && lane == 0) EmPublish(grec, tag | 1u, group_count, group_has, group_out);
-      EmLookBack(em, em.group_records, t >> 5, &groups_before, &st_before, &have_before);
+      if (closes_group && lane == 0) EmPublish(grec, tag | 1u, group_count, group_has, group_out, rem_group + tile_removed);
+      EmLookBack<kRebuild>(em, em.group_records, t >> 5, &groups_before, &st_before, &have_before, &rem_groups_before);
       before = groups_before + in_group;
+      removed_before = rem_groups_before + rem_group;
       arriving = have_group ? st_group : st_before;
-      if (closes_group && lane == 0) EmPublish(grec, tag | 2u, groups_before + group_count, true, group_has ? group_out : st_before);
+      if (closes_group && lane == 0)
+        EmPublish(grec, tag | 2u, groups_before + group_count, true, group_has ? group_out : st_before,
+                  rem_groups_before + rem_group + tile_removed);
       if (cnt && !EmTakes(arriving, tile_base + EmRel(first), EmLen(first))) flags |= kFinOverlap;   // the chain from the left reaches in
+    }
+    // (fused ReplaceAll) the first text byte that is mine to copy, and its place in the rebuilt text: an output byte
+    // sits at (its text offset) - (bytes removed before it) + rep_w x (matches before it).  Every match counted by the
+    // look-back ends at or before rb_in, so the sums must fit under it; numbers that do not (a tile before me has
+    // raised a flag and published nothing, or its last match runs into my first) write nothing and send the call to
+    // the separate rebuild.
+    uint64_t rb_in = 0, rb_out = 0;
+    if (kRebuild) {
+      rb_in = tile_lo;
+      if (arriving.ne && arriving.cur > rb_in) rb_in = arriving.cur;           // a match from the left ends here
+      const uint64_t added = (uint64_t)em.rep_w * before;
+      if (removed_before > rb_in || added > removed_before) flags |= kFinOverlap;
+      rb_out = rb_in - removed_before + added;
     }
     if (lane == 0) {
       if (flags) atomicOr(&em.sync[2], flags);
@@ -734,10 +783,69 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
         atomicExch(&em.final_state[0], before + cnt);
         atomicExch(&em.final_state[1], fin.cur);
         atomicExch(&em.final_state[2], (unsigned long long)fin.ne);
+        if (kRebuild) atomicExch(&em.final_state[3], removed_before + tile_removed);
       }
     }
-    // ---- my matches, at their final place ------------------------------------------------------------------------
-    {
+    if (kRebuild) {
+      // ---- fused ReplaceAll: my part of the rebuilt text.  The bytes between my matches are copied (lanes take
+      // consecutive bytes: a gap is a few coalesced sectors), each match leaves the replacement string.  Four gaps per
+      // step, their loads issued together: one gap per step was one load latency per match (a FASTA tile has 400).
+      if (!flags) {
+        const uint64_t tile_hi = tile_lo + tile_bytes < n ? tile_lo + tile_bytes : n;
+        uint8_t* __restrict__ outb = em.rep_out;
+        uint64_t in_pos = rb_in, o = rb_out;
+        const uint32_t w = em.rep_w;
+        const uint8_t wb = (uint32_t)lane < w ? __ldg(em.rep_with + lane) : (uint8_t)0;
+#pragma unroll 1
+        for (uint32_t i = 0; i <= cnt; i += 4) {
+          uint64_t src[4], dst[4];
+          uint32_t gap[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t k = i + u;
+            uint64_t b = in_pos, e = in_pos;                  // (entries past the end: nothing)
+            if (k < cnt) { const uint32_t c = my_cand[k]; b = tile_base + EmRel(c); e = b + EmLen(c); }
+            else if (k == cnt) { b = tile_hi; e = tile_hi; }  // the bytes after my last match
+            src[u] = in_pos;
+            gap[u] = b > in_pos ? (uint32_t)(b - in_pos) : 0u;
+            dst[u] = o;
+            o += gap[u] + (k < cnt ? w : 0u);
+            if (e > in_pos) in_pos = e;
+          }
+          uint8_t x[4], y[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            x[u] = 0; y[u] = 0;
+            if ((uint32_t)lane < gap[u]) x[u] = text[src[u] + lane];
+            if ((uint32_t)lane + 32u < gap[u]) y[u] = text[src[u] + 32 + lane];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if ((uint32_t)lane < gap[u]) outb[dst[u] + lane] = x[u];
+            if ((uint32_t)lane + 32u < gap[u]) outb[dst[u] + 32 + lane] = y[u];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            // a long gap: eight bytes per lane in flight
+            uint32_t k = 64u + lane;
+            for (; k + 224u < gap[u]; k += 256u) {
+              uint8_t z[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) z[q] = text[src[u] + k + 32 * q];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) outb[dst[u] + k + 32 * q] = z[q];
+            }
+            for (; k < gap[u]; k += 32u) outb[dst[u] + k] = text[src[u] + k];
+            if (i + u < cnt && w) {
+              const uint64_t at = dst[u] + gap[u];
+              if ((uint32_t)lane < w) outb[at + lane] = wb;
+              for (uint32_t q = 32u + lane; q < w; q += 32u) outb[at + q] = __ldg(em.rep_with + q);
+            }
+          }
+        }
+      }
+    } else {
+      // ---- my matches, at their final place ----------------------------------------------------------------------
       ulonglong2* outp = reinterpret_cast<ulonglong2*>(em.out_pairs);
       for (uint32_t i = lane; i < cnt; i += 32) {
         const uint32_t c = my_cand[i];
@@ -780,6 +888,14 @@ k_scan_emit(const uint8_t* __restrict__ text, uint64_t n, EmLit lit, NfaTables n
                      "r"((unsigned int)(last_end >> 32)), "r"(0u), "r"(em.seq) : "memory");
         asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 2), "r"((unsigned int)last_ne),
                      "r"((unsigned int)(last_ne >> 32)), "r"(0u), "r"(em.seq) : "memory");
+        if (kRebuild) {
+          // a second FinRecord: n_matches = bytes removed (the host computes the length of the rebuilt text from it)
+          const unsigned long long removed = __ldcg(&em.final_state[3]);
+          asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 3), "r"((unsigned int)removed),
+                       "r"((unsigned int)(removed >> 32)), "r"(0u), "r"(em.seq) : "memory");
+          asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 4), "r"(0u), "r"(0u), "r"(0u), "r"(em.seq) : "memory");
+          asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst + 5), "r"(0u), "r"(0u), "r"(0u), "r"(em.seq) : "memory");
+        }
       }
     }
   }

@@ -722,6 +722,75 @@ def test_replace_all_set_one_pass(rj):
         src.free()
 
 
+def test_replace_all_fused_into_the_scan(rj):
+    """Round 2: generic scans whose replacement is not longer than their shortest match write the rebuilt text from
+    `k_scan_emit` itself (scan_emit.cuh, kRebuild; engine.cu ReplaceAllDevice) — one launch instead of scan + lengths +
+    prefix sum + index + staging.  Same contract as `Regej::ReplaceAll` (src/rejit.cc:97-112, 221-226): the oracle's
+    matches applied in Python, byte for byte.  Sizes sit on tile edges (24 KB tiles), cross the groups of 32 tiles and
+    the look-back step of 32 groups; gaps of 0 bytes, of a few bytes, of whole tiles; matches that end in the next
+    tile; replacements of 0, 1, 3 and more than 32 bytes; cases the single pass must hand back (matches longer than a
+    tile, replacement longer than the shortest match) still come out right."""
+    rng = np.random.default_rng(77)
+
+    def text(alpha, n, p=None):
+        return np.frombuffer(alpha, dtype=np.uint8)[rng.choice(len(alpha), size=n, p=p)].tobytes()
+
+    tile = 24576
+    cases = []
+    for n in (1, 63, tile - 1, tile, tile + 1, 2 * tile, 3 * tile + 5, 33 * tile + 11):
+        dense = text(b"abx\n", n)
+        sparse = text(b"abx\n", n, p=[0.4995, 0.4995, 0.0005, 0.0005])
+        for t in (dense, sparse):
+            cases += [("x+", t, b""), ("x+", t, b"Q"), ("ab|ba", t, b"Z"), ("ab|ba", t, b"YZ"), ("x*", t, b""),
+                      ("(^|$|[x])", t, b""), ("[ab]{3,}", t, b"QQQ"), ("a.*", t, b"L"), (">.*\n|\n", t, b"")]
+    # lines longer than a tile (every `a` is a start and each start runs to the end of its line: kept short, the
+    # speculative evaluation is quadratic in the line length), and ONE match that covers a whole tile and more
+    lines = text(b"ab", 40 * tile)
+    cases += [("a.*", lines[:2 * tile + 100], b""), ("a.*", lines[:tile + 100] + b"\n" + lines[:tile + 50], b"-")]
+    header = b"ab\n>" + lines[:2 * tile + 300] + b"\nab\nba\n"
+    cases += [(">.*\n|\n", header, b""), (">.*\n|\n", lines[:tile - 2] + header, b"")]
+    runs = bytearray(text(b"ab", 6 * tile))
+    for at in (100, tile - 20, 3 * tile - 45, 5 * tile):        # runs of x across tile edges, 90 bytes each
+        runs[at:at + 90] = b"x" * 90
+    w35 = bytes(range(65, 100))
+    cases += [("x{40,}", bytes(runs), w35), ("x{40,}", bytes(runs), b""), ("x{40,}", bytes(runs), b"x" * 40)]
+    cases += [("x+", text(b"abx", 2 * tile), b"QQ"), (".*", b"x" * 9000, b"y")]      # not fused: replacement too long
+    for pat, t, w in cases:
+        got = rj.Regej(pat).replace_all(t, w)
+        assert got == _replace_expected(pat, t, w), (pat, len(t), w)
+    # one launch where the fusion applies (the strip of a FASTA file: SURVEY section 8f, sample/regexdna.cc:49)
+    from rejit_b200 import workloads as W
+    fa = W.fasta_file(100_000)                                  # ~1 MB, 60-column lines
+    exp, n_strip = _replace_expected(W.STRIP_PATTERN, fa, b"")
+    raw = rj.Text(fa)
+    strip = rj.Regej(W.STRIP_PATTERN)
+    for _ in range(2):
+        st = rj.Stats()
+        out, k = strip.replace_all_text(raw, b"", stats=st)
+        assert k == n_strip and out.download() == exp
+        import os
+        if not os.environ.get("RJ_NO_FUSED_REBUILD") and not os.environ.get("RJ_NO_EMIT"):
+            assert st.launches == 1, st.launches
+        out.free()
+    raw.free()
+    # 60 MB = 2500 tiles = 79 groups: three look-back steps carry the removed bytes.  Expected with numpy: runs of x
+    big = np.frombuffer(b"abx\n", dtype=np.uint8)[rng.choice(4, size=60_000_000, p=[0.45, 0.45, 0.09, 0.01])]
+    is_x = big == ord("x")
+    starts = is_x.copy()
+    starts[1:] &= ~is_x[:-1]
+    src = rj.Text(big)
+    r = rj.Regej("x+")
+    out, k = r.replace_all_text(src, b"")
+    assert k == int(starts.sum()) and (_np_text(out.download()) == big[~is_x]).all()
+    out.free()
+    out, k = r.replace_all_text(src, b"Q")
+    exp = big.copy()
+    exp[starts] = ord("Q")
+    assert k == int(starts.sum()) and (_np_text(out.download()) == exp[~is_x | starts]).all()
+    out.free()
+    src.free()
+
+
 def test_regexdna_chain_at_size(rj):
     """BASELINE configs[4] on one GPU's share: strip, nine counts, eleven substitutions over a 510 MB FASTA file on
     device-resident texts.  Size-independent checks: the stripped text IS the sequence the file was made from, the
