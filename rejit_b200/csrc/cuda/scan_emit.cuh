@@ -95,11 +95,12 @@ struct EmitArgs {
   unsigned int* sync;               // [0..1] ticket (64 bit), [2] flags, [3] tiles done; zeroed by the host before the launch
   unsigned long long* final_state;  // [3]: total matches, chain state (cur, non-empty); written by the last tile
   uint64_t tile0, ntiles;           // tiles [tile0, tile0 + ntiles) hold every owned start (and needle hit)
-  // ReplaceAll fused into the scan (generic scans, replacement not longer than the shortest match: the output is never
-  // longer than the text): instead of the match pairs the kernel writes the rebuilt text — every tile copies the bytes
-  // between its matches and the replacement strings to their final place (the look-back also carries the bytes removed
-  // so far) — and the lengths pass, the prefix sum, the index and the staged rebuild of the separate path are not run.
-  uint8_t* rep_out;                 // the rebuilt text (NULL: the usual MatchAll)
+  // ReplaceAll fused into the scan (the kRebuild instantiation; generic scans, replacement not longer than the
+  // shortest match, so the output is never longer than the text): instead of the match pairs the kernel writes the
+  // rebuilt text — every tile copies the bytes between its matches and the replacement strings to their final place
+  // (tile and group records also carry the bytes inside their matches, summed by the same look-back) — and the
+  // lengths pass, the prefix sum, the index and the staged rebuild of the separate path (replace.cuh) are not run.
+  uint8_t* rep_out;                 // the rebuilt text, >= n + 64 bytes (only read by the kRebuild kernel)
   const uint8_t* rep_with;          // the replacement string, device memory
   uint32_t rep_w;                   // its length
   uint32_t static_stride;           // warps of the grid when the tiles are dealt round robin, 0: ticket counter
