@@ -546,7 +546,7 @@ def config_rows(rj, W, torch, peak, device, rank, world, dist, tdev, reps):
                           "histogram -> substitution counts and final length, shifted compares -> the first variant's count",
                 "stitch": "slabs are cut at line ends; the nine counts use a 16-byte halo exchanged by ONE NCCL all-gather per step"
                           if world > 1 else "one slab",
-                "launches": "strip 1 scan + 3 rebuild, counts 1, substitutions 5"}
+                "launches": "strip 1 (the scan writes the stripped text itself; RJ_NO_FUSED_REBUILD=1: 1 scan + 5 rebuild), counts 1, substitutions 5"}
     guarded("C5", c5)
     return rows
 
