@@ -6,6 +6,7 @@
 #include <cstring>
 #include <exception>
 #include <mutex>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,17 @@ void SetErr(char* err, size_t len, const std::string& msg) {
   memcpy(err, msg.data(), k);
   err[k] = 0;
 }
+
+// Nothing may leave an extern "C" function by exception (std::terminate in a C, cgo or ctypes caller): every entry
+// point that can allocate is a function-try-block closed by this handler.  (The message is built without allocating
+// when memory is what ran out.)
+void SetErrNoAlloc(char* err, size_t len, const char* where, const char* what) {
+  if (!err || !len) return;
+  snprintf(err, len, "%s: %s", where, what ? what : "exception");
+}
+#define RJ_CATCH(where, fail)                                                                 \
+  catch (const std::exception& e) { SetErrNoAlloc(err, err_length, where, e.what()); return fail; } \
+  catch (...) { SetErrNoAlloc(err, err_length, where, nullptr); return fail; }
 
 void PutU16(std::vector<uint8_t>* v, size_t x) {
   v->push_back(static_cast<uint8_t>(x & 0xFF));
@@ -261,7 +273,8 @@ static void FillStats(const RunStats& s, rejit_b200_stats* out) {
 }
 
 int64_t rejit_b200_match_all_alloc(rejit_b200_program* program, const char* text, size_t text_length,
-                                   uint64_t** out_pairs, rejit_b200_stats* stats, char* err, size_t err_length) {
+                                   uint64_t** out_pairs, rejit_b200_stats* stats, char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_all_alloc: null program"); return -1; }
   std::string error;
   RunStats rs;
   uint64_t* pairs = nullptr;
@@ -271,10 +284,11 @@ int64_t rejit_b200_match_all_alloc(rejit_b200_program* program, const char* text
   FillStats(rs, stats);
   if (out_pairs) *out_pairs = pairs; else free(pairs);
   return r;
-}
+} RJ_CATCH("rejit_b200_match_all_alloc", -1)
 
 int64_t rejit_b200_match_all(rejit_b200_program* program, const char* text, size_t text_length,
-                             uint64_t* out_pairs, size_t capacity, char* err, size_t err_length) {
+                             uint64_t* out_pairs, size_t capacity, char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_all: null program"); return -1; }
   uint64_t* pairs = nullptr;
   int64_t r = rejit_b200_match_all_alloc(program, text, text_length, &pairs, nullptr, err, err_length);
   if (r < 0) return r;
@@ -282,10 +296,11 @@ int64_t rejit_b200_match_all(rejit_b200_program* program, const char* text, size
   if (k && out_pairs) memcpy(out_pairs, pairs, k * 16);
   free(pairs);
   return r;
-}
+} RJ_CATCH("rejit_b200_match_all", -1)
 
 int rejit_b200_match_first(rejit_b200_program* program, const char* text, size_t text_length,
-                           uint64_t out_pair[2], char* err, size_t err_length) {
+                           uint64_t out_pair[2], char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_first: null program"); return -1; }
   // MatchFirst := first element of MatchAll, found slab by slab with early exit
   std::string error;
   if (!CudaOk(&error)) { SetErr(err, err_length, error); return -1; }
@@ -294,28 +309,31 @@ int rejit_b200_match_first(rejit_b200_program* program, const char* text, size_t
   if (r < 0) { SetErr(err, err_length, error); return -1; }
   if (r > 0 && out_pair) { out_pair[0] = pair[0]; out_pair[1] = pair[1]; }
   return r;
-}
+} RJ_CATCH("rejit_b200_match_first", -1)
 
 int rejit_b200_match_full(rejit_b200_program* program, const char* text, size_t text_length,
-                          char* err, size_t err_length) {
+                          char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_full: null program"); return -1; }
   std::string error;
   int r = MatchFullHost(0, program->prog, reinterpret_cast<const uint8_t*>(text), text_length, &error);
   if (r < 0) SetErr(err, err_length, error);
   return r;
-}
+} RJ_CATCH("rejit_b200_match_full", -1)
 
 int rejit_b200_match_anywhere(rejit_b200_program* program, const char* text, size_t text_length,
-                              char* err, size_t err_length) {
+                              char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_anywhere: null program"); return -1; }
   std::string error;
   if (!CudaOk(&error)) { SetErr(err, err_length, error); return -1; }
   int r = MatchFirstHost(0, program->prog, reinterpret_cast<const uint8_t*>(text), text_length, nullptr, &error);
   if (r < 0) SetErr(err, err_length, error);
   return r;
-}
+} RJ_CATCH("rejit_b200_match_anywhere", -1)
 
 int64_t rejit_b200_match_all_multi_gpu(rejit_b200_program* program, const char* text, size_t text_length,
                                        int n_gpus, uint64_t** out_pairs, rejit_b200_stats* stats,
-                                       char* err, size_t err_length) {
+                                       char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_all_multi_gpu: null program"); return -1; }
   std::string error;
   RunStats rs;
   uint64_t* pairs = nullptr;
@@ -325,7 +343,7 @@ int64_t rejit_b200_match_all_multi_gpu(rejit_b200_program* program, const char* 
   FillStats(rs, stats);
   if (out_pairs) *out_pairs = pairs; else free(pairs);
   return r;
-}
+} RJ_CATCH("rejit_b200_match_all_multi_gpu", -1)
 
 int rejit_b200_device_count(void) { return DeviceCount(); }
 
@@ -356,7 +374,8 @@ void rejit_b200_flush_l2(int device) { FlushL2(device); }
 int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, const void* d_text,
                                     size_t text_length, uint64_t* d_out_pairs, size_t capacity,
                                     const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
-                                    rejit_b200_stats* stats, char* err, size_t err_length) {
+                                    rejit_b200_stats* stats, char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_all_device: null program"); return -1; }
   std::string error;
   Carry in, out;
   if (carry_in) { in.cur = carry_in->cur; in.tail = carry_in->tail; }
@@ -368,10 +387,10 @@ int64_t rejit_b200_match_all_device(rejit_b200_program* program, int device, con
   if (carry_out) { carry_out->cur = out.cur; carry_out->tail = out.tail; }
   FillStats(rs, stats);
   return r;
-}
+} RJ_CATCH("rejit_b200_match_all_device", -1)
 
 rejit_b200_text* rejit_b200_text_upload(int device, const char* text, size_t text_length, char* err,
-                                        size_t err_length) {
+                                        size_t err_length) try {
   std::string error;
   void* d = nullptr;
   size_t capacity = 0;
@@ -401,10 +420,10 @@ rejit_b200_text* rejit_b200_text_upload(int device, const char* text, size_t tex
   t->length = text_length;
   t->capacity = capacity;
   return t;
-}
+} RJ_CATCH("rejit_b200_text_upload", nullptr)
 
 rejit_b200_text* rejit_b200_text_from_device(int device, const void* d_text, size_t text_length, char* err,
-                                             size_t err_length) {
+                                             size_t err_length) try {
   std::string error;
   void* d = DeviceAlloc(device, text_length ? text_length : 1, &error);
   if (!d) { SetErr(err, err_length, error); return nullptr; }
@@ -419,7 +438,7 @@ rejit_b200_text* rejit_b200_text_from_device(int device, const void* d_text, siz
   t->length = text_length;
   t->capacity = text_length ? text_length : 1;
   return t;
-}
+} RJ_CATCH("rejit_b200_text_from_device", nullptr)
 
 void rejit_b200_text_free(rejit_b200_text* text) {
   if (!text) return;
@@ -435,7 +454,9 @@ void rejit_b200_text_free(rejit_b200_text* text) {
 }
 
 int64_t rejit_b200_match_all_text(rejit_b200_program* program, const rejit_b200_text* text, uint64_t** out_pairs,
-                                  rejit_b200_stats* stats, char* err, size_t err_length) {
+                                  rejit_b200_stats* stats, char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_all_text: null program"); return -1; }
+  if (!text) { SetErr(err, err_length, "rejit_b200_match_all_text: null text"); return -1; }
   std::string error;
   RunStats rs;
   uint64_t* pairs = nullptr;
@@ -445,15 +466,22 @@ int64_t rejit_b200_match_all_text(rejit_b200_program* program, const rejit_b200_
   FillStats(rs, stats);
   if (out_pairs) *out_pairs = pairs; else free(pairs);
   return r;
-}
+} RJ_CATCH("rejit_b200_match_all_text", -1)
 
 rejit_b200_set* rejit_b200_set_create(rejit_b200_program* const* programs, int count) {
   if (!programs || count < 1) return nullptr;
-  std::vector<Program*> members;
-  for (int i = 0; i < count; ++i) members.push_back(programs[i]->prog);
-  rejit_b200_set* s = new rejit_b200_set;
-  s->set = SetProgram::Create(members);
-  return s;
+  try {
+    std::vector<Program*> members;
+    for (int i = 0; i < count; ++i) {
+      if (!programs[i]) return nullptr;
+      members.push_back(programs[i]->prog);
+    }
+    std::unique_ptr<rejit_b200_set> s(new rejit_b200_set);
+    s->set = SetProgram::Create(members);
+    return s->set ? s.release() : nullptr;
+  } catch (...) {
+    return nullptr;
+  }
 }
 
 void rejit_b200_set_free(rejit_b200_set* set) {
@@ -478,7 +506,8 @@ int rejit_b200_set_kmer_tables(const rejit_b200_set* set, uint32_t* info, uint32
 }
 
 int rejit_b200_match_all_set_device(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
-                                    int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) {
+                                    int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) try {
+  if (!set) { SetErr(err, err_length, "rejit_b200_match_all_set_device: null set"); return -1; }
   std::string error;
   RunStats rs;
   int r = MatchAllSetResident(device, set->set, static_cast<const uint8_t*>(d_text), text_length, out_counts, nullptr,
@@ -486,12 +515,13 @@ int rejit_b200_match_all_set_device(rejit_b200_set* set, int device, const void*
   if (r < 0) { SetErr(err, err_length, error); return -1; }
   FillStats(rs, stats);
   return 0;
-}
+} RJ_CATCH("rejit_b200_match_all_set_device", -1)
 
 int rejit_b200_match_all_set_device_slab(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
                                          uint64_t own_begin, uint64_t own_end, uint64_t base_offset,
                                          const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
-                                         int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) {
+                                         int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) try {
+  if (!set) { SetErr(err, err_length, "rejit_b200_match_all_set_device_slab: null set"); return -1; }
   std::string error;
   RunStats rs;
   const int k = set->set->size();
@@ -509,10 +539,12 @@ int rejit_b200_match_all_set_device_slab(rejit_b200_set* set, int device, const 
   if (carry_out) for (int j = 0; j < k; ++j) { carry_out[j].cur = out[j].cur; carry_out[j].tail = out[j].tail; }
   FillStats(rs, stats);
   return 0;
-}
+} RJ_CATCH("rejit_b200_match_all_set_device_slab", -1)
 
 int rejit_b200_match_all_set_text(rejit_b200_set* set, const rejit_b200_text* text, int64_t* out_counts,
-                                  uint64_t** out_pairs, rejit_b200_stats* stats, char* err, size_t err_length) {
+                                  uint64_t** out_pairs, rejit_b200_stats* stats, char* err, size_t err_length) try {
+  if (!text) { SetErr(err, err_length, "rejit_b200_match_all_set_text: null text"); return -1; }
+  if (!set) { SetErr(err, err_length, "rejit_b200_match_all_set_text: null set"); return -1; }
   std::string error;
   RunStats rs;
   int r = MatchAllSetResident(text->device, set->set, static_cast<const uint8_t*>(text->d_ptr), text->length,
@@ -520,13 +552,14 @@ int rejit_b200_match_all_set_text(rejit_b200_set* set, const rejit_b200_text* te
   if (r < 0) { SetErr(err, err_length, error); return -1; }
   FillStats(rs, stats);
   return 0;
-}
+} RJ_CATCH("rejit_b200_match_all_set_text", -1)
 
 int64_t rejit_b200_match_all_device_slab(rejit_b200_program* program, int device, const void* d_text,
                                          size_t text_length, uint64_t own_begin, uint64_t own_end,
                                          uint64_t base_offset, uint64_t* d_out_pairs, size_t capacity,
                                          const rejit_b200_carry* carry_in, rejit_b200_carry* carry_out,
-                                         rejit_b200_stats* stats, char* err, size_t err_length) {
+                                         rejit_b200_stats* stats, char* err, size_t err_length) try {
+  if (!program) { SetErr(err, err_length, "rejit_b200_match_all_device_slab: null program"); return -1; }
   std::string error;
   Carry in, out;
   if (carry_in) { in.cur = carry_in->cur; in.tail = carry_in->tail; }
@@ -542,11 +575,11 @@ int64_t rejit_b200_match_all_device_slab(rejit_b200_program* program, int device
   if (carry_out) { carry_out->cur = out.cur; carry_out->tail = out.tail; }
   FillStats(rs, stats);
   return r;
-}
+} RJ_CATCH("rejit_b200_match_all_device_slab", -1)
 
 int64_t rejit_b200_replace_all(rejit_b200_program* program, const char* text, size_t text_length, const char* with,
                                size_t with_length, char** out, size_t* out_length, rejit_b200_stats* stats,
-                               char* err, size_t err_length) {
+                               char* err, size_t err_length) try {
   std::string error;
   if (!program || !out || !out_length) { SetErr(err, err_length, "rejit_b200: null argument"); return -1; }
   if (!CudaOk(&error)) { SetErr(err, err_length, error); return -1; }
@@ -561,11 +594,11 @@ int64_t rejit_b200_replace_all(rejit_b200_program* program, const char* text, si
   *out = reinterpret_cast<char*>(rebuilt);
   *out_length = len;
   return r;
-}
+} RJ_CATCH("rejit_b200_replace_all", -1)
 
 rejit_b200_text* rejit_b200_replace_all_text(rejit_b200_program* program, const rejit_b200_text* text, const char* with,
                                              size_t with_length, int64_t* n_matches, rejit_b200_stats* stats,
-                                             char* err, size_t err_length) {
+                                             char* err, size_t err_length) try {
   std::string error;
   if (!program || !text) { SetErr(err, err_length, "rejit_b200: null argument"); return nullptr; }
   RunStats rs;
@@ -583,11 +616,11 @@ rejit_b200_text* rejit_b200_replace_all_text(rejit_b200_program* program, const 
   t->length = len;
   t->capacity = cap;
   return t;
-}
+} RJ_CATCH("rejit_b200_replace_all_text", nullptr)
 
 rejit_b200_text* rejit_b200_replace_all_set_text(rejit_b200_program* const* programs, int count, const rejit_b200_text* text,
                                                  const char* const* withs, const size_t* with_lengths, int64_t* n_matches,
-                                                 rejit_b200_stats* stats, char* err, size_t err_length) {
+                                                 rejit_b200_stats* stats, char* err, size_t err_length) try {
   std::string error;
   if (!programs || count < 1 || !text || !withs || !with_lengths) { SetErr(err, err_length, "rejit_b200: null argument"); return nullptr; }
   std::vector<Program*> progs;
@@ -630,12 +663,12 @@ rejit_b200_text* rejit_b200_replace_all_set_text(rejit_b200_program* const* prog
   }
   if (stats) { *stats = acc; stats->strategy = -1; }
   return owned;
-}
+} RJ_CATCH("rejit_b200_replace_all_set_text", nullptr)
 
 size_t rejit_b200_text_length(const rejit_b200_text* text) { return text ? text->length : 0; }
 const void* rejit_b200_text_device_ptr(const rejit_b200_text* text) { return text ? text->d_ptr : nullptr; }
 
-int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capacity, char* err, size_t err_length) {
+int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capacity, char* err, size_t err_length) try {
   std::string error;
   if (!text || (!dst && text->length)) { SetErr(err, err_length, "rejit_b200: null argument"); return -1; }
   if (capacity < text->length) { SetErr(err, err_length, "rejit_b200: destination too small"); return -1; }
@@ -644,25 +677,25 @@ int rejit_b200_text_download(const rejit_b200_text* text, char* dst, size_t capa
     return -1;
   }
   return 0;
-}
+} RJ_CATCH("rejit_b200_text_download", -1)
 
-int rejit_b200_stitch_open(int device, int rank, int world, void* handle_out, char* err, size_t err_length) {
+int rejit_b200_stitch_open(int device, int rank, int world, void* handle_out, char* err, size_t err_length) try {
   std::string error;
   if (!handle_out) { SetErr(err, err_length, "rejit_b200: null argument"); return -1; }
   if (!StitchOpen(device, rank, world, handle_out, &error)) { SetErr(err, err_length, error); return -1; }
   return 0;
-}
+} RJ_CATCH("rejit_b200_stitch_open", -1)
 
-int rejit_b200_stitch_connect(int device, const void* left_handle, const void* right_handle, char* err, size_t err_length) {
+int rejit_b200_stitch_connect(int device, const void* left_handle, const void* right_handle, char* err, size_t err_length) try {
   std::string error;
   if (!StitchConnect(device, left_handle, right_handle, &error)) { SetErr(err, err_length, error); return -1; }
   return 0;
-}
+} RJ_CATCH("rejit_b200_stitch_connect", -1)
 
 void rejit_b200_stitch_close(int device) { StitchClose(device); }
 
 int rejit_b200_stitch_exchange(int device, int count, const rejit_b200_carry* leaving, uint64_t slab_begin,
-                               rejit_b200_carry* arrived, uint32_t* redo_mask, char* err, size_t err_length) {
+                               rejit_b200_carry* arrived, uint32_t* redo_mask, char* err, size_t err_length) try {
   std::string error;
   if (count < 1 || count > 32 || !leaving || !arrived || !redo_mask) { SetErr(err, err_length, "rejit_b200: bad argument"); return -1; }
   Carry out[32], in[32];
@@ -670,12 +703,13 @@ int rejit_b200_stitch_exchange(int device, int count, const rejit_b200_carry* le
   if (!StitchExchange(device, count, out, slab_begin, in, redo_mask, &error)) { SetErr(err, err_length, error); return -1; }
   for (int j = 0; j < count; ++j) { arrived[j].cur = in[j].cur; arrived[j].tail = in[j].tail; }
   return 0;
-}
+} RJ_CATCH("rejit_b200_stitch_exchange", -1)
 
 int rejit_b200_match_all_set_device_stitched(rejit_b200_set* set, int device, const void* d_text, size_t text_length,
                                              uint64_t own_begin, uint64_t own_end, uint64_t base_offset,
                                              rejit_b200_carry* carry_out, rejit_b200_carry* arrived, uint32_t* redo_mask,
-                                             int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) {
+                                             int64_t* out_counts, rejit_b200_stats* stats, char* err, size_t err_length) try {
+  if (!set) { SetErr(err, err_length, "rejit_b200_match_all_set_device_stitched: null set"); return -1; }
   std::string error;
   RunStats rs;
   const int k = set->set->size();
@@ -715,7 +749,7 @@ int rejit_b200_match_all_set_device_stitched(rejit_b200_set* set, int device, co
   }
   FillStats(rs, stats);
   return 0;
-}
+} RJ_CATCH("rejit_b200_match_all_set_device_stitched", -1)
 
 void rejit_b200_free(void* ptr) { free(ptr); }
 

@@ -133,6 +133,45 @@ def test_slab_entry_points_refuse_reentrant_patterns(lib):
     assert r == -1 and b"re-entrant" in err.value
 
 
+def test_entry_points_refuse_null_handles(lib):
+    """A C, cgo or ctypes caller that passes a NULL program / set / text handle gets -1 (or NULL) and a message, not a
+    segmentation fault; and every entry point that can allocate is a function-try-block, so no exception crosses the C
+    ABI (capi.cc RJ_CATCH).  The checks run before any device work: no GPU needed."""
+    L = lib.lib()
+    err = ctypes.create_string_buffer(256)
+    n = len(err)
+    pair = (ctypes.c_uint64 * 2)()
+    pairs = ctypes.POINTER(ctypes.c_uint64)()
+    counts = (ctypes.c_int64 * 2)()
+    calls = [
+        ("rejit_b200_match_all_alloc", lambda: L.rejit_b200_match_all_alloc(None, b"abc", 3, ctypes.byref(pairs), None, err, n)),
+        ("rejit_b200_match_all", lambda: L.rejit_b200_match_all(None, b"abc", 3, None, 0, err, n)),
+        ("rejit_b200_match_first", lambda: L.rejit_b200_match_first(None, b"abc", 3, pair, err, n)),
+        ("rejit_b200_match_full", lambda: L.rejit_b200_match_full(None, b"abc", 3, err, n)),
+        ("rejit_b200_match_anywhere", lambda: L.rejit_b200_match_anywhere(None, b"abc", 3, err, n)),
+        ("rejit_b200_match_all_multi_gpu", lambda: L.rejit_b200_match_all_multi_gpu(None, b"abc", 3, 2, ctypes.byref(pairs), None, err, n)),
+        ("rejit_b200_match_all_device", lambda: L.rejit_b200_match_all_device(None, 0, None, 0, None, 0, None, None, None, err, n)),
+        ("rejit_b200_match_all_device_slab", lambda: L.rejit_b200_match_all_device_slab(None, 0, None, 0, 0, 1, 0, None, 0, None, None, None, err, n)),
+        ("rejit_b200_match_all_text", lambda: L.rejit_b200_match_all_text(None, None, ctypes.byref(pairs), None, err, n)),
+        ("rejit_b200_match_all_set_device", lambda: L.rejit_b200_match_all_set_device(None, 0, None, 0, counts, None, err, n)),
+        ("rejit_b200_match_all_set_device_slab", lambda: L.rejit_b200_match_all_set_device_slab(None, 0, None, 0, 0, 1, 0, None, None, counts, None, err, n)),
+        ("rejit_b200_match_all_set_text", lambda: L.rejit_b200_match_all_set_text(None, None, counts, None, None, err, n)),
+        ("rejit_b200_match_all_set_device_stitched", lambda: L.rejit_b200_match_all_set_device_stitched(None, 0, None, 0, 0, 1, 0, None, None, None, counts, None, err, n)),
+    ]
+    for name, call in calls:
+        err.value = b""
+        assert call() == -1, name
+        assert name.encode() in err.value and b"null" in err.value, (name, err.value)
+    good = lib.Regej("abc")
+    assert good.compile()
+    err.value = b""
+    assert L.rejit_b200_match_all_text(good._prog, None, ctypes.byref(pairs), None, err, n) == -1 and b"null text" in err.value
+    assert not L.rejit_b200_replace_all_text(None, None, b"", 0, None, None, err, n)
+    assert not L.rejit_b200_set_create(None, 0)
+    two = (ctypes.c_void_p * 2)(good._prog, None)
+    assert not L.rejit_b200_set_create(two, 2)
+
+
 def test_compile_survives_malformed_ir():
     """The C ABI takes the lowered regexp from a foreign binding: out-of-range states, kinds,
     payload ranges and header fields must come back as an error (entry_state = 255 of 5 states used to fault)."""
