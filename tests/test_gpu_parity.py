@@ -726,10 +726,13 @@ def test_replace_all_fused_into_the_scan(rj):
     """Round 2: generic scans whose replacement is not longer than their shortest match write the rebuilt text from
     `k_scan_emit` itself (scan_emit.cuh, kRebuild; engine.cu ReplaceAllDevice) — one launch instead of scan + lengths +
     prefix sum + index + staging.  Same contract as `Regej::ReplaceAll` (src/rejit.cc:97-112, 221-226): the oracle's
-    matches applied in Python, byte for byte.  Sizes sit on tile edges (24 KB tiles), cross the groups of 32 tiles and
-    the look-back step of 32 groups; gaps of 0 bytes, of a few bytes, of whole tiles; matches that end in the next
-    tile; replacements of 0, 1, 3 and more than 32 bytes; cases the single pass must hand back (matches longer than a
-    tile, replacement longer than the shortest match) still come out right."""
+    matches applied in Python, byte for byte.  Sizes sit on tile edges (24 KB tiles) and cross a group of 32 tiles;
+    gaps of 0 bytes, of a few bytes, of whole tiles; matches that end in the next tile or cover one; replacements of
+    0, 1 and 3 bytes.  The fused kernel takes `>.*\\n|\\n`, `[ab]{3,}`, `(^|$|[x])`, `a.*` (the last two mostly hand the
+    call back: chains across tile edges, dense tiles); the other patterns are the same contract on the paths the fusion
+    does NOT apply to — `x+` / `x*` re-enter their start (faithful resolve), `ab|ba` is a DFA scan, `x{40,}` a literal
+    window, replacements longer than the shortest match — so that both sides of the switch in `ReplaceAllDevice` are
+    held to the same bytes.  Many look-back steps with the fused kernel: `test_regexdna_chain_at_size` (510 MB)."""
     rng = np.random.default_rng(77)
 
     def text(alpha, n, p=None):
@@ -773,7 +776,7 @@ def test_replace_all_fused_into_the_scan(rj):
             assert st.launches == 1, st.launches
         out.free()
     raw.free()
-    # 60 MB = 2500 tiles = 79 groups: three look-back steps carry the removed bytes.  Expected with numpy: runs of x
+    # 60 MB through the separate passes (`x+` re-enters its start: no single-pass scan).  Expected with numpy: runs of x
     big = np.frombuffer(b"abx\n", dtype=np.uint8)[rng.choice(4, size=60_000_000, p=[0.45, 0.45, 0.09, 0.01])]
     is_x = big == ord("x")
     starts = is_x.copy()
