@@ -25,8 +25,12 @@ while time.time() - t0 < budget:
             got = [list(m) for m in o.match_all(t)]
             exp = ref.match_all(pb, t)
             checked += 1
+            if got != exp and o.longest_literal > 16 and \
+                    [list(m) for m in O.Oracle(pat, long_literal_defect=True).match_all(t)] == exp:
+                known = globals().get("known_b20", 0) + 1; globals()["known_b20"] = known   # defect B20, as modelled
+                continue
             if got != exp:
                 fresh = subprocess.run([sys.executable, "-c", T._FRESH, T.REF_SO, pb.hex(), t.hex()], capture_output=True, text=True).stdout.strip()
                 if str(got) != fresh:
                     fails += 1; print("DIFF", repr(pat), repr(t[:120]), len(t), flush=True)
-print("checked", checked, "fails", fails, flush=True)
+print("checked", checked, "fails", fails, "explained by defect B20", globals().get("known_b20", 0), flush=True)
