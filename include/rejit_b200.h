@@ -17,6 +17,11 @@
  *
  * There is no CPU fallback: every matching entry point fails with an error
  * when no CUDA device (or the CUDA part of the library) is available.
+ *
+ * Error convention: entry points that take (err, err_length) return -1 (or
+ * NULL) and write a NUL-terminated message; a NULL program / set / text handle
+ * is such an error, not a crash; no C++ exception leaves the library (an
+ * allocation failure inside is reported the same way).
  */
 #ifndef REJIT_B200_H_
 #define REJIT_B200_H_
