@@ -402,3 +402,109 @@ def test_replace_all_placement(hostsim):
         exp = expected(pat, t, w)
         got = hostsim.replace_all(pat, t, w)
         assert got == exp, (pat, len(t), w, got[0], exp[0])
+
+
+def test_fused_rebuild_placement_model():
+    """A MODEL of the placement arithmetic of the fused ReplaceAll (scan_emit.cuh, kRebuild — restated here, not shared
+    code; the kernel itself is held to the same bytes by the GPU tier's test_replace_all_fused_into_the_scan): the text
+    is cut into tiles, a tile owns the matches that BEGIN in it, publishes (matches, bytes inside them, chain state after
+    its last match), reads the sums over the tiles before it, and writes its part of the output starting at
+        rb_in  = max(tile_lo, end of a non-empty match arriving from the left)
+        rb_out = rb_in - removed_before + w * matches_before
+    four gaps per step.  A tile whose numbers cannot be right (removed_before > rb_in) or whose first match is reached
+    by the chain from the left raises the flag that sends the call to the separate rebuild.  Checked against the
+    reference's Replace (src/rejit.cc:97-112) applied to the oracle's matches, for tile sizes that put matches across
+    one and several tile edges; and, with overlapping per-tile lists made up on purpose, that the flag is raised and
+    nothing is written out of bounds."""
+    import random
+    import rejit_oracle as O
+    import fuzzgen
+
+    def rebuild(text, matches, w, tile):
+        n = len(text)
+        ntiles = n // tile + 1
+        per = [[] for _ in range(ntiles)]
+        for b, e in matches:
+            per[min(b // tile, ntiles - 1)].append((b, e))
+        out = bytearray(b"\xEE" * (n + 64))
+        flagged = False
+        before = removed = 0
+        arriving = (0, 0)                                    # (cur, non-empty): where the next match may begin
+        for t in range(ntiles):
+            tile_lo, tile_hi = t * tile, min(t * tile + tile, n)
+            mine = per[t]
+            local = False                                    # (tiles decide alone: a flag elsewhere does not stop this one)
+            if mine:                                         # the seam: does the chain from the left take my first match?
+                b, e = mine[0]
+                cur, ne = arriving
+                if not (b > cur or (b == cur and (e > b or not ne))):
+                    local = True
+            rb_in = tile_lo
+            if arriving[1] and arriving[0] > rb_in:
+                rb_in = arriving[0]
+            added = len(w) * before
+            if removed > rb_in or added > removed:
+                local = True
+            flagged |= local
+            if not local:
+                in_pos, o = rb_in, rb_in - removed + added
+                entries = mine + [(tile_hi, tile_hi)]        # the bytes after my last match
+                for i in range(0, len(entries), 4):          # four gaps per step
+                    step = []
+                    for k in range(i, min(i + 4, len(entries))):
+                        b, e = entries[k]
+                        gap = b - in_pos if b > in_pos else 0
+                        step.append((in_pos, gap, o, k < len(mine)))
+                        o += gap + (len(w) if k < len(mine) else 0)
+                        if e > in_pos:
+                            in_pos = e
+                    for src, gap, dst, is_match in step:
+                        assert dst + gap + (len(w) if is_match else 0) <= n, "out of bounds"
+                        out[dst:dst + gap] = text[src:src + gap]
+                        if is_match:
+                            out[dst + gap:dst + gap + len(w)] = w
+            # publish: what the tiles after me will read
+            before += len(mine)
+            removed += sum(e - b for b, e in mine)
+            if mine:
+                b, e = mine[-1]
+                arriving = (e, 1) if e > b else (b + 1, 0)
+        total = n - removed + len(w) * before
+        return flagged, bytes(out[:total]), out[total:]
+
+    def expected(text, matches, w):
+        res, at = bytearray(), 0
+        for b, e in matches:
+            res += text[at:b] + w
+            at = e
+        return bytes(res + text[at:])
+
+    rng = random.Random(11)
+    cases = [(">.*\n|\n", "ab>\n", b""), ("[ab]{3,}", "abx\n", b"QQQ"), ("(^|$|[x])", "abx\n", b""), ("b+", "abx", b"Q"),
+             ("a.*", "abx\n", b"L"), ("x{2,}", "xa", b"--")]
+    checked = 0
+    for pat, alpha, w in cases:
+        o = O.Oracle(pat)
+        for n in (0, 1, 7, 64, 65, 300, 1000):
+            text = fuzzgen.rand_text(rng, alpha, n)
+            matches = o.match_all(text)
+            if any(e - b < len(w) for b, e in matches):
+                continue                                     # the engine fuses only when w <= the shortest match
+            for tile in (8, 16, 64, 256, 4096):
+                flagged, got, slack = rebuild(text, matches, w, tile)
+                assert not flagged, (pat, n, tile)           # disjoint leftmost-longest matches: every seam is clean
+                assert got == expected(text, matches, w), (pat, n, tile)
+                assert slack == b"\xEE" * len(slack)
+                checked += 1
+    assert checked > 100
+    # per-tile lists that are not a chain (a match of tile 0 runs over the first match of tile 1, as two tiles that
+    # each resolved alone can produce): the flag is raised, whatever was written stayed inside the buffer
+    text = b"a" * 64
+    flagged, _, slack = rebuild(text, [(2, 20), (16, 30), (40, 44)], b"", 16)
+    assert flagged and slack == b"\xEE" * len(slack)
+    flagged, _, slack = rebuild(text, [(2, 60), (17, 63), (33, 64)], b"", 16)
+    assert flagged and slack == b"\xEE" * len(slack)
+    # ... and a later tile whose numbers still pass the check writes (garbage, the call is handed back) in bounds
+    text = bytes(range(256)) * 4
+    flagged, _, slack = rebuild(text, [(2, 20), (16, 30), (100, 104), (1000, 1024)], b"", 16)
+    assert flagged and slack == b"\xEE" * len(slack)
