@@ -1860,8 +1860,8 @@ int64_t ReplaceAllDevice(int device, Program* prog, const uint8_t* d_text, uint6
   if (!no_fused_rebuild && c->emit && !dp->emit_off && !ca.reentrant && ca.strategy == ScanStrategy::Generic &&
       with_len <= ca.nfa.min_len && n > 0) {
     FusedRebuild fr;
+    RJ_TRY_COUNT(cudaSetDevice(c->device));            // (Buffer::Reserve allocates on the current device)
     if (!c->with_buf.Reserve(with_len + 16, error)) return -1;
-    RJ_TRY_COUNT(cudaSetDevice(c->device));
     if (with_len) RJ_TRY_COUNT(cudaMemcpyAsync(c->with_buf.p, with, with_len, cudaMemcpyHostToDevice, s));
     void* out = DeviceAlloc(device, n + 64, error);
     if (!out) return -1;
